@@ -1,0 +1,799 @@
+"""numpy restatement of the reference hot path (TEST INFRASTRUCTURE - see oracle/__init__.py).
+
+Each function cites the reference file:line it restates (paths relative to
+``/root/reference/waveform_analysis``).  The restatements are written for clarity and for
+vectorised execution over many records; they are not copies of the reference loops.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from waveformanalysis_b200.dtypes import (
+    BASIC_FEATURES_DTYPE,
+    HIT_MERGE_CLUSTERS_DTYPE,
+    HIT_MERGED_COMPONENTS_DTYPE,
+    HIT_MERGED_DTYPE,
+    RECORDS_DTYPE,
+    THRESHOLD_HIT_DTYPE,
+    WAVEFORM_WIDTH_DTYPE,
+    WAVEFORM_WIDTH_INTEGRAL_DTYPE,
+)
+
+# --------------------------------------------------------------------------------------
+# helpers
+# --------------------------------------------------------------------------------------
+
+
+def resolve_slice(start, end, length: int) -> tuple[int, int]:
+    """Python ``seq[start:end]`` bounds for a sequence of ``length`` (basic_features.py:155-156)."""
+    lo, hi, _ = slice(start, end).indices(int(length))
+    return lo, max(lo, hi)
+
+
+def _is_fixed_contiguous(records: np.ndarray) -> int | None:
+    """Return L when every record has event_length L and wave_offset == i*L, else None."""
+    if len(records) == 0:
+        return None
+    ln = records["event_length"]
+    L = int(ln[0])
+    if L <= 0 or np.any(ln != L):
+        return None
+    off = records["wave_offset"]
+    if np.array_equal(off, np.arange(len(records), dtype=np.int64) * L):
+        return L
+    return None
+
+
+def _record_wave(records, pool, i):
+    o = int(records["wave_offset"][i])
+    return pool[o : o + int(records["event_length"][i])]
+
+
+# --------------------------------------------------------------------------------------
+# K1: records builder (core/processing/records_builder.py)
+# --------------------------------------------------------------------------------------
+
+
+def baseline_mean(samples: np.ndarray, start: int, end: int) -> np.ndarray:
+    """records.baseline = mean(float64(samples[:, start:end])) (records_builder.py:243-257).
+
+    ``samples`` is the (n, L) sample matrix (header columns already stripped), so the VX2730
+    default window raw[:, 7:47] is ``start=0, end=40``.  Empty window -> NaN.
+    """
+    n, L = samples.shape
+    end = min(int(end), L)
+    if end <= start:
+        return np.full(n, np.nan, dtype=np.float64)
+    return np.mean(samples[:, start:end].astype(float), axis=1)
+
+
+def build_records(
+    timestamps_ps: np.ndarray,
+    boards: np.ndarray,
+    channels: np.ndarray,
+    samples: np.ndarray,
+    *,
+    dt_ns: int,
+    baseline_window: tuple[int, int] = (0, 40),
+    baselines: np.ndarray | None = None,
+    epoch_ns: int | None = None,
+    flags: np.ndarray | None = None,
+) -> tuple[np.ndarray, np.ndarray]:
+    """Fixed-length records + wave_pool in the reference's global order.
+
+    Restates ``_build_records_part_from_raw_array`` (records_builder.py:212-302) followed by
+    ``_merge_records_part_refs`` (:341-426): the merged order is ascending
+    (timestamp, pid=0, board, channel, input order), which is what one global
+    ``lexsort((seq, channel, board, pid, timestamp))`` (:115-120) gives when the inputs are
+    concatenated in part order.  ``record_id`` = arange after the merge (:425), ``wave_offset``
+    = record_id * L (:300, 408), ``time`` = timestamp // 1000 (+ epoch) (:279, 507-510),
+    wave_pool = int16 samples reinterpreted as uint16 (:108-112, 299).
+    """
+    n, L = samples.shape
+    rec = np.zeros(n, dtype=RECORDS_DTYPE)
+    rec["timestamp"] = np.asarray(timestamps_ps, dtype=np.int64)
+    rec["pid"] = 0
+    rec["board"] = np.asarray(boards, dtype=np.int16)
+    rec["channel"] = np.asarray(channels, dtype=np.int16)
+    if baselines is None:
+        rec["baseline"] = baseline_mean(samples, baseline_window[0], baseline_window[1])
+    else:
+        rec["baseline"] = np.asarray(baselines, dtype=np.float64)
+    rec["baseline_upstream"] = np.nan
+    rec["polarity"] = "unknown"
+    rec["dt"] = np.int32(dt_ns)
+    rec["trigger_type"] = 0
+    rec["flags"] = 0 if flags is None else np.asarray(flags, dtype=np.uint32)
+    rec["event_length"] = np.int32(L)
+    rec["time"] = rec["timestamp"] // 1000
+    if epoch_ns is not None:
+        rec["time"] += np.int64(epoch_ns)
+    seq = np.arange(n, dtype=np.int64)
+    order = np.lexsort((seq, rec["channel"], rec["board"], rec["pid"], rec["timestamp"]))
+    rec = rec[order]
+    rec["record_id"] = np.arange(n, dtype=np.int64)
+    rec["wave_offset"] = np.arange(n, dtype=np.int64) * L
+    pool = np.ascontiguousarray(samples[order]).astype(np.uint16, copy=False).reshape(-1)
+    return rec, pool
+
+
+# --------------------------------------------------------------------------------------
+# basic_features (core/plugins/builtin/cpu/basic_features.py:108-195, records branch)
+# --------------------------------------------------------------------------------------
+
+
+def basic_features(
+    records: np.ndarray,
+    pool: np.ndarray,
+    *,
+    height_range=(40, 90),
+    area_range=(0, None),
+    fixed_baseline: dict | None = None,
+) -> np.ndarray:
+    """Restates the records branch of BasicFeaturesPlugin.compute.
+
+    ``fixed_baseline`` maps (board, channel) -> float override (the resolved
+    ``channel_config`` value, basic_features.py:134-146).  ``pool`` is the uint16 wave_pool or
+    the float32 wave_pool_filtered.
+    """
+    n = len(records)
+    out = np.zeros(n, dtype=BASIC_FEATURES_DTYPE)
+    if n == 0:
+        return out
+    base = records["baseline"].astype(np.float64).copy()
+    if fixed_baseline:
+        for (b, c), v in fixed_baseline.items():
+            if v is None:
+                continue
+            sel = (records["board"] == b) & (records["channel"] == c)
+            base[sel] = float(v)
+    pol = np.asarray(records["polarity"])
+    known = (pol == "positive") | (pol == "negative")
+    positive = pol == "positive"
+
+    out["timestamp"] = records["timestamp"]
+    out["board"] = records["board"]
+    out["channel"] = records["channel"]
+    out["event_index"] = np.arange(n, dtype=np.int64)
+
+    L = _is_fixed_contiguous(records)
+    if L is not None:
+        W = pool[: n * L].reshape(n, L)
+        p0, p1 = resolve_slice(height_range[0], height_range[1], L)
+        c0, c1 = resolve_slice(area_range[0], area_range[1], L)
+        _basic_block(out, W, base, known, positive, p0, p1, c0, c1)
+        return out
+    for i in range(n):
+        w = _record_wave(records, pool, i)
+        Li = len(w)
+        p0, p1 = resolve_slice(height_range[0], height_range[1], Li)
+        c0, c1 = resolve_slice(area_range[0], area_range[1], Li)
+        _basic_block(
+            out[i : i + 1], w.reshape(1, Li), base[i : i + 1], known[i : i + 1],
+            positive[i : i + 1], p0, p1, c0, c1,
+        )
+    return out
+
+
+def _basic_block(out, W, base, known, positive, p0, p1, c0, c1):
+    n, L = W.shape
+    height = np.zeros(n, dtype=np.float64)
+    amp = np.zeros(n, dtype=np.float64)
+    area = np.zeros(n, dtype=np.float64)
+    unk = ~known
+    if np.any(unk):
+        Wu = W[unk]
+        bu = base[unk]
+        if p1 > p0:
+            wmin = Wu[:, p0:p1].min(axis=1).astype(np.float64)
+            wmax = Wu[:, p0:p1].max(axis=1).astype(np.float64)
+            height[unk] = bu - wmin  # basic_features.py:174 (unknown -> "negative")
+            amp[unk] = wmax - wmin  # :175
+        if c1 > c0:
+            area[unk] = np.sum(bu[:, None] - Wu[:, c0:c1].astype(np.float64), axis=1)  # :180-185
+    if np.any(known):
+        Wk = W[known]
+        b32 = base[known].astype(np.float32)
+        s = Wk.astype(np.float32) - b32[:, None]  # records_view.py:94-96
+        flip = ~positive[known]  # negative: s = -(w-b); positive: -(-(w-b)) = w-b (:98-99 + bf:151)
+        s[flip] = -s[flip]
+        if p1 > p0:
+            smax = s[:, p0:p1].max(axis=1).astype(np.float64)
+            smin = s[:, p0:p1].min(axis=1).astype(np.float64)
+            height[known] = smax  # :166
+            amp[known] = smax - smin  # :167
+        if c1 > c0:
+            area[known] = np.sum(s[:, c0:c1].astype(np.float64), axis=1)  # :178
+    out["height"] = height
+    out["amp"] = amp
+    out["area"] = area
+    if L > 1:
+        d = np.abs(np.diff(W.astype(np.float64), axis=1))  # :187-189
+        out["max_abs_diff"] = d.max(axis=1)
+
+
+# --------------------------------------------------------------------------------------
+# hit_threshold (core/plugins/builtin/cpu/hit_finder.py:122-255, 329-413)
+# --------------------------------------------------------------------------------------
+
+
+def threshold_hits(
+    records: np.ndarray,
+    pool: np.ndarray,
+    *,
+    threshold: float = 10.0,
+    thresholds: dict | None = None,
+    left_extension: int = 2,
+    right_extension: int = 2,
+    block: int = 4096,
+) -> np.ndarray:
+    """Restates ThresholdHitPlugin.compute (records branch) + _build_hits_from_signal_matrix.
+
+    ``thresholds`` maps (board, channel) -> per-channel threshold override
+    (hit_finder.py:288-327).  Rows come out record-major, then by start sample (:352-355).
+    """
+    n = len(records)
+    if n == 0:
+        return np.zeros(0, dtype=THRESHOLD_HIT_DTYPE)
+    left = max(0, int(left_extension))
+    right = max(0, int(right_extension))
+    lens = records["event_length"].astype(np.int64)
+    Lmax = int(lens.max())  # padded matrix width (records_view.py:179-189, hit_finder.py:364)
+    thr = np.full(n, float(threshold), dtype=np.float64)
+    if thresholds:
+        for (b, c), v in thresholds.items():
+            sel = (records["board"] == b) & (records["channel"] == c)
+            thr[sel] = float(v)
+    positive = np.asarray(records["polarity"]) == "positive"  # hit_finder.py:323-325
+    base = records["baseline"].astype(np.float64)
+    fixedL = _is_fixed_contiguous(records)
+    rows = []
+    for r0 in range(0, n, block):
+        r1 = min(n, r0 + block)
+        m = r1 - r0
+        W = np.zeros((m, Lmax), dtype=np.float64)  # padding is 0.0 (records_view.py:189)
+        if fixedL is not None:
+            W[:, :] = pool[r0 * fixedL : r1 * fixedL].reshape(m, fixedL)
+        else:
+            for k in range(m):
+                w = _record_wave(records, pool, r0 + k)
+                W[k, : len(w)] = w
+        b = base[r0:r1, None]
+        sig = np.where(positive[r0:r1, None], W - b, b - W)  # :240-241
+        valid = np.arange(Lmax)[None, :] < lens[r0:r1, None]
+        msk = (sig >= thr[r0:r1, None]) & valid  # :346-348
+        edge = np.zeros((m, Lmax + 2), dtype=np.int8)
+        edge[:, 1:-1] = msk
+        flips = np.flatnonzero(edge[:, 1:] != edge[:, :-1])  # alternating start, end per row
+        if flips.size == 0:
+            continue
+        rr, cc = np.divmod(flips, Lmax + 1)
+        starts, ends, rws = cc[0::2], cc[1::2], rr[0::2]
+        for s, e, k in zip(starts.tolist(), ends.tolist(), rws.tolist()):
+            i = r0 + k
+            a0 = max(0, s - left)
+            a1 = min(Lmax, e + right)  # :369-370
+            if a1 <= a0:
+                continue
+            seg = sig[k, a0:a1]
+            rel = int(np.argmax(seg))  # first maximum (:378)
+            p = a0 + rel
+            dt_ns = int(records["dt"][i])
+            ts = np.int64(records["timestamp"][i]) + p * (float(dt_ns) * 1e3)  # f64 (:383-386)
+            rl = max(int(lens[i]), 0)
+            es = min(max(a0, 0), rl)
+            ee = max(min(max(a1, 0), rl), es)  # :388-391
+            rows.append(
+                (
+                    p,
+                    float(seg[rel]),
+                    float(np.sum(np.maximum(seg, 0.0))),
+                    es,
+                    ee,
+                    float(ee - es),
+                    dt_ns,
+                    float(max(p - s, 0) * dt_ns),
+                    float(max((e - 1) - p, 0) * dt_ns),
+                    int(ts),
+                    int(records["board"][i]),
+                    int(records["channel"][i]),
+                    int(records["record_id"][i]),
+                )
+            )
+    if not rows:
+        return np.zeros(0, dtype=THRESHOLD_HIT_DTYPE)
+    return np.array(rows, dtype=THRESHOLD_HIT_DTYPE)
+
+
+# --------------------------------------------------------------------------------------
+# wave_pool_filtered (core/plugins/builtin/cpu/filtering.py:181-241, records.py:368-438)
+# --------------------------------------------------------------------------------------
+
+
+def sg_coefficients(window: int, poly: int) -> np.ndarray:
+    """Savitzky-Golay smoothing (deriv 0) FIR taps.
+
+    scipy.signal.savgol_coeffs (scipy 1.18.1, signal/_savitzky_golay.py:14-138, an
+    un-vendored dependency: pyproject.toml:31 ``scipy>=1.7.0``) solves the least-squares
+    system A c = e0 with A[k, j] = x_j**k for x = halflen .. -halflen; restated here.
+    """
+    h = window // 2
+    x = np.arange(-h, window - h, dtype=float)[::-1]
+    A = x ** np.arange(poly + 1).reshape(-1, 1)
+    y = np.zeros(poly + 1)
+    y[0] = 1.0
+    c, *_ = np.linalg.lstsq(A, y, rcond=None)
+    return c
+
+
+def sg_edge_matrix(window: int, poly: int) -> np.ndarray:
+    """(window x window) projector P = A pinv(A): the degree-``poly`` LSQ fit over ``window``
+    samples evaluated at each of the window positions (savgol mode='interp' edge rule,
+    scipy/signal/_savitzky_golay.py:141-186)."""
+    A = np.vander(np.arange(window, dtype=float), poly + 1)
+    return A @ np.linalg.pinv(A)
+
+
+def effective_sg_window(n_samples: int, sg_window: int, poly: int) -> int | None:
+    """filtering.py:181-195: window = min(sg_window, L) forced odd; None (identity) if <= poly."""
+    w = min(int(sg_window), int(n_samples))
+    if w % 2 == 0:
+        w -= 1
+    if w <= int(poly):
+        return None
+    return w
+
+
+def sg_filter_rows(X: np.ndarray, sg_window: int, poly: int) -> np.ndarray:
+    """SG 'interp' filter of every row of float32 X (n, L) -> float32 (filtering.py:226-241).
+
+    Interior: f64-accumulated correlation with the symmetric taps, stored f32 (bit-exact with
+    scipy on interior samples).  Edges: closed-form projector in f64 - scipy runs
+    that fit through polyfit on f32 data, so the 2*halflen edge samples agree to rel ~1e-6,
+    not bit-exactly.
+    """
+    X = np.asarray(X, dtype=np.float32)
+    n, L = X.shape
+    w = effective_sg_window(L, sg_window, poly)
+    if w is None:
+        return X.copy()
+    h = w // 2
+    c = sg_coefficients(w, poly)
+    Xd = X.astype(np.float64)
+    out = np.empty((n, L), dtype=np.float64)
+    acc = np.zeros((n, L - 2 * h), dtype=np.float64)
+    for j in range(w):
+        acc += c[w - 1 - j] * Xd[:, j : j + L - 2 * h]
+    out[:, h : L - h] = acc
+    P = sg_edge_matrix(w, poly)
+    out[:, :h] = Xd[:, :w] @ P[:h].T
+    out[:, L - h :] = Xd[:, L - w :] @ P[w - h :].T
+    return out.astype(np.float32)
+
+
+def bw_padlen(sos: np.ndarray) -> int:
+    """filtering.py:198-203 (= scipy sosfiltfilt default padlen)."""
+    ns = int(sos.shape[0])
+    return 3 * (2 * ns + 1 - min(int((sos[:, 2] == 0).sum()), int((sos[:, 5] == 0).sum())))
+
+
+def sos_steady_state(sos: np.ndarray) -> np.ndarray:
+    """Step-response steady state of each DF2T biquad, scaled by the DC gain of the sections
+    before it.  Restates scipy.signal.sosfilt_zi / lfilter_zi as of scipy 1.18.1 (the version
+    in the build image; the reference leaves scipy unpinned, pyproject.toml:31):
+    y_inf = sum(b)/sum(a); zi = reversed cumulative sum of (b - y_inf*a), first entry dropped.
+    """
+    ns = sos.shape[0]
+    zi = np.zeros((ns, 2))
+    scale = 1.0
+    for s in range(ns):
+        b = sos[s, :3]
+        a = sos[s, 3:]
+        if a[0] != 1:
+            b, a = b / a[0], a / a[0]
+        y_inf = np.sum(b) / np.sum(a)
+        v = b - y_inf * a
+        zi[s, 1] = scale * v[2]
+        zi[s, 0] = scale * (v[2] + v[1])
+        scale *= np.sum(sos[s, :3]) / np.sum(sos[s, 3:])
+    return zi
+
+
+def bw_filter_rows(X: np.ndarray, sos: np.ndarray, zi: np.ndarray | None = None) -> np.ndarray:
+    """Zero-phase cascade of biquads on every row of float32 X, float64 inside, f32 out.
+
+    Restates scipy.signal.sosfiltfilt as called at filtering.py:218-224: odd extension by
+    ``padlen`` samples, DF2T forward pass started from zi*x0, reversed pass started from
+    zi*y_last, extension dropped.  Separate multiply and add (no FMA) reproduces scipy
+    bit-for-bit.  Rows of length <= padlen are returned unfiltered (:221-222).
+    """
+    X = np.asarray(X, dtype=np.float32)
+    n, L = X.shape
+    edge = bw_padlen(sos)
+    if L <= edge:
+        return X.copy()
+    if zi is None:
+        zi = sos_steady_state(sos)
+    x = X.astype(np.float64)
+    left = 2.0 * x[:, :1] - x[:, edge:0:-1]
+    right = 2.0 * x[:, -1:] - x[:, -2 : -edge - 2 : -1]
+    ext = np.concatenate([left, x, right], axis=1)
+
+    def cascade(sig, x0):
+        y = sig
+        for s in range(sos.shape[0]):
+            b0, b1, b2, _a0, a1, a2 = sos[s]
+            z0 = zi[s, 0] * x0
+            z1 = zi[s, 1] * x0
+            o = np.empty_like(y)
+            for t in range(y.shape[1]):
+                xt = y[:, t]
+                yt = b0 * xt + z0
+                z0 = (b1 * xt - a1 * yt) + z1
+                z1 = b2 * xt - a2 * yt
+                o[:, t] = yt
+            y = o
+        return y
+
+    # scipy: zi is scaled by the *input* edge value x0 for every section
+    fwd = cascade(ext, ext[:, 0])
+    rev = cascade(fwd[:, ::-1], fwd[:, -1])
+    y = rev[:, ::-1][:, edge:-edge]
+    return y.astype(np.float32)
+
+
+def wave_pool_filtered(records, pool, *, configs: dict, default: dict) -> np.ndarray:
+    """Per-(board,channel) filter of every record (records.py:368-438).
+
+    ``default`` / ``configs[(board, channel)]`` are dicts with ``filter_type`` 'SG'
+    (``sg_window_size``, ``sg_poly_order``) or 'BW' (``sos`` ndarray).
+    """
+    out = np.zeros(len(pool), dtype=np.float32)
+    if len(records) == 0 or len(pool) == 0:
+        return out
+    keys = np.stack([records["board"].astype(np.int64), records["channel"].astype(np.int64)], 1)
+    for key in {tuple(k) for k in keys.tolist()}:
+        cfg = configs.get(key, default)
+        idx = np.flatnonzero((keys[:, 0] == key[0]) & (keys[:, 1] == key[1]))
+        lens = records["event_length"][idx]
+        for Lk in np.unique(lens):
+            if Lk <= 0:
+                continue
+            sub = idx[lens == Lk]
+            offs = records["wave_offset"][sub].astype(np.int64)
+            gather = offs[:, None] + np.arange(int(Lk))[None, :]
+            X = pool[gather].astype(np.float32)
+            if cfg["filter_type"] == "BW":
+                Y = bw_filter_rows(X, np.asarray(cfg["sos"], dtype=np.float64))
+            else:
+                Y = sg_filter_rows(X, cfg["sg_window_size"], cfg["sg_poly_order"])
+            out[gather] = Y
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# waveform_width (core/plugins/builtin/cpu/waveform_width.py:97-194, 205-374)
+# --------------------------------------------------------------------------------------
+
+
+def _crossing(y: np.ndarray, thr, rising: bool, interpolation: bool):
+    if len(y) == 0:
+        return None
+    idx = np.flatnonzero(y >= thr) if rising else np.flatnonzero(y <= thr)
+    if idx.size == 0:
+        return None
+    i = int(idx[0])
+    if not interpolation or i == 0:
+        return float(i)
+    y0, y1 = y[i - 1], y[i]
+    if abs(y1 - y0) < 1e-10:
+        return float(i)
+    return float(i - 1) + (thr - y0) / (y1 - y0)
+
+
+def waveform_width(
+    hits: np.ndarray,
+    wave_record_ids: np.ndarray,
+    waves: np.ndarray,
+    *,
+    sampling_rate: float | None = None,
+    rise_low=0.1,
+    rise_high=0.9,
+    fall_high=0.9,
+    fall_low=0.1,
+    interpolation=True,
+) -> np.ndarray:
+    """Restates WaveformWidthPlugin.compute for ``hits`` (HIT_DTYPE-like: position, timestamp,
+    board, channel, record_id) over AoS waves (n, L) int16 (st_waveforms) or float32
+    (filtered_waveforms); ``wave_record_ids[i]`` is the record_id of row i (first match wins,
+    waveform_width.py:164-168).  Arithmetic dtype follows numpy promotion exactly as the
+    reference: int16 rows -> float64, float32 rows -> float32 (:240-241)."""
+    if sampling_rate is None:
+        sampling_rate = 0.5
+    rows = []
+    first_row: dict[int, int] = {}
+    for i, rid in enumerate(np.asarray(wave_record_ids).tolist()):
+        first_row.setdefault(int(rid), i)
+    for hrow in hits:
+        rid = int(hrow["record_id"])
+        if rid not in first_row:
+            continue
+        w = waves[first_row[rid]]
+        pos = hrow["position"]
+        bl = np.mean(w[:50])
+        wc = w - bl
+        if pos >= len(wc):
+            continue
+        pv = wc[pos]
+        if pv <= 0:
+            continue
+        left, right = wc[:pos], wc[pos:]
+        rl = _crossing(left, pv * rise_low, True, interpolation)
+        rh = _crossing(left, pv * rise_high, True, interpolation)
+        rts = (rh - rl) if (rl is not None and rh is not None) else 0.0
+        fh = _crossing(right, pv * fall_high, False, interpolation)
+        fl = _crossing(right, pv * fall_low, False, interpolation)
+        if fh is not None and fl is not None:
+            fh += pos
+            fl += pos
+            fts = fl - fh
+        else:
+            fts = 0.0
+        tws = (fl - rl) if (rl is not None and fl is not None) else 0.0
+        rows.append(
+            (
+                float(rts / sampling_rate),
+                float(fts / sampling_rate),
+                float(tws / sampling_rate),
+                float(rts),
+                float(fts),
+                float(tws),
+                int(pos),
+                float(pv),
+                int(hrow["timestamp"]),
+                int(hrow["board"]) if "board" in hrow.dtype.names else 0,
+                int(hrow["channel"]),
+                rid,
+            )
+        )
+    if not rows:
+        return np.zeros(0, dtype=WAVEFORM_WIDTH_DTYPE)
+    return np.array(rows, dtype=WAVEFORM_WIDTH_DTYPE)
+
+
+# --------------------------------------------------------------------------------------
+# waveform_width_integral (core/plugins/builtin/cpu/waveform_width_integral.py:166-231)
+# --------------------------------------------------------------------------------------
+
+
+def width_integral(
+    records: np.ndarray,
+    pool: np.ndarray,
+    *,
+    q_low=0.10,
+    q_high=0.90,
+    sampling_rate=0.5,
+    dt=None,
+) -> np.ndarray:
+    """Records branch: cumulative-charge quantile indices per record."""
+    if dt is None:
+        dt = 1.0 / float(sampling_rate)
+    n = len(records)
+    out = np.zeros(n, dtype=WAVEFORM_WIDTH_INTEGRAL_DTYPE)
+    for i in range(n):
+        w = _record_wave(records, pool, i)
+        b = float(records["baseline"][i])
+        pol = str(records["polarity"][i])
+        if pol in ("positive", "negative"):
+            s = w.astype(np.float32) - np.float32(b)  # records_view.signals
+            if pol == "positive":
+                s = -s
+            sig = -s.astype(np.float64)  # :185
+        else:
+            raw = w.astype(np.float64) - b
+            sig = raw if pol == "positive" else -raw  # :187-191
+        x = np.maximum(sig, 0.0)
+        q = float(np.sum(x))
+        if q <= 0 or not np.isfinite(q):
+            lo = hi = 0
+        else:
+            cs = np.cumsum(x)
+            lo = int(np.searchsorted(cs, q_low * q, side="left"))
+            hi = int(np.searchsorted(cs, q_high * q, side="left"))
+        ws = float(max(hi - lo, 0))
+        out[i] = (
+            float(lo) * dt, float(hi) * dt, ws * dt, float(lo), float(hi), ws, q,
+            int(records["timestamp"][i]), int(records["board"][i]), int(records["channel"][i]), i,
+        )
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# hit_merge (core/plugins/builtin/cpu/hit_merge.py:115-181, 256-322, 353-534)
+# --------------------------------------------------------------------------------------
+
+
+def hit_abs_windows(hits: np.ndarray, start_name="edge_start", end_name="edge_end"):
+    """abs_start/abs_end in ps as float64 (hit_merge.py:75-81, event_grouping.py:365-367)."""
+    ts = hits["timestamp"].astype(np.float64)
+    pos = hits["position"].astype(np.float64)
+    dt_ps = hits["dt"].astype(np.float64) * 1e3
+    a0 = ts + (hits[start_name].astype(np.float64) - pos) * dt_ps
+    a1 = ts + (hits[end_name].astype(np.float64) - pos) * dt_ps
+    return a0, a1
+
+
+def hit_merge(hits: np.ndarray, *, merge_gap_ns=0.0, max_total_width_ns=10000.0):
+    """Returns (hit_merge_clusters, hit_merged, hit_merged_components).
+
+    Per hardware channel in ascending (board, channel): stable sort by abs_start, chain while
+    merge_gap_ns > 0, same dt, gap <= merge_gap, total width <= max width (hit_merge.py:137-179).
+    Cluster row = the single hit, or for multi-hit clusters the anchor = highest hit (earliest
+    timestamp among equal heights), summed integral, sample window only when all members share
+    a record (:256-322).
+    """
+    nh = len(hits)
+    if nh == 0:
+        return (
+            np.zeros(0, dtype=HIT_MERGE_CLUSTERS_DTYPE),
+            np.zeros(0, dtype=HIT_MERGED_DTYPE),
+            np.zeros(0, dtype=HIT_MERGED_COMPONENTS_DTYPE),
+        )
+    a0, a1 = hit_abs_windows(hits)
+    key = hits["board"].astype(np.int64) * 65536 + (hits["channel"].astype(np.int64) & 0xFFFF)
+    # board is the primary key, signed ordering as in the reference's structured sort
+    order = np.lexsort((np.arange(nh), a0, hits["channel"].astype(np.int32), hits["board"].astype(np.int32)))
+    del key
+    gap_ps = merge_gap_ns * 1e3
+    maxw_ps = max_total_width_ns * 1e3
+    cluster_of = np.zeros(nh, dtype=np.int64)  # in sorted order
+    cid = -1
+    prev_b = prev_c = None
+    for k, i in enumerate(order.tolist()):
+        b, c = int(hits["board"][i]), int(hits["channel"][i])
+        new = True
+        if (b, c) == (prev_b, prev_c) and merge_gap_ns > 0:
+            nxt_end = max(c_end, a1[i])
+            if hits["dt"][i] == last_dt and (a0[i] - c_end) <= gap_ps and (nxt_end - c_start) <= maxw_ps:
+                new = False
+                c_end = nxt_end
+        if new:
+            cid += 1
+            c_start, c_end = a0[i], a1[i]
+        last_dt = hits["dt"][i]
+        prev_b, prev_c = b, c
+        cluster_of[k] = cid
+    clusters = np.zeros(nh, dtype=HIT_MERGE_CLUSTERS_DTYPE)
+    clusters["cluster_index"] = cluster_of
+    clusters["hit_index"] = order
+    ncl = cid + 1
+    merged = np.zeros(ncl, dtype=HIT_MERGED_DTYPE)
+    bounds = np.flatnonzero(np.r_[True, cluster_of[1:] != cluster_of[:-1], True])
+    for ci in range(ncl):
+        s, e = int(bounds[ci]), int(bounds[ci + 1])
+        members = order[s:e]
+        if e - s == 1:
+            h = hits[members[0]]
+            merged[ci] = (
+                h["position"], h["height"], h["integral"], h["edge_start"], h["edge_end"], h["width"],
+                h["dt"], h["rise_time"], h["fall_time"], h["timestamp"], h["board"], h["channel"],
+                h["record_id"], s, 1,
+            )
+            continue
+        hh = hits[members]
+        hts = hh["height"].astype(np.float64)
+        cand = np.flatnonzero(hts == hts.max())
+        anchor = cand[0] if len(cand) == 1 else cand[np.argmin(hh["timestamp"][cand])]
+        a = hh[anchor]
+        if len(set(hh["record_id"].tolist())) == 1:
+            ss, se = int(hh["edge_start"].min()), int(hh["edge_end"].max())
+        else:
+            ss, se = -1, -1
+        width = float(max(se - ss, 0.0))
+        if ss < 0 or se < 0:
+            width = -1.0
+        integ = float(np.sum([float(v) for v in hh["integral"]]))
+        merged[ci] = (
+            a["position"], float(hts.max()), integ, ss, se, width, a["dt"], a["rise_time"],
+            a["fall_time"], a["timestamp"], a["board"], a["channel"], a["record_id"], s, e - s,
+        )
+    comps = np.zeros(nh, dtype=HIT_MERGED_COMPONENTS_DTYPE)
+    comps["merged_index"] = cluster_of
+    comps["hit_index"] = order
+    return clusters, merged, comps
+
+
+# --------------------------------------------------------------------------------------
+# event grouping (core/processing/event_grouping.py)
+# --------------------------------------------------------------------------------------
+
+
+def group_hit_windows(hits: np.ndarray, time_window_ns: float) -> dict:
+    """Restates group_hit_windows (event_grouping.py:287-471) for rows whose sample windows
+    are valid (no negative edges), as a prefix-max scan.
+
+    Returns dict with per-event arrays (event_id, t_min, t_max, dt_ns, n_hits), ``offsets``
+    (n_events+1) and ``members`` (hit indices, event-major, each event ordered by
+    (board, channel, dt, abs_start, timestamp, record_id), :423-432), plus ``event_of_hit``.
+    """
+    names = hits.dtype.names
+    sn, en = ("sample_start", "sample_end") if "sample_start" in names else ("edge_start", "edge_end")
+    nh = len(hits)
+    if nh == 0:
+        z = np.zeros(0, dtype=np.int64)
+        return dict(event_id=z, t_min=z, t_max=z, dt_ns=np.zeros(0), n_hits=z, offsets=np.zeros(1, np.int64), members=z, event_of_hit=z)
+    a0, a1 = hit_abs_windows(hits, sn, en)
+    ts = hits["timestamp"].astype(np.int64)
+    dtv = hits["dt"].astype(np.int32)
+    rid = hits["record_id"].astype(np.int64)
+    order = np.lexsort((rid, ts, dtv, a0))  # :418
+    gap = time_window_ns * 1e3
+    pm = np.maximum.accumulate(a1[order])
+    new = np.ones(nh, dtype=bool)
+    new[1:] = a0[order][1:] > pm[:-1] + gap  # :462
+    ev_sorted = np.cumsum(new) - 1
+    event_of_hit = np.empty(nh, dtype=np.int64)
+    event_of_hit[order] = ev_sorted
+    n_ev = int(ev_sorted[-1]) + 1
+    morder = np.lexsort((rid, ts, a0, dtv, hits["channel"].astype(np.int16), hits["board"].astype(np.int16), event_of_hit))
+    counts = np.bincount(event_of_hit, minlength=n_ev)
+    offsets = np.zeros(n_ev + 1, dtype=np.int64)
+    np.cumsum(counts, out=offsets[1:])
+    tmin = np.full(n_ev, np.inf)
+    tmax = np.full(n_ev, -np.inf)
+    np.minimum.at(tmin, event_of_hit, a0)
+    np.maximum.at(tmax, event_of_hit, a1)
+    t_min = tmin.astype(np.int64)  # int() truncation (:434-435)
+    t_max = tmax.astype(np.int64)
+    return dict(
+        event_id=np.arange(n_ev, dtype=np.int64),
+        t_min=t_min,
+        t_max=t_max,
+        dt_ns=(t_max - t_min) / 1e3,
+        n_hits=counts.astype(np.int64),
+        offsets=offsets,
+        members=morder.astype(np.int64),
+        event_of_hit=event_of_hit,
+    )
+
+
+def group_time_window(timestamps: np.ndarray, channels: np.ndarray, time_window_ns: float) -> dict:
+    """Restates group_multi_channel_hits (event_grouping.py:99-283, 477-510).
+
+    Input must have unique timestamps (the reference sorts with an unstable quicksort, SURVEY
+    'unstable sorts').  Anchored windows: next anchor = first ts > ts[anchor] + W (float64
+    compare).  Members ordered by channel; t_min / t_max are the timestamps of the lowest /
+    highest channel member (:250-257).
+    """
+    ts_in = np.asarray(timestamps, dtype=np.int64)
+    n = len(ts_in)
+    order = np.argsort(ts_in, kind="stable")
+    ts = ts_in[order]
+    ch = np.asarray(channels)[order]
+    W = time_window_ns * 1e3
+    bounds = [0]
+    cur = 0
+    while cur < n:
+        cur = int(np.searchsorted(ts.astype(np.float64), float(ts[cur]) + W, side="right"))
+        bounds.append(cur)
+    bounds = np.asarray(bounds, dtype=np.int64)
+    n_ev = len(bounds) - 1
+    members = np.empty(n, dtype=np.int64)
+    t_min = np.zeros(n_ev, dtype=np.int64)
+    t_max = np.zeros(n_ev, dtype=np.int64)
+    for e in range(n_ev):
+        s, t = int(bounds[e]), int(bounds[e + 1])
+        o = np.argsort(ch[s:t], kind="stable")
+        members[s:t] = order[s:t][o]
+        t_min[e] = ts[s:t][o][0]
+        t_max[e] = ts[s:t][o][-1]
+    return dict(
+        event_id=np.arange(n_ev, dtype=np.int64),
+        t_min=t_min,
+        t_max=t_max,
+        dt_ns=(t_max - t_min) / 1e3,
+        n_hits=np.diff(bounds),
+        offsets=bounds,
+        members=members,
+    )

@@ -1,0 +1,271 @@
+/*
+ * wfb200.h - C ABI of libwfb200.so: the B200 (sm_100a) hot path of WaveformAnalysis.
+ *
+ * Plain C: device/host pointers + sizes + POD parameter blocks, int status codes.
+ * No torch / numpy types.  Every entry point cites the reference code it replaces
+ * (paths relative to waveform_analysis/ in SnowingWolf/WaveformAnalysis).
+ *
+ * Conventions
+ *   - "_dev" pointers are CUDA device pointers owned by the caller; the library never frees
+ *     them.  Scratch comes from a caller-provided workspace (size from *_workspace_bytes).
+ *   - `stream` is a cudaStream_t passed as void*; NULL = legacy default stream.  Calls are
+ *     asynchronous with respect to the host unless stated otherwise and are re-entrant
+ *     (no global mutable state; the last error string is thread-local).
+ *   - Packed row layouts are the reference numpy dtypes byte for byte:
+ *       RECORDS_DTYPE         102 B  core/processing/dtypes.py:80-100
+ *       BASIC_FEATURES_DTYPE   36 B  core/plugins/builtin/cpu/basic_features.py:29-40
+ *       THRESHOLD_HIT_DTYPE    60 B  core/plugins/builtin/cpu/hit_finder.py:33-49
+ *       WAVEFORM_WIDTH_DTYPE   56 B  core/plugins/builtin/cpu/waveform_width.py:22-37
+ *       WAVEFORM_WIDTH_INTEGRAL_DTYPE 52 B  .../waveform_width_integral.py:25-39
+ *   - Return value: 0 = WFB_OK, negative = error (wfb_last_error() has the text).
+ */
+#ifndef WFB200_H
+#define WFB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WFB_OK 0
+#define WFB_ERR_INVALID (-1)  /* bad argument (maps to ValueError in the Python plugins) */
+#define WFB_ERR_CUDA (-2)     /* CUDA runtime failure (RuntimeError) */
+#define WFB_ERR_LAYOUT (-3)   /* records reference samples outside wave_pool (ValueError) */
+#define WFB_ERR_NOMEM (-4)
+
+#define WFB_POL_UNKNOWN 0
+#define WFB_POL_POSITIVE 1
+#define WFB_POL_NEGATIVE 2
+
+#define WFB_DO_FEATURES 1
+#define WFB_DO_HITS 2
+
+#define WFB_SLICE_END_NONE INT64_MAX /* python slice end=None */
+
+/* Device-side record metadata, 48 bytes, 16-byte aligned: the fields of RECORDS_DTYPE the
+ * kernels read (core/processing/dtypes.py:80-100), unpacked once by wfb_records_unpack. */
+typedef struct wfb_rec_meta {
+    int64_t timestamp;    /* ps */
+    double baseline;      /* records["baseline"] */
+    int64_t wave_offset;  /* first sample in wave_pool */
+    int32_t event_length; /* samples */
+    int32_t dt;           /* ns */
+    int16_t board;
+    int16_t channel;
+    uint8_t polarity; /* WFB_POL_* ('positive' / 'negative' / anything else) */
+    uint8_t pad_[3];
+    int64_t record_id;
+} wfb_rec_meta;
+
+/* Per-(board, channel) overrides resolved on the host from the reference's channel_config
+ * (core/hardware/channel.py:412-431): hit_threshold.threshold (hit_finder.py:288-327) and
+ * basic_features.fixed_baseline (basic_features.py:134-146). */
+typedef struct wfb_chan_rule {
+    int32_t board;
+    int32_t channel;
+    double threshold;
+    double fixed_baseline;
+    int32_t has_threshold;
+    int32_t has_fixed_baseline;
+} wfb_chan_rule;
+
+/* Parameters of the fused baseline -> threshold hits -> basic_features pass. */
+typedef struct wfb_fh_params {
+    int32_t flags;        /* WFB_DO_FEATURES | WFB_DO_HITS */
+    int32_t pool_is_f32;  /* 0: uint16 wave_pool, 1: float32 wave_pool_filtered */
+    int64_t height_start; /* basic_features.height_range, python slice semantics */
+    int64_t height_end;   /* WFB_SLICE_END_NONE for None */
+    int64_t area_start;   /* basic_features.area_range */
+    int64_t area_end;
+    double threshold;        /* hit_threshold.threshold (default 10.0) */
+    int32_t left_extension;  /* >= 0 */
+    int32_t right_extension; /* >= 0 */
+    int32_t lmax; /* padded matrix width = max event_length over ALL records of the run
+                     (hit_finder.py:364); 0 = use the maximum over the records passed */
+    int32_t n_rules;
+    const wfb_chan_rule* rules_dev; /* n_rules entries on the device, may be NULL */
+    int64_t pool_base;  /* sample index of pool_dev[0] inside the run's wave_pool */
+    int64_t row_base;   /* event_index of the first record passed (basic_features.py:194) */
+} wfb_fh_params;
+
+const char* wfb_last_error(void);
+int wfb_version(void);
+/* Number of SMs / device name of the current device (diagnostics). */
+int wfb_device_info(int* sm_count, int* cc_major, int* cc_minor, char* name, int name_len);
+
+/* ---- K1: records ---------------------------------------------------------------------- */
+
+/* RECORDS_DTYPE rows (102 B packed, device) -> wfb_rec_meta[n].  Replaces the per-record
+ * field access of RecordsView (core/data/records_view.py:16-33). */
+int wfb_records_unpack(const void* records_aos_dev, int64_t n, wfb_rec_meta* meta_dev, void* stream);
+
+/* Raw int16 rows -> time-sorted records + wave_pool.  Replaces
+ * _build_records_part_from_raw_array + _records_sort_order + _merge_records_part_refs
+ * (core/processing/records_builder.py:212-302, 115-120, 341-426).
+ *   samples_dev   int16[n * n_samples]  rows in input (per-channel file) order
+ *   ts_dev        int64[n] timestamps already in ps; board_dev/channel_dev int16[n]
+ *   baseline window [bl_start, bl_end) in samples (VX2730 default 0..40); if
+ *   baselines_in_dev != NULL it is used instead (V1725 header baseline, v1725.py:99)
+ * Outputs: records_aos_dev (n * 102 B, RECORDS_DTYPE), pool_dev uint16[n * n_samples],
+ *          meta_dev (optional, may be NULL), in ascending (timestamp, pid=0, board, channel,
+ *          input order); record_id = arange, wave_offset = record_id * n_samples,
+ *          time = timestamp / 1000 + epoch_ns. */
+int wfb_build_records(const int16_t* samples_dev, const int64_t* ts_dev, const int16_t* board_dev,
+                      const int16_t* channel_dev, const double* baselines_in_dev, int64_t n,
+                      int32_t n_samples, int32_t bl_start, int32_t bl_end, int32_t dt_ns,
+                      int64_t epoch_ns, void* records_aos_dev, uint16_t* pool_dev,
+                      wfb_rec_meta* meta_dev, void* workspace_dev, size_t workspace_bytes,
+                      void* stream);
+size_t wfb_build_records_workspace_bytes(int64_t n);
+
+/* ---- K2 + K3: fused baseline / threshold hits / basic_features ----------------------------- */
+
+size_t wfb_features_hits_workspace_bytes(int64_t n);
+
+/* One pass over the samples of n records.  Replaces BasicFeaturesPlugin.compute (records
+ * branch, basic_features.py:108-195) and ThresholdHitPlugin.compute +
+ * _build_hits_from_signal_matrix (hit_finder.py:122-255, 329-413).
+ *   pool_dev      uint16 or float32 samples; 16-byte aligned; pool_len samples
+ *   feat_out_dev  n * 36 B BASIC_FEATURES rows (if WFB_DO_FEATURES)
+ *   hit_out_dev   hit_cap * 60 B THRESHOLD_HIT rows in reference order: record-major, then
+ *                 start sample (if WFB_DO_HITS).  Rows beyond hit_cap are counted, not stored.
+ *   hit_counts_dev optional int32[n] per-record hit counts (may be NULL)
+ *   hit_base_dev  optional const int64*: running hit total of previous calls (row offset of
+ *                 this call's first hit); NULL = 0
+ *   total_hits_dev int64*: receives hit_base + hits found by this call
+ * The caller compares *total_hits_dev with hit_cap after synchronising and re-runs with a
+ * larger buffer if it overflowed. */
+int wfb_features_hits(const void* pool_dev, int64_t pool_len, const wfb_rec_meta* meta_dev,
+                      int64_t n, const wfb_fh_params* params, void* feat_out_dev,
+                      void* hit_out_dev, int64_t hit_cap, int32_t* hit_counts_dev,
+                      const int64_t* hit_base_dev, int64_t* total_hits_dev, void* workspace_dev,
+                      size_t workspace_bytes, void* stream);
+
+/* Error flag of the last wfb_features_hits call that used this workspace: WFB_ERR_LAYOUT if a
+ * record pointed outside the pool (RecordsView._validate_wave_bounds,
+ * core/data/records_view.py:47-56).  Synchronises the stream. */
+int wfb_features_hits_check(void* workspace_dev, void* stream);
+
+/* Host-buffer front end of the same pass: the reference-facing call.  records_host is the
+ * RECORDS_DTYPE array and pool_host the wave_pool exactly as Context hands them to a plugin;
+ * outputs are host arrays.  Internally a chunked, double-buffered H2D -> kernels -> D2H
+ * pipeline on private streams (synchronous for the caller).  wave_offsets must ascend with
+ * the record index (always true for pools built by the reference, records_builder.py:300,408).
+ * On return *n_hits is the number of hits found; if it exceeds hit_cap only the first hit_cap
+ * rows were stored (call again with a larger buffer). */
+int wfb_process_host(const void* records_host, int64_t n, const void* pool_host, int64_t pool_len,
+                     const wfb_fh_params* params, const wfb_chan_rule* rules_host,
+                     void* feat_out_host, void* hit_out_host, int64_t hit_cap,
+                     int32_t* hit_counts_host, int64_t* n_hits, int64_t chunk_records);
+
+/* ---- wave_pool_filtered -------------------------------------------------------------------- */
+
+#define WFB_FILTER_SG 0
+#define WFB_FILTER_BW 1
+#define WFB_MAX_SG_WINDOW 129
+#define WFB_MAX_SOS_SECTIONS 16
+
+/* One filter configuration (host side builds one per distinct (board, channel) config;
+ * filtering.py:47-130).  SG: taps = savgol coefficients (window), edge = (halflen x window)
+ * projection rows for the first half-window (the last half-window uses the mirrored rows).
+ * BW: sos[n_sections][6] and zi[n_sections][2] (sosfilt_zi). */
+typedef struct wfb_filter_cfg {
+    int32_t type;       /* WFB_FILTER_SG / WFB_FILTER_BW */
+    int32_t sg_window;  /* requested window (odd); the kernel applies min(window, L) forced odd */
+    int32_t sg_poly;
+    int32_t n_sections;
+    double sos[WFB_MAX_SOS_SECTIONS][6];
+    double zi[WFB_MAX_SOS_SECTIONS][2];
+} wfb_filter_cfg;
+
+/* uint16 (or float32) pool -> float32 filtered pool aligned with the same wave_offsets.
+ * Replaces WavePoolFilteredPlugin.compute -> filter_wave_pool_batch -> _apply_filter_core
+ * (records.py:368-438, filtering.py:206-241, 377-407).
+ *   cfg_index_dev  int32[n]: index into cfgs for each record; cfgs_dev: wfb_filter_cfg[n_cfg]
+ *   sg_tables_dev  double tables built by the host for every distinct effective SG window,
+ *                  see waveformanalysis_b200/filters.py (layout: per table [window taps |
+ *                  halflen*window edge rows]); sg_table_offset_dev int32[n]: offset of the
+ *                  record's table (or -1 = identity) */
+int wfb_filter_pool(const void* pool_dev, int32_t pool_is_f32, int64_t pool_len,
+                    const wfb_rec_meta* meta_dev, int64_t n, const wfb_filter_cfg* cfgs_dev,
+                    int32_t n_cfg, const int32_t* cfg_index_dev, const double* sg_tables_dev,
+                    const int32_t* sg_table_offset_dev, float* out_dev, int64_t pool_base,
+                    void* stream);
+
+/* ---- waveform_width / waveform_width_integral --------------------------------------------- */
+
+typedef struct wfb_width_params {
+    double rise_low, rise_high, fall_high, fall_low;
+    double sampling_rate; /* GHz */
+    int32_t interpolation;
+    int32_t wave_is_f32; /* 0: int16 samples (st_waveforms), 1: float32 (filtered_waveforms) */
+} wfb_width_params;
+
+/* Per hit: 10/90 (configurable) rise / fall / total widths with linear interpolation.
+ * Replaces WaveformWidthPlugin._calculate_width_from_peak + _find_threshold_crossing
+ * (waveform_width.py:205-374).  hit_row_dev[i] = row index of the waveform of hit i (or -1:
+ * no matching record -> row dropped); waves are rows of `stride` samples (first `length`
+ * valid).  valid_dev[i] = 1 if a row was produced (pv > 0 and position < length).
+ * out_dev: n_hits * 56 B WAVEFORM_WIDTH rows (only rows with valid=1 are written). */
+int wfb_waveform_width(const void* waves_dev, int64_t n_waves, int32_t length, int64_t stride,
+                       const int64_t* hit_row_dev, const int64_t* hit_position_dev,
+                       const int64_t* hit_timestamp_dev, const int16_t* hit_board_dev,
+                       const int16_t* hit_channel_dev, const int64_t* hit_record_id_dev,
+                       int64_t n_hits, const wfb_width_params* params, void* out_dev,
+                       uint8_t* valid_dev, void* stream);
+
+/* Per record cumulative-charge quantile indices.  Replaces
+ * WaveformWidthIntegralPlugin.compute records branch (waveform_width_integral.py:166-231).
+ * out_dev: n * 52 B WAVEFORM_WIDTH_INTEGRAL rows. */
+int wfb_width_integral(const void* pool_dev, int32_t pool_is_f32, int64_t pool_len,
+                       const wfb_rec_meta* meta_dev, int64_t n, double q_low, double q_high,
+                       double dt_ns, int64_t pool_base, int64_t row_base, void* out_dev,
+                       void* stream);
+
+/* ---- K4: event grouping ------------------------------------------------------------------- */
+
+size_t wfb_group_workspace_bytes(int64_t n_hits);
+
+/* Chain clustering of absolute hit windows.  Replaces the sort + sequential chain of
+ * group_hit_windows (core/processing/event_grouping.py:365-367, 418, 453-470).
+ * Inputs are SoA columns of hit_merged (device).  Outputs (device, n_hits each):
+ *   order_dev     int64: permutation lexsort((record_id, timestamp, dt, abs_start))
+ *   event_id_dev  int64: event id of hit i (in input order)
+ *   abs_start_dev / abs_end_dev  double: absolute windows in ps
+ * *n_events_dev receives the number of events. */
+int wfb_group_hit_windows(const int64_t* timestamp_dev, const int64_t* position_dev,
+                          const int32_t* start_dev, const int32_t* end_dev, const int32_t* dt_dev,
+                          const int64_t* record_id_dev, int64_t n_hits, double time_window_ns,
+                          int64_t* order_dev, int64_t* event_id_dev, double* abs_start_dev,
+                          double* abs_end_dev, int64_t* n_events_dev, void* workspace_dev,
+                          size_t workspace_bytes, void* stream);
+
+/* Anchored fixed-window clustering of time-sorted timestamps.  Replaces
+ * _find_cluster_boundaries_numba (event_grouping.py:477-510): cluster k starts at the first
+ * timestamp > ts[anchor_k-1] + window.  ts_sorted_dev int64[n] ascending.
+ * event_id_dev int64[n]; *n_events_dev. */
+int wfb_group_time_window(const int64_t* ts_sorted_dev, int64_t n, double time_window_ns,
+                          int64_t* event_id_dev, int64_t* n_events_dev, void* workspace_dev,
+                          size_t workspace_bytes, void* stream);
+
+/* Stable LSD radix sort of int64 keys carrying int64 values (device, n each); used by the
+ * plugins for the time sort (records_builder.py:115-120, event_grouping.py:142). */
+int wfb_sort_pairs_i64(const int64_t* keys_in_dev, const int64_t* vals_in_dev, int64_t* keys_out_dev,
+                       int64_t* vals_out_dev, int64_t n, void* workspace_dev,
+                       size_t workspace_bytes, void* stream);
+size_t wfb_sort_workspace_bytes(int64_t n);
+
+/* ---- synthetic input (bench / tests) ------------------------------------------------------- */
+
+/* Fill pool_dev / meta_dev with a seeded synthetic run of n fixed-length records
+ * (baseline 8000+10*channel, N(0,3) noise, 1-3 negative pulses), time-sorted. */
+int wfb_synth_fill(uint16_t* pool_dev, wfb_rec_meta* meta_dev, void* records_aos_dev, int64_t n,
+                   int32_t n_samples, int32_t n_channels, int32_t dt_ns, uint64_t seed,
+                   int64_t record_base, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WFB200_H */

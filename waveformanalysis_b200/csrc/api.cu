@@ -1,0 +1,309 @@
+// C-ABI plumbing: errors, device info, RECORDS_DTYPE unpack, the host-buffer pipeline.
+#include <stdarg.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace wfb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return WFB_ERR_CUDA;
+}
+
+int sm_count() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+    return n;
+}
+
+// ---- RECORDS_DTYPE (102 B packed, 2-byte aligned rows) -> wfb_rec_meta -----------------------
+// field offsets: core/processing/dtypes.py:80-100
+//   timestamp i8@0  pid i4@8  board i2@12  channel i2@14  baseline f8@16  baseline_upstream f8@24
+//   polarity U8@32 (UTF-32, 32 B)  record_id i8@64  dt i4@72  trigger_type i2@76  flags u4@78
+//   wave_offset i8@82  event_length i4@90  time i8@94
+__device__ __forceinline__ unsigned long long rd64(const uint16_t* h) {
+    return (unsigned long long)h[0] | ((unsigned long long)h[1] << 16) | ((unsigned long long)h[2] << 32) |
+           ((unsigned long long)h[3] << 48);
+}
+__device__ __forceinline__ unsigned rd32(const uint16_t* h) { return (unsigned)h[0] | ((unsigned)h[1] << 16); }
+
+__global__ void records_unpack_kernel(const uint16_t* __restrict__ rows, long long n, wfb_rec_meta* __restrict__ meta) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint16_t* h = rows + i * (kRecordsRowBytes / 2);
+    wfb_rec_meta m;
+    m.timestamp = (long long)rd64(h + 0);
+    m.board = (short)h[6];
+    m.channel = (short)h[7];
+    m.baseline = __longlong_as_double((long long)rd64(h + 8));
+    // polarity: 'positive' / 'negative' / other, compared on the first UTF-32 code units and the
+    // terminator so that e.g. 'pos' is not mistaken for 'positive'
+    unsigned c0 = rd32(h + 16), c1 = rd32(h + 18), c7 = rd32(h + 30);
+    int pol = WFB_POL_UNKNOWN;
+    if (c7 == 'e') {
+        // full 8-character compare
+        const char* pos = "positive";
+        const char* neg = "negative";
+        bool isp = true, isn = true;
+        for (int k = 0; k < 8; ++k) {
+            unsigned ck = rd32(h + 16 + 2 * k);
+            isp = isp && ck == (unsigned)pos[k];
+            isn = isn && ck == (unsigned)neg[k];
+        }
+        pol = isp ? WFB_POL_POSITIVE : (isn ? WFB_POL_NEGATIVE : WFB_POL_UNKNOWN);
+    }
+    (void)c0; (void)c1;
+    m.polarity = (uint8_t)pol;
+    m.pad_[0] = m.pad_[1] = m.pad_[2] = 0;
+    m.record_id = (long long)rd64(h + 32);
+    m.dt = (int)rd32(h + 36);
+    m.wave_offset = (long long)rd64(h + 41);
+    m.event_length = (int)rd32(h + 45);
+    meta[i] = m;
+}
+
+}  // namespace wfb
+
+using namespace wfb;
+
+extern "C" const char* wfb_last_error(void) { return g_err; }
+extern "C" int wfb_version(void) { return 100; }
+
+extern "C" int wfb_device_info(int* sm, int* cc_major, int* cc_minor, char* name, int name_len) {
+    int dev = 0;
+    WFB_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    WFB_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (sm) *sm = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    if (name && name_len > 0) {
+        strncpy(name, prop.name, name_len - 1);
+        name[name_len - 1] = 0;
+    }
+    return WFB_OK;
+}
+
+extern "C" int wfb_records_unpack(const void* records_aos_dev, int64_t n, wfb_rec_meta* meta_dev, void* stream) {
+    WFB_REQUIRE(n >= 0, "wfb_records_unpack: negative n");
+    if (n == 0) return WFB_OK;
+    WFB_REQUIRE(records_aos_dev && meta_dev, "wfb_records_unpack: NULL pointer");
+    WFB_REQUIRE(((uintptr_t)records_aos_dev & 1) == 0, "wfb_records_unpack: records must be 2-byte aligned");
+    WFB_REQUIRE(((uintptr_t)meta_dev & 15) == 0, "wfb_records_unpack: meta_dev must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    records_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(static_cast<const uint16_t*>(records_aos_dev), n, meta_dev);
+    WFB_CUDA(cudaGetLastError());
+    return WFB_OK;
+}
+
+// ---- host-buffer pipeline -----------------------------------------------------------------------
+// Chunked over records: H2D (copy stream) -> unpack + fused kernel (compute stream) -> D2H of
+// the feature rows; hit rows accumulate in one device buffer and are copied back at the end.
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return WFB_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {
+            set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+            return WFB_ERR_NOMEM;
+        }
+        cap = bytes;
+        return WFB_OK;
+    }
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+};
+
+struct Slot {
+    DevBuf pool, rows, meta, feat, counts, ws;
+    cudaEvent_t copied = nullptr, computed = nullptr, drained = nullptr;
+};
+
+inline long long rec_i64(const uint8_t* row, int off) {
+    long long v;
+    memcpy(&v, row + off, 8);
+    return v;
+}
+inline int rec_i32(const uint8_t* row, int off) {
+    int v;
+    memcpy(&v, row + off, 4);
+    return v;
+}
+
+}  // namespace
+
+extern "C" int wfb_process_host(const void* records_host, int64_t n, const void* pool_host, int64_t pool_len,
+                                const wfb_fh_params* params, const wfb_chan_rule* rules_host, void* feat_out_host,
+                                void* hit_out_host, int64_t hit_cap, int32_t* hit_counts_host, int64_t* n_hits,
+                                int64_t chunk_records) {
+    WFB_REQUIRE(params != nullptr && n_hits != nullptr, "wfb_process_host: NULL params / n_hits");
+    WFB_REQUIRE(n >= 0 && pool_len >= 0 && hit_cap >= 0, "wfb_process_host: negative size");
+    *n_hits = 0;
+    if (n == 0) return WFB_OK;
+    WFB_REQUIRE(records_host && pool_host, "wfb_process_host: NULL input");
+    const int flags = params->flags;
+    const bool do_feat = flags & WFB_DO_FEATURES, do_hits = flags & WFB_DO_HITS;
+    WFB_REQUIRE(do_feat || do_hits, "wfb_process_host: flags select nothing");
+    WFB_REQUIRE(!do_feat || feat_out_host, "wfb_process_host: feat_out_host is NULL");
+    WFB_REQUIRE(!do_hits || hit_cap == 0 || hit_out_host, "wfb_process_host: hit_out_host is NULL");
+    const size_t esz = params->pool_is_f32 ? 4 : 2;
+    const uint8_t* rows = static_cast<const uint8_t*>(records_host);
+    const uint8_t* pool = static_cast<const uint8_t*>(pool_host);
+    if (chunk_records <= 0) chunk_records = 1 << 18;
+    chunk_records = std::min<int64_t>(chunk_records, n);
+
+    // padded matrix width = max event_length over the whole run (hit_finder.py:364)
+    int lmax = params->lmax;
+    if (do_hits && lmax <= 0) {
+        for (int64_t i = 0; i < n; ++i) lmax = std::max(lmax, rec_i32(rows + i * kRecordsRowBytes, 90));
+    }
+
+    cudaStream_t s_copy = nullptr, s_comp = nullptr, s_out = nullptr;
+    WFB_CUDA(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
+    WFB_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
+    WFB_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+    constexpr int kSlots = 3;
+    Slot slots[kSlots];
+    DevBuf d_hits, d_rules, d_tot;
+    int rc = WFB_OK;
+    auto cleanup = [&]() {
+        cudaStreamSynchronize(s_copy);
+        cudaStreamSynchronize(s_comp);
+        cudaStreamSynchronize(s_out);
+        for (auto& s : slots) {
+            if (s.copied) cudaEventDestroy(s.copied);
+            if (s.computed) cudaEventDestroy(s.computed);
+            if (s.drained) cudaEventDestroy(s.drained);
+        }
+        cudaStreamDestroy(s_copy);
+        cudaStreamDestroy(s_comp);
+        cudaStreamDestroy(s_out);
+    };
+#define PH_CHECK(expr)                \
+    do {                              \
+        rc = (expr);                  \
+        if (rc != WFB_OK) {           \
+            cleanup();                \
+            return rc;                \
+        }                             \
+    } while (0)
+#define PH_CUDA(call)                                   \
+    do {                                                \
+        cudaError_t e__ = (call);                       \
+        if (e__ != cudaSuccess) {                       \
+            rc = cuda_fail(e__, #call);                 \
+            cleanup();                                  \
+            return rc;                                  \
+        }                                               \
+    } while (0)
+
+    for (auto& s : slots) {
+        PH_CUDA(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
+        PH_CUDA(cudaEventCreateWithFlags(&s.computed, cudaEventDisableTiming));
+        PH_CUDA(cudaEventCreateWithFlags(&s.drained, cudaEventDisableTiming));
+    }
+    if (do_hits) PH_CHECK(d_hits.ensure(std::max<size_t>((size_t)hit_cap * kHitRowBytes, 64)));
+    PH_CHECK(d_tot.ensure(64));  // ping-pong running totals
+    PH_CUDA(cudaMemsetAsync(d_tot.p, 0, 64, s_comp));
+    wfb_fh_params p = *params;
+    p.lmax = lmax;
+    p.rules_dev = nullptr;
+    if (p.n_rules > 0) {
+        WFB_REQUIRE(rules_host != nullptr, "wfb_process_host: n_rules > 0 but rules_host is NULL");
+        PH_CHECK(d_rules.ensure(sizeof(wfb_chan_rule) * p.n_rules));
+        PH_CUDA(cudaMemcpyAsync(d_rules.p, rules_host, sizeof(wfb_chan_rule) * p.n_rules, cudaMemcpyHostToDevice, s_comp));
+        p.rules_dev = static_cast<const wfb_chan_rule*>(d_rules.p);
+    }
+
+    int64_t chunk_idx = 0;
+    for (int64_t r0 = 0; r0 < n; r0 += chunk_records, ++chunk_idx) {
+        const int64_t r1 = std::min<int64_t>(n, r0 + chunk_records), m = r1 - r0;
+        Slot& s = slots[chunk_idx % kSlots];
+        // pool range of the chunk: wave_offsets ascend with the record index
+        long long lo = -1, hi = -1;
+        for (int64_t i = r0; i < r1; ++i) {
+            if (rec_i32(rows + i * kRecordsRowBytes, 90) > 0) { lo = rec_i64(rows + i * kRecordsRowBytes, 82); break; }
+        }
+        for (int64_t i = r1 - 1; i >= r0; --i) {
+            int len = rec_i32(rows + i * kRecordsRowBytes, 90);
+            if (len > 0) { hi = rec_i64(rows + i * kRecordsRowBytes, 82) + len; break; }
+        }
+        if (lo < 0) lo = hi = 0;
+        if (lo > hi || hi > pool_len || lo < 0) {
+            set_error("records reference samples outside wave_pool bounds");
+            rc = WFB_ERR_LAYOUT;
+            cleanup();
+            return rc;
+        }
+        const long long lo_al = lo & ~7ll;  // keep 16-byte alignment of record starts relative to the pool
+        const size_t pool_bytes = (size_t)(hi - lo_al) * esz;
+        PH_CHECK(s.pool.ensure(pool_bytes + 64));
+        PH_CHECK(s.rows.ensure((size_t)m * kRecordsRowBytes + 64));
+        PH_CHECK(s.meta.ensure((size_t)m * sizeof(wfb_rec_meta) + 64));
+        if (do_feat) PH_CHECK(s.feat.ensure((size_t)m * kFeatRowBytes + 64));
+        if (do_hits && hit_counts_host) PH_CHECK(s.counts.ensure((size_t)m * 4 + 64));
+        PH_CHECK(s.ws.ensure(wfb_features_hits_workspace_bytes(m)));
+        // the slot's previous results must have left the device before we overwrite them
+        PH_CUDA(cudaStreamWaitEvent(s_copy, s.drained, 0));
+        PH_CUDA(cudaStreamWaitEvent(s_copy, s.computed, 0));
+        if (pool_bytes) PH_CUDA(cudaMemcpyAsync(s.pool.p, pool + (size_t)lo_al * esz, pool_bytes, cudaMemcpyHostToDevice, s_copy));
+        PH_CUDA(cudaMemcpyAsync(s.rows.p, rows + (size_t)r0 * kRecordsRowBytes, (size_t)m * kRecordsRowBytes, cudaMemcpyHostToDevice, s_copy));
+        PH_CUDA(cudaEventRecord(s.copied, s_copy));
+        PH_CUDA(cudaStreamWaitEvent(s_comp, s.copied, 0));
+        PH_CUDA(cudaStreamWaitEvent(s_comp, s.drained, 0));
+        PH_CHECK(wfb_records_unpack(s.rows.p, m, static_cast<wfb_rec_meta*>(s.meta.p), s_comp));
+        p.pool_base = params->pool_base + lo_al;
+        p.row_base = params->row_base + r0;
+        int64_t* tot = static_cast<int64_t*>(d_tot.p);
+        PH_CHECK(wfb_features_hits(s.pool.p, hi - lo_al, static_cast<const wfb_rec_meta*>(s.meta.p), m, &p, s.feat.p,
+                                   d_hits.p, hit_cap, (do_hits && hit_counts_host) ? static_cast<int32_t*>(s.counts.p) : nullptr,
+                                   tot + (chunk_idx & 1), tot + ((chunk_idx + 1) & 1), s.ws.p, s.ws.cap, s_comp));
+        PH_CUDA(cudaEventRecord(s.computed, s_comp));
+        PH_CUDA(cudaStreamWaitEvent(s_out, s.computed, 0));
+        if (do_feat)
+            PH_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(feat_out_host) + (size_t)r0 * kFeatRowBytes, s.feat.p,
+                                    (size_t)m * kFeatRowBytes, cudaMemcpyDeviceToHost, s_out));
+        if (do_hits && hit_counts_host)
+            PH_CUDA(cudaMemcpyAsync(hit_counts_host + r0, s.counts.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s_out));
+        PH_CUDA(cudaEventRecord(s.drained, s_out));
+    }
+    PH_CUDA(cudaStreamSynchronize(s_comp));
+    for (auto& s : slots) {
+        if (!s.ws.p) continue;
+        int err = wfb_features_hits_check(s.ws.p, s_comp);
+        if (err != WFB_OK) { cleanup(); return err; }
+    }
+    if (do_hits) {
+        long long total = 0;
+        PH_CUDA(cudaMemcpy(&total, static_cast<int64_t*>(d_tot.p) + (chunk_idx & 1), 8, cudaMemcpyDeviceToHost));
+        *n_hits = total;
+        long long keep = std::min<long long>(total, hit_cap);
+        if (keep > 0) PH_CUDA(cudaMemcpyAsync(hit_out_host, d_hits.p, (size_t)keep * kHitRowBytes, cudaMemcpyDeviceToHost, s_out));
+    }
+    PH_CUDA(cudaStreamSynchronize(s_out));
+    cleanup();
+    return WFB_OK;
+#undef PH_CHECK
+#undef PH_CUDA
+}

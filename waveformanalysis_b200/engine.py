@@ -1,0 +1,354 @@
+"""Host-side runtime over the C-ABI: device buffers (torch tensors as owners only), parameter
+blocks, and the two ways into the fused pass:
+
+  * ``process_host``  - reference-facing: host numpy records + wave_pool in, host rows out
+                        (chunked H2D -> kernels -> D2H pipeline inside ``wfb_process_host``).
+  * ``DeviceRun``     - device-resident records + pool for repeated passes (bench ``value``,
+                        multi-GPU shards, plugin chains that reuse one upload).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .dtypes import (
+    BASIC_FEATURES_DTYPE,
+    RECORDS_DTYPE,
+    THRESHOLD_HIT_DTYPE,
+)
+
+CHAN_RULE_DTYPE = np.dtype(
+    [
+        ("board", "i4"),
+        ("channel", "i4"),
+        ("threshold", "f8"),
+        ("fixed_baseline", "f8"),
+        ("has_threshold", "i4"),
+        ("has_fixed_baseline", "i4"),
+    ]
+)
+assert CHAN_RULE_DTYPE.itemsize == C.sizeof(_lib.ChanRule)
+
+
+def _torch():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("no CUDA device visible: the B200 plugins have no CPU fallback")
+    return torch
+
+
+def _ptr(t) -> C.c_void_p:
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(_torch().cuda.current_stream().cuda_stream)
+
+
+def _hptr(a: np.ndarray | None) -> C.c_void_p:
+    return C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(0)
+
+
+# --------------------------------------------------------------------------------------------
+# host-side argument preparation
+# --------------------------------------------------------------------------------------------
+
+
+def packed_records(records: np.ndarray, explicit_dt: int | None = None) -> np.ndarray:
+    """Return ``records`` as a C-contiguous RECORDS_DTYPE array (no copy when it already is).
+
+    Arrays with a subset of the fields (as RecordsView accepts, records_view.py:18-23) are
+    widened with the defaults the reference plugins use: board/channel 0, polarity 'unknown',
+    record_id = arange (basic_features.py:115-129), dt from ``explicit_dt``.
+    """
+    if records.dtype == RECORDS_DTYPE:
+        return np.ascontiguousarray(records)
+    names = records.dtype.names
+    if names is None:
+        raise ValueError("records must be a structured array")
+    required = ("wave_offset", "event_length", "timestamp", "baseline")
+    missing = [f for f in required if f not in names]
+    if missing:
+        raise ValueError(f"records missing required fields: {missing}")
+    out = np.zeros(len(records), dtype=RECORDS_DTYPE)
+    out["baseline_upstream"] = np.nan
+    out["polarity"] = "unknown"
+    out["record_id"] = np.arange(len(records), dtype=np.int64)
+    for f in RECORDS_DTYPE.names:
+        if f in names:
+            out[f] = records[f]
+    if "dt" not in names:
+        if explicit_dt is None:
+            raise ValueError("records is missing required field 'dt'; provide explicit config 'dt'")
+        out["dt"] = int(explicit_dt)
+    return out
+
+
+def check_pool(pool: np.ndarray) -> tuple[np.ndarray, int]:
+    if not isinstance(pool, np.ndarray):
+        raise ValueError("wave_pool must be a numpy array")
+    if pool.dtype == np.uint16:
+        return np.ascontiguousarray(pool).reshape(-1), 0
+    if pool.dtype == np.float32:
+        return np.ascontiguousarray(pool).reshape(-1), 1
+    raise ValueError(f"wave_pool dtype must be uint16 or float32, got {pool.dtype}")
+
+
+def make_rules(thresholds: dict | None = None, fixed_baselines: dict | None = None) -> np.ndarray:
+    """(board, channel) -> override tables -> wfb_chan_rule array."""
+    keys = sorted(set(thresholds or {}) | set(k for k, v in (fixed_baselines or {}).items() if v is not None))
+    rules = np.zeros(len(keys), dtype=CHAN_RULE_DTYPE)
+    for i, (b, c) in enumerate(keys):
+        rules[i]["board"], rules[i]["channel"] = int(b), int(c)
+        if thresholds and (b, c) in thresholds:
+            rules[i]["threshold"] = float(thresholds[(b, c)])
+            rules[i]["has_threshold"] = 1
+        if fixed_baselines and fixed_baselines.get((b, c)) is not None:
+            rules[i]["fixed_baseline"] = float(fixed_baselines[(b, c)])
+            rules[i]["has_fixed_baseline"] = 1
+    return rules
+
+
+def _slice_arg(v, default):
+    if v is None:
+        return default
+    return int(v)
+
+
+def make_params(
+    *,
+    flags: int,
+    pool_is_f32: int,
+    height_range=(40, 90),
+    area_range=(0, None),
+    threshold: float = 10.0,
+    left_extension: int = 2,
+    right_extension: int = 2,
+    lmax: int = 0,
+    n_rules: int = 0,
+    rules_dev: int = 0,
+    pool_base: int = 0,
+    row_base: int = 0,
+) -> _lib.FHParams:
+    p = _lib.FHParams()
+    p.flags = int(flags)
+    p.pool_is_f32 = int(pool_is_f32)
+    p.height_start = _slice_arg(height_range[0], 0)
+    p.height_end = _slice_arg(height_range[1], _lib.SLICE_END_NONE)
+    p.area_start = _slice_arg(area_range[0], 0)
+    p.area_end = _slice_arg(area_range[1], _lib.SLICE_END_NONE)
+    p.threshold = float(threshold)
+    p.left_extension = max(0, int(left_extension))
+    p.right_extension = max(0, int(right_extension))
+    p.lmax = int(lmax)
+    p.n_rules = int(n_rules)
+    p.rules_dev = rules_dev
+    p.pool_base = int(pool_base)
+    p.row_base = int(row_base)
+    return p
+
+
+# --------------------------------------------------------------------------------------------
+# reference-facing call: host buffers in, host rows out
+# --------------------------------------------------------------------------------------------
+
+
+def process_host(
+    records: np.ndarray,
+    pool: np.ndarray,
+    *,
+    features: bool = True,
+    hits: bool = True,
+    height_range=(40, 90),
+    area_range=(0, None),
+    threshold: float = 10.0,
+    left_extension: int = 2,
+    right_extension: int = 2,
+    thresholds: dict | None = None,
+    fixed_baselines: dict | None = None,
+    explicit_dt: int | None = None,
+    want_counts: bool = False,
+    hit_cap: int | None = None,
+    chunk_records: int = 0,
+    out_features: np.ndarray | None = None,
+) -> dict:
+    """Fused pass over host buffers through ``wfb_process_host``.  Returns a dict with
+    ``features`` (BASIC_FEATURES_DTYPE), ``hits`` (THRESHOLD_HIT_DTYPE), ``counts`` (int32)."""
+    lib = _lib.load()
+    _torch()
+    rec = packed_records(records, explicit_dt)
+    pool, is_f32 = check_pool(pool)
+    n = len(rec)
+    flags = (_lib.DO_FEATURES if features else 0) | (_lib.DO_HITS if hits else 0)
+    rules = make_rules(thresholds, fixed_baselines)
+    lmax = int(rec["event_length"].max()) if (hits and n) else 0
+    p = make_params(flags=flags, pool_is_f32=is_f32, height_range=height_range, area_range=area_range,
+                    threshold=threshold, left_extension=left_extension, right_extension=right_extension,
+                    lmax=max(lmax, 0), n_rules=len(rules))
+    feat = None
+    if features:
+        feat = out_features if out_features is not None else np.empty(n, dtype=BASIC_FEATURES_DTYPE)
+    counts = np.empty(n, dtype=np.int32) if (hits and want_counts) else None
+    cap = int(hit_cap) if hit_cap is not None else max(1024, 4 * n)
+    hit_rows = None
+    n_hits = C.c_int64(0)
+    while True:
+        hit_rows = np.empty(cap if hits else 0, dtype=THRESHOLD_HIT_DTYPE)
+        rc = lib.wfb_process_host(_hptr(rec), n, _hptr(pool), len(pool), C.byref(p), _hptr(rules if len(rules) else None),
+                                  _hptr(feat), _hptr(hit_rows if hits and cap else None), cap if hits else 0,
+                                  _hptr(counts), C.byref(n_hits), int(chunk_records))
+        _lib.check(rc, "wfb_process_host")
+        if not hits or n_hits.value <= cap:
+            break
+        cap = int(n_hits.value)  # rare: more hits than the initial estimate, run again with room
+    return dict(features=feat, hits=hit_rows[: n_hits.value] if hits else None, counts=counts, n_hits=int(n_hits.value))
+
+
+# --------------------------------------------------------------------------------------------
+# device-resident run
+# --------------------------------------------------------------------------------------------
+
+
+class DeviceRun:
+    """records (as wfb_rec_meta) + wave_pool resident in HBM."""
+
+    def __init__(self, meta, pool, n: int, pool_is_f32: int, lmax: int, records_rows=None, pool_base: int = 0, row_base: int = 0):
+        self.meta = meta  # torch.uint8 [n*48]
+        self.pool = pool  # torch tensor (uint16 stored as int16, or float32)
+        self.n = int(n)
+        self.pool_is_f32 = int(pool_is_f32)
+        self.lmax = int(lmax)
+        self.records_rows = records_rows
+        self.pool_base = int(pool_base)
+        self.row_base = int(row_base)
+        self._ws = None
+
+    @property
+    def pool_len(self) -> int:
+        return int(self.pool.numel())
+
+    @classmethod
+    def from_host(cls, records: np.ndarray, pool: np.ndarray, explicit_dt: int | None = None, *, pool_base: int = 0, row_base: int = 0) -> "DeviceRun":
+        torch = _torch()
+        lib = _lib.load()
+        rec = packed_records(records, explicit_dt)
+        pool, is_f32 = check_pool(pool)
+        n = len(rec)
+        rows = torch.from_numpy(rec.view(np.uint8).reshape(-1).copy() if n else np.zeros(0, np.uint8)).cuda()
+        if is_f32:
+            d_pool = torch.empty(len(pool) + 16, dtype=torch.float32, device="cuda")[: len(pool)]
+            d_pool.copy_(torch.from_numpy(pool))
+        else:
+            d_pool = torch.empty(len(pool) + 16, dtype=torch.int16, device="cuda")[: len(pool)]
+            d_pool.copy_(torch.from_numpy(pool.view(np.int16)))
+        meta = torch.empty(max(n, 1) * 48, dtype=torch.uint8, device="cuda")
+        _lib.check(lib.wfb_records_unpack(_ptr(rows), n, _ptr(meta), _stream()), "wfb_records_unpack")
+        lmax = int(rec["event_length"].max()) if n else 0
+        return cls(meta, d_pool, n, is_f32, max(lmax, 0), records_rows=rows, pool_base=pool_base, row_base=row_base)
+
+    @classmethod
+    def synth(cls, n: int, n_samples: int, n_channels: int, *, dt_ns: int = 2, seed: int = 1234, with_rows: bool = False) -> "DeviceRun":
+        torch = _torch()
+        lib = _lib.load()
+        pool = torch.empty(n * n_samples + 16, dtype=torch.int16, device="cuda")[: n * n_samples]
+        meta = torch.empty(max(n, 1) * 48, dtype=torch.uint8, device="cuda")
+        rows = torch.empty(n * 102, dtype=torch.uint8, device="cuda") if with_rows else None
+        _lib.check(lib.wfb_synth_fill(_ptr(pool), _ptr(meta), _ptr(rows), n, n_samples, n_channels, dt_ns, seed, 0, _stream()), "wfb_synth_fill")
+        return cls(meta, pool, n, 0, n_samples, records_rows=rows)
+
+    def workspace(self):
+        torch = _torch()
+        need = _lib.load().wfb_features_hits_workspace_bytes(self.n)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+        return self._ws
+
+    def features_hits(
+        self,
+        *,
+        features: bool = True,
+        hits: bool = True,
+        height_range=(40, 90),
+        area_range=(0, None),
+        threshold: float = 10.0,
+        left_extension: int = 2,
+        right_extension: int = 2,
+        rules: np.ndarray | None = None,
+        hit_cap: int | None = None,
+        out=None,
+        want_counts: bool = False,
+        lmax: int | None = None,
+    ) -> dict:
+        """One fused pass; returns device tensors (uint8 row buffers) + the int64 total tensor.
+        Asynchronous: nothing is copied to the host."""
+        torch = _torch()
+        lib = _lib.load()
+        flags = (_lib.DO_FEATURES if features else 0) | (_lib.DO_HITS if hits else 0)
+        d_rules = None
+        if rules is not None and len(rules):
+            d_rules = torch.from_numpy(rules.view(np.uint8).reshape(-1).copy()).cuda()
+        p = make_params(flags=flags, pool_is_f32=self.pool_is_f32, height_range=height_range, area_range=area_range,
+                        threshold=threshold, left_extension=left_extension, right_extension=right_extension,
+                        lmax=self.lmax if lmax is None else lmax, n_rules=0 if d_rules is None else len(rules),
+                        rules_dev=0 if d_rules is None else d_rules.data_ptr(), pool_base=self.pool_base, row_base=self.row_base)
+        out = out or {}
+        n = self.n
+        feat = out.get("features")
+        if features and feat is None:
+            feat = torch.empty(max(n, 1) * 36, dtype=torch.uint8, device="cuda")
+        cap = int(hit_cap) if hit_cap is not None else max(1024, 4 * n)
+        hit_rows = out.get("hits")
+        if hits and hit_rows is None:
+            hit_rows = torch.empty(max(cap, 1) * 60, dtype=torch.uint8, device="cuda")
+        if hits and hit_rows is not None:
+            cap = min(cap, hit_rows.numel() // 60) if hit_cap is not None else hit_rows.numel() // 60
+        total = out.get("total")
+        if total is None:
+            total = torch.zeros(1, dtype=torch.int64, device="cuda")
+        counts = out.get("counts")
+        if hits and want_counts and counts is None:
+            counts = torch.empty(max(n, 1), dtype=torch.int32, device="cuda")
+        ws = self.workspace()
+        rc = lib.wfb_features_hits(_ptr(self.pool), self.pool_len, _ptr(self.meta), n, C.byref(p), _ptr(feat if features else None),
+                                   _ptr(hit_rows if hits else None), cap if hits else 0, _ptr(counts if hits else None),
+                                   C.c_void_p(0), _ptr(total), _ptr(ws), ws.numel(), _stream())
+        _lib.check(rc, "wfb_features_hits")
+        return dict(features=feat, hits=hit_rows, total=total, counts=counts, cap=cap, rules=d_rules)
+
+    def check(self):
+        _lib.check(_lib.load().wfb_features_hits_check(_ptr(self.workspace()), _stream()), "wfb_features_hits")
+
+    def run_to_host(self, **kw) -> dict:
+        """features_hits + copy the rows to host numpy arrays (re-runs if the hit buffer was small)."""
+        torch = _torch()
+        res = self.features_hits(**kw)
+        self.check()
+        out = {}
+        if res["features"] is not None and kw.get("features", True):
+            out["features"] = res["features"][: self.n * 36].cpu().numpy().view(BASIC_FEATURES_DTYPE)
+        if kw.get("hits", True):
+            total = int(res["total"].item())
+            if total > res["cap"]:
+                kw2 = dict(kw)
+                kw2["hit_cap"] = total
+                kw2.pop("out", None)
+                res = self.features_hits(**kw2)
+                torch.cuda.synchronize()
+                total = int(res["total"].item())
+            out["hits"] = res["hits"][: total * 60].cpu().numpy().view(THRESHOLD_HIT_DTYPE)
+            if res["counts"] is not None:
+                out["counts"] = res["counts"][: self.n].cpu().numpy()
+        return out
+
+    def records_to_host(self) -> np.ndarray:
+        if self.records_rows is None:
+            raise ValueError("this DeviceRun holds no packed records rows")
+        return self.records_rows.cpu().numpy().view(RECORDS_DTYPE)
+
+    def pool_to_host(self) -> np.ndarray:
+        a = self.pool.cpu().numpy()
+        return a if self.pool_is_f32 else a.view(np.uint16)

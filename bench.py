@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""bench.py - records/s of the fused records -> baseline -> threshold hits -> basic_features path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): 16 channels x 1M records x 800 int16 samples per GPU
+(16 M records, 25.6 GB of samples), synthetic, generated on the device.
+A step = one fused pass over all records of the rank.  Weak scaling: every rank owns its own
+time shard of 16 M records; there is no data-path collective in this pass.
+
+Printed JSON line (rank 0): `value` = records/s with inputs resident in HBM (CUDA events, max
+over ranks); `e2e` = the same pass through the reference-facing plugin call with pinned HOST
+buffers (H2D + kernels + D2H inside the timed region); `roofline` for the fused kernel against
+the measured HBM copy bandwidth; `cpu_baseline` = the CPU oracle port on a bounded sample.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "records_per_s"
+UNIT = "records/s"
+N_CHANNELS = 16
+N_SAMPLES = 800
+RECORDS_PER_GPU = 16 * 1_000_000
+THRESHOLD = 15.0
+FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--records", type=int, default=RECORDS_PER_GPU, help="records per GPU (default: configs[1])")
+    ap.add_argument("--e2e-records", type=int, default=4_000_000, help="records per GPU for the host-buffer e2e leg")
+    ap.add_argument("--cpu-sample", type=int, default=16384, help="records per CPU worker for the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, extra=None):
+    cfg = {
+        "workload": f"fused records->baseline->hits->basic_features, {N_CHANNELS} ch x {args.records // N_CHANNELS} records x {N_SAMPLES} int16 samples per GPU (BASELINE configs[1])",
+        "records_per_gpu": args.records,
+        "samples_per_record": N_SAMPLES,
+        "threshold": THRESHOLD,
+        "height_range": [40, 90],
+        "area_range": [0, None],
+        "l2_policy": "inputs (25.6 GB per GPU) exceed the 126 MB L2; no flush needed",
+        "sharding": "time shards, one per rank, no data-path collective",
+    }
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (oracle port)
+# ------------------------------------------------------------------------------------------------
+
+
+def _cpu_worker(task):
+    seed, n = task
+    import numpy as np  # noqa: F401
+
+    from oracle import np_oracle as O
+    from waveformanalysis_b200.synth import make_raw_run, records_from_raw
+
+    raw = make_raw_run(N_CHANNELS, max(1, n // N_CHANNELS), N_SAMPLES, seed=seed)
+    rec, pool = records_from_raw(raw)
+    t0 = time.perf_counter()
+    O.basic_features(rec, pool)
+    O.threshold_hits(rec, pool, threshold=THRESHOLD)
+    return len(rec), time.perf_counter() - t0
+
+
+def cpu_port_throughput(n_per_worker: int, workers: int, seed0: int = 100):
+    """records/s of the numpy oracle (basic_features + threshold_hits) over `workers` processes.
+    Wall time is that of the slowest worker (generation of the synthetic sample is not timed)."""
+    import multiprocessing as mp
+
+    tasks = [(seed0 + i, n_per_worker) for i in range(workers)]
+    if workers == 1:
+        res = [_cpu_worker(tasks[0])]
+    else:
+        ctx = mp.get_context("spawn")
+        with ctx.Pool(workers) as pool:
+            res = pool.map(_cpu_worker, tasks)
+    n_total = sum(r[0] for r in res)
+    wall = max(r[1] for r in res)
+    return n_total / wall, n_total, wall
+
+
+def run_reference(args):
+    """--impl reference: the reference's algorithm for this path on the host cores.  The reference
+    is pure Python and cannot travel to the GPU box, so this is the oracle port (kind 'port'),
+    one process per host core."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    vals = []
+    for step in range(args.warmup + args.steps):
+        v, n_total, wall = cpu_port_throughput(args.cpu_sample // 2, cores, seed0=1000 + 17 * step)
+        if step >= args.warmup:
+            vals.append((v, n_total, wall))
+    value = sum(v[0] for v in vals) / len(vals)
+    ms = 1e3 * sum(v[2] for v in vals) / len(vals)
+    sample = f"{vals[0][1]} records per step ({cores} processes x {args.cpu_sample // 2} records), numpy oracle basic_features+threshold_hits"
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": ms,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "u16",
+        "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU legs
+# ------------------------------------------------------------------------------------------------
+
+
+class ClockSampler:
+    QUERY = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.strip().splitlines():
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic_per_launch():
+    """dram bytes per launch of the fused kernel from the committed ncu capture, if present."""
+    path = os.path.join(ROOT, "profiles", "fused_kernel_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from waveformanalysis_b200 import engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    n = args.records
+    run = engine.DeviceRun.synth(n, N_SAMPLES, N_CHANNELS, seed=1234 + 1 + 1000 * rank)
+    torch.cuda.synchronize()
+    # size the hit buffer from one counting pass (hits beyond the capacity are only counted)
+    res = run.features_hits(threshold=THRESHOLD, hit_cap=1024)
+    torch.cuda.synchronize()
+    n_hits = int(res["total"].item())
+    cap = n_hits + 1024
+    out = {
+        "features": torch.empty(n * 36, dtype=torch.uint8, device="cuda"),
+        "hits": torch.empty(cap * 60, dtype=torch.uint8, device="cuda"),
+        "total": torch.zeros(1, dtype=torch.int64, device="cuda"),
+    }
+    kw = dict(threshold=THRESHOLD, hit_cap=cap, out=out)
+
+    for _ in range(max(args.warmup, 3)):
+        run.features_hits(**kw)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record()
+    for i in range(args.steps):
+        run.features_hits(**kw)
+        ev[i + 1].record()
+    barrier()
+    step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    total_ms = ev[0].elapsed_time(ev[args.steps])
+    clocks = sampler.stop() if sampler else None
+    run.check()
+    assert int(out["total"].item()) == n_hits, "hit count changed between passes"
+    total_ms = max_over_ranks(total_ms)
+    ms_per_step = total_ms / args.steps
+    records_all = sum_over_ranks(float(n))
+    hits_all = sum_over_ranks(float(n_hits))
+    value = records_all / (ms_per_step * 1e-3)
+
+    # ---- roofline of the fused kernel (rank 0's launches; SURVEY.md 8(d): 2L + 72 + 60h bytes per record)
+    h = n_hits / n
+    bytes_per_record = 2 * N_SAMPLES + 72 + 60 * h
+    kernel_ms = sum(step_ms) / len(step_ms)
+    achieved = n * bytes_per_record / (kernel_ms * 1e-3) / 1e9
+    peak, peak_src = measured_peak()
+    traffic = ncu_traffic_per_launch()
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+        "peak_source": peak_src, "kernel": "fused_features_hits_kernel<uint16,true,true>",
+        "bytes_per_record": bytes_per_record, "hits_per_record": h, "kernel_ms": kernel_ms,
+        "raw_sample_GBps": n * 2 * N_SAMPLES / (kernel_ms * 1e-3) / 1e9,
+    }
+    if traffic:
+        roofline["traffic_source"] = traffic.get("source")
+
+    # ---- e2e: host buffers through the reference-facing call
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, engine, torch, barrier, max_over_ranks, sum_over_ranks, rank)
+
+    # free the device-resident run before the CPU leg
+    del run, out, res
+    torch.cuda.empty_cache()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        v, n_total, wall = cpu_port_throughput(args.cpu_sample, cores)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n_total} records ({cores} processes x {args.cpu_sample}), numpy oracle basic_features+threshold_hits, wall {wall:.2f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC,
+            "value": value,
+            "unit": UNIT,
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "u16",
+            "data": "synthetic",
+            "config": workload_config(args, {"hits_per_record": hits_all / records_all}),
+            "raw_sample_GBps": records_all * 2 * N_SAMPLES / (ms_per_step * 1e-3) / 1e9,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "e2e": e2e,
+            "gpu_launches": args.steps * 1,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e(args, engine, torch, barrier, max_over_ranks, sum_over_ranks, rank):
+    """Same pass through the plugin-facing host call: pinned host records + wave_pool in,
+    host feature / hit rows out, every step."""
+    import numpy as np
+
+    n = min(args.e2e_records, args.records)
+    dev = engine.DeviceRun.synth(n, N_SAMPLES, N_CHANNELS, seed=77 + rank, with_rows=True)
+    pool_pin = torch.empty(n * N_SAMPLES, dtype=torch.int16).pin_memory()
+    rows_pin = torch.empty(n * 102, dtype=torch.uint8).pin_memory()
+    pool_pin.copy_(dev.pool)
+    rows_pin.copy_(dev.records_rows)
+    torch.cuda.synchronize()
+    del dev
+    torch.cuda.empty_cache()
+    from waveformanalysis_b200.dtypes import BASIC_FEATURES_DTYPE, RECORDS_DTYPE
+
+    records = rows_pin.numpy().view(RECORDS_DTYPE)
+    pool = pool_pin.numpy().view(np.uint16)
+    feat_pin = torch.empty(n * 36, dtype=torch.uint8).pin_memory()
+    out_features = feat_pin.numpy().view(BASIC_FEATURES_DTYPE)
+    first = engine.process_host(records, pool, threshold=THRESHOLD, out_features=out_features)
+    cap = first["n_hits"] + 1024
+    from waveformanalysis_b200.dtypes import THRESHOLD_HIT_DTYPE
+
+    hits_pin = torch.empty(cap * 60, dtype=torch.uint8).pin_memory()
+    out_hits = hits_pin.numpy().view(THRESHOLD_HIT_DTYPE)
+    steps = max(2, min(args.steps, 5))
+    for _ in range(1):
+        engine.process_host(records, pool, threshold=THRESHOLD, out_features=out_features, out_hits=out_hits)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        res = engine.process_host(records, pool, threshold=THRESHOLD, out_features=out_features, out_hits=out_hits)
+    barrier()
+    wall = max_over_ranks(time.perf_counter() - t0)
+    assert res["n_hits"] == first["n_hits"]
+    n_all = sum_over_ranks(float(n))
+    return {
+        "value": n_all * steps / wall,
+        "unit": UNIT,
+        "h2d_bytes_per_step": int(n * (2 * N_SAMPLES + 102)),
+        "d2h_bytes_per_step": int(n * 36 + res["n_hits"] * 60),
+        "records_per_gpu": n,
+        "steps": steps,
+        "call": "waveformanalysis_b200.engine.process_host (wfb_process_host): pinned host records+wave_pool -> host feature/hit rows",
+    }
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -188,3 +188,33 @@ def test_device_synth_matches_oracle(eng):
     # linearity / idempotence properties usable at full bench size: same input -> identical bytes
     again = run.run_to_host(threshold=15.0)
     assert np.array_equal(got["hits"].view(np.uint8), again["hits"].view(np.uint8))
+
+
+@pytest.mark.parametrize("variant", ["global", "staged"])
+def test_kernel_variants_agree(eng, golden, variant, monkeypatch):
+    """All data-movement variants of the fused kernel (TMA-staged slot ring,
+    and the global-memory accessor used for very long records) produce identical bytes."""
+    monkeypatch.setenv("WFB_FUSED_VARIANT", variant)
+    rec, pool = golden["records"], golden["wave_pool"]
+    out = eng.DeviceRun.from_host(rec, pool).run_to_host(threshold=15.0)
+    assert_rows_match(out["features"], golden["bf_default"], what="bf", float_exact=FX_BF)
+    assert_rows_match(out["hits"], golden["hits_thr15"], what="hits", float_exact=FX_HIT)
+    rr, rp = golden["rag_records"], golden["rag_pool"]
+    out = eng.DeviceRun.from_host(rr, rp).run_to_host(height_range=(5, -5), threshold=15.0, left_extension=3, right_extension=4)
+    assert_rows_match(out["features"], golden["rag_bf"], what="rag_bf", float_exact=FX_BF)
+    assert_rows_match(out["hits"], golden["rag_hits"], what="rag_hits", float_exact=("height", "width"))
+    fp = golden["filt_sg"]
+    out = eng.DeviceRun.from_host(golden["filt_records"], fp).run_to_host(threshold=15.0)
+    assert_rows_match(out["features"], golden["filt_bf"], what="filt_bf")
+    assert_rows_match(out["hits"], golden["filt_hits"], what="filt_hits")
+
+
+def test_long_records_use_global_path(eng):
+    from oracle import np_oracle as O
+    from waveformanalysis_b200.synth import make_raw_run, records_from_raw
+
+    raw = make_raw_run(2, 6, 120_000, seed=3)  # 240 KB per record: does not fit a shared-memory slot
+    rec, pool = records_from_raw(raw)
+    out = eng.DeviceRun.from_host(rec, pool).run_to_host(threshold=15.0, height_range=(0, None))
+    assert_rows_match(out["features"], O.basic_features(rec, pool, height_range=(0, None)), what="long bf", float_exact=FX_BF)
+    assert_rows_match(out["hits"], O.threshold_hits(rec, pool, threshold=15.0), what="long hits", float_exact=FX_HIT)

@@ -1,31 +1,48 @@
-// K2 + K3: fused baseline-subtract -> threshold hit finding -> basic_features, one warp per
-// record, with single-pass stream compaction of the variable-length hit rows
-// (decoupled look-back over tiles of 32 records, so rows come out in the reference's order:
-// record-major, then start sample).
+// K2 + K3: fused baseline-subtract -> threshold hit finding -> basic_features with single-pass
+// stream compaction of the variable-length hit rows.
 //
 // Reference semantics restated here (paths relative to waveform_analysis/):
 //   basic_features  core/plugins/builtin/cpu/basic_features.py:108-195 (records branch)
 //   signals()       core/data/records_view.py:87-100
 //   hit_threshold   core/plugins/builtin/cpu/hit_finder.py:122-255, 329-413
 //
-// uint16 pool: every per-sample operation is integer (min / max / sum / |diff| / compare with
-// a per-record integer threshold that is exactly equivalent to the reference's float64
-// `baseline - wave >= thr`); float64 is only used per record / per hit.
+// Work decomposition
+//   * block = 8 warps = one tile of 256 consecutive records; warp w owns 32 of them, and LANE j
+//     of the warp keeps the bookkeeping of record j (metadata, per-channel rule, integer
+//     threshold, python-slice bounds, feature results, hit count) so all per-record scalar work
+//     is done 32-wide.  The samples of one record are then scanned by the whole warp.
+//   * samples reach the SM through a per-warp ring of shared-memory slots filled by 1-D TMA bulk
+//     copies (cp.async.bulk + one mbarrier per slot), issued kSlots-1 records ahead, so the scan
+//     reads LDS.128 chunks and the per-hit segment reductions never go back to L2/HBM.  Records
+//     too long for a slot run the same code over a global-memory accessor.
+//   * hits are staged per warp in shared memory; one decoupled look-back per 256-record tile
+//     gives the tile's first output row, so rows come out in the reference's order
+//     (record-major, then start sample); rows are assembled lane-parallel (one hit per lane),
+//     transposed through shared memory and written coalesced.
+//
+// uint16 pool: every per-sample operation is integer (packed 16x2 min / max, IDP.2A sums,
+// |diff| via max-min, compare against a per-record integer threshold that is exactly equivalent
+// to the reference's float64 `baseline - wave >= thr`); float64 only per record / per hit.
 // float32 pool (wave_pool_filtered): per-sample float64, as the reference does.
 #include <float.h>
 #include <limits.h>
+#include <stdlib.h>
+
+#include <algorithm>
 
 #include "common.cuh"
 
 namespace wfb {
 
-constexpr int kWarps = 8;                     // warps per block
-constexpr int kRecPerWarp = 4;                // consecutive records handled by one warp per tile
-constexpr int kTile = kWarps * kRecPerWarp;   // records per tile (one look-back unit)
-constexpr int kEntPerWarp = 64;               // staged hits per warp per tile before re-scan
+constexpr int kWarps = 8;                 // warps per block
+constexpr int kTile = kWarps * 32;        // records per tile / look-back unit
+constexpr int kEntPerWarp = 256;          // staged hits per warp per tile (8 per record on average)
+constexpr int kSlots = 3;                 // TMA slot ring depth per warp
+constexpr int kRowBufBytes = 32 * 17 * 4; // row transposition buffer per warp (32 rows x (15 + 2) words)
 
 struct HitEnt {  // a found hit, staged in shared memory until the tile's output offset is known
-    int p, s, e;
+    int p, s;
+    unsigned e_rec;  // end sample | owning lane << 27
     float height, integral;
 };
 
@@ -36,6 +53,8 @@ struct FHArgs {
     long long n;
     wfb_fh_params p;
     int lmax;
+    int slot_bytes;  // shared-memory bytes per staged record (0: read samples from global memory)
+    int ring_bytes;  // shared-memory bytes per warp (slot ring, reused as the row transposition buffer)
     uint8_t* feat_out;
     uint8_t* hit_out;
     long long hit_cap;
@@ -48,10 +67,18 @@ struct FHArgs {
     int n_tiles;
 };
 
-struct RecInfo {
-    long long off, ts, rid;
-    int len, dt, board, channel, pol;
+// what the scan of one record needs (warp-uniform, broadcast from the owning lane)
+struct ScanRec {
+    int mis, len, pol;
     double b_rec, b_feat, thr;
+    int kmax;
+    int p0, p1, c0, c1;
+};
+// what a hit row needs beyond the staged entry
+struct RowRec {
+    long long ts, rid;
+    int len, dt;
+    unsigned bc;  // board | channel << 16
 };
 
 // ---- tile descriptor: status in the top 2 bits, value below ---------------------------------
@@ -66,48 +93,61 @@ __device__ __forceinline__ void st_state(unsigned long long* p, unsigned long lo
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// ---- sample chunks: 8 consecutive samples per lane -------------------------------------------
-template <typename T>
-struct Chunk {
-    T v[8];
-};
+// ---- mbarrier + TMA bulk copy (global -> shared) ---------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WFB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WFB_DONE;\n"
+        "bra WFB_WAIT;\n"
+        "WFB_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ void load_chunk(const uint16_t* pool, long long pool_len, long long a, int lo, int hi,
-                                           Chunk<uint16_t>& c) {
-    if (hi <= lo) {
+// ---- sample sources ---------------------------------------------------------------------------
+// Both expose the record on a grid of 16-byte chunks: virtual index v = mis + i, where i is the
+// sample index in the record and mis the number of samples between the 16-byte boundary below
+// the record start and the record start.
+template <typename T>
+struct GlobalSrc {
+    const T* base;     // pool + (off - mis): 16-byte aligned
+    long long avail;   // samples readable from base
+    __device__ __forceinline__ uint4 load16(int v) const {
+        constexpr int PER = 16 / sizeof(T);
+        if (v + PER <= avail) return ldg_stream16(base + v);
+        T tmp[PER];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) c.v[j] = 0;
-        return;
+        for (int j = 0; j < PER; ++j) tmp[j] = (v + j < avail) ? base[v + j] : T(0);
+        return *reinterpret_cast<uint4*>(tmp);
     }
-    if (a + 8 <= pool_len) {
-        uint4 q = ldg_stream16(pool + a);
-        c.v[0] = q.x & 0xffff; c.v[1] = q.x >> 16;
-        c.v[2] = q.y & 0xffff; c.v[3] = q.y >> 16;
-        c.v[4] = q.z & 0xffff; c.v[5] = q.z >> 16;
-        c.v[6] = q.w & 0xffff; c.v[7] = q.w >> 16;
-    } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) c.v[j] = (a + j < pool_len) ? pool[a + j] : (uint16_t)0;
-    }
-}
-__device__ __forceinline__ void load_chunk(const float* pool, long long pool_len, long long a, int lo, int hi,
-                                           Chunk<float>& c) {
-    if (hi <= lo) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) c.v[j] = 0.f;
-        return;
-    }
-    if (a + 8 <= pool_len) {
-        uint4 q0 = ldg_stream16(pool + a), q1 = ldg_stream16(pool + a + 4);
-        c.v[0] = __uint_as_float(q0.x); c.v[1] = __uint_as_float(q0.y);
-        c.v[2] = __uint_as_float(q0.z); c.v[3] = __uint_as_float(q0.w);
-        c.v[4] = __uint_as_float(q1.x); c.v[5] = __uint_as_float(q1.y);
-        c.v[6] = __uint_as_float(q1.z); c.v[7] = __uint_as_float(q1.w);
-    } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) c.v[j] = (a + j < pool_len) ? pool[a + j] : 0.f;
-    }
-}
+    __device__ __forceinline__ T at(int v) const { return base[v]; }
+};
+template <typename T>
+struct SmemSrc {
+    const T* base;  // slot start (16-byte aligned shared memory)
+    __device__ __forceinline__ uint4 load16(int v) const { return *reinterpret_cast<const uint4*>(base + v); }
+    __device__ __forceinline__ T at(int v) const { return base[v]; }
+};
 
 // ---- the reference's float64 threshold test as an exact integer bound (uint16 pool) ---------
 // negative/unknown polarity: hit iff fl(b - w) >= thr  <=>  w <= kmax   (monotone in w)
@@ -116,17 +156,17 @@ __device__ __forceinline__ bool hit_test_u16(double b, double thr, bool positive
     double sig = positive ? __dsub_rn((double)w, b) : __dsub_rn(b, (double)w);
     return sig >= thr;
 }
-__device__ int integer_threshold_u16(double b, double thr, bool positive) {
+__device__ __noinline__ int integer_threshold_u16(double b, double thr, bool positive) {
     // largest k in [-1, 65535] such that every key kv <= k passes, kv = positive ? 65535 - w : w
     if (!(b == b) || !(thr == thr)) return -1;
     double guess = positive ? (65535.0 - (b + thr)) : (b - thr);
-    int k = guess >= 65535.0 ? 65535 : (guess < -1.0 ? -1 : (int)floor(guess));
+    int k = !(guess < 65535.0) ? 65535 : (guess < -1.0 ? -1 : (int)floor(guess));
     auto pass = [&](int kv) { return hit_test_u16(b, thr, positive, positive ? 65535 - kv : kv); };
     for (int it = 0; it < 4 && k < 65535 && pass(k + 1); ++it) ++k;
     for (int it = 0; it < 4 && k >= 0 && !pass(k); ++it) --k;
     // the guess is within one step of the true bound; verify and fall back to a bisection if not
     if ((k >= 0 && !pass(k)) || (k < 65535 && pass(k + 1))) {
-        int lo = -1, hi = 65535;  // invariant: pass(lo) (or lo == -1), !pass(hi + 1)
+        int lo = -1, hi = 65535;
         while (lo < hi) {
             int mid = lo + (hi - lo + 1) / 2;
             if (pass(mid)) lo = mid; else hi = mid - 1;
@@ -136,165 +176,164 @@ __device__ int integer_threshold_u16(double b, double thr, bool positive) {
     return k;
 }
 
-// ---- output rows ----------------------------------------------------------------------------
-__device__ __forceinline__ void write_feature_row(uint8_t* out, long long row, const RecInfo& r, float height,
-                                                  float amp, float area, float mad, long long event_index) {
-    int lane = lane_id();
-    if (lane < 9) {
-        unsigned w;
-        switch (lane) {
-            case 0: w = __float_as_uint(height); break;
-            case 1: w = __float_as_uint(amp); break;
-            case 2: w = __float_as_uint(area); break;
-            case 3: w = __float_as_uint(mad); break;
-            case 4: w = (unsigned)(r.ts & 0xffffffffll); break;
-            case 5: w = (unsigned)((unsigned long long)r.ts >> 32); break;
-            case 6: w = ((unsigned)r.board & 0xffffu) | ((unsigned)r.channel << 16); break;
-            case 7: w = (unsigned)(event_index & 0xffffffffll); break;
-            default: w = (unsigned)((unsigned long long)event_index >> 32); break;
-        }
-        reinterpret_cast<unsigned*>(out + row * kFeatRowBytes)[lane] = w;
-    }
-}
-
-// word `k` (0..14) of the packed 60-byte THRESHOLD_HIT row (hit_finder.py:33-49, 382-409)
-__device__ __forceinline__ unsigned hit_row_word(int k, const HitEnt& h, const RecInfo& r, int left, int right,
-                                                 int lmax) {
-    int a0 = max(0, h.s - left);
-    int a1 = min(lmax, h.e + right);
+// ---- packed THRESHOLD_HIT row (hit_finder.py:33-49, 382-409): 15 little-endian words ----------
+__device__ __forceinline__ void hit_row_words(unsigned w[15], int p, int s, int e, float height, float integral,
+                                              const RowRec& r, int left, int right, int lmax) {
+    int a0 = max(0, s - left);
+    int a1 = min(lmax, e + right);
     int rl = max(r.len, 0);
     int es = min(max(a0, 0), rl);
     int ee = max(min(max(a1, 0), rl), es);
-    switch (k) {
-        case 0: return (unsigned)h.p;
-        case 1: return 0u;  // position < 2^31
-        case 2: return __float_as_uint(h.height);
-        case 3: return __float_as_uint(h.integral);
-        case 4: return (unsigned)es;
-        case 5: return (unsigned)ee;
-        case 6: return __float_as_uint((float)(ee - es));
-        case 7: return (unsigned)r.dt;
-        case 8: return __float_as_uint((float)((long long)max(h.p - h.s, 0) * r.dt));
-        case 9: return __float_as_uint((float)((long long)max((h.e - 1) - h.p, 0) * r.dt));
-        case 10:
-        case 11: {
-            // int(timestamp + pos * (dt * 1e3)) evaluated in float64, no FMA contraction
-            double step = __dmul_rn((double)r.dt, 1e3);
-            double t = __dadd_rn((double)r.ts, __dmul_rn((double)h.p, step));
-            long long ti = (long long)t;
-            return k == 10 ? (unsigned)(ti & 0xffffffffll) : (unsigned)((unsigned long long)ti >> 32);
-        }
-        case 12: return ((unsigned)r.board & 0xffffu) | ((unsigned)r.channel << 16);
-        case 13: return (unsigned)(r.rid & 0xffffffffll);
-        default: return (unsigned)((unsigned long long)r.rid >> 32);
-    }
+    // int(timestamp + pos * (dt * 1e3)) evaluated in float64, no FMA contraction
+    double step = __dmul_rn((double)r.dt, 1e3);
+    long long ti = (long long)__dadd_rn((double)r.ts, __dmul_rn((double)p, step));
+    w[0] = (unsigned)p;
+    w[1] = 0u;  // position < 2^31
+    w[2] = __float_as_uint(height);
+    w[3] = __float_as_uint(integral);
+    w[4] = (unsigned)es;
+    w[5] = (unsigned)ee;
+    w[6] = __float_as_uint((float)(ee - es));
+    w[7] = (unsigned)r.dt;
+    w[8] = __float_as_uint((float)((long long)max(p - s, 0) * r.dt));
+    w[9] = __float_as_uint((float)((long long)max((e - 1) - p, 0) * r.dt));
+    w[10] = (unsigned)(ti & 0xffffffffll);
+    w[11] = (unsigned)((unsigned long long)ti >> 32);
+    w[12] = r.bc;
+    w[13] = (unsigned)(r.rid & 0xffffffffll);
+    w[14] = (unsigned)((unsigned long long)r.rid >> 32);
 }
 
 // ---- hit sinks --------------------------------------------------------------------------------
 struct StageSink {  // phase A: count every hit, keep the rows that fit the warp's staging area
-    HitEnt* buf;
-    int room;   // entries still free in the warp buffer
-    int n;      // hits of this record
-    __device__ __forceinline__ void store(const HitEnt& h, const RecInfo&, const FHArgs&) {
-        if (n < room && lane_id() == 0) buf[n] = h;
+    HitEnt* buf;    // next free entry of the warp
+    int room;
+    int n;
+    unsigned owner;  // lane that owns the record
+    __device__ __forceinline__ void store(int p, int s, int e, float height, float integral) {
+        if (n < room && lane_id() == 0) {
+            HitEnt h;
+            h.p = p;
+            h.s = s;
+            h.e_rec = (unsigned)e | (owner << 27);
+            h.height = height;
+            h.integral = integral;
+            buf[n] = h;
+        }
         ++n;
     }
 };
 struct RowSink {  // re-scan of a record whose hits did not fit: write rows straight to the output
-    long long row;
+    uint8_t* out;
+    long long row, cap;
+    RowRec r;
+    int left, right, lmax;
     int n;
-    __device__ __forceinline__ void store(const HitEnt& h, const RecInfo& r, const FHArgs& a) {
-        int lane = lane_id();
-        if (row < a.hit_cap && lane < 15)
-            reinterpret_cast<unsigned*>(a.hit_out + row * kHitRowBytes)[lane] =
-                hit_row_word(lane, h, r, a.p.left_extension, a.p.right_extension, a.lmax);
+    __device__ __forceinline__ void store(int p, int s, int e, float height, float integral) {
+        if (lane_id() == 0 && row < cap) {
+            unsigned w[15];
+            hit_row_words(w, p, s, e, height, integral, r, left, right, lmax);
+            unsigned* dst = reinterpret_cast<unsigned*>(out + row * kHitRowBytes);
+#pragma unroll
+            for (int k = 0; k < 15; ++k) dst[k] = w[k];
+        }
         ++row;
         ++n;
     }
 };
 
 // ---- per-hit segment reduction (hit_finder.py:369-381) --------------------------------------
-template <typename T, typename Sink>
-__device__ void emit_hit(const T* __restrict__ pool, const RecInfo& r, const FHArgs& a, int s, int e, Sink& sink) {
+template <typename T, typename Src, typename Sink>
+__device__ __forceinline__ void emit_hit(const Src& src, const ScanRec& r, const FHArgs& a, int s, int e, Sink& sink) {
     const int lane = lane_id();
     const bool positive = r.pol == WFB_POL_POSITIVE;
     const int a0 = max(0, s - a.p.left_extension);
     const int a1 = min(a.lmax, e + a.p.right_extension);
     if (a1 <= a0) return;
     const double b = r.b_rec;
-    double acc = 0.0;
-    HitEnt h;
-    h.s = s;
-    h.e = e;
+    int hp;
+    float hheight, hint;
     if constexpr (sizeof(T) == 2) {
+        // integral = sum(max(sig, 0)) = +-(cnt*b - sum(w)) over the samples on the signal side of b
+        const double bi = floor(b);
+        const int ib = (fabs(b) < 2e9) ? (int)bi : (b > 0 ? INT_MAX : INT_MIN);
+        // negative: w < b  <=>  w <= ceil(b)-1 ; positive: w > b  <=>  w >= floor(b)+1
+        const int wlim = positive ? ib + 1 : ((bi == b) ? ib - 1 : ib);
         int kbest = INT_MAX, ibest = INT_MAX;
+        unsigned cnt = 0;
+        unsigned long long sw = 0;
         for (int i = a0 + lane; i < a1; i += 32) {
-            int w = (i < r.len) ? (int)pool[r.off + i] : 0;  // padding samples are 0 (records_view.py:189)
+            int w = (i < r.len) ? (int)src.at(r.mis + i) : 0;  // padding samples are 0 (records_view.py:189)
             int kv = positive ? 65535 - w : w;
             if (kv < kbest) { kbest = kv; ibest = i; }
-            double sig = positive ? __dsub_rn((double)w, b) : __dsub_rn(b, (double)w);
-            acc += fmax(sig, 0.0);
+            bool in = positive ? (w >= wlim) : (w <= wlim);
+            cnt += in ? 1u : 0u;
+            sw += in ? (unsigned)w : 0u;
         }
         int kmin = __reduce_min_sync(kFull, kbest);
-        h.p = __reduce_min_sync(kFull, kbest == kmin ? ibest : INT_MAX);
+        hp = __reduce_min_sync(kFull, kbest == kmin ? ibest : INT_MAX);
         int wp = positive ? 65535 - kmin : kmin;
-        h.height = (float)(positive ? __dsub_rn((double)wp, b) : __dsub_rn(b, (double)wp));
+        hheight = (float)(positive ? __dsub_rn((double)wp, b) : __dsub_rn(b, (double)wp));
+        long long c = (long long)__reduce_add_sync(kFull, cnt);
+        long long swt = (a1 - a0 <= 32768) ? (long long)__reduce_add_sync(kFull, (unsigned)sw) : warp_sum_i64((long long)sw);
+        double integ;
+        if (fabs(b) < 2e9) {
+            double bf = __dsub_rn(b, bi);
+            long long ipart = positive ? (swt - c * (long long)bi) : (c * (long long)bi - swt);
+            double fpart = __dmul_rn((double)c, bf);
+            integ = positive ? __dsub_rn((double)ipart, fpart) : __dadd_rn((double)ipart, fpart);
+        } else {
+            integ = positive ? __dsub_rn((double)swt, __dmul_rn((double)c, b)) : __dsub_rn(__dmul_rn((double)c, b), (double)swt);
+        }
+        hint = (float)integ;
     } else {
-        double sbest = -DBL_MAX;
+        double sbest = -DBL_MAX, acc = 0.0;
         int ibest = INT_MAX;
         for (int i = a0 + lane; i < a1; i += 32) {
-            double x = (i < r.len) ? (double)pool[r.off + i] : 0.0;
+            double x = (i < r.len) ? (double)src.at(r.mis + i) : 0.0;
             double sig = positive ? __dsub_rn(x, b) : __dsub_rn(b, x);
             if (sig > sbest) { sbest = sig; ibest = i; }
             acc += fmax(sig, 0.0);
         }
         double smax = warp_max_f64(sbest);
-        h.p = __reduce_min_sync(kFull, sbest == smax ? ibest : INT_MAX);
-        h.height = (float)smax;
+        hp = __reduce_min_sync(kFull, sbest == smax ? ibest : INT_MAX);
+        hheight = (float)smax;
+        hint = (float)warp_sum_f64(acc);
     }
-    h.integral = (float)warp_sum_f64(acc);
-    sink.store(h, r, a);
+    sink.store(hp, s, e, hheight, hint);
 }
 
-// ---- one record: features + threshold-run detection -----------------------------------------
 struct FeatAcc {
     float height, amp, area, mad;
 };
 
-template <typename T, bool FEAT, bool HITS, typename Sink>
-__device__ void scan_record(const T* __restrict__ pool, const RecInfo& r, const FHArgs& a, Sink& sink, FeatAcc& fa) {
+__device__ __forceinline__ unsigned umin16x2(unsigned a, unsigned b) { return __vminu2(a, b); }
+__device__ __forceinline__ unsigned umax16x2(unsigned a, unsigned b) { return __vmaxu2(a, b); }
+
+// ---- one record: features + threshold-run detection -----------------------------------------
+template <typename T, bool FEAT, bool HITS, typename Src, typename Sink>
+__device__ __forceinline__ void scan_record(const Src& src, const ScanRec& r, const FHArgs& a, Sink& sink, FeatAcc& fa) {
     constexpr bool U16 = sizeof(T) == 2;
-    constexpr int AL = U16 ? 8 : 4;  // samples per 16 bytes
     const int lane = lane_id();
     const int len = r.len;
-    const int mis = (int)(r.off & (AL - 1));
-    const long long abase = r.off - mis;
-    const int vtotal = mis + max(len, 0);
+    const int mis = r.mis;
+    const int vtotal = mis + len;
     const bool positive = r.pol == WFB_POL_POSITIVE;
     const bool known = r.pol != WFB_POL_UNKNOWN;
-
-    int p0 = 0, p1 = 0, c0 = 0, c1 = 0;
-    if (FEAT) {
-        resolve_slice(a.p.height_start, a.p.height_end, max(len, 0), p0, p1);
-        resolve_slice(a.p.area_start, a.p.area_end, max(len, 0), c0, c1);
-    }
-    // hit threshold
-    int kmax = -1;
-    int xormask = 0;
-    if (HITS && U16) {
-        kmax = integer_threshold_u16(r.b_rec, r.thr, positive);
-        xormask = positive ? 0xffff : 0;
-    }
+    const int p0 = r.p0, p1 = r.p1, c0 = r.c0, c1 = r.c1;
+    const int kmax = r.kmax;
+    const unsigned xm = (HITS && U16 && positive) ? 0xffffffffu : 0u;
     const float b32 = (float)r.b_feat;
-
-    // accumulators
-    int imin = INT_MAX, imax = INT_MIN;            // u16: min/max over height range
-    float fmin_ = FLT_MAX, fmax_ = -FLT_MAX;       // f32 pool (raw) or known-polarity signal
-    unsigned long long isum = 0;                   // u16 unknown polarity: sum over area range
-    double dsum = 0.0;                             // everything else
+    // u16 fast path accumulators (packed 16x2)
+    unsigned pmin = 0xffffffffu, pmax = 0u, pdiff = 0u, isum32 = 0;
+    // generic accumulators
+    int imin = INT_MAX, imax = INT_MIN;
+    float fmin_ = FLT_MAX, fmax_ = -FLT_MAX;
+    unsigned long long isum = 0;
+    double dsum = 0.0;
     int idiff = 0;
     double ddiff = 0.0;
-    T carry_last = T(0);
+    unsigned carry_w = 0;  // last 32-bit word of the previous window (u16: 2 samples, f32: 1 sample)
     bool open = false;
     int run_start = 0;
 
@@ -302,83 +341,154 @@ __device__ void scan_record(const T* __restrict__ pool, const RecInfo& r, const 
         const int v0 = vb + lane * 8;
         const int lo = min(max(mis - v0, 0), 8);
         const int hi = min(max(vtotal - v0, 0), 8);
-        const int i0 = v0 - mis;  // record index of c.v[0]
-        Chunk<T> c;
-        load_chunk(pool, a.pool_len, abase + v0, lo, hi, c);
+        const int i0 = v0 - mis;  // record index of sample 0 of this lane's chunk
+        uint4 q0 = make_uint4(0, 0, 0, 0), q1 = make_uint4(0, 0, 0, 0);
+        if (hi > lo) {
+            q0 = src.load16(v0);
+            if (!U16) q1 = src.load16(v0 + 4);
+        }
+        const unsigned lastw = U16 ? q0.w : q1.w;
+        unsigned prevw = __shfl_up_sync(kFull, lastw, 1);
+        if (lane == 0) prevw = carry_w;
+        carry_w = __shfl_sync(kFull, lastw, 31);
+        unsigned m8 = 0;
 
-        if (FEAT) {
-            // ---- max |diff| over the whole record (basic_features.py:187-189)
-            T prev = __shfl_up_sync(kFull, c.v[7], 1);
-            if (lane == 0) prev = carry_last;
-            carry_last = __shfl_sync(kFull, c.v[7], 31);
-            if (hi > lo) {
+        if (U16 && hi - lo == 8) {
+            // ---------------- fast path: 8 valid uint16 samples in q0 ------------------------
+            if (FEAT) {
+                // |diff| against the previous sample, packed: max - min per halfword; the first
+                // sample of the record has no predecessor (pair it with itself)
+                unsigned pw = (i0 > 0) ? prevw : (q0.x << 16);
+                unsigned f0 = __funnelshift_r(pw, q0.x, 16), f1 = __funnelshift_r(q0.x, q0.y, 16);
+                unsigned f2 = __funnelshift_r(q0.y, q0.z, 16), f3 = __funnelshift_r(q0.z, q0.w, 16);
+                unsigned d0 = umax16x2(q0.x, f0) - umin16x2(q0.x, f0), d1 = umax16x2(q0.y, f1) - umin16x2(q0.y, f1);
+                unsigned d2 = umax16x2(q0.z, f2) - umin16x2(q0.z, f2), d3 = umax16x2(q0.w, f3) - umin16x2(q0.w, f3);
+                pdiff = umax16x2(pdiff, umax16x2(umax16x2(d0, d1), umax16x2(d2, d3)));
+                // height range
+                const int jlo = max(0, p0 - i0), jhi = min(8, p1 - i0);
+                if (jhi > jlo) {
+                    if (jlo == 0 && jhi == 8) {
+                        pmin = umin16x2(pmin, umin16x2(umin16x2(q0.x, q0.y), umin16x2(q0.z, q0.w)));
+                        pmax = umax16x2(pmax, umax16x2(umax16x2(q0.x, q0.y), umax16x2(q0.z, q0.w)));
+                    } else {
+                        const unsigned ww[4] = {q0.x, q0.y, q0.z, q0.w};
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            int w = (int)((ww[j >> 1] >> ((j & 1) * 16)) & 0xffffu);
+                            if (j >= jlo && j < jhi) { imin = min(imin, w); imax = max(imax, w); }
+                        }
+                    }
+                }
+                // area range
+                const int klo = max(0, c0 - i0), khi = min(8, c1 - i0);
+                if (khi > klo) {
+                    if (klo == 0 && khi == 8 && !known) {
+                        unsigned s = __dp2a_lo(q0.x, 0x0101u, isum32);
+                        s = __dp2a_lo(q0.y, 0x0101u, s);
+                        s = __dp2a_lo(q0.z, 0x0101u, s);
+                        isum32 = __dp2a_lo(q0.w, 0x0101u, s);
+                    } else {
+                        const unsigned ww[4] = {q0.x, q0.y, q0.z, q0.w};
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            unsigned w = (ww[j >> 1] >> ((j & 1) * 16)) & 0xffffu;
+                            if (j >= klo && j < khi) {
+                                if (!known) {
+                                    isum += w;
+                                } else {
+                                    float sv = positive ? __fsub_rn((float)w, b32) : __fsub_rn(b32, (float)w);
+                                    dsum += (double)sv;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            if (HITS) {
+                unsigned k0 = q0.x ^ xm, k1 = q0.y ^ xm, k2 = q0.z ^ xm, k3 = q0.w ^ xm;
+                unsigned mn = umin16x2(umin16x2(k0, k1), umin16x2(k2, k3));
+                int lmin = (int)min(mn & 0xffffu, mn >> 16);
+                if (lmin <= kmax) {
+                    const unsigned kk[4] = {k0, k1, k2, k3};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        int kv = (int)((kk[j >> 1] >> ((j & 1) * 16)) & 0xffffu);
+                        m8 |= (kv <= kmax ? 1u : 0u) << j;
+                    }
+                }
+            }
+        } else if (hi > lo) {
+            // ---------------- generic path: partial chunks and the float32 pool ---------------
+            T c[8];
+            if (U16) {
+                const unsigned ww[4] = {q0.x, q0.y, q0.z, q0.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) c[j] = (T)((ww[j >> 1] >> ((j & 1) * 16)) & 0xffffu);
+            } else {
+                const unsigned ww[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) c[j] = (T)__uint_as_float(ww[j]);
+            }
+            const T prev = U16 ? (T)(prevw >> 16) : (T)__uint_as_float(prevw);
+            if (FEAT) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    T pj = (j == 0) ? prev : c.v[j - 1];
+                    T pj = (j == 0) ? prev : c[j - 1];
                     bool ok = (j >= lo) && (j < hi) && (i0 + j > 0);
                     if (U16) {
-                        int d = abs((int)c.v[j] - (int)pj);
+                        int d = abs((int)c[j] - (int)pj);
                         if (ok) idiff = max(idiff, d);
                     } else {
-                        double d = fabs((double)c.v[j] - (double)pj);
+                        double d = fabs((double)c[j] - (double)pj);
                         if (ok) ddiff = fmax(ddiff, d);
                     }
                 }
-                // ---- height range [p0, p1)
                 int jlo = max(lo, p0 - i0), jhi = min(hi, p1 - i0);
                 if (jhi > jlo) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         if (j >= jlo && j < jhi) {
                             if (U16) {
-                                imin = min(imin, (int)c.v[j]);
-                                imax = max(imax, (int)c.v[j]);
+                                imin = min(imin, (int)c[j]);
+                                imax = max(imax, (int)c[j]);
                             } else if (!known) {
-                                fmin_ = fminf(fmin_, (float)c.v[j]);
-                                fmax_ = fmaxf(fmax_, (float)c.v[j]);
+                                fmin_ = fminf(fmin_, (float)c[j]);
+                                fmax_ = fmaxf(fmax_, (float)c[j]);
                             } else {
                                 // -signals(): negative -> b32 - x, positive -> x - b32 (float32)
-                                float sv = positive ? __fsub_rn((float)c.v[j], b32) : __fsub_rn(b32, (float)c.v[j]);
+                                float sv = positive ? __fsub_rn((float)c[j], b32) : __fsub_rn(b32, (float)c[j]);
                                 fmin_ = fminf(fmin_, sv);
                                 fmax_ = fmaxf(fmax_, sv);
                             }
                         }
                     }
                 }
-                // ---- area range [c0, c1)
                 jlo = max(lo, c0 - i0);
                 jhi = min(hi, c1 - i0);
                 if (jhi > jlo) {
-                    if (U16 && !known) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            if (j >= jlo && j < jhi) isum += (unsigned)c.v[j];
-                    } else if (!known) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            if (j >= jlo && j < jhi) dsum += __dsub_rn(r.b_feat, (double)c.v[j]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            if (j >= jlo && j < jhi) {
-                                float sv = positive ? __fsub_rn((float)c.v[j], b32) : __fsub_rn(b32, (float)c.v[j]);
+                    for (int j = 0; j < 8; ++j) {
+                        if (j >= jlo && j < jhi) {
+                            if (U16 && !known) {
+                                isum += (unsigned)c[j];
+                            } else if (!known) {
+                                dsum += __dsub_rn(r.b_feat, (double)c[j]);
+                            } else {
+                                float sv = positive ? __fsub_rn((float)c[j], b32) : __fsub_rn(b32, (float)c[j]);
                                 dsum += (double)sv;
                             }
+                        }
                     }
                 }
             }
-        }
-
-        if (HITS) {
-            unsigned m8 = 0;
-            if (hi > lo) {
+            if (HITS) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     bool bit;
                     if (U16) {
-                        bit = (((int)c.v[j]) ^ xormask) <= kmax;
+                        bit = (int)(((unsigned)c[j]) ^ (xm & 0xffffu)) <= kmax;
                     } else {
-                        double x = (double)c.v[j];
+                        double x = (double)c[j];
                         double sig = positive ? __dsub_rn(x, r.b_rec) : __dsub_rn(r.b_rec, x);
                         bit = sig >= r.thr;
                     }
@@ -386,14 +496,17 @@ __device__ void scan_record(const T* __restrict__ pool, const RecInfo& r, const 
                     m8 |= (bit ? 1u : 0u) << j;
                 }
             }
+        }
+
+        if (HITS) {
             unsigned anyb = __ballot_sync(kFull, m8 != 0);
             if (anyb == 0 && !open) continue;
             // 32-bit mask word shared by each group of 4 lanes: samples [vb + 32q, vb + 32q + 32)
             const int g = lane & ~3;
             unsigned m32 = __shfl_sync(kFull, m8, g) | (__shfl_sync(kFull, m8, g + 1) << 8) |
                            (__shfl_sync(kFull, m8, g + 2) << 16) | (__shfl_sync(kFull, m8, g + 3) << 24);
-            unsigned prevw = __shfl_up_sync(kFull, m32, 4);
-            unsigned pbit = (lane < 4) ? (open ? 1u : 0u) : (prevw >> 31);
+            unsigned prevm = __shfl_up_sync(kFull, m32, 4);
+            unsigned pbit = (lane < 4) ? (open ? 1u : 0u) : (prevm >> 31);
             unsigned tr = m32 ^ ((m32 << 1) | pbit);  // set where the mask flips
             unsigned tb = __ballot_sync(kFull, tr != 0 && (lane & 3) == 0);
             while (tb) {
@@ -406,24 +519,27 @@ __device__ void scan_record(const T* __restrict__ pool, const RecInfo& r, const 
                     run_start = pos;
                 } else {
                     open = false;
-                    emit_hit<T>(pool, r, a, run_start, pos, sink);
+                    emit_hit<T>(src, r, a, run_start, pos, sink);
                 }
                 if ((lane >> 2) == (ql >> 2)) tr &= tr - 1;
                 tb = __ballot_sync(kFull, tr != 0 && (lane & 3) == 0);
             }
         }
     }
-    if (HITS && open) emit_hit<T>(pool, r, a, run_start, max(len, 0), sink);
+    if (HITS && open) emit_hit<T>(src, r, a, run_start, len, sink);
 
     if (FEAT) {
         fa.height = fa.amp = fa.area = fa.mad = 0.f;
         if (U16) {
-            fa.mad = (float)__reduce_max_sync(kFull, idiff);
+            int d = max(idiff, (int)max(pdiff & 0xffffu, pdiff >> 16));
+            fa.mad = (float)__reduce_max_sync(kFull, d);
         } else {
             fa.mad = (float)warp_max_f64(ddiff);
         }
         if (p1 > p0) {
             if (U16) {
+                imin = min(imin, (int)min(pmin & 0xffffu, pmin >> 16));
+                imax = max(imax, (int)max(pmax & 0xffffu, pmax >> 16));
                 int wmin = __reduce_min_sync(kFull, imin);
                 int wmax = __reduce_max_sync(kFull, imax);
                 if (!known) {
@@ -449,7 +565,7 @@ __device__ void scan_record(const T* __restrict__ pool, const RecInfo& r, const 
         if (c1 > c0) {
             if (U16 && !known) {
                 // sum(b - w) = n*floor(b) - sum(w) (exact integer) + n*frac(b)
-                long long sw = warp_sum_i64((long long)isum);
+                long long sw = (long long)__reduce_add_sync(kFull, isum32) + warp_sum_i64((long long)isum);
                 double b = r.b_feat;
                 long long nC = c1 - c0;
                 double area;
@@ -469,104 +585,201 @@ __device__ void scan_record(const T* __restrict__ pool, const RecInfo& r, const 
     }
 }
 
-// ---- per-channel rule lookup ------------------------------------------------------------------
-__device__ __forceinline__ void apply_rules(const FHArgs& a, RecInfo& r) {
-    r.thr = a.p.threshold;
-    r.b_feat = r.b_rec;
-    const wfb_chan_rule* rules = a.p.rules_dev;
-    for (int i = 0; i < a.p.n_rules; ++i) {
-        if (rules[i].board == r.board && rules[i].channel == r.channel) {
-            if (rules[i].has_threshold) r.thr = rules[i].threshold;
-            if (rules[i].has_fixed_baseline) r.b_feat = rules[i].fixed_baseline;
-        }
-    }
-}
-
-__device__ __forceinline__ bool load_rec(const FHArgs& a, long long rec, RecInfo& r) {
-    const wfb_rec_meta* m = a.meta + rec;
-    const uint4* q = reinterpret_cast<const uint4*>(m);
-    uint4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
-    r.ts = (long long)(((unsigned long long)q0.y << 32) | q0.x);
-    r.b_rec = __hiloint2double((int)q0.w, (int)q0.z);
-    r.off = (long long)(((unsigned long long)q1.y << 32) | q1.x) - a.p.pool_base;
-    r.len = (int)q1.z;
-    r.dt = (int)q1.w;
-    r.board = (int)(short)(q2.x & 0xffff);
-    r.channel = (int)(short)(q2.x >> 16);
-    r.pol = (int)(q2.y & 0xff);
-    r.rid = (long long)(((unsigned long long)q2.w << 32) | q2.z);
-    apply_rules(a, r);
-    bool ok = r.len <= 0 || (r.off >= 0 && r.off + r.len <= a.pool_len);
-    if (!ok) {
-        if (lane_id() == 0) atomicExch(a.err_flag, 1);
-        r.len = 0;
-    }
-    return ok;
+__device__ __forceinline__ double bcast_f64(double v, int src) { return shfl_f64(v, src); }
+__device__ __forceinline__ long long bcast_i64(long long v, int src) {
+    int lo = __shfl_sync(kFull, (int)(v & 0xffffffffll), src);
+    int hi = __shfl_sync(kFull, (int)(v >> 32), src);
+    return ((long long)hi << 32) | (unsigned)lo;
 }
 
 // ---- the kernel --------------------------------------------------------------------------------
-template <typename T, bool FEAT, bool HITS>
+template <typename T, bool STAGED, bool FEAT, bool HITS>
 __global__ void __launch_bounds__(kWarps * 32) fused_features_hits_kernel(const FHArgs a) {
-    __shared__ HitEnt s_ent[kWarps][kEntPerWarp];
-    __shared__ int s_cnt[kTile];
-    __shared__ long long s_off[kTile];  // absolute output row of each record's first hit
+    constexpr bool U16 = sizeof(T) == 2;
+    constexpr int AL = U16 ? 8 : 4;
+    extern __shared__ __align__(16) uint8_t dyn_smem[];  // per warp: ring_bytes (slot ring / row buffer)
+    __shared__ HitEnt s_ent[HITS ? kWarps : 1][HITS ? kEntPerWarp : 1];
+    __shared__ long long s_wtot[kWarps];
+    __shared__ long long s_wbase[kWarps];
     __shared__ int s_tile;
+    __shared__ __align__(8) unsigned long long s_bar[kWarps * kSlots];
 
     const int warp = threadIdx.x >> 5, lane = lane_id();
     const T* pool = static_cast<const T*>(a.pool);
+    uint8_t* ring = dyn_smem + (size_t)warp * a.ring_bytes;
+    unsigned long long* bars = &s_bar[warp * kSlots];
+    if (STAGED) {
+        if (lane < kSlots) mbar_init(&bars[lane], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    unsigned phase_bits = 0;  // parity to wait for next, per slot
 
     for (;;) {
         if (threadIdx.x == 0) s_tile = (int)atomicAdd(a.ticket, 1u);
         __syncthreads();
         const int tile = s_tile;
         if (tile >= a.n_tiles) break;
-        const long long rec0 = (long long)tile * kTile + warp * kRecPerWarp;
 
-        // ---------------- phase A: scan my records, stage hits, write features
-        int used = 0;              // staged entries of this warp
-        int cnt[kRecPerWarp];
-        int ent0[kRecPerWarp];     // first staged entry of record k, or -1 if it did not fit
-#pragma unroll
-        for (int k = 0; k < kRecPerWarp; ++k) {
-            cnt[k] = 0;
-            ent0[k] = 0;
-            long long rec = rec0 + k;
-            if (rec < a.n) {
-                RecInfo r;
-                load_rec(a, rec, r);
-                StageSink sink{&s_ent[warp][used], kEntPerWarp - used, 0};
-                FeatAcc fa;
-                scan_record<T, FEAT, HITS, StageSink>(pool, r, a, sink, fa);
-                if (FEAT) write_feature_row(a.feat_out, rec, r, fa.height, fa.amp, fa.area, fa.mad, a.p.row_base + rec);
-                if (HITS) {
-                    cnt[k] = sink.n;
-                    if (sink.n <= kEntPerWarp - used) {
-                        ent0[k] = used;
-                        used += sink.n;
-                    } else {
-                        ent0[k] = -1;
-                    }
-                    if (a.hit_counts != nullptr && lane == 0) a.hit_counts[rec] = sink.n;
+        // ---------------- per-lane bookkeeping of record `lane` of this warp
+        const long long rec = (long long)tile * kTile + warp * 32 + lane;
+        const bool have = rec < a.n;
+        long long off = 0, ts = 0, rid = 0;
+        int len = 0, dt = 1, pol = 0;
+        unsigned bc = 0;
+        double b_rec = 0.0, b_feat = 0.0, thr = a.p.threshold;
+        if (have) {
+            const uint4* q = reinterpret_cast<const uint4*>(a.meta + rec);
+            uint4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+            ts = (long long)(((unsigned long long)q0.y << 32) | q0.x);
+            b_rec = __hiloint2double((int)q0.w, (int)q0.z);
+            off = (long long)(((unsigned long long)q1.y << 32) | q1.x) - a.p.pool_base;
+            len = (int)q1.z;
+            dt = (int)q1.w;
+            bc = q2.x;
+            pol = (int)(q2.y & 0xff);
+            rid = (long long)(((unsigned long long)q2.w << 32) | q2.z);
+            b_feat = b_rec;
+            const int board = (int)(short)(bc & 0xffff), channel = (int)(short)(bc >> 16);
+            for (int i = 0; i < a.p.n_rules; ++i) {
+                const wfb_chan_rule rule = a.p.rules_dev[i];
+                if (rule.board == board && rule.channel == channel) {
+                    if (rule.has_threshold) thr = rule.threshold;
+                    if (rule.has_fixed_baseline) b_feat = rule.fixed_baseline;
                 }
             }
-            if (HITS && lane == 0) s_cnt[warp * kRecPerWarp + k] = cnt[k];
+            if (len < 0) len = 0;
+            if (len > 0 && (off < 0 || off + len > a.pool_len)) {
+                atomicExch(a.err_flag, 1);  // records reference samples outside the pool
+                len = 0;
+            }
+        }
+        const int mis = (int)(off & (AL - 1));
+        int p0 = 0, p1 = 0, c0 = 0, c1 = 0;
+        if (FEAT) {
+            resolve_slice(a.p.height_start, a.p.height_end, len, p0, p1);
+            resolve_slice(a.p.area_start, a.p.area_end, len, c0, c1);
+        }
+        int kmax = -1;
+        if (HITS && U16 && len > 0) kmax = integer_threshold_u16(b_rec, thr, pol == WFB_POL_POSITIVE);
+        unsigned copy_bytes = 0;
+        if (STAGED && len > 0) {
+            copy_bytes = (unsigned)((((long long)mis + len + AL - 1) & ~(long long)(AL - 1)) * (long long)sizeof(T));
+            if ((int)copy_bytes > a.slot_bytes) {
+                atomicExch(a.err_flag, 2);  // lmax passed by the caller is too small
+                copy_bytes = 0;
+                len = 0;
+            }
+        }
+        auto issue = [&](int slot) {  // called by the lane that owns the record
+            if (copy_bytes) {
+                mbar_arrive_expect_tx(&bars[slot], copy_bytes);
+                tma_bulk_g2s(ring + (size_t)slot * a.slot_bytes, pool + (off - mis), copy_bytes, &bars[slot]);
+            } else {
+                mbar_arrive(&bars[slot]);
+            }
+        };
+        if (STAGED) {
+            fence_proxy_async();  // generic-proxy accesses of the ring (previous tile) before the refill
+            if (lane < kSlots - 1) issue(lane);
+        }
+
+        // ---------------- phase A: the warp scans its 32 records one after the other
+        FeatAcc my_fa = {0.f, 0.f, 0.f, 0.f};
+        int my_cnt = 0, my_ent0 = 0;
+        int used = 0;
+        unsigned ovf_mask = 0;
+        const int nrec = (int)max((long long)0, min((long long)32, a.n - ((long long)tile * kTile + warp * 32)));
+        for (int j = 0; j < nrec; ++j) {
+            ScanRec r;
+            r.mis = __shfl_sync(kFull, mis, j);
+            r.len = __shfl_sync(kFull, len, j);
+            r.pol = __shfl_sync(kFull, pol, j);
+            r.b_rec = bcast_f64(b_rec, j);
+            r.b_feat = FEAT ? bcast_f64(b_feat, j) : 0.0;
+            r.thr = (HITS && !U16) ? bcast_f64(thr, j) : 0.0;
+            r.kmax = (HITS && U16) ? __shfl_sync(kFull, kmax, j) : -1;
+            r.p0 = FEAT ? __shfl_sync(kFull, p0, j) : 0;
+            r.p1 = FEAT ? __shfl_sync(kFull, p1, j) : 0;
+            r.c0 = FEAT ? __shfl_sync(kFull, c0, j) : 0;
+            r.c1 = FEAT ? __shfl_sync(kFull, c1, j) : 0;
+            StageSink sink{HITS ? &s_ent[warp][used] : nullptr, kEntPerWarp - used, 0, (unsigned)j};
+            FeatAcc fa = {0.f, 0.f, 0.f, 0.f};
+            if (STAGED) {
+                const int slot = j % kSlots;
+                // prefetch record j + kSlots - 1 into the slot record j - 1 just left
+                const int jn = j + kSlots - 1;
+                if (jn < 32) {
+                    __syncwarp();
+                    if (lane == jn) {
+                        fence_proxy_async();
+                        issue(jn % kSlots);
+                    }
+                }
+                mbar_wait(&bars[slot], (phase_bits >> slot) & 1u);
+                phase_bits ^= 1u << slot;
+                SmemSrc<T> src{reinterpret_cast<const T*>(ring + (size_t)slot * a.slot_bytes)};
+                scan_record<T, FEAT, HITS>(src, r, a, sink, fa);
+            } else {
+                const long long offj = bcast_i64(off, j);
+                GlobalSrc<T> src{pool + (offj - r.mis), a.pool_len - (offj - r.mis)};
+                scan_record<T, FEAT, HITS>(src, r, a, sink, fa);
+            }
+            if (lane == j) {
+                my_fa = fa;
+                my_cnt = sink.n;
+                my_ent0 = used;
+            }
+            if (HITS) {
+                if (sink.n <= kEntPerWarp - used) used += sink.n;
+                else ovf_mask |= 1u << j;
+            }
+        }
+        if (STAGED) {
+            // drain the barriers of slots armed for records >= nrec (tail tile) so phases stay in step
+            for (int j = nrec; j < min(32, nrec + kSlots - 1); ++j) {
+                const int slot = j % kSlots;
+                mbar_wait(&bars[slot], (phase_bits >> slot) & 1u);
+                phase_bits ^= 1u << slot;
+            }
+        }
+        if (FEAT && have) {
+            unsigned* dst = reinterpret_cast<unsigned*>(a.feat_out + rec * kFeatRowBytes);
+            const long long ev = a.p.row_base + rec;
+            dst[0] = __float_as_uint(my_fa.height);
+            dst[1] = __float_as_uint(my_fa.amp);
+            dst[2] = __float_as_uint(my_fa.area);
+            dst[3] = __float_as_uint(my_fa.mad);
+            dst[4] = (unsigned)(ts & 0xffffffffll);
+            dst[5] = (unsigned)((unsigned long long)ts >> 32);
+            dst[6] = bc;
+            dst[7] = (unsigned)(ev & 0xffffffffll);
+            dst[8] = (unsigned)((unsigned long long)ev >> 32);
         }
         if (!HITS) {
             __syncthreads();  // s_tile reuse
             continue;
         }
-        __syncthreads();
+        if (a.hit_counts != nullptr && have) a.hit_counts[rec] = my_cnt;
 
-        // ---------------- tile scan + decoupled look-back (warp 0)
-        if (warp == 0) {
-            int c = s_cnt[lane];  // kTile == 32
-            int incl = c;
+        // ---------------- warp scan of the per-record counts, tile scan, decoupled look-back
+        int incl = my_cnt;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                int t = __shfl_up_sync(kFull, incl, d);
-                if (lane >= d) incl += t;
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(kFull, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) s_wtot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            long long c = (lane < kWarps) ? s_wtot[lane] : 0;
+            long long wincl = c;
+#pragma unroll
+            for (int d = 1; d < kWarps; d <<= 1) {
+                long long t = bcast_i64(wincl, max(lane - d, 0));
+                if (lane >= d) wincl += t;
             }
-            const long long total = __shfl_sync(kFull, incl, 31);
+            const long long total = bcast_i64(wincl, kWarps - 1);
             if (lane == 0) st_state(a.tile_state + tile, kStAgg | (unsigned long long)total);
             long long excl = 0;
             int look = tile - 1;
@@ -589,34 +802,75 @@ __global__ void __launch_bounds__(kWarps * 32) fused_features_hits_kernel(const 
                 st_state(a.tile_state + tile, kStPrefix | (unsigned long long)(excl + total));
                 if (tile == a.n_tiles - 1) *a.total_out = excl + total;
             }
-            s_off[lane] = excl + (incl - c);
+            if (lane < kWarps) s_wbase[lane] = excl + (wincl - c);
         }
         __syncthreads();
 
-        // ---------------- phase B: write my records' rows at their final position
+        // ---------------- phase B: one staged hit per lane -> packed rows -> coalesced stores
+        const long long my_row0 = s_wbase[warp] + (incl - my_cnt);  // first output row of record `lane`
+        unsigned* rowbuf = reinterpret_cast<unsigned*>(ring);
+        for (int e0 = 0; e0 < used; e0 += 32) {
+            const int e = e0 + lane;
+            const bool act = e < used;
+            HitEnt h = s_ent[warp][act ? e : 0];
+            const int owner = (int)(h.e_rec >> 27);
+            RowRec rr;
+            rr.ts = bcast_i64(ts, owner);
+            rr.rid = bcast_i64(rid, owner);
+            rr.len = __shfl_sync(kFull, len, owner);
+            rr.dt = __shfl_sync(kFull, dt, owner);
+            rr.bc = __shfl_sync(kFull, bc, owner);
+            const long long row = bcast_i64(my_row0, owner) + (e - __shfl_sync(kFull, my_ent0, owner));
+            unsigned w[15];
+            hit_row_words(w, h.p, h.s, (int)(h.e_rec & 0x7ffffffu), h.height, h.integral, rr, a.p.left_extension,
+                          a.p.right_extension, a.lmax);
+            __syncwarp();
+            if (act) {
 #pragma unroll
-        for (int k = 0; k < kRecPerWarp; ++k) {
-            long long rec = rec0 + k;
-            if (rec >= a.n || cnt[k] == 0) continue;
-            const long long row0 = s_off[warp * kRecPerWarp + k];
-            RecInfo r;
-            load_rec(a, rec, r);
-            if (ent0[k] >= 0) {
-                const HitEnt* ents = &s_ent[warp][ent0[k]];
-                for (int idx = lane; idx < cnt[k] * 15; idx += 32) {
-                    int hrow = idx / 15, word = idx - hrow * 15;
-                    long long row = row0 + hrow;
-                    if (row < a.hit_cap)
-                        reinterpret_cast<unsigned*>(a.hit_out + row * kHitRowBytes)[word] =
-                            hit_row_word(word, ents[hrow], r, a.p.left_extension, a.p.right_extension, a.lmax);
-                }
-            } else {
-                RowSink sink{row0, 0};
-                FeatAcc fa;
-                scan_record<T, false, true, RowSink>(pool, r, a, sink, fa);
+                for (int k = 0; k < 15; ++k) rowbuf[lane * 17 + k] = w[k];
+                rowbuf[lane * 17 + 15] = (unsigned)(row & 0xffffffffll);
+                rowbuf[lane * 17 + 16] = (unsigned)((unsigned long long)row >> 32);
+            }
+            __syncwarp();
+            const int nrow = min(32, used - e0);
+            for (int k = lane; k < nrow * 15; k += 32) {
+                const int hr = k / 15, word = k - hr * 15;
+                const long long grow = (long long)(((unsigned long long)rowbuf[hr * 17 + 16] << 32) | rowbuf[hr * 17 + 15]);
+                if (grow < a.hit_cap) reinterpret_cast<unsigned*>(a.hit_out + grow * kHitRowBytes)[word] = rowbuf[hr * 17 + word];
             }
         }
-        __syncthreads();  // staging buffers and s_tile are reused by the next tile
+        // records whose hits did not fit the staging area: scan them again, rows go straight out
+        while (ovf_mask) {
+            const int j = __ffs(ovf_mask) - 1;
+            ovf_mask &= ovf_mask - 1;
+            ScanRec r;
+            r.mis = __shfl_sync(kFull, mis, j);
+            r.len = __shfl_sync(kFull, len, j);
+            r.pol = __shfl_sync(kFull, pol, j);
+            r.b_rec = bcast_f64(b_rec, j);
+            r.b_feat = 0.0;
+            r.thr = bcast_f64(thr, j);
+            r.kmax = __shfl_sync(kFull, kmax, j);
+            r.p0 = r.p1 = r.c0 = r.c1 = 0;
+            RowSink sink;
+            sink.out = a.hit_out;
+            sink.row = bcast_i64(my_row0, j);
+            sink.cap = a.hit_cap;
+            sink.r.ts = bcast_i64(ts, j);
+            sink.r.rid = bcast_i64(rid, j);
+            sink.r.len = r.len;
+            sink.r.dt = __shfl_sync(kFull, dt, j);
+            sink.r.bc = __shfl_sync(kFull, bc, j);
+            sink.left = a.p.left_extension;
+            sink.right = a.p.right_extension;
+            sink.lmax = a.lmax;
+            sink.n = 0;
+            const long long offj = bcast_i64(off, j);
+            GlobalSrc<T> src{pool + (offj - r.mis), a.pool_len - (offj - r.mis)};
+            FeatAcc fa;
+            scan_record<T, false, true>(src, r, a, sink, fa);
+        }
+        __syncthreads();  // staging buffers, ring and s_tile are reused by the next tile
     }
 }
 
@@ -643,6 +897,44 @@ static WsLayout ws_layout(long long n) {
     return w;
 }
 
+template <typename T, bool STAGED>
+static int launch_variant(FHArgs a, int flags, cudaStream_t st) {
+    const bool f = flags & WFB_DO_FEATURES, h = flags & WFB_DO_HITS;
+    const size_t dyn = (size_t)kWarps * a.ring_bytes;
+    a.n_tiles = (int)((a.n + kTile - 1) / kTile);
+    auto go = [&](auto kern) -> int {
+        // static (staged hits) + dynamic (slot rings) shared memory exceeds the 48 KB default: opt in
+        WFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        int per_sm = 0;
+        WFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWarps * 32, dyn));
+        if (per_sm < 1) per_sm = 1;
+        int grid = (int)std::min<long long>((long long)sm_count() * per_sm, a.n_tiles);
+        kern<<<grid, kWarps * 32, dyn, st>>>(a);
+        WFB_CUDA(cudaGetLastError());
+        return WFB_OK;
+    };
+    if (f && h) return go(fused_features_hits_kernel<T, STAGED, true, true>);
+    if (f) return go(fused_features_hits_kernel<T, STAGED, true, false>);
+    return go(fused_features_hits_kernel<T, STAGED, false, true>);
+}
+
+template <typename T>
+static int launch_fused(FHArgs a, int flags, cudaStream_t st) {
+    // shared-memory slot: the record rounded out to 16-byte boundaries on both sides
+    const long long slot = (((long long)a.lmax * (long long)sizeof(T) + 15) & ~15ll) + 16;
+    const char* force = getenv("WFB_FUSED_VARIANT");  // diagnostics: "global" | "staged"
+    const bool want_global = force && !strcmp(force, "global");
+    // three resident blocks per SM need <= ~64 KB each (ring + 20 KB of staged hits)
+    if (!want_global && slot * kSlots * kWarps <= 150 * 1024 && a.lmax < (1 << 27)) {
+        a.slot_bytes = (int)slot;
+        a.ring_bytes = (int)std::max<long long>(slot * kSlots, kRowBufBytes);
+        return launch_variant<T, true>(a, flags, st);
+    }
+    a.slot_bytes = 0;
+    a.ring_bytes = kRowBufBytes;
+    return launch_variant<T, false>(a, flags, st);
+}
+
 }  // namespace wfb
 
 using namespace wfb;
@@ -650,14 +942,6 @@ using namespace wfb;
 extern "C" size_t wfb_features_hits_workspace_bytes(int64_t n) {
     if (n < 0) n = 0;
     return ws_layout(n).total + 64;
-}
-
-template <typename T>
-static void launch_fused(const FHArgs& a, int flags, int grid, cudaStream_t st) {
-    const bool f = flags & WFB_DO_FEATURES, h = flags & WFB_DO_HITS;
-    if (f && h) fused_features_hits_kernel<T, true, true><<<grid, kWarps * 32, 0, st>>>(a);
-    else if (f) fused_features_hits_kernel<T, true, false><<<grid, kWarps * 32, 0, st>>>(a);
-    else fused_features_hits_kernel<T, false, true><<<grid, kWarps * 32, 0, st>>>(a);
 }
 
 extern "C" int wfb_features_hits(const void* pool_dev, int64_t pool_len, const wfb_rec_meta* meta_dev, int64_t n,
@@ -702,40 +986,36 @@ extern "C" int wfb_features_hits(const void* pool_dev, int64_t pool_len, const w
     a.ticket = reinterpret_cast<unsigned*>(ws + w.ticket);
     a.err_flag = reinterpret_cast<int*>(ws + w.err);
     a.tile_state = reinterpret_cast<unsigned long long*>(ws + w.state);
-    a.n_tiles = (int)((n + kTile - 1) / kTile);
+    a.n_tiles = 0;
+    a.slot_bytes = 0;
+    a.ring_bytes = 0;
     a.lmax = params->lmax;
-    if ((flags & WFB_DO_HITS) && a.lmax <= 0) {
-        // padded width = max event_length of the records passed (hit_finder.py:364)
+    if (a.lmax <= 0) {
+        // padded width = max event_length of the records passed (hit_finder.py:364); costs a sync
         int* d_l = reinterpret_cast<int*>(ws + w.lmax);
-        max_len_kernel<<<std::min<long long>(1024, (n + 255) / 256), 256, 0, st>>>(meta_dev, n, d_l);
+        max_len_kernel<<<(unsigned)std::min<long long>(1024, (n + 255) / 256), 256, 0, st>>>(meta_dev, n, d_l);
         int h_l = 0;
         WFB_CUDA(cudaMemcpyAsync(&h_l, d_l, 4, cudaMemcpyDeviceToHost, st));
         WFB_CUDA(cudaStreamSynchronize(st));
         a.lmax = h_l;
     }
-    int blocks_per_sm = 0;
-    if (params->pool_is_f32)
-        WFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fused_features_hits_kernel<float, true, true>, kWarps * 32, 0));
-    else
-        WFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fused_features_hits_kernel<uint16_t, true, true>, kWarps * 32, 0));
-    if (blocks_per_sm < 1) blocks_per_sm = 1;
-    int grid = (int)std::min<long long>((long long)sm_count() * blocks_per_sm, a.n_tiles);
-    if (params->pool_is_f32) launch_fused<float>(a, flags, grid, st);
-    else launch_fused<uint16_t>(a, flags, grid, st);
-    WFB_CUDA(cudaGetLastError());
-    return WFB_OK;
+    if (params->pool_is_f32) return launch_fused<float>(a, flags, st);
+    return launch_fused<uint16_t>(a, flags, st);
 }
 
-// error flag of the last wfb_features_hits call on this workspace (1 = a record pointed outside
-// the pool).  Synchronises the stream.
+// error flag of the last wfb_features_hits call on this workspace.  Synchronises the stream.
 extern "C" int wfb_features_hits_check(void* workspace_dev, void* stream) {
     int flag = 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     WFB_CUDA(cudaMemcpyAsync(&flag, static_cast<uint8_t*>(workspace_dev) + 4, 4, cudaMemcpyDeviceToHost, st));
     WFB_CUDA(cudaStreamSynchronize(st));
-    if (flag) {
+    if (flag == 1) {
         set_error("records reference samples outside wave_pool bounds");
         return WFB_ERR_LAYOUT;
+    }
+    if (flag == 2) {
+        set_error("lmax is smaller than the longest record passed");
+        return WFB_ERR_INVALID;
     }
     return WFB_OK;
 }

@@ -175,6 +175,7 @@ def process_host(
     hit_cap: int | None = None,
     chunk_records: int = 0,
     out_features: np.ndarray | None = None,
+    out_hits: np.ndarray | None = None,
 ) -> dict:
     """Fused pass over host buffers through ``wfb_process_host``.  Returns a dict with
     ``features`` (BASIC_FEATURES_DTYPE), ``hits`` (THRESHOLD_HIT_DTYPE), ``counts`` (int32)."""
@@ -194,10 +195,15 @@ def process_host(
         feat = out_features if out_features is not None else np.empty(n, dtype=BASIC_FEATURES_DTYPE)
     counts = np.empty(n, dtype=np.int32) if (hits and want_counts) else None
     cap = int(hit_cap) if hit_cap is not None else max(1024, 4 * n)
+    if out_hits is not None:
+        cap = len(out_hits)
     hit_rows = None
     n_hits = C.c_int64(0)
     while True:
-        hit_rows = np.empty(cap if hits else 0, dtype=THRESHOLD_HIT_DTYPE)
+        if out_hits is not None and len(out_hits) >= cap:
+            hit_rows = out_hits  # caller-provided (e.g. pinned) output rows
+        else:
+            hit_rows = np.empty(cap if hits else 0, dtype=THRESHOLD_HIT_DTYPE)
         rc = lib.wfb_process_host(_hptr(rec), n, _hptr(pool), len(pool), C.byref(p), _hptr(rules if len(rules) else None),
                                   _hptr(feat), _hptr(hit_rows if hits and cap else None), cap if hits else 0,
                                   _hptr(counts), C.byref(n_hits), int(chunk_records))

@@ -73,6 +73,11 @@ struct ScanRec {
     double b_rec, b_feat, thr;
     int kmax;
     int p0, p1, c0, c1;
+    // uint16 hits: floor(b_rec) / its int value / frac(b_rec), and the integer bound of the samples
+    // on the signal side of the baseline (negative: w <= wlim, positive: w >= wlim)
+    double bi, bf;
+    int wlim;
+    bool b_small;  // |b_rec| < 2e9: the integer split is usable
 };
 // what a hit row needs beyond the staged entry
 struct RowRec {
@@ -255,32 +260,49 @@ __device__ __forceinline__ void emit_hit(const Src& src, const ScanRec& r, const
     float hheight, hint;
     if constexpr (sizeof(T) == 2) {
         // integral = sum(max(sig, 0)) = +-(cnt*b - sum(w)) over the samples on the signal side of b
-        const double bi = floor(b);
-        const int ib = (fabs(b) < 2e9) ? (int)bi : (b > 0 ? INT_MAX : INT_MIN);
-        // negative: w < b  <=>  w <= ceil(b)-1 ; positive: w > b  <=>  w >= floor(b)+1
-        const int wlim = positive ? ib + 1 : ((bi == b) ? ib - 1 : ib);
-        int kbest = INT_MAX, ibest = INT_MAX;
-        unsigned cnt = 0;
-        unsigned long long sw = 0;
-        for (int i = a0 + lane; i < a1; i += 32) {
-            int w = (i < r.len) ? (int)src.at(r.mis + i) : 0;  // padding samples are 0 (records_view.py:189)
-            int kv = positive ? 65535 - w : w;
-            if (kv < kbest) { kbest = kv; ibest = i; }
-            bool in = positive ? (w >= wlim) : (w <= wlim);
-            cnt += in ? 1u : 0u;
-            sw += in ? (unsigned)w : 0u;
+        const int wlim = r.wlim;
+        const int seg = a1 - a0;
+        int kmin, cnt_i;
+        long long swt;
+        if (seg <= 32) {
+            // one sample per lane: argmin-first and (count, sum) each in a single warp reduction
+            const int i = a0 + lane;
+            const bool act = lane < seg;
+            const int w = (act && i < r.len) ? (int)src.at(r.mis + i) : 0;  // padding samples are 0 (records_view.py:189)
+            const int kv = positive ? 65535 - w : w;
+            const unsigned key = act ? (((unsigned)kv << 16) | (unsigned)lane) : 0xffffffffu;
+            const unsigned kred = __reduce_min_sync(kFull, key);
+            kmin = (int)(kred >> 16);
+            hp = a0 + (int)(kred & 0xffffu);
+            const bool in = act && (positive ? (w >= wlim) : (w <= wlim));
+            const unsigned packed = in ? ((1u << 26) | (unsigned)w) : 0u;
+            const unsigned pred = __reduce_add_sync(kFull, packed);
+            cnt_i = (int)(pred >> 26);
+            swt = (long long)(pred & 0x3ffffffu);
+        } else {
+            int kbest = INT_MAX, ibest = INT_MAX;
+            unsigned cnt = 0;
+            unsigned long long sw = 0;
+            for (int i = a0 + lane; i < a1; i += 32) {
+                int w = (i < r.len) ? (int)src.at(r.mis + i) : 0;
+                int kv = positive ? 65535 - w : w;
+                if (kv < kbest) { kbest = kv; ibest = i; }
+                bool in = positive ? (w >= wlim) : (w <= wlim);
+                cnt += in ? 1u : 0u;
+                sw += in ? (unsigned)w : 0u;
+            }
+            kmin = __reduce_min_sync(kFull, kbest);
+            hp = __reduce_min_sync(kFull, kbest == kmin ? ibest : INT_MAX);
+            cnt_i = (int)__reduce_add_sync(kFull, cnt);
+            swt = (seg <= 32768) ? (long long)__reduce_add_sync(kFull, (unsigned)sw) : warp_sum_i64((long long)sw);
         }
-        int kmin = __reduce_min_sync(kFull, kbest);
-        hp = __reduce_min_sync(kFull, kbest == kmin ? ibest : INT_MAX);
-        int wp = positive ? 65535 - kmin : kmin;
+        const int wp = positive ? 65535 - kmin : kmin;
         hheight = (float)(positive ? __dsub_rn((double)wp, b) : __dsub_rn(b, (double)wp));
-        long long c = (long long)__reduce_add_sync(kFull, cnt);
-        long long swt = (a1 - a0 <= 32768) ? (long long)__reduce_add_sync(kFull, (unsigned)sw) : warp_sum_i64((long long)sw);
+        const long long c = cnt_i;
         double integ;
-        if (fabs(b) < 2e9) {
-            double bf = __dsub_rn(b, bi);
-            long long ipart = positive ? (swt - c * (long long)bi) : (c * (long long)bi - swt);
-            double fpart = __dmul_rn((double)c, bf);
+        if (r.b_small) {
+            long long ipart = positive ? (swt - c * (long long)r.bi) : (c * (long long)r.bi - swt);
+            double fpart = __dmul_rn((double)c, r.bf);
             integ = positive ? __dsub_rn((double)ipart, fpart) : __dadd_rn((double)ipart, fpart);
         } else {
             integ = positive ? __dsub_rn((double)swt, __dmul_rn((double)c, b)) : __dsub_rn(__dmul_rn((double)c, b), (double)swt);
@@ -347,6 +369,11 @@ __device__ __forceinline__ void scan_record(const Src& src, const ScanRec& r, co
             q0 = src.load16(v0);
             if (!U16) q1 = src.load16(v0 + 4);
         }
+        // warp-uniform: every lane holds 8 valid samples that all lie inside the area range and
+        // outside the height range (the common case away from the record edges)
+        const int wi0 = vb - mis;
+        const bool ultra = U16 && FEAT && !known && wi0 > 0 && vb + 256 <= vtotal && c0 <= wi0 && c1 >= wi0 + 256 &&
+                           (p1 <= p0 || p1 <= wi0 || p0 >= wi0 + 256);
         const unsigned lastw = U16 ? q0.w : q1.w;
         unsigned prevw = __shfl_up_sync(kFull, lastw, 1);
         if (lane == 0) prevw = carry_w;
@@ -364,40 +391,48 @@ __device__ __forceinline__ void scan_record(const Src& src, const ScanRec& r, co
                 unsigned d0 = umax16x2(q0.x, f0) - umin16x2(q0.x, f0), d1 = umax16x2(q0.y, f1) - umin16x2(q0.y, f1);
                 unsigned d2 = umax16x2(q0.z, f2) - umin16x2(q0.z, f2), d3 = umax16x2(q0.w, f3) - umin16x2(q0.w, f3);
                 pdiff = umax16x2(pdiff, umax16x2(umax16x2(d0, d1), umax16x2(d2, d3)));
+                if (ultra) {
+                    // whole window inside the area range and outside the height range: sum only
+                    unsigned s = __dp2a_lo(q0.x, 0x0101u, isum32);
+                    s = __dp2a_lo(q0.y, 0x0101u, s);
+                    s = __dp2a_lo(q0.z, 0x0101u, s);
+                    isum32 = __dp2a_lo(q0.w, 0x0101u, s);
+                } else {
                 // height range
-                const int jlo = max(0, p0 - i0), jhi = min(8, p1 - i0);
-                if (jhi > jlo) {
-                    if (jlo == 0 && jhi == 8) {
-                        pmin = umin16x2(pmin, umin16x2(umin16x2(q0.x, q0.y), umin16x2(q0.z, q0.w)));
-                        pmax = umax16x2(pmax, umax16x2(umax16x2(q0.x, q0.y), umax16x2(q0.z, q0.w)));
-                    } else {
-                        const unsigned ww[4] = {q0.x, q0.y, q0.z, q0.w};
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            int w = (int)((ww[j >> 1] >> ((j & 1) * 16)) & 0xffffu);
-                            if (j >= jlo && j < jhi) { imin = min(imin, w); imax = max(imax, w); }
+                    const int jlo = max(0, p0 - i0), jhi = min(8, p1 - i0);
+                    if (jhi > jlo) {
+                        if (jlo == 0 && jhi == 8) {
+                            pmin = umin16x2(pmin, umin16x2(umin16x2(q0.x, q0.y), umin16x2(q0.z, q0.w)));
+                            pmax = umax16x2(pmax, umax16x2(umax16x2(q0.x, q0.y), umax16x2(q0.z, q0.w)));
+                        } else {
+                            const unsigned ww[4] = {q0.x, q0.y, q0.z, q0.w};
+    #pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                int w = (int)((ww[j >> 1] >> ((j & 1) * 16)) & 0xffffu);
+                                if (j >= jlo && j < jhi) { imin = min(imin, w); imax = max(imax, w); }
+                            }
                         }
                     }
-                }
-                // area range
-                const int klo = max(0, c0 - i0), khi = min(8, c1 - i0);
-                if (khi > klo) {
-                    if (klo == 0 && khi == 8 && !known) {
-                        unsigned s = __dp2a_lo(q0.x, 0x0101u, isum32);
-                        s = __dp2a_lo(q0.y, 0x0101u, s);
-                        s = __dp2a_lo(q0.z, 0x0101u, s);
-                        isum32 = __dp2a_lo(q0.w, 0x0101u, s);
-                    } else {
-                        const unsigned ww[4] = {q0.x, q0.y, q0.z, q0.w};
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            unsigned w = (ww[j >> 1] >> ((j & 1) * 16)) & 0xffffu;
-                            if (j >= klo && j < khi) {
-                                if (!known) {
-                                    isum += w;
-                                } else {
-                                    float sv = positive ? __fsub_rn((float)w, b32) : __fsub_rn(b32, (float)w);
-                                    dsum += (double)sv;
+                    // area range
+                    const int klo = max(0, c0 - i0), khi = min(8, c1 - i0);
+                    if (khi > klo) {
+                        if (klo == 0 && khi == 8 && !known) {
+                            unsigned s = __dp2a_lo(q0.x, 0x0101u, isum32);
+                            s = __dp2a_lo(q0.y, 0x0101u, s);
+                            s = __dp2a_lo(q0.z, 0x0101u, s);
+                            isum32 = __dp2a_lo(q0.w, 0x0101u, s);
+                        } else {
+                            const unsigned ww[4] = {q0.x, q0.y, q0.z, q0.w};
+    #pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                unsigned w = (ww[j >> 1] >> ((j & 1) * 16)) & 0xffffu;
+                                if (j >= klo && j < khi) {
+                                    if (!known) {
+                                        isum += w;
+                                    } else {
+                                        float sv = positive ? __fsub_rn((float)w, b32) : __fsub_rn(b32, (float)w);
+                                        dsum += (double)sv;
+                                    }
                                 }
                             }
                         }
@@ -585,6 +620,17 @@ __device__ __forceinline__ void scan_record(const Src& src, const ScanRec& r, co
     }
 }
 
+__device__ __forceinline__ void hit_constants(ScanRec& r) {
+    const double b = r.b_rec;
+    const bool positive = r.pol == WFB_POL_POSITIVE;
+    r.b_small = fabs(b) < 2e9;
+    r.bi = floor(b);
+    r.bf = __dsub_rn(b, r.bi);
+    const int ib = r.b_small ? (int)r.bi : (b > 0 ? INT_MAX : INT_MIN);
+    // negative: w < b  <=>  w <= ceil(b)-1 ; positive: w > b  <=>  w >= floor(b)+1
+    r.wlim = positive ? ib + 1 : ((r.bi == b) ? ib - 1 : ib);
+}
+
 __device__ __forceinline__ double bcast_f64(double v, int src) { return shfl_f64(v, src); }
 __device__ __forceinline__ long long bcast_i64(long long v, int src) {
     int lo = __shfl_sync(kFull, (int)(v & 0xffffffffll), src);
@@ -703,6 +749,7 @@ __global__ void __launch_bounds__(kWarps * 32) fused_features_hits_kernel(const 
             r.p1 = FEAT ? __shfl_sync(kFull, p1, j) : 0;
             r.c0 = FEAT ? __shfl_sync(kFull, c0, j) : 0;
             r.c1 = FEAT ? __shfl_sync(kFull, c1, j) : 0;
+            if (HITS && U16) hit_constants(r);
             StageSink sink{HITS ? &s_ent[warp][used] : nullptr, kEntPerWarp - used, 0, (unsigned)j};
             FeatAcc fa = {0.f, 0.f, 0.f, 0.f};
             if (STAGED) {
@@ -852,6 +899,7 @@ __global__ void __launch_bounds__(kWarps * 32) fused_features_hits_kernel(const 
             r.thr = bcast_f64(thr, j);
             r.kmax = __shfl_sync(kFull, kmax, j);
             r.p0 = r.p1 = r.c0 = r.c1 = 0;
+            hit_constants(r);
             RowSink sink;
             sink.out = a.hit_out;
             sink.row = bcast_i64(my_row0, j);

@@ -192,7 +192,10 @@ int wfb_filter_pool(const void* pool_dev, int32_t pool_is_f32, int64_t pool_len,
                     const wfb_rec_meta* meta_dev, int64_t n, const wfb_filter_cfg* cfgs_dev,
                     int32_t n_cfg, const int32_t* cfg_index_dev, const double* sg_tables_dev,
                     const int32_t* sg_table_offset_dev, float* out_dev, int64_t pool_base,
-                    void* stream);
+                    void* workspace_dev, size_t workspace_bytes, int32_t lmax, void* stream);
+/* Scratch for the Butterworth forward pass (float64, one row of lmax + 2*padlen per resident
+ * thread); SG-only runs may pass a NULL workspace. */
+size_t wfb_filter_workspace_bytes(int64_t n, int32_t lmax);
 
 /* ---- waveform_width / waveform_width_integral --------------------------------------------- */
 

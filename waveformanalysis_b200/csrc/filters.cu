@@ -1,0 +1,201 @@
+// wave_pool_filtered on the device: Savitzky-Golay (mode="interp") and zero-phase Butterworth
+// (sosfiltfilt) per record, float32 output aligned with the input wave_offsets.
+//
+// Reference: core/plugins/builtin/cpu/filtering.py:181-241 (_apply_filter_core),
+// :377-407 (filter_wave_pool_batch), records.py:368-438 (WavePoolFilteredPlugin.compute).
+// Third-party arithmetic restated (scipy 1.18.1, un-vendored dependency of the reference):
+//   savgol_filter(mode="interp"): interior = correlation with the savgol taps accumulated in
+//     float64 and stored float32; first/last halflen samples = degree-`poly` least-squares fit over
+//     the first/last `window` samples evaluated at those positions (projection rows from the host).
+//   sosfiltfilt: odd extension by padlen, DF2T cascade forward from zi*x0, reversed pass from
+//     zi*y_last, extension dropped; float64 with separate multiply/add (no FMA) = bit-exact.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace wfb {
+
+template <typename T>
+__device__ __forceinline__ double sample_f64(const T* p, long long i) {
+    return (double)(float)p[i];  // reference casts the pool to float32 first (filtering.py:169)
+}
+
+// ---- Savitzky-Golay: one warp per record -----------------------------------------------------
+// table layout (doubles): [0, w) taps (y[k] = sum_j taps[j] * x[k-h+j]); [w, w + h*w) rows of the
+// projector for outputs 0..h-1 over x[0..w); [w + h*w, w + 2*h*w) rows for outputs L-h..L-1 over
+// x[L-w..L).  The effective window w is stored in front: table[-1] is not used; w comes from
+// sg_window_eff[rec].
+template <typename T>
+__global__ void __launch_bounds__(256) sg_filter_kernel(const T* __restrict__ pool, long long pool_len,
+                                                       const wfb_rec_meta* __restrict__ meta, long long n,
+                                                       const double* __restrict__ tables,
+                                                       const int* __restrict__ table_offset,
+                                                       const int* __restrict__ cfg_index,
+                                                       const wfb_filter_cfg* __restrict__ cfgs, float* __restrict__ out,
+                                                       long long pool_base) {
+    const int lane = lane_id();
+    const long long rec = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    if (rec >= n) return;
+    const wfb_filter_cfg& cfg = cfgs[cfg_index[rec]];
+    if (cfg.type != WFB_FILTER_SG) return;
+    const long long off = meta[rec].wave_offset - pool_base;
+    const int L = meta[rec].event_length;
+    if (L <= 0 || off < 0 || off + L > pool_len) return;
+    const T* x = pool + off;
+    float* y = out + off;
+    const int toff = table_offset[rec];
+    if (toff < 0) {  // window <= poly: identity (filtering.py:231-232)
+        for (int k = lane; k < L; k += 32) y[k] = (float)x[k];
+        return;
+    }
+    int w = min(cfg.sg_window, L);
+    if ((w & 1) == 0) --w;
+    const int h = w >> 1;
+    const double* taps = tables + toff;
+    const double* first = taps + w;
+    const double* last = first + (size_t)h * w;
+    for (int k = lane; k < L; k += 32) {
+        double acc = 0.0;
+        if (k >= h && k < L - h) {
+            for (int j = 0; j < w; ++j) acc = __dadd_rn(acc, __dmul_rn(taps[j], sample_f64(x, k - h + j)));
+        } else if (k < h) {
+            const double* row = first + (size_t)k * w;
+            for (int j = 0; j < w; ++j) acc = __dadd_rn(acc, __dmul_rn(row[j], sample_f64(x, j)));
+        } else {
+            const double* row = last + (size_t)(k - (L - h)) * w;
+            for (int j = 0; j < w; ++j) acc = __dadd_rn(acc, __dmul_rn(row[j], sample_f64(x, L - w + j)));
+        }
+        y[k] = (float)acc;
+    }
+}
+
+// ---- Butterworth sosfiltfilt: one thread per record, time-serial recursion --------------------
+// scratch: float64 forward-pass output, time-major and interleaved over the threads of the grid
+// (scratch[t * n_threads + tid]) so that the 32 lanes of a warp store consecutive doubles.
+template <typename T>
+__global__ void __launch_bounds__(128) bw_filter_kernel(const T* __restrict__ pool, long long pool_len,
+                                                       const wfb_rec_meta* __restrict__ meta, long long n,
+                                                       const int* __restrict__ cfg_index,
+                                                       const wfb_filter_cfg* __restrict__ cfgs, float* __restrict__ out,
+                                                       long long pool_base, double* __restrict__ scratch,
+                                                       int scratch_len) {
+    const long long n_threads = (long long)gridDim.x * blockDim.x;
+    const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    for (long long rec = tid; rec < n; rec += n_threads) {
+        const wfb_filter_cfg& cfg = cfgs[cfg_index[rec]];
+        if (cfg.type != WFB_FILTER_BW) continue;
+        const long long off = meta[rec].wave_offset - pool_base;
+        const int L = meta[rec].event_length;
+        if (L <= 0 || off < 0 || off + L > pool_len) continue;
+        const T* x = pool + off;
+        float* y = out + off;
+        const int ns = cfg.n_sections;
+        int z_b = 0, z_a = 0;
+        for (int s = 0; s < ns; ++s) {
+            z_b += cfg.sos[s][2] == 0.0;
+            z_a += cfg.sos[s][5] == 0.0;
+        }
+        const int edge = 3 * (2 * ns + 1 - min(z_b, z_a));  // filtering.py:198-203
+        if (L <= edge || L + 2 * edge > scratch_len) {       // unfiltered copy (filtering.py:221-222)
+            for (int k = 0; k < L; ++k) y[k] = (float)x[k];
+            continue;
+        }
+        const int n_ext = L + 2 * edge;
+        const double x_first = sample_f64(x, 0), x_last = sample_f64(x, L - 1);
+        auto ext = [&](int t) -> double {
+            if (t < edge) return __dsub_rn(__dmul_rn(2.0, x_first), sample_f64(x, edge - t));
+            if (t < edge + L) return sample_f64(x, t - edge);
+            return __dsub_rn(__dmul_rn(2.0, x_last), sample_f64(x, L - 2 - (t - edge - L)));
+        };
+        double z0[WFB_MAX_SOS_SECTIONS], z1[WFB_MAX_SOS_SECTIONS];
+        const double x0 = ext(0);
+        for (int s = 0; s < ns; ++s) {
+            z0[s] = __dmul_rn(cfg.zi[s][0], x0);
+            z1[s] = __dmul_rn(cfg.zi[s][1], x0);
+        }
+        double v = 0.0;
+        for (int t = 0; t < n_ext; ++t) {
+            v = ext(t);
+            for (int s = 0; s < ns; ++s) {
+                const double b0 = cfg.sos[s][0], b1 = cfg.sos[s][1], b2 = cfg.sos[s][2];
+                const double a1 = cfg.sos[s][4], a2 = cfg.sos[s][5];
+                const double o = __dadd_rn(__dmul_rn(b0, v), z0[s]);
+                z0[s] = __dadd_rn(__dsub_rn(__dmul_rn(b1, v), __dmul_rn(a1, o)), z1[s]);
+                z1[s] = __dsub_rn(__dmul_rn(b2, v), __dmul_rn(a2, o));
+                v = o;
+            }
+            scratch[(size_t)t * n_threads + tid] = v;
+        }
+        const double y0 = v;  // last forward output
+        for (int s = 0; s < ns; ++s) {
+            z0[s] = __dmul_rn(cfg.zi[s][0], y0);
+            z1[s] = __dmul_rn(cfg.zi[s][1], y0);
+        }
+        for (int t = n_ext - 1; t >= 0; --t) {
+            v = scratch[(size_t)t * n_threads + tid];
+            for (int s = 0; s < ns; ++s) {
+                const double b0 = cfg.sos[s][0], b1 = cfg.sos[s][1], b2 = cfg.sos[s][2];
+                const double a1 = cfg.sos[s][4], a2 = cfg.sos[s][5];
+                const double o = __dadd_rn(__dmul_rn(b0, v), z0[s]);
+                z0[s] = __dadd_rn(__dsub_rn(__dmul_rn(b1, v), __dmul_rn(a1, o)), z1[s]);
+                z1[s] = __dsub_rn(__dmul_rn(b2, v), __dmul_rn(a2, o));
+                v = o;
+            }
+            if (t >= edge && t < edge + L) y[t - edge] = (float)v;
+        }
+    }
+}
+
+}  // namespace wfb
+
+using namespace wfb;
+
+extern "C" int wfb_filter_pool(const void* pool_dev, int32_t pool_is_f32, int64_t pool_len, const wfb_rec_meta* meta_dev,
+                               int64_t n, const wfb_filter_cfg* cfgs_dev, int32_t n_cfg, const int32_t* cfg_index_dev,
+                               const double* sg_tables_dev, const int32_t* sg_table_offset_dev, float* out_dev,
+                               int64_t pool_base, void* workspace_dev, size_t workspace_bytes, int32_t lmax,
+                               void* stream) {
+    WFB_REQUIRE(n >= 0 && pool_len >= 0 && n_cfg >= 0, "wfb_filter_pool: negative size");
+    if (n == 0) return WFB_OK;
+    WFB_REQUIRE(pool_dev && meta_dev && cfgs_dev && cfg_index_dev && out_dev, "wfb_filter_pool: NULL pointer");
+    WFB_REQUIRE(n_cfg > 0, "wfb_filter_pool: no filter configuration");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // the output pool is zero where no record points (records.py:382)
+    WFB_CUDA(cudaMemsetAsync(out_dev, 0, (size_t)pool_len * sizeof(float), st));
+    const unsigned sg_blocks = (unsigned)((n * 32 + 255) / 256);
+    // BW: as many threads as the scratch allows, at most one per record
+    const long long scratch_len = (long long)lmax + 2 * 3 * (2 * WFB_MAX_SOS_SECTIONS + 1);
+    long long bw_threads = 0;
+    if (workspace_dev && workspace_bytes >= (size_t)scratch_len * 8 * 128) {
+        bw_threads = (long long)(workspace_bytes / ((size_t)scratch_len * 8));
+        bw_threads = std::min<long long>(bw_threads, (long long)sm_count() * 2048);
+        bw_threads = std::min<long long>(bw_threads, ((n + 127) / 128) * 128);
+        bw_threads = (bw_threads / 128) * 128;
+    }
+    if (pool_is_f32) {
+        if (sg_tables_dev && sg_table_offset_dev)
+            sg_filter_kernel<float><<<sg_blocks, 256, 0, st>>>(static_cast<const float*>(pool_dev), pool_len, meta_dev, n, sg_tables_dev,
+                                                             sg_table_offset_dev, cfg_index_dev, cfgs_dev, out_dev, pool_base);
+        if (bw_threads > 0)
+            bw_filter_kernel<float><<<(unsigned)(bw_threads / 128), 128, 0, st>>>(static_cast<const float*>(pool_dev), pool_len, meta_dev, n,
+                                                                                cfg_index_dev, cfgs_dev, out_dev, pool_base,
+                                                                                static_cast<double*>(workspace_dev), (int)scratch_len);
+    } else {
+        if (sg_tables_dev && sg_table_offset_dev)
+            sg_filter_kernel<uint16_t><<<sg_blocks, 256, 0, st>>>(static_cast<const uint16_t*>(pool_dev), pool_len, meta_dev, n, sg_tables_dev,
+                                                                sg_table_offset_dev, cfg_index_dev, cfgs_dev, out_dev, pool_base);
+        if (bw_threads > 0)
+            bw_filter_kernel<uint16_t><<<(unsigned)(bw_threads / 128), 128, 0, st>>>(static_cast<const uint16_t*>(pool_dev), pool_len, meta_dev,
+                                                                                   n, cfg_index_dev, cfgs_dev, out_dev, pool_base,
+                                                                                   static_cast<double*>(workspace_dev), (int)scratch_len);
+    }
+    WFB_CUDA(cudaGetLastError());
+    return WFB_OK;
+}
+
+extern "C" size_t wfb_filter_workspace_bytes(int64_t n, int32_t lmax) {
+    // float64 forward-pass scratch of the Butterworth kernel, one row per resident thread
+    const long long scratch_len = (long long)lmax + 2 * 3 * (2 * WFB_MAX_SOS_SECTIONS + 1);
+    long long threads = std::min<long long>((long long)sm_count() * 2048, ((std::max<int64_t>(n, 1) + 127) / 128) * 128);
+    return (size_t)scratch_len * 8 * (size_t)threads;
+}

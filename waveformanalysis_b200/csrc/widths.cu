@@ -1,0 +1,355 @@
+// waveform_width (per hit, threshold crossings with linear interpolation) and
+// waveform_width_integral (per record, cumulative-charge quantiles).
+//
+// Reference: core/plugins/builtin/cpu/waveform_width.py:205-374,
+//            core/plugins/builtin/cpu/waveform_width_integral.py:166-231.
+#include "common.cuh"
+
+namespace wfb {
+
+// ---------------------------------------------------------------------------------------------
+// waveform_width: one warp per hit.  numpy promotion rules are followed as the reference gets
+// them: int16 rows -> everything float64; float32 rows -> baseline, corrected wave, thresholds
+// and the interpolated crossing in float32, sums with the int64 peak position in float64.
+// ---------------------------------------------------------------------------------------------
+
+// np.mean of the first n (<= 50) float32 samples: numpy's pairwise sum for n < 128 keeps eight
+// partial sums and folds them as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then adds the tail.
+__device__ float numpy_mean_f32(const float* w, int n) {
+    float res;
+    if (n < 8) {
+        res = 0.f;
+        for (int i = 0; i < n; ++i) res = __fadd_rn(res, w[i]);
+    } else {
+        float r[8];
+        for (int k = 0; k < 8; ++k) r[k] = w[k];
+        int i;
+        for (i = 8; i < n - (n % 8); i += 8)
+            for (int k = 0; k < 8; ++k) r[k] = __fadd_rn(r[k], w[i + k]);
+        res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                        __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+        for (; i < n; ++i) res = __fadd_rn(res, w[i]);
+    }
+    return __fdiv_rn(res, (float)n);
+}
+
+// first index in [lo, hi) where pred(i) holds, -1 if none; warp-cooperative
+template <typename F>
+__device__ __forceinline__ int warp_find_first(int lo, int hi, F pred) {
+    const int lane = lane_id();
+    for (int base = lo; base < hi; base += 32) {
+        int i = base + lane;
+        unsigned m = __ballot_sync(kFull, i < hi && pred(i));
+        if (m) return base + __ffs(m) - 1;
+    }
+    return -1;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) waveform_width_kernel(const T* __restrict__ waves, long long n_waves, int length,
+                                                            long long stride, const long long* __restrict__ hit_row,
+                                                            const long long* __restrict__ hit_pos,
+                                                            const long long* __restrict__ hit_ts,
+                                                            const short* __restrict__ hit_board,
+                                                            const short* __restrict__ hit_channel,
+                                                            const long long* __restrict__ hit_rid, long long n_hits,
+                                                            const wfb_width_params p, uint8_t* __restrict__ out,
+                                                            uint8_t* __restrict__ valid) {
+    constexpr bool F32 = sizeof(T) == 4;
+    const int lane = lane_id();
+    const long long hit = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    if (hit >= n_hits) return;
+    const long long row = hit_row[hit];
+    const long long pos64 = hit_pos[hit];
+    bool ok = row >= 0 && row < n_waves && pos64 < length && length > 0;
+    // numpy negative indices wrap: position in [-length, 0) addresses from the end
+    long long posw = pos64 < 0 ? pos64 + length : pos64;
+    ok = ok && posw >= 0 && posw < length;
+    if (!ok) {
+        if (lane == 0) valid[hit] = 0;
+        return;
+    }
+    const T* w = waves + row * stride;
+    const int pos = (int)posw;
+    const int nb = min(50, length);
+    double bl64 = 0.0;
+    float bl32 = 0.f;
+    if (F32) {
+        if (lane == 0) bl32 = numpy_mean_f32(reinterpret_cast<const float*>(w), nb);
+        bl32 = __shfl_sync(kFull, bl32, 0);
+    } else {
+        long long s = 0;
+        for (int i = lane; i < nb; i += 32) s += (long long)w[i];
+        s = warp_sum_i64(s);
+        bl64 = (double)s / (double)nb;  // integer sum is exact, one division as np.mean
+    }
+    auto wc64 = [&](int i) -> double { return __dsub_rn((double)w[i], bl64); };
+    auto wc32 = [&](int i) -> float { return __fsub_rn((float)w[i], bl32); };
+    const double pv = F32 ? (double)wc32(pos) : wc64(pos);
+    if (!(pv > 0.0)) {  // peak_value <= 0 (or NaN compares false in the reference too: NaN <= 0 is False!)
+        if (pv <= 0.0) {
+            if (lane == 0) valid[hit] = 0;
+            return;
+        }
+    }
+    // the slices wave[:pos] / wave[pos:] use the raw (possibly negative) position
+    const int left_hi = pos64 < 0 ? pos : pos;
+    // thresholds
+    double t64[4];
+    float t32[4];
+    const double fr[4] = {p.rise_low, p.rise_high, p.fall_high, p.fall_low};
+    for (int k = 0; k < 4; ++k) {
+        t64[k] = __dmul_rn(pv, fr[k]);
+        t32[k] = __fmul_rn((float)pv, (float)fr[k]);
+    }
+    // crossing positions: value + kind (interpolated positions are float32 for float32 rows)
+    double cross[4];
+    bool found[4];
+    for (int k = 0; k < 4; ++k) {
+        const bool rising = k < 2;
+        const int lo = rising ? 0 : pos, hi = rising ? left_hi : length;
+        int idx;
+        if (F32) {
+            const float th = t32[k];
+            idx = rising ? warp_find_first(lo, hi, [&](int i) { return wc32(i) >= th; })
+                         : warp_find_first(lo, hi, [&](int i) { return wc32(i) <= th; });
+        } else {
+            const double th = t64[k];
+            idx = rising ? warp_find_first(lo, hi, [&](int i) { return wc64(i) >= th; })
+                         : warp_find_first(lo, hi, [&](int i) { return wc64(i) <= th; });
+        }
+        found[k] = idx >= 0;
+        cross[k] = 0.0;
+        if (idx >= 0) {
+            const int rel = idx - lo;  // index inside the slice
+            if (!p.interpolation || rel == 0) {
+                cross[k] = (double)rel;
+            } else if (F32) {
+                float y0 = wc32(idx - 1), y1 = wc32(idx);
+                float dy = __fsub_rn(y1, y0);
+                if (fabsf(dy) < 1e-10f) cross[k] = (double)rel;
+                else cross[k] = (double)__fadd_rn((float)(rel - 1), __fdiv_rn(__fsub_rn(t32[k], y0), dy));
+            } else {
+                double y0 = wc64(idx - 1), y1 = wc64(idx);
+                double dy = __dsub_rn(y1, y0);
+                if (fabs(dy) < 1e-10) cross[k] = (double)rel;
+                else cross[k] = __dadd_rn((double)(rel - 1), __ddiv_rn(__dsub_rn(t64[k], y0), dy));
+            }
+        }
+    }
+    double rts = 0.0, rt = 0.0, fts = 0.0, ft = 0.0, tws = 0.0, tw = 0.0;
+    if (found[0] && found[1]) {
+        rts = F32 ? (double)__fsub_rn((float)cross[1], (float)cross[0]) : __dsub_rn(cross[1], cross[0]);
+        rt = F32 ? (double)__fdiv_rn((float)rts, (float)p.sampling_rate) : __ddiv_rn(rts, p.sampling_rate);
+    }
+    double fh = 0.0, fl = 0.0;
+    if (found[2] && found[3]) {
+        fh = __dadd_rn(cross[2], (double)pos64);  // + np.int64 position -> float64
+        fl = __dadd_rn(cross[3], (double)pos64);
+        fts = __dsub_rn(fl, fh);
+        ft = __ddiv_rn(fts, p.sampling_rate);
+    }
+    if (found[0] && found[3]) {
+        if (found[2]) {
+            tws = __dsub_rn(fl, cross[0]);
+            tw = __ddiv_rn(tws, p.sampling_rate);
+        } else {  // fall_low_pos was not shifted by the peak position (waveform_width.py:294-306)
+            tws = F32 ? (double)__fsub_rn((float)cross[3], (float)cross[0]) : __dsub_rn(cross[3], cross[0]);
+            tw = F32 ? (double)__fdiv_rn((float)tws, (float)p.sampling_rate) : __ddiv_rn(tws, p.sampling_rate);
+        }
+    }
+    if (lane < 14) {
+        unsigned word;
+        switch (lane) {
+            case 0: word = __float_as_uint((float)rt); break;
+            case 1: word = __float_as_uint((float)ft); break;
+            case 2: word = __float_as_uint((float)tw); break;
+            case 3: word = __float_as_uint((float)rts); break;
+            case 4: word = __float_as_uint((float)fts); break;
+            case 5: word = __float_as_uint((float)tws); break;
+            case 6: word = (unsigned)(pos64 & 0xffffffffll); break;
+            case 7: word = (unsigned)((unsigned long long)pos64 >> 32); break;
+            case 8: word = __float_as_uint((float)pv); break;
+            case 9: word = (unsigned)(hit_ts[hit] & 0xffffffffll); break;
+            case 10: word = (unsigned)((unsigned long long)hit_ts[hit] >> 32); break;
+            case 11: word = ((unsigned)(unsigned short)(hit_board ? hit_board[hit] : 0)) | ((unsigned)(unsigned short)hit_channel[hit] << 16); break;
+            case 12: word = (unsigned)(hit_rid[hit] & 0xffffffffll); break;
+            default: word = (unsigned)((unsigned long long)hit_rid[hit] >> 32); break;
+        }
+        reinterpret_cast<unsigned*>(out + hit * kWidthRowBytes)[lane] = word;
+    }
+    if (lane == 0) valid[hit] = 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// waveform_width_integral: one THREAD per record, strictly sequential float64 arithmetic so the
+// cumulative sums round exactly as np.cumsum and the total exactly as numpy's pairwise np.sum.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct ChargeSrc {
+    const T* w;
+    double b;
+    float b32;
+    int mode;  // 0: unknown polarity (b - w in f64), 1: negative known (b32 - w in f32), 2: positive known
+    __device__ __forceinline__ double operator()(int i) const {
+        double sig;
+        if (mode == 0) sig = __dsub_rn(b, (double)w[i]);
+        else if (mode == 1) sig = (double)__fsub_rn(b32, (float)w[i]);
+        else sig = (double)__fsub_rn((float)w[i], b32);
+        return fmax(sig, 0.0);
+    }
+};
+
+// numpy pairwise summation (numpy/_core/src/umath/loops_utils.h.src: pairwise_sum), iterative
+template <typename Src>
+__device__ double numpy_pairwise_sum(const Src& x, int n) {
+    // explicit stack of (offset, length) blocks; the recursion halves until length <= 128
+    int st_off[40], st_len[40];
+    double st_val[40];
+    int st_state[40];  // 0: to expand, 1: left done (value holds left sum)
+    int sp = 0;
+    st_off[0] = 0; st_len[0] = n; st_state[0] = 0;
+    double ret = 0.0;
+    bool have_ret = false;
+    while (sp >= 0) {
+        const int off = st_off[sp], len = st_len[sp];
+        if (st_state[sp] == 0) {
+            if (len < 8) {
+                double res = 0.0;
+                for (int i = 0; i < len; ++i) res = __dadd_rn(res, x(off + i));
+                ret = res; have_ret = true; --sp;
+            } else if (len <= 128) {
+                double r[8];
+                for (int k = 0; k < 8; ++k) r[k] = x(off + k);
+                int i;
+                for (i = 8; i < len - (len % 8); i += 8)
+                    for (int k = 0; k < 8; ++k) r[k] = __dadd_rn(r[k], x(off + i + k));
+                double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                                       __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+                for (; i < len; ++i) res = __dadd_rn(res, x(off + i));
+                ret = res; have_ret = true; --sp;
+            } else {
+                int n2 = len / 2;
+                n2 -= n2 % 8;
+                st_state[sp] = 1;
+                st_val[sp] = 0.0;
+                // push left
+                ++sp;
+                st_off[sp] = off; st_len[sp] = n2; st_state[sp] = 0;
+            }
+        } else if (st_state[sp] == 1) {
+            // left returned in ret; remember it and descend right
+            int n2 = len / 2;
+            n2 -= n2 % 8;
+            st_val[sp] = ret;
+            st_state[sp] = 2;
+            ++sp;
+            st_off[sp] = off + n2; st_len[sp] = len - n2; st_state[sp] = 0;
+        } else {
+            ret = __dadd_rn(st_val[sp], ret);
+            --sp;
+        }
+    }
+    (void)have_ret;
+    return ret;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) width_integral_kernel(const T* __restrict__ pool, long long pool_len,
+                                                            const wfb_rec_meta* __restrict__ meta, long long n,
+                                                            double q_low, double q_high, double dt, long long pool_base,
+                                                            long long row_base, uint8_t* __restrict__ out) {
+    const long long rec = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (rec >= n) return;
+    const wfb_rec_meta m = meta[rec];
+    long long off = m.wave_offset - pool_base;
+    int L = m.event_length;
+    if (L < 0 || off < 0 || off + L > pool_len) L = 0;
+    ChargeSrc<T> x;
+    x.w = pool + off;
+    x.b = m.baseline;
+    x.b32 = (float)m.baseline;
+    x.mode = m.polarity == WFB_POL_NEGATIVE ? 1 : (m.polarity == WFB_POL_POSITIVE ? 2 : 0);
+    const double q = numpy_pairwise_sum(x, L);
+    int lo = 0, hi = 0;
+    if (q > 0.0 && isfinite(q)) {
+        const double tl = __dmul_rn(q_low, q), th = __dmul_rn(q_high, q);
+        lo = hi = L;  // searchsorted returns len when no element reaches the target
+        bool fl = false, fh = false;
+        double cs = 0.0;
+        for (int i = 0; i < L; ++i) {
+            cs = (i == 0) ? x(0) : __dadd_rn(cs, x(i));
+            if (!fl && cs >= tl) { lo = i; fl = true; }
+            if (!fh && cs >= th) { hi = i; fh = true; break; }
+        }
+    }
+    const double ws = (double)max(hi - lo, 0);
+    unsigned* dst = reinterpret_cast<unsigned*>(out + rec * kWidthIntRowBytes);
+    dst[0] = __float_as_uint((float)__dmul_rn((double)lo, dt));
+    dst[1] = __float_as_uint((float)__dmul_rn((double)hi, dt));
+    dst[2] = __float_as_uint((float)__dmul_rn(ws, dt));
+    dst[3] = __float_as_uint((float)lo);
+    dst[4] = __float_as_uint((float)hi);
+    dst[5] = __float_as_uint((float)ws);
+    const long long qb = __double_as_longlong(q);
+    dst[6] = (unsigned)(qb & 0xffffffffll);
+    dst[7] = (unsigned)((unsigned long long)qb >> 32);
+    dst[8] = (unsigned)(m.timestamp & 0xffffffffll);
+    dst[9] = (unsigned)((unsigned long long)m.timestamp >> 32);
+    dst[10] = ((unsigned)(unsigned short)m.board) | ((unsigned)(unsigned short)m.channel << 16);
+    const long long ev = row_base + rec;
+    dst[11] = (unsigned)(ev & 0xffffffffll);
+    dst[12] = (unsigned)((unsigned long long)ev >> 32);
+}
+
+}  // namespace wfb
+
+using namespace wfb;
+
+extern "C" int wfb_waveform_width(const void* waves_dev, int64_t n_waves, int32_t length, int64_t stride,
+                                  const int64_t* hit_row_dev, const int64_t* hit_position_dev,
+                                  const int64_t* hit_timestamp_dev, const int16_t* hit_board_dev,
+                                  const int16_t* hit_channel_dev, const int64_t* hit_record_id_dev, int64_t n_hits,
+                                  const wfb_width_params* params, void* out_dev, uint8_t* valid_dev, void* stream) {
+    WFB_REQUIRE(params != nullptr, "wfb_waveform_width: params is NULL");
+    WFB_REQUIRE(n_hits >= 0 && n_waves >= 0 && length >= 0, "wfb_waveform_width: negative size");
+    if (n_hits == 0) return WFB_OK;
+    WFB_REQUIRE(hit_row_dev && hit_position_dev && hit_timestamp_dev && hit_channel_dev && hit_record_id_dev && out_dev && valid_dev,
+                "wfb_waveform_width: NULL pointer");
+    WFB_REQUIRE(params->sampling_rate != 0.0, "wfb_waveform_width: sampling_rate is 0");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned blocks = (unsigned)((n_hits * 32 + 255) / 256);
+    const long long* row = reinterpret_cast<const long long*>(hit_row_dev);
+    const long long* pos = reinterpret_cast<const long long*>(hit_position_dev);
+    const long long* ts = reinterpret_cast<const long long*>(hit_timestamp_dev);
+    const long long* rid = reinterpret_cast<const long long*>(hit_record_id_dev);
+    if (params->wave_is_f32)
+        waveform_width_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(waves_dev), n_waves, length, stride, row, pos, ts,
+                                                           hit_board_dev, hit_channel_dev, rid, n_hits, *params,
+                                                           static_cast<uint8_t*>(out_dev), valid_dev);
+    else
+        waveform_width_kernel<short><<<blocks, 256, 0, st>>>(static_cast<const short*>(waves_dev), n_waves, length, stride, row, pos, ts,
+                                                           hit_board_dev, hit_channel_dev, rid, n_hits, *params,
+                                                           static_cast<uint8_t*>(out_dev), valid_dev);
+    WFB_CUDA(cudaGetLastError());
+    return WFB_OK;
+}
+
+extern "C" int wfb_width_integral(const void* pool_dev, int32_t pool_is_f32, int64_t pool_len, const wfb_rec_meta* meta_dev,
+                                  int64_t n, double q_low, double q_high, double dt_ns, int64_t pool_base, int64_t row_base,
+                                  void* out_dev, void* stream) {
+    WFB_REQUIRE(n >= 0 && pool_len >= 0, "wfb_width_integral: negative size");
+    WFB_REQUIRE(q_low > 0 && q_high < 1 && q_low < q_high, "q_low/q_high invalid: q_low=%g, q_high=%g", q_low, q_high);
+    if (n == 0) return WFB_OK;
+    WFB_REQUIRE(meta_dev && out_dev, "wfb_width_integral: NULL pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned blocks = (unsigned)((n + 127) / 128);
+    if (pool_is_f32)
+        width_integral_kernel<float><<<blocks, 128, 0, st>>>(static_cast<const float*>(pool_dev), pool_len, meta_dev, n, q_low, q_high,
+                                                           dt_ns, pool_base, row_base, static_cast<uint8_t*>(out_dev));
+    else
+        width_integral_kernel<uint16_t><<<blocks, 128, 0, st>>>(static_cast<const uint16_t*>(pool_dev), pool_len, meta_dev, n, q_low,
+                                                              q_high, dt_ns, pool_base, row_base, static_cast<uint8_t*>(out_dev));
+    WFB_CUDA(cudaGetLastError());
+    return WFB_OK;
+}

@@ -1,0 +1,396 @@
+"""Host-array front ends of the remaining C-ABI entry points: records builder (K1),
+wave_pool_filtered, waveform_width, waveform_width_integral, hit merging and event grouping (K4).
+
+Every function takes / returns host numpy arrays in the reference's dtypes and does its
+arithmetic on the device through libwfb200.so; torch tensors only own device memory.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .dtypes import (
+    HIT_MERGE_CLUSTERS_DTYPE,
+    HIT_MERGED_COMPONENTS_DTYPE,
+    HIT_MERGED_DTYPE,
+    RECORDS_DTYPE,
+    WAVEFORM_WIDTH_DTYPE,
+    WAVEFORM_WIDTH_INTEGRAL_DTYPE,
+)
+from .engine import DeviceRun, _ptr, _stream, _torch, check_pool, packed_records
+
+# --------------------------------------------------------------------------------------------
+# small helpers
+# --------------------------------------------------------------------------------------------
+
+
+def _dev(a: np.ndarray):
+    torch = _torch()
+    a = np.ascontiguousarray(a)
+    if a.dtype == np.uint16:
+        return torch.from_numpy(a.view(np.int16)).cuda()
+    if a.dtype.names is not None or a.dtype.kind in "US":
+        return torch.from_numpy(a.view(np.uint8).reshape(-1)).cuda()
+    return torch.from_numpy(a).cuda()
+
+
+def _empty(nbytes: int):
+    return _torch().empty(max(int(nbytes), 16), dtype=_torch().uint8, device="cuda")
+
+
+# --------------------------------------------------------------------------------------------
+# K1: records builder
+# --------------------------------------------------------------------------------------------
+
+
+def build_records(timestamps_ps, boards, channels, samples, *, dt_ns: int, baseline_window=(0, 40),
+                  baselines=None, epoch_ns: int | None = None):
+    """raw rows (per-channel file order) -> (records[RECORDS_DTYPE], wave_pool[uint16]) in the
+    reference's global order (records_builder.py:115-120, 212-302, 341-426)."""
+    lib = _lib.load()
+    torch = _torch()
+    samples = np.ascontiguousarray(samples)
+    if samples.dtype not in (np.int16, np.uint16):
+        raise ValueError(f"samples must be int16, got {samples.dtype}")
+    n, L = samples.shape
+    if n == 0:
+        return np.zeros(0, dtype=RECORDS_DTYPE), np.zeros(0, dtype=np.uint16)
+    d_s = torch.empty(n * L + 16, dtype=torch.int16, device="cuda")[: n * L]
+    d_s.copy_(torch.from_numpy(samples.view(np.int16).reshape(-1)))
+    d_ts = _dev(np.asarray(timestamps_ps, dtype=np.int64))
+    d_b = _dev(np.asarray(boards, dtype=np.int16))
+    d_c = _dev(np.asarray(channels, dtype=np.int16))
+    d_bl = _dev(np.asarray(baselines, dtype=np.float64)) if baselines is not None else None
+    rows = _empty(n * 102)
+    pool = torch.empty(n * L + 16, dtype=torch.int16, device="cuda")[: n * L]
+    ws = _empty(lib.wfb_build_records_workspace_bytes(n))
+    _lib.check(lib.wfb_build_records(_ptr(d_s), _ptr(d_ts), _ptr(d_b), _ptr(d_c), _ptr(d_bl), n, L, int(baseline_window[0]),
+                                     int(baseline_window[1]), int(dt_ns), int(epoch_ns or 0), _ptr(rows), _ptr(pool), C.c_void_p(0),
+                                     _ptr(ws), ws.numel(), _stream()), "wfb_build_records")
+    rec = rows[: n * 102].cpu().numpy().view(RECORDS_DTYPE)
+    return rec, pool.cpu().numpy().view(np.uint16)
+
+
+def sort_pairs(keys: np.ndarray, vals: np.ndarray):
+    lib = _lib.load()
+    torch = _torch()
+    n = len(keys)
+    dk, dv = _dev(np.asarray(keys, np.int64)), _dev(np.asarray(vals, np.int64))
+    ok, ov = torch.empty_like(dk), torch.empty_like(dv)
+    ws = _empty(lib.wfb_sort_workspace_bytes(n))
+    _lib.check(lib.wfb_sort_pairs_i64(_ptr(dk), _ptr(dv), _ptr(ok), _ptr(ov), n, _ptr(ws), ws.numel(), _stream()), "wfb_sort_pairs_i64")
+    return ok.cpu().numpy(), ov.cpu().numpy()
+
+
+# --------------------------------------------------------------------------------------------
+# wave_pool_filtered
+# --------------------------------------------------------------------------------------------
+
+
+def sg_tables(window: int, poly: int) -> np.ndarray:
+    """[taps (w) | projector rows for outputs 0..h-1 (h*w) | rows for outputs L-h..L-1 (h*w)].
+
+    Host-side filter design, the analogue of scipy.signal.savgol_coeffs and the polynomial edge
+    fit of savgol_filter(mode='interp') (filtering.py:226-241): least-squares solve, done once per
+    distinct window."""
+    h = window // 2
+    x = np.arange(-h, window - h, dtype=float)[::-1]
+    A = x ** np.arange(poly + 1).reshape(-1, 1)
+    y = np.zeros(poly + 1)
+    y[0] = 1.0
+    c, *_ = np.linalg.lstsq(A, y, rcond=None)
+    taps = c[::-1].copy()  # y[k] = sum_j taps[j] * x[k-h+j]
+    V = np.vander(np.arange(window, dtype=float), poly + 1)
+    P = V @ np.linalg.pinv(V)
+    return np.concatenate([taps, P[:h].reshape(-1), P[window - h:].reshape(-1)])
+
+
+def butter_bandpass_sos(order: int, lowcut: float, highcut: float, fs: float) -> np.ndarray:
+    """Filter design is host-side configuration exactly as in the reference
+    (filtering.py:101: scipy.signal.butter(..., output='sos'))."""
+    from scipy.signal import butter
+
+    return butter(int(order), [float(lowcut), float(highcut)], btype="band", output="sos", fs=float(fs))
+
+
+def sos_zi(sos: np.ndarray) -> np.ndarray:
+    """Steady-state DF2T state per section (scipy.signal.sosfilt_zi, scipy 1.18 formula):
+    y_inf = sum(b)/sum(a); zi = reversed cumulative sum of (b - y_inf*a) without its first entry,
+    scaled by the DC gain of the sections before."""
+    sos = np.asarray(sos, dtype=np.float64)
+    zi = np.zeros((sos.shape[0], 2))
+    scale = 1.0
+    for s in range(sos.shape[0]):
+        b, a = sos[s, :3], sos[s, 3:]
+        if a[0] != 1:
+            b, a = b / a[0], a / a[0]
+        y_inf = np.sum(b) / np.sum(a)
+        v = b - y_inf * a
+        zi[s, 1] = scale * v[2]
+        zi[s, 0] = scale * (v[2] + v[1])
+        scale *= np.sum(sos[s, :3]) / np.sum(sos[s, 3:])
+    return zi
+
+
+def filter_pool(records: np.ndarray, pool: np.ndarray, *, configs: dict, default: dict, run: DeviceRun | None = None) -> np.ndarray:
+    """uint16 wave_pool -> float32 wave_pool_filtered (records.py:368-438).
+
+    ``default`` / ``configs[(board, channel)]``: {"filter_type": "SG", "sg_window_size", "sg_poly_order"} or
+    {"filter_type": "BW", "sos": ndarray (n_sections, 6)}.
+    """
+    lib = _lib.load()
+    torch = _torch()
+    pool_h, is_f32 = check_pool(pool)
+    out = np.zeros(len(pool_h), dtype=np.float32)
+    rec = packed_records(records, explicit_dt=1)
+    n = len(rec)
+    if n == 0 or len(pool_h) == 0:
+        return out
+    # distinct configs -> wfb_filter_cfg[]
+    keys = rec["board"].astype(np.int64) * 65536 + (rec["channel"].astype(np.int64) & 0xFFFF)
+    uniq, inv = np.unique(keys, return_inverse=True)
+    cfg_list = []
+    for k in uniq.tolist():
+        b, c = int(k >> 16), int(np.int16(k & 0xFFFF))
+        cfg_list.append(configs.get((b, c), default))
+    cfgs = (_lib.FilterCfg * len(cfg_list))()
+    tables: list[np.ndarray] = []
+    table_off: dict[tuple[int, int], int] = {}
+    cursor = 0
+    lens = rec["event_length"].astype(np.int64)
+    tab_off = np.full(n, -1, dtype=np.int32)
+    for ci, cfg in enumerate(cfg_list):
+        if cfg["filter_type"] == "BW":
+            sos = np.asarray(cfg["sos"], dtype=np.float64)
+            if sos.shape[0] > _lib.MAX_SOS_SECTIONS:
+                raise ValueError(f"filter_order too high: {sos.shape[0]} sections > {_lib.MAX_SOS_SECTIONS}")
+            zi = sos_zi(sos)
+            cfgs[ci].type = 1
+            cfgs[ci].n_sections = sos.shape[0]
+            for s in range(sos.shape[0]):
+                for j in range(6):
+                    cfgs[ci].sos[s][j] = sos[s, j]
+                cfgs[ci].zi[s][0], cfgs[ci].zi[s][1] = zi[s, 0], zi[s, 1]
+        else:
+            w0, poly = int(cfg["sg_window_size"]), int(cfg["sg_poly_order"])
+            cfgs[ci].type = 0
+            cfgs[ci].sg_window = w0
+            cfgs[ci].sg_poly = poly
+            sel = np.flatnonzero(inv == ci)
+            weff = np.minimum(w0, lens[sel])
+            weff = weff - (weff % 2 == 0)
+            for w in np.unique(weff).tolist():
+                if w <= poly or w <= 0:
+                    continue  # identity (filtering.py:193-194)
+                if (w, poly) not in table_off:
+                    t = sg_tables(int(w), poly)
+                    table_off[(w, poly)] = cursor
+                    tables.append(t)
+                    cursor += len(t)
+                tab_off[sel[weff == w]] = table_off[(w, poly)]
+    d_cfg = torch.from_numpy(np.frombuffer(bytes(cfgs), dtype=np.uint8).copy()).cuda()
+    d_idx = _dev(inv.astype(np.int32))
+    d_tab = _dev(np.concatenate(tables) if tables else np.zeros(1))
+    d_toff = _dev(tab_off)
+    own = run is None
+    if own:
+        run = DeviceRun.from_host(rec, pool_h)
+    d_out = torch.empty(len(pool_h) + 16, dtype=torch.float32, device="cuda")[: len(pool_h)]
+    lmax = max(int(lens.max()), 1)
+    has_bw = any(c["filter_type"] == "BW" for c in cfg_list)
+    ws = _empty(lib.wfb_filter_workspace_bytes(n, lmax)) if has_bw else None
+    _lib.check(lib.wfb_filter_pool(_ptr(run.pool), is_f32, len(pool_h), _ptr(run.meta), n, _ptr(d_cfg), len(cfg_list), _ptr(d_idx),
+                                   _ptr(d_tab), _ptr(d_toff), _ptr(d_out), 0, _ptr(ws), 0 if ws is None else ws.numel(), lmax,
+                                   _stream()), "wfb_filter_pool")
+    return d_out.cpu().numpy()
+
+
+# --------------------------------------------------------------------------------------------
+# waveform_width / waveform_width_integral
+# --------------------------------------------------------------------------------------------
+
+
+def waveform_width(hits: np.ndarray, wave_record_ids: np.ndarray, waves: np.ndarray, *, sampling_rate=None, rise_low=0.1,
+                   rise_high=0.9, fall_high=0.9, fall_low=0.1, interpolation=True) -> np.ndarray:
+    """Per-hit rise / fall / total widths (waveform_width.py:97-194).  ``waves`` is the (n, L)
+    int16 (st_waveforms) or float32 (filtered_waveforms) sample matrix (may be a strided view of
+    the structured array's ``wave`` field); ``wave_record_ids[i]`` the record_id of row i."""
+    lib = _lib.load()
+    torch = _torch()
+    if sampling_rate is None:
+        sampling_rate = 0.5
+    nh = len(hits)
+    if nh == 0 or len(waves) == 0:
+        return np.zeros(0, dtype=WAVEFORM_WIDTH_DTYPE)
+    if waves.dtype == np.int16:
+        is_f32 = 0
+    elif waves.dtype == np.float32:
+        is_f32 = 1
+    else:
+        raise ValueError(f"waveform samples must be int16 or float32, got {waves.dtype}")
+    n_w, L = waves.shape
+    # first row whose record_id matches (np.flatnonzero(...)[0], waveform_width.py:165-168)
+    rids = np.asarray(wave_record_ids, dtype=np.int64)
+    uniq, first = np.unique(rids, return_index=True)
+    h_rid = hits["record_id"].astype(np.int64)
+    loc = np.searchsorted(uniq, h_rid)
+    loc_c = np.minimum(loc, len(uniq) - 1)
+    hit_row = np.where(uniq[loc_c] == h_rid, first[loc_c], -1).astype(np.int64)
+    d_w = _dev(np.ascontiguousarray(waves).reshape(-1))
+    p = _lib.WidthParams(float(rise_low), float(rise_high), float(fall_high), float(fall_low), float(sampling_rate),
+                         1 if interpolation else 0, is_f32)
+    names = hits.dtype.names
+    d_row, d_pos = _dev(hit_row), _dev(hits["position"].astype(np.int64))
+    d_ts, d_rid = _dev(hits["timestamp"].astype(np.int64)), _dev(h_rid)
+    d_b = _dev(hits["board"].astype(np.int16)) if "board" in names else None
+    d_c = _dev(hits["channel"].astype(np.int16))
+    out = _empty(nh * 56)
+    valid = _empty(nh)
+    _lib.check(lib.wfb_waveform_width(_ptr(d_w), n_w, L, L, _ptr(d_row), _ptr(d_pos), _ptr(d_ts), _ptr(d_b), _ptr(d_c), _ptr(d_rid), nh,
+                                      C.byref(p), _ptr(out), _ptr(valid), _stream()), "wfb_waveform_width")
+    rows = out[: nh * 56].cpu().numpy().view(WAVEFORM_WIDTH_DTYPE)
+    keep = valid[:nh].cpu().numpy().astype(bool)
+    return rows[keep].copy()
+
+
+def width_integral(records: np.ndarray, pool: np.ndarray, *, q_low=0.10, q_high=0.90, sampling_rate=0.5, dt=None,
+                   run: DeviceRun | None = None) -> np.ndarray:
+    """Per-record cumulative-charge quantile widths (waveform_width_integral.py:83-231)."""
+    lib = _lib.load()
+    if dt is None:
+        if sampling_rate <= 0:
+            raise ValueError(f"sampling_rate ({sampling_rate}) must be > 0")
+        dt = 1.0 / float(sampling_rate)
+    if q_low <= 0 or q_high >= 1 or q_low >= q_high:
+        raise ValueError(f"q_low/q_high invalid: q_low={q_low}, q_high={q_high}")
+    n = len(records)
+    if n == 0:
+        return np.zeros(0, dtype=WAVEFORM_WIDTH_INTEGRAL_DTYPE)
+    if run is None:
+        run = DeviceRun.from_host(records, pool, explicit_dt=1)
+    out = _empty(n * 52)
+    _lib.check(lib.wfb_width_integral(_ptr(run.pool), run.pool_is_f32, run.pool_len, _ptr(run.meta), n, float(q_low), float(q_high),
+                                      float(dt), run.pool_base, run.row_base, _ptr(out), _stream()), "wfb_width_integral")
+    return out[: n * 52].cpu().numpy().view(WAVEFORM_WIDTH_INTEGRAL_DTYPE)
+
+
+# --------------------------------------------------------------------------------------------
+# K4: grouping
+# --------------------------------------------------------------------------------------------
+
+
+def group_hit_windows(hits: np.ndarray, time_window_ns: float) -> dict:
+    """Chain clustering of absolute hit windows (event_grouping.py:287-471) for rows with valid
+    sample windows.  The sort, running maximum, boundary flags and event ids are computed on the
+    device; the per-event member ordering (a small lexsort) and the ragged packaging stay on the
+    host.  Returns the same dict as the oracle."""
+    lib = _lib.load()
+    torch = _torch()
+    if time_window_ns < 0:
+        raise ValueError("time_window_ns must be >= 0")
+    names = hits.dtype.names
+    sn, en = ("sample_start", "sample_end") if "sample_start" in names else ("edge_start", "edge_end")
+    nh = len(hits)
+    if nh == 0:
+        z = np.zeros(0, dtype=np.int64)
+        return dict(event_id=z, t_min=z, t_max=z, dt_ns=np.zeros(0), n_hits=z, offsets=np.zeros(1, np.int64), members=z, event_of_hit=z)
+    d_ts, d_pos = _dev(hits["timestamp"].astype(np.int64)), _dev(hits["position"].astype(np.int64))
+    d_s, d_e = _dev(hits[sn].astype(np.int32)), _dev(hits[en].astype(np.int32))
+    d_dt, d_rid = _dev(hits["dt"].astype(np.int32)), _dev(hits["record_id"].astype(np.int64))
+    order = torch.empty(nh, dtype=torch.int64, device="cuda")
+    ev = torch.empty(nh, dtype=torch.int64, device="cuda")
+    a0 = torch.empty(nh, dtype=torch.float64, device="cuda")
+    a1 = torch.empty(nh, dtype=torch.float64, device="cuda")
+    n_ev = torch.zeros(1, dtype=torch.int64, device="cuda")
+    ws = _empty(lib.wfb_group_workspace_bytes(nh))
+    _lib.check(lib.wfb_group_hit_windows(_ptr(d_ts), _ptr(d_pos), _ptr(d_s), _ptr(d_e), _ptr(d_dt), _ptr(d_rid), nh, float(time_window_ns),
+                                         _ptr(order), _ptr(ev), _ptr(a0), _ptr(a1), _ptr(n_ev), _ptr(ws), ws.numel(), _stream()),
+               "wfb_group_hit_windows")
+    event_of_hit = ev.cpu().numpy()
+    abs0, abs1 = a0.cpu().numpy(), a1.cpu().numpy()
+    n_events = int(n_ev.item())
+    morder = np.lexsort((hits["record_id"].astype(np.int64), hits["timestamp"].astype(np.int64), abs0, hits["dt"].astype(np.int32),
+                         hits["channel"].astype(np.int16), hits["board"].astype(np.int16), event_of_hit))
+    counts = np.bincount(event_of_hit, minlength=n_events)
+    offsets = np.zeros(n_events + 1, dtype=np.int64)
+    np.cumsum(counts, out=offsets[1:])
+    tmin = np.full(n_events, np.inf)
+    tmax = np.full(n_events, -np.inf)
+    np.minimum.at(tmin, event_of_hit, abs0)
+    np.maximum.at(tmax, event_of_hit, abs1)
+    t_min, t_max = tmin.astype(np.int64), tmax.astype(np.int64)
+    return dict(event_id=np.arange(n_events, dtype=np.int64), t_min=t_min, t_max=t_max, dt_ns=(t_max - t_min) / 1e3,
+                n_hits=counts.astype(np.int64), offsets=offsets, members=morder.astype(np.int64), event_of_hit=event_of_hit,
+                order=order.cpu().numpy())
+
+
+def group_time_window(timestamps: np.ndarray, channels: np.ndarray, time_window_ns: float) -> dict:
+    """Anchored fixed-window clustering (event_grouping.py:99-283, 477-510): device time sort +
+    anchor search + event ids; member ordering by channel on the host."""
+    lib = _lib.load()
+    torch = _torch()
+    ts_in = np.asarray(timestamps, dtype=np.int64)
+    n = len(ts_in)
+    if n == 0:
+        z = np.zeros(0, dtype=np.int64)
+        return dict(event_id=z, t_min=z, t_max=z, dt_ns=np.zeros(0), n_hits=z, offsets=np.zeros(1, np.int64), members=z)
+    ts_sorted, order = sort_pairs(ts_in, np.arange(n, dtype=np.int64))
+    d_ts = _dev(ts_sorted)
+    ev = torch.empty(n, dtype=torch.int64, device="cuda")
+    n_ev = torch.zeros(1, dtype=torch.int64, device="cuda")
+    ws = _empty(lib.wfb_group_workspace_bytes(n))
+    _lib.check(lib.wfb_group_time_window(_ptr(d_ts), n, float(time_window_ns), _ptr(ev), _ptr(n_ev), _ptr(ws), ws.numel(), _stream()),
+               "wfb_group_time_window")
+    ev_sorted = ev.cpu().numpy()
+    n_events = int(n_ev.item())
+    ch = np.asarray(channels)[order]
+    inner = np.lexsort((np.arange(n), ch, ev_sorted))  # by event, then channel (stable)
+    members = order[inner]
+    counts = np.bincount(ev_sorted, minlength=n_events)
+    offsets = np.zeros(n_events + 1, dtype=np.int64)
+    np.cumsum(counts, out=offsets[1:])
+    ts_m = ts_in[members]
+    t_min, t_max = ts_m[offsets[:-1]], ts_m[offsets[1:] - 1]
+    return dict(event_id=np.arange(n_events, dtype=np.int64), t_min=t_min, t_max=t_max, dt_ns=(t_max - t_min) / 1e3,
+                n_hits=counts.astype(np.int64), offsets=offsets, members=members)
+
+
+# --------------------------------------------------------------------------------------------
+# hit_merge (hit_merge.py:115-181, 256-322): ordering on the device, chain on the host-free path
+# --------------------------------------------------------------------------------------------
+
+
+def hit_merge_default(hits: np.ndarray):
+    """merge_gap_ns <= 0 (the default): every hit is its own cluster, rows regrouped by
+    (board, channel) and ordered by absolute window start (stable).  Device sorts."""
+    nh = len(hits)
+    if nh == 0:
+        return (np.zeros(0, dtype=HIT_MERGE_CLUSTERS_DTYPE), np.zeros(0, dtype=HIT_MERGED_DTYPE),
+                np.zeros(0, dtype=HIT_MERGED_COMPONENTS_DTYPE))
+    ts = hits["timestamp"].astype(np.float64)
+    a0 = ts + (hits["edge_start"].astype(np.float64) - hits["position"].astype(np.float64)) * (hits["dt"].astype(np.float64) * 1e3)
+    # float64 keys -> order-preserving int64 (abs_start >= 0 for real data; general mapping kept)
+    bits = a0.view(np.int64)
+    keys = np.where(bits >= 0, bits, np.int64(-(2**63)) - bits - 1 + 0)  # negative floats reversed
+    _, o1 = sort_pairs(keys, np.arange(nh, dtype=np.int64))
+    ck = hits["board"].astype(np.int64)[o1] * 65536 + (hits["channel"].astype(np.int64)[o1] + 32768)
+    _, order = sort_pairs(ck, o1)
+    clusters = np.zeros(nh, dtype=HIT_MERGE_CLUSTERS_DTYPE)
+    clusters["cluster_index"] = np.arange(nh)
+    clusters["hit_index"] = order
+    merged = np.zeros(nh, dtype=HIT_MERGED_DTYPE)
+    h = hits[order]
+    for f_out, f_in in (("position", "position"), ("height", "height"), ("integral", "integral"), ("sample_start", "edge_start"),
+                        ("sample_end", "edge_end"), ("width", "width"), ("dt", "dt"), ("rise_time", "rise_time"),
+                        ("fall_time", "fall_time"), ("timestamp", "timestamp"), ("board", "board"), ("channel", "channel"),
+                        ("record_id", "record_id")):
+        merged[f_out] = h[f_in]
+    merged["component_offset"] = np.arange(nh)
+    merged["component_count"] = 1
+    comps = np.zeros(nh, dtype=HIT_MERGED_COMPONENTS_DTYPE)
+    comps["merged_index"] = np.arange(nh)
+    comps["hit_index"] = order
+    return clusters, merged, comps

@@ -38,6 +38,8 @@ extern "C" {
 #define WFB_POL_UNKNOWN 0
 #define WFB_POL_POSITIVE 1
 #define WFB_POL_NEGATIVE 2
+#define WFB_POL_RAW_POSITIVE 3 /* positive pulses, raw float64 arithmetic (st_waveforms branch of
+                                   basic_features.py:241-262; records polarity tag "rawpos") */
 
 #define WFB_DO_FEATURES 1
 #define WFB_DO_HITS 2
@@ -88,6 +90,8 @@ typedef struct wfb_fh_params {
     const wfb_chan_rule* rules_dev; /* n_rules entries on the device, may be NULL */
     int64_t pool_base;  /* sample index of pool_dev[0] inside the run's wave_pool */
     int64_t row_base;   /* event_index of the first record passed (basic_features.py:194) */
+    int32_t signed_samples; /* 1: the 16-bit samples are int16 (st_waveforms rows), not uint16 */
+    int32_t reserved_;
 } wfb_fh_params;
 
 const char* wfb_last_error(void);

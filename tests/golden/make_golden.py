@@ -226,6 +226,38 @@ def main(out_dir=HERE):
             G[f"{tag}_timestamps"] = np.concatenate([np.asarray(v, np.int64) for v in ev["timestamps"]])
             G[f"{tag}_channels"] = np.concatenate([np.asarray(v, np.int64) for v in ev["channels"]])
 
+    # ---------------------------------------------------------------- st_waveforms / filtered_waveforms sources
+    from unittest.mock import patch
+
+    st_small = st_from_records(records[:300], pool[: 300 * 800], create_record_dtype)
+    G["st_bf_default"] = run(BasicFeaturesPlugin(), {"st_waveforms": st_small}, {})
+    st_pos = st_small.copy()
+    st_pos["polarity"][::2] = "positive"
+    st_pos["polarity"][1::4] = "negative"
+    G["st_polarity"] = st_pos["polarity"]
+    G["st_bf_polarity"] = run(BasicFeaturesPlugin(), {"st_waveforms": st_pos}, {"height_range": (0, None), "area_range": (10, 700),
+                                                                             "channel_config": {"channels": {"0:2": {"fixed_baseline": 8011.25}}}})
+    st_neg = st_pos.copy()
+    st_neg["wave"] = st_neg["wave"] - 9000  # genuinely negative int16 samples
+    st_neg["baseline"] = st_neg["baseline"] - 9000
+    G["st_neg_bf"] = run(BasicFeaturesPlugin(), {"st_waveforms": st_neg}, {"height_range": (0, None)})
+
+    def st_hits(stw, cfg):
+        bundle = rb.build_records_from_st_waveforms(stw, default_dt_ns=2)
+        with patch("waveform_analysis.core.plugins.builtin.cpu.records.get_records_bundle", return_value=bundle):
+            return run(ThresholdHitPlugin(), {"st_waveforms": stw}, cfg)
+
+    G["st_hits"] = st_hits(st_pos, {"threshold": 15.0})
+    G["st_neg_hits"] = st_hits(st_neg, {"threshold": 15.0, "left_extension": 4, "right_extension": 1})
+    G["st_wint"] = run(WaveformWidthIntegralPlugin(), {"st_waveforms": st_pos}, {})
+    stf_small = np.zeros(len(st_small), dtype=create_filtered_waveform_dtype(st_small.dtype))
+    for f in st_small.dtype.names:
+        if f != "wave":
+            stf_small[f] = st_pos[f]
+    stf_small["wave"] = run(WavePoolFilteredPlugin(), {"records": records[:300], "wave_pool": pool[: 300 * 800]}, {"max_workers": 1}).reshape(300, 800)
+    G["stf_wave"] = stf_small["wave"]
+    G["stf_bf"] = run(BasicFeaturesPlugin(), {"filtered_waveforms": stf_small}, {"use_filtered": True})
+
     out = os.path.join(out_dir, "hotpath_golden.npz")
     np.savez_compressed(out, **G)
     print("wrote", out, "keys:", len(G), "size MB:", os.path.getsize(out) / 1e6)

@@ -38,7 +38,7 @@ def test_struct_layouts_match_header():
 
     assert C.sizeof(_lib.RecMeta) == 48 and _lib.RecMeta.record_id.offset == 40
     assert C.sizeof(_lib.ChanRule) == 32
-    assert _lib.FHParams.rules_dev.offset == 64 and C.sizeof(_lib.FHParams) == 88
+    assert _lib.FHParams.rules_dev.offset == 64 and C.sizeof(_lib.FHParams) == 96
     assert C.sizeof(_lib.FilterCfg) == 16 + 16 * 6 * 8 + 16 * 2 * 8
 
 

@@ -1,0 +1,166 @@
+"""GPU: the drop-in plugins' compute() (the reference-facing boundary) against the golden vectors
+produced by the reference's own plugins with the same configs (tests/golden/make_golden.py)."""
+
+import numpy as np
+import pytest
+
+from conftest import assert_rows_match
+from fakes import Ctx
+
+pytestmark = pytest.mark.gpu
+
+FX_BF = ("height", "amp", "max_abs_diff")
+FX_HIT = ("height", "width", "rise_time", "fall_time")
+
+
+@pytest.fixture(scope="module")
+def P():
+    from waveformanalysis_b200 import plugins
+
+    return plugins
+
+
+def run(plugin, data, config=None):
+    return plugin.compute(Ctx(config, data), "run")
+
+
+def st_from_records(records, pool, L=800):
+    from waveformanalysis_b200.dtypes import create_record_dtype
+
+    st = np.zeros(len(records), dtype=create_record_dtype(L))
+    for f in ("baseline", "baseline_upstream", "polarity", "timestamp", "record_id", "dt", "event_length", "board", "channel"):
+        st[f] = records[f]
+    st["wave"] = pool.reshape(len(records), L).view(np.int16)
+    return st
+
+
+def test_basic_features_plugin_records_source(P, golden):
+    base = {"records": golden["records"], "wave_pool": golden["wave_pool"]}
+    assert_rows_match(run(P.B200BasicFeaturesPlugin(), base, {"wave_source": "records"}), golden["bf_default"], what="bf", float_exact=FX_BF)
+    out = run(P.B200BasicFeaturesPlugin(), base, {"wave_source": "records", "channel_config": {"channels": {"0:1": {"fixed_baseline": 8000.5}, "0:3": {"fixed_baseline": 7990.0}}}})
+    assert_rows_match(out, golden["bf_fixed"], what="bf_fixed", float_exact=FX_BF)
+    fsg = {"records": golden["filt_records"], "wave_pool": golden["filt_pool"], "wave_pool_filtered": golden["filt_sg"]}
+    assert_rows_match(run(P.B200BasicFeaturesPlugin(), fsg, {"wave_source": "records", "use_filtered": True}), golden["filt_bf"], what="filt_bf")
+
+
+def test_threshold_hit_plugin_records_source(P, golden):
+    base = {"records": golden["records"], "wave_pool": golden["wave_pool"]}
+    assert_rows_match(run(P.B200ThresholdHitPlugin(), base, {"wave_source": "records", "threshold": 15.0}), golden["hits_thr15"], what="thr15", float_exact=FX_HIT)
+    cfg = {"wave_source": "records", "threshold": 12.0, "left_extension": 5, "right_extension": 0, "channel_config": {"channels": {"0:2": {"threshold": 40.0}}}}
+    assert_rows_match(run(P.B200ThresholdHitPlugin(), base, cfg), golden["hits_chan"], what="chan", float_exact=FX_HIT)
+    with pytest.raises(ValueError, match="Invalid channel key"):
+        run(P.B200ThresholdHitPlugin(), base, {"wave_source": "records", "channel_config": {"run": {"1": {"threshold": 5.0}}}})
+    assert len(run(P.B200ThresholdHitPlugin(), {"records": golden["records"][:0], "wave_pool": golden["wave_pool"][:0]}, {"wave_source": "records"})) == 0
+
+
+def test_structured_waveform_sources(P, golden):
+    """wave_source='auto' (the reference default): st_waveforms / filtered_waveforms rows are used in
+    place as the sample pool, including genuinely negative int16 samples."""
+    rec, pool = golden["records"][:300], golden["wave_pool"][: 300 * 800]
+    st = st_from_records(rec, pool)
+    assert_rows_match(run(P.B200BasicFeaturesPlugin(), {"st_waveforms": st}, {}), golden["st_bf_default"], what="st_bf", float_exact=FX_BF)
+    st_pos = st.copy()
+    st_pos["polarity"] = golden["st_polarity"]
+    cfg = {"height_range": (0, None), "area_range": (10, 700), "channel_config": {"channels": {"0:2": {"fixed_baseline": 8011.25}}}}
+    assert_rows_match(run(P.B200BasicFeaturesPlugin(), {"st_waveforms": st_pos}, cfg), golden["st_bf_polarity"], what="st_bf_pol", float_exact=FX_BF)
+    st_neg = st_pos.copy()
+    st_neg["wave"] = st_neg["wave"] - 9000
+    st_neg["baseline"] = st_neg["baseline"] - 9000
+    assert_rows_match(run(P.B200BasicFeaturesPlugin(), {"st_waveforms": st_neg}, {"height_range": (0, None)}), golden["st_neg_bf"], what="st_neg_bf", float_exact=FX_BF)
+    assert_rows_match(run(P.B200ThresholdHitPlugin(), {"st_waveforms": st_pos}, {"threshold": 15.0}), golden["st_hits"], what="st_hits", float_exact=FX_HIT)
+    assert_rows_match(run(P.B200ThresholdHitPlugin(), {"st_waveforms": st_neg}, {"threshold": 15.0, "left_extension": 4, "right_extension": 1}),
+                      golden["st_neg_hits"], what="st_neg_hits", float_exact=FX_HIT)
+    assert_rows_match(run(P.B200WaveformWidthIntegralPlugin(), {"st_waveforms": st_pos}, {}), golden["st_wint"], what="st_wint")
+    from waveformanalysis_b200.dtypes import create_record_dtype
+
+    stf = np.zeros(len(st), dtype=[(n, (np.float32, (800,)) if n == "wave" else create_record_dtype(800)[n]) for n in create_record_dtype(800).names])
+    for f in st.dtype.names:
+        if f != "wave":
+            stf[f] = st_pos[f]
+    stf["wave"] = golden["stf_wave"]
+    assert_rows_match(run(P.B200BasicFeaturesPlugin(), {"filtered_waveforms": stf}, {"use_filtered": True}), golden["stf_bf"], what="stf_bf")
+
+
+def test_wave_pool_filtered_plugin(P, golden):
+    fbase = {"records": golden["filt_records"], "wave_pool": golden["filt_pool"]}
+    assert np.allclose(run(P.B200WavePoolFilteredPlugin(), fbase, {}), golden["filt_sg"], rtol=1e-5, atol=1e-3)
+    bw = {"filter_type": "BW", "lowcut": 0.01, "highcut": 0.1, "fs": 0.5, "filter_order": 4}
+    assert np.array_equal(run(P.B200WavePoolFilteredPlugin(), fbase, bw), golden["filt_bw"])
+    mixed = {"channel_config": {"channels": {"0:1": {"filter_type": "BW", "lowcut": 0.02, "highcut": 0.2, "fs": 1.0, "filter_order": 2}}}}
+    assert np.allclose(run(P.B200WavePoolFilteredPlugin(), fbase, mixed), golden["filt_mixed"], rtol=1e-5, atol=1e-3)
+    with pytest.raises(ValueError):  # the reference's default BW options are invalid (highcut >= fs/2), filtering.py:98-99
+        run(P.B200WavePoolFilteredPlugin(), fbase, {"filter_type": "BW"})
+    with pytest.raises(ValueError):
+        run(P.B200WavePoolFilteredPlugin(), fbase, {"filter_type": "XX"})
+
+
+def test_width_plugins(P, golden):
+    rec, pool, hits = golden["ww_records"], golden["ww_pool"], golden["ww_hit"]
+    st = st_from_records(rec, pool)
+    fx = ("rise_time", "fall_time", "total_width", "rise_time_samples", "fall_time_samples", "total_width_samples", "peak_height")
+    assert_rows_match(run(P.B200WaveformWidthPlugin(), {"hit": hits, "st_waveforms": st}, {}), golden["ww_default"], what="ww", float_exact=fx)
+    cfg = {"rise_low": 0.1, "rise_high": 0.5, "fall_high": 0.5, "fall_low": 0.1, "sampling_rate": 0.25}
+    assert_rows_match(run(P.B200WaveformWidthPlugin(), {"hit": hits, "st_waveforms": st}, cfg), golden["ww_50"], what="ww50", float_exact=fx)
+    base = {"records": golden["records"][:200], "wave_pool": golden["wave_pool"]}
+    fxi = ("t_low", "t_high", "width", "t_low_samples", "t_high_samples", "width_samples", "q_total")
+    assert_rows_match(run(P.B200WaveformWidthIntegralPlugin(), base, {"wave_source": "records"}), golden["wint_default"], what="wint", float_exact=fxi)
+
+
+def test_merge_and_grouping_plugins(P, golden):
+    h = golden["hits_thr15"]
+    ctx = Ctx({}, {"hit_threshold": h}, plugins={"hit_merged": P.B200HitMergePlugin()})
+    cl = P.B200HitMergeClustersPlugin().compute(ctx, "run")
+    ctx._set_data("run", "hit_merge_clusters", cl)
+    mg = P.B200HitMergePlugin().compute(ctx, "run")
+    ctx._set_data("run", "hit_merged", mg)
+    cp = P.B200HitMergedComponentsPlugin().compute(ctx, "run")
+    ctx._set_data("run", "hit_merged_components", cp)
+    assert_rows_match(cl, golden["m0_clusters"], what="clusters")
+    assert_rows_match(mg, golden["m0_merged"], what="merged", float_exact=("height", "integral", "width", "rise_time", "fall_time"))
+    assert_rows_match(cp, golden["m0_components"], what="components")
+    with pytest.raises(NotImplementedError):
+        P.B200HitMergePlugin().compute(Ctx({"merge_gap_ns": 50.0}, {"hit_threshold": h}), "run")
+    for wname, w in (("w100", 100.0), ("w0", 0.0)):
+        ctx.config = {"time_window_ns": w}
+        df = P.B200HitGroupedPlugin().compute(ctx, "run")
+        assert list(df.columns) == ["event_id", "t_min", "t_max", "dt/ns", "n_hits", "dt", "boards", "channels", "heights", "integrals",
+                                    "timestamps", "record_ids", "sample_starts", "sample_ends"]
+        assert np.array_equal(df["t_min"].to_numpy(), golden[f"hg_{wname}_t_min"])
+        assert np.array_equal(df["t_max"].to_numpy(), golden[f"hg_{wname}_t_max"])
+        assert np.array_equal(df["n_hits"].to_numpy(), golden[f"hg_{wname}_n_hits"])
+        assert np.array_equal(df["dt/ns"].to_numpy(), golden[f"hg_{wname}_dt_ns"])
+        assert np.array_equal(np.concatenate(list(df["record_ids"])), golden[f"hg_{wname}_record_ids"])
+        assert np.array_equal(np.concatenate(list(df["channels"])), golden[f"hg_{wname}_channels"])
+    empty = P.B200HitGroupedPlugin().compute(Ctx({}, {"hit_merged": mg[:0], "hit_merged_components": cp[:0], "hit_threshold": h[:0]}), "run")
+    assert empty.empty and len(empty.columns) == 14
+
+
+def test_df_events_plugin(P, golden):
+    import pandas as pd
+
+    bf = golden["bf_default"]
+    df = pd.DataFrame({"timestamp": bf["timestamp"], "channel": bf["channel"], "area": bf["area"], "height": bf["height"]})
+    ev = P.B200GroupedEventsPlugin().compute(Ctx({"time_window_ns": 100.0}, {"df": df}), "run")
+    assert np.array_equal(ev["t_min"].to_numpy(), golden["ge_w100_nb_t_min"])
+    assert np.array_equal(ev["t_max"].to_numpy(), golden["ge_w100_nb_t_max"])
+    assert np.array_equal(ev["n_hits"].to_numpy(), golden["ge_w100_nb_n_hits"])
+    assert np.array_equal(np.concatenate(list(ev["timestamps"])), golden["ge_w100_nb_timestamps"])
+
+
+def test_records_plugins_from_raw_arrays(P, golden):
+    """records / wave_pool from per-channel raw rows (VX2730 column layout: board, channel, timestamp
+    at 0..2, samples from column 7), the arrays the reference's readers hand to the builder."""
+    raws = []
+    for c in range(4):
+        sel = golden["raw_channels"] == c
+        arr = np.zeros((int(sel.sum()), 7 + 800), dtype=np.int64)
+        arr[:, 0], arr[:, 1], arr[:, 2] = golden["raw_boards"][sel], c, golden["raw_timestamps_ps"][sel]
+        arr[:, 7:] = golden["raw_samples"][sel]
+        raws.append(arr)
+    ctx = Ctx({"dt": 2}, {"raw_arrays": raws})
+    rec = P.B200RecordsPlugin().compute(ctx, "run")
+    pool = P.B200WavePoolPlugin().compute(ctx, "run")
+    want = golden["records"]
+    for name in want.dtype.names:
+        assert np.array_equal(rec[name], want[name], equal_nan=(want[name].dtype.kind == "f")), name
+    assert np.array_equal(pool, golden["wave_pool"])

@@ -1,0 +1,178 @@
+"""CPU: the B200 plugins expose the reference's plugin contract (names, versions, dtypes, options,
+dynamic dependencies) and the host-side helpers resolve configs exactly like the reference.
+Comparisons against the live reference run when /root/reference is present (build container)."""
+
+import os
+import sys
+from unittest.mock import MagicMock
+
+import numpy as np
+import pytest
+
+from fakes import Ctx
+
+REF = os.environ.get("WFB_REFERENCE_ROOT", "/root/reference")
+HAVE_REF = os.path.isdir(os.path.join(REF, "waveform_analysis"))
+
+
+def _import_ref():
+    for mod in ("matplotlib", "matplotlib.pyplot", "matplotlib.patches", "matplotlib.colors", "matplotlib.figure",
+                "matplotlib.axes", "matplotlib.gridspec", "matplotlib.lines", "matplotlib.collections", "matplotlib.cm",
+                "matplotlib.ticker", "matplotlib.dates"):
+        sys.modules.setdefault(mod, MagicMock())
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import waveform_analysis  # noqa: F401
+
+
+def test_profile_provides_the_hot_path_names():
+    from waveformanalysis_b200 import profiles
+
+    names = [p.provides for p in profiles.b200_default()]
+    assert names == ["records", "wave_pool", "wave_pool_filtered", "basic_features", "hit_threshold", "waveform_width",
+                     "waveform_width_integral", "hit_merge_clusters", "hit_merged", "hit_merged_components", "hit_grouped",
+                     "df_events"]
+    for p in profiles.b200_default():
+        assert callable(p.compute) and isinstance(p.options, dict) and p.version
+
+
+def test_dynamic_dependencies_follow_wave_source():
+    from waveformanalysis_b200.plugins import B200BasicFeaturesPlugin, B200ThresholdHitPlugin, B200WaveformWidthPlugin
+
+    p = B200ThresholdHitPlugin()
+    assert p.resolve_depends_on(Ctx({"wave_source": "records", "use_filtered": True})) == ["records", "wave_pool_filtered"]
+    assert p.resolve_depends_on(Ctx({"wave_source": "records"})) == ["records", "wave_pool"]
+    assert p.resolve_depends_on(Ctx({})) == ["st_waveforms"]
+    assert B200BasicFeaturesPlugin().resolve_depends_on(Ctx({"use_filtered": True})) == ["filtered_waveforms"]
+    assert B200WaveformWidthPlugin().resolve_depends_on(Ctx({"use_filtered": True})) == ["hit", "filtered_waveforms"]
+    with pytest.raises(ValueError, match="Invalid wave_source"):
+        p.resolve_depends_on(Ctx({"wave_source": "nope"}))
+
+
+def test_channel_config_layers_and_errors():
+    from waveformanalysis_b200.channel_config import per_channel_option, resolve_channel_values
+
+    cfg = {"defaults": {"threshold": 7.0}, "groups": {"g": {"channels": ["0:1", (0, 2)], "config": {"threshold": 8.0}}},
+           "channels": {"0:2": {"threshold": 9.0}}}
+    assert resolve_channel_values(cfg, "run", 0, 0, {"threshold": 10.0})["threshold"] == 7.0
+    assert resolve_channel_values(cfg, "run", 0, 1, {"threshold": 10.0})["threshold"] == 8.0
+    assert resolve_channel_values(cfg, "run", 0, 2, {"threshold": 10.0})["threshold"] == 9.0
+    per_run = {"run": {"0:0": {"threshold": 25.0}}, "other": {"0:0": {"threshold": 1.0}}}
+    assert resolve_channel_values(per_run, "run", 0, 0, {"threshold": 10.0})["threshold"] == 25.0
+    with pytest.raises(ValueError, match="Invalid channel key"):
+        resolve_channel_values({"run": {"1": {"threshold": 5.0}}}, "run", 0, 1, {})
+    got = per_channel_option(cfg, "run", np.array([0, 0, 1]), np.array([1, 2, 1]), "threshold", 10.0)
+    assert got == {(0, 1): 8.0, (0, 2): 9.0, (1, 1): 7.0}
+
+
+def test_structured_rows_as_pool_without_repacking():
+    from waveformanalysis_b200.aos import structured_as_records
+    from waveformanalysis_b200.dtypes import create_record_dtype
+
+    st = np.zeros(5, dtype=create_record_dtype(37))
+    st["wave"] = np.arange(5 * 37).reshape(5, 37) - 40
+    st["polarity"] = ["positive", "negative", "unknown", "", "positive"]
+    rec, pool, signed = structured_as_records(st, raw_polarity=True)
+    assert signed and pool.dtype == np.uint16 and np.shares_memory(pool, st)
+    for i in range(5):
+        o = int(rec["wave_offset"][i])
+        assert np.array_equal(pool[o : o + 37].view(np.int16), st["wave"][i])
+    assert rec["polarity"].tolist() == ["rawpos", "unknown", "unknown", "unknown", "rawpos"]
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference checkout not available")
+def test_contract_matches_reference_plugins():
+    _import_ref()
+    from waveform_analysis.core.plugins.builtin.cpu import basic_features, event_analysis, hit_finder, hit_merge, records, waveform_width, waveform_width_integral
+
+    from waveformanalysis_b200 import plugins as P
+
+    pairs = [
+        (P.B200BasicFeaturesPlugin, basic_features.BasicFeaturesPlugin),
+        (P.B200ThresholdHitPlugin, hit_finder.ThresholdHitPlugin),
+        (P.B200WavePoolFilteredPlugin, records.WavePoolFilteredPlugin),
+        (P.B200WaveformWidthPlugin, waveform_width.WaveformWidthPlugin),
+        (P.B200WaveformWidthIntegralPlugin, waveform_width_integral.WaveformWidthIntegralPlugin),
+        (P.B200HitMergeClustersPlugin, hit_merge.HitMergeClustersPlugin),
+        (P.B200HitMergePlugin, hit_merge.HitMergePlugin),
+        (P.B200HitMergedComponentsPlugin, hit_merge.HitMergedComponentsPlugin),
+        (P.B200HitGroupedPlugin, event_analysis.HitGroupedPlugin),
+        (P.B200GroupedEventsPlugin, event_analysis.GroupedEventsPlugin),
+        (P.B200RecordsPlugin, records.RecordsPlugin),
+        (P.B200WavePoolPlugin, records.WavePoolPlugin),
+    ]
+    for ours, ref in pairs:
+        assert ours.provides == ref.provides
+        assert ours.version == ref.version, ours.provides
+        assert ours.save_when == ref.save_when, ours.provides
+        assert list(ours.depends_on) == list(ref.depends_on), ours.provides
+        if ref.output_dtype is not None:
+            assert np.dtype(ours.output_dtype) == np.dtype(ref.output_dtype), ours.provides
+        assert set(ours.options) == set(ref.options), (ours.provides, set(ours.options) ^ set(ref.options))
+        for k, opt in ref.options.items():
+            assert ours.options[k].default == opt.default, (ours.provides, k)
+            assert ours.options[k].type == opt.type, (ours.provides, k)
+            assert getattr(ours.options[k], "track", True) == getattr(opt, "track", True), (ours.provides, k)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference checkout not available")
+def test_channel_config_matches_reference_resolution():
+    _import_ref()
+    from waveform_analysis.core.hardware.channel import resolve_effective_channel_config
+
+    from waveformanalysis_b200.channel_config import resolve_channel_values
+
+    cfgs = [
+        None,
+        {"channels": {"0:1": {"threshold": 5.0}}},
+        {"0:1": {"threshold": 5.0}, (1, 2): {"threshold": 6.0}},
+        {"run": {"defaults": {"threshold": 3.0}, "groups": [{"channels": ["1:2"], "config": {"threshold": 4.0}}]}},
+        {"defaults": {"fixed_baseline": 1.0}, "groups": {"a": {"channels": [(0, 0)], "config": {"fixed_baseline": 2.0}}},
+         "channels": {"0:0": {"fixed_baseline": 3.0}}},
+    ]
+    for cfg in cfgs:
+        for b, c in ((0, 0), (0, 1), (1, 2)):
+            want = resolve_effective_channel_config(context=None, plugin=None, run_id="run", board=b, channel=c,
+                                                    base_values={"threshold": 10.0, "fixed_baseline": None}, channel_config=cfg).values
+            got = resolve_channel_values(cfg, "run", b, c, {"threshold": 10.0, "fixed_baseline": None})
+            assert got == want, (cfg, b, c)
+
+
+REAL_CONTEXT_SCRIPT = r"""
+import sys
+from unittest.mock import MagicMock
+for mod in ("matplotlib", "matplotlib.pyplot", "matplotlib.patches", "matplotlib.colors", "matplotlib.figure", "matplotlib.axes",
+            "matplotlib.gridspec", "matplotlib.lines", "matplotlib.collections", "matplotlib.cm", "matplotlib.ticker", "matplotlib.dates"):
+    sys.modules.setdefault(mod, MagicMock())
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[2])
+from waveform_analysis.core.context import Context
+from waveform_analysis.core.plugins import profiles as ref_profiles
+from waveform_analysis.core.plugins.core.base import Plugin
+from waveformanalysis_b200 import plugin_api, profiles
+assert plugin_api.HAVE_REFERENCE and plugin_api.Plugin is Plugin
+ctx = Context(storage_dir=sys.argv[3])
+ctx.register(*ref_profiles.cpu_default())
+for p in profiles.b200_default():
+    assert isinstance(p, Plugin)
+    ctx.register(p, allow_override=True)
+assert type(ctx._plugins["basic_features"]).__name__ == "B200BasicFeaturesPlugin"
+ctx.set_config({"wave_source": "records"}, plugin_name="basic_features")
+lineage = ctx.get_lineage("basic_features")
+assert lineage["plugin_class"] == "B200BasicFeaturesPlugin", lineage
+assert set(lineage["depends_on"]) == {"records", "wave_pool"}, lineage
+ctx.set_config({"wave_source": "records", "use_filtered": True}, plugin_name="hit_threshold")
+assert set(ctx.get_lineage("hit_threshold")["depends_on"]) == {"records", "wave_pool_filtered"}
+print("REAL_CONTEXT_OK")
+"""
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference checkout not available")
+def test_registers_in_a_real_context(tmp_path):
+    """ctx.register(..., allow_override=True) swaps the provider and changes the lineage class
+    (core/context.py:532-621, core/foundation/mixins.py:80-107).  Runs in a fresh interpreter so that
+    the B200 plugins pick up the reference's own Plugin / Option base classes."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-c", REAL_CONTEXT_SCRIPT, root, REF, str(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert "REAL_CONTEXT_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-3000:]

@@ -75,6 +75,8 @@ class FHParams(C.Structure):
         ("rules_dev", C.c_void_p),
         ("pool_base", C.c_int64),
         ("row_base", C.c_int64),
+        ("signed_samples", C.c_int32),
+        ("reserved_", C.c_int32),
     ]
 
 

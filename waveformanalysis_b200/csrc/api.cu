@@ -65,7 +65,12 @@ __global__ void records_unpack_kernel(const uint16_t* __restrict__ rows, long lo
         }
         pol = isp ? WFB_POL_POSITIVE : (isn ? WFB_POL_NEGATIVE : WFB_POL_UNKNOWN);
     }
-    (void)c0; (void)c1;
+    if (c0 == 'r' && c1 == 'a') {  // internal tag "rawpos" (waveformanalysis_b200/aos.py)
+        const char* rp = "rawpos";
+        bool isr = true;
+        for (int k = 0; k < 8; ++k) isr = isr && rd32(h + 16 + 2 * k) == (k < 6 ? (unsigned)rp[k] : 0u);
+        if (isr) pol = WFB_POL_RAW_POSITIVE;
+    }
     m.polarity = (uint8_t)pol;
     m.pad_[0] = m.pad_[1] = m.pad_[2] = 0;
     m.record_id = (long long)rd64(h + 32);

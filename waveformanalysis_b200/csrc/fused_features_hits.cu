@@ -78,6 +78,7 @@ struct ScanRec {
     double bi, bf;
     int wlim;
     bool b_small;  // |b_rec| < 2e9: the integer split is usable
+    int bias;      // 32768 when the 16-bit samples are int16: the kernel works on w' = w + 32768
 };
 // what a hit row needs beyond the staged entry
 struct RowRec {
@@ -161,12 +162,13 @@ __device__ __forceinline__ bool hit_test_u16(double b, double thr, bool positive
     double sig = positive ? __dsub_rn((double)w, b) : __dsub_rn(b, (double)w);
     return sig >= thr;
 }
-__device__ __noinline__ int integer_threshold_u16(double b, double thr, bool positive) {
-    // largest k in [-1, 65535] such that every key kv <= k passes, kv = positive ? 65535 - w : w
+__device__ __noinline__ int integer_threshold_u16(double b, double thr, bool positive, int bias) {
+    // largest k in [-1, 65535] such that every key kv <= k passes, kv = positive ? 65535 - w' : w',
+    // w' = w + bias the stored (offset) sample and w the true sample value
     if (!(b == b) || !(thr == thr)) return -1;
-    double guess = positive ? (65535.0 - (b + thr)) : (b - thr);
+    double guess = positive ? (65535.0 - (b + thr + bias)) : (b - thr + bias);
     int k = !(guess < 65535.0) ? 65535 : (guess < -1.0 ? -1 : (int)floor(guess));
-    auto pass = [&](int kv) { return hit_test_u16(b, thr, positive, positive ? 65535 - kv : kv); };
+    auto pass = [&](int kv) { return hit_test_u16(b, thr, positive, (positive ? 65535 - kv : kv) - bias); };
     for (int it = 0; it < 4 && k < 65535 && pass(k + 1); ++it) ++k;
     for (int it = 0; it < 4 && k >= 0 && !pass(k); ++it) --k;
     // the guess is within one step of the true bound; verify and fall back to a bisection if not
@@ -251,7 +253,7 @@ struct RowSink {  // re-scan of a record whose hits did not fit: write rows stra
 template <typename T, typename Src, typename Sink>
 __device__ __forceinline__ void emit_hit(const Src& src, const ScanRec& r, const FHArgs& a, int s, int e, Sink& sink) {
     const int lane = lane_id();
-    const bool positive = r.pol == WFB_POL_POSITIVE;
+    const bool positive = r.pol == WFB_POL_POSITIVE || r.pol == WFB_POL_RAW_POSITIVE;
     const int a0 = max(0, s - a.p.left_extension);
     const int a1 = min(a.lmax, e + a.p.right_extension);
     if (a1 <= a0) return;
@@ -260,7 +262,8 @@ __device__ __forceinline__ void emit_hit(const Src& src, const ScanRec& r, const
     float hheight, hint;
     if constexpr (sizeof(T) == 2) {
         // integral = sum(max(sig, 0)) = +-(cnt*b - sum(w)) over the samples on the signal side of b
-        const int wlim = r.wlim;
+        const int wlim = r.wlim + r.bias;  // bound in the offset domain
+        const int sx = r.bias ? 0x8000 : 0;
         const int seg = a1 - a0;
         int kmin, cnt_i;
         long long swt;
@@ -268,7 +271,8 @@ __device__ __forceinline__ void emit_hit(const Src& src, const ScanRec& r, const
             // one sample per lane: argmin-first and (count, sum) each in a single warp reduction
             const int i = a0 + lane;
             const bool act = lane < seg;
-            const int w = (act && i < r.len) ? (int)src.at(r.mis + i) : 0;  // padding samples are 0 (records_view.py:189)
+            // padding samples are 0 (records_view.py:189), i.e. `bias` in the offset domain
+            const int w = (act && i < r.len) ? ((int)src.at(r.mis + i) ^ sx) : r.bias;
             const int kv = positive ? 65535 - w : w;
             const unsigned key = act ? (((unsigned)kv << 16) | (unsigned)lane) : 0xffffffffu;
             const unsigned kred = __reduce_min_sync(kFull, key);
@@ -284,7 +288,7 @@ __device__ __forceinline__ void emit_hit(const Src& src, const ScanRec& r, const
             unsigned cnt = 0;
             unsigned long long sw = 0;
             for (int i = a0 + lane; i < a1; i += 32) {
-                int w = (i < r.len) ? (int)src.at(r.mis + i) : 0;
+                int w = (i < r.len) ? ((int)src.at(r.mis + i) ^ sx) : r.bias;
                 int kv = positive ? 65535 - w : w;
                 if (kv < kbest) { kbest = kv; ibest = i; }
                 bool in = positive ? (w >= wlim) : (w <= wlim);
@@ -296,9 +300,10 @@ __device__ __forceinline__ void emit_hit(const Src& src, const ScanRec& r, const
             cnt_i = (int)__reduce_add_sync(kFull, cnt);
             swt = (seg <= 32768) ? (long long)__reduce_add_sync(kFull, (unsigned)sw) : warp_sum_i64((long long)sw);
         }
-        const int wp = positive ? 65535 - kmin : kmin;
+        const int wp = (positive ? 65535 - kmin : kmin) - r.bias;
         hheight = (float)(positive ? __dsub_rn((double)wp, b) : __dsub_rn(b, (double)wp));
         const long long c = cnt_i;
+        swt -= c * r.bias;
         double integ;
         if (r.b_small) {
             long long ipart = positive ? (swt - c * (long long)r.bi) : (c * (long long)r.bi - swt);
@@ -340,8 +345,10 @@ __device__ __forceinline__ void scan_record(const Src& src, const ScanRec& r, co
     const int len = r.len;
     const int mis = r.mis;
     const int vtotal = mis + len;
-    const bool positive = r.pol == WFB_POL_POSITIVE;
-    const bool known = r.pol != WFB_POL_UNKNOWN;
+    const bool rawpos = r.pol == WFB_POL_RAW_POSITIVE;  // positive pulses, raw float64 arithmetic
+    const bool positive = r.pol == WFB_POL_POSITIVE || rawpos;
+    const bool known = r.pol == WFB_POL_POSITIVE || r.pol == WFB_POL_NEGATIVE;  // float32 signal path
+    const unsigned sx32 = (U16 && r.bias) ? 0x80008000u : 0u;
     const int p0 = r.p0, p1 = r.p1, c0 = r.c0, c1 = r.c1;
     const int kmax = r.kmax;
     const unsigned xm = (HITS && U16 && positive) ? 0xffffffffu : 0u;
@@ -368,6 +375,7 @@ __device__ __forceinline__ void scan_record(const Src& src, const ScanRec& r, co
         if (hi > lo) {
             q0 = src.load16(v0);
             if (!U16) q1 = src.load16(v0 + 4);
+            if (U16) { q0.x ^= sx32; q0.y ^= sx32; q0.z ^= sx32; q0.w ^= sx32; }  // int16 -> offset binary
         }
         // warp-uniform: every lane holds 8 valid samples that all lie inside the area range and
         // outside the height range (the common case away from the record edges)
@@ -507,7 +515,7 @@ __device__ __forceinline__ void scan_record(const Src& src, const ScanRec& r, co
                             if (U16 && !known) {
                                 isum += (unsigned)c[j];
                             } else if (!known) {
-                                dsum += __dsub_rn(r.b_feat, (double)c[j]);
+                                dsum += rawpos ? __dsub_rn((double)c[j], r.b_feat) : __dsub_rn(r.b_feat, (double)c[j]);
                             } else {
                                 float sv = positive ? __fsub_rn((float)c[j], b32) : __fsub_rn(b32, (float)c[j]);
                                 dsum += (double)sv;
@@ -578,7 +586,9 @@ __device__ __forceinline__ void scan_record(const Src& src, const ScanRec& r, co
                 int wmin = __reduce_min_sync(kFull, imin);
                 int wmax = __reduce_max_sync(kFull, imax);
                 if (!known) {
-                    fa.height = (float)__dsub_rn(r.b_feat, (double)wmin);  // baseline - min(wave)
+                    // baseline - min(wave), or max(wave) - baseline for raw positive pulses
+                    fa.height = rawpos ? (float)__dsub_rn((double)(wmax - r.bias), r.b_feat)
+                                       : (float)__dsub_rn(r.b_feat, (double)(wmin - r.bias));
                     fa.amp = (float)(wmax - wmin);
                 } else {
                     float smax = positive ? __fsub_rn((float)wmax, b32) : __fsub_rn(b32, (float)wmin);
@@ -589,7 +599,7 @@ __device__ __forceinline__ void scan_record(const Src& src, const ScanRec& r, co
             } else {
                 float vmin = warp_min_f32(fmin_), vmax = warp_max_f32(fmax_);
                 if (!known) {
-                    fa.height = (float)__dsub_rn(r.b_feat, (double)vmin);
+                    fa.height = rawpos ? (float)__dsub_rn((double)vmax, r.b_feat) : (float)__dsub_rn(r.b_feat, (double)vmin);
                     fa.amp = (float)__dsub_rn((double)vmax, (double)vmin);
                 } else {
                     fa.height = vmax;
@@ -600,17 +610,18 @@ __device__ __forceinline__ void scan_record(const Src& src, const ScanRec& r, co
         if (c1 > c0) {
             if (U16 && !known) {
                 // sum(b - w) = n*floor(b) - sum(w) (exact integer) + n*frac(b)
-                long long sw = (long long)__reduce_add_sync(kFull, isum32) + warp_sum_i64((long long)isum);
-                double b = r.b_feat;
                 long long nC = c1 - c0;
+                long long sw = (long long)__reduce_add_sync(kFull, isum32) + warp_sum_i64((long long)isum) - nC * r.bias;
+                double b = r.b_feat;
                 double area;
                 if (fabs(b) < 1e12) {
                     double bi = floor(b);
                     double bf = __dsub_rn(b, bi);
-                    long long ipart = nC * (long long)bi - sw;
-                    area = __dadd_rn((double)ipart, __dmul_rn((double)nC, bf));
+                    double fpart = __dmul_rn((double)nC, bf);
+                    if (rawpos) area = __dsub_rn((double)(sw - nC * (long long)bi), fpart);  // sum(w - b)
+                    else area = __dadd_rn((double)(nC * (long long)bi - sw), fpart);        // sum(b - w)
                 } else {
-                    area = __dsub_rn(__dmul_rn((double)nC, b), (double)sw);
+                    area = rawpos ? __dsub_rn((double)sw, __dmul_rn((double)nC, b)) : __dsub_rn(__dmul_rn((double)nC, b), (double)sw);
                 }
                 fa.area = (float)area;
             } else {
@@ -622,7 +633,7 @@ __device__ __forceinline__ void scan_record(const Src& src, const ScanRec& r, co
 
 __device__ __forceinline__ void hit_constants(ScanRec& r) {
     const double b = r.b_rec;
-    const bool positive = r.pol == WFB_POL_POSITIVE;
+    const bool positive = r.pol == WFB_POL_POSITIVE || r.pol == WFB_POL_RAW_POSITIVE;
     r.b_small = fabs(b) < 2e9;
     r.bi = floor(b);
     r.bf = __dsub_rn(b, r.bi);
@@ -707,7 +718,9 @@ __global__ void __launch_bounds__(kWarps * 32) fused_features_hits_kernel(const 
             resolve_slice(a.p.area_start, a.p.area_end, len, c0, c1);
         }
         int kmax = -1;
-        if (HITS && U16 && len > 0) kmax = integer_threshold_u16(b_rec, thr, pol == WFB_POL_POSITIVE);
+        const int bias = (U16 && a.p.signed_samples) ? 32768 : 0;
+        if (HITS && U16 && len > 0)
+            kmax = integer_threshold_u16(b_rec, thr, pol == WFB_POL_POSITIVE || pol == WFB_POL_RAW_POSITIVE, bias);
         unsigned copy_bytes = 0;
         if (STAGED && len > 0) {
             copy_bytes = (unsigned)((((long long)mis + len + AL - 1) & ~(long long)(AL - 1)) * (long long)sizeof(T));
@@ -749,6 +762,7 @@ __global__ void __launch_bounds__(kWarps * 32) fused_features_hits_kernel(const 
             r.p1 = FEAT ? __shfl_sync(kFull, p1, j) : 0;
             r.c0 = FEAT ? __shfl_sync(kFull, c0, j) : 0;
             r.c1 = FEAT ? __shfl_sync(kFull, c1, j) : 0;
+            r.bias = bias;
             if (HITS && U16) hit_constants(r);
             StageSink sink{HITS ? &s_ent[warp][used] : nullptr, kEntPerWarp - used, 0, (unsigned)j};
             FeatAcc fa = {0.f, 0.f, 0.f, 0.f};
@@ -899,6 +913,7 @@ __global__ void __launch_bounds__(kWarps * 32) fused_features_hits_kernel(const 
             r.thr = bcast_f64(thr, j);
             r.kmax = __shfl_sync(kFull, kmax, j);
             r.p0 = r.p1 = r.c0 = r.c1 = 0;
+            r.bias = bias;
             hit_constants(r);
             RowSink sink;
             sink.out = a.hit_out;

@@ -190,12 +190,14 @@ struct ChargeSrc {
     const T* w;
     double b;
     float b32;
-    int mode;  // 0: unknown polarity (b - w in f64), 1: negative known (b32 - w in f32), 2: positive known
+    int mode;  // 0: unknown polarity (b - w in f64), 1: negative known (b32 - w in f32), 2: positive known,
+               // 3: raw positive (w - b in f64; st_waveforms branch, waveform_width_integral.py:187-191)
     __device__ __forceinline__ double operator()(int i) const {
         double sig;
         if (mode == 0) sig = __dsub_rn(b, (double)w[i]);
         else if (mode == 1) sig = (double)__fsub_rn(b32, (float)w[i]);
-        else sig = (double)__fsub_rn((float)w[i], b32);
+        else if (mode == 2) sig = (double)__fsub_rn((float)w[i], b32);
+        else sig = __dsub_rn((double)w[i], b);
         return fmax(sig, 0.0);
     }
 };
@@ -269,7 +271,7 @@ __global__ void __launch_bounds__(128) width_integral_kernel(const T* __restrict
     x.w = pool + off;
     x.b = m.baseline;
     x.b32 = (float)m.baseline;
-    x.mode = m.polarity == WFB_POL_NEGATIVE ? 1 : (m.polarity == WFB_POL_POSITIVE ? 2 : 0);
+    x.mode = m.polarity == WFB_POL_NEGATIVE ? 1 : (m.polarity == WFB_POL_POSITIVE ? 2 : (m.polarity == WFB_POL_RAW_POSITIVE ? 3 : 0));
     const double q = numpy_pairwise_sum(x, L);
     int lo = 0, hi = 0;
     if (q > 0.0 && isfinite(q)) {

@@ -133,6 +133,7 @@ def make_params(
     rules_dev: int = 0,
     pool_base: int = 0,
     row_base: int = 0,
+    signed_samples: bool = False,
 ) -> _lib.FHParams:
     p = _lib.FHParams()
     p.flags = int(flags)
@@ -149,6 +150,7 @@ def make_params(
     p.rules_dev = rules_dev
     p.pool_base = int(pool_base)
     p.row_base = int(row_base)
+    p.signed_samples = 1 if signed_samples else 0
     return p
 
 
@@ -176,6 +178,7 @@ def process_host(
     chunk_records: int = 0,
     out_features: np.ndarray | None = None,
     out_hits: np.ndarray | None = None,
+    signed_samples: bool = False,
 ) -> dict:
     """Fused pass over host buffers through ``wfb_process_host``.  Returns a dict with
     ``features`` (BASIC_FEATURES_DTYPE), ``hits`` (THRESHOLD_HIT_DTYPE), ``counts`` (int32)."""
@@ -189,7 +192,7 @@ def process_host(
     lmax = int(rec["event_length"].max()) if (hits and n) else 0
     p = make_params(flags=flags, pool_is_f32=is_f32, height_range=height_range, area_range=area_range,
                     threshold=threshold, left_extension=left_extension, right_extension=right_extension,
-                    lmax=max(lmax, 0), n_rules=len(rules))
+                    lmax=max(lmax, 0), n_rules=len(rules), signed_samples=signed_samples)
     feat = None
     if features:
         feat = out_features if out_features is not None else np.empty(n, dtype=BASIC_FEATURES_DTYPE)

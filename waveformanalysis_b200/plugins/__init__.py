@@ -1,0 +1,28 @@
+"""B200 drop-in plugins: same ``provides`` names, options, versions and output dtypes as the
+reference's CPU plugins (core/plugins/builtin/cpu/*.py); only ``compute`` differs - it calls the
+sm_100a kernels through libwfb200.so.  Register with
+``ctx.register(*waveformanalysis_b200.profiles.b200_default(), allow_override=True)``.
+"""
+
+from .features import B200BasicFeaturesPlugin
+from .filtering import B200WavePoolFilteredPlugin
+from .grouping import B200GroupedEventsPlugin, B200HitGroupedPlugin
+from .hits import B200ThresholdHitPlugin
+from .merge import B200HitMergeClustersPlugin, B200HitMergedComponentsPlugin, B200HitMergePlugin
+from .records import B200RecordsPlugin, B200WavePoolPlugin
+from .widths import B200WaveformWidthIntegralPlugin, B200WaveformWidthPlugin
+
+__all__ = [
+    "B200BasicFeaturesPlugin",
+    "B200ThresholdHitPlugin",
+    "B200WavePoolFilteredPlugin",
+    "B200WaveformWidthPlugin",
+    "B200WaveformWidthIntegralPlugin",
+    "B200HitMergeClustersPlugin",
+    "B200HitMergePlugin",
+    "B200HitMergedComponentsPlugin",
+    "B200HitGroupedPlugin",
+    "B200GroupedEventsPlugin",
+    "B200RecordsPlugin",
+    "B200WavePoolPlugin",
+]

@@ -179,6 +179,8 @@ def process_host(
     out_features: np.ndarray | None = None,
     out_hits: np.ndarray | None = None,
     signed_samples: bool = False,
+    row_base: int = 0,
+    lmax: int | None = None,
 ) -> dict:
     """Fused pass over host buffers through ``wfb_process_host``.  Returns a dict with
     ``features`` (BASIC_FEATURES_DTYPE), ``hits`` (THRESHOLD_HIT_DTYPE), ``counts`` (int32)."""
@@ -189,10 +191,11 @@ def process_host(
     n = len(rec)
     flags = (_lib.DO_FEATURES if features else 0) | (_lib.DO_HITS if hits else 0)
     rules = make_rules(thresholds, fixed_baselines)
-    lmax = int(rec["event_length"].max()) if (hits and n) else 0
+    if lmax is None:  # a shard of a run passes the run-wide maximum (hit_finder.py:364)
+        lmax = int(rec["event_length"].max()) if (hits and n) else 0
     p = make_params(flags=flags, pool_is_f32=is_f32, height_range=height_range, area_range=area_range,
                     threshold=threshold, left_extension=left_extension, right_extension=right_extension,
-                    lmax=max(lmax, 0), n_rules=len(rules), signed_samples=signed_samples)
+                    lmax=max(lmax, 0), n_rules=len(rules), signed_samples=signed_samples, row_base=row_base)
     feat = None
     if features:
         feat = out_features if out_features is not None else np.empty(n, dtype=BASIC_FEATURES_DTYPE)

@@ -190,7 +190,7 @@ def test_device_synth_matches_oracle(eng):
     assert np.array_equal(got["hits"].view(np.uint8), again["hits"].view(np.uint8))
 
 
-@pytest.mark.parametrize("variant", ["global", "staged"])
+@pytest.mark.parametrize("variant", ["global", "staged", "auto"])
 def test_kernel_variants_agree(eng, golden, variant, monkeypatch):
     """All data-movement variants of the fused kernel (TMA-staged slot ring,
     and the global-memory accessor used for very long records) produce identical bytes."""

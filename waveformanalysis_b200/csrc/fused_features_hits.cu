@@ -30,7 +30,7 @@
 
 #include <algorithm>
 
-#include "common.cuh"
+#include "fused_common.cuh"
 
 namespace wfb {
 
@@ -39,96 +39,6 @@ constexpr int kTile = kWarps * 32;        // records per tile / look-back unit
 constexpr int kEntPerWarp = 256;          // staged hits per warp per tile (8 per record on average)
 constexpr int kSlots = 3;                 // TMA slot ring depth per warp
 constexpr int kRowBufBytes = 32 * 17 * 4; // row transposition buffer per warp (32 rows x (15 + 2) words)
-
-struct HitEnt {  // a found hit, staged in shared memory until the tile's output offset is known
-    int p, s;
-    unsigned e_rec;  // end sample | owning lane << 27
-    float height, integral;
-};
-
-struct FHArgs {
-    const void* pool;
-    long long pool_len;
-    const wfb_rec_meta* meta;
-    long long n;
-    wfb_fh_params p;
-    int lmax;
-    int slot_bytes;  // shared-memory bytes per staged record (0: read samples from global memory)
-    int ring_bytes;  // shared-memory bytes per warp (slot ring, reused as the row transposition buffer)
-    uint8_t* feat_out;
-    uint8_t* hit_out;
-    long long hit_cap;
-    int* hit_counts;
-    const long long* hit_base;
-    long long* total_out;
-    unsigned long long* tile_state;  // [n_tiles] decoupled look-back descriptors
-    unsigned* ticket;                // dynamic tile counter
-    int* err_flag;
-    int n_tiles;
-};
-
-// what the scan of one record needs (warp-uniform, broadcast from the owning lane)
-struct ScanRec {
-    int mis, len, pol;
-    double b_rec, b_feat, thr;
-    int kmax;
-    int p0, p1, c0, c1;
-    // uint16 hits: floor(b_rec) / its int value / frac(b_rec), and the integer bound of the samples
-    // on the signal side of the baseline (negative: w <= wlim, positive: w >= wlim)
-    double bi, bf;
-    int wlim;
-    bool b_small;  // |b_rec| < 2e9: the integer split is usable
-    int bias;      // 32768 when the 16-bit samples are int16: the kernel works on w' = w + 32768
-};
-// what a hit row needs beyond the staged entry
-struct RowRec {
-    long long ts, rid;
-    int len, dt;
-    unsigned bc;  // board | channel << 16
-};
-
-// ---- tile descriptor: status in the top 2 bits, value below ---------------------------------
-constexpr unsigned long long kStAgg = 1ull << 62, kStPrefix = 2ull << 62, kStMask = 3ull << 62;
-
-__device__ __forceinline__ unsigned long long ld_state(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_state(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
-// ---- mbarrier + TMA bulk copy (global -> shared) ---------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WFB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WFB_DONE;\n"
-        "bra WFB_WAIT;\n"
-        "WFB_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- sample sources ---------------------------------------------------------------------------
 // Both expose the record on a grid of 16-byte chunks: virtual index v = mis + i, where i is the
@@ -154,62 +64,6 @@ struct SmemSrc {
     __device__ __forceinline__ uint4 load16(int v) const { return *reinterpret_cast<const uint4*>(base + v); }
     __device__ __forceinline__ T at(int v) const { return base[v]; }
 };
-
-// ---- the reference's float64 threshold test as an exact integer bound (uint16 pool) ---------
-// negative/unknown polarity: hit iff fl(b - w) >= thr  <=>  w <= kmax   (monotone in w)
-// positive polarity:         hit iff fl(w - b) >= thr  <=>  (65535 - w) <= kmax
-__device__ __forceinline__ bool hit_test_u16(double b, double thr, bool positive, int w) {
-    double sig = positive ? __dsub_rn((double)w, b) : __dsub_rn(b, (double)w);
-    return sig >= thr;
-}
-__device__ __noinline__ int integer_threshold_u16(double b, double thr, bool positive, int bias) {
-    // largest k in [-1, 65535] such that every key kv <= k passes, kv = positive ? 65535 - w' : w',
-    // w' = w + bias the stored (offset) sample and w the true sample value
-    if (!(b == b) || !(thr == thr)) return -1;
-    double guess = positive ? (65535.0 - (b + thr + bias)) : (b - thr + bias);
-    int k = !(guess < 65535.0) ? 65535 : (guess < -1.0 ? -1 : (int)floor(guess));
-    auto pass = [&](int kv) { return hit_test_u16(b, thr, positive, (positive ? 65535 - kv : kv) - bias); };
-    for (int it = 0; it < 4 && k < 65535 && pass(k + 1); ++it) ++k;
-    for (int it = 0; it < 4 && k >= 0 && !pass(k); ++it) --k;
-    // the guess is within one step of the true bound; verify and fall back to a bisection if not
-    if ((k >= 0 && !pass(k)) || (k < 65535 && pass(k + 1))) {
-        int lo = -1, hi = 65535;
-        while (lo < hi) {
-            int mid = lo + (hi - lo + 1) / 2;
-            if (pass(mid)) lo = mid; else hi = mid - 1;
-        }
-        k = lo;
-    }
-    return k;
-}
-
-// ---- packed THRESHOLD_HIT row (hit_finder.py:33-49, 382-409): 15 little-endian words ----------
-__device__ __forceinline__ void hit_row_words(unsigned w[15], int p, int s, int e, float height, float integral,
-                                              const RowRec& r, int left, int right, int lmax) {
-    int a0 = max(0, s - left);
-    int a1 = min(lmax, e + right);
-    int rl = max(r.len, 0);
-    int es = min(max(a0, 0), rl);
-    int ee = max(min(max(a1, 0), rl), es);
-    // int(timestamp + pos * (dt * 1e3)) evaluated in float64, no FMA contraction
-    double step = __dmul_rn((double)r.dt, 1e3);
-    long long ti = (long long)__dadd_rn((double)r.ts, __dmul_rn((double)p, step));
-    w[0] = (unsigned)p;
-    w[1] = 0u;  // position < 2^31
-    w[2] = __float_as_uint(height);
-    w[3] = __float_as_uint(integral);
-    w[4] = (unsigned)es;
-    w[5] = (unsigned)ee;
-    w[6] = __float_as_uint((float)(ee - es));
-    w[7] = (unsigned)r.dt;
-    w[8] = __float_as_uint((float)((long long)max(p - s, 0) * r.dt));
-    w[9] = __float_as_uint((float)((long long)max((e - 1) - p, 0) * r.dt));
-    w[10] = (unsigned)(ti & 0xffffffffll);
-    w[11] = (unsigned)((unsigned long long)ti >> 32);
-    w[12] = r.bc;
-    w[13] = (unsigned)(r.rid & 0xffffffffll);
-    w[14] = (unsigned)((unsigned long long)r.rid >> 32);
-}
 
 // ---- hit sinks --------------------------------------------------------------------------------
 struct StageSink {  // phase A: count every hit, keep the rows that fit the warp's staging area
@@ -643,11 +497,6 @@ __device__ __forceinline__ void hit_constants(ScanRec& r) {
 }
 
 __device__ __forceinline__ double bcast_f64(double v, int src) { return shfl_f64(v, src); }
-__device__ __forceinline__ long long bcast_i64(long long v, int src) {
-    int lo = __shfl_sync(kFull, (int)(v & 0xffffffffll), src);
-    int hi = __shfl_sync(kFull, (int)(v >> 32), src);
-    return ((long long)hi << 32) | (unsigned)lo;
-}
 
 // ---- the kernel --------------------------------------------------------------------------------
 template <typename T, bool STAGED, bool FEAT, bool HITS>
@@ -841,28 +690,7 @@ __global__ void __launch_bounds__(kWarps * 32) fused_features_hits_kernel(const 
                 if (lane >= d) wincl += t;
             }
             const long long total = bcast_i64(wincl, kWarps - 1);
-            if (lane == 0) st_state(a.tile_state + tile, kStAgg | (unsigned long long)total);
-            long long excl = 0;
-            int look = tile - 1;
-            for (;;) {
-                int idx = look - lane;
-                unsigned long long v;
-                if (idx >= 0) {
-                    do { v = ld_state(a.tile_state + idx); } while ((v & kStMask) == 0);
-                } else {
-                    v = (idx == -1) ? (kStPrefix | (unsigned long long)(a.hit_base ? *a.hit_base : 0)) : kStPrefix;
-                }
-                unsigned isp = __ballot_sync(kFull, (v & kStMask) == kStPrefix);
-                int first = __ffs(isp) - 1;  // nearest predecessor holding an inclusive prefix
-                long long val = (first < 0 || lane <= first) ? (long long)(v & ~kStMask) : 0;
-                excl += warp_sum_i64(val);
-                if (first >= 0) break;
-                look -= 32;
-            }
-            if (lane == 0) {
-                st_state(a.tile_state + tile, kStPrefix | (unsigned long long)(excl + total));
-                if (tile == a.n_tiles - 1) *a.total_out = excl + total;
-            }
+            const long long excl = tile_lookback(a, tile, total);
             if (lane < kWarps) s_wbase[lane] = excl + (wincl - c);
         }
         __syncthreads();
@@ -950,7 +778,7 @@ struct WsLayout {
     size_t ticket, err, lmax, state, total;
 };
 static WsLayout ws_layout(long long n) {
-    long long n_tiles = (n + kTile - 1) / kTile;
+    long long n_tiles = (n + 127) / 128;  // smallest tile of the kernel variants
     WsLayout w;
     w.ticket = 0;
     w.err = 4;
@@ -1063,6 +891,9 @@ extern "C" int wfb_features_hits(const void* pool_dev, int64_t pool_len, const w
         a.lmax = h_l;
     }
     if (params->pool_is_f32) return launch_fused<float>(a, flags, st);
+    // 16-bit pools: lane-per-record kernel when the records fit its shared-memory slots
+    const int rc = launch_lpr(a, flags, st);
+    if (rc != 1) return rc;
     return launch_fused<uint16_t>(a, flags, st);
 }
 

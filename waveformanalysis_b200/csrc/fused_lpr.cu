@@ -1,0 +1,532 @@
+// K2 + K3, lane-per-record variant (uint16 / int16 pools, records of up to 1024 samples).
+//
+// Each LANE owns one record: its samples are staged by a 1-D TMA bulk copy into the lane's own
+// shared-memory slot (slot stride = odd multiple of 16 bytes, so the 32 lanes' LDS.128 hit
+// distinct bank groups), and the lane walks them 8 samples at a time with packed 16x2 integer
+// ops.  No cross-lane traffic at all in the sample loop: no shuffles, no warp reductions.  While
+// scanning, the lane records in a register bitmask which 8-sample chunks contain samples above
+// threshold; a second, lane-parallel pass visits only those chunks (still in the slot), walks the
+// threshold runs with bit tricks and accumulates each hit's argmax / integral on the fly.  Hits
+// go to a per-warp shared-memory pool (claimed with a shared-memory atomic); one decoupled
+// look-back per 128-record tile gives the first output row; rows are assembled one hit per lane.
+//
+// Reference semantics: see fused_features_hits.cu (same arithmetic, same results).
+#include <stdlib.h>
+
+#include <algorithm>
+
+#include "fused_common.cuh"
+
+namespace wfb {
+
+constexpr int kLprWarps = 4;
+constexpr int kLprTile = kLprWarps * 32;  // records per tile / look-back unit
+constexpr int kLprEnt = 320;              // staged hits per warp per tile (10 per record on average)
+constexpr int kLprMaskWords = 4;          // 128 chunks = 1024 samples (+ misalignment slack)
+constexpr int kLprMaxChunks = kLprMaskWords * 32;
+
+struct LprEnt {  // 16 bytes
+    unsigned ps;   // p | s << 16
+    unsigned eo;   // e | owner lane << 16 | ordinal << 21
+    float height, integral;
+};
+
+struct LaneRec {  // everything a lane knows about its record
+    long long off, ts, rid;
+    int len, dt, pol, mis, bias;
+    unsigned bc;
+    double b_rec, b_feat, thr;
+    int kmax;
+    // hit integral constants (see hit_constants in fused_features_hits.cu)
+    double bi, bf;
+    int wlim;
+    bool b_small, positive;
+};
+
+__device__ __forceinline__ int u16_at(const uint4& q, int j) {
+    const unsigned w = (j < 4) ? ((j < 2) ? q.x : q.y) : ((j < 6) ? q.z : q.w);
+    return (int)((w >> ((j & 1) * 16)) & 0xffffu);
+}
+
+// ---- hit sinks (per lane) ---------------------------------------------------------------------
+struct PoolSink {
+    LprEnt* pool;
+    int* counter;
+    bool overflow;
+    __device__ __forceinline__ void store(int p, int s, int e, float height, float integral, int ord, const LaneRec&, const FHArgs&) {
+        int idx = atomicAdd(counter, 1);
+        if (idx < kLprEnt) {
+            LprEnt h;
+            h.ps = (unsigned)p | ((unsigned)s << 16);
+            h.eo = (unsigned)e | ((unsigned)lane_id() << 16) | ((unsigned)ord << 21);
+            h.height = height;
+            h.integral = integral;
+            *reinterpret_cast<uint4*>(&pool[idx]) = *reinterpret_cast<uint4*>(&h);
+        } else {
+            overflow = true;
+        }
+    }
+};
+struct DirectSink {  // rows straight to the output (records whose hits did not fit the pool)
+    long long row0;
+    __device__ __forceinline__ void store(int p, int s, int e, float height, float integral, int ord, const LaneRec& r, const FHArgs& a) {
+        long long row = row0 + ord;
+        if (row < a.hit_cap) {
+            RowRec rr{r.ts, r.rid, r.len, r.dt, r.bc};
+            unsigned w[15];
+            hit_row_words(w, p, s, e, height, integral, rr, a.p.left_extension, a.p.right_extension, a.lmax);
+            unsigned* dst = reinterpret_cast<unsigned*>(a.hit_out + row * kHitRowBytes);
+#pragma unroll
+            for (int k = 0; k < 15; ++k) dst[k] = w[k];
+        }
+    }
+};
+
+// running aggregates of the open run of a lane
+struct RunAgg {
+    int kbest, ibest;
+    unsigned cnt;
+    unsigned long long sw;
+    __device__ __forceinline__ void reset() { kbest = INT_MAX; ibest = INT_MAX; cnt = 0; sw = 0; }
+    // one sample at record index i with stored (offset-domain) value w
+    __device__ __forceinline__ void add(int i, int w, const LaneRec& r) {
+        int kv = r.positive ? 65535 - w : w;
+        if (kv < kbest) { kbest = kv; ibest = i; }
+        bool in = r.positive ? (w >= r.wlim + r.bias) : (w <= r.wlim + r.bias);
+        cnt += in ? 1u : 0u;
+        sw += in ? (unsigned)w : 0u;
+    }
+};
+
+// ---- lane-parallel hit pass over the interesting chunks of each lane's record ----------------
+template <typename Sink>
+__device__ __forceinline__ int lpr_hit_pass(const uint8_t* slot, const LaneRec& r, const FHArgs& a, const unsigned (&mask)[kLprMaskWords],
+                                            Sink& sink) {
+    const unsigned sx = r.bias ? 0x80008000u : 0u;
+    const unsigned xm = r.positive ? 0xffffffffu : 0u;
+    const unsigned short* s16 = reinterpret_cast<const unsigned short*>(slot);
+    const int left = a.p.left_extension, right = a.p.right_extension;
+    const int vtotal = r.mis + r.len;
+    int nh = 0;
+    bool open = false;
+    int run_s = 0, prev_c = -2;
+    RunAgg g;
+    g.reset();
+    auto sample = [&](int i) -> int {  // stored value of record sample i, padding = 0 in the true domain
+        return (i < r.len) ? ((int)s16[r.mis + i] ^ (int)(sx & 0xffffu)) : r.bias;
+    };
+    auto close_run = [&](int e) {
+        const int a1 = min(a.lmax, e + right);
+        for (int i = e; i < a1; ++i) g.add(i, sample(i), r);
+        const int wp = (r.positive ? 65535 - g.kbest : g.kbest) - r.bias;
+        const float height = (float)(r.positive ? __dsub_rn((double)wp, r.b_rec) : __dsub_rn(r.b_rec, (double)wp));
+        const long long c = g.cnt;
+        const long long swt = (long long)g.sw - c * r.bias;
+        double integ;
+        if (r.b_small) {
+            long long ipart = r.positive ? (swt - c * (long long)r.bi) : (c * (long long)r.bi - swt);
+            double fpart = __dmul_rn((double)c, r.bf);
+            integ = r.positive ? __dsub_rn((double)ipart, fpart) : __dadd_rn((double)ipart, fpart);
+        } else {
+            integ = r.positive ? __dsub_rn((double)swt, __dmul_rn((double)c, r.b_rec)) : __dsub_rn(__dmul_rn((double)c, r.b_rec), (double)swt);
+        }
+        sink.store(g.ibest, run_s, e, height, (float)integ, nh, r, a);
+        ++nh;
+        open = false;
+    };
+    auto open_run = [&](int s) {
+        open = true;
+        run_s = s;
+        g.reset();
+        for (int i = max(0, s - left); i < s; ++i) g.add(i, sample(i), r);
+    };
+#pragma unroll
+    for (int wd = 0; wd < kLprMaskWords; ++wd) {
+        unsigned m = mask[wd];
+        while (m) {
+            const int c = wd * 32 + __ffs(m) - 1;
+            m &= m - 1;
+            if (open && c != prev_c + 1) close_run((prev_c + 1) * 8 - r.mis);  // the chunk in between is below threshold
+            prev_c = c;
+            uint4 q = *reinterpret_cast<const uint4*>(slot + c * 16);
+            q.x ^= sx; q.y ^= sx; q.z ^= sx; q.w ^= sx;
+            const int v0 = c * 8;
+            const int lo = min(max(r.mis - v0, 0), 8), hi = min(max(vtotal - v0, 0), 8);
+            int wv[8];
+            unsigned m8 = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                wv[j] = u16_at(q, j);
+                int kv = (int)((unsigned)wv[j] ^ (xm & 0xffffu));
+                m8 |= ((kv <= r.kmax && j >= lo && j < hi) ? 1u : 0u) << j;
+            }
+            const int i0 = v0 - r.mis;
+            int j = 0;
+            while (j < 8) {
+                if (open) {
+                    const unsigned t = (~(m8 >> j)) | 0x100u;          // first zero at or after j
+                    const int ones = min(__ffs(t) - 1, 8 - j);
+                    const unsigned rm = ((1u << (j + ones)) - 1u) & ~((1u << j) - 1u);
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj)
+                        if ((rm >> jj) & 1u) g.add(i0 + jj, wv[jj], r);
+                    j += ones;
+                    if (j < 8) close_run(i0 + j);
+                } else {
+                    const unsigned t = m8 >> j;
+                    if (!t) break;
+                    j += __ffs(t) - 1;
+                    open_run(i0 + j);
+                }
+            }
+        }
+    }
+    if (open) close_run(min(r.len, (prev_c + 1) * 8 - r.mis));
+    return nh;
+}
+
+// ---- the kernel --------------------------------------------------------------------------------
+template <bool FEAT, bool HITS>
+__global__ void __launch_bounds__(kLprWarps * 32, 1) lpr_kernel(const FHArgs a) {
+    extern __shared__ __align__(16) uint8_t dyn_smem[];  // [warp][lane] slots of a.slot_bytes
+    __shared__ __align__(16) LprEnt s_ent[HITS ? kLprWarps : 1][HITS ? kLprEnt : 1];
+    __shared__ int s_pool[kLprWarps];
+    __shared__ long long s_wtot[kLprWarps];
+    __shared__ long long s_wbase[kLprWarps];
+    __shared__ int s_tile;
+    __shared__ __align__(8) unsigned long long s_bar[kLprWarps];
+
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const uint16_t* pool = static_cast<const uint16_t*>(a.pool);
+    uint8_t* slot = dyn_smem + ((size_t)warp * 32 + lane) * a.slot_bytes;
+    if (lane == 0) mbar_init(&s_bar[warp], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    unsigned parity = 0;
+
+    for (;;) {
+        if (threadIdx.x == 0) s_tile = (int)atomicAdd(a.ticket, 1u);
+        __syncthreads();
+        const int tile = s_tile;
+        if (tile >= a.n_tiles) break;
+
+        // ---------------- per-lane bookkeeping
+        const long long rec = (long long)tile * kLprTile + warp * 32 + lane;
+        const bool have = rec < a.n;
+        LaneRec r;
+        r.off = 0; r.ts = 0; r.rid = 0; r.len = 0; r.dt = 1; r.pol = 0; r.bc = 0;
+        r.b_rec = 0.0; r.b_feat = 0.0; r.thr = a.p.threshold;
+        if (have) {
+            const uint4* q = reinterpret_cast<const uint4*>(a.meta + rec);
+            uint4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+            r.ts = (long long)(((unsigned long long)q0.y << 32) | q0.x);
+            r.b_rec = __hiloint2double((int)q0.w, (int)q0.z);
+            r.off = (long long)(((unsigned long long)q1.y << 32) | q1.x) - a.p.pool_base;
+            r.len = (int)q1.z;
+            r.dt = (int)q1.w;
+            r.bc = q2.x;
+            r.pol = (int)(q2.y & 0xff);
+            r.rid = (long long)(((unsigned long long)q2.w << 32) | q2.z);
+            r.b_feat = r.b_rec;
+            const int board = (int)(short)(r.bc & 0xffff), channel = (int)(short)(r.bc >> 16);
+            for (int i = 0; i < a.p.n_rules; ++i) {
+                const wfb_chan_rule rule = a.p.rules_dev[i];
+                if (rule.board == board && rule.channel == channel) {
+                    if (rule.has_threshold) r.thr = rule.threshold;
+                    if (rule.has_fixed_baseline) r.b_feat = rule.fixed_baseline;
+                }
+            }
+            if (r.len < 0) r.len = 0;
+            if (r.len > 0 && (r.off < 0 || r.off + r.len > a.pool_len)) {
+                atomicExch(a.err_flag, 1);
+                r.len = 0;
+            }
+        }
+        r.mis = (int)(r.off & 7);
+        r.bias = a.p.signed_samples ? 32768 : 0;
+        r.positive = r.pol == WFB_POL_POSITIVE || r.pol == WFB_POL_RAW_POSITIVE;
+        const bool rawpos = r.pol == WFB_POL_RAW_POSITIVE;
+        const bool known = r.pol == WFB_POL_POSITIVE || r.pol == WFB_POL_NEGATIVE;
+        const int len = r.len, mis = r.mis;
+        int vtotal = mis + len;
+        unsigned copy_bytes = len > 0 ? (unsigned)(((vtotal + 7) & ~7) * 2) : 0u;
+        if ((int)copy_bytes > a.slot_bytes) {
+            atomicExch(a.err_flag, 2);  // lmax passed by the caller is too small
+            copy_bytes = 0;
+            r.len = 0;
+            vtotal = mis;
+        }
+        int p0 = 0, p1 = 0, c0 = 0, c1 = 0;
+        if (FEAT) {
+            resolve_slice(a.p.height_start, a.p.height_end, r.len, p0, p1);
+            resolve_slice(a.p.area_start, a.p.area_end, r.len, c0, c1);
+        }
+        r.kmax = -1;
+        if (HITS && r.len > 0) {
+            r.kmax = integer_threshold_u16(r.b_rec, r.thr, r.positive, r.bias);
+            r.b_small = fabs(r.b_rec) < 2e9;
+            r.bi = floor(r.b_rec);
+            r.bf = __dsub_rn(r.b_rec, r.bi);
+            const int ib = r.b_small ? (int)r.bi : (r.b_rec > 0 ? INT_MAX : INT_MIN);
+            r.wlim = r.positive ? ib + 1 : ((r.bi == r.b_rec) ? ib - 1 : ib);
+        } else {
+            r.b_small = true; r.bi = 0; r.bf = 0; r.wlim = 0;
+        }
+
+        // ---------------- stage the 32 records of this warp: one TMA bulk copy per lane
+        {
+            fence_proxy_async();
+            const unsigned total = __reduce_add_sync(kFull, copy_bytes);
+            if (lane == 0) {
+                if (total) mbar_arrive_expect_tx(&s_bar[warp], total);
+                else mbar_arrive(&s_bar[warp]);
+            }
+            __syncwarp();
+            if (copy_bytes) tma_bulk_g2s(slot, pool + (r.off - mis), copy_bytes, &s_bar[warp]);
+            mbar_wait(&s_bar[warp], parity);
+            parity ^= 1u;
+        }
+
+        // ---------------- scan: features + interesting-chunk mask, 8 samples per step
+        const int nch = (vtotal > mis) ? ((vtotal + 7) >> 3) : 0;
+        const int nch_max = __reduce_max_sync(kFull, nch);
+        const unsigned sx32 = r.bias ? 0x80008000u : 0u;
+        const unsigned xm = r.positive ? 0xffffffffu : 0u;
+        const float b32 = (float)r.b_feat;
+        unsigned pmin = 0xffffffffu, pmax = 0u, pdiff = 0u, isum32 = 0;
+        int imin = INT_MAX, imax = INT_MIN, idiff = 0;
+        double dsum = 0.0;
+        unsigned prev_w = 0;
+        unsigned mask[kLprMaskWords];
+#pragma unroll
+        for (int wd = 0; wd < kLprMaskWords; ++wd) {
+            unsigned mw = 0;
+            const int cend = min(32, nch_max - wd * 32);
+            for (int cb = 0; cb < cend; ++cb) {
+                const int vc = wd * 32 + cb;
+                if (vc >= nch) continue;
+                uint4 q = *reinterpret_cast<const uint4*>(slot + vc * 16);
+                q.x ^= sx32; q.y ^= sx32; q.z ^= sx32; q.w ^= sx32;  // int16 -> offset binary
+                const int v0 = vc * 8;
+                const int lo = max(mis - v0, 0), hi = min(vtotal - v0, 8);
+                const int i0 = v0 - mis;
+                if (lo == 0 && hi == 8) {
+                    if (FEAT) {
+                        const unsigned pw = (i0 > 0) ? prev_w : (q.x << 16);
+                        unsigned f0 = __funnelshift_r(pw, q.x, 16), f1 = __funnelshift_r(q.x, q.y, 16);
+                        unsigned f2 = __funnelshift_r(q.y, q.z, 16), f3 = __funnelshift_r(q.z, q.w, 16);
+                        unsigned d0 = __vmaxu2(q.x, f0) - __vminu2(q.x, f0), d1 = __vmaxu2(q.y, f1) - __vminu2(q.y, f1);
+                        unsigned d2 = __vmaxu2(q.z, f2) - __vminu2(q.z, f2), d3 = __vmaxu2(q.w, f3) - __vminu2(q.w, f3);
+                        pdiff = __vmaxu2(pdiff, __vmaxu2(__vmaxu2(d0, d1), __vmaxu2(d2, d3)));
+                        const int jlo = max(0, p0 - i0), jhi = min(8, p1 - i0);
+                        if (jhi > jlo) {
+                            if (jlo == 0 && jhi == 8) {
+                                pmin = __vminu2(pmin, __vminu2(__vminu2(q.x, q.y), __vminu2(q.z, q.w)));
+                                pmax = __vmaxu2(pmax, __vmaxu2(__vmaxu2(q.x, q.y), __vmaxu2(q.z, q.w)));
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    int w = u16_at(q, j);
+                                    if (j >= jlo && j < jhi) { imin = min(imin, w); imax = max(imax, w); }
+                                }
+                            }
+                        }
+                        const int klo = max(0, c0 - i0), khi = min(8, c1 - i0);
+                        if (khi > klo) {
+                            if (klo == 0 && khi == 8 && !known) {
+                                unsigned s = __dp2a_lo(q.x, 0x0101u, isum32);
+                                s = __dp2a_lo(q.y, 0x0101u, s);
+                                s = __dp2a_lo(q.z, 0x0101u, s);
+                                isum32 = __dp2a_lo(q.w, 0x0101u, s);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    unsigned w = (unsigned)u16_at(q, j);
+                                    if (j >= klo && j < khi) {
+                                        if (!known) isum32 += w;
+                                        else dsum += (double)(r.positive ? __fsub_rn((float)w, b32) : __fsub_rn(b32, (float)w));
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    if (HITS) {
+                        unsigned mn = __vminu2(__vminu2(q.x ^ xm, q.y ^ xm), __vminu2(q.z ^ xm, q.w ^ xm));
+                        int lmin = (int)min(mn & 0xffffu, mn >> 16);
+                        mw |= (lmin <= r.kmax ? 1u : 0u) << cb;
+                    }
+                } else {
+                    // partial chunk (record start / end): per-sample
+                    const int prev_s = (int)(prev_w >> 16);
+                    bool any = false;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int w = u16_at(q, j);
+                        const bool ok = (j >= lo) && (j < hi);
+                        if (FEAT && ok) {
+                            const int i = i0 + j;
+                            if (i > 0) idiff = max(idiff, abs(w - ((j == 0) ? prev_s : u16_at(q, j - 1))));
+                            if (i >= p0 && i < p1) { imin = min(imin, w); imax = max(imax, w); }
+                            if (i >= c0 && i < c1) {
+                                if (!known) isum32 += (unsigned)w;
+                                else dsum += (double)(r.positive ? __fsub_rn((float)w, b32) : __fsub_rn(b32, (float)w));
+                            }
+                        }
+                        if (HITS && ok) any = any || ((int)((unsigned)w ^ (xm & 0xffffu)) <= r.kmax);
+                    }
+                    if (HITS) mw |= (any ? 1u : 0u) << cb;
+                }
+                prev_w = q.w;
+            }
+            mask[wd] = mw;
+        }
+
+        // ---------------- features of my record
+        if (FEAT && have) {
+            float height = 0.f, amp = 0.f, area = 0.f;
+            const float mad = (float)max(idiff, (int)max(pdiff & 0xffffu, pdiff >> 16));
+            if (p1 > p0) {
+                const int wmin = min(imin, (int)min(pmin & 0xffffu, pmin >> 16));
+                const int wmax = max(imax, (int)max(pmax & 0xffffu, pmax >> 16));
+                if (!known) {
+                    height = rawpos ? (float)__dsub_rn((double)(wmax - r.bias), r.b_feat) : (float)__dsub_rn(r.b_feat, (double)(wmin - r.bias));
+                    amp = (float)(wmax - wmin);
+                } else {
+                    float smax = r.positive ? __fsub_rn((float)wmax, b32) : __fsub_rn(b32, (float)wmin);
+                    float smin = r.positive ? __fsub_rn((float)wmin, b32) : __fsub_rn(b32, (float)wmax);
+                    height = smax;
+                    amp = (float)__dsub_rn((double)smax, (double)smin);
+                }
+            }
+            if (c1 > c0) {
+                if (!known) {
+                    const long long nC = c1 - c0;
+                    const long long sw = (long long)isum32 - nC * r.bias;
+                    const double b = r.b_feat;
+                    double ar;
+                    if (fabs(b) < 1e12) {
+                        double bi = floor(b), bf = __dsub_rn(b, bi);
+                        double fpart = __dmul_rn((double)nC, bf);
+                        if (rawpos) ar = __dsub_rn((double)(sw - nC * (long long)bi), fpart);
+                        else ar = __dadd_rn((double)(nC * (long long)bi - sw), fpart);
+                    } else {
+                        ar = rawpos ? __dsub_rn((double)sw, __dmul_rn((double)nC, b)) : __dsub_rn(__dmul_rn((double)nC, b), (double)sw);
+                    }
+                    area = (float)ar;
+                } else {
+                    area = (float)dsum;
+                }
+            }
+            unsigned* dst = reinterpret_cast<unsigned*>(a.feat_out + rec * kFeatRowBytes);
+            const long long ev = a.p.row_base + rec;
+            dst[0] = __float_as_uint(height);
+            dst[1] = __float_as_uint(amp);
+            dst[2] = __float_as_uint(area);
+            dst[3] = __float_as_uint(mad);
+            dst[4] = (unsigned)(r.ts & 0xffffffffll);
+            dst[5] = (unsigned)((unsigned long long)r.ts >> 32);
+            dst[6] = r.bc;
+            dst[7] = (unsigned)(ev & 0xffffffffll);
+            dst[8] = (unsigned)((unsigned long long)ev >> 32);
+        }
+        if (!HITS) {
+            __syncthreads();  // s_tile reuse; slots are refilled after the next ticket
+            continue;
+        }
+
+        // ---------------- hits: lane-parallel pass over the interesting chunks
+        if (lane == 0) s_pool[warp] = 0;
+        __syncwarp();
+        PoolSink psink{&s_ent[warp][0], &s_pool[warp], false};
+        const int my_cnt = lpr_hit_pass(slot, r, a, mask, psink);
+        if (a.hit_counts != nullptr && have) a.hit_counts[rec] = my_cnt;
+
+        int incl = my_cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(kFull, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) s_wtot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            long long c = (lane < kLprWarps) ? s_wtot[lane] : 0;
+            long long wincl = c;
+#pragma unroll
+            for (int d = 1; d < kLprWarps; d <<= 1) {
+                long long t = bcast_i64(wincl, max(lane - d, 0));
+                if (lane >= d) wincl += t;
+            }
+            const long long total = bcast_i64(wincl, kLprWarps - 1);
+            const long long excl = tile_lookback(a, tile, total);
+            if (lane < kLprWarps) s_wbase[lane] = excl + (wincl - c);
+        }
+        __syncthreads();
+
+        // ---------------- phase B: one pooled hit per lane -> packed row
+        const long long my_row0 = s_wbase[warp] + (incl - my_cnt);
+        const unsigned ovf = __ballot_sync(kFull, psink.overflow);
+        const int used = min(s_pool[warp], kLprEnt);
+        for (int e0 = 0; e0 < used; e0 += 32) {
+            const int e = e0 + lane;
+            const bool act = e < used;
+            LprEnt h;
+            *reinterpret_cast<uint4*>(&h) = *reinterpret_cast<const uint4*>(&s_ent[warp][act ? e : 0]);
+            const int owner = (int)((h.eo >> 16) & 31u);
+            RowRec rr;
+            rr.ts = bcast_i64(r.ts, owner);
+            rr.rid = bcast_i64(r.rid, owner);
+            rr.len = __shfl_sync(kFull, r.len, owner);
+            rr.dt = __shfl_sync(kFull, r.dt, owner);
+            rr.bc = __shfl_sync(kFull, r.bc, owner);
+            const long long row = bcast_i64(my_row0, owner) + (long long)(h.eo >> 21);
+            if (act && !((ovf >> owner) & 1u) && row < a.hit_cap) {
+                unsigned w[15];
+                hit_row_words(w, (int)(h.ps & 0xffffu), (int)(h.ps >> 16), (int)(h.eo & 0xffffu), h.height, h.integral, rr,
+                              a.p.left_extension, a.p.right_extension, a.lmax);
+                unsigned* dst = reinterpret_cast<unsigned*>(a.hit_out + row * kHitRowBytes);
+#pragma unroll
+                for (int k = 0; k < 15; ++k) dst[k] = w[k];
+            }
+        }
+        if (psink.overflow) {  // my hits did not all fit the pool: write all of them directly
+            DirectSink dsink{my_row0};
+            lpr_hit_pass(slot, r, a, mask, dsink);
+        }
+        __syncthreads();  // pool, slots and s_tile are reused by the next tile
+    }
+}
+
+int launch_lpr(FHArgs a, int flags, cudaStream_t st) {
+    if (a.p.pool_is_f32) return 1;
+    const char* force = getenv("WFB_FUSED_VARIANT");
+    if (force && (!strcmp(force, "global") || !strcmp(force, "staged"))) return 1;
+    if (a.lmax + 8 > kLprMaxChunks * 8 - 8 || a.lmax >= 65536) return 1;
+    // slot: record rounded out to 16-byte boundaries, stride an odd multiple of 16 bytes so the
+    // 32 lanes of a warp read distinct bank groups
+    long long slot = ((long long)a.lmax * 2 + 15 + 14) & ~15ll;
+    if (((slot >> 4) & 1) == 0) slot += 16;
+    const size_t dyn = (size_t)kLprTile * slot;
+    if (dyn > 200 * 1024) return 1;
+    a.slot_bytes = (int)slot;
+    a.n_tiles = (int)((a.n + kLprTile - 1) / kLprTile);
+    const bool f = flags & WFB_DO_FEATURES, h = flags & WFB_DO_HITS;
+    auto go = [&](auto kern) -> int {
+        WFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        int per_sm = 0;
+        WFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kLprWarps * 32, dyn));
+        if (per_sm < 1) {
+            set_error("lane-per-record kernel does not fit the SM");
+            return WFB_ERR_CUDA;
+        }
+        int grid = (int)std::min<long long>((long long)sm_count() * per_sm, a.n_tiles);
+        kern<<<grid, kLprWarps * 32, dyn, st>>>(a);
+        WFB_CUDA(cudaGetLastError());
+        return WFB_OK;
+    };
+    if (f && h) return go(lpr_kernel<true, true>);
+    if (f) return go(lpr_kernel<true, false>);
+    return go(lpr_kernel<false, true>);
+}
+
+}  // namespace wfb

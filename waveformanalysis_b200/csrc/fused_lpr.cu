@@ -1,14 +1,20 @@
-// K2 + K3, lane-per-record variant (uint16 / int16 pools, records of up to 1024 samples).
+// K2 + K3, lane-per-record streaming variant (uint16 / int16 pools).
 //
-// Each LANE owns one record: its samples are staged by a 1-D TMA bulk copy into the lane's own
-// shared-memory slot (slot stride = odd multiple of 16 bytes, so the 32 lanes' LDS.128 hit
-// distinct bank groups), and the lane walks them 8 samples at a time with packed 16x2 integer
-// ops.  No cross-lane traffic at all in the sample loop: no shuffles, no warp reductions.  While
-// scanning, the lane records in a register bitmask which 8-sample chunks contain samples above
-// threshold; a second, lane-parallel pass visits only those chunks (still in the slot), walks the
-// threshold runs with bit tricks and accumulates each hit's argmax / integral on the fly.  Hits
-// go to a per-warp shared-memory pool (claimed with a shared-memory atomic); one decoupled
-// look-back per 128-record tile gives the first output row; rows are assembled one hit per lane.
+// Each LANE owns one record and streams it through a small double-buffered shared-memory slot:
+// segments of kSC 16-byte chunks (8 samples each) arrive by 1-D TMA bulk copies (one copy per
+// lane per segment, one mbarrier per warp buffer, issued one segment ahead), the slot stride is
+// an odd multiple of 16 bytes so the 32 lanes' LDS.128 hit distinct bank groups.  The sample
+// loop has no cross-lane traffic at all - no shuffles, no warp reductions - only packed 16x2
+// integer ops on the lane's own registers.
+//
+// Hits: while scanning, a lane notes in a bitmask which chunks contain samples above threshold;
+// after each segment a lane-parallel pass visits only those chunks (still in the slot), walks the
+// threshold runs with bit tricks and accumulates each hit's argmax / integral on the fly; runs
+// may stay open across segments.  The pass lags the scan by kOV chunks and each slot carries
+// 2*kOV chunks of history, so the left / right extensions (<= 8*kOV samples) of any run it
+// closes are always inside the slot.  Hits go to a per-warp shared-memory pool (claimed with a
+// shared-memory atomic); one decoupled look-back per 128-record tile gives the first output
+// row; rows are assembled one hit per lane.
 //
 // Reference semantics: see fused_features_hits.cu (same arithmetic, same results).
 #include <stdlib.h>
@@ -22,8 +28,8 @@ namespace wfb {
 constexpr int kLprWarps = 4;
 constexpr int kLprTile = kLprWarps * 32;  // records per tile / look-back unit
 constexpr int kLprEnt = 320;              // staged hits per warp per tile (10 per record on average)
-constexpr int kLprMaskWords = 4;          // 128 chunks = 1024 samples (+ misalignment slack)
-constexpr int kLprMaxChunks = kLprMaskWords * 32;
+constexpr int kOV = 2;                    // chunks of lag / history: extensions up to 16 samples
+constexpr int kNBuf = 2;                  // slot buffers per lane
 
 struct LprEnt {  // 16 bytes
     unsigned ps;   // p | s << 16
@@ -37,10 +43,37 @@ struct LaneRec {  // everything a lane knows about its record
     unsigned bc;
     double b_rec, b_feat, thr;
     int kmax;
-    // hit integral constants (see hit_constants in fused_features_hits.cu)
-    double bi, bf;
+    double bi, bf;  // floor / frac of b_rec, integer bound of the signal side (hit integral)
     int wlim;
     bool b_small, positive;
+};
+
+struct FeatState {  // per-lane feature accumulators
+    unsigned pmin, pmax, pdiff, isum32, prev_w;
+    int imin, imax, idiff;
+    double dsum;
+};
+
+// running aggregates of the open run of a lane
+struct RunAgg {
+    int kbest, ibest;
+    unsigned cnt;
+    unsigned long long sw;
+    __device__ __forceinline__ void reset() { kbest = INT_MAX; ibest = INT_MAX; cnt = 0; sw = 0; }
+    __device__ __forceinline__ void add(int i, int w, const LaneRec& r) {  // w in the offset domain
+        int kv = r.positive ? 65535 - w : w;
+        if (kv < kbest) { kbest = kv; ibest = i; }
+        bool in = r.positive ? (w >= r.wlim + r.bias) : (w <= r.wlim + r.bias);
+        cnt += in ? 1u : 0u;
+        sw += in ? (unsigned)w : 0u;
+    }
+};
+
+struct HitState {  // per-lane state of the run walker, lives across segments
+    bool open;
+    int run_s, prev_c, nh;
+    unsigned carry;  // interesting-chunk bits of the previous segment not yet visited
+    RunAgg g;
 };
 
 __device__ __forceinline__ int u16_at(const uint4& q, int j) {
@@ -69,9 +102,10 @@ struct PoolSink {
 };
 struct DirectSink {  // rows straight to the output (records whose hits did not fit the pool)
     long long row0;
+    bool active;
     __device__ __forceinline__ void store(int p, int s, int e, float height, float integral, int ord, const LaneRec& r, const FHArgs& a) {
         long long row = row0 + ord;
-        if (row < a.hit_cap) {
+        if (active && row < a.hit_cap) {
             RowRec rr{r.ts, r.rid, r.len, r.dt, r.bc};
             unsigned w[15];
             hit_row_words(w, p, s, e, height, integral, rr, a.p.left_extension, a.p.right_extension, a.lmax);
@@ -82,46 +116,27 @@ struct DirectSink {  // rows straight to the output (records whose hits did not 
     }
 };
 
-// running aggregates of the open run of a lane
-struct RunAgg {
-    int kbest, ibest;
-    unsigned cnt;
-    unsigned long long sw;
-    __device__ __forceinline__ void reset() { kbest = INT_MAX; ibest = INT_MAX; cnt = 0; sw = 0; }
-    // one sample at record index i with stored (offset-domain) value w
-    __device__ __forceinline__ void add(int i, int w, const LaneRec& r) {
-        int kv = r.positive ? 65535 - w : w;
-        if (kv < kbest) { kbest = kv; ibest = i; }
-        bool in = r.positive ? (w >= r.wlim + r.bias) : (w <= r.wlim + r.bias);
-        cnt += in ? 1u : 0u;
-        sw += in ? (unsigned)w : 0u;
-    }
-};
-
-// ---- lane-parallel hit pass over the interesting chunks of each lane's record ----------------
+// ---- lane-parallel hit pass over one window of chunks ------------------------------------------
+// `buf` is the lane's slot for the current segment; slot chunk k holds global chunk c = cbase + k.
+// `hw` bit t marks global chunk c = c0 + t as interesting.
 template <typename Sink>
-__device__ __forceinline__ int lpr_hit_pass(const uint8_t* slot, const LaneRec& r, const FHArgs& a, const unsigned (&mask)[kLprMaskWords],
-                                            Sink& sink) {
+__device__ __forceinline__ void lpr_hit_window(const uint8_t* buf, int cbase, int c0, int c_end, unsigned hw, const LaneRec& r,
+                                               const FHArgs& a, HitState& hs, Sink& sink) {
     const unsigned sx = r.bias ? 0x80008000u : 0u;
     const unsigned xm = r.positive ? 0xffffffffu : 0u;
-    const unsigned short* s16 = reinterpret_cast<const unsigned short*>(slot);
+    const unsigned short* s16 = reinterpret_cast<const unsigned short*>(buf);
     const int left = a.p.left_extension, right = a.p.right_extension;
     const int vtotal = r.mis + r.len;
-    int nh = 0;
-    bool open = false;
-    int run_s = 0, prev_c = -2;
-    RunAgg g;
-    g.reset();
-    auto sample = [&](int i) -> int {  // stored value of record sample i, padding = 0 in the true domain
-        return (i < r.len) ? ((int)s16[r.mis + i] ^ (int)(sx & 0xffffu)) : r.bias;
+    auto sample = [&](int i) -> int {  // stored (offset-domain) value of record sample i; padding = true 0
+        return (i < r.len) ? ((int)s16[r.mis + i - cbase * 8] ^ (int)(sx & 0xffffu)) : r.bias;
     };
     auto close_run = [&](int e) {
         const int a1 = min(a.lmax, e + right);
-        for (int i = e; i < a1; ++i) g.add(i, sample(i), r);
-        const int wp = (r.positive ? 65535 - g.kbest : g.kbest) - r.bias;
+        for (int i = e; i < a1; ++i) hs.g.add(i, sample(i), r);
+        const int wp = (r.positive ? 65535 - hs.g.kbest : hs.g.kbest) - r.bias;
         const float height = (float)(r.positive ? __dsub_rn((double)wp, r.b_rec) : __dsub_rn(r.b_rec, (double)wp));
-        const long long c = g.cnt;
-        const long long swt = (long long)g.sw - c * r.bias;
+        const long long c = hs.g.cnt;
+        const long long swt = (long long)hs.g.sw - c * r.bias;
         double integ;
         if (r.b_small) {
             long long ipart = r.positive ? (swt - c * (long long)r.bi) : (c * (long long)r.bi - swt);
@@ -130,79 +145,223 @@ __device__ __forceinline__ int lpr_hit_pass(const uint8_t* slot, const LaneRec& 
         } else {
             integ = r.positive ? __dsub_rn((double)swt, __dmul_rn((double)c, r.b_rec)) : __dsub_rn(__dmul_rn((double)c, r.b_rec), (double)swt);
         }
-        sink.store(g.ibest, run_s, e, height, (float)integ, nh, r, a);
-        ++nh;
-        open = false;
+        sink.store(hs.g.ibest, hs.run_s, e, height, (float)integ, hs.nh, r, a);
+        ++hs.nh;
+        hs.open = false;
     };
     auto open_run = [&](int s) {
-        open = true;
-        run_s = s;
-        g.reset();
-        for (int i = max(0, s - left); i < s; ++i) g.add(i, sample(i), r);
+        hs.open = true;
+        hs.run_s = s;
+        hs.g.reset();
+        for (int i = max(0, s - left); i < s; ++i) hs.g.add(i, sample(i), r);
     };
+    // a run left open by the previous window ends at the window start if the next chunk is quiet
+    if (hs.open && hs.prev_c + 1 == c0 && !(hw & 1u)) close_run(c0 * 8 - r.mis);
+    unsigned m = hw;
+    while (m) {
+        const int t = __ffs(m) - 1;
+        m &= m - 1;
+        const int c = c0 + t;
+        if (hs.open && c != hs.prev_c + 1) close_run((hs.prev_c + 1) * 8 - r.mis);  // a quiet chunk in between
+        hs.prev_c = c;
+        uint4 q = *reinterpret_cast<const uint4*>(buf + (c - cbase) * 16);
+        q.x ^= sx; q.y ^= sx; q.z ^= sx; q.w ^= sx;
+        const int v0 = c * 8;
+        const int lo = min(max(r.mis - v0, 0), 8), hi = min(max(vtotal - v0, 0), 8);
+        int wv[8];
+        unsigned m8 = 0;
 #pragma unroll
-    for (int wd = 0; wd < kLprMaskWords; ++wd) {
-        unsigned m = mask[wd];
-        while (m) {
-            const int c = wd * 32 + __ffs(m) - 1;
-            m &= m - 1;
-            if (open && c != prev_c + 1) close_run((prev_c + 1) * 8 - r.mis);  // the chunk in between is below threshold
-            prev_c = c;
-            uint4 q = *reinterpret_cast<const uint4*>(slot + c * 16);
-            q.x ^= sx; q.y ^= sx; q.z ^= sx; q.w ^= sx;
-            const int v0 = c * 8;
-            const int lo = min(max(r.mis - v0, 0), 8), hi = min(max(vtotal - v0, 0), 8);
-            int wv[8];
-            unsigned m8 = 0;
+        for (int j = 0; j < 8; ++j) {
+            wv[j] = u16_at(q, j);
+            int kv = (int)((unsigned)wv[j] ^ (xm & 0xffffu));
+            m8 |= ((kv <= r.kmax && j >= lo && j < hi) ? 1u : 0u) << j;
+        }
+        const int i0 = v0 - r.mis;
+        int j = 0;
+        while (j < 8) {
+            if (hs.open) {
+                const unsigned tz = (~(m8 >> j)) | 0x100u;  // first zero at or after j
+                const int ones = min(__ffs(tz) - 1, 8 - j);
+                const unsigned rm = ((1u << (j + ones)) - 1u) & ~((1u << j) - 1u);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                wv[j] = u16_at(q, j);
-                int kv = (int)((unsigned)wv[j] ^ (xm & 0xffffu));
-                m8 |= ((kv <= r.kmax && j >= lo && j < hi) ? 1u : 0u) << j;
-            }
-            const int i0 = v0 - r.mis;
-            int j = 0;
-            while (j < 8) {
-                if (open) {
-                    const unsigned t = (~(m8 >> j)) | 0x100u;          // first zero at or after j
-                    const int ones = min(__ffs(t) - 1, 8 - j);
-                    const unsigned rm = ((1u << (j + ones)) - 1u) & ~((1u << j) - 1u);
-#pragma unroll
-                    for (int jj = 0; jj < 8; ++jj)
-                        if ((rm >> jj) & 1u) g.add(i0 + jj, wv[jj], r);
-                    j += ones;
-                    if (j < 8) close_run(i0 + j);
-                } else {
-                    const unsigned t = m8 >> j;
-                    if (!t) break;
-                    j += __ffs(t) - 1;
-                    open_run(i0 + j);
-                }
+                for (int jj = 0; jj < 8; ++jj)
+                    if ((rm >> jj) & 1u) hs.g.add(i0 + jj, wv[jj], r);
+                j += ones;
+                if (j < 8) close_run(i0 + j);
+            } else {
+                const unsigned tt = m8 >> j;
+                if (!tt) break;
+                j += __ffs(tt) - 1;
+                open_run(i0 + j);
             }
         }
     }
-    if (open) close_run(min(r.len, (prev_c + 1) * 8 - r.mis));
-    return nh;
+    // still open after the last interesting chunk of the window and the next chunk (quiet, or past
+    // the record end) belongs to this window: the run ends there, its extension is in the slot
+    if (hs.open && hs.prev_c + 1 < c_end) close_run(min(r.len, (hs.prev_c + 1) * 8 - r.mis));
+}
+
+// ---- stream one record per lane through the slot ring -------------------------------------------
+struct Ring {
+    uint8_t* slot;  // this lane's slots: kNBuf buffers at stride buf_stride
+    int buf_stride;
+    unsigned long long* bars;  // kNBuf mbarriers of this warp
+    unsigned* phase_bits;
+};
+
+template <bool FEAT, bool HITS, typename Sink>
+__device__ __forceinline__ void lpr_stream(const FHArgs& a, const uint16_t* pool, const LaneRec& r, int sc, const Ring& ring,
+                                           int p0, int p1, int c0, int c1, FeatState& fs, HitState& hs, Sink& sink) {
+    const int lane = lane_id();
+    const int mis = r.mis, vtotal = r.mis + r.len;
+    const int nch = (r.len > 0) ? ((vtotal + 7) >> 3) : 0;
+    const int nch_max = __reduce_max_sync(kFull, nch);
+    const int nseg = (nch_max + sc - 1) / sc;
+    const bool known = r.pol == WFB_POL_POSITIVE || r.pol == WFB_POL_NEGATIVE;
+    const unsigned sx32 = r.bias ? 0x80008000u : 0u;
+    const unsigned xm = r.positive ? 0xffffffffu : 0u;
+    const float b32 = (float)r.b_feat;
+
+    auto issue = [&](int s) {
+        const int b = s % kNBuf;
+        const int cb = s * sc - 2 * kOV;  // global chunk held by slot chunk 0
+        const int clo = max(0, cb), chi = min(nch, (s + 1) * sc);
+        const unsigned bytes = chi > clo ? (unsigned)(chi - clo) * 16u : 0u;
+        fence_proxy_async();  // generic reads of this buffer (two segments ago) before the refill
+        const unsigned total = __reduce_add_sync(kFull, bytes);
+        if (lane == 0) {
+            if (total) mbar_arrive_expect_tx(&ring.bars[b], total);
+            else mbar_arrive(&ring.bars[b]);
+        }
+        __syncwarp();
+        if (bytes) tma_bulk_g2s(ring.slot + b * ring.buf_stride + (clo - cb) * 16, pool + (r.off - mis) + (long long)clo * 8, bytes, &ring.bars[b]);
+    };
+
+    if (nseg > 0) issue(0);
+    for (int s = 0; s < nseg; ++s) {
+        const int b = s % kNBuf;
+        if (s + 1 < nseg) issue(s + 1);
+        mbar_wait(&ring.bars[b], (*ring.phase_bits >> b) & 1u);
+        *ring.phase_bits ^= 1u << b;
+        const uint8_t* buf = ring.slot + b * ring.buf_stride;
+        const int cbase = s * sc - 2 * kOV;
+        unsigned mw = 0;
+        const int cend = min(sc, nch_max - s * sc);
+        for (int cb = 0; cb < cend; ++cb) {
+            const int vc = s * sc + cb;
+            if (vc >= nch) continue;
+            uint4 q = *reinterpret_cast<const uint4*>(buf + (2 * kOV + cb) * 16);
+            q.x ^= sx32; q.y ^= sx32; q.z ^= sx32; q.w ^= sx32;  // int16 -> offset binary
+            const int v0 = vc * 8;
+            const int lo = max(mis - v0, 0), hi = min(vtotal - v0, 8);
+            const int i0 = v0 - mis;
+            if (lo == 0 && hi == 8) {
+                if (FEAT) {
+                    const unsigned pw = (i0 > 0) ? fs.prev_w : (q.x << 16);
+                    unsigned f0 = __funnelshift_r(pw, q.x, 16), f1 = __funnelshift_r(q.x, q.y, 16);
+                    unsigned f2 = __funnelshift_r(q.y, q.z, 16), f3 = __funnelshift_r(q.z, q.w, 16);
+                    unsigned d0 = __vmaxu2(q.x, f0) - __vminu2(q.x, f0), d1 = __vmaxu2(q.y, f1) - __vminu2(q.y, f1);
+                    unsigned d2 = __vmaxu2(q.z, f2) - __vminu2(q.z, f2), d3 = __vmaxu2(q.w, f3) - __vminu2(q.w, f3);
+                    fs.pdiff = __vmaxu2(fs.pdiff, __vmaxu2(__vmaxu2(d0, d1), __vmaxu2(d2, d3)));
+                    const int jlo = max(0, p0 - i0), jhi = min(8, p1 - i0);
+                    if (jhi > jlo) {
+                        if (jlo == 0 && jhi == 8) {
+                            fs.pmin = __vminu2(fs.pmin, __vminu2(__vminu2(q.x, q.y), __vminu2(q.z, q.w)));
+                            fs.pmax = __vmaxu2(fs.pmax, __vmaxu2(__vmaxu2(q.x, q.y), __vmaxu2(q.z, q.w)));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                int w = u16_at(q, j);
+                                if (j >= jlo && j < jhi) { fs.imin = min(fs.imin, w); fs.imax = max(fs.imax, w); }
+                            }
+                        }
+                    }
+                    const int klo = max(0, c0 - i0), khi = min(8, c1 - i0);
+                    if (khi > klo) {
+                        if (klo == 0 && khi == 8 && !known) {
+                            unsigned sacc = __dp2a_lo(q.x, 0x0101u, fs.isum32);
+                            sacc = __dp2a_lo(q.y, 0x0101u, sacc);
+                            sacc = __dp2a_lo(q.z, 0x0101u, sacc);
+                            fs.isum32 = __dp2a_lo(q.w, 0x0101u, sacc);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                unsigned w = (unsigned)u16_at(q, j);
+                                if (j >= klo && j < khi) {
+                                    if (!known) fs.isum32 += w;
+                                    else fs.dsum += (double)(r.positive ? __fsub_rn((float)w, b32) : __fsub_rn(b32, (float)w));
+                                }
+                            }
+                        }
+                    }
+                }
+                if (HITS) {
+                    unsigned mn = __vminu2(__vminu2(q.x ^ xm, q.y ^ xm), __vminu2(q.z ^ xm, q.w ^ xm));
+                    int lmin = (int)min(mn & 0xffffu, mn >> 16);
+                    mw |= (lmin <= r.kmax ? 1u : 0u) << cb;
+                }
+            } else {
+                // partial chunk (record start / end): per-sample
+                const int prev_s = (int)(fs.prev_w >> 16);
+                bool any = false;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int w = u16_at(q, j);
+                    const bool ok = (j >= lo) && (j < hi);
+                    if (FEAT && ok) {
+                        const int i = i0 + j;
+                        if (i > 0) fs.idiff = max(fs.idiff, abs(w - ((j == 0) ? prev_s : u16_at(q, j - 1))));
+                        if (i >= p0 && i < p1) { fs.imin = min(fs.imin, w); fs.imax = max(fs.imax, w); }
+                        if (i >= c0 && i < c1) {
+                            if (!known) fs.isum32 += (unsigned)w;
+                            else fs.dsum += (double)(r.positive ? __fsub_rn((float)w, b32) : __fsub_rn(b32, (float)w));
+                        }
+                    }
+                    if (HITS && ok) any = any || ((int)((unsigned)w ^ (xm & 0xffffu)) <= r.kmax);
+                }
+                if (HITS) mw |= (any ? 1u : 0u) << cb;
+            }
+            fs.prev_w = q.w;
+        }
+        if (HITS) {
+            // window of this pass: chunks [s*sc - kOV, (s+1)*sc - kOV), the last segment runs to the end
+            const bool last = (s == nseg - 1);
+            unsigned hw = hs.carry | (mw << kOV);
+            if (!last) {
+                hs.carry = hw >> sc;                 // chunks (s+1)*sc - kOV .. : next pass
+                hw &= (sc >= 32) ? 0xffffffffu : ((1u << sc) - 1u);
+            }
+            // chunks past the end of the window: the last pass covers everything that is left
+            const int c_end = last ? (1 << 28) : (s + 1) * sc - kOV;
+            lpr_hit_window(buf, cbase, s * sc - kOV, c_end, hw, r, a, hs, sink);
+        }
+        __syncwarp();  // every lane is done with buffer b before it is refilled
+    }
 }
 
 // ---- the kernel --------------------------------------------------------------------------------
 template <bool FEAT, bool HITS>
-__global__ void __launch_bounds__(kLprWarps * 32, 1) lpr_kernel(const FHArgs a) {
-    extern __shared__ __align__(16) uint8_t dyn_smem[];  // [warp][lane] slots of a.slot_bytes
+__global__ void __launch_bounds__(kLprWarps * 32) lpr_kernel(const FHArgs a, const int sc) {
+    extern __shared__ __align__(16) uint8_t dyn_smem[];  // [warp][lane][kNBuf] slots of a.slot_bytes
     __shared__ __align__(16) LprEnt s_ent[HITS ? kLprWarps : 1][HITS ? kLprEnt : 1];
     __shared__ int s_pool[kLprWarps];
     __shared__ long long s_wtot[kLprWarps];
     __shared__ long long s_wbase[kLprWarps];
     __shared__ int s_tile;
-    __shared__ __align__(8) unsigned long long s_bar[kLprWarps];
+    __shared__ __align__(8) unsigned long long s_bar[kLprWarps * kNBuf];
 
     const int warp = threadIdx.x >> 5, lane = lane_id();
     const uint16_t* pool = static_cast<const uint16_t*>(a.pool);
-    uint8_t* slot = dyn_smem + ((size_t)warp * 32 + lane) * a.slot_bytes;
-    if (lane == 0) mbar_init(&s_bar[warp], 1);
+    unsigned phase_bits = 0;
+    Ring ring;
+    // lane stride = slot_bytes (odd multiple of 16): conflict-free LDS.128; buffers kNBuf apart by 32 lanes
+    ring.buf_stride = 32 * a.slot_bytes;
+    ring.slot = dyn_smem + (size_t)warp * kNBuf * ring.buf_stride + (size_t)lane * a.slot_bytes;
+    ring.bars = &s_bar[warp * kNBuf];
+    ring.phase_bits = &phase_bits;
+    if (lane < kNBuf) mbar_init(&ring.bars[lane], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
-    unsigned parity = 0;
 
     for (;;) {
         if (threadIdx.x == 0) s_tile = (int)atomicAdd(a.ticket, 1u);
@@ -241,27 +400,23 @@ __global__ void __launch_bounds__(kLprWarps * 32, 1) lpr_kernel(const FHArgs a) 
                 atomicExch(a.err_flag, 1);
                 r.len = 0;
             }
+            if (r.len > a.lmax) {
+                atomicExch(a.err_flag, 2);  // lmax passed by the caller is too small
+                r.len = 0;
+            }
         }
         r.mis = (int)(r.off & 7);
         r.bias = a.p.signed_samples ? 32768 : 0;
         r.positive = r.pol == WFB_POL_POSITIVE || r.pol == WFB_POL_RAW_POSITIVE;
         const bool rawpos = r.pol == WFB_POL_RAW_POSITIVE;
         const bool known = r.pol == WFB_POL_POSITIVE || r.pol == WFB_POL_NEGATIVE;
-        const int len = r.len, mis = r.mis;
-        int vtotal = mis + len;
-        unsigned copy_bytes = len > 0 ? (unsigned)(((vtotal + 7) & ~7) * 2) : 0u;
-        if ((int)copy_bytes > a.slot_bytes) {
-            atomicExch(a.err_flag, 2);  // lmax passed by the caller is too small
-            copy_bytes = 0;
-            r.len = 0;
-            vtotal = mis;
-        }
         int p0 = 0, p1 = 0, c0 = 0, c1 = 0;
         if (FEAT) {
             resolve_slice(a.p.height_start, a.p.height_end, r.len, p0, p1);
             resolve_slice(a.p.area_start, a.p.area_end, r.len, c0, c1);
         }
         r.kmax = -1;
+        r.b_small = true; r.bi = 0; r.bf = 0; r.wlim = 0;
         if (HITS && r.len > 0) {
             r.kmax = integer_threshold_u16(r.b_rec, r.thr, r.positive, r.bias);
             r.b_small = fabs(r.b_rec) < 2e9;
@@ -269,125 +424,27 @@ __global__ void __launch_bounds__(kLprWarps * 32, 1) lpr_kernel(const FHArgs a) 
             r.bf = __dsub_rn(r.b_rec, r.bi);
             const int ib = r.b_small ? (int)r.bi : (r.b_rec > 0 ? INT_MAX : INT_MIN);
             r.wlim = r.positive ? ib + 1 : ((r.bi == r.b_rec) ? ib - 1 : ib);
-        } else {
-            r.b_small = true; r.bi = 0; r.bf = 0; r.wlim = 0;
         }
 
-        // ---------------- stage the 32 records of this warp: one TMA bulk copy per lane
-        {
-            fence_proxy_async();
-            const unsigned total = __reduce_add_sync(kFull, copy_bytes);
-            if (lane == 0) {
-                if (total) mbar_arrive_expect_tx(&s_bar[warp], total);
-                else mbar_arrive(&s_bar[warp]);
-            }
-            __syncwarp();
-            if (copy_bytes) tma_bulk_g2s(slot, pool + (r.off - mis), copy_bytes, &s_bar[warp]);
-            mbar_wait(&s_bar[warp], parity);
-            parity ^= 1u;
-        }
-
-        // ---------------- scan: features + interesting-chunk mask, 8 samples per step
-        const int nch = (vtotal > mis) ? ((vtotal + 7) >> 3) : 0;
-        const int nch_max = __reduce_max_sync(kFull, nch);
-        const unsigned sx32 = r.bias ? 0x80008000u : 0u;
-        const unsigned xm = r.positive ? 0xffffffffu : 0u;
-        const float b32 = (float)r.b_feat;
-        unsigned pmin = 0xffffffffu, pmax = 0u, pdiff = 0u, isum32 = 0;
-        int imin = INT_MAX, imax = INT_MIN, idiff = 0;
-        double dsum = 0.0;
-        unsigned prev_w = 0;
-        unsigned mask[kLprMaskWords];
-#pragma unroll
-        for (int wd = 0; wd < kLprMaskWords; ++wd) {
-            unsigned mw = 0;
-            const int cend = min(32, nch_max - wd * 32);
-            for (int cb = 0; cb < cend; ++cb) {
-                const int vc = wd * 32 + cb;
-                if (vc >= nch) continue;
-                uint4 q = *reinterpret_cast<const uint4*>(slot + vc * 16);
-                q.x ^= sx32; q.y ^= sx32; q.z ^= sx32; q.w ^= sx32;  // int16 -> offset binary
-                const int v0 = vc * 8;
-                const int lo = max(mis - v0, 0), hi = min(vtotal - v0, 8);
-                const int i0 = v0 - mis;
-                if (lo == 0 && hi == 8) {
-                    if (FEAT) {
-                        const unsigned pw = (i0 > 0) ? prev_w : (q.x << 16);
-                        unsigned f0 = __funnelshift_r(pw, q.x, 16), f1 = __funnelshift_r(q.x, q.y, 16);
-                        unsigned f2 = __funnelshift_r(q.y, q.z, 16), f3 = __funnelshift_r(q.z, q.w, 16);
-                        unsigned d0 = __vmaxu2(q.x, f0) - __vminu2(q.x, f0), d1 = __vmaxu2(q.y, f1) - __vminu2(q.y, f1);
-                        unsigned d2 = __vmaxu2(q.z, f2) - __vminu2(q.z, f2), d3 = __vmaxu2(q.w, f3) - __vminu2(q.w, f3);
-                        pdiff = __vmaxu2(pdiff, __vmaxu2(__vmaxu2(d0, d1), __vmaxu2(d2, d3)));
-                        const int jlo = max(0, p0 - i0), jhi = min(8, p1 - i0);
-                        if (jhi > jlo) {
-                            if (jlo == 0 && jhi == 8) {
-                                pmin = __vminu2(pmin, __vminu2(__vminu2(q.x, q.y), __vminu2(q.z, q.w)));
-                                pmax = __vmaxu2(pmax, __vmaxu2(__vmaxu2(q.x, q.y), __vmaxu2(q.z, q.w)));
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    int w = u16_at(q, j);
-                                    if (j >= jlo && j < jhi) { imin = min(imin, w); imax = max(imax, w); }
-                                }
-                            }
-                        }
-                        const int klo = max(0, c0 - i0), khi = min(8, c1 - i0);
-                        if (khi > klo) {
-                            if (klo == 0 && khi == 8 && !known) {
-                                unsigned s = __dp2a_lo(q.x, 0x0101u, isum32);
-                                s = __dp2a_lo(q.y, 0x0101u, s);
-                                s = __dp2a_lo(q.z, 0x0101u, s);
-                                isum32 = __dp2a_lo(q.w, 0x0101u, s);
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    unsigned w = (unsigned)u16_at(q, j);
-                                    if (j >= klo && j < khi) {
-                                        if (!known) isum32 += w;
-                                        else dsum += (double)(r.positive ? __fsub_rn((float)w, b32) : __fsub_rn(b32, (float)w));
-                                    }
-                                }
-                            }
-                        }
-                    }
-                    if (HITS) {
-                        unsigned mn = __vminu2(__vminu2(q.x ^ xm, q.y ^ xm), __vminu2(q.z ^ xm, q.w ^ xm));
-                        int lmin = (int)min(mn & 0xffffu, mn >> 16);
-                        mw |= (lmin <= r.kmax ? 1u : 0u) << cb;
-                    }
-                } else {
-                    // partial chunk (record start / end): per-sample
-                    const int prev_s = (int)(prev_w >> 16);
-                    bool any = false;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int w = u16_at(q, j);
-                        const bool ok = (j >= lo) && (j < hi);
-                        if (FEAT && ok) {
-                            const int i = i0 + j;
-                            if (i > 0) idiff = max(idiff, abs(w - ((j == 0) ? prev_s : u16_at(q, j - 1))));
-                            if (i >= p0 && i < p1) { imin = min(imin, w); imax = max(imax, w); }
-                            if (i >= c0 && i < c1) {
-                                if (!known) isum32 += (unsigned)w;
-                                else dsum += (double)(r.positive ? __fsub_rn((float)w, b32) : __fsub_rn(b32, (float)w));
-                            }
-                        }
-                        if (HITS && ok) any = any || ((int)((unsigned)w ^ (xm & 0xffffu)) <= r.kmax);
-                    }
-                    if (HITS) mw |= (any ? 1u : 0u) << cb;
-                }
-                prev_w = q.w;
-            }
-            mask[wd] = mw;
-        }
+        // ---------------- stream the record: features + hits into the warp's pool
+        FeatState fs;
+        fs.pmin = 0xffffffffu; fs.pmax = 0u; fs.pdiff = 0u; fs.isum32 = 0u; fs.prev_w = 0u;
+        fs.imin = INT_MAX; fs.imax = INT_MIN; fs.idiff = 0; fs.dsum = 0.0;
+        HitState hs;
+        hs.open = false; hs.run_s = 0; hs.prev_c = -4; hs.nh = 0; hs.carry = 0u; hs.g.reset();
+        if (HITS && lane == 0) s_pool[warp] = 0;
+        __syncwarp();
+        PoolSink psink{HITS ? &s_ent[warp][0] : nullptr, &s_pool[warp], false};
+        lpr_stream<FEAT, HITS>(a, pool, r, sc, ring, p0, p1, c0, c1, fs, hs, psink);
 
         // ---------------- features of my record
         if (FEAT && have) {
+            const float b32 = (float)r.b_feat;
             float height = 0.f, amp = 0.f, area = 0.f;
-            const float mad = (float)max(idiff, (int)max(pdiff & 0xffffu, pdiff >> 16));
+            const float mad = (float)max(fs.idiff, (int)max(fs.pdiff & 0xffffu, fs.pdiff >> 16));
             if (p1 > p0) {
-                const int wmin = min(imin, (int)min(pmin & 0xffffu, pmin >> 16));
-                const int wmax = max(imax, (int)max(pmax & 0xffffu, pmax >> 16));
+                const int wmin = min(fs.imin, (int)min(fs.pmin & 0xffffu, fs.pmin >> 16));
+                const int wmax = max(fs.imax, (int)max(fs.pmax & 0xffffu, fs.pmax >> 16));
                 if (!known) {
                     height = rawpos ? (float)__dsub_rn((double)(wmax - r.bias), r.b_feat) : (float)__dsub_rn(r.b_feat, (double)(wmin - r.bias));
                     amp = (float)(wmax - wmin);
@@ -401,7 +458,7 @@ __global__ void __launch_bounds__(kLprWarps * 32, 1) lpr_kernel(const FHArgs a) 
             if (c1 > c0) {
                 if (!known) {
                     const long long nC = c1 - c0;
-                    const long long sw = (long long)isum32 - nC * r.bias;
+                    const long long sw = (long long)fs.isum32 - nC * r.bias;
                     const double b = r.b_feat;
                     double ar;
                     if (fabs(b) < 1e12) {
@@ -414,7 +471,7 @@ __global__ void __launch_bounds__(kLprWarps * 32, 1) lpr_kernel(const FHArgs a) 
                     }
                     area = (float)ar;
                 } else {
-                    area = (float)dsum;
+                    area = (float)fs.dsum;
                 }
             }
             unsigned* dst = reinterpret_cast<unsigned*>(a.feat_out + rec * kFeatRowBytes);
@@ -430,15 +487,10 @@ __global__ void __launch_bounds__(kLprWarps * 32, 1) lpr_kernel(const FHArgs a) 
             dst[8] = (unsigned)((unsigned long long)ev >> 32);
         }
         if (!HITS) {
-            __syncthreads();  // s_tile reuse; slots are refilled after the next ticket
+            __syncthreads();  // s_tile reuse
             continue;
         }
-
-        // ---------------- hits: lane-parallel pass over the interesting chunks
-        if (lane == 0) s_pool[warp] = 0;
-        __syncwarp();
-        PoolSink psink{&s_ent[warp][0], &s_pool[warp], false};
-        const int my_cnt = lpr_hit_pass(slot, r, a, mask, psink);
+        const int my_cnt = hs.nh;
         if (a.hit_counts != nullptr && have) a.hit_counts[rec] = my_cnt;
 
         int incl = my_cnt;
@@ -489,9 +541,12 @@ __global__ void __launch_bounds__(kLprWarps * 32, 1) lpr_kernel(const FHArgs a) 
                 for (int k = 0; k < 15; ++k) dst[k] = w[k];
             }
         }
-        if (psink.overflow) {  // my hits did not all fit the pool: write all of them directly
-            DirectSink dsink{my_row0};
-            lpr_hit_pass(slot, r, a, mask, dsink);
+        if (ovf) {  // some records' hits did not all fit the pool: stream those again, rows go straight out
+            FeatState fs2 = fs;
+            HitState hs2;
+            hs2.open = false; hs2.run_s = 0; hs2.prev_c = -4; hs2.nh = 0; hs2.carry = 0u; hs2.g.reset();
+            DirectSink dsink{my_row0, psink.overflow};
+            lpr_stream<false, true>(a, pool, r, sc, ring, 0, 0, 0, 0, fs2, hs2, dsink);
         }
         __syncthreads();  // pool, slots and s_tile are reused by the next tile
     }
@@ -501,14 +556,15 @@ int launch_lpr(FHArgs a, int flags, cudaStream_t st) {
     if (a.p.pool_is_f32) return 1;
     const char* force = getenv("WFB_FUSED_VARIANT");
     if (force && (!strcmp(force, "global") || !strcmp(force, "staged"))) return 1;
-    if (a.lmax + 8 > kLprMaxChunks * 8 - 8 || a.lmax >= 65536) return 1;
-    // slot: record rounded out to 16-byte boundaries, stride an odd multiple of 16 bytes so the
-    // 32 lanes of a warp read distinct bank groups
-    long long slot = ((long long)a.lmax * 2 + 15 + 14) & ~15ll;
-    if (((slot >> 4) & 1) == 0) slot += 16;
-    const size_t dyn = (size_t)kLprTile * slot;
-    if (dyn > 200 * 1024) return 1;
-    a.slot_bytes = (int)slot;
+    if (a.lmax >= 65536 - 16) return 1;  // positions are packed in 16 bits
+    if (a.p.left_extension > 8 * kOV || a.p.right_extension > 8 * kOV) return 1;
+    // segment length in chunks: 2 * kOV history chunks + sc new chunks per slot, sc + kOV <= 32 mask bits
+    int sc = 12;
+    if (const char* e = getenv("WFB_LPR_SC")) sc = std::max(4, std::min(30, atoi(e)));
+    int slot_chunks = sc + 2 * kOV;
+    if ((slot_chunks & 1) == 0) ++slot_chunks;  // odd multiple of 16 bytes: conflict-free LDS.128
+    a.slot_bytes = slot_chunks * 16;
+    const size_t dyn = (size_t)kLprTile * kNBuf * a.slot_bytes;
     a.n_tiles = (int)((a.n + kLprTile - 1) / kLprTile);
     const bool f = flags & WFB_DO_FEATURES, h = flags & WFB_DO_HITS;
     auto go = [&](auto kern) -> int {
@@ -520,7 +576,7 @@ int launch_lpr(FHArgs a, int flags, cudaStream_t st) {
             return WFB_ERR_CUDA;
         }
         int grid = (int)std::min<long long>((long long)sm_count() * per_sm, a.n_tiles);
-        kern<<<grid, kLprWarps * 32, dyn, st>>>(a);
+        kern<<<grid, kLprWarps * 32, dyn, st>>>(a, sc);
         WFB_CUDA(cudaGetLastError());
         return WFB_OK;
     };

@@ -17,6 +17,7 @@
 // row; rows are assembled one hit per lane.
 //
 // Reference semantics: see fused_features_hits.cu (same arithmetic, same results).
+#include <cuda.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -207,7 +208,19 @@ struct Ring {
     int buf_stride;
     unsigned long long* bars;  // kNBuf mbarriers of this warp
     unsigned* phase_bits;
+    // 2-D tensor-map path: the 32 records of the warp are rows of one box (fixed-length contiguous
+    // records), fetched by ONE cp.async.bulk.tensor per segment instead of 32 bulk copies
+    const CUtensorMap* tmap;
+    bool use2d;
+    int row0;  // pool row (= record index in the pool) of lane 0's record
 };
+
+__device__ __forceinline__ void tma_tensor2d_g2s(void* dst_smem, const CUtensorMap* tmap, int x, int y, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar))
+                 : "memory");
+}
 
 template <bool FEAT, bool HITS, typename Sink>
 __device__ __forceinline__ void lpr_stream(const FHArgs& a, const uint16_t* pool, const LaneRec& r, int sc, const Ring& ring,
@@ -221,6 +234,15 @@ __device__ __forceinline__ void lpr_stream(const FHArgs& a, const uint16_t* pool
     const unsigned sx32 = r.bias ? 0x80008000u : 0u;
     const unsigned xm = r.positive ? 0xffffffffu : 0u;
     const float b32 = (float)r.b_feat;
+    // chunk ranges of the "plain" fast path: [plainA, plainB) minus [plainHa, plainHb)
+    int plainA = 0, plainB = 0, plainHa = 0, plainHb = 0;
+    if (r.len > 0 && (!FEAT || !known)) {
+        const int vlo = FEAT ? mis + max(c0, 1) : mis + 1;     // first sample that has a predecessor, inside the area range
+        const int vhi = FEAT ? mis + min(c1, r.len) : vtotal;  // end of the area range
+        plainA = (vlo + 7) >> 3;
+        plainB = vhi >> 3;
+        if (FEAT && p1 > p0) { plainHa = (mis + p0) >> 3; plainHb = (mis + p1 + 7) >> 3; }
+    }
 
     auto issue = [&](int s) {
         const int b = s % kNBuf;
@@ -228,6 +250,14 @@ __device__ __forceinline__ void lpr_stream(const FHArgs& a, const uint16_t* pool
         const int clo = max(0, cb), chi = min(nch, (s + 1) * sc);
         const unsigned bytes = chi > clo ? (unsigned)(chi - clo) * 16u : 0u;
         fence_proxy_async();  // generic reads of this buffer (two segments ago) before the refill
+        if (ring.use2d) {
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&ring.bars[b], (unsigned)ring.buf_stride);
+                tma_tensor2d_g2s(ring.slot + b * ring.buf_stride, ring.tmap, cb * 8, ring.row0, &ring.bars[b]);
+            }
+            return;
+        }
         const unsigned total = __reduce_add_sync(kFull, bytes);
         if (lane == 0) {
             if (total) mbar_arrive_expect_tx(&ring.bars[b], total);
@@ -251,11 +281,29 @@ __device__ __forceinline__ void lpr_stream(const FHArgs& a, const uint16_t* pool
             const int vc = s * sc + cb;
             if (vc >= nch) continue;
             uint4 q = *reinterpret_cast<const uint4*>(buf + (2 * kOV + cb) * 16);
-            q.x ^= sx32; q.y ^= sx32; q.z ^= sx32; q.w ^= sx32;  // int16 -> offset binary
+            if (sx32) { q.x ^= sx32; q.y ^= sx32; q.z ^= sx32; q.w ^= sx32; }  // int16 -> offset binary
             const int v0 = vc * 8;
             const int lo = max(mis - v0, 0), hi = min(vtotal - v0, 8);
             const int i0 = v0 - mis;
-            if (lo == 0 && hi == 8) {
+            if (vc >= plainA && vc < plainB && (vc < plainHa || vc >= plainHb)) {
+                // plain interior chunk: 8 valid samples inside the area range, outside the height range
+                if (FEAT) {
+                    unsigned f0 = __funnelshift_r(fs.prev_w, q.x, 16), f1 = __funnelshift_r(q.x, q.y, 16);
+                    unsigned f2 = __funnelshift_r(q.y, q.z, 16), f3 = __funnelshift_r(q.z, q.w, 16);
+                    unsigned d0 = __vmaxu2(q.x, f0) - __vminu2(q.x, f0), d1 = __vmaxu2(q.y, f1) - __vminu2(q.y, f1);
+                    unsigned d2 = __vmaxu2(q.z, f2) - __vminu2(q.z, f2), d3 = __vmaxu2(q.w, f3) - __vminu2(q.w, f3);
+                    fs.pdiff = __vmaxu2(fs.pdiff, __vmaxu2(__vmaxu2(d0, d1), __vmaxu2(d2, d3)));
+                    unsigned sacc = __dp2a_lo(q.x, 0x0101u, fs.isum32);
+                    sacc = __dp2a_lo(q.y, 0x0101u, sacc);
+                    sacc = __dp2a_lo(q.z, 0x0101u, sacc);
+                    fs.isum32 = __dp2a_lo(q.w, 0x0101u, sacc);
+                }
+                if (HITS) {
+                    unsigned mn = __vminu2(__vminu2(q.x ^ xm, q.y ^ xm), __vminu2(q.z ^ xm, q.w ^ xm));
+                    int lmin = (int)min(mn & 0xffffu, mn >> 16);
+                    mw |= (lmin <= r.kmax ? 1u : 0u) << cb;
+                }
+            } else if (lo == 0 && hi == 8) {
                 if (FEAT) {
                     const unsigned pw = (i0 > 0) ? fs.prev_w : (q.x << 16);
                     unsigned f0 = __funnelshift_r(pw, q.x, 16), f1 = __funnelshift_r(q.x, q.y, 16);
@@ -341,8 +389,9 @@ __device__ __forceinline__ void lpr_stream(const FHArgs& a, const uint16_t* pool
 
 // ---- the kernel --------------------------------------------------------------------------------
 template <bool FEAT, bool HITS>
-__global__ void __launch_bounds__(kLprWarps * 32) lpr_kernel(const FHArgs a, const int sc) {
-    extern __shared__ __align__(16) uint8_t dyn_smem[];  // [warp][lane][kNBuf] slots of a.slot_bytes
+__global__ void __launch_bounds__(kLprWarps * 32) lpr_kernel(const FHArgs a, const int sc, const __grid_constant__ CUtensorMap tmap,
+                                                             const int have_tmap) {
+    extern __shared__ __align__(128) uint8_t dyn_smem[];  // [warp][kNBuf][lane] slots of a.slot_bytes
     __shared__ __align__(16) LprEnt s_ent[HITS ? kLprWarps : 1][HITS ? kLprEnt : 1];
     __shared__ int s_pool[kLprWarps];
     __shared__ long long s_wtot[kLprWarps];
@@ -359,6 +408,9 @@ __global__ void __launch_bounds__(kLprWarps * 32) lpr_kernel(const FHArgs a, con
     ring.slot = dyn_smem + (size_t)warp * kNBuf * ring.buf_stride + (size_t)lane * a.slot_bytes;
     ring.bars = &s_bar[warp * kNBuf];
     ring.phase_bits = &phase_bits;
+    ring.tmap = &tmap;
+    ring.use2d = false;
+    ring.row0 = 0;
     if (lane < kNBuf) mbar_init(&ring.bars[lane], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
@@ -426,6 +478,13 @@ __global__ void __launch_bounds__(kLprWarps * 32) lpr_kernel(const FHArgs a, con
             r.wlim = r.positive ? ib + 1 : ((r.bi == r.b_rec) ? ib - 1 : ib);
         }
 
+        // one tensor copy per segment when the warp's records are rows of the fixed-length pool
+        {
+            const long long row = (long long)tile * kLprTile + warp * 32 + lane;  // record index == pool row
+            const bool fits = !have || (r.len == a.lmax && r.off == row * (long long)a.lmax);
+            ring.use2d = have_tmap && __all_sync(kFull, fits);
+            ring.row0 = (int)((long long)tile * kLprTile + warp * 32);
+        }
         // ---------------- stream the record: features + hits into the warp's pool
         FeatState fs;
         fs.pmin = 0xffffffffu; fs.pmax = 0u; fs.pdiff = 0u; fs.isum32 = 0u; fs.prev_w = 0u;
@@ -567,6 +626,33 @@ int launch_lpr(FHArgs a, int flags, cudaStream_t st) {
     const size_t dyn = (size_t)kLprTile * kNBuf * a.slot_bytes;
     a.n_tiles = (int)((a.n + kLprTile - 1) / kLprTile);
     const bool f = flags & WFB_DO_FEATURES, h = flags & WFB_DO_HITS;
+    // tensor map over the pool seen as rows of lmax samples: one box = 32 records x one slot
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    int have_tmap = 0;
+    const char* no2d = getenv("WFB_LPR_NO_TMAP");
+    if (!(no2d && no2d[0] == '1') && a.lmax > 0 && a.lmax % 8 == 0 && a.pool_len >= a.lmax && a.n < (1ll << 31)) {
+        typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        static encode_fn encode = nullptr;
+        if (!encode) {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+                encode = reinterpret_cast<encode_fn>(fn);
+        }
+        if (encode) {
+            cuuint64_t dims[2] = {(cuuint64_t)a.lmax, (cuuint64_t)(a.pool_len / a.lmax)};
+            cuuint64_t strides[1] = {(cuuint64_t)a.lmax * 2};
+            cuuint32_t box[2] = {(cuuint32_t)(a.slot_bytes / 2), 32};
+            cuuint32_t estr[2] = {1, 1};
+            CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(a.pool), dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            have_tmap = (cr == CUDA_SUCCESS) ? 1 : 0;
+        }
+    }
     auto go = [&](auto kern) -> int {
         WFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
         int per_sm = 0;
@@ -576,7 +662,7 @@ int launch_lpr(FHArgs a, int flags, cudaStream_t st) {
             return WFB_ERR_CUDA;
         }
         int grid = (int)std::min<long long>((long long)sm_count() * per_sm, a.n_tiles);
-        kern<<<grid, kLprWarps * 32, dyn, st>>>(a, sc);
+        kern<<<grid, kLprWarps * 32, dyn, st>>>(a, sc, tmap, have_tmap);
         WFB_CUDA(cudaGetLastError());
         return WFB_OK;
     };

@@ -1,20 +1,27 @@
 // K2 + K3, lane-per-record streaming variant (uint16 / int16 pools).
 //
 // Each LANE owns one record and streams it through a small double-buffered shared-memory slot:
-// segments of kSC 16-byte chunks (8 samples each) arrive by 1-D TMA bulk copies (one copy per
-// lane per segment, one mbarrier per warp buffer, issued one segment ahead), the slot stride is
-// an odd multiple of 16 bytes so the 32 lanes' LDS.128 hit distinct bank groups.  The sample
-// loop has no cross-lane traffic at all - no shuffles, no warp reductions - only packed 16x2
-// integer ops on the lane's own registers.
+// segments of `sc` 16-byte chunks (8 samples each) arrive by TMA - one 2-D tensor copy per warp
+// and segment when the 32 records are rows of a fixed-length pool, else one 1-D bulk copy per
+// lane - issued one segment ahead; the slot stride is an odd multiple of 16 bytes so the 32 lanes'
+// LDS.128 hit distinct bank groups.  The sample loop has no cross-lane traffic: packed 16x2
+// integer min / max / |diff| / dot-product-sum on the lane's own registers.
 //
-// Hits: while scanning, a lane notes in a bitmask which chunks contain samples above threshold;
-// after each segment a lane-parallel pass visits only those chunks (still in the slot), walks the
-// threshold runs with bit tricks and accumulates each hit's argmax / integral on the fly; runs
-// may stay open across segments.  The pass lags the scan by kOV chunks and each slot carries
-// 2*kOV chunks of history, so the left / right extensions (<= 8*kOV samples) of any run it
-// closes are always inside the slot.  Hits go to a per-warp shared-memory pool (claimed with a
-// shared-memory atomic); one decoupled look-back per 128-record tile gives the first output
-// row; rows are assembled one hit per lane.
+// Hits are found in two layers so that the per-sample run walking is done densely:
+//   * the converged scan classifies each chunk from two packed reductions (min and max of the
+//     threshold keys): QUIET (no sample above threshold), FULL (all eight above) or MIXED.  FULL
+//     chunks only feed a per-lane running aggregate (first arg-min key, count, sum) - they are
+//     interior to a run.  Every run start and end lies in a non-FULL chunk that is MIXED, follows
+//     an above-threshold sample or precedes a FULL chunk; those chunks become ITEMS: the lane
+//     copies the chunk with both neighbours (48 bytes: the extensions, <= 8 samples, live there)
+//     plus a snapshot of its FULL-chunk aggregate into a 32-entry per-warp queue;
+//   * whenever the queue fills, the warp runs a DENSE ROUND: lane t takes item t whoever owns it,
+//     fetches the owner's record constants by shuffle, walks the runs of that chunk, and stitches
+//     "run still open at the chunk end" fragments to the next item of the same record through a
+//     per-owner carry in shared memory (the items of one record are consecutive in chunk order
+//     and only FULL chunks can lie between the two ends of a run).  Finished hits carry their
+//     owner and per-record ordinal into a per-warp pool; one decoupled look-back per 128-record
+//     tile gives the first output row; rows are assembled one hit per lane.
 //
 // Reference semantics: see fused_features_hits.cu (same arithmetic, same results).
 #include <cuda.h>
@@ -28,9 +35,11 @@ namespace wfb {
 
 constexpr int kLprWarps = 4;
 constexpr int kLprTile = kLprWarps * 32;  // records per tile / look-back unit
-constexpr int kLprEnt = 320;              // staged hits per warp per tile (10 per record on average)
-constexpr int kOV = 2;                    // chunks of lag / history: extensions up to 16 samples
+constexpr int kLprEnt = 256;              // staged hits per warp per tile (8 per record on average)
+constexpr int kHist = 2;                  // chunks of history in front of each segment
+constexpr int kMaxExt = 8;                // extensions must fit the neighbouring chunk
 constexpr int kNBuf = 2;                  // slot buffers per lane
+constexpr int kQCap = 32;                 // items per dense round
 
 struct LprEnt {  // 16 bytes
     unsigned ps;   // p | s << 16
@@ -44,9 +53,8 @@ struct LaneRec {  // everything a lane knows about its record
     unsigned bc;
     double b_rec, b_feat, thr;
     int kmax;
-    double bi, bf;  // floor / frac of b_rec, integer bound of the signal side (hit integral)
-    int wlim;
-    bool b_small, positive;
+    int wlim;  // integer bound of the samples on the signal side of the baseline (hit integral)
+    bool positive, degen;
 };
 
 struct FeatState {  // per-lane feature accumulators
@@ -55,26 +63,22 @@ struct FeatState {  // per-lane feature accumulators
     double dsum;
 };
 
-// running aggregates of the open run of a lane
-struct RunAgg {
-    int kbest, ibest;
-    unsigned cnt;
-    unsigned long long sw;
-    __device__ __forceinline__ void reset() { kbest = INT_MAX; ibest = INT_MAX; cnt = 0; sw = 0; }
-    __device__ __forceinline__ void add(int i, int w, const LaneRec& r) {  // w in the offset domain
-        int kv = r.positive ? 65535 - w : w;
-        if (kv < kbest) { kbest = kv; ibest = i; }
-        bool in = r.positive ? (w >= r.wlim + r.bias) : (w <= r.wlim + r.bias);
-        cnt += in ? 1u : 0u;
-        sw += in ? (unsigned)w : 0u;
-    }
+struct HitScan {  // per-lane chunk classification pipeline, lives across segments
+    unsigned fa_key, fa_cnt, fa_sw;  // aggregate of the FULL chunks since the last non-FULL one
+    unsigned sn_key, sn_cnt, sn_sw;  // its value in front of the most recent non-FULL chunk
+    bool p_full, p_int, p_last, pp_last;  // chunk vc-1: FULL / has samples above / last sample above; vc-2: last above
 };
 
-struct HitState {  // per-lane state of the run walker, lives across segments
-    bool open;
-    int run_s, prev_c, nh;
-    unsigned carry;  // interesting-chunk bits of the previous segment not yet visited
-    RunAgg g;
+struct WarpHits {  // per-warp shared memory of the hit machinery
+    uint4 q_ch[3][kQCap];  // item samples: chunk P-1, P, P+1
+    uint4 q_hdr[kQCap];    // owner | (P + 1) << 5 | in_open << 24 | next_full << 25 ; snapshot key, cnt, sum
+    uint4 stage[32];       // this round's "open at chunk end" fragments: start | has << 16 ; key, cnt, sum
+    uint4 carry[32];       // the same, per owner, across rounds
+    int stage_n[32];       // runs started by this round's items
+    int carry_n[32];       // runs started so far, per owner
+    LprEnt ent[kLprEnt];
+    int pool_cnt;
+    unsigned ovf;  // owners whose hits did not all fit the pool
 };
 
 __device__ __forceinline__ int u16_at(const uint4& q, int j) {
@@ -82,32 +86,44 @@ __device__ __forceinline__ int u16_at(const uint4& q, int j) {
     return (int)((w >> ((j & 1) * 16)) & 0xffffu);
 }
 
-// ---- hit sinks (per lane) ---------------------------------------------------------------------
+// ---- hit sinks ---------------------------------------------------------------------------------
 struct PoolSink {
-    LprEnt* pool;
-    int* counter;
-    bool overflow;
-    __device__ __forceinline__ void store(int p, int s, int e, float height, float integral, int ord, const LaneRec&, const FHArgs&) {
-        int idx = atomicAdd(counter, 1);
+    static constexpr bool kDirect = false;
+    WarpHits* ws;
+    __device__ __forceinline__ void prepare(int, const LaneRec&) {}
+    __device__ __forceinline__ void store(int p, int s, int e, float height, float integral, int ord, int owner, const FHArgs&) {
+        int idx = atomicAdd(&ws->pool_cnt, 1);
         if (idx < kLprEnt) {
             LprEnt h;
             h.ps = (unsigned)p | ((unsigned)s << 16);
-            h.eo = (unsigned)e | ((unsigned)lane_id() << 16) | ((unsigned)ord << 21);
+            h.eo = (unsigned)e | ((unsigned)owner << 16) | ((unsigned)ord << 21);
             h.height = height;
             h.integral = integral;
-            *reinterpret_cast<uint4*>(&pool[idx]) = *reinterpret_cast<uint4*>(&h);
+            *reinterpret_cast<uint4*>(&ws->ent[idx]) = *reinterpret_cast<uint4*>(&h);
         } else {
-            overflow = true;
+            atomicOr(&ws->ovf, 1u << owner);
         }
     }
 };
 struct DirectSink {  // rows straight to the output (records whose hits did not fit the pool)
+    static constexpr bool kDirect = true;
+    long long my_row0;
+    bool my_active;
     long long row0;
     bool active;
-    __device__ __forceinline__ void store(int p, int s, int e, float height, float integral, int ord, const LaneRec& r, const FHArgs& a) {
+    RowRec rr;
+    __device__ __forceinline__ void prepare(int src, const LaneRec& r) {  // converged: fetch the owner's row data
+        row0 = bcast_i64(my_row0, src);
+        active = __shfl_sync(kFull, (int)my_active, src) != 0;
+        rr.ts = bcast_i64(r.ts, src);
+        rr.rid = bcast_i64(r.rid, src);
+        rr.len = __shfl_sync(kFull, r.len, src);
+        rr.dt = __shfl_sync(kFull, r.dt, src);
+        rr.bc = __shfl_sync(kFull, r.bc, src);
+    }
+    __device__ __forceinline__ void store(int p, int s, int e, float height, float integral, int ord, int, const FHArgs& a) {
         long long row = row0 + ord;
         if (active && row < a.hit_cap) {
-            RowRec rr{r.ts, r.rid, r.len, r.dt, r.bc};
             unsigned w[15];
             hit_row_words(w, p, s, e, height, integral, rr, a.p.left_extension, a.p.right_extension, a.lmax);
             unsigned* dst = reinterpret_cast<unsigned*>(a.hit_out + row * kHitRowBytes);
@@ -117,89 +133,130 @@ struct DirectSink {  // rows straight to the output (records whose hits did not 
     }
 };
 
-// ---- lane-parallel hit pass over one window of chunks ------------------------------------------
-// `buf` is the lane's slot for the current segment; slot chunk k holds global chunk c = cbase + k.
-// `hw` bit t marks global chunk c = c0 + t as interesting.
+// ---- dense round: lane t walks the runs of queued item t ---------------------------------------
 template <typename Sink>
-__device__ __forceinline__ void lpr_hit_window(const uint8_t* buf, int cbase, int c0, int c_end, unsigned hw, const LaneRec& r,
-                                               const FHArgs& a, HitState& hs, Sink& sink) {
-    const unsigned sx = r.bias ? 0x80008000u : 0u;
-    const unsigned xm = r.positive ? 0xffffffffu : 0u;
-    const unsigned short* s16 = reinterpret_cast<const unsigned short*>(buf);
+__device__ __forceinline__ void lpr_round(WarpHits& ws, int qn, const LaneRec& r, const FHArgs& a, Sink& sink) {
+    __syncwarp();  // the pushes are visible
+    const int lane = lane_id();
+    const bool act = lane < qn;
+    const uint4 hd = ws.q_hdr[act ? lane : 0];
+    const int src = act ? (int)(hd.x & 31u) : lane;     // owner lane
+    const int P = (int)((hd.x >> 5) & 0x3fffu) - 1;  // -1: the virtual chunk in front of a record that starts FULL
+    const bool in_open = act && ((hd.x >> 24) & 1u);
+    const bool next_full = act && ((hd.x >> 25) & 1u);
+    // the owner's record constants
+    const int o_kmax = __shfl_sync(kFull, r.kmax, src);
+    const int o_mis = __shfl_sync(kFull, r.mis, src);
+    const int o_len = __shfl_sync(kFull, r.len, src);
+    const int o_wlim = __shfl_sync(kFull, r.wlim, src);
+    const bool o_pos = __shfl_sync(kFull, (int)r.positive, src) != 0;
+    const double o_b = shfl_f64(r.b_rec, src);
+    sink.prepare(src, r);
+    const int bias = r.bias;  // uniform
+    const int sx = bias ? 0x8000 : 0;
+    const int xm16 = o_pos ? 0xffff : 0;
     const int left = a.p.left_extension, right = a.p.right_extension;
-    const int vtotal = r.mis + r.len;
+    const int i0 = 8 * P - o_mis;
+    const int inb = o_wlim + bias;
     auto sample = [&](int i) -> int {  // stored (offset-domain) value of record sample i; padding = true 0
-        return (i < r.len) ? ((int)s16[r.mis + i - cbase * 8] ^ (int)(sx & 0xffffu)) : r.bias;
+        const int u = i - i0 + 8;      // 0 .. 23
+        const unsigned short* row = reinterpret_cast<const unsigned short*>(&ws.q_ch[u >> 3][lane]);
+        return (i < o_len) ? ((int)row[u & 7] ^ sx) : bias;
     };
-    auto close_run = [&](int e) {
-        const int a1 = min(a.lmax, e + right);
-        for (int i = e; i < a1; ++i) hs.g.add(i, sample(i), r);
-        const int wp = (r.positive ? 65535 - hs.g.kbest : hs.g.kbest) - r.bias;
-        const float height = (float)(r.positive ? __dsub_rn((double)wp, r.b_rec) : __dsub_rn(r.b_rec, (double)wp));
-        const long long c = hs.g.cnt;
-        const long long swt = (long long)hs.g.sw - c * r.bias;
-        double integ;
-        if (r.b_small) {
-            long long ipart = r.positive ? (swt - c * (long long)r.bi) : (c * (long long)r.bi - swt);
-            double fpart = __dmul_rn((double)c, r.bf);
-            integ = r.positive ? __dsub_rn((double)ipart, fpart) : __dadd_rn((double)ipart, fpart);
-        } else {
-            integ = r.positive ? __dsub_rn((double)swt, __dmul_rn((double)c, r.b_rec)) : __dsub_rn(__dmul_rn((double)c, r.b_rec), (double)swt);
-        }
-        sink.store(hs.g.ibest, hs.run_s, e, height, (float)integ, hs.nh, r, a);
-        ++hs.nh;
-        hs.open = false;
-    };
-    auto open_run = [&](int s) {
-        hs.open = true;
-        hs.run_s = s;
-        hs.g.reset();
-        for (int i = max(0, s - left); i < s; ++i) hs.g.add(i, sample(i), r);
-    };
-    // a run left open by the previous window ends at the window start if the next chunk is quiet
-    if (hs.open && hs.prev_c + 1 == c0 && !(hw & 1u)) close_run(c0 * 8 - r.mis);
-    unsigned m = hw;
-    while (m) {
-        const int t = __ffs(m) - 1;
-        m &= m - 1;
-        const int c = c0 + t;
-        if (hs.open && c != hs.prev_c + 1) close_run((hs.prev_c + 1) * 8 - r.mis);  // a quiet chunk in between
-        hs.prev_c = c;
-        uint4 q = *reinterpret_cast<const uint4*>(buf + (c - cbase) * 16);
-        q.x ^= sx; q.y ^= sx; q.z ^= sx; q.w ^= sx;
-        const int v0 = c * 8;
-        const int lo = min(max(r.mis - v0, 0), 8), hi = min(max(vtotal - v0, 0), 8);
-        int wv[8];
-        unsigned m8 = 0;
+    // above-threshold mask of the item's own chunk
+    unsigned m8 = 0;
+    if (act) {
+        const uint4 c1 = ws.q_ch[1][lane];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            wv[j] = u16_at(q, j);
-            int kv = (int)((unsigned)wv[j] ^ (xm & 0xffffu));
-            m8 |= ((kv <= r.kmax && j >= lo && j < hi) ? 1u : 0u) << j;
-        }
-        const int i0 = v0 - r.mis;
-        int j = 0;
-        while (j < 8) {
-            if (hs.open) {
-                const unsigned tz = (~(m8 >> j)) | 0x100u;  // first zero at or after j
-                const int ones = min(__ffs(tz) - 1, 8 - j);
-                const unsigned rm = ((1u << (j + ones)) - 1u) & ~((1u << j) - 1u);
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj)
-                    if ((rm >> jj) & 1u) hs.g.add(i0 + jj, wv[jj], r);
-                j += ones;
-                if (j < 8) close_run(i0 + j);
-            } else {
-                const unsigned tt = m8 >> j;
-                if (!tt) break;
-                j += __ffs(tt) - 1;
-                open_run(i0 + j);
-            }
+            const int kv = (u16_at(c1, j) ^ sx) ^ xm16;
+            const int i = i0 + j;
+            m8 |= ((i >= 0 && i < o_len && kv <= o_kmax) ? 1u : 0u) << j;
         }
     }
-    // still open after the last interesting chunk of the window and the next chunk (quiet, or past
-    // the record end) belongs to this window: the run ends there, its extension is in the slot
-    if (hs.open && hs.prev_c + 1 < c_end) close_run(min(r.len, (hs.prev_c + 1) * 8 - r.mis));
+    const bool nfs = next_full && !(m8 & 0x80u);  // a run starts with the FULL chunk that follows
+    const bool has_trail = (m8 & 0x80u) || nfs;
+    const int nstarts = __popc(m8 & ~((m8 << 1) | (in_open ? 1u : 0u))) + (nfs ? 1 : 0);
+    ws.stage_n[lane] = nstarts;
+    const unsigned peers = __match_any_sync(kFull, act ? src : 32 + lane);
+    const unsigned lt = peers & ((1u << lane) - 1u);
+    __syncwarp();
+    int ord_base = act ? ws.carry_n[src] : 0;
+    for (unsigned m = lt; m; m &= m - 1) ord_base += ws.stage_n[__ffs(m) - 1];
+
+    auto agg = [&](int a0, int a1, unsigned& key, unsigned& cnt, unsigned& sw) {
+        for (int i = a0; i < a1; ++i) {
+            const int w = sample(i);
+            key = min(key, ((unsigned)(w ^ xm16) << 16) | (unsigned)i);
+            const bool in = o_pos ? (w >= inb) : (w <= inb);
+            cnt += in ? 1u : 0u;
+            sw += in ? (unsigned)w : 0u;
+        }
+    };
+    // the fragment still open at the chunk end: from its start (minus the left extension) to the chunk end
+    int js_tr = 8;
+    if (has_trail) {
+        if (!nfs) js_tr = 8 - __clz(~(m8 << 24));
+        const int s_tr = i0 + js_tr;
+        unsigned key = 0xffffffffu, cnt = 0, sw = 0;
+        agg(max(0, s_tr - left), i0 + 8, key, cnt, sw);
+        ws.stage[lane] = make_uint4((unsigned)s_tr, key, cnt, sw);
+    }
+    __syncwarp();
+    // runs that end in this chunk
+    uint4 prev = make_uint4(0u, 0xffffffffu, 0u, 0u);
+    if (in_open) prev = lt ? ws.stage[31 - __clz(lt)] : ws.carry[src];
+    const double bi = floor(o_b), bf = __dsub_rn(o_b, bi);
+    const bool b_small = fabs(o_b) < 2e9;
+    unsigned mm = (has_trail && !nfs) ? (m8 & ((1u << js_tr) - 1u)) : m8;
+    bool lead = in_open;
+    int k = 0;
+    while (lead || mm) {
+        int s, e, a0, ord;
+        unsigned key = 0xffffffffu, cnt = 0, sw = 0;
+        if (lead) {
+            const int t0 = __ffs(~m8 & 0x1ffu) - 1;  // the incoming run ends at the first sample below threshold
+            e = i0 + t0;
+            s = (int)(prev.x & 0xffffu);
+            a0 = i0;
+            key = min(prev.y, hd.y);
+            cnt = prev.z + hd.z;
+            sw = prev.w + hd.w;
+            ord = ord_base - 1;
+            mm &= ~((1u << t0) - 1u);
+            lead = false;
+        } else {
+            const int js = __ffs(mm) - 1;
+            const int je = js + __ffs(~(mm >> js)) - 1;
+            s = i0 + js;
+            e = i0 + je;
+            a0 = max(0, s - left);
+            ord = ord_base + k;
+            ++k;
+            mm &= ~((1u << je) - 1u);
+        }
+        agg(a0, min(a.lmax, e + right), key, cnt, sw);
+        const int kbest = (int)(key >> 16), ibest = (int)(key & 0xffffu);
+        const int wp = (o_pos ? 65535 - kbest : kbest) - bias;
+        const float height = (float)(o_pos ? __dsub_rn((double)wp, o_b) : __dsub_rn(o_b, (double)wp));
+        const long long c = cnt;
+        const long long swt = (long long)sw - c * bias;
+        double integ;
+        if (b_small) {
+            const long long ipart = o_pos ? (swt - c * (long long)bi) : (c * (long long)bi - swt);
+            const double fpart = __dmul_rn((double)c, bf);
+            integ = o_pos ? __dsub_rn((double)ipart, fpart) : __dadd_rn((double)ipart, fpart);
+        } else {
+            integ = o_pos ? __dsub_rn((double)swt, __dmul_rn((double)c, o_b)) : __dsub_rn(__dmul_rn((double)c, o_b), (double)swt);
+        }
+        sink.store(ibest, s, e, height, (float)integ, ord, src, a);
+    }
+    __syncwarp();  // every read of stage / carry is done
+    if (act && !(peers >> lane >> 1)) {  // the last item of this owner in the round
+        if (has_trail) ws.carry[src] = ws.stage[lane];
+        ws.carry_n[src] = ord_base + nstarts;
+    }
+    __syncwarp();
 }
 
 // ---- stream one record per lane through the slot ring -------------------------------------------
@@ -224,29 +281,37 @@ __device__ __forceinline__ void tma_tensor2d_g2s(void* dst_smem, const CUtensorM
 
 template <bool FEAT, bool HITS, typename Sink>
 __device__ __forceinline__ void lpr_stream(const FHArgs& a, const uint16_t* pool, const LaneRec& r, int sc, const Ring& ring,
-                                           int p0, int p1, int c0, int c1, FeatState& fs, HitState& hs, Sink& sink) {
+                                           int p0, int p1, int c0, int c1, FeatState& fs, WarpHits& ws, Sink& sink) {
     const int lane = lane_id();
     const int mis = r.mis, vtotal = r.mis + r.len;
     const int nch = (r.len > 0) ? ((vtotal + 7) >> 3) : 0;
     const int nch_max = __reduce_max_sync(kFull, nch);
-    const int nseg = (nch_max + sc - 1) / sc;
+    // the hit pipeline lags the scan by one chunk, closes runs at a virtual chunk behind the record
+    // and flushes the item queue one step later: three steps past the last chunk
+    const int nsteps = (nch_max > 0) ? (HITS ? nch_max + 3 : nch_max) : 0;
+    const int nseg = (nsteps + sc - 1) / sc;
     const bool known = r.pol == WFB_POL_POSITIVE || r.pol == WFB_POL_NEGATIVE;
     const unsigned sx32 = r.bias ? 0x80008000u : 0u;
     const unsigned xm = r.positive ? 0xffffffffu : 0u;
     const float b32 = (float)r.b_feat;
     // chunk ranges of the "plain" fast path: [plainA, plainB) minus [plainHa, plainHb)
     int plainA = 0, plainB = 0, plainHa = 0, plainHb = 0;
-    if (r.len > 0 && (!FEAT || !known)) {
-        const int vlo = FEAT ? mis + max(c0, 1) : mis + 1;     // first sample that has a predecessor, inside the area range
-        const int vhi = FEAT ? mis + min(c1, r.len) : vtotal;  // end of the area range
+    if (FEAT && r.len > 0 && !known) {
+        const int vlo = mis + max(c0, 1);     // first sample that has a predecessor, inside the area range
+        const int vhi = mis + min(c1, r.len);  // end of the area range
         plainA = (vlo + 7) >> 3;
         plainB = vhi >> 3;
-        if (FEAT && p1 > p0) { plainHa = (mis + p0) >> 3; plainHb = (mis + p1 + 7) >> 3; }
+        if (p1 > p0) { plainHa = (mis + p0) >> 3; plainHb = (mis + p1 + 7) >> 3; }
     }
+    HitScan hs;
+    hs.fa_key = 0xffffffffu; hs.fa_cnt = 0; hs.fa_sw = 0;
+    hs.sn_key = 0xffffffffu; hs.sn_cnt = 0; hs.sn_sw = 0;
+    hs.p_full = false; hs.p_int = false; hs.p_last = false; hs.pp_last = false;
+    int qn = 0;  // queued items (warp-uniform)
 
     auto issue = [&](int s) {
         const int b = s % kNBuf;
-        const int cb = s * sc - 2 * kOV;  // global chunk held by slot chunk 0
+        const int cb = s * sc - kHist;  // global chunk held by slot chunk 0
         const int clo = max(0, cb), chi = min(nch, (s + 1) * sc);
         const unsigned bytes = chi > clo ? (unsigned)(chi - clo) * 16u : 0u;
         fence_proxy_async();  // generic reads of this buffer (two segments ago) before the refill
@@ -274,114 +339,167 @@ __device__ __forceinline__ void lpr_stream(const FHArgs& a, const uint16_t* pool
         mbar_wait(&ring.bars[b], (*ring.phase_bits >> b) & 1u);
         *ring.phase_bits ^= 1u << b;
         const uint8_t* buf = ring.slot + b * ring.buf_stride;
-        const int cbase = s * sc - 2 * kOV;
-        unsigned mw = 0;
-        const int cend = min(sc, nch_max - s * sc);
+        const int cbase = s * sc - kHist;
+        const int cend = min(sc, nsteps - s * sc);
         for (int cb = 0; cb < cend; ++cb) {
             const int vc = s * sc + cb;
-            if (vc >= nch) continue;
-            uint4 q = *reinterpret_cast<const uint4*>(buf + (2 * kOV + cb) * 16);
-            if (sx32) { q.x ^= sx32; q.y ^= sx32; q.z ^= sx32; q.w ^= sx32; }  // int16 -> offset binary
-            const int v0 = vc * 8;
-            const int lo = max(mis - v0, 0), hi = min(vtotal - v0, 8);
-            const int i0 = v0 - mis;
-            if (vc >= plainA && vc < plainB && (vc < plainHa || vc >= plainHb)) {
-                // plain interior chunk: 8 valid samples inside the area range, outside the height range
-                if (FEAT) {
-                    unsigned f0 = __funnelshift_r(fs.prev_w, q.x, 16), f1 = __funnelshift_r(q.x, q.y, 16);
-                    unsigned f2 = __funnelshift_r(q.y, q.z, 16), f3 = __funnelshift_r(q.z, q.w, 16);
-                    unsigned d0 = __vmaxu2(q.x, f0) - __vminu2(q.x, f0), d1 = __vmaxu2(q.y, f1) - __vminu2(q.y, f1);
-                    unsigned d2 = __vmaxu2(q.z, f2) - __vminu2(q.z, f2), d3 = __vmaxu2(q.w, f3) - __vminu2(q.w, f3);
-                    fs.pdiff = __vmaxu2(fs.pdiff, __vmaxu2(__vmaxu2(d0, d1), __vmaxu2(d2, d3)));
-                    unsigned sacc = __dp2a_lo(q.x, 0x0101u, fs.isum32);
-                    sacc = __dp2a_lo(q.y, 0x0101u, sacc);
-                    sacc = __dp2a_lo(q.z, 0x0101u, sacc);
-                    fs.isum32 = __dp2a_lo(q.w, 0x0101u, sacc);
+            // classification of chunk vc (a chunk behind the record end is QUIET)
+            bool c_full = false, c_int = false, c_last = false;
+            unsigned ckey = 0xffffffffu, csum = 0;
+            if (vc < nch) {
+                uint4 q = *reinterpret_cast<const uint4*>(buf + (kHist + cb) * 16);
+                if (sx32) { q.x ^= sx32; q.y ^= sx32; q.z ^= sx32; q.w ^= sx32; }  // int16 -> offset binary
+                const int v0 = vc * 8;
+                const int lo = max(mis - v0, 0), hi = min(vtotal - v0, 8);
+                const int i0 = v0 - mis;
+                const bool whole = lo == 0 && hi == 8;
+                if (whole && (HITS || !known)) {
+                    csum = __dp2a_lo(q.x, 0x0101u, 0u);
+                    csum = __dp2a_lo(q.y, 0x0101u, csum);
+                    csum = __dp2a_lo(q.z, 0x0101u, csum);
+                    csum = __dp2a_lo(q.w, 0x0101u, csum);
                 }
-                if (HITS) {
-                    unsigned mn = __vminu2(__vminu2(q.x ^ xm, q.y ^ xm), __vminu2(q.z ^ xm, q.w ^ xm));
-                    int lmin = (int)min(mn & 0xffffu, mn >> 16);
-                    mw |= (lmin <= r.kmax ? 1u : 0u) << cb;
-                }
-            } else if (lo == 0 && hi == 8) {
                 if (FEAT) {
-                    const unsigned pw = (i0 > 0) ? fs.prev_w : (q.x << 16);
-                    unsigned f0 = __funnelshift_r(pw, q.x, 16), f1 = __funnelshift_r(q.x, q.y, 16);
-                    unsigned f2 = __funnelshift_r(q.y, q.z, 16), f3 = __funnelshift_r(q.z, q.w, 16);
-                    unsigned d0 = __vmaxu2(q.x, f0) - __vminu2(q.x, f0), d1 = __vmaxu2(q.y, f1) - __vminu2(q.y, f1);
-                    unsigned d2 = __vmaxu2(q.z, f2) - __vminu2(q.z, f2), d3 = __vmaxu2(q.w, f3) - __vminu2(q.w, f3);
-                    fs.pdiff = __vmaxu2(fs.pdiff, __vmaxu2(__vmaxu2(d0, d1), __vmaxu2(d2, d3)));
-                    const int jlo = max(0, p0 - i0), jhi = min(8, p1 - i0);
-                    if (jhi > jlo) {
-                        if (jlo == 0 && jhi == 8) {
-                            fs.pmin = __vminu2(fs.pmin, __vminu2(__vminu2(q.x, q.y), __vminu2(q.z, q.w)));
-                            fs.pmax = __vmaxu2(fs.pmax, __vmaxu2(__vmaxu2(q.x, q.y), __vmaxu2(q.z, q.w)));
-                        } else {
+                    if (vc >= plainA && vc < plainB && (vc < plainHa || vc >= plainHb)) {
+                        // plain interior chunk: 8 valid samples inside the area range, outside the height range
+                        unsigned f0 = __funnelshift_r(fs.prev_w, q.x, 16), f1 = __funnelshift_r(q.x, q.y, 16);
+                        unsigned f2 = __funnelshift_r(q.y, q.z, 16), f3 = __funnelshift_r(q.z, q.w, 16);
+                        unsigned d0 = __vmaxu2(q.x, f0) - __vminu2(q.x, f0), d1 = __vmaxu2(q.y, f1) - __vminu2(q.y, f1);
+                        unsigned d2 = __vmaxu2(q.z, f2) - __vminu2(q.z, f2), d3 = __vmaxu2(q.w, f3) - __vminu2(q.w, f3);
+                        fs.pdiff = __vmaxu2(fs.pdiff, __vmaxu2(__vmaxu2(d0, d1), __vmaxu2(d2, d3)));
+                        fs.isum32 += csum;
+                    } else if (whole) {
+                        const unsigned pw = (i0 > 0) ? fs.prev_w : (q.x << 16);
+                        unsigned f0 = __funnelshift_r(pw, q.x, 16), f1 = __funnelshift_r(q.x, q.y, 16);
+                        unsigned f2 = __funnelshift_r(q.y, q.z, 16), f3 = __funnelshift_r(q.z, q.w, 16);
+                        unsigned d0 = __vmaxu2(q.x, f0) - __vminu2(q.x, f0), d1 = __vmaxu2(q.y, f1) - __vminu2(q.y, f1);
+                        unsigned d2 = __vmaxu2(q.z, f2) - __vminu2(q.z, f2), d3 = __vmaxu2(q.w, f3) - __vminu2(q.w, f3);
+                        fs.pdiff = __vmaxu2(fs.pdiff, __vmaxu2(__vmaxu2(d0, d1), __vmaxu2(d2, d3)));
+                        const int jlo = max(0, p0 - i0), jhi = min(8, p1 - i0);
+                        if (jhi > jlo) {
+                            if (jlo == 0 && jhi == 8) {
+                                fs.pmin = __vminu2(fs.pmin, __vminu2(__vminu2(q.x, q.y), __vminu2(q.z, q.w)));
+                                fs.pmax = __vmaxu2(fs.pmax, __vmaxu2(__vmaxu2(q.x, q.y), __vmaxu2(q.z, q.w)));
+                            } else {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                int w = u16_at(q, j);
-                                if (j >= jlo && j < jhi) { fs.imin = min(fs.imin, w); fs.imax = max(fs.imax, w); }
+                                for (int j = 0; j < 8; ++j) {
+                                    int w = u16_at(q, j);
+                                    if (j >= jlo && j < jhi) { fs.imin = min(fs.imin, w); fs.imax = max(fs.imax, w); }
+                                }
                             }
                         }
-                    }
-                    const int klo = max(0, c0 - i0), khi = min(8, c1 - i0);
-                    if (khi > klo) {
-                        if (klo == 0 && khi == 8 && !known) {
-                            unsigned sacc = __dp2a_lo(q.x, 0x0101u, fs.isum32);
-                            sacc = __dp2a_lo(q.y, 0x0101u, sacc);
-                            sacc = __dp2a_lo(q.z, 0x0101u, sacc);
-                            fs.isum32 = __dp2a_lo(q.w, 0x0101u, sacc);
-                        } else {
+                        const int klo = max(0, c0 - i0), khi = min(8, c1 - i0);
+                        if (khi > klo) {
+                            if (klo == 0 && khi == 8 && !known) {
+                                fs.isum32 += csum;
+                            } else {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                unsigned w = (unsigned)u16_at(q, j);
-                                if (j >= klo && j < khi) {
-                                    if (!known) fs.isum32 += w;
+                                for (int j = 0; j < 8; ++j) {
+                                    unsigned w = (unsigned)u16_at(q, j);
+                                    if (j >= klo && j < khi) {
+                                        if (!known) fs.isum32 += w;
+                                        else fs.dsum += (double)(r.positive ? __fsub_rn((float)w, b32) : __fsub_rn(b32, (float)w));
+                                    }
+                                }
+                            }
+                        }
+                    } else {
+                        // partial chunk (record start / end): per-sample
+                        const int prev_s = (int)(fs.prev_w >> 16);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int w = u16_at(q, j);
+                            if (j >= lo && j < hi) {
+                                const int i = i0 + j;
+                                if (i > 0) fs.idiff = max(fs.idiff, abs(w - ((j == 0) ? prev_s : u16_at(q, j - 1))));
+                                if (i >= p0 && i < p1) { fs.imin = min(fs.imin, w); fs.imax = max(fs.imax, w); }
+                                if (i >= c0 && i < c1) {
+                                    if (!known) fs.isum32 += (unsigned)w;
                                     else fs.dsum += (double)(r.positive ? __fsub_rn((float)w, b32) : __fsub_rn(b32, (float)w));
                                 }
                             }
                         }
                     }
+                    fs.prev_w = q.w;
                 }
                 if (HITS) {
-                    unsigned mn = __vminu2(__vminu2(q.x ^ xm, q.y ^ xm), __vminu2(q.z ^ xm, q.w ^ xm));
-                    int lmin = (int)min(mn & 0xffffu, mn >> 16);
-                    mw |= (lmin <= r.kmax ? 1u : 0u) << cb;
-                }
-            } else {
-                // partial chunk (record start / end): per-sample
-                const int prev_s = (int)(fs.prev_w >> 16);
-                bool any = false;
+                    const unsigned k0 = q.x ^ xm, k1 = q.y ^ xm, k2 = q.z ^ xm, k3 = q.w ^ xm;  // threshold keys: above <=> key <= kmax
+                    if (whole) {
+                        // 32-bit keys  kv << 16 | j : their minimum is the chunk's first arg-min
+                        const unsigned e0 = (k0 << 16), o0 = (k0 & 0xffff0000u) | 1u;
+                        const unsigned e1 = (k1 << 16) | 2u, o1 = (k1 & 0xffff0000u) | 3u;
+                        const unsigned e2 = (k2 << 16) | 4u, o2 = (k2 & 0xffff0000u) | 5u;
+                        const unsigned e3 = (k3 << 16) | 6u, o3 = (k3 & 0xffff0000u) | 7u;
+                        const unsigned mn = min(min(min(e0, o0), min(e1, o1)), min(min(e2, o2), min(e3, o3)));
+                        const unsigned mx = max(max(max(e0, o0), max(e1, o1)), max(max(e2, o2), max(e3, o3)));
+                        c_int = (int)(mn >> 16) <= r.kmax;
+                        c_full = (int)(mx >> 16) <= r.kmax;
+                        c_last = (int)(k3 >> 16) <= r.kmax;
+                        ckey = mn + (unsigned)i0;
+                    } else {
+                        const uint4 kq = make_uint4(k0, k1, k2, k3);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int w = u16_at(q, j);
-                    const bool ok = (j >= lo) && (j < hi);
-                    if (FEAT && ok) {
-                        const int i = i0 + j;
-                        if (i > 0) fs.idiff = max(fs.idiff, abs(w - ((j == 0) ? prev_s : u16_at(q, j - 1))));
-                        if (i >= p0 && i < p1) { fs.imin = min(fs.imin, w); fs.imax = max(fs.imax, w); }
-                        if (i >= c0 && i < c1) {
-                            if (!known) fs.isum32 += (unsigned)w;
-                            else fs.dsum += (double)(r.positive ? __fsub_rn((float)w, b32) : __fsub_rn(b32, (float)w));
+                        for (int j = 0; j < 8; ++j) {
+                            const bool ab = (j >= lo) && (j < hi) && (u16_at(kq, j) <= r.kmax);
+                            c_int = c_int || ab;
+                            if (j == 7) c_last = ab;
                         }
                     }
-                    if (HITS && ok) any = any || ((int)((unsigned)w ^ (xm & 0xffffu)) <= r.kmax);
+                    if (c_full && r.degen) {  // negative threshold: samples above it may lie on the far side of the baseline
+                        unsigned cnt = 0, sw = 0;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int w = u16_at(q, j);
+                            const bool in = r.positive ? (w >= r.wlim + r.bias) : (w <= r.wlim + r.bias);
+                            cnt += in ? 1u : 0u;
+                            sw += in ? (unsigned)w : 0u;
+                        }
+                        csum = sw;
+                        hs.fa_cnt += cnt;
+                    } else if (c_full) {
+                        hs.fa_cnt += 8u;
+                    }
                 }
-                if (HITS) mw |= (any ? 1u : 0u) << cb;
             }
-            fs.prev_w = q.w;
-        }
-        if (HITS) {
-            // window of this pass: chunks [s*sc - kOV, (s+1)*sc - kOV), the last segment runs to the end
-            const bool last = (s == nseg - 1);
-            unsigned hw = hs.carry | (mw << kOV);
-            if (!last) {
-                hs.carry = hw >> sc;                 // chunks (s+1)*sc - kOV .. : next pass
-                hw &= (sc >= 32) ? 0xffffffffu : ((1u << sc) - 1u);
+            if (HITS) {
+                // chunk P = vc - 1 is an item if it is not FULL and holds, follows or precedes samples above threshold
+                const int P = vc - 1;
+                const bool want = P >= -1 && P <= nch && !hs.p_full && (hs.p_int || hs.pp_last || c_full);
+                const unsigned bal = __ballot_sync(kFull, want);
+                const bool flush = vc == nsteps - 1;
+                if (bal || flush) {
+                    const int np = __popc(bal);  // nothing is wanted at the flush step
+                    if (qn + np > kQCap || (flush && qn > 0)) {
+                        lpr_round(ws, qn, r, a, sink);
+                        qn = 0;
+                    }
+                    if (want) {
+                        const int slot = qn + __popc(bal & ((1u << lane) - 1u));
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            const int ch = P - 1 + k;
+                            uint4 d = make_uint4(0u, 0u, 0u, 0u);
+                            if (ch >= 0 && ch < nch) d = *reinterpret_cast<const uint4*>(buf + (ch - cbase) * 16);
+                            ws.q_ch[k][slot] = d;
+                        }
+                        ws.q_hdr[slot] = make_uint4((unsigned)lane | ((unsigned)(P + 1) << 5) | (hs.pp_last ? 1u << 24 : 0u) | (c_full ? 1u << 25 : 0u),
+                                                    hs.sn_key, hs.sn_cnt, hs.sn_sw);
+                    }
+                    qn += np;
+                }
+                // chunk vc enters the pipeline
+                hs.pp_last = hs.p_last;
+                hs.p_last = c_last;
+                hs.p_full = c_full;
+                hs.p_int = c_int;
+                if (c_full) {
+                    hs.fa_key = min(hs.fa_key, ckey);
+                    hs.fa_sw += csum;
+                } else {
+                    hs.sn_key = hs.fa_key; hs.sn_cnt = hs.fa_cnt; hs.sn_sw = hs.fa_sw;
+                    hs.fa_key = 0xffffffffu; hs.fa_cnt = 0; hs.fa_sw = 0;
+                }
             }
-            // chunks past the end of the window: the last pass covers everything that is left
-            const int c_end = last ? (1 << 28) : (s + 1) * sc - kOV;
-            lpr_hit_window(buf, cbase, s * sc - kOV, c_end, hw, r, a, hs, sink);
         }
         __syncwarp();  // every lane is done with buffer b before it is refilled
     }
@@ -392,8 +510,7 @@ template <bool FEAT, bool HITS>
 __global__ void __launch_bounds__(kLprWarps * 32) lpr_kernel(const FHArgs a, const int sc, const __grid_constant__ CUtensorMap tmap,
                                                              const int have_tmap) {
     extern __shared__ __align__(128) uint8_t dyn_smem[];  // [warp][kNBuf][lane] slots of a.slot_bytes
-    __shared__ __align__(16) LprEnt s_ent[HITS ? kLprWarps : 1][HITS ? kLprEnt : 1];
-    __shared__ int s_pool[kLprWarps];
+    __shared__ __align__(16) WarpHits s_hits[HITS ? kLprWarps : 1];
     __shared__ long long s_wtot[kLprWarps];
     __shared__ long long s_wbase[kLprWarps];
     __shared__ int s_tile;
@@ -401,6 +518,7 @@ __global__ void __launch_bounds__(kLprWarps * 32) lpr_kernel(const FHArgs a, con
 
     const int warp = threadIdx.x >> 5, lane = lane_id();
     const uint16_t* pool = static_cast<const uint16_t*>(a.pool);
+    WarpHits& ws = s_hits[HITS ? warp : 0];
     unsigned phase_bits = 0;
     Ring ring;
     // lane stride = slot_bytes (odd multiple of 16): conflict-free LDS.128; buffers kNBuf apart by 32 lanes
@@ -468,16 +586,14 @@ __global__ void __launch_bounds__(kLprWarps * 32) lpr_kernel(const FHArgs a, con
             resolve_slice(a.p.area_start, a.p.area_end, r.len, c0, c1);
         }
         r.kmax = -1;
-        r.b_small = true; r.bi = 0; r.bf = 0; r.wlim = 0;
+        r.wlim = 0;
+        r.degen = r.thr < 0.0;
         if (HITS && r.len > 0) {
             r.kmax = integer_threshold_u16(r.b_rec, r.thr, r.positive, r.bias);
-            r.b_small = fabs(r.b_rec) < 2e9;
-            r.bi = floor(r.b_rec);
-            r.bf = __dsub_rn(r.b_rec, r.bi);
-            const int ib = r.b_small ? (int)r.bi : (r.b_rec > 0 ? INT_MAX : INT_MIN);
-            r.wlim = r.positive ? ib + 1 : ((r.bi == r.b_rec) ? ib - 1 : ib);
+            const double bi = floor(r.b_rec);
+            const int ib = (fabs(r.b_rec) < 2e9) ? (int)bi : (r.b_rec > 0 ? INT_MAX - 65536 : INT_MIN + 65536);
+            r.wlim = r.positive ? ib + 1 : ((bi == r.b_rec) ? ib - 1 : ib);
         }
-
         // one tensor copy per segment when the warp's records are rows of the fixed-length pool
         {
             const long long row = (long long)tile * kLprTile + warp * 32 + lane;  // record index == pool row
@@ -489,12 +605,13 @@ __global__ void __launch_bounds__(kLprWarps * 32) lpr_kernel(const FHArgs a, con
         FeatState fs;
         fs.pmin = 0xffffffffu; fs.pmax = 0u; fs.pdiff = 0u; fs.isum32 = 0u; fs.prev_w = 0u;
         fs.imin = INT_MAX; fs.imax = INT_MIN; fs.idiff = 0; fs.dsum = 0.0;
-        HitState hs;
-        hs.open = false; hs.run_s = 0; hs.prev_c = -4; hs.nh = 0; hs.carry = 0u; hs.g.reset();
-        if (HITS && lane == 0) s_pool[warp] = 0;
+        if (HITS) {
+            ws.carry_n[lane] = 0;
+            if (lane == 0) { ws.pool_cnt = 0; ws.ovf = 0u; }
+        }
         __syncwarp();
-        PoolSink psink{HITS ? &s_ent[warp][0] : nullptr, &s_pool[warp], false};
-        lpr_stream<FEAT, HITS>(a, pool, r, sc, ring, p0, p1, c0, c1, fs, hs, psink);
+        PoolSink psink{&ws};
+        lpr_stream<FEAT, HITS>(a, pool, r, sc, ring, p0, p1, c0, c1, fs, ws, psink);
 
         // ---------------- features of my record
         if (FEAT && have) {
@@ -549,7 +666,8 @@ __global__ void __launch_bounds__(kLprWarps * 32) lpr_kernel(const FHArgs a, con
             __syncthreads();  // s_tile reuse
             continue;
         }
-        const int my_cnt = hs.nh;
+        __syncwarp();
+        const int my_cnt = ws.carry_n[lane];
         if (a.hit_counts != nullptr && have) a.hit_counts[rec] = my_cnt;
 
         int incl = my_cnt;
@@ -576,13 +694,13 @@ __global__ void __launch_bounds__(kLprWarps * 32) lpr_kernel(const FHArgs a, con
 
         // ---------------- phase B: one pooled hit per lane -> packed row
         const long long my_row0 = s_wbase[warp] + (incl - my_cnt);
-        const unsigned ovf = __ballot_sync(kFull, psink.overflow);
-        const int used = min(s_pool[warp], kLprEnt);
+        const unsigned ovf = ws.ovf;
+        const int used = min(ws.pool_cnt, kLprEnt);
         for (int e0 = 0; e0 < used; e0 += 32) {
             const int e = e0 + lane;
             const bool act = e < used;
             LprEnt h;
-            *reinterpret_cast<uint4*>(&h) = *reinterpret_cast<const uint4*>(&s_ent[warp][act ? e : 0]);
+            *reinterpret_cast<uint4*>(&h) = *reinterpret_cast<const uint4*>(&ws.ent[act ? e : 0]);
             const int owner = (int)((h.eo >> 16) & 31u);
             RowRec rr;
             rr.ts = bcast_i64(r.ts, owner);
@@ -601,11 +719,14 @@ __global__ void __launch_bounds__(kLprWarps * 32) lpr_kernel(const FHArgs a, con
             }
         }
         if (ovf) {  // some records' hits did not all fit the pool: stream those again, rows go straight out
+            __syncwarp();
+            ws.carry_n[lane] = 0;
+            __syncwarp();
             FeatState fs2 = fs;
-            HitState hs2;
-            hs2.open = false; hs2.run_s = 0; hs2.prev_c = -4; hs2.nh = 0; hs2.carry = 0u; hs2.g.reset();
-            DirectSink dsink{my_row0, psink.overflow};
-            lpr_stream<false, true>(a, pool, r, sc, ring, 0, 0, 0, 0, fs2, hs2, dsink);
+            DirectSink dsink;
+            dsink.my_row0 = my_row0;
+            dsink.my_active = (ovf >> lane) & 1u;
+            lpr_stream<false, true>(a, pool, r, sc, ring, 0, 0, 0, 0, fs2, ws, dsink);
         }
         __syncthreads();  // pool, slots and s_tile are reused by the next tile
     }
@@ -616,11 +737,11 @@ int launch_lpr(FHArgs a, int flags, cudaStream_t st) {
     const char* force = getenv("WFB_FUSED_VARIANT");
     if (force && (!strcmp(force, "global") || !strcmp(force, "staged"))) return 1;
     if (a.lmax >= 65536 - 16) return 1;  // positions are packed in 16 bits
-    if (a.p.left_extension > 8 * kOV || a.p.right_extension > 8 * kOV) return 1;
-    // segment length in chunks: 2 * kOV history chunks + sc new chunks per slot, sc + kOV <= 32 mask bits
-    int sc = 12;
+    if (a.p.left_extension > kMaxExt || a.p.right_extension > kMaxExt) return 1;
+    // segment length in chunks: kHist history chunks + sc new chunks per slot
+    int sc = 8;
     if (const char* e = getenv("WFB_LPR_SC")) sc = std::max(4, std::min(30, atoi(e)));
-    int slot_chunks = sc + 2 * kOV;
+    int slot_chunks = sc + kHist;
     if ((slot_chunks & 1) == 0) ++slot_chunks;  // odd multiple of 16 bytes: conflict-free LDS.128
     a.slot_bytes = slot_chunks * 16;
     const size_t dyn = (size_t)kLprTile * kNBuf * a.slot_bytes;

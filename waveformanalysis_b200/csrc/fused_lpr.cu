@@ -35,16 +35,17 @@ namespace wfb {
 
 constexpr int kLprWarps = 4;
 constexpr int kLprTile = kLprWarps * 32;  // records per tile / look-back unit
-constexpr int kLprEnt = 256;              // staged hits per warp per tile (8 per record on average)
+constexpr int kLprEnt = 320;              // staged hits per warp per tile (10 per record on average)
 constexpr int kHist = 2;                  // chunks of history in front of each segment
 constexpr int kMaxExt = 8;                // extensions must fit the neighbouring chunk
 constexpr int kNBuf = 2;                  // slot buffers per lane
 constexpr int kQCap = 32;                 // items per dense round
 
-struct LprEnt {  // 16 bytes
-    unsigned ps;   // p | s << 16
-    unsigned eo;   // e | owner lane << 16 | ordinal << 21
-    float height, integral;
+struct LprEnt {  // 16 bytes, raw aggregates: height / integral are finished one hit per lane in phase B
+    unsigned ps;  // p | s << 16
+    unsigned eo;  // e | owner lane << 16 | ordinal << 21
+    unsigned kc;  // best threshold key | signal-side sample count << 16
+    unsigned sw;  // sum of the signal-side samples (offset domain)
 };
 
 struct LaneRec {  // everything a lane knows about its record
@@ -63,16 +64,20 @@ struct FeatState {  // per-lane feature accumulators
     double dsum;
 };
 
-struct HitScan {  // per-lane chunk classification pipeline, lives across segments
-    unsigned fa_key, fa_cnt, fa_sw;  // aggregate of the FULL chunks since the last non-FULL one
-    unsigned sn_key, sn_cnt, sn_sw;  // its value in front of the most recent non-FULL chunk
-    bool p_full, p_int, p_last, pp_last;  // chunk vc-1: FULL / has samples above / last sample above; vc-2: last above
+// per-lane chunk classification pipeline, lives across segments.  `flags`: bit 0 chunk vc-1 is
+// FULL, bit 1 it has samples above threshold, bit 2 its last sample is above, bit 3 the last
+// sample of chunk vc-2 is above, bit 4 the FULL-chunk aggregate is to be cleared.
+struct HitScan {
+    unsigned flags;
+    unsigned fa_key, fa_n, fa_sw;  // FULL chunks since the last non-FULL one: min key << 16 | chunk, samples, sum
 };
 
 struct WarpHits {  // per-warp shared memory of the hit machinery
-    uint4 q_ch[3][kQCap];  // item samples: chunk P-1, P, P+1
-    uint4 q_hdr[kQCap];    // owner | (P + 1) << 5 | in_open << 24 | next_full << 25 ; snapshot key, cnt, sum
-    uint4 stage[32];       // this round's "open at chunk end" fragments: start | has << 16 ; key, cnt, sum
+    uint4 q_ch[3][kQCap];  // item samples (raw): chunk P-1, P, P+1
+    uint4 q_best[kQCap];   // the FULL chunk that holds the aggregate's minimum
+    uint4 q_hdr[kQCap];    // owner | (P + 1) << 5 | in_open << 24 | next_full << 25 ; aggregate key, samples, sum
+    uint4 best[32];        // per lane: the chunk behind fa_key
+    uint4 stage[32];       // this round's "open at chunk end" fragments: start ; key, count, key sum
     uint4 carry[32];       // the same, per owner, across rounds
     int stage_n[32];       // runs started by this round's items
     int carry_n[32];       // runs started so far, per owner
@@ -86,44 +91,64 @@ __device__ __forceinline__ int u16_at(const uint4& q, int j) {
     return (int)((w >> ((j & 1) * 16)) & 0xffffu);
 }
 
+// height / integral of a hit from its raw aggregates (hit_finder.py:372-381; float64, no contraction)
+__device__ __forceinline__ void hit_values(int kbest, unsigned cnt, unsigned sw, bool pos, double b, int bias, float& height, float& integral) {
+    const int wp = (pos ? 65535 - kbest : kbest) - bias;
+    height = (float)(pos ? __dsub_rn((double)wp, b) : __dsub_rn(b, (double)wp));
+    const long long c = cnt;
+    const long long swt = (long long)sw - c * bias;
+    double integ;
+    if (fabs(b) < 2e9) {
+        const double bi = floor(b), bf = __dsub_rn(b, bi);
+        const long long ipart = pos ? (swt - c * (long long)bi) : (c * (long long)bi - swt);
+        const double fpart = __dmul_rn((double)c, bf);
+        integ = pos ? __dsub_rn((double)ipart, fpart) : __dadd_rn((double)ipart, fpart);
+    } else {
+        integ = pos ? __dsub_rn((double)swt, __dmul_rn((double)c, b)) : __dsub_rn(__dmul_rn((double)c, b), (double)swt);
+    }
+    integral = (float)integ;
+}
+
 // ---- hit sinks ---------------------------------------------------------------------------------
 struct PoolSink {
-    static constexpr bool kDirect = false;
     WarpHits* ws;
+    int cap;
     __device__ __forceinline__ void prepare(int, const LaneRec&) {}
-    __device__ __forceinline__ void store(int p, int s, int e, float height, float integral, int ord, int owner, const FHArgs&) {
+    __device__ __forceinline__ void store(int p, int s, int e, int kbest, unsigned cnt, unsigned sw, int ord, int owner, const FHArgs&) {
         int idx = atomicAdd(&ws->pool_cnt, 1);
-        if (idx < kLprEnt) {
-            LprEnt h;
-            h.ps = (unsigned)p | ((unsigned)s << 16);
-            h.eo = (unsigned)e | ((unsigned)owner << 16) | ((unsigned)ord << 21);
-            h.height = height;
-            h.integral = integral;
-            *reinterpret_cast<uint4*>(&ws->ent[idx]) = *reinterpret_cast<uint4*>(&h);
+        if (idx < cap) {
+            *reinterpret_cast<uint4*>(&ws->ent[idx]) = make_uint4((unsigned)p | ((unsigned)s << 16), (unsigned)e | ((unsigned)owner << 16) | ((unsigned)ord << 21),
+                                                                  (unsigned)kbest | (cnt << 16), sw);
         } else {
             atomicOr(&ws->ovf, 1u << owner);
         }
     }
 };
 struct DirectSink {  // rows straight to the output (records whose hits did not fit the pool)
-    static constexpr bool kDirect = true;
     long long my_row0;
     bool my_active;
     long long row0;
-    bool active;
+    bool active, pos;
+    double b;
+    int bias;
     RowRec rr;
     __device__ __forceinline__ void prepare(int src, const LaneRec& r) {  // converged: fetch the owner's row data
         row0 = bcast_i64(my_row0, src);
         active = __shfl_sync(kFull, (int)my_active, src) != 0;
+        pos = __shfl_sync(kFull, (int)r.positive, src) != 0;
+        b = shfl_f64(r.b_rec, src);
+        bias = r.bias;
         rr.ts = bcast_i64(r.ts, src);
         rr.rid = bcast_i64(r.rid, src);
         rr.len = __shfl_sync(kFull, r.len, src);
         rr.dt = __shfl_sync(kFull, r.dt, src);
         rr.bc = __shfl_sync(kFull, r.bc, src);
     }
-    __device__ __forceinline__ void store(int p, int s, int e, float height, float integral, int ord, int, const FHArgs& a) {
+    __device__ __forceinline__ void store(int p, int s, int e, int kbest, unsigned cnt, unsigned sw, int ord, int, const FHArgs& a) {
         long long row = row0 + ord;
         if (active && row < a.hit_cap) {
+            float height, integral;
+            hit_values(kbest, cnt, sw, pos, b, bias, height, integral);
             unsigned w[15];
             hit_row_words(w, p, s, e, height, integral, rr, a.p.left_extension, a.p.right_extension, a.lmax);
             unsigned* dst = reinterpret_cast<unsigned*>(a.hit_out + row * kHitRowBytes);
@@ -134,13 +159,17 @@ struct DirectSink {  // rows straight to the output (records whose hits did not 
 };
 
 // ---- dense round: lane t walks the runs of queued item t ---------------------------------------
+// Aggregates are kept in the key domain (kv = w for negative pulses, 65535 - w for positive ones;
+// above threshold <=> kv <= kmax, signal side <=> kv <= kin): a 32-bit key kv << 16 | sample index
+// whose minimum is the first arg-max of the signal, and count << 21 | sum(kv) of the signal-side
+// samples (at most 24 samples per fragment, so the packed sum cannot carry into the count).
 template <typename Sink>
 __device__ __forceinline__ void lpr_round(WarpHits& ws, int qn, const LaneRec& r, const FHArgs& a, Sink& sink) {
     __syncwarp();  // the pushes are visible
     const int lane = lane_id();
     const bool act = lane < qn;
     const uint4 hd = ws.q_hdr[act ? lane : 0];
-    const int src = act ? (int)(hd.x & 31u) : lane;     // owner lane
+    const int src = act ? (int)(hd.x & 31u) : lane;  // owner lane
     const int P = (int)((hd.x >> 5) & 0x3fffu) - 1;  // -1: the virtual chunk in front of a record that starts FULL
     const bool in_open = act && ((hd.x >> 24) & 1u);
     const bool next_full = act && ((hd.x >> 25) & 1u);
@@ -150,29 +179,25 @@ __device__ __forceinline__ void lpr_round(WarpHits& ws, int qn, const LaneRec& r
     const int o_len = __shfl_sync(kFull, r.len, src);
     const int o_wlim = __shfl_sync(kFull, r.wlim, src);
     const bool o_pos = __shfl_sync(kFull, (int)r.positive, src) != 0;
-    const double o_b = shfl_f64(r.b_rec, src);
     sink.prepare(src, r);
     const int bias = r.bias;  // uniform
-    const int sx = bias ? 0x8000 : 0;
-    const int xm16 = o_pos ? 0xffff : 0;
+    const unsigned cx = (bias ? 0x8000u : 0u) ^ (o_pos ? 0xffffu : 0u);  // raw sample -> key
+    const int padkv = o_pos ? 65535 - bias : bias;                       // key of a padding sample (true 0)
+    const int kin = o_pos ? 65535 - (o_wlim + bias) : o_wlim + bias;     // signal side <=> kv <= kin
     const int left = a.p.left_extension, right = a.p.right_extension;
     const int i0 = 8 * P - o_mis;
-    const int inb = o_wlim + bias;
-    auto sample = [&](int i) -> int {  // stored (offset-domain) value of record sample i; padding = true 0
-        const int u = i - i0 + 8;      // 0 .. 23
-        const unsigned short* row = reinterpret_cast<const unsigned short*>(&ws.q_ch[u >> 3][lane]);
-        return (i < o_len) ? ((int)row[u & 7] ^ sx) : bias;
-    };
-    // above-threshold mask of the item's own chunk
+    constexpr unsigned kOne = 1u << 21;
+    // keys of the item's own chunk, packed contributions, above-threshold mask
+    const uint4 c1 = ws.q_ch[1][lane];
+    unsigned ckey[8], cval[8];
     unsigned m8 = 0;
-    if (act) {
-        const uint4 c1 = ws.q_ch[1][lane];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int kv = (u16_at(c1, j) ^ sx) ^ xm16;
-            const int i = i0 + j;
-            m8 |= ((i >= 0 && i < o_len && kv <= o_kmax) ? 1u : 0u) << j;
-        }
+    for (int j = 0; j < 8; ++j) {
+        const int i = i0 + j;
+        const int kv = (i < o_len) ? (int)((unsigned)u16_at(c1, j) ^ cx) : padkv;
+        ckey[j] = ((unsigned)kv << 16) + (unsigned)i;
+        cval[j] = (kv <= kin) ? kOne + (unsigned)kv : 0u;
+        m8 |= ((act && i >= 0 && i < o_len && kv <= o_kmax) ? 1u : 0u) << j;
     }
     const bool nfs = next_full && !(m8 & 0x80u);  // a run starts with the FULL chunk that follows
     const bool has_trail = (m8 & 0x80u) || nfs;
@@ -184,13 +209,24 @@ __device__ __forceinline__ void lpr_round(WarpHits& ws, int qn, const LaneRec& r
     int ord_base = act ? ws.carry_n[src] : 0;
     for (unsigned m = lt; m; m &= m - 1) ord_base += ws.stage_n[__ffs(m) - 1];
 
-    auto agg = [&](int a0, int a1, unsigned& key, unsigned& cnt, unsigned& sw) {
-        for (int i = a0; i < a1; ++i) {
-            const int w = sample(i);
-            key = min(key, ((unsigned)(w ^ xm16) << 16) | (unsigned)i);
-            const bool in = o_pos ? (w >= inb) : (w <= inb);
-            cnt += in ? 1u : 0u;
-            sw += in ? (unsigned)w : 0u;
+    // aggregate of samples [a0, a1): own chunk from registers, the neighbours' few samples from the queue
+    auto frag = [&](int a0, int a1, unsigned& key, unsigned& acc) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const bool in = (i0 + j >= a0) && (i0 + j < a1);
+            if (in) { key = min(key, ckey[j]); acc += cval[j]; }
+        }
+        const unsigned short* lo_row = reinterpret_cast<const unsigned short*>(&ws.q_ch[0][lane]);
+        for (int i = a0; i < min(a1, i0); ++i) {  // left neighbour (never padding: i < i0 <= len)
+            const int kv = (int)((unsigned)lo_row[i - i0 + 8] ^ cx);
+            key = min(key, ((unsigned)kv << 16) + (unsigned)i);
+            acc += (kv <= kin) ? kOne + (unsigned)kv : 0u;
+        }
+        const unsigned short* hi_row = reinterpret_cast<const unsigned short*>(&ws.q_ch[2][lane]);
+        for (int i = max(a0, i0 + 8); i < a1; ++i) {  // right neighbour
+            const int kv = (i < o_len) ? (int)((unsigned)hi_row[i - i0 - 8] ^ cx) : padkv;
+            key = min(key, ((unsigned)kv << 16) + (unsigned)i);
+            acc += (kv <= kin) ? kOne + (unsigned)kv : 0u;
         }
     };
     // the fragment still open at the chunk end: from its start (minus the left extension) to the chunk end
@@ -198,30 +234,41 @@ __device__ __forceinline__ void lpr_round(WarpHits& ws, int qn, const LaneRec& r
     if (has_trail) {
         if (!nfs) js_tr = 8 - __clz(~(m8 << 24));
         const int s_tr = i0 + js_tr;
-        unsigned key = 0xffffffffu, cnt = 0, sw = 0;
-        agg(max(0, s_tr - left), i0 + 8, key, cnt, sw);
-        ws.stage[lane] = make_uint4((unsigned)s_tr, key, cnt, sw);
+        unsigned key = 0xffffffffu, acc = 0;
+        frag(max(0, s_tr - left), i0 + 8, key, acc);
+        ws.stage[lane] = make_uint4((unsigned)s_tr, key, acc >> 21, acc & (kOne - 1u));
     }
     __syncwarp();
     // runs that end in this chunk
     uint4 prev = make_uint4(0u, 0xffffffffu, 0u, 0u);
-    if (in_open) prev = lt ? ws.stage[31 - __clz(lt)] : ws.carry[src];
-    const double bi = floor(o_b), bf = __dsub_rn(o_b, bi);
-    const bool b_small = fabs(o_b) < 2e9;
+    if (in_open) {
+        prev = lt ? ws.stage[31 - __clz(lt)] : ws.carry[src];
+        if (hd.y != 0xffffffffu) {  // FULL chunks between the two items: their minimum sits in the saved chunk
+            const uint4 bq = ws.q_best[lane];
+            const unsigned bkv = hd.y >> 16;
+            int jb = 7;
+#pragma unroll
+            for (int j = 6; j >= 0; --j)
+                if (((unsigned)u16_at(bq, j) ^ cx) == bkv) jb = j;
+            prev.y = min(prev.y, (bkv << 16) + (unsigned)(8 * (int)(hd.y & 0xffffu) - o_mis + jb));
+            prev.z += hd.z;
+            prev.w += o_pos ? hd.z * 65535u - hd.w : hd.w;
+        }
+    }
     unsigned mm = (has_trail && !nfs) ? (m8 & ((1u << js_tr) - 1u)) : m8;
     bool lead = in_open;
     int k = 0;
     while (lead || mm) {
         int s, e, a0, ord;
-        unsigned key = 0xffffffffu, cnt = 0, sw = 0;
+        unsigned key = 0xffffffffu, cnt = 0, skv = 0;
         if (lead) {
             const int t0 = __ffs(~m8 & 0x1ffu) - 1;  // the incoming run ends at the first sample below threshold
             e = i0 + t0;
-            s = (int)(prev.x & 0xffffu);
+            s = (int)prev.x;
             a0 = i0;
-            key = min(prev.y, hd.y);
-            cnt = prev.z + hd.z;
-            sw = prev.w + hd.w;
+            key = prev.y;
+            cnt = prev.z;
+            skv = prev.w;
             ord = ord_base - 1;
             mm &= ~((1u << t0) - 1u);
             lead = false;
@@ -235,21 +282,11 @@ __device__ __forceinline__ void lpr_round(WarpHits& ws, int qn, const LaneRec& r
             ++k;
             mm &= ~((1u << je) - 1u);
         }
-        agg(a0, min(a.lmax, e + right), key, cnt, sw);
-        const int kbest = (int)(key >> 16), ibest = (int)(key & 0xffffu);
-        const int wp = (o_pos ? 65535 - kbest : kbest) - bias;
-        const float height = (float)(o_pos ? __dsub_rn((double)wp, o_b) : __dsub_rn(o_b, (double)wp));
-        const long long c = cnt;
-        const long long swt = (long long)sw - c * bias;
-        double integ;
-        if (b_small) {
-            const long long ipart = o_pos ? (swt - c * (long long)bi) : (c * (long long)bi - swt);
-            const double fpart = __dmul_rn((double)c, bf);
-            integ = o_pos ? __dsub_rn((double)ipart, fpart) : __dadd_rn((double)ipart, fpart);
-        } else {
-            integ = o_pos ? __dsub_rn((double)swt, __dmul_rn((double)c, o_b)) : __dsub_rn(__dmul_rn((double)c, o_b), (double)swt);
-        }
-        sink.store(ibest, s, e, height, (float)integ, ord, src, a);
+        unsigned acc = 0;
+        frag(a0, min(a.lmax, e + right), key, acc);
+        cnt += acc >> 21;
+        skv += acc & (kOne - 1u);
+        sink.store((int)(key & 0xffffu), s, e, (int)(key >> 16), cnt, o_pos ? cnt * 65535u - skv : skv, ord, src, a);
     }
     __syncwarp();  // every read of stage / carry is done
     if (act && !(peers >> lane >> 1)) {  // the last item of this owner in the round
@@ -279,7 +316,7 @@ __device__ __forceinline__ void tma_tensor2d_g2s(void* dst_smem, const CUtensorM
                  : "memory");
 }
 
-template <bool FEAT, bool HITS, typename Sink>
+template <bool FEAT, bool HITS, bool SGN, typename Sink>
 __device__ __forceinline__ void lpr_stream(const FHArgs& a, const uint16_t* pool, const LaneRec& r, int sc, const Ring& ring,
                                            int p0, int p1, int c0, int c1, FeatState& fs, WarpHits& ws, Sink& sink) {
     const int lane = lane_id();
@@ -291,8 +328,6 @@ __device__ __forceinline__ void lpr_stream(const FHArgs& a, const uint16_t* pool
     const int nsteps = (nch_max > 0) ? (HITS ? nch_max + 3 : nch_max) : 0;
     const int nseg = (nsteps + sc - 1) / sc;
     const bool known = r.pol == WFB_POL_POSITIVE || r.pol == WFB_POL_NEGATIVE;
-    const unsigned sx32 = r.bias ? 0x80008000u : 0u;
-    const unsigned xm = r.positive ? 0xffffffffu : 0u;
     const float b32 = (float)r.b_feat;
     // chunk ranges of the "plain" fast path: [plainA, plainB) minus [plainHa, plainHb)
     int plainA = 0, plainB = 0, plainHa = 0, plainHb = 0;
@@ -304,9 +339,9 @@ __device__ __forceinline__ void lpr_stream(const FHArgs& a, const uint16_t* pool
         if (p1 > p0) { plainHa = (mis + p0) >> 3; plainHb = (mis + p1 + 7) >> 3; }
     }
     HitScan hs;
-    hs.fa_key = 0xffffffffu; hs.fa_cnt = 0; hs.fa_sw = 0;
-    hs.sn_key = 0xffffffffu; hs.sn_cnt = 0; hs.sn_sw = 0;
-    hs.p_full = false; hs.p_int = false; hs.p_last = false; hs.pp_last = false;
+    hs.flags = 0u; hs.fa_key = 0xffffffffu; hs.fa_n = 0u; hs.fa_sw = 0u;
+    // threshold test on the raw offset-domain sample w: negative pulses w <= kmax, positive ones w >= 65535 - kmax
+    const int wthr = r.positive ? 65535 - r.kmax : r.kmax;
     int qn = 0;  // queued items (warp-uniform)
 
     auto issue = [&](int s) {
@@ -344,11 +379,13 @@ __device__ __forceinline__ void lpr_stream(const FHArgs& a, const uint16_t* pool
         for (int cb = 0; cb < cend; ++cb) {
             const int vc = s * sc + cb;
             // classification of chunk vc (a chunk behind the record end is QUIET)
-            bool c_full = false, c_int = false, c_last = false;
-            unsigned ckey = 0xffffffffu, csum = 0;
+            unsigned c_full = 0u, c_int = 0u, c_last = 0u;
+            unsigned cand = 0xffffffffu, csum = 0u;
+            uint4 raw = make_uint4(0u, 0u, 0u, 0u);
             if (vc < nch) {
-                uint4 q = *reinterpret_cast<const uint4*>(buf + (kHist + cb) * 16);
-                if (sx32) { q.x ^= sx32; q.y ^= sx32; q.z ^= sx32; q.w ^= sx32; }  // int16 -> offset binary
+                raw = *reinterpret_cast<const uint4*>(buf + (kHist + cb) * 16);
+                uint4 q = raw;
+                if (SGN) { q.x ^= 0x80008000u; q.y ^= 0x80008000u; q.z ^= 0x80008000u; q.w ^= 0x80008000u; }  // int16 -> offset binary
                 const int v0 = vc * 8;
                 const int lo = max(mis - v0, 0), hi = min(vtotal - v0, 8);
                 const int i0 = v0 - mis;
@@ -423,48 +460,34 @@ __device__ __forceinline__ void lpr_stream(const FHArgs& a, const uint16_t* pool
                     fs.prev_w = q.w;
                 }
                 if (HITS) {
-                    const unsigned k0 = q.x ^ xm, k1 = q.y ^ xm, k2 = q.z ^ xm, k3 = q.w ^ xm;  // threshold keys: above <=> key <= kmax
                     if (whole) {
-                        // 32-bit keys  kv << 16 | j : their minimum is the chunk's first arg-min
-                        const unsigned e0 = (k0 << 16), o0 = (k0 & 0xffff0000u) | 1u;
-                        const unsigned e1 = (k1 << 16) | 2u, o1 = (k1 & 0xffff0000u) | 3u;
-                        const unsigned e2 = (k2 << 16) | 4u, o2 = (k2 & 0xffff0000u) | 5u;
-                        const unsigned e3 = (k3 << 16) | 6u, o3 = (k3 & 0xffff0000u) | 7u;
-                        const unsigned mn = min(min(min(e0, o0), min(e1, o1)), min(min(e2, o2), min(e3, o3)));
-                        const unsigned mx = max(max(max(e0, o0), max(e1, o1)), max(max(e2, o2), max(e3, o3)));
-                        c_int = (int)(mn >> 16) <= r.kmax;
-                        c_full = (int)(mx >> 16) <= r.kmax;
-                        c_last = (int)(k3 >> 16) <= r.kmax;
-                        ckey = mn + (unsigned)i0;
-                    } else {
-                        const uint4 kq = make_uint4(k0, k1, k2, k3);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const bool ab = (j >= lo) && (j < hi) && (u16_at(kq, j) <= r.kmax);
-                            c_int = c_int || ab;
-                            if (j == 7) c_last = ab;
+                        const unsigned mn2 = __vminu2(__vimin3_u16x2(q.x, q.y, q.z), q.w);
+                        const unsigned mx2 = __vmaxu2(__vimax3_u16x2(q.x, q.y, q.z), q.w);
+                        const int wmin = (int)min(mn2 & 0xffffu, mn2 >> 16), wmax = (int)max(mx2 & 0xffffu, mx2 >> 16);
+                        const int wl = (int)(q.w >> 16);
+                        if (r.positive) {
+                            c_int = wmax >= wthr; c_full = wmin >= wthr; c_last = wl >= wthr;
+                            cand = ((unsigned)(65535 - wmax) << 16) | (unsigned)vc;
+                        } else {
+                            c_int = wmin <= wthr; c_full = wmax <= wthr; c_last = wl <= wthr;
+                            cand = ((unsigned)wmin << 16) | (unsigned)vc;
                         }
-                    }
-                    if (c_full && r.degen) {  // negative threshold: samples above it may lie on the far side of the baseline
-                        unsigned cnt = 0, sw = 0;
+                    } else {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const int w = u16_at(q, j);
-                            const bool in = r.positive ? (w >= r.wlim + r.bias) : (w <= r.wlim + r.bias);
-                            cnt += in ? 1u : 0u;
-                            sw += in ? (unsigned)w : 0u;
+                            const bool ab = (j >= lo) && (j < hi) && (r.positive ? (w >= wthr) : (w <= wthr));
+                            c_int |= ab ? 1u : 0u;
+                            if (j == 7) c_last = ab ? 1u : 0u;
                         }
-                        csum = sw;
-                        hs.fa_cnt += cnt;
-                    } else if (c_full) {
-                        hs.fa_cnt += 8u;
                     }
                 }
             }
             if (HITS) {
                 // chunk P = vc - 1 is an item if it is not FULL and holds, follows or precedes samples above threshold
                 const int P = vc - 1;
-                const bool want = P >= -1 && P <= nch && !hs.p_full && (hs.p_int || hs.pp_last || c_full);
+                const unsigned f = hs.flags;
+                const bool want = (~f & ((f >> 1) | (f >> 3) | c_full) & 1u) != 0u;
                 const unsigned bal = __ballot_sync(kFull, want);
                 const bool flush = vc == nsteps - 1;
                 if (bal || flush) {
@@ -475,30 +498,38 @@ __device__ __forceinline__ void lpr_stream(const FHArgs& a, const uint16_t* pool
                     }
                     if (want) {
                         const int slot = qn + __popc(bal & ((1u << lane) - 1u));
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) {
-                            const int ch = P - 1 + k;
-                            uint4 d = make_uint4(0u, 0u, 0u, 0u);
-                            if (ch >= 0 && ch < nch) d = *reinterpret_cast<const uint4*>(buf + (ch - cbase) * 16);
-                            ws.q_ch[k][slot] = d;
-                        }
-                        ws.q_hdr[slot] = make_uint4((unsigned)lane | ((unsigned)(P + 1) << 5) | (hs.pp_last ? 1u << 24 : 0u) | (c_full ? 1u << 25 : 0u),
-                                                    hs.sn_key, hs.sn_cnt, hs.sn_sw);
+                        const uint8_t* src = buf + cb * 16;  // chunks P-1, P, P+1 (positions outside the record are never used)
+                        ws.q_ch[0][slot] = *reinterpret_cast<const uint4*>(src);
+                        ws.q_ch[1][slot] = *reinterpret_cast<const uint4*>(src + 16);
+                        ws.q_ch[2][slot] = *reinterpret_cast<const uint4*>(src + 32);
+                        ws.q_best[slot] = ws.best[lane];
+                        ws.q_hdr[slot] = make_uint4((unsigned)lane | ((unsigned)(P + 1) << 5) | ((f & 8u) << 21) | (c_full << 25), hs.fa_key, hs.fa_n, hs.fa_sw);
                     }
                     qn += np;
                 }
                 // chunk vc enters the pipeline
-                hs.pp_last = hs.p_last;
-                hs.p_last = c_last;
-                hs.p_full = c_full;
-                hs.p_int = c_int;
+                if (f & 16u) { hs.fa_key = 0xffffffffu; hs.fa_n = 0u; hs.fa_sw = 0u; }
                 if (c_full) {
-                    hs.fa_key = min(hs.fa_key, ckey);
-                    hs.fa_sw += csum;
-                } else {
-                    hs.sn_key = hs.fa_key; hs.sn_cnt = hs.fa_cnt; hs.sn_sw = hs.fa_sw;
-                    hs.fa_key = 0xffffffffu; hs.fa_cnt = 0; hs.fa_sw = 0;
+                    if (cand < hs.fa_key) {
+                        hs.fa_key = cand;
+                        ws.best[lane] = raw;
+                    }
+                    if (!r.degen) {
+                        hs.fa_n += 8u;
+                        hs.fa_sw += csum;
+                    } else {  // negative threshold: samples above it may lie on the far side of the baseline
+                        uint4 q = raw;
+                        if (SGN) { q.x ^= 0x80008000u; q.y ^= 0x80008000u; q.z ^= 0x80008000u; q.w ^= 0x80008000u; }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int w = u16_at(q, j);
+                            const bool in = r.positive ? (w >= r.wlim + r.bias) : (w <= r.wlim + r.bias);
+                            hs.fa_n += in ? 1u : 0u;
+                            hs.fa_sw += in ? (unsigned)w : 0u;
+                        }
+                    }
                 }
+                hs.flags = c_full | (c_int << 1) | (c_last << 2) | ((f & 4u) << 1) | (c_full ? 0u : 16u);
             }
         }
         __syncwarp();  // every lane is done with buffer b before it is refilled
@@ -506,9 +537,9 @@ __device__ __forceinline__ void lpr_stream(const FHArgs& a, const uint16_t* pool
 }
 
 // ---- the kernel --------------------------------------------------------------------------------
-template <bool FEAT, bool HITS>
+template <bool FEAT, bool HITS, bool SGN>
 __global__ void __launch_bounds__(kLprWarps * 32) lpr_kernel(const FHArgs a, const int sc, const __grid_constant__ CUtensorMap tmap,
-                                                             const int have_tmap) {
+                                                             const int have_tmap, const int ent_cap) {
     extern __shared__ __align__(128) uint8_t dyn_smem[];  // [warp][kNBuf][lane] slots of a.slot_bytes
     __shared__ __align__(16) WarpHits s_hits[HITS ? kLprWarps : 1];
     __shared__ long long s_wtot[kLprWarps];
@@ -610,8 +641,8 @@ __global__ void __launch_bounds__(kLprWarps * 32) lpr_kernel(const FHArgs a, con
             if (lane == 0) { ws.pool_cnt = 0; ws.ovf = 0u; }
         }
         __syncwarp();
-        PoolSink psink{&ws};
-        lpr_stream<FEAT, HITS>(a, pool, r, sc, ring, p0, p1, c0, c1, fs, ws, psink);
+        PoolSink psink{&ws, ent_cap};
+        lpr_stream<FEAT, HITS, SGN>(a, pool, r, sc, ring, p0, p1, c0, c1, fs, ws, psink);
 
         // ---------------- features of my record
         if (FEAT && have) {
@@ -695,7 +726,7 @@ __global__ void __launch_bounds__(kLprWarps * 32) lpr_kernel(const FHArgs a, con
         // ---------------- phase B: one pooled hit per lane -> packed row
         const long long my_row0 = s_wbase[warp] + (incl - my_cnt);
         const unsigned ovf = ws.ovf;
-        const int used = min(ws.pool_cnt, kLprEnt);
+        const int used = min(ws.pool_cnt, ent_cap);
         for (int e0 = 0; e0 < used; e0 += 32) {
             const int e = e0 + lane;
             const bool act = e < used;
@@ -708,10 +739,14 @@ __global__ void __launch_bounds__(kLprWarps * 32) lpr_kernel(const FHArgs a, con
             rr.len = __shfl_sync(kFull, r.len, owner);
             rr.dt = __shfl_sync(kFull, r.dt, owner);
             rr.bc = __shfl_sync(kFull, r.bc, owner);
+            const double o_b = shfl_f64(r.b_rec, owner);
+            const bool o_pos = __shfl_sync(kFull, (int)r.positive, owner) != 0;
             const long long row = bcast_i64(my_row0, owner) + (long long)(h.eo >> 21);
             if (act && !((ovf >> owner) & 1u) && row < a.hit_cap) {
+                float height, integral;
+                hit_values((int)(h.kc & 0xffffu), h.kc >> 16, h.sw, o_pos, o_b, r.bias, height, integral);
                 unsigned w[15];
-                hit_row_words(w, (int)(h.ps & 0xffffu), (int)(h.ps >> 16), (int)(h.eo & 0xffffu), h.height, h.integral, rr,
+                hit_row_words(w, (int)(h.ps & 0xffffu), (int)(h.ps >> 16), (int)(h.eo & 0xffffu), height, integral, rr,
                               a.p.left_extension, a.p.right_extension, a.lmax);
                 unsigned* dst = reinterpret_cast<unsigned*>(a.hit_out + row * kHitRowBytes);
 #pragma unroll
@@ -726,7 +761,7 @@ __global__ void __launch_bounds__(kLprWarps * 32) lpr_kernel(const FHArgs a, con
             DirectSink dsink;
             dsink.my_row0 = my_row0;
             dsink.my_active = (ovf >> lane) & 1u;
-            lpr_stream<false, true>(a, pool, r, sc, ring, 0, 0, 0, 0, fs2, ws, dsink);
+            lpr_stream<false, true, SGN>(a, pool, r, sc, ring, 0, 0, 0, 0, fs2, ws, dsink);
         }
         __syncthreads();  // pool, slots and s_tile are reused by the next tile
     }
@@ -739,8 +774,10 @@ int launch_lpr(FHArgs a, int flags, cudaStream_t st) {
     if (a.lmax >= 65536 - 16) return 1;  // positions are packed in 16 bits
     if (a.p.left_extension > kMaxExt || a.p.right_extension > kMaxExt) return 1;
     // segment length in chunks: kHist history chunks + sc new chunks per slot
-    int sc = 8;
+    int sc = 6;
     if (const char* e = getenv("WFB_LPR_SC")) sc = std::max(4, std::min(30, atoi(e)));
+    int ent_cap = kLprEnt;  // WFB_LPR_POOL shrinks the per-warp hit pool (exercises the overflow path in tests)
+    if (const char* e = getenv("WFB_LPR_POOL")) ent_cap = std::max(0, std::min(kLprEnt, atoi(e)));
     int slot_chunks = sc + kHist;
     if ((slot_chunks & 1) == 0) ++slot_chunks;  // odd multiple of 16 bytes: conflict-free LDS.128
     a.slot_bytes = slot_chunks * 16;
@@ -783,13 +820,18 @@ int launch_lpr(FHArgs a, int flags, cudaStream_t st) {
             return WFB_ERR_CUDA;
         }
         int grid = (int)std::min<long long>((long long)sm_count() * per_sm, a.n_tiles);
-        kern<<<grid, kLprWarps * 32, dyn, st>>>(a, sc, tmap, have_tmap);
+        kern<<<grid, kLprWarps * 32, dyn, st>>>(a, sc, tmap, have_tmap, ent_cap);
         WFB_CUDA(cudaGetLastError());
         return WFB_OK;
     };
-    if (f && h) return go(lpr_kernel<true, true>);
-    if (f) return go(lpr_kernel<true, false>);
-    return go(lpr_kernel<false, true>);
+    if (a.p.signed_samples) {
+        if (f && h) return go(lpr_kernel<true, true, true>);
+        if (f) return go(lpr_kernel<true, false, true>);
+        return go(lpr_kernel<false, true, true>);
+    }
+    if (f && h) return go(lpr_kernel<true, true, false>);
+    if (f) return go(lpr_kernel<true, false, false>);
+    return go(lpr_kernel<false, true, false>);
 }
 
 }  // namespace wfb

@@ -287,7 +287,7 @@ def run_ours(args):
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": (traffic or {}).get("dram_bytes_per_launch"),
-        "peak_source": peak_src, "kernel": "fused_features_hits_kernel<uint16,true,true>",
+        "peak_source": peak_src, "kernel": "lpr_kernel<features,hits,u16> (fused_lpr.cu)",
         "bytes_per_record": bytes_per_record, "hits_per_record": h, "kernel_ms": kernel_ms,
         "raw_sample_GBps": n * 2 * N_SAMPLES / (kernel_ms * 1e-3) / 1e9,
     }

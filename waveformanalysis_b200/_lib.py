@@ -13,7 +13,7 @@ import os
 import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libwfb200.so")
+LIB_PATH = os.environ.get("WFB200_LIB") or os.path.join(HERE, "libwfb200.so")  # WFB200_LIB: development override
 
 WFB_OK = 0
 WFB_ERR_INVALID = -1

@@ -35,7 +35,10 @@ namespace wfb {
 
 constexpr int kLprWarps = 4;
 constexpr int kLprTile = kLprWarps * 32;  // records per tile / look-back unit
-constexpr int kLprEnt = 320;              // staged hits per warp per tile (10 per record on average)
+#ifndef WFB_LPR_ENT
+#define WFB_LPR_ENT 320
+#endif
+constexpr int kLprEnt = WFB_LPR_ENT;              // staged hits per warp per tile (10 per record on average)
 constexpr int kHist = 2;                  // chunks of history in front of each segment
 constexpr int kMaxExt = 8;                // extensions must fit the neighbouring chunk
 constexpr int kNBuf = 2;                  // slot buffers per lane
@@ -374,7 +377,6 @@ __device__ __forceinline__ void lpr_stream(const FHArgs& a, const uint16_t* pool
         mbar_wait(&ring.bars[b], (*ring.phase_bits >> b) & 1u);
         *ring.phase_bits ^= 1u << b;
         const uint8_t* buf = ring.slot + b * ring.buf_stride;
-        const int cbase = s * sc - kHist;
         const int cend = min(sc, nsteps - s * sc);
         for (int cb = 0; cb < cend; ++cb) {
             const int vc = s * sc + cb;

@@ -36,9 +36,9 @@ namespace wfb {
 constexpr int kLprWarps = 4;
 constexpr int kLprTile = kLprWarps * 32;  // records per tile / look-back unit
 #ifndef WFB_LPR_ENT
-#define WFB_LPR_ENT 320
+#define WFB_LPR_ENT 256
 #endif
-constexpr int kLprEnt = WFB_LPR_ENT;              // staged hits per warp per tile (10 per record on average)
+constexpr int kLprEnt = WFB_LPR_ENT;              // staged hits per warp per tile (8 per record on average)
 constexpr int kHist = 2;                  // chunks of history in front of each segment
 constexpr int kMaxExt = 8;                // extensions must fit the neighbouring chunk
 constexpr int kNBuf = 2;                  // slot buffers per lane
@@ -67,19 +67,9 @@ struct FeatState {  // per-lane feature accumulators
     double dsum;
 };
 
-// per-lane chunk classification pipeline, lives across segments.  `flags`: bit 0 chunk vc-1 is
-// FULL, bit 1 it has samples above threshold, bit 2 its last sample is above, bit 3 the last
-// sample of chunk vc-2 is above, bit 4 the FULL-chunk aggregate is to be cleared.
-struct HitScan {
-    unsigned flags;
-    unsigned fa_key, fa_n, fa_sw;  // FULL chunks since the last non-FULL one: min key << 16 | chunk, samples, sum
-};
-
 struct WarpHits {  // per-warp shared memory of the hit machinery
     uint4 q_ch[3][kQCap];  // item samples (raw): chunk P-1, P, P+1
-    uint4 q_best[kQCap];   // the FULL chunk that holds the aggregate's minimum
     uint4 q_hdr[kQCap];    // owner | (P + 1) << 5 | in_open << 24 | next_full << 25 ; aggregate key, samples, sum
-    uint4 best[32];        // per lane: the chunk behind fa_key
     uint4 stage[32];       // this round's "open at chunk end" fragments: start ; key, count, key sum
     uint4 carry[32];       // the same, per owner, across rounds
     int stage_n[32];       // runs started by this round's items
@@ -182,6 +172,7 @@ __device__ __forceinline__ void lpr_round(WarpHits& ws, int qn, const LaneRec& r
     const int o_len = __shfl_sync(kFull, r.len, src);
     const int o_wlim = __shfl_sync(kFull, r.wlim, src);
     const bool o_pos = __shfl_sync(kFull, (int)r.positive, src) != 0;
+    const long long o_off = bcast_i64(r.off, src);
     sink.prepare(src, r);
     const int bias = r.bias;  // uniform
     const unsigned cx = (bias ? 0x8000u : 0u) ^ (o_pos ? 0xffffu : 0u);  // raw sample -> key
@@ -246,8 +237,8 @@ __device__ __forceinline__ void lpr_round(WarpHits& ws, int qn, const LaneRec& r
     uint4 prev = make_uint4(0u, 0xffffffffu, 0u, 0u);
     if (in_open) {
         prev = lt ? ws.stage[31 - __clz(lt)] : ws.carry[src];
-        if (hd.y != 0xffffffffu) {  // FULL chunks between the two items: their minimum sits in the saved chunk
-            const uint4 bq = ws.q_best[lane];
+        if (hd.y != 0xffffffffu) {  // FULL chunks between the two items: re-read the one that holds their minimum (L2)
+            const uint4 bq = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(a.pool) + (o_off - o_mis) + 8ll * (long long)(hd.y & 0xffffu)));
             const unsigned bkv = hd.y >> 16;
             int jb = 7;
 #pragma unroll
@@ -319,6 +310,13 @@ __device__ __forceinline__ void tma_tensor2d_g2s(void* dst_smem, const CUtensorM
                  : "memory");
 }
 
+// chunk summary handed from the sample code to the block-level hit bookkeeping
+struct ChunkSum {
+    unsigned f, i, l;   // FULL / has samples above threshold / last sample above (0 or 1)
+    unsigned cand;      // min key << 16 | chunk index (FULL chunks)
+    unsigned n, sw;     // signal-side samples and their sum (FULL chunks)
+};
+
 template <bool FEAT, bool HITS, bool SGN, typename Sink>
 __device__ __forceinline__ void lpr_stream(const FHArgs& a, const uint16_t* pool, const LaneRec& r, int sc, const Ring& ring,
                                            int p0, int p1, int c0, int c1, FeatState& fs, WarpHits& ws, Sink& sink) {
@@ -326,10 +324,13 @@ __device__ __forceinline__ void lpr_stream(const FHArgs& a, const uint16_t* pool
     const int mis = r.mis, vtotal = r.mis + r.len;
     const int nch = (r.len > 0) ? ((vtotal + 7) >> 3) : 0;
     const int nch_max = __reduce_max_sync(kFull, nch);
-    // the hit pipeline lags the scan by one chunk, closes runs at a virtual chunk behind the record
-    // and flushes the item queue one step later: three steps past the last chunk
-    const int nsteps = (nch_max > 0) ? (HITS ? nch_max + 3 : nch_max) : 0;
-    const int nseg = (nsteps + sc - 1) / sc;
+    // the scan advances in blocks of four chunks; the hit bookkeeping of a block covers the chunks
+    // one behind it (it needs each chunk's successor), runs are closed at a virtual chunk behind the
+    // record, so the scan runs two chunks past the longest record of the warp
+    const int nsteps = (nch_max > 0) ? (HITS ? nch_max + 2 : nch_max) : 0;
+    const int nblk = (nsteps + 3) >> 2;
+    const int bps = sc >> 2;  // blocks per segment
+    const int nseg = (nblk + bps - 1) / bps;
     const bool known = r.pol == WFB_POL_POSITIVE || r.pol == WFB_POL_NEGATIVE;
     const float b32 = (float)r.b_feat;
     // chunk ranges of the "plain" fast path: [plainA, plainB) minus [plainHa, plainHb)
@@ -341,10 +342,14 @@ __device__ __forceinline__ void lpr_stream(const FHArgs& a, const uint16_t* pool
         plainB = vhi >> 3;
         if (p1 > p0) { plainHa = (mis + p0) >> 3; plainHb = (mis + p1 + 7) >> 3; }
     }
-    HitScan hs;
-    hs.flags = 0u; hs.fa_key = 0xffffffffu; hs.fa_n = 0u; hs.fa_sw = 0u;
-    // threshold test on the raw offset-domain sample w: negative pulses w <= kmax, positive ones w >= 65535 - kmax
+    const int wholeA = (mis + 7) >> 3, wholeB = vtotal >> 3;  // chunks [wholeA, wholeB) hold 8 samples of the record
+    // threshold test on the offset-domain sample w: negative pulses w <= kmax, positive ones w >= 65535 - kmax
     const int wthr = r.positive ? 65535 - r.kmax : r.kmax;
+    const unsigned xm16 = r.positive ? 0xffffu : 0u;
+    // block-level class masks: bit 0 chunk 4b-2, bit 1 chunk 4b-1, bits 2..5 the block's own chunks
+    unsigned Fm = 0u, Im = 0u, Lm = 0u;
+    // aggregate of the FULL chunks in front of chunk 4b-1 and of chunk 4b
+    unsigned am_key = 0xffffffffu, am_n = 0u, am_sw = 0u, a0_key = 0xffffffffu, a0_n = 0u, a0_sw = 0u;
     int qn = 0;  // queued items (warp-uniform)
 
     auto issue = [&](int s) {
@@ -370,6 +375,137 @@ __device__ __forceinline__ void lpr_stream(const FHArgs& a, const uint16_t* pool
         if (bytes) tma_bulk_g2s(ring.slot + b * ring.buf_stride + (clo - cb) * 16, pool + (r.off - mis) + (long long)clo * 8, bytes, &ring.bars[b]);
     };
 
+    // features of a plain chunk: 8 samples inside the area range, outside the height range
+    auto feat_plain = [&](const uint4& q, unsigned csum) {
+        unsigned f0 = __funnelshift_r(fs.prev_w, q.x, 16), f1 = __funnelshift_r(q.x, q.y, 16);
+        unsigned f2 = __funnelshift_r(q.y, q.z, 16), f3 = __funnelshift_r(q.z, q.w, 16);
+        unsigned d0 = __vmaxu2(q.x, f0) - __vminu2(q.x, f0), d1 = __vmaxu2(q.y, f1) - __vminu2(q.y, f1);
+        unsigned d2 = __vmaxu2(q.z, f2) - __vminu2(q.z, f2), d3 = __vmaxu2(q.w, f3) - __vminu2(q.w, f3);
+        fs.pdiff = __vimax3_u16x2(fs.pdiff, __vmaxu2(d0, d1), __vmaxu2(d2, d3));
+        fs.isum32 += csum;
+        fs.prev_w = q.w;
+    };
+    // class of a chunk that holds 8 samples of the record
+    auto class_whole = [&](const uint4& q, int vc, unsigned csum, ChunkSum& c) {
+        const unsigned mn2 = __vminu2(__vimin3_u16x2(q.x, q.y, q.z), q.w);
+        const unsigned mx2 = __vmaxu2(__vimax3_u16x2(q.x, q.y, q.z), q.w);
+        const int wmin = (int)min(mn2 & 0xffffu, mn2 >> 16), wmax = (int)max(mx2 & 0xffffu, mx2 >> 16);
+        const int kvmin = (int)((unsigned)(r.positive ? wmax : wmin) ^ xm16), kvmax = (int)((unsigned)(r.positive ? wmin : wmax) ^ xm16);
+        const int kvl = (int)((q.w >> 16) ^ xm16);
+        c.i = kvmin <= r.kmax;
+        c.f = kvmax <= r.kmax;
+        c.l = kvl <= r.kmax;
+        c.cand = ((unsigned)kvmin << 16) | (unsigned)vc;
+        c.n = 8u;
+        c.sw = csum;
+    };
+    // any chunk (record start / end, height range, known polarity, behind the record)
+    auto chunk_generic = [&](const uint8_t* buf, int pos, int vc, ChunkSum& c) {
+        c.f = 0u; c.i = 0u; c.l = 0u; c.cand = 0xffffffffu; c.n = 0u; c.sw = 0u;
+        if (vc >= nch) return;
+        uint4 q = *reinterpret_cast<const uint4*>(buf + pos * 16);
+        if (SGN) { q.x ^= 0x80008000u; q.y ^= 0x80008000u; q.z ^= 0x80008000u; q.w ^= 0x80008000u; }  // int16 -> offset binary
+        const int v0 = vc * 8;
+        const int lo = max(mis - v0, 0), hi = min(vtotal - v0, 8);
+        const int i0 = v0 - mis;
+        const bool whole = lo == 0 && hi == 8;
+        unsigned csum = 0u;
+        if (whole && (HITS || !known)) {
+            csum = __dp2a_lo(q.x, 0x0101u, 0u);
+            csum = __dp2a_lo(q.y, 0x0101u, csum);
+            csum = __dp2a_lo(q.z, 0x0101u, csum);
+            csum = __dp2a_lo(q.w, 0x0101u, csum);
+        }
+        if (FEAT) {
+            if (vc >= plainA && vc < plainB && (vc < plainHa || vc >= plainHb)) {
+                feat_plain(q, csum);
+            } else if (whole) {
+                const unsigned pw = (i0 > 0) ? fs.prev_w : (q.x << 16);
+                unsigned f0 = __funnelshift_r(pw, q.x, 16), f1 = __funnelshift_r(q.x, q.y, 16);
+                unsigned f2 = __funnelshift_r(q.y, q.z, 16), f3 = __funnelshift_r(q.z, q.w, 16);
+                unsigned d0 = __vmaxu2(q.x, f0) - __vminu2(q.x, f0), d1 = __vmaxu2(q.y, f1) - __vminu2(q.y, f1);
+                unsigned d2 = __vmaxu2(q.z, f2) - __vminu2(q.z, f2), d3 = __vmaxu2(q.w, f3) - __vminu2(q.w, f3);
+                fs.pdiff = __vmaxu2(fs.pdiff, __vmaxu2(__vmaxu2(d0, d1), __vmaxu2(d2, d3)));
+                const int jlo = max(0, p0 - i0), jhi = min(8, p1 - i0);
+                if (jhi > jlo) {
+                    if (jlo == 0 && jhi == 8) {
+                        fs.pmin = __vminu2(fs.pmin, __vminu2(__vminu2(q.x, q.y), __vminu2(q.z, q.w)));
+                        fs.pmax = __vmaxu2(fs.pmax, __vmaxu2(__vmaxu2(q.x, q.y), __vmaxu2(q.z, q.w)));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            int w = u16_at(q, j);
+                            if (j >= jlo && j < jhi) { fs.imin = min(fs.imin, w); fs.imax = max(fs.imax, w); }
+                        }
+                    }
+                }
+                const int klo = max(0, c0 - i0), khi = min(8, c1 - i0);
+                if (khi > klo) {
+                    if (klo == 0 && khi == 8 && !known) {
+                        fs.isum32 += csum;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            unsigned w = (unsigned)u16_at(q, j);
+                            if (j >= klo && j < khi) {
+                                if (!known) fs.isum32 += w;
+                                else fs.dsum += (double)(r.positive ? __fsub_rn((float)w, b32) : __fsub_rn(b32, (float)w));
+                            }
+                        }
+                    }
+                }
+                fs.prev_w = q.w;
+            } else {
+                // partial chunk (record start / end): per-sample
+                const int prev_s = (int)(fs.prev_w >> 16);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int w = u16_at(q, j);
+                    if (j >= lo && j < hi) {
+                        const int i = i0 + j;
+                        if (i > 0) fs.idiff = max(fs.idiff, abs(w - ((j == 0) ? prev_s : u16_at(q, j - 1))));
+                        if (i >= p0 && i < p1) { fs.imin = min(fs.imin, w); fs.imax = max(fs.imax, w); }
+                        if (i >= c0 && i < c1) {
+                            if (!known) fs.isum32 += (unsigned)w;
+                            else fs.dsum += (double)(r.positive ? __fsub_rn((float)w, b32) : __fsub_rn(b32, (float)w));
+                        }
+                    }
+                }
+                fs.prev_w = q.w;
+            }
+        }
+        if (HITS) {
+            if (whole) {
+                class_whole(q, vc, csum, c);
+                if (c.f && r.degen) {  // negative threshold: samples above it may lie on the far side of the baseline
+                    c.n = 0u; c.sw = 0u;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int w = u16_at(q, j);
+                        const bool in = r.positive ? (w >= r.wlim + r.bias) : (w <= r.wlim + r.bias);
+                        c.n += in ? 1u : 0u;
+                        c.sw += in ? (unsigned)w : 0u;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int w = u16_at(q, j);
+                    const bool ab = (j >= lo) && (j < hi) && (r.positive ? (w >= wthr) : (w <= wthr));
+                    c.i |= ab ? 1u : 0u;
+                    if (j == 7) c.l = ab ? 1u : 0u;
+                }
+            }
+        }
+    };
+    // FULL-chunk aggregate in front of the next chunk
+    auto fa_next = [&](const ChunkSum& c, unsigned& key, unsigned& n, unsigned& sw) {
+        const unsigned k2 = min(key, c.cand), n2 = n + c.n, s2 = sw + c.sw;
+        key = c.f ? k2 : 0xffffffffu;
+        n = c.f ? n2 : 0u;
+        sw = c.f ? s2 : 0u;
+    };
+
     if (nseg > 0) issue(0);
     for (int s = 0; s < nseg; ++s) {
         const int b = s % kNBuf;
@@ -377,161 +513,91 @@ __device__ __forceinline__ void lpr_stream(const FHArgs& a, const uint16_t* pool
         mbar_wait(&ring.bars[b], (*ring.phase_bits >> b) & 1u);
         *ring.phase_bits ^= 1u << b;
         const uint8_t* buf = ring.slot + b * ring.buf_stride;
-        const int cend = min(sc, nsteps - s * sc);
-        for (int cb = 0; cb < cend; ++cb) {
-            const int vc = s * sc + cb;
-            // classification of chunk vc (a chunk behind the record end is QUIET)
-            unsigned c_full = 0u, c_int = 0u, c_last = 0u;
-            unsigned cand = 0xffffffffu, csum = 0u;
-            uint4 raw = make_uint4(0u, 0u, 0u, 0u);
-            if (vc < nch) {
-                raw = *reinterpret_cast<const uint4*>(buf + (kHist + cb) * 16);
-                uint4 q = raw;
-                if (SGN) { q.x ^= 0x80008000u; q.y ^= 0x80008000u; q.z ^= 0x80008000u; q.w ^= 0x80008000u; }  // int16 -> offset binary
-                const int v0 = vc * 8;
-                const int lo = max(mis - v0, 0), hi = min(vtotal - v0, 8);
-                const int i0 = v0 - mis;
-                const bool whole = lo == 0 && hi == 8;
-                if (whole && (HITS || !known)) {
-                    csum = __dp2a_lo(q.x, 0x0101u, 0u);
-                    csum = __dp2a_lo(q.y, 0x0101u, csum);
-                    csum = __dp2a_lo(q.z, 0x0101u, csum);
-                    csum = __dp2a_lo(q.w, 0x0101u, csum);
+        const int tend = min(bps, nblk - s * bps);
+        for (int t = 0; t < tend; ++t) {
+            const int vc0 = s * sc + 4 * t;        // first chunk of the block
+            const int pos0 = kHist + 4 * t;        // its slot position
+            ChunkSum c0s, c1s, c2s, c3s;
+            bool fast = vc0 >= wholeA && vc0 + 4 <= wholeB && !(HITS && r.degen);
+            if (FEAT) fast = fast && vc0 >= plainA && vc0 + 4 <= plainB && (vc0 + 4 <= plainHa || vc0 >= plainHb);
+            if (fast) {
+                uint4 q0 = *reinterpret_cast<const uint4*>(buf + pos0 * 16);
+                uint4 q1 = *reinterpret_cast<const uint4*>(buf + pos0 * 16 + 16);
+                uint4 q2 = *reinterpret_cast<const uint4*>(buf + pos0 * 16 + 32);
+                uint4 q3 = *reinterpret_cast<const uint4*>(buf + pos0 * 16 + 48);
+                if (SGN) {
+                    q0.x ^= 0x80008000u; q0.y ^= 0x80008000u; q0.z ^= 0x80008000u; q0.w ^= 0x80008000u;
+                    q1.x ^= 0x80008000u; q1.y ^= 0x80008000u; q1.z ^= 0x80008000u; q1.w ^= 0x80008000u;
+                    q2.x ^= 0x80008000u; q2.y ^= 0x80008000u; q2.z ^= 0x80008000u; q2.w ^= 0x80008000u;
+                    q3.x ^= 0x80008000u; q3.y ^= 0x80008000u; q3.z ^= 0x80008000u; q3.w ^= 0x80008000u;
                 }
-                if (FEAT) {
-                    if (vc >= plainA && vc < plainB && (vc < plainHa || vc >= plainHb)) {
-                        // plain interior chunk: 8 valid samples inside the area range, outside the height range
-                        unsigned f0 = __funnelshift_r(fs.prev_w, q.x, 16), f1 = __funnelshift_r(q.x, q.y, 16);
-                        unsigned f2 = __funnelshift_r(q.y, q.z, 16), f3 = __funnelshift_r(q.z, q.w, 16);
-                        unsigned d0 = __vmaxu2(q.x, f0) - __vminu2(q.x, f0), d1 = __vmaxu2(q.y, f1) - __vminu2(q.y, f1);
-                        unsigned d2 = __vmaxu2(q.z, f2) - __vminu2(q.z, f2), d3 = __vmaxu2(q.w, f3) - __vminu2(q.w, f3);
-                        fs.pdiff = __vmaxu2(fs.pdiff, __vmaxu2(__vmaxu2(d0, d1), __vmaxu2(d2, d3)));
-                        fs.isum32 += csum;
-                    } else if (whole) {
-                        const unsigned pw = (i0 > 0) ? fs.prev_w : (q.x << 16);
-                        unsigned f0 = __funnelshift_r(pw, q.x, 16), f1 = __funnelshift_r(q.x, q.y, 16);
-                        unsigned f2 = __funnelshift_r(q.y, q.z, 16), f3 = __funnelshift_r(q.z, q.w, 16);
-                        unsigned d0 = __vmaxu2(q.x, f0) - __vminu2(q.x, f0), d1 = __vmaxu2(q.y, f1) - __vminu2(q.y, f1);
-                        unsigned d2 = __vmaxu2(q.z, f2) - __vminu2(q.z, f2), d3 = __vmaxu2(q.w, f3) - __vminu2(q.w, f3);
-                        fs.pdiff = __vmaxu2(fs.pdiff, __vmaxu2(__vmaxu2(d0, d1), __vmaxu2(d2, d3)));
-                        const int jlo = max(0, p0 - i0), jhi = min(8, p1 - i0);
-                        if (jhi > jlo) {
-                            if (jlo == 0 && jhi == 8) {
-                                fs.pmin = __vminu2(fs.pmin, __vminu2(__vminu2(q.x, q.y), __vminu2(q.z, q.w)));
-                                fs.pmax = __vmaxu2(fs.pmax, __vmaxu2(__vmaxu2(q.x, q.y), __vmaxu2(q.z, q.w)));
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    int w = u16_at(q, j);
-                                    if (j >= jlo && j < jhi) { fs.imin = min(fs.imin, w); fs.imax = max(fs.imax, w); }
-                                }
-                            }
-                        }
-                        const int klo = max(0, c0 - i0), khi = min(8, c1 - i0);
-                        if (khi > klo) {
-                            if (klo == 0 && khi == 8 && !known) {
-                                fs.isum32 += csum;
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    unsigned w = (unsigned)u16_at(q, j);
-                                    if (j >= klo && j < khi) {
-                                        if (!known) fs.isum32 += w;
-                                        else fs.dsum += (double)(r.positive ? __fsub_rn((float)w, b32) : __fsub_rn(b32, (float)w));
-                                    }
-                                }
-                            }
-                        }
-                    } else {
-                        // partial chunk (record start / end): per-sample
-                        const int prev_s = (int)(fs.prev_w >> 16);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int w = u16_at(q, j);
-                            if (j >= lo && j < hi) {
-                                const int i = i0 + j;
-                                if (i > 0) fs.idiff = max(fs.idiff, abs(w - ((j == 0) ? prev_s : u16_at(q, j - 1))));
-                                if (i >= p0 && i < p1) { fs.imin = min(fs.imin, w); fs.imax = max(fs.imax, w); }
-                                if (i >= c0 && i < c1) {
-                                    if (!known) fs.isum32 += (unsigned)w;
-                                    else fs.dsum += (double)(r.positive ? __fsub_rn((float)w, b32) : __fsub_rn(b32, (float)w));
-                                }
-                            }
-                        }
-                    }
-                    fs.prev_w = q.w;
-                }
+                auto csum4 = [](const uint4& q) {
+                    unsigned cs = __dp2a_lo(q.x, 0x0101u, 0u);
+                    cs = __dp2a_lo(q.y, 0x0101u, cs);
+                    cs = __dp2a_lo(q.z, 0x0101u, cs);
+                    return __dp2a_lo(q.w, 0x0101u, cs);
+                };
+                const unsigned s0 = csum4(q0), s1 = csum4(q1), s2 = csum4(q2), s3 = csum4(q3);
+                if (FEAT) { feat_plain(q0, s0); feat_plain(q1, s1); feat_plain(q2, s2); feat_plain(q3, s3); }
                 if (HITS) {
-                    if (whole) {
-                        const unsigned mn2 = __vminu2(__vimin3_u16x2(q.x, q.y, q.z), q.w);
-                        const unsigned mx2 = __vmaxu2(__vimax3_u16x2(q.x, q.y, q.z), q.w);
-                        const int wmin = (int)min(mn2 & 0xffffu, mn2 >> 16), wmax = (int)max(mx2 & 0xffffu, mx2 >> 16);
-                        const int wl = (int)(q.w >> 16);
-                        if (r.positive) {
-                            c_int = wmax >= wthr; c_full = wmin >= wthr; c_last = wl >= wthr;
-                            cand = ((unsigned)(65535 - wmax) << 16) | (unsigned)vc;
-                        } else {
-                            c_int = wmin <= wthr; c_full = wmax <= wthr; c_last = wl <= wthr;
-                            cand = ((unsigned)wmin << 16) | (unsigned)vc;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int w = u16_at(q, j);
-                            const bool ab = (j >= lo) && (j < hi) && (r.positive ? (w >= wthr) : (w <= wthr));
-                            c_int |= ab ? 1u : 0u;
-                            if (j == 7) c_last = ab ? 1u : 0u;
-                        }
-                    }
+                    class_whole(q0, vc0, s0, c0s);
+                    class_whole(q1, vc0 + 1, s1, c1s);
+                    class_whole(q2, vc0 + 2, s2, c2s);
+                    class_whole(q3, vc0 + 3, s3, c3s);
                 }
+            } else {
+                chunk_generic(buf, pos0, vc0, c0s);
+                chunk_generic(buf, pos0 + 1, vc0 + 1, c1s);
+                chunk_generic(buf, pos0 + 2, vc0 + 2, c2s);
+                chunk_generic(buf, pos0 + 3, vc0 + 3, c3s);
             }
             if (HITS) {
-                // chunk P = vc - 1 is an item if it is not FULL and holds, follows or precedes samples above threshold
-                const int P = vc - 1;
-                const unsigned f = hs.flags;
-                const bool want = (~f & ((f >> 1) | (f >> 3) | c_full) & 1u) != 0u;
-                const unsigned bal = __ballot_sync(kFull, want);
-                const bool flush = vc == nsteps - 1;
-                if (bal || flush) {
-                    const int np = __popc(bal);  // nothing is wanted at the flush step
-                    if (qn + np > kQCap || (flush && qn > 0)) {
+                Fm |= (c0s.f << 2) | (c1s.f << 3) | (c2s.f << 4) | (c3s.f << 5);
+                Im |= (c0s.i << 2) | (c1s.i << 3) | (c2s.i << 4) | (c3s.i << 5);
+                Lm |= (c0s.l << 2) | (c1s.l << 3) | (c2s.l << 4) | (c3s.l << 5);
+                // aggregates in front of chunks 1, 2 (items) and 3, 4 (carried to the next block)
+                unsigned a1_key = a0_key, a1_n = a0_n, a1_sw = a0_sw;
+                fa_next(c0s, a1_key, a1_n, a1_sw);
+                unsigned a2_key = a1_key, a2_n = a1_n, a2_sw = a1_sw;
+                fa_next(c1s, a2_key, a2_n, a2_sw);
+                unsigned a3_key = a2_key, a3_n = a2_n, a3_sw = a2_sw;
+                fa_next(c2s, a3_key, a3_n, a3_sw);
+                unsigned a4_key = a3_key, a4_n = a3_n, a4_sw = a3_sw;
+                fa_next(c3s, a4_key, a4_n, a4_sw);
+                // chunks 4b-1 .. 4b+2 (bits 1..4): an item is a non-FULL chunk that holds, follows or precedes samples above threshold
+                unsigned pend = ~Fm & (Im | (Lm << 1) | (Fm >> 1)) & 0x1eu;
+                const bool last_step = (s == nseg - 1) && (t == tend - 1);
+                for (;;) {
+                    const bool want = pend != 0u;
+                    const unsigned bal = __ballot_sync(kFull, want);
+                    const int np = __popc(bal);
+                    if (qn + np > kQCap || (bal == 0u && last_step && qn > 0)) {
                         lpr_round(ws, qn, r, a, sink);
                         qn = 0;
                     }
+                    if (bal == 0u) break;
                     if (want) {
+                        const int j = __ffs(pend) - 1;  // bit j <-> chunk vc0 + j - 2
+                        pend &= pend - 1u;
                         const int slot = qn + __popc(bal & ((1u << lane) - 1u));
-                        const uint8_t* src = buf + cb * 16;  // chunks P-1, P, P+1 (positions outside the record are never used)
+                        const uint8_t* src = buf + (pos0 + j - 3) * 16;  // chunks P-1, P, P+1 (positions outside the record are never used)
                         ws.q_ch[0][slot] = *reinterpret_cast<const uint4*>(src);
                         ws.q_ch[1][slot] = *reinterpret_cast<const uint4*>(src + 16);
                         ws.q_ch[2][slot] = *reinterpret_cast<const uint4*>(src + 32);
-                        ws.q_best[slot] = ws.best[lane];
-                        ws.q_hdr[slot] = make_uint4((unsigned)lane | ((unsigned)(P + 1) << 5) | ((f & 8u) << 21) | (c_full << 25), hs.fa_key, hs.fa_n, hs.fa_sw);
+                        const unsigned sk = j == 1 ? am_key : (j == 2 ? a0_key : (j == 3 ? a1_key : a2_key));
+                        const unsigned sn = j == 1 ? am_n : (j == 2 ? a0_n : (j == 3 ? a1_n : a2_n));
+                        const unsigned ss = j == 1 ? am_sw : (j == 2 ? a0_sw : (j == 3 ? a1_sw : a2_sw));
+                        const unsigned in_open = (Lm >> (j - 1)) & 1u, next_full = (Fm >> (j + 1)) & 1u;
+                        ws.q_hdr[slot] = make_uint4((unsigned)lane | ((unsigned)(vc0 + j - 1) << 5) | (in_open << 24) | (next_full << 25), sk, sn, ss);
                     }
                     qn += np;
                 }
-                // chunk vc enters the pipeline
-                if (f & 16u) { hs.fa_key = 0xffffffffu; hs.fa_n = 0u; hs.fa_sw = 0u; }
-                if (c_full) {
-                    if (cand < hs.fa_key) {
-                        hs.fa_key = cand;
-                        ws.best[lane] = raw;
-                    }
-                    if (!r.degen) {
-                        hs.fa_n += 8u;
-                        hs.fa_sw += csum;
-                    } else {  // negative threshold: samples above it may lie on the far side of the baseline
-                        uint4 q = raw;
-                        if (SGN) { q.x ^= 0x80008000u; q.y ^= 0x80008000u; q.z ^= 0x80008000u; q.w ^= 0x80008000u; }
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int w = u16_at(q, j);
-                            const bool in = r.positive ? (w >= r.wlim + r.bias) : (w <= r.wlim + r.bias);
-                            hs.fa_n += in ? 1u : 0u;
-                            hs.fa_sw += in ? (unsigned)w : 0u;
-                        }
-                    }
-                }
-                hs.flags = c_full | (c_int << 1) | (c_last << 2) | ((f & 4u) << 1) | (c_full ? 0u : 16u);
+                // carry to the next block
+                Fm = (Fm >> 4) & 0x2u;
+                Im = (Im >> 4) & 0x2u;
+                Lm = (Lm >> 4) & 0x3u;
+                am_key = a3_key; am_n = a3_n; am_sw = a3_sw;
+                a0_key = a4_key; a0_n = a4_n; a0_sw = a4_sw;
             }
         }
         __syncwarp();  // every lane is done with buffer b before it is refilled
@@ -776,8 +842,8 @@ int launch_lpr(FHArgs a, int flags, cudaStream_t st) {
     if (a.lmax >= 65536 - 16) return 1;  // positions are packed in 16 bits
     if (a.p.left_extension > kMaxExt || a.p.right_extension > kMaxExt) return 1;
     // segment length in chunks: kHist history chunks + sc new chunks per slot
-    int sc = 6;
-    if (const char* e = getenv("WFB_LPR_SC")) sc = std::max(4, std::min(30, atoi(e)));
+    int sc = 8;  // a multiple of the 4-chunk scan block
+    if (const char* e = getenv("WFB_LPR_SC")) sc = std::max(4, std::min(28, atoi(e) & ~3));
     int ent_cap = kLprEnt;  // WFB_LPR_POOL shrinks the per-warp hit pool (exercises the overflow path in tests)
     if (const char* e = getenv("WFB_LPR_POOL")) ent_cap = std::max(0, std::min(kLprEnt, atoi(e)));
     int slot_chunks = sc + kHist;

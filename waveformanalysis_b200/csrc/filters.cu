@@ -11,6 +11,8 @@
 //     zi*y_last, extension dropped; float64 with separate multiply/add (no FMA) = bit-exact.
 #include <algorithm>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace wfb {
@@ -72,7 +74,7 @@ __global__ void __launch_bounds__(256) sg_filter_kernel(const T* __restrict__ po
 // ---- Butterworth sosfiltfilt: one thread per record, time-serial recursion --------------------
 // scratch: float64 forward-pass output, time-major and interleaved over the threads of the grid
 // (scratch[t * n_threads + tid]) so that the 32 lanes of a warp store consecutive doubles.
-template <typename T>
+template <typename T, int MAXS>
 __global__ void __launch_bounds__(128) bw_filter_kernel(const T* __restrict__ pool, long long pool_len,
                                                        const wfb_rec_meta* __restrict__ meta, long long n,
                                                        const int* __restrict__ cfg_index,
@@ -83,7 +85,7 @@ __global__ void __launch_bounds__(128) bw_filter_kernel(const T* __restrict__ po
     const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     for (long long rec = tid; rec < n; rec += n_threads) {
         const wfb_filter_cfg& cfg = cfgs[cfg_index[rec]];
-        if (cfg.type != WFB_FILTER_BW) continue;
+        if (cfg.type != WFB_FILTER_BW || cfg.n_sections > MAXS) continue;
         const long long off = meta[rec].wave_offset - pool_base;
         const int L = meta[rec].event_length;
         if (L <= 0 || off < 0 || off + L > pool_len) continue;
@@ -107,40 +109,46 @@ __global__ void __launch_bounds__(128) bw_filter_kernel(const T* __restrict__ po
             if (t < edge + L) return sample_f64(x, t - edge);
             return __dsub_rn(__dmul_rn(2.0, x_last), sample_f64(x, L - 2 - (t - edge - L)));
         };
-        double z0[WFB_MAX_SOS_SECTIONS], z1[WFB_MAX_SOS_SECTIONS];
+        // coefficients and delay lines live in registers (sections unrolled to the compile-time maximum)
+        double cb0[MAXS], cb1[MAXS], cb2[MAXS], ca1[MAXS], ca2[MAXS];
+        double z0[MAXS], z1[MAXS];
+#pragma unroll
+        for (int s = 0; s < MAXS; ++s) {
+            const bool on = s < ns;
+            cb0[s] = on ? cfg.sos[s][0] : 1.0; cb1[s] = on ? cfg.sos[s][1] : 0.0; cb2[s] = on ? cfg.sos[s][2] : 0.0;
+            ca1[s] = on ? cfg.sos[s][4] : 0.0; ca2[s] = on ? cfg.sos[s][5] : 0.0;
+        }
+        auto cascade = [&](double v) -> double {
+#pragma unroll
+            for (int s = 0; s < MAXS; ++s) {
+                if (s < ns) {
+                    const double o = __dadd_rn(__dmul_rn(cb0[s], v), z0[s]);
+                    z0[s] = __dadd_rn(__dsub_rn(__dmul_rn(cb1[s], v), __dmul_rn(ca1[s], o)), z1[s]);
+                    z1[s] = __dsub_rn(__dmul_rn(cb2[s], v), __dmul_rn(ca2[s], o));
+                    v = o;
+                }
+            }
+            return v;
+        };
         const double x0 = ext(0);
-        for (int s = 0; s < ns; ++s) {
-            z0[s] = __dmul_rn(cfg.zi[s][0], x0);
-            z1[s] = __dmul_rn(cfg.zi[s][1], x0);
+#pragma unroll
+        for (int s = 0; s < MAXS; ++s) {
+            z0[s] = s < ns ? __dmul_rn(cfg.zi[s][0], x0) : 0.0;
+            z1[s] = s < ns ? __dmul_rn(cfg.zi[s][1], x0) : 0.0;
         }
         double v = 0.0;
         for (int t = 0; t < n_ext; ++t) {
-            v = ext(t);
-            for (int s = 0; s < ns; ++s) {
-                const double b0 = cfg.sos[s][0], b1 = cfg.sos[s][1], b2 = cfg.sos[s][2];
-                const double a1 = cfg.sos[s][4], a2 = cfg.sos[s][5];
-                const double o = __dadd_rn(__dmul_rn(b0, v), z0[s]);
-                z0[s] = __dadd_rn(__dsub_rn(__dmul_rn(b1, v), __dmul_rn(a1, o)), z1[s]);
-                z1[s] = __dsub_rn(__dmul_rn(b2, v), __dmul_rn(a2, o));
-                v = o;
-            }
+            v = cascade(ext(t));
             scratch[(size_t)t * n_threads + tid] = v;
         }
         const double y0 = v;  // last forward output
-        for (int s = 0; s < ns; ++s) {
-            z0[s] = __dmul_rn(cfg.zi[s][0], y0);
-            z1[s] = __dmul_rn(cfg.zi[s][1], y0);
+#pragma unroll
+        for (int s = 0; s < MAXS; ++s) {
+            z0[s] = s < ns ? __dmul_rn(cfg.zi[s][0], y0) : 0.0;
+            z1[s] = s < ns ? __dmul_rn(cfg.zi[s][1], y0) : 0.0;
         }
         for (int t = n_ext - 1; t >= 0; --t) {
-            v = scratch[(size_t)t * n_threads + tid];
-            for (int s = 0; s < ns; ++s) {
-                const double b0 = cfg.sos[s][0], b1 = cfg.sos[s][1], b2 = cfg.sos[s][2];
-                const double a1 = cfg.sos[s][4], a2 = cfg.sos[s][5];
-                const double o = __dadd_rn(__dmul_rn(b0, v), z0[s]);
-                z0[s] = __dadd_rn(__dsub_rn(__dmul_rn(b1, v), __dmul_rn(a1, o)), z1[s]);
-                z1[s] = __dsub_rn(__dmul_rn(b2, v), __dmul_rn(a2, o));
-                v = o;
-            }
+            v = cascade(scratch[(size_t)t * n_threads + tid]);
             if (t >= edge && t < edge + L) y[t - edge] = (float)v;
         }
     }
@@ -172,22 +180,38 @@ extern "C" int wfb_filter_pool(const void* pool_dev, int32_t pool_is_f32, int64_
         bw_threads = std::min<long long>(bw_threads, ((n + 127) / 128) * 128);
         bw_threads = (bw_threads / 128) * 128;
     }
+    // the Butterworth kernel keeps the section coefficients in registers: pick the smallest compiled size
+    int max_sections = 0;
+    if (bw_threads > 0) {
+        std::vector<wfb_filter_cfg> host_cfg((size_t)n_cfg);
+        WFB_CUDA(cudaMemcpyAsync(host_cfg.data(), cfgs_dev, sizeof(wfb_filter_cfg) * (size_t)n_cfg, cudaMemcpyDeviceToHost, st));
+        WFB_CUDA(cudaStreamSynchronize(st));
+        for (const auto& c : host_cfg)
+            if (c.type == WFB_FILTER_BW) max_sections = std::max(max_sections, (int)c.n_sections);
+        WFB_REQUIRE(max_sections <= WFB_MAX_SOS_SECTIONS, "wfb_filter_pool: too many second-order sections");
+    }
+    auto launch_bw = [&](auto tag) {
+        typedef decltype(tag) T;
+        const T* p = static_cast<const T*>(pool_dev);
+        double* scr = static_cast<double*>(workspace_dev);
+        const unsigned grid = (unsigned)(bw_threads / 128);
+        if (max_sections <= 4)
+            bw_filter_kernel<T, 4><<<grid, 128, 0, st>>>(p, pool_len, meta_dev, n, cfg_index_dev, cfgs_dev, out_dev, pool_base, scr, (int)scratch_len);
+        else if (max_sections <= 8)
+            bw_filter_kernel<T, 8><<<grid, 128, 0, st>>>(p, pool_len, meta_dev, n, cfg_index_dev, cfgs_dev, out_dev, pool_base, scr, (int)scratch_len);
+        else
+            bw_filter_kernel<T, WFB_MAX_SOS_SECTIONS><<<grid, 128, 0, st>>>(p, pool_len, meta_dev, n, cfg_index_dev, cfgs_dev, out_dev, pool_base, scr, (int)scratch_len);
+    };
     if (pool_is_f32) {
         if (sg_tables_dev && sg_table_offset_dev)
             sg_filter_kernel<float><<<sg_blocks, 256, 0, st>>>(static_cast<const float*>(pool_dev), pool_len, meta_dev, n, sg_tables_dev,
                                                              sg_table_offset_dev, cfg_index_dev, cfgs_dev, out_dev, pool_base);
-        if (bw_threads > 0)
-            bw_filter_kernel<float><<<(unsigned)(bw_threads / 128), 128, 0, st>>>(static_cast<const float*>(pool_dev), pool_len, meta_dev, n,
-                                                                                cfg_index_dev, cfgs_dev, out_dev, pool_base,
-                                                                                static_cast<double*>(workspace_dev), (int)scratch_len);
+        if (bw_threads > 0 && max_sections > 0) launch_bw(float());
     } else {
         if (sg_tables_dev && sg_table_offset_dev)
             sg_filter_kernel<uint16_t><<<sg_blocks, 256, 0, st>>>(static_cast<const uint16_t*>(pool_dev), pool_len, meta_dev, n, sg_tables_dev,
                                                                 sg_table_offset_dev, cfg_index_dev, cfgs_dev, out_dev, pool_base);
-        if (bw_threads > 0)
-            bw_filter_kernel<uint16_t><<<(unsigned)(bw_threads / 128), 128, 0, st>>>(static_cast<const uint16_t*>(pool_dev), pool_len, meta_dev,
-                                                                                   n, cfg_index_dev, cfgs_dev, out_dev, pool_base,
-                                                                                   static_cast<double*>(workspace_dev), (int)scratch_len);
+        if (bw_threads > 0 && max_sections > 0) launch_bw(uint16_t());
     }
     WFB_CUDA(cudaGetLastError());
     return WFB_OK;

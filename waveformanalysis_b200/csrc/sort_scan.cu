@@ -33,27 +33,66 @@ __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const unsigned
     block_hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
 }
 
-// exclusive scan of `total` unsigned counters in place, one block
-__global__ void __launch_bounds__(1024) radix_scan_kernel(unsigned* __restrict__ v, long long total) {
-    __shared__ unsigned long long sums[1024];
-    const long long chunk = (total + 1023) / 1024;
-    const long long lo = min(total, chunk * (long long)threadIdx.x), hi = min(total, lo + chunk);
-    unsigned long long s = 0;
-    for (long long i = lo; i < hi; ++i) s += v[i];
-    sums[threadIdx.x] = s;
-    __syncthreads();
-    // Hillis-Steele inclusive scan over 1024 partial sums
-    for (int d = 1; d < 1024; d <<= 1) {
-        unsigned long long t = threadIdx.x >= d ? sums[threadIdx.x - d] : 0;
-        __syncthreads();
-        sums[threadIdx.x] += t;
-        __syncthreads();
+// exclusive scan of `total` unsigned counters in place: per-tile sums, one block over the (<= 1024)
+// tile sums, then each tile scans itself from its offset; all loads and stores are coalesced
+__device__ __forceinline__ unsigned block_exclusive_scan_1024(unsigned v, unsigned* warp_sums /*[32]*/, unsigned& block_total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned t = __shfl_up_sync(kFull, incl, d);
+        if (lane >= d) incl += t;
     }
-    unsigned long long run = threadIdx.x ? sums[threadIdx.x - 1] : 0;
-    for (long long i = lo; i < hi; ++i) {
-        unsigned c = v[i];
-        v[i] = (unsigned)run;
-        run += c;
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned w = warp_sums[lane], wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned t = __shfl_up_sync(kFull, wi, d);
+            if (lane >= d) wi += t;
+        }
+        warp_sums[lane] = wi - w;  // exclusive prefix of the warp
+        if (lane == 31) warp_sums[32] = wi;
+    }
+    __syncthreads();
+    const unsigned excl = warp_sums[warp] + incl - v;
+    block_total = warp_sums[32];
+    __syncthreads();
+    return excl;
+}
+
+__global__ void __launch_bounds__(1024) radix_tile_sums_kernel(const unsigned* __restrict__ v, long long total, long long tile,
+                                                              unsigned* __restrict__ sums) {
+    __shared__ unsigned ws[33];
+    const long long lo = (long long)blockIdx.x * tile, hi = min(total, lo + tile);
+    unsigned s = 0;
+    for (long long i = lo + threadIdx.x; i < hi; i += 1024) s += v[i];
+    unsigned tot;
+    block_exclusive_scan_1024(s, ws, tot);
+    if (threadIdx.x == 0) sums[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(1024) radix_scan_sums_kernel(unsigned* __restrict__ sums, int ntiles) {
+    __shared__ unsigned ws[33];
+    unsigned tot;
+    const unsigned v = (int)threadIdx.x < ntiles ? sums[threadIdx.x] : 0u;
+    const unsigned e = block_exclusive_scan_1024(v, ws, tot);
+    if ((int)threadIdx.x < ntiles) sums[threadIdx.x] = e;
+}
+
+__global__ void __launch_bounds__(1024) radix_scan_tiles_kernel(unsigned* __restrict__ v, long long total, long long tile,
+                                                               const unsigned* __restrict__ sums) {
+    __shared__ unsigned ws[33];
+    const long long lo = (long long)blockIdx.x * tile, hi = min(total, lo + tile);
+    unsigned run = sums[blockIdx.x];
+    for (long long base = lo; base < hi; base += 1024) {
+        const long long i = base + threadIdx.x;
+        const unsigned c = i < hi ? v[i] : 0u;
+        unsigned tot;
+        const unsigned e = block_exclusive_scan_1024(c, ws, tot);
+        if (i < hi) v[i] = run + e;
+        run += tot;
     }
 }
 
@@ -112,7 +151,7 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 size_t radix_sort_workspace_bytes(long long n) {
     long long nblocks = (std::max<long long>(n, 1) + kSortTile - 1) / kSortTile;
-    return align256((size_t)std::max<long long>(n, 1) * 8) * 2 + align256((size_t)nblocks * 256 * 4) + 256;
+    return align256((size_t)std::max<long long>(n, 1) * 8) * 2 + align256((size_t)nblocks * 256 * 4 + 1024 * 4) + 256;
 }
 
 int radix_sort_pairs(const unsigned long long* keys_in, const long long* vals_in, unsigned long long* keys_out,
@@ -126,13 +165,20 @@ int radix_sort_pairs(const unsigned long long* keys_in, const long long* vals_in
     unsigned long long* tmp_k = reinterpret_cast<unsigned long long*>(ws);
     long long* tmp_v = reinterpret_cast<long long*>(ws + align256((size_t)n * 8));
     unsigned* hist = reinterpret_cast<unsigned*>(ws + 2 * align256((size_t)n * 8));
+    // the counter scan runs over <= 1024 tiles
+    const long long total = (long long)nblocks * 256;
+    const long long tile = std::max<long long>(4096, (total + 1023) / 1024);
+    const int ntiles = (int)((total + tile - 1) / tile);
+    unsigned* tile_sums = hist + total;
     const unsigned long long* src_k = keys_in;
     const long long* src_v = vals_in;
     for (int pass = 0; pass < 8; ++pass) {
         unsigned long long* dst_k = (pass & 1) ? keys_out : tmp_k;  // the 8th pass lands in keys_out
         long long* dst_v = (pass & 1) ? vals_out : tmp_v;
         radix_hist_kernel<<<nblocks, kSortThreads, 0, st>>>(src_k, n, pass * 8, (int)kind, hist, nblocks);
-        radix_scan_kernel<<<1, 1024, 0, st>>>(hist, (long long)nblocks * 256);
+        radix_tile_sums_kernel<<<ntiles, 1024, 0, st>>>(hist, total, tile, tile_sums);
+        radix_scan_sums_kernel<<<1, 1024, 0, st>>>(tile_sums, ntiles);
+        radix_scan_tiles_kernel<<<ntiles, 1024, 0, st>>>(hist, total, tile, tile_sums);
         radix_scatter_kernel<<<nblocks, kSortThreads, 0, st>>>(src_k, src_v, dst_k, dst_v, n, pass * 8, (int)kind, hist, nblocks);
         src_k = dst_k;
         src_v = dst_v;

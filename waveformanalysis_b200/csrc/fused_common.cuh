@@ -165,7 +165,7 @@ __device__ __forceinline__ long long tile_lookback(const FHArgs& a, int tile, lo
         int idx = look - lane;
         unsigned long long v;
         if (idx >= 0) {
-            do { v = ld_state(a.tile_state + idx); } while ((v & kStMask) == 0);
+            while (((v = ld_state(a.tile_state + idx)) & kStMask) == 0) __nanosleep(64);  // do not steal issue slots from the streaming warps
         } else {
             v = (idx == -1) ? (kStPrefix | (unsigned long long)(a.hit_base ? *a.hit_base : 0)) : kStPrefix;
         }

@@ -69,7 +69,7 @@ struct FeatState {  // per-lane feature accumulators
 
 struct WarpHits {  // per-warp shared memory of the hit machinery
     uint4 q_ch[3][kQCap];  // item samples (raw): chunk P-1, P, P+1
-    uint4 q_hdr[kQCap];    // owner | (P + 1) << 5 | in_open << 24 | next_full << 25 ; aggregate key, samples, sum
+    uint4 q_hdr[kQCap];    // owner | (P + 1) << 5 ; aggregate key, samples, sum of the FULL chunks in front
     uint4 stage[32];       // this round's "open at chunk end" fragments: start ; key, count, key sum
     uint4 carry[32];       // the same, per owner, across rounds
     int stage_n[32];       // runs started by this round's items
@@ -164,8 +164,6 @@ __device__ __forceinline__ void lpr_round(WarpHits& ws, int qn, const LaneRec& r
     const uint4 hd = ws.q_hdr[act ? lane : 0];
     const int src = act ? (int)(hd.x & 31u) : lane;  // owner lane
     const int P = (int)((hd.x >> 5) & 0x3fffu) - 1;  // -1: the virtual chunk in front of a record that starts FULL
-    const bool in_open = act && ((hd.x >> 24) & 1u);
-    const bool next_full = act && ((hd.x >> 25) & 1u);
     // the owner's record constants
     const int o_kmax = __shfl_sync(kFull, r.kmax, src);
     const int o_mis = __shfl_sync(kFull, r.mis, src);
@@ -193,6 +191,12 @@ __device__ __forceinline__ void lpr_round(WarpHits& ws, int qn, const LaneRec& r
         cval[j] = (kv <= kin) ? kOne + (unsigned)kv : 0u;
         m8 |= ((act && i >= 0 && i < o_len && kv <= o_kmax) ? 1u : 0u) << j;
     }
+    // does a run enter the chunk (last sample of chunk P-1 above threshold), is chunk P+1 FULL?
+    const uint4 c0q = ws.q_ch[0][lane], c2q = ws.q_ch[2][lane];
+    const bool in_open = act && i0 >= 1 && i0 - 1 < o_len && (int)((c0q.w >> 16) ^ cx) <= o_kmax;
+    const unsigned cx32 = cx | (cx << 16);
+    const unsigned nmx = __vmaxu2(__vimax3_u16x2(c2q.x ^ cx32, c2q.y ^ cx32, c2q.z ^ cx32), c2q.w ^ cx32);
+    const bool next_full = act && i0 + 8 >= 0 && i0 + 16 <= o_len && (int)max(nmx & 0xffffu, nmx >> 16) <= o_kmax;
     const bool nfs = next_full && !(m8 & 0x80u);  // a run starts with the FULL chunk that follows
     const bool has_trail = (m8 & 0x80u) || nfs;
     const int nstarts = __popc(m8 & ~((m8 << 1) | (in_open ? 1u : 0u))) + (nfs ? 1 : 0);
@@ -210,17 +214,24 @@ __device__ __forceinline__ void lpr_round(WarpHits& ws, int qn, const LaneRec& r
             const bool in = (i0 + j >= a0) && (i0 + j < a1);
             if (in) { key = min(key, ckey[j]); acc += cval[j]; }
         }
+        // the neighbours' samples: warp-uniform trip counts (the extensions), predicated bodies
         const unsigned short* lo_row = reinterpret_cast<const unsigned short*>(&ws.q_ch[0][lane]);
-        for (int i = a0; i < min(a1, i0); ++i) {  // left neighbour (never padding: i < i0 <= len)
-            const int kv = (int)((unsigned)lo_row[i - i0 + 8] ^ cx);
-            key = min(key, ((unsigned)kv << 16) + (unsigned)i);
-            acc += (kv <= kin) ? kOne + (unsigned)kv : 0u;
+        for (int e = 1; e <= left; ++e) {  // left neighbour (never padding: i < i0 <= len)
+            const int i = i0 - e;
+            const int kv = (int)((unsigned)lo_row[8 - e] ^ cx);
+            if (i >= a0 && i < a1) {
+                key = min(key, ((unsigned)kv << 16) + (unsigned)i);
+                acc += (kv <= kin) ? kOne + (unsigned)kv : 0u;
+            }
         }
         const unsigned short* hi_row = reinterpret_cast<const unsigned short*>(&ws.q_ch[2][lane]);
-        for (int i = max(a0, i0 + 8); i < a1; ++i) {  // right neighbour
-            const int kv = (i < o_len) ? (int)((unsigned)hi_row[i - i0 - 8] ^ cx) : padkv;
-            key = min(key, ((unsigned)kv << 16) + (unsigned)i);
-            acc += (kv <= kin) ? kOne + (unsigned)kv : 0u;
+        for (int e = 0; e < right; ++e) {  // right neighbour
+            const int i = i0 + 8 + e;
+            const int kv = (i < o_len) ? (int)((unsigned)hi_row[e] ^ cx) : padkv;
+            if (i >= a0 && i < a1) {
+                key = min(key, ((unsigned)kv << 16) + (unsigned)i);
+                acc += (kv <= kin) ? kOne + (unsigned)kv : 0u;
+            }
         }
     };
     // the fragment still open at the chunk end: from its start (minus the left extension) to the chunk end
@@ -587,8 +598,7 @@ __device__ __forceinline__ void lpr_stream(const FHArgs& a, const uint16_t* pool
                         const unsigned sk = j == 1 ? am_key : (j == 2 ? a0_key : (j == 3 ? a1_key : a2_key));
                         const unsigned sn = j == 1 ? am_n : (j == 2 ? a0_n : (j == 3 ? a1_n : a2_n));
                         const unsigned ss = j == 1 ? am_sw : (j == 2 ? a0_sw : (j == 3 ? a1_sw : a2_sw));
-                        const unsigned in_open = (Lm >> (j - 1)) & 1u, next_full = (Fm >> (j + 1)) & 1u;
-                        ws.q_hdr[slot] = make_uint4((unsigned)lane | ((unsigned)(vc0 + j - 1) << 5) | (in_open << 24) | (next_full << 25), sk, sn, ss);
+                        ws.q_hdr[slot] = make_uint4((unsigned)lane | ((unsigned)(vc0 + j - 1) << 5), sk, sn, ss);
                     }
                     qn += np;
                 }

@@ -154,8 +154,9 @@ int wfb_features_hits_check(void* workspace_dev, void* stream);
 
 /* Host-buffer front end of the same pass: the reference-facing call.  records_host is the
  * RECORDS_DTYPE array and pool_host the wave_pool exactly as Context hands them to a plugin;
- * outputs are host arrays.  Internally a chunked, double-buffered H2D -> kernels -> D2H
- * pipeline on private streams (synchronous for the caller).  wave_offsets must ascend with
+ * outputs are host arrays.  Internally a chunked, triple-buffered H2D -> kernels -> D2H
+ * pipeline on private streams (synchronous for the caller); hit rows are copied back two chunks
+ * behind the compute stream.  wave_offsets must ascend with
  * the record index (always true for pools built by the reference, records_builder.py:300,408).
  * On return *n_hits is the number of hits found; if it exceeds hit_cap only the first hit_cap
  * rows were stored (call again with a larger buffer). */
@@ -163,6 +164,11 @@ int wfb_process_host(const void* records_host, int64_t n, const void* pool_host,
                      const wfb_fh_params* params, const wfb_chan_rule* rules_host,
                      void* feat_out_host, void* hit_out_host, int64_t hit_cap,
                      int32_t* hit_counts_host, int64_t* n_hits, int64_t chunk_records);
+
+/* wfb_process_host keeps its streams, events and device staging buffers between calls (one set per
+ * device, calls on one device are serialised).  This frees the device buffers; the reference has
+ * no counterpart (its plugins hold no device state), call it when a Context is done with the GPU. */
+int wfb_release_cache(void);
 
 /* ---- wave_pool_filtered -------------------------------------------------------------------- */
 

@@ -218,3 +218,108 @@ def test_long_records_use_global_path(eng):
     out = eng.DeviceRun.from_host(rec, pool).run_to_host(threshold=15.0, height_range=(0, None))
     assert_rows_match(out["features"], O.basic_features(rec, pool, height_range=(0, None)), what="long bf", float_exact=FX_BF)
     assert_rows_match(out["hits"], O.threshold_hits(rec, pool, threshold=15.0), what="long hits", float_exact=FX_HIT)
+
+
+@pytest.mark.parametrize("knobs", [{"WFB_LPR_SC": "4"}, {"WFB_LPR_SC": "12"}, {"WFB_LPR_POOL": "24"}, {"WFB_LPR_POOL": "0", "WFB_LPR_SC": "4"},
+                                   {"WFB_LPR_NO_TMAP": "1"}])
+def test_lane_per_record_kernel_knobs(eng, golden, knobs, monkeypatch):
+    """The lane-per-record kernel with other segment lengths, a tiny / absent per-warp hit pool (every
+    record goes through the overflow re-stream with the direct row sink) and without the 2-D tensor
+    map (per-lane bulk copies) must give the same rows."""
+    from oracle import np_oracle as O
+    from waveformanalysis_b200.synth import make_raw_run, records_from_raw
+
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    rec, pool = golden["records"], golden["wave_pool"]
+    out = eng.DeviceRun.from_host(rec, pool).run_to_host(threshold=15.0)
+    assert_rows_match(out["features"], golden["bf_default"], what="bf", float_exact=FX_BF)
+    assert_rows_match(out["hits"], golden["hits_thr15"], what="hits", float_exact=FX_HIT)
+    rpos = rec.copy()
+    rpos["polarity"] = "positive"
+    out = eng.DeviceRun.from_host(rpos, pool).run_to_host(features=False, threshold=-20.0)
+    assert_rows_match(out["hits"], golden["hits_positive"], what="pos", float_exact=FX_HIT)
+    rr, rp = golden["rag_records"], golden["rag_pool"]
+    out = eng.DeviceRun.from_host(rr, rp).run_to_host(height_range=(5, -5), threshold=15.0, left_extension=3, right_extension=4)
+    assert_rows_match(out["features"], golden["rag_bf"], what="rag_bf", float_exact=FX_BF)
+    assert_rows_match(out["hits"], golden["rag_hits"], what="rag_hits", float_exact=("height", "width"))
+    # fixed-length run from the device generator (the tensor-map layout), maximum supported extensions
+    raw = make_raw_run(8, 700, 800, seed=77)
+    r2, p2 = records_from_raw(raw)
+    want = O.threshold_hits(r2, p2, threshold=6.0, left_extension=8, right_extension=8)
+    got = eng.DeviceRun.from_host(r2, p2).run_to_host(features=False, threshold=6.0, left_extension=8, right_extension=8)
+    assert_rows_match(got["hits"], want, what="ext8", float_exact=FX_HIT)
+
+
+def test_full_size_properties(eng):
+    """BASELINE configs[1] size (16 M records x 800 samples on one GPU): properties that do not need the
+    oracle at full size - hit rows ordered by (record, start), per-record counts sum to the total,
+    a slice re-processed on its own gives the same bytes, a second pass is idempotent - plus the
+    oracle on a slice copied back to the host."""
+    import torch
+
+    from oracle import np_oracle as O
+    from waveformanalysis_b200.dtypes import BASIC_FEATURES_DTYPE, THRESHOLD_HIT_DTYPE
+
+    free, _ = torch.cuda.mem_get_info()
+    n = 16_000_000 if free > 60e9 else 2_000_000
+    L = 800
+    run = eng.DeviceRun.synth(n, L, 16, seed=2025, with_rows=False)
+    res = run.features_hits(threshold=15.0, hit_cap=1024, want_counts=True)
+    total = int(res["total"].item())
+    assert 2 * n < total < 20 * n
+    counts = res["counts"]
+    assert int(counts.sum().item()) == total
+    out = {"features": torch.empty(n * 36, dtype=torch.uint8, device="cuda"),
+           "hits": torch.empty((total + 16) * 60, dtype=torch.uint8, device="cuda"),
+           "total": torch.zeros(1, dtype=torch.int64, device="cuda")}
+    run.features_hits(threshold=15.0, hit_cap=total + 16, out=out)
+    run.check()
+    assert int(out["total"].item()) == total
+    hits = out["hits"][: total * 60].view(total, 60)
+    rid = hits[:, 52:60].contiguous().view(torch.int64).view(-1)
+    es = hits[:, 16:20].contiguous().view(torch.int32).view(-1)
+    ee = hits[:, 20:24].contiguous().view(torch.int32).view(-1)
+    pos = hits[:, 0:8].contiguous().view(torch.int64).view(-1)
+    key = rid * 65536 + es.to(torch.int64)
+    assert bool((key[1:] >= key[:-1]).all()), "hit rows are not ordered by (record, start)"
+    assert bool(((pos >= es) & (pos < ee) & (es >= 0) & (ee <= L)).all())
+    assert torch.equal(torch.bincount(rid, minlength=n).to(counts.dtype), counts)
+    feats = out["features"].view(n, 36)
+    ev = feats[:, 28:36].contiguous().view(torch.int64).view(-1)
+    assert torch.equal(ev, torch.arange(n, device="cuda"))
+    # idempotence
+    first_hits = out["hits"][: total * 60].clone()
+    first_feat = out["features"].clone()
+    run.features_hits(threshold=15.0, hit_cap=total + 16, out=out)
+    assert torch.equal(out["hits"][: total * 60], first_hits) and torch.equal(out["features"], first_feat)
+    # a slice in the middle, processed on its own and checked with the oracle on the host
+    lo, m = n // 2 + 12345, 4096
+    sub = eng.DeviceRun(run.meta[lo * 48:(lo + m) * 48].clone(), run.pool, m, 0, L)
+    got = sub.run_to_host(threshold=15.0)
+    f_full = first_feat.view(n, 36)[lo:lo + m].cpu().numpy().view(BASIC_FEATURES_DTYPE).reshape(-1)
+    gf = got["features"].copy()
+    gf["event_index"] += lo  # row index is relative to the run that was processed
+    assert np.array_equal(gf.view(np.uint8), f_full.view(np.uint8))
+    h0 = int(counts[:lo].sum().item())
+    h1 = h0 + int(counts[lo:lo + m].sum().item())
+    h_full = first_hits.view(total, 60)[h0:h1].cpu().numpy().view(THRESHOLD_HIT_DTYPE).reshape(-1)
+    assert np.array_equal(got["hits"].view(np.uint8), h_full.view(np.uint8))
+    pool_h = run.pool[lo * L:(lo + m) * L].cpu().numpy().view(np.uint16)
+    from waveformanalysis_b200.dtypes import RECORDS_DTYPE
+
+    rec = np.zeros(m, RECORDS_DTYPE)
+    meta = run.meta[lo * 48:(lo + m) * 48].cpu().numpy()
+    rec["timestamp"] = meta.view(np.int64).reshape(m, 6)[:, 0]
+    rec["baseline"] = meta.view(np.float64).reshape(m, 6)[:, 1]
+    rec["wave_offset"] = np.arange(m) * L
+    rec["event_length"] = L
+    rec["dt"] = meta.view(np.int32).reshape(m, 12)[:, 7]
+    rec["board"] = meta.view(np.int16).reshape(m, 24)[:, 16]
+    rec["channel"] = meta.view(np.int16).reshape(m, 24)[:, 17]
+    rec["record_id"] = meta.view(np.int64).reshape(m, 6)[:, 5]
+    rec["polarity"] = "unknown"
+    want_f = O.basic_features(rec, pool_h)
+    want_f["event_index"] += lo
+    assert_rows_match(f_full, want_f, what="full-size slice features", float_exact=FX_BF)
+    assert_rows_match(h_full, O.threshold_hits(rec, pool_h, threshold=15.0), what="full-size slice hits", float_exact=FX_HIT)

@@ -2,6 +2,7 @@
 #include <stdarg.h>
 
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -124,19 +125,28 @@ struct DevBuf {
     size_t cap = 0;
     int ensure(size_t bytes) {
         if (bytes <= cap) return WFB_OK;
+        release();
+        // grow with some slack so that runs of slightly different size reuse the buffer
+        const size_t want = bytes + bytes / 8;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            e = cudaMalloc(&p, bytes);
+            if (e != cudaSuccess) {
+                p = nullptr;
+                set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+                return WFB_ERR_NOMEM;
+            }
+            cap = bytes;
+            return WFB_OK;
+        }
+        cap = want;
+        return WFB_OK;
+    }
+    void release() {
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
-        cudaError_t e = cudaMalloc(&p, bytes);
-        if (e != cudaSuccess) {
-            set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
-            return WFB_ERR_NOMEM;
-        }
-        cap = bytes;
-        return WFB_OK;
-    }
-    ~DevBuf() {
-        if (p) cudaFree(p);
     }
 };
 
@@ -144,6 +154,36 @@ struct Slot {
     DevBuf pool, rows, meta, feat, counts, ws;
     cudaEvent_t copied = nullptr, computed = nullptr, drained = nullptr;
 };
+
+constexpr int kSlots = 3;
+constexpr int kMaxDevices = 64;
+
+// Streams, events and device buffers of wfb_process_host, kept between calls (one set per device,
+// calls on the same device are serialised by the mutex).  wfb_release_cache() frees them; they
+// are deliberately not freed at process exit (the CUDA context may already be gone).
+struct HostPipe {
+    std::mutex mu;
+    bool ready = false;
+    cudaStream_t s_copy = nullptr, s_comp = nullptr, s_out = nullptr;
+    Slot slots[kSlots];
+    DevBuf d_hits, d_rules, d_tot;
+    long long* mailbox = nullptr;  // pinned: the running hit total after each chunk
+    void release_buffers() {
+        for (auto& s : slots) {
+            s.pool.release(); s.rows.release(); s.meta.release(); s.feat.release(); s.counts.release(); s.ws.release();
+        }
+        d_hits.release(); d_rules.release(); d_tot.release();
+    }
+};
+HostPipe* g_pipes[kMaxDevices];
+std::mutex g_pipes_mu;
+
+HostPipe* host_pipe(int device) {
+    std::lock_guard<std::mutex> lock(g_pipes_mu);
+    if (device < 0 || device >= kMaxDevices) return nullptr;
+    if (!g_pipes[device]) g_pipes[device] = new HostPipe();
+    return g_pipes[device];
+}
 
 inline long long rec_i64(const uint8_t* row, int off) {
     long long v;
@@ -184,26 +224,31 @@ extern "C" int wfb_process_host(const void* records_host, int64_t n, const void*
         for (int64_t i = 0; i < n; ++i) lmax = std::max(lmax, rec_i32(rows + i * kRecordsRowBytes, 90));
     }
 
-    cudaStream_t s_copy = nullptr, s_comp = nullptr, s_out = nullptr;
-    WFB_CUDA(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
-    WFB_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
-    WFB_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
-    constexpr int kSlots = 3;
-    Slot slots[kSlots];
-    DevBuf d_hits, d_rules, d_tot;
+    int device = 0;
+    WFB_CUDA(cudaGetDevice(&device));
+    HostPipe* hp = host_pipe(device);
+    WFB_REQUIRE(hp != nullptr, "wfb_process_host: device index %d out of range", device);
+    std::lock_guard<std::mutex> pipe_lock(hp->mu);
     int rc = WFB_OK;
-    auto cleanup = [&]() {
+    if (!hp->ready) {
+        WFB_CUDA(cudaStreamCreateWithFlags(&hp->s_copy, cudaStreamNonBlocking));
+        WFB_CUDA(cudaStreamCreateWithFlags(&hp->s_comp, cudaStreamNonBlocking));
+        WFB_CUDA(cudaStreamCreateWithFlags(&hp->s_out, cudaStreamNonBlocking));
+        for (auto& s : hp->slots) {
+            WFB_CUDA(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
+            WFB_CUDA(cudaEventCreateWithFlags(&s.computed, cudaEventDisableTiming));
+            WFB_CUDA(cudaEventCreateWithFlags(&s.drained, cudaEventDisableTiming));
+        }
+        WFB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&hp->mailbox), sizeof(long long) * kSlots, cudaHostAllocDefault));
+        hp->ready = true;
+    }
+    cudaStream_t s_copy = hp->s_copy, s_comp = hp->s_comp, s_out = hp->s_out;
+    Slot* slots = hp->slots;
+    DevBuf &d_hits = hp->d_hits, &d_rules = hp->d_rules, &d_tot = hp->d_tot;
+    auto cleanup = [&]() {  // leave the pipeline idle: nothing of this call is still in flight
         cudaStreamSynchronize(s_copy);
         cudaStreamSynchronize(s_comp);
         cudaStreamSynchronize(s_out);
-        for (auto& s : slots) {
-            if (s.copied) cudaEventDestroy(s.copied);
-            if (s.computed) cudaEventDestroy(s.computed);
-            if (s.drained) cudaEventDestroy(s.drained);
-        }
-        cudaStreamDestroy(s_copy);
-        cudaStreamDestroy(s_comp);
-        cudaStreamDestroy(s_out);
     };
 #define PH_CHECK(expr)                \
     do {                              \
@@ -223,11 +268,6 @@ extern "C" int wfb_process_host(const void* records_host, int64_t n, const void*
         }                                               \
     } while (0)
 
-    for (auto& s : slots) {
-        PH_CUDA(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
-        PH_CUDA(cudaEventCreateWithFlags(&s.computed, cudaEventDisableTiming));
-        PH_CUDA(cudaEventCreateWithFlags(&s.drained, cudaEventDisableTiming));
-    }
     if (do_hits) PH_CHECK(d_hits.ensure(std::max<size_t>((size_t)hit_cap * kHitRowBytes, 64)));
     PH_CHECK(d_tot.ensure(64));  // ping-pong running totals
     PH_CUDA(cudaMemsetAsync(d_tot.p, 0, 64, s_comp));
@@ -240,6 +280,26 @@ extern "C" int wfb_process_host(const void* records_host, int64_t n, const void*
         PH_CUDA(cudaMemcpyAsync(d_rules.p, rules_host, sizeof(wfb_chan_rule) * p.n_rules, cudaMemcpyHostToDevice, s_comp));
         p.rules_dev = static_cast<const wfb_chan_rule*>(d_rules.p);
     }
+
+    // hit rows leave the device two chunks behind the compute stream: the running total of chunk j is
+    // read from the pinned mailbox once its event has fired, then the new rows are copied on s_out
+    long long hits_copied = 0;
+    auto drain_hits = [&](int64_t j) -> int {
+        Slot& sj = slots[j % kSlots];
+        cudaError_t e = cudaEventSynchronize(sj.computed);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaEventSynchronize");
+        const long long upto = std::min<long long>(hp->mailbox[j % kSlots], hit_cap);
+        if (upto > hits_copied) {
+            e = cudaStreamWaitEvent(s_out, sj.computed, 0);
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(static_cast<uint8_t*>(hit_out_host) + (size_t)hits_copied * kHitRowBytes,
+                                    static_cast<uint8_t*>(d_hits.p) + (size_t)hits_copied * kHitRowBytes,
+                                    (size_t)(upto - hits_copied) * kHitRowBytes, cudaMemcpyDeviceToHost, s_out);
+            if (e != cudaSuccess) return cuda_fail(e, "hit rows D2H");
+            hits_copied = upto;
+        }
+        return WFB_OK;
+    };
 
     int64_t chunk_idx = 0;
     for (int64_t r0 = 0; r0 < n; r0 += chunk_records, ++chunk_idx) {
@@ -261,8 +321,13 @@ extern "C" int wfb_process_host(const void* records_host, int64_t n, const void*
             cleanup();
             return rc;
         }
+        if (do_hits && hit_out_host && chunk_idx >= 2) PH_CHECK(drain_hits(chunk_idx - 2));
         const long long lo_al = lo & ~7ll;  // keep 16-byte alignment of record starts relative to the pool
         const size_t pool_bytes = (size_t)(hi - lo_al) * esz;
+        // (re)allocation waits for the slot's previous work: only ever happens while the buffers grow
+        const bool grow = pool_bytes + 64 > s.pool.cap || (size_t)m * kRecordsRowBytes + 64 > s.rows.cap ||
+                          wfb_features_hits_workspace_bytes(m) > s.ws.cap;
+        if (grow) cleanup();
         PH_CHECK(s.pool.ensure(pool_bytes + 64));
         PH_CHECK(s.rows.ensure((size_t)m * kRecordsRowBytes + 64));
         PH_CHECK(s.meta.ensure((size_t)m * sizeof(wfb_rec_meta) + 64));
@@ -284,6 +349,7 @@ extern "C" int wfb_process_host(const void* records_host, int64_t n, const void*
         PH_CHECK(wfb_features_hits(s.pool.p, hi - lo_al, static_cast<const wfb_rec_meta*>(s.meta.p), m, &p, s.feat.p,
                                    d_hits.p, hit_cap, (do_hits && hit_counts_host) ? static_cast<int32_t*>(s.counts.p) : nullptr,
                                    tot + (chunk_idx & 1), tot + ((chunk_idx + 1) & 1), s.ws.p, s.ws.cap, s_comp));
+        PH_CUDA(cudaMemcpyAsync(&hp->mailbox[chunk_idx % kSlots], tot + ((chunk_idx + 1) & 1), 8, cudaMemcpyDeviceToHost, s_comp));
         PH_CUDA(cudaEventRecord(s.computed, s_comp));
         PH_CUDA(cudaStreamWaitEvent(s_out, s.computed, 0));
         if (do_feat)
@@ -294,21 +360,35 @@ extern "C" int wfb_process_host(const void* records_host, int64_t n, const void*
         PH_CUDA(cudaEventRecord(s.drained, s_out));
     }
     PH_CUDA(cudaStreamSynchronize(s_comp));
-    for (auto& s : slots) {
-        if (!s.ws.p) continue;
-        int err = wfb_features_hits_check(s.ws.p, s_comp);
+    for (int k = 0; k < kSlots && k < chunk_idx; ++k) {
+        int err = wfb_features_hits_check(slots[k].ws.p, s_comp);
         if (err != WFB_OK) { cleanup(); return err; }
     }
     if (do_hits) {
-        long long total = 0;
-        PH_CUDA(cudaMemcpy(&total, static_cast<int64_t*>(d_tot.p) + (chunk_idx & 1), 8, cudaMemcpyDeviceToHost));
-        *n_hits = total;
-        long long keep = std::min<long long>(total, hit_cap);
-        if (keep > 0) PH_CUDA(cudaMemcpyAsync(hit_out_host, d_hits.p, (size_t)keep * kHitRowBytes, cudaMemcpyDeviceToHost, s_out));
+        *n_hits = hp->mailbox[(chunk_idx - 1) % kSlots];
+        if (hit_out_host) {
+            if (chunk_idx >= 2) PH_CHECK(drain_hits(chunk_idx - 2));
+            PH_CHECK(drain_hits(chunk_idx - 1));
+        }
     }
     PH_CUDA(cudaStreamSynchronize(s_out));
     cleanup();
     return WFB_OK;
 #undef PH_CHECK
 #undef PH_CUDA
+}
+
+extern "C" int wfb_release_cache(void) {
+    std::lock_guard<std::mutex> lock(g_pipes_mu);
+    for (HostPipe* hp : g_pipes) {
+        if (!hp) continue;
+        std::lock_guard<std::mutex> pipe_lock(hp->mu);
+        if (hp->ready) {
+            cudaStreamSynchronize(hp->s_copy);
+            cudaStreamSynchronize(hp->s_comp);
+            cudaStreamSynchronize(hp->s_out);
+        }
+        hp->release_buffers();
+    }
+    return WFB_OK;
 }

@@ -68,7 +68,7 @@ struct FeatState {  // per-lane feature accumulators
 };
 
 struct WarpHits {  // per-warp shared memory of the hit machinery
-    uint4 q_ch[3][kQCap];  // item samples (raw): chunk P-1, P, P+1
+    uint4 q_nb[2][32];     // the round's scratch: chunks P-1 and P+1 of lane t's item
     uint4 q_hdr[kQCap];    // owner | (P + 1) << 5 ; aggregate key, samples, sum of the FULL chunks in front
     uint4 stage[32];       // this round's "open at chunk end" fragments: start ; key, count, key sum
     uint4 carry[32];       // the same, per owner, across rounds
@@ -179,8 +179,18 @@ __device__ __forceinline__ void lpr_round(WarpHits& ws, int qn, const LaneRec& r
     const int left = a.p.left_extension, right = a.p.right_extension;
     const int i0 = 8 * P - o_mis;
     constexpr unsigned kOne = 1u << 21;
+    // the item's chunk and its two neighbours come back from L2 (they were streamed a few microseconds
+    // ago); chunks outside the record are never dereferenced.  They are parked in shared memory for the
+    // dynamically indexed extension samples.
+    const int o_nch = (o_len > 0) ? ((o_mis + o_len + 7) >> 3) : 0;
+    const uint4* gsrc = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(a.pool) + (o_off - o_mis)) + (P - 1);
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    const uint4 c0q = (act && P - 1 >= 0 && P - 1 < o_nch) ? __ldg(gsrc) : zero4;
+    const uint4 c1 = (act && P >= 0 && P < o_nch) ? __ldg(gsrc + 1) : zero4;
+    const uint4 c2q = (act && P + 1 < o_nch) ? __ldg(gsrc + 2) : zero4;
+    ws.q_nb[0][lane] = c0q;
+    ws.q_nb[1][lane] = c2q;
     // keys of the item's own chunk, packed contributions, above-threshold mask
-    const uint4 c1 = ws.q_ch[1][lane];
     unsigned ckey[8], cval[8];
     unsigned m8 = 0;
 #pragma unroll
@@ -192,7 +202,6 @@ __device__ __forceinline__ void lpr_round(WarpHits& ws, int qn, const LaneRec& r
         m8 |= ((act && i >= 0 && i < o_len && kv <= o_kmax) ? 1u : 0u) << j;
     }
     // does a run enter the chunk (last sample of chunk P-1 above threshold), is chunk P+1 FULL?
-    const uint4 c0q = ws.q_ch[0][lane], c2q = ws.q_ch[2][lane];
     const bool in_open = act && i0 >= 1 && i0 - 1 < o_len && (int)((c0q.w >> 16) ^ cx) <= o_kmax;
     const unsigned cx32 = cx | (cx << 16);
     const unsigned nmx = __vmaxu2(__vimax3_u16x2(c2q.x ^ cx32, c2q.y ^ cx32, c2q.z ^ cx32), c2q.w ^ cx32);
@@ -215,7 +224,7 @@ __device__ __forceinline__ void lpr_round(WarpHits& ws, int qn, const LaneRec& r
             if (in) { key = min(key, ckey[j]); acc += cval[j]; }
         }
         // the neighbours' samples: warp-uniform trip counts (the extensions), predicated bodies
-        const unsigned short* lo_row = reinterpret_cast<const unsigned short*>(&ws.q_ch[0][lane]);
+        const unsigned short* lo_row = reinterpret_cast<const unsigned short*>(&ws.q_nb[0][lane]);
         for (int e = 1; e <= left; ++e) {  // left neighbour (never padding: i < i0 <= len)
             const int i = i0 - e;
             const int kv = (int)((unsigned)lo_row[8 - e] ^ cx);
@@ -224,7 +233,7 @@ __device__ __forceinline__ void lpr_round(WarpHits& ws, int qn, const LaneRec& r
                 acc += (kv <= kin) ? kOne + (unsigned)kv : 0u;
             }
         }
-        const unsigned short* hi_row = reinterpret_cast<const unsigned short*>(&ws.q_ch[2][lane]);
+        const unsigned short* hi_row = reinterpret_cast<const unsigned short*>(&ws.q_nb[1][lane]);
         for (int e = 0; e < right; ++e) {  // right neighbour
             const int i = i0 + 8 + e;
             const int kv = (i < o_len) ? (int)((unsigned)hi_row[e] ^ cx) : padkv;
@@ -591,10 +600,6 @@ __device__ __forceinline__ void lpr_stream(const FHArgs& a, const uint16_t* pool
                         const int j = __ffs(pend) - 1;  // bit j <-> chunk vc0 + j - 2
                         pend &= pend - 1u;
                         const int slot = qn + __popc(bal & ((1u << lane) - 1u));
-                        const uint8_t* src = buf + (pos0 + j - 3) * 16;  // chunks P-1, P, P+1 (positions outside the record are never used)
-                        ws.q_ch[0][slot] = *reinterpret_cast<const uint4*>(src);
-                        ws.q_ch[1][slot] = *reinterpret_cast<const uint4*>(src + 16);
-                        ws.q_ch[2][slot] = *reinterpret_cast<const uint4*>(src + 32);
                         const unsigned sk = j == 1 ? am_key : (j == 2 ? a0_key : (j == 3 ? a1_key : a2_key));
                         const unsigned sn = j == 1 ? am_n : (j == 2 ? a0_n : (j == 3 ? a1_n : a2_n));
                         const unsigned ss = j == 1 ? am_sw : (j == 2 ? a0_sw : (j == 3 ? a1_sw : a2_sw));

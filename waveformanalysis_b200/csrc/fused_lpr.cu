@@ -38,6 +38,9 @@ constexpr int kLprTile = kLprWarps * 32;  // records per tile / look-back unit
 #ifndef WFB_LPR_ENT
 #define WFB_LPR_ENT 256
 #endif
+#ifndef WFB_LPR_MINBLOCKS
+#define WFB_LPR_MINBLOCKS 3  // blocks per SM the register allocation must allow
+#endif
 constexpr int kLprEnt = WFB_LPR_ENT;              // staged hits per warp per tile (8 per record on average)
 constexpr int kHist = 2;                  // chunks of history in front of each segment
 constexpr int kMaxExt = 8;                // extensions must fit the neighbouring chunk
@@ -621,7 +624,7 @@ __device__ __forceinline__ void lpr_stream(const FHArgs& a, const uint16_t* pool
 
 // ---- the kernel --------------------------------------------------------------------------------
 template <bool FEAT, bool HITS, bool SGN>
-__global__ void __launch_bounds__(kLprWarps * 32) lpr_kernel(const FHArgs a, const int sc, const __grid_constant__ CUtensorMap tmap,
+__global__ void __launch_bounds__(kLprWarps * 32, WFB_LPR_MINBLOCKS) lpr_kernel(const FHArgs a, const int sc, const __grid_constant__ CUtensorMap tmap,
                                                              const int have_tmap, const int ent_cap) {
     extern __shared__ __align__(128) uint8_t dyn_smem[];  // [warp][kNBuf][lane] slots of a.slot_bytes
     __shared__ __align__(16) WarpHits s_hits[HITS ? kLprWarps : 1];

@@ -263,6 +263,17 @@ int wfb_group_time_window(const int64_t* ts_sorted_dev, int64_t n, double time_w
                           int64_t* event_id_dev, int64_t* n_events_dev, void* workspace_dev,
                           size_t workspace_bytes, void* stream);
 
+/* hit_merge (core/plugins/builtin/cpu/hit_merge.py:115-181 cluster chain, :256-322 merged rows) on
+ * packed THRESHOLD_HIT rows: per hardware channel, hits ordered by absolute window start are chained
+ * while merge_gap_ns > 0, dt matches, gap <= merge_gap_ns and total width <= max_total_width_ns.
+ * Outputs, all in cluster order: order_dev[k] = index of the k-th hit (hit_merge_clusters.hit_index),
+ * cluster_index_dev[k] (hit_merge_clusters.cluster_index), merged_dev = *n_clusters_dev packed
+ * HIT_MERGED rows (72 B; room for n rows). */
+size_t wfb_hit_merge_workspace_bytes(int64_t n);
+int wfb_hit_merge(const void* hits_dev, int64_t n, double merge_gap_ns, double max_total_width_ns, int64_t* order_dev,
+                  int64_t* cluster_index_dev, void* merged_dev, int64_t* n_clusters_dev, void* workspace_dev,
+                  size_t workspace_bytes, void* stream);
+
 /* Stable LSD radix sort of int64 keys carrying int64 values (device, n each); used by the
  * plugins for the time sort (records_builder.py:115-120, event_grouping.py:142). */
 int wfb_sort_pairs_i64(const int64_t* keys_in_dev, const int64_t* vals_in_dev, int64_t* keys_out_dev,

@@ -148,6 +148,42 @@ def test_hit_merge_default_golden(ops, golden):
     assert_rows_match(cp, golden["m0_components"], what="components")
 
 
+FX_MERGED = ("height", "integral", "width", "rise_time", "fall_time")
+
+
+def test_hit_merge_chain_golden(ops, golden):
+    cl, mg, cp = ops.hit_merge(golden["hits_thr15"])
+    assert_rows_match(cl, golden["m0_clusters"], what="clusters")
+    assert_rows_match(mg, golden["m0_merged"], what="merged", float_exact=FX_MERGED)
+    assert_rows_match(cp, golden["m0_components"], what="components")
+    cl, mg, cp = ops.hit_merge(golden["hits_thr15"], merge_gap_ns=50.0, max_total_width_ns=400.0)
+    assert_rows_match(cl, golden["m50_clusters"], what="m50 clusters")
+    assert_rows_match(mg, golden["m50_merged"], what="m50 merged", float_exact=FX_MERGED)
+    assert_rows_match(cp, golden["m50_components"], what="m50 components")
+
+
+@pytest.mark.parametrize("gap,maxw", [(20.0, 10000.0), (200.0, 300.0), (1e6, 1e9), (5.0, 0.0)])
+def test_hit_merge_chain_vs_oracle(ops, gap, maxw):
+    """Noise-level threshold: long chains, clusters across records of a channel, equal heights, the width cut
+    inside a gap-free piece, and one cluster per channel-dt run (huge gap)."""
+    from oracle import np_oracle as O
+    from waveformanalysis_b200 import engine
+    from waveformanalysis_b200.synth import make_raw_run, records_from_raw
+
+    raw = make_raw_run(6, 400, 500, seed=11)
+    rec, pool = records_from_raw(raw)
+    rec["dt"][rec["channel"] == 2] = 4  # a second sampling interval
+    hits = engine.process_host(rec, pool, features=False, threshold=4.0)["hits"]
+    hits["dt"][::97] = 8  # dt changes inside a channel break chains
+    assert len(hits) > 20 * len(rec)
+    got = ops.hit_merge(hits, merge_gap_ns=gap, max_total_width_ns=maxw)
+    want = O.hit_merge(hits, merge_gap_ns=gap, max_total_width_ns=maxw)
+    assert_rows_match(got[0], want[0], what="clusters")
+    assert_rows_match(got[1], want[1], what="merged", float_exact=FX_MERGED)
+    assert_rows_match(got[2], want[2], what="components")
+    assert len(want[1]) < len(hits) or maxw == 0.0
+
+
 def test_group_hit_windows_golden(ops, golden):
     mg = golden["m0_merged"]
     for wname, w in (("w100", 100.0), ("w0", 0.0), ("w2000", 2000.0)):

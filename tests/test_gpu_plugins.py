@@ -118,8 +118,14 @@ def test_merge_and_grouping_plugins(P, golden):
     assert_rows_match(cl, golden["m0_clusters"], what="clusters")
     assert_rows_match(mg, golden["m0_merged"], what="merged", float_exact=("height", "integral", "width", "rise_time", "fall_time"))
     assert_rows_match(cp, golden["m0_components"], what="components")
-    with pytest.raises(NotImplementedError):
-        P.B200HitMergePlugin().compute(Ctx({"merge_gap_ns": 50.0}, {"hit_threshold": h}), "run")
+    # chain merging (merge_gap_ns > 0) with the max-total-width cut
+    cfg = {"merge_gap_ns": 50.0, "max_total_width_ns": 400.0}
+    c50 = Ctx(cfg, {"hit_threshold": h}, plugins={"hit_merged": P.B200HitMergePlugin()})
+    cl50 = P.B200HitMergeClustersPlugin().compute(c50, "run")
+    mg50 = P.B200HitMergePlugin().compute(c50, "run")
+    assert_rows_match(cl50, golden["m50_clusters"], what="m50 clusters")
+    assert_rows_match(mg50, golden["m50_merged"], what="m50 merged", float_exact=("height", "integral", "width", "rise_time", "fall_time"))
+    assert len(mg50) < len(mg)
     for wname, w in (("w100", 100.0), ("w0", 0.0)):
         ctx.config = {"time_window_ns": w}
         df = P.B200HitGroupedPlugin().compute(ctx, "run")

@@ -203,6 +203,16 @@ struct OpMaxF64 {
     __device__ static T op(T a, T b) { return fmax(a, b); }
 };
 
+struct OpSegMax {
+    typedef SegMax T;
+    __device__ static T id() { return SegMax{__longlong_as_double((long long)0xfff0000000000000ull), -1}; }
+    __device__ static T op(T a, T b) {
+        if (b.seg < 0) return a;
+        if (a.seg == b.seg) b.v = fmax(a.v, b.v);
+        return b;
+    }
+};
+
 template <typename Op>
 __device__ typename Op::T block_inclusive_scan(typename Op::T v, typename Op::T* smem /*[kScanThreads]*/) {
     typedef typename Op::T T;
@@ -297,6 +307,9 @@ int inclusive_scan_sum_i64(const long long* in, long long* out, long long n, voi
 }
 int inclusive_scan_max_f64(const double* in, double* out, long long n, void* workspace, cudaStream_t st) {
     return run_scan<OpMaxF64>(in, out, n, workspace, st);
+}
+int inclusive_scan_segmax(const SegMax* in, SegMax* out, long long n, void* workspace, cudaStream_t st) {
+    return run_scan<OpSegMax>(in, out, n, workspace, st);
 }
 
 }  // namespace wfb

@@ -21,4 +21,11 @@ size_t scan_workspace_bytes(long long n);
 int inclusive_scan_sum_i64(const long long* in, long long* out, long long n, void* workspace, cudaStream_t st);
 int inclusive_scan_max_f64(const double* in, double* out, long long n, void* workspace, cudaStream_t st);
 
+// running maximum that restarts with every segment (seg ascending); needs 2 * scan_workspace_bytes(n)
+struct SegMax {
+    double v;
+    long long seg;
+};
+int inclusive_scan_segmax(const SegMax* in, SegMax* out, long long n, void* workspace, cudaStream_t st);
+
 }  // namespace wfb

@@ -13,6 +13,7 @@ import numpy as np
 
 from . import _lib
 from .dtypes import (
+    THRESHOLD_HIT_DTYPE,
     HIT_MERGE_CLUSTERS_DTYPE,
     HIT_MERGED_COMPONENTS_DTYPE,
     HIT_MERGED_DTYPE,
@@ -393,4 +394,35 @@ def hit_merge_default(hits: np.ndarray):
     comps = np.zeros(nh, dtype=HIT_MERGED_COMPONENTS_DTYPE)
     comps["merged_index"] = np.arange(nh)
     comps["hit_index"] = order
+    return clusters, merged, comps
+
+
+def hit_merge(hits: np.ndarray, *, merge_gap_ns: float = 0.0, max_total_width_ns: float = 10000.0):
+    """hit_merge_clusters / hit_merged / hit_merged_components for any merge_gap_ns
+    (hit_merge.py:115-181, 256-322): sort, certain-break flags, per-piece greedy replay and the
+    merged rows all run on the device (wfb_hit_merge)."""
+    nh = len(hits)
+    if nh == 0:
+        return (np.zeros(0, dtype=HIT_MERGE_CLUSTERS_DTYPE), np.zeros(0, dtype=HIT_MERGED_DTYPE),
+                np.zeros(0, dtype=HIT_MERGED_COMPONENTS_DTYPE))
+    if hits.dtype != THRESHOLD_HIT_DTYPE:
+        raise ValueError("hit_merge expects THRESHOLD_HIT_DTYPE rows")
+    lib = _lib.load()
+    torch = _torch()
+    d_hits = torch.from_numpy(np.ascontiguousarray(hits).view(np.uint8).reshape(-1).copy()).cuda()
+    d_order = torch.empty(nh, dtype=torch.int64, device="cuda")
+    d_cidx = torch.empty(nh, dtype=torch.int64, device="cuda")
+    d_merged = torch.empty(nh * HIT_MERGED_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    d_ncl = torch.zeros(1, dtype=torch.int64, device="cuda")
+    ws = _empty(lib.wfb_hit_merge_workspace_bytes(nh))
+    _lib.check(lib.wfb_hit_merge(_ptr(d_hits), nh, float(merge_gap_ns), float(max_total_width_ns), _ptr(d_order), _ptr(d_cidx),
+                                 _ptr(d_merged), _ptr(d_ncl), _ptr(ws), ws.numel(), _stream()), "wfb_hit_merge")
+    ncl = int(d_ncl.item())
+    clusters = np.zeros(nh, dtype=HIT_MERGE_CLUSTERS_DTYPE)
+    clusters["cluster_index"] = d_cidx.cpu().numpy()
+    clusters["hit_index"] = d_order.cpu().numpy()
+    merged = d_merged[: ncl * HIT_MERGED_DTYPE.itemsize].cpu().numpy().view(HIT_MERGED_DTYPE).copy()
+    comps = np.zeros(nh, dtype=HIT_MERGED_COMPONENTS_DTYPE)
+    comps["merged_index"] = clusters["cluster_index"]
+    comps["hit_index"] = clusters["hit_index"]
     return clusters, merged, comps

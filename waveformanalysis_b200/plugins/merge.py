@@ -2,10 +2,10 @@
 core/plugins/builtin/cpu/hit_merge.py:325-534).
 
 With the default ``merge_gap_ns <= 0`` nothing is merged: every threshold hit is its own cluster,
-but rows are regrouped by (board, channel) and ordered by absolute window start - two device
-radix sorts.  ``merge_gap_ns > 0`` (chain merging with the max-width cut, a sequential rule) is
-not offloaded in this round: these plugins raise and the reference's CPU plugins should stay
-registered for that configuration."""
+but rows are regrouped by (board, channel) and ordered by absolute window start.  With
+``merge_gap_ns > 0`` hits are chained greedily (gap and max-total-width rule); the device cuts the
+ordered hits where a break is certain and one thread replays the reference loop inside each
+piece (``wfb_hit_merge``)."""
 
 from __future__ import annotations
 
@@ -33,13 +33,11 @@ def _merge_all(context: Any, plugin: Plugin, run_id: str):
         getter = getattr(context, "get_plugin", None)
         merge_plugin = getter("hit_merged") if callable(getter) else B200HitMergePlugin()
     merge_gap_ns = float(context.get_config(merge_plugin, "merge_gap_ns"))
-    if merge_gap_ns > 0:
-        raise NotImplementedError("merge_gap_ns > 0 is not offloaded to the B200 in this round; keep the CPU hit_merge plugins "
-                                  "registered for chain merging")
+    max_total_width_ns = float(context.get_config(merge_plugin, "max_total_width_ns"))
     if len(hits):
         explicit_dt = resolve_dt_config(context, merge_plugin, deprecated_keys=("sampling_interval_ns", "dt_ns"))
         check_dt_array(hits, explicit_dt, plugin.provides, "hit_threshold[channel]")
-    key = (run_id, "_b200_hit_merge", id(hits))
+    key = (run_id, "_b200_hit_merge", id(hits), merge_gap_ns, max_total_width_ns)
     cache = getattr(context, "_b200_cache", None)
     if cache is None:
         cache = {}
@@ -49,7 +47,7 @@ def _merge_all(context: Any, plugin: Plugin, run_id: str):
             pass
     if key not in cache:
         cache.clear()
-        cache[key] = ops.hit_merge_default(hits)
+        cache[key] = ops.hit_merge(hits, merge_gap_ns=merge_gap_ns, max_total_width_ns=max_total_width_ns)
     return cache[key]
 
 

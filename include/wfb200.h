@@ -263,6 +263,25 @@ int wfb_group_time_window(const int64_t* ts_sorted_dev, int64_t n, double time_w
                           int64_t* event_id_dev, int64_t* n_events_dev, void* workspace_dev,
                           size_t workspace_bytes, void* stream);
 
+/* CAEN V1725 DAW_DEMO binary ingest (utils/formats/v1725.py:69-114, the per-waveform Python loop of
+ * V1725Reader.iter_waves; core/processing/records_builder.py:164-209, 798-830).
+ * wfb_v1725_scan_host walks the header chain of one .bin stream in HOST memory and fills one index entry
+ * per waveform (payload byte offset, samples, channel, 48-bit sample-index timestamp, 16-bit baseline,
+ * trunc flag); parsing stops at the first short read like the reference's reader.  capacity == 0 only
+ * counts.  wfb_build_records_v1725 takes the stream bytes of all files (concatenated, offsets rebased, on
+ * the device) plus the index columns and writes RECORDS_DTYPE rows, wave_pool and wfb_rec_meta in the
+ * reference's order: timestamp_ps = timestamp * dt_ns * 1000, lexsort((seq, channel, board, pid,
+ * timestamp)), ragged wave_offsets, baseline = header field, flags = trunc, time = timestamp_ps // 1000. */
+int wfb_v1725_scan_host(const uint8_t* blob_host, int64_t n_bytes, int64_t capacity, int64_t* payload_offset,
+                        int32_t* n_samples, int16_t* channel, int64_t* timestamp, uint16_t* baseline, uint8_t* trunc,
+                        int64_t* n_records, int64_t* n_samples_total);
+size_t wfb_build_records_v1725_workspace_bytes(int64_t n);
+int wfb_build_records_v1725(const uint8_t* blob_dev, int64_t blob_bytes, const int64_t* payload_offset_dev,
+                            const int32_t* n_samples_dev, const int64_t* timestamp_dev, const int16_t* board_dev,
+                            const int16_t* channel_dev, const uint16_t* baseline_dev, const uint8_t* trunc_dev, int64_t n,
+                            int32_t dt_ns, void* records_aos_dev, uint16_t* pool_dev, int64_t pool_len,
+                            wfb_rec_meta* meta_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* hit_merge (core/plugins/builtin/cpu/hit_merge.py:115-181 cluster chain, :256-322 merged rows) on
  * packed THRESHOLD_HIT rows: per hardware channel, hits ordered by absolute window start are chained
  * while merge_gap_ns > 0, dt matches, gap <= merge_gap_ns and total width <= max_total_width_ns.

@@ -7,6 +7,8 @@ vectorised execution over many records; they are not copies of the reference loo
 
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from waveformanalysis_b200.dtypes import (
@@ -797,3 +799,106 @@ def group_time_window(timestamps: np.ndarray, channels: np.ndarray, time_window_
         offsets=bounds,
         members=members,
     )
+
+
+# --------------------------------------------------------------------------------------------
+# CAEN V1725 DAW_DEMO binary ingest
+# --------------------------------------------------------------------------------------------
+def v1725_board_from_name(name: str) -> int:
+    """Board id from the file name, 0 when absent (utils/formats/v1725.py:62-67)."""
+    import re
+
+    m = re.search(r"_b(\d+)", os.path.basename(str(name)), flags=re.IGNORECASE)
+    return int(m.group(1)) if m else 0
+
+
+def v1725_scan(blob) -> dict:
+    """Walk the event / channel header chain of one .bin stream (utils/formats/v1725.py:69-114): per
+    event a 16-byte header (channel mask = byte 4 | byte 11 << 8), per fired channel (ascending) a
+    12-byte header - size in 32-bit words = low 22 bits of bytes 0..2, trunc = bit 6 of byte 3,
+    timestamp = bytes 4..9, baseline = bytes 10..11 - then (size - 3) * 4 payload bytes.  Parsing stops
+    at the first short read, exactly like the reference's reader."""
+    b = bytes(blob)
+    pos, n = 0, len(b)
+    off, ns, ch, ts, bl, tr = [], [], [], [], [], []
+    while True:
+        if n - pos <= 0:
+            break
+        if n - pos < 16:
+            break
+        hdr = b[pos:pos + 16]
+        pos += 16
+        mask = hdr[4] + (hdr[11] << 8)
+        stop = False
+        for c in range(16):
+            if not (mask >> c) & 1:
+                continue
+            if n - pos < 12:
+                pos = n  # the reader has consumed the partial header
+                stop = True
+                break
+            h = b[pos:pos + 12]
+            pos += 12
+            size = int.from_bytes(h[:3], "little") & ((1 << 22) - 1)
+            sig = (size - 3) << 2
+            if sig < 0:
+                raise ValueError("V1725 channel header with size < 3 words")
+            if n - pos < sig:
+                pos = n
+                stop = True
+                break
+            off.append(pos)
+            ns.append(sig // 2)
+            ch.append(c)
+            ts.append(int.from_bytes(h[4:10], "little"))
+            bl.append(int.from_bytes(h[10:12], "little"))
+            tr.append((h[3] >> 6) & 1)
+            pos += sig
+        if stop:
+            continue  # the next header read hits EOF
+    return dict(payload_offset=np.array(off, dtype=np.int64), n_samples=np.array(ns, dtype=np.int32),
+                channel=np.array(ch, dtype=np.int16), timestamp=np.array(ts, dtype=np.int64),
+                baseline=np.array(bl, dtype=np.uint16), trunc=np.array(tr, dtype=np.uint8))
+
+
+def build_records_from_v1725(blobs, names, dt_ns: int):
+    """records + wave_pool from V1725 streams (core/processing/records_builder.py:164-209, 798-830):
+    timestamp_ps = sample-index timestamp * dt_ns * 1000 (formats/base.py:184-186), baseline = header
+    field, flags = trunc, samples reinterpreted as uint16 (:108-112), time = timestamp_ps // 1000; rows
+    ordered by lexsort((seq, channel, board, pid, timestamp)) over all files, which equals the reference's
+    per-file sort followed by its k-way merge (tie-break part index, then row)."""
+    cols = {k: [] for k in ("board", "channel", "timestamp", "baseline", "flags", "n_samples")}
+    waves = []
+    for blob, name in zip(blobs, names):
+        s = v1725_scan(blob)
+        raw = np.frombuffer(bytes(blob), dtype=np.uint8)
+        k = len(s["channel"])
+        cols["board"].append(np.full(k, v1725_board_from_name(name), dtype=np.int16))
+        cols["channel"].append(s["channel"])
+        cols["timestamp"].append(s["timestamp"] * np.int64(int(dt_ns) * 1000))
+        cols["baseline"].append(s["baseline"].astype(np.float64))
+        cols["flags"].append(s["trunc"].astype(np.uint32))
+        cols["n_samples"].append(s["n_samples"])
+        for o, m in zip(s["payload_offset"].tolist(), s["n_samples"].tolist()):
+            waves.append(raw[o:o + 2 * m].view(np.uint16))
+    c = {k: (np.concatenate(v) if v else np.zeros(0)) for k, v in cols.items()}
+    n = len(waves)
+    rec = np.zeros(n, dtype=RECORDS_DTYPE)
+    if n == 0:
+        return rec, np.zeros(0, dtype=np.uint16)
+    order = np.lexsort((np.arange(n), c["channel"], c["board"], np.zeros(n, np.int32), c["timestamp"]))
+    rec["timestamp"] = c["timestamp"][order]
+    rec["board"] = c["board"][order]
+    rec["channel"] = c["channel"][order]
+    rec["baseline"] = c["baseline"][order]
+    rec["baseline_upstream"] = np.nan
+    rec["polarity"] = "unknown"
+    rec["dt"] = dt_ns
+    rec["flags"] = c["flags"][order]
+    rec["event_length"] = c["n_samples"][order]
+    rec["time"] = rec["timestamp"] // 1000
+    lens = rec["event_length"].astype(np.int64)
+    rec["wave_offset"] = np.cumsum(lens) - lens
+    rec["record_id"] = np.arange(n)
+    pool = np.concatenate([waves[i] for i in order.tolist()]) if n else np.zeros(0, dtype=np.uint16)
+    return rec, pool.astype(np.uint16, copy=False)

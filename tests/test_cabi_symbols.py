@@ -54,3 +54,21 @@ def test_no_cpu_fallback_without_gpu():
 
     with pytest.raises(RuntimeError, match="no CUDA device"):
         engine.process_host(np.zeros(1, RECORDS_DTYPE), np.zeros(4, np.uint16))
+
+
+def test_v1725_host_scan_matches_oracle():
+    """wfb_v1725_scan_host is a host function (no GPU needed): same index as the oracle's header walk,
+    including streams cut in the middle of an event header, a channel header or a payload."""
+    import numpy as np
+
+    from oracle import np_oracle as O
+    from waveformanalysis_b200 import ops
+    from waveformanalysis_b200.synth import make_v1725_blob
+
+    blob = make_v1725_blob(n_events=60, n_channels=16, seed=5, lengths=(2, 90), tie_every=4)
+    for cut in (0, 1, 7, 15, 16, 17, 27, 28, 29, 31, 200, 1001, len(blob) - 1, len(blob)):
+        part = blob[:cut]
+        got, want = ops.v1725_scan(part), O.v1725_scan(part)
+        for k in ("payload_offset", "n_samples", "channel", "timestamp", "baseline", "trunc"):
+            assert np.array_equal(got[k], want[k]), (cut, k)
+        assert got["n_samples_total"] == int(want["n_samples"].sum())

@@ -236,3 +236,31 @@ def test_grouping_large_vs_oracle(ops):
         got, want = ops.group_time_window(feats["timestamp"], feats["channel"], w), O.group_time_window(feats["timestamp"], feats["channel"], w)
         for k in ("t_min", "t_max", "n_hits", "offsets", "members"):
             assert np.array_equal(got[k], want[k]), (w, k)
+
+
+def test_v1725_ingest_golden(ops):
+    from test_oracle_golden import v1725_cases
+
+    for tag, blobs, names, dt_ns, want_rec, want_pool in v1725_cases():
+        rec, pool = ops.build_records_from_v1725(blobs, names, dt_ns)
+        assert np.array_equal(pool, want_pool), tag
+        assert_rows_match(rec, want_rec, what=f"v1725 {tag}", float_exact=("baseline",))
+
+
+def test_v1725_ingest_large_vs_oracle(ops):
+    """Several files, many timestamp ties across files and channels, ragged lengths; the records feed the
+    fused kernel unchanged."""
+    from oracle import np_oracle as O
+    from waveformanalysis_b200 import engine
+    from waveformanalysis_b200.synth import make_v1725_blob
+
+    blobs = [make_v1725_blob(n_events=700, n_channels=16, seed=20 + k, lengths=(16, 600), tie_every=2, t0=3 * k) for k in range(4)]
+    names = [f"run_b{k % 3}_seg{k}.bin" for k in range(4)]
+    rec, pool = ops.build_records_from_v1725(blobs, names, 4)
+    want_rec, want_pool = O.build_records_from_v1725(blobs, names, 4)
+    assert len(rec) > 20000 and np.array_equal(pool, want_pool)
+    assert_rows_match(rec, want_rec, what="v1725 large", float_exact=("baseline",))
+    out = engine.process_host(rec, pool, threshold=25.0, signed_samples=False)
+    assert_rows_match(out["features"], O.basic_features(rec, pool), what="v1725 features", float_exact=("height", "amp", "max_abs_diff"))
+    assert_rows_match(out["hits"], O.threshold_hits(rec, pool, threshold=25.0), what="v1725 hits", float_exact=("height", "width", "rise_time", "fall_time"))
+    assert ops.build_records_from_v1725([], [], 4)[0].shape == (0,)

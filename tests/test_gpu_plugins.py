@@ -170,3 +170,24 @@ def test_records_plugins_from_raw_arrays(P, golden):
     for name in want.dtype.names:
         assert np.array_equal(rec[name], want[name], equal_nan=(want[name].dtype.kind == "f")), name
     assert np.array_equal(pool, golden["wave_pool"])
+
+
+def test_records_plugins_from_v1725_files(P, tmp_path):
+    """daq_adapter="v1725": the .bin files named in raw_files are indexed on the host and decoded on the
+    device; rows must equal the reference's build_records_from_v1725_files output (golden)."""
+    from test_oracle_golden import v1725_cases
+
+    for tag, blobs, names, dt_ns, want_rec, want_pool in v1725_cases():
+        paths = []
+        for blob, name in zip(blobs, names):
+            p = tmp_path / tag / name
+            p.parent.mkdir(parents=True, exist_ok=True)
+            p.write_bytes(blob)
+            paths.append(str(p))
+        # the reference groups files per channel / board and lists may repeat a path
+        groups = [[paths[0]]] + [[p] for p in paths[1:]] + [[paths[0]]]
+        ctx = Ctx({"daq_adapter": "v1725", "dt": dt_ns}, {"raw_files": groups})
+        rec = P.B200RecordsPlugin().compute(ctx, "run")
+        pool = P.B200WavePoolPlugin().compute(ctx, "run")
+        assert np.array_equal(pool, want_pool), tag
+        assert_rows_match(rec, want_rec, what=f"v1725 plugin {tag}", float_exact=("baseline",))

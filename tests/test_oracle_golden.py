@@ -144,3 +144,22 @@ def test_group_time_window(golden):
             assert np.array_equal(ev["n_hits"], golden[f"{tag}_n_hits"])
             assert np.array_equal(bf["timestamp"][ev["members"]], golden[f"{tag}_timestamps"])
             assert np.array_equal(bf["channel"][ev["members"]], golden[f"{tag}_channels"])
+
+
+def v1725_cases():
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "v1725_golden.npz"), allow_pickle=False)
+    for tag in ("a", "b", "cut"):
+        k = int(g[f"{tag}_nfiles"])
+        blobs = [g[f"{tag}_blob{i}"].tobytes() for i in range(k)]
+        names = [str(g[f"{tag}_name{i}"]) for i in range(k)]
+        yield tag, blobs, names, int(g[f"{tag}_dt_ns"]), g[f"{tag}_records"], g[f"{tag}_pool"]
+
+
+def test_v1725_ingest_matches_reference():
+    for tag, blobs, names, dt_ns, want_rec, want_pool in v1725_cases():
+        rec, pool = O.build_records_from_v1725(blobs, names, dt_ns)
+        assert np.array_equal(pool, want_pool), tag
+        assert_rows_match(rec, want_rec, what=f"v1725 {tag}", float_exact=("baseline",))
+        assert np.all(np.isnan(rec["baseline_upstream"]))

@@ -118,6 +118,9 @@ PROTOTYPES = {
     "wfb_features_hits_check": (C.c_int, [_vp, _vp]),
     "wfb_process_host": (C.c_int, [_vp, _i64, _vp, _i64, C.POINTER(FHParams), _vp, _vp, _vp, _i64, _vp, C.POINTER(_i64), _i64]),
     "wfb_release_cache": (C.c_int, []),
+    "wfb_v1725_scan_host": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i64), C.POINTER(_i64)]),
+    "wfb_build_records_v1725_workspace_bytes": (_sz, [_i64]),
+    "wfb_build_records_v1725": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
     "wfb_hit_merge_workspace_bytes": (_sz, [_i64]),
     "wfb_hit_merge": (C.c_int, [_vp, _i64, _dbl, _dbl, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "wfb_filter_pool": (C.c_int, [_vp, _i32, _i64, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _sz, _i32, _vp]),

@@ -426,3 +426,73 @@ def hit_merge(hits: np.ndarray, *, merge_gap_ns: float = 0.0, max_total_width_ns
     comps["merged_index"] = clusters["cluster_index"]
     comps["hit_index"] = clusters["hit_index"]
     return clusters, merged, comps
+
+
+# --------------------------------------------------------------------------------------------
+# CAEN V1725 binary ingest
+# --------------------------------------------------------------------------------------------
+def v1725_board_from_name(name) -> int:
+    """Board id from the file name, 0 when absent (utils/formats/v1725.py:62-67)."""
+    import os
+    import re
+
+    m = re.search(r"_b(\d+)", os.path.basename(str(name)), flags=re.IGNORECASE)
+    return int(m.group(1)) if m else 0
+
+
+def v1725_scan(blob) -> dict:
+    """Header-chain index of one .bin stream (wfb_v1725_scan_host): one entry per waveform."""
+    lib = _lib.load()
+    buf = np.frombuffer(blob, dtype=np.uint8) if not isinstance(blob, np.ndarray) else np.ascontiguousarray(blob).view(np.uint8).reshape(-1)
+    n_rec, n_tot = C.c_int64(0), C.c_int64(0)
+    _lib.check(lib.wfb_v1725_scan_host(_hp(buf), len(buf), 0, None, None, None, None, None, None, C.byref(n_rec), C.byref(n_tot)),
+               "wfb_v1725_scan_host")
+    n = int(n_rec.value)
+    cols = dict(payload_offset=np.empty(n, np.int64), n_samples=np.empty(n, np.int32), channel=np.empty(n, np.int16),
+                timestamp=np.empty(n, np.int64), baseline=np.empty(n, np.uint16), trunc=np.empty(n, np.uint8))
+    if n:
+        _lib.check(lib.wfb_v1725_scan_host(_hp(buf), len(buf), n, _hp(cols["payload_offset"]), _hp(cols["n_samples"]), _hp(cols["channel"]),
+                                           _hp(cols["timestamp"]), _hp(cols["baseline"]), _hp(cols["trunc"]), C.byref(n_rec), C.byref(n_tot)),
+                   "wfb_v1725_scan_host")
+    cols["n_samples_total"] = int(n_tot.value)
+    cols["bytes"] = buf
+    return cols
+
+
+def _hp(a: np.ndarray | None):
+    return C.c_void_p(0) if a is None or a.size == 0 else C.c_void_p(a.ctypes.data)
+
+
+def build_records_from_v1725(blobs, names, dt_ns: int):
+    """V1725 .bin streams (bytes / uint8 arrays, one per file, with their file names for the board id)
+    -> (records[RECORDS_DTYPE], wave_pool[uint16]) in the reference's order
+    (records_builder.py:798-830 build_records_from_v1725_files)."""
+    lib = _lib.load()
+    torch = _torch()
+    scans = [v1725_scan(b) for b in blobs]
+    n = sum(len(s["channel"]) for s in scans)
+    total = sum(s["n_samples_total"] for s in scans)
+    if n == 0:
+        return np.zeros(0, dtype=RECORDS_DTYPE), np.zeros(0, dtype=np.uint16)
+    # one device buffer with every stream at a 16-byte aligned base, payload offsets rebased
+    bases, cursor = [], 0
+    for s in scans:
+        bases.append(cursor)
+        cursor += (len(s["bytes"]) + 15) & ~15
+    d_blob = torch.empty(cursor + 16, dtype=torch.uint8, device="cuda")
+    for s, base in zip(scans, bases):
+        if len(s["bytes"]):
+            d_blob[base:base + len(s["bytes"])].copy_(torch.from_numpy(s["bytes"].copy()))
+    off = np.concatenate([s["payload_offset"] + base for s, base in zip(scans, bases)])
+    board = np.concatenate([np.full(len(s["channel"]), v1725_board_from_name(nm), dtype=np.int16) for s, nm in zip(scans, names)])
+    cat = {k: np.concatenate([s[k] for s in scans]) for k in ("n_samples", "channel", "timestamp", "baseline", "trunc")}
+    rows = _empty(n * 102)
+    pool = torch.empty(total + 16, dtype=torch.int16, device="cuda")[:total]
+    ws = _empty(lib.wfb_build_records_v1725_workspace_bytes(n))
+    d = {k: _dev(v) for k, v in cat.items()}
+    d_off, d_board = _dev(off), _dev(board)
+    _lib.check(lib.wfb_build_records_v1725(_ptr(d_blob), cursor, _ptr(d_off), _ptr(d["n_samples"]), _ptr(d["timestamp"]), _ptr(d_board),
+                                           _ptr(d["channel"]), _ptr(d["baseline"]), _ptr(d["trunc"]), n, int(dt_ns), _ptr(rows), _ptr(pool),
+                                           total, C.c_void_p(0), _ptr(ws), ws.numel(), _stream()), "wfb_build_records_v1725")
+    rec = rows[: n * 102].cpu().numpy().view(RECORDS_DTYPE)
+    return rec, pool.cpu().numpy().view(np.uint16)

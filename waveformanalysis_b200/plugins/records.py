@@ -1,11 +1,14 @@
 """records / wave_pool on the B200 (reference: core/plugins/builtin/cpu/records.py:209-331,
 core/processing/records_builder.py:429-642).
 
-File reading stays with the reference's DAQ readers (text/binary parsing is host I/O);
+CSV reading stays with the reference's DAQ readers (text parsing is host I/O);
 the per-channel raw int16 rows they return are uploaded once and the baseline, the global
 (timestamp, pid, board, channel, input order) sort, the gather into the contiguous wave_pool and the
 packed RECORDS_DTYPE rows are produced by the K1 kernels.  Without the reference package installed
-the plugins still build records from raw arrays seeded into the context as ``raw_arrays``."""
+the plugins still build records from raw arrays seeded into the context as ``raw_arrays``.
+V1725 ``.bin`` streams (``daq_adapter="v1725"``) do not go through the reference's per-waveform
+Python reader at all: the file bytes are indexed by one host pass over the header chain and decoded,
+sorted and packed on the device (``ops.build_records_from_v1725``)."""
 
 from __future__ import annotations
 
@@ -45,12 +48,54 @@ def _read_raw_arrays(context: Any, run_id: str, adapter_name: str):
     return out, adapter
 
 
+def _apply_polarity(context: Any, run_id: str, records: np.ndarray) -> None:
+    """records["polarity"] from the channel metadata layers (records.py:40-63 of the reference)."""
+    if not HAVE_REFERENCE or len(records) == 0:
+        return
+    try:
+        from waveform_analysis.core.hardware.channel import HardwareChannel  # type: ignore
+        from waveform_analysis.core.plugins.builtin.cpu.waveforms import _build_polarity_lookup  # type: ignore
+    except Exception:
+        return
+    keys = np.unique(np.stack([records["board"].astype(np.int64), records["channel"].astype(np.int64)], axis=1), axis=0)
+    try:
+        lookup = _build_polarity_lookup(context, run_id, keys[:, 0], keys[:, 1])
+    except Exception:
+        return
+    for b, c in keys.tolist():
+        pol = lookup.get(HardwareChannel(int(b), int(c)), "unknown")
+        if pol != "unknown":
+            records["polarity"][(records["board"] == b) & (records["channel"] == c)] = pol
+
+
+def _v1725_bundle(context: Any, run_id: str, plugin: Plugin):
+    """raw_files (groups of .bin paths) -> records + wave_pool (records.py:133-152 of the reference)."""
+    raw_files = context.get_data(run_id, "raw_files")
+    paths, seen = [], set()
+    for group in raw_files or []:
+        for path in group or []:
+            if path not in seen:
+                seen.add(path)
+                paths.append(path)
+    dt_ns = context.get_config(plugin, "dt")
+    if dt_ns is None:
+        dt_ns = 4  # 250 MS/s (utils/formats/v1725.py:189)
+    blobs = [np.fromfile(str(p), dtype=np.uint8) for p in paths]
+    return ops.build_records_from_v1725(blobs, [str(p) for p in paths], int(dt_ns))
+
+
 def build_bundle(context: Any, run_id: str, plugin: Plugin):
     cache = getattr(context, "_results", None)
     key = (run_id, _CACHE_ATTR)
     if isinstance(cache, dict) and key in cache:
         return cache[key]
     adapter_name = (context.get_config(plugin, "daq_adapter") or getattr(context, "config", {}).get("daq_adapter") or "vx2730").lower()
+    if adapter_name == "v1725" and (not hasattr(context, "get_data") or context.get_data(run_id, "raw_arrays") is None):
+        bundle = _v1725_bundle(context, run_id, plugin)
+        _apply_polarity(context, run_id, bundle[0])
+        if isinstance(cache, dict):
+            cache[key] = bundle
+        return bundle
     arrays, adapter = _read_raw_arrays(context, run_id, adapter_name)
     dt_ns = context.get_config(plugin, "dt")
     if adapter is not None:
@@ -85,6 +130,7 @@ def build_bundle(context: Any, run_id: str, plugin: Plugin):
             raise NotImplementedError("records: channels with different record lengths are not built on the B200 in this round")
         bundle = ops.build_records(np.concatenate(ts), np.concatenate(boards), np.concatenate(chans), np.vstack(samples),
                                    dt_ns=int(dt_ns), baseline_window=(bl0, bl1))
+    _apply_polarity(context, run_id, bundle[0])
     if isinstance(cache, dict):
         cache[key] = bundle
     return bundle

@@ -131,3 +131,42 @@ def make_ragged_records(n: int, *, seed: int = 7, min_len: int = 1, max_len: int
     rec["event_length"] = lens
     rec["time"] = rec["timestamp"] // 1000
     return rec, pool
+
+
+def make_v1725_blob(*, n_events: int, n_channels: int = 16, seed: int = 0, lengths=(64, 64), tie_every: int = 0, t0: int = 0) -> bytes:
+    """A synthetic CAEN V1725 DAW_DEMO .bin stream (layout: utils/formats/v1725.py:62-114 of the
+    reference): per event a 16-byte header whose bytes 4 and 11 hold the channel mask, then per fired
+    channel a 12-byte header (size in 32-bit words incl. the header: 22 bits; bit 6 of byte 3 = trunc;
+    48-bit sample-index timestamp; 16-bit baseline) followed by (size - 3) * 4 bytes of int16 samples.
+    ``lengths`` = (min, max) samples per waveform (rounded to even); ``tie_every`` repeats timestamps."""
+    rng = np.random.default_rng(seed)
+    out = bytearray()
+    t = int(t0)
+    for ev in range(n_events):
+        mask = int(rng.integers(1, 1 << n_channels))
+        hdr = bytearray(16)
+        hdr[0:4] = int(rng.integers(0, 2**31)).to_bytes(4, "little")  # bytes the reader ignores
+        hdr[4] = mask & 0xFF
+        hdr[11] = (mask >> 8) & 0xFF
+        out += hdr
+        if not (tie_every and ev % tie_every == 0):
+            t += int(rng.integers(1, 5000))
+        for ch in range(16):
+            if not (mask >> ch) & 1:
+                continue
+            ns = int(rng.integers(lengths[0], lengths[1] + 1))
+            ns += ns & 1
+            size = 3 + ns // 2
+            ch_hdr = bytearray(12)
+            ch_hdr[0] = size & 0xFF
+            ch_hdr[1] = (size >> 8) & 0xFF
+            ch_hdr[2] = (size >> 16) & 0x3F
+            ch_hdr[3] = (0x40 if rng.random() < 0.2 else 0) | int(rng.integers(0, 64))
+            ts = t + (0 if (tie_every and ev % tie_every == 0) else int(rng.integers(0, 3)))
+            ch_hdr[4:10] = int(ts).to_bytes(6, "little")
+            ch_hdr[10:12] = int(rng.integers(0, 16384)).to_bytes(2, "little")
+            out += ch_hdr
+            wave = (8000 + rng.normal(0, 30, ns)).astype(np.int16)
+            wave[:: max(ns // 5, 1)] -= 9000  # some genuinely negative int16 samples
+            out += wave.tobytes()
+    return bytes(out)

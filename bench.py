@@ -294,6 +294,27 @@ def run_ours(args):
     if traffic:
         roofline["traffic_source"] = traffic.get("source")
 
+    # ---- the same kernel without the hit path (records -> baseline -> basic_features only): how far the
+    # sample stream itself is from the HBM roofline; algorithmic bytes 2L + 72 per record
+    feat_only = None
+    if rank == 0:
+        kwf = dict(hits=False, out={"features": out["features"]})
+        for _ in range(3):
+            run.features_hits(**kwf)
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            run.features_hits(**kwf)
+        f1.record()
+        torch.cuda.synchronize()
+        fms = f0.elapsed_time(f1) / args.steps
+        fgbs = n * (2 * N_SAMPLES + 72) / (fms * 1e-3) / 1e9
+        feat_only = {"kernel": "lpr_kernel<features,-,u16>", "kernel_ms": fms, "records_per_s": n / (fms * 1e-3),
+                     "achieved": fgbs, "peak": peak, "unit": "GB/s", "frac": fgbs / peak, "bytes_per_record": 2 * N_SAMPLES + 72}
+    if world > 1:
+        dist.barrier()
+
     # ---- e2e: host buffers through the reference-facing call
     e2e = None
     if not args.no_e2e:
@@ -327,6 +348,7 @@ def run_ours(args):
             "config": workload_config(args, {"hits_per_record": hits_all / records_all}),
             "raw_sample_GBps": records_all * 2 * N_SAMPLES / (ms_per_step * 1e-3) / 1e9,
             "roofline": roofline,
+            "roofline_features_only": feat_only,
             "cpu_baseline": cpu,
             "e2e": e2e,
             "gpu_launches": args.steps * 1,

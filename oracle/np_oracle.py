@@ -902,3 +902,130 @@ def build_records_from_v1725(blobs, names, dt_ns: int):
     rec["record_id"] = np.arange(n)
     pool = np.concatenate([waves[i] for i in order.tolist()]) if n else np.zeros(0, dtype=np.uint16)
     return rec, pool.astype(np.uint16, copy=False)
+
+
+# --------------------------------------------------------------------------------------------
+# `hit` = scipy.signal.find_peaks per record.  scipy is an un-vendored dependency of the
+# reference (pyproject.toml: scipy>=1.7.0; 1.18.1 in the build container); the algorithm below restates
+# scipy/signal/_peak_finding.py (find_peaks) and _peak_finding_utils.pyx (_local_maxima_1d,
+# _select_by_peak_distance, _peak_prominences, _peak_widths) and is pinned against live scipy in
+# tests/test_oracle_known_answers.py and against the reference plugin's output in tests/golden/hit_golden.npz.
+# --------------------------------------------------------------------------------------------
+def find_peaks_1d(x, *, height=None, threshold=None, distance=None, prominence=None, width=None, rel_height=0.5):
+    """Returns (peaks, left_ips, right_ips, prominences) for the conditions the reference uses
+    (lower bounds only).  Plain loops: use on small inputs."""
+    x = np.asarray(x, dtype=np.float64)
+    n = len(x)
+    peaks = []
+    i, i_max = 1, n - 1
+    while i < i_max:  # _local_maxima_1d: strict rise, plateau midpoint, strict fall
+        if x[i - 1] < x[i]:
+            ahead = i + 1
+            while ahead < i_max and x[ahead] == x[i]:
+                ahead += 1
+            if x[ahead] < x[i]:
+                peaks.append((i + ahead - 1) // 2)
+                i = ahead
+        i += 1
+    peaks = np.array(peaks, dtype=np.int64)
+    if height is not None:
+        peaks = peaks[x[peaks] >= height]
+    if threshold is not None and len(peaks):
+        peaks = peaks[np.minimum(x[peaks] - x[peaks - 1], x[peaks] - x[peaks + 1]) >= threshold]
+    if distance is not None and len(peaks):
+        d = int(np.ceil(distance))
+        keep = np.ones(len(peaks), dtype=bool)
+        order = np.argsort(x[peaks], kind="stable")
+        for j in order[::-1].tolist():  # highest first
+            if not keep[j]:
+                continue
+            k = j - 1
+            while k >= 0 and peaks[j] - peaks[k] < d:
+                keep[k] = False
+                k -= 1
+            k = j + 1
+            while k < len(peaks) and peaks[k] - peaks[j] < d:
+                keep[k] = False
+                k += 1
+        peaks = peaks[keep]
+    proms = np.zeros(len(peaks))
+    lb = np.zeros(len(peaks), dtype=np.int64)
+    rb = np.zeros(len(peaks), dtype=np.int64)
+    for q, p in enumerate(peaks.tolist()):  # _peak_prominences, wlen=None
+        i, left_min, lb[q] = p, x[p], p
+        while i >= 0 and x[i] <= x[p]:
+            if x[i] < left_min:
+                left_min, lb[q] = x[i], i
+            i -= 1
+        i, right_min, rb[q] = p, x[p], p
+        while i <= n - 1 and x[i] <= x[p]:
+            if x[i] < right_min:
+                right_min, rb[q] = x[i], i
+            i += 1
+        proms[q] = x[p] - max(left_min, right_min)
+    if prominence is not None:
+        sel = proms >= prominence
+        peaks, proms, lb, rb = peaks[sel], proms[sel], lb[sel], rb[sel]
+    lips = np.zeros(len(peaks))
+    rips = np.zeros(len(peaks))
+    for q, p in enumerate(peaks.tolist()):  # _peak_widths
+        h = x[p] - proms[q] * rel_height
+        i = p
+        while lb[q] < i and h < x[i]:
+            i -= 1
+        lip = float(i)
+        if x[i] < h:
+            lip += (h - x[i]) / (x[i + 1] - x[i])
+        i = p
+        while i < rb[q] and h < x[i]:
+            i += 1
+        rip = float(i)
+        if x[i] < h:
+            rip -= (h - x[i]) / (x[i - 1] - x[i])
+        lips[q], rips[q] = lip, rip
+    if width is not None:
+        sel = (rips - lips) >= width
+        peaks, proms, lips, rips = peaks[sel], proms[sel], lips[sel], rips[sel]
+    return peaks, lips, rips, proms
+
+
+def _peak_height(w, edge_start, edge_end, method, ext):
+    """peak_finding.py:567-614: minmax over the rounded (half-to-even) edge window +- ext, or the diff sum."""
+    s = max(0, int(np.round(edge_start)))
+    e = min(len(w) - 1, int(np.round(edge_end)))
+    if method == "diff":
+        return float(np.sum(np.diff(-w)[s:e])) if e > s else 0.0
+    if method != "minmax":
+        raise ValueError(f"unsupported height_method: {method}")
+    ext = max(0, int(ext))
+    win = w[max(0, s - ext):min(len(w), e + ext)]
+    return float(np.max(win) - np.min(win))
+
+
+def hit_find_peaks(waves, meta, *, source: str, use_derivative=True, height=30.0, distance=2, prominence=0.7, width=4,
+                   threshold=None, height_method="minmax", height_window_extension=4):
+    """HitFinderPlugin rows (peak_finding.py:213-565).  ``source``: "aos" - rows of st_waveforms /
+    filtered_waveforms (``waves`` = list of per-record arrays in their stored dtype, negative pulses:
+    detection = -diff(wave) or baseline - wave); "records" - ``waves`` = -RecordsView.signals() in float64
+    (detection = +diff or the signal itself).  ``meta`` = structured array with timestamp, board, channel,
+    record_id, dt, baseline."""
+    from waveformanalysis_b200.dtypes import HIT_DTYPE
+
+    rows = []
+    for k, w in enumerate(waves):
+        w = np.asarray(w)
+        if len(w) == 0:
+            continue
+        if source == "records":
+            det = np.diff(w) if use_derivative else (w - 0.0)
+        elif use_derivative:
+            det = -np.diff(w)
+        else:
+            det = np.float64(meta["baseline"][k]) - w
+        peaks, lips, rips, _ = find_peaks_1d(det, height=height, threshold=threshold, distance=distance, prominence=prominence, width=width)
+        dt_ns = int(meta["dt"][k])
+        for p, a, b in zip(peaks.tolist(), lips.tolist(), rips.tolist()):
+            rows.append((p, _peak_height(w, a, b, height_method, height_window_extension), 0.0, a, b, dt_ns,
+                         int(meta["timestamp"][k] + p * (dt_ns * 1e3)), int(meta["board"][k]), int(meta["channel"][k]),
+                         int(meta["record_id"][k])))
+    return np.array(rows, dtype=HIT_DTYPE) if rows else np.zeros(0, dtype=HIT_DTYPE)

@@ -163,3 +163,36 @@ def test_v1725_ingest_matches_reference():
         assert np.array_equal(pool, want_pool), tag
         assert_rows_match(rec, want_rec, what=f"v1725 {tag}", float_exact=("baseline",))
         assert np.all(np.isnan(rec["baseline_upstream"]))
+
+
+def hit_cases():
+    """(tag, waves, meta, source, options, reference rows) for the `hit` golden file."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "hit_golden.npz"), allow_pickle=False)
+    rec, pool, fpool = g["records"], g["pool"], g["filtered_pool"]
+    n, L = len(rec), 800
+    w_i16 = pool.view(np.int16).reshape(n, L)
+    w_f32 = fpool.reshape(n, L)
+    aos = [("filt_default", w_f32, {}),
+           ("filt_lowcut", w_f32, {"height": 3.0, "prominence": 0.5, "width": 2, "distance": 6, "height_window_extension": 1}),
+           ("filt_thr", w_f32, {"height": 5.0, "threshold": 0.5, "width": 1}),
+           ("filt_diffheight", w_f32, {"height": 10.0, "height_method": "diff"}),
+           ("st_default", w_i16, {"height": 12.0, "width": 2}),
+           ("st_level", w_i16, {"use_derivative": False, "height": 20.0, "prominence": 4.0, "width": 3})]
+    for tag, w, kw in aos:
+        yield tag, w, rec, "aos", kw, g[tag]
+    sig = -(pool.reshape(n, L).astype(np.float32) - rec["baseline"].astype(np.float32)[:, None])
+    yield "rec_default", (-sig).astype(np.float64) * -1.0, rec, "records", {"height": 12.0, "width": 2}, g["rec_default"]
+    prec, ppool = g["pos_records"], g["pos_pool"]
+    m = len(prec)
+    s = ppool.reshape(m, L).astype(np.float32) - prec["baseline"].astype(np.float32)[:, None]  # signals() negates positive pulses ...
+    psig = s.astype(np.float64)                                                                 # ... and the plugin negates again
+    yield "pos_level", psig, prec, "records", {"use_derivative": False, "height": 30.0, "prominence": 5.0, "width": 2}, g["pos_level"]
+    yield "pos_deriv", psig, prec, "records", {"height": 8.0, "width": 2}, g["pos_deriv"]
+
+
+def test_hit_find_peaks_matches_reference():
+    for tag, waves, meta, source, kw, want in hit_cases():
+        got = O.hit_find_peaks(list(waves), meta, source=source, **kw)
+        assert_rows_match(got, want, what=f"hit {tag}", float_exact=("height", "edge_start", "edge_end"))

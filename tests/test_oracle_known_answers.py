@@ -59,3 +59,30 @@ def test_grouping_known_answer():
     assert ev["t_max"].tolist() == want["t_max"]
     assert ev["dt_ns"].tolist() == want["dt_ns"]
     assert ev["n_hits"].tolist() == want["n_hits"]
+
+
+def test_find_peaks_restatement_matches_live_scipy():
+    """The oracle's find_peaks restatement against scipy.signal.find_peaks itself (the un-vendored
+    dependency that holds the arithmetic of the reference's `hit` plugin): random walks with plateaus
+    and ties, every condition the plugin passes."""
+    from scipy.signal import find_peaks
+
+    from oracle import np_oracle as O
+
+    rng = np.random.default_rng(3)
+    for trial in range(60):
+        n = int(rng.integers(3, 400))
+        x = np.cumsum(rng.normal(0, 3, n))
+        if trial % 3 == 0:
+            x = np.round(x)  # plateaus and equal heights
+        kw = dict(height=float(rng.uniform(-5, 5)), prominence=float(rng.uniform(0.2, 6)), width=float(rng.uniform(0.5, 6)),
+                  distance=int(rng.integers(1, 12)) if trial % 2 else 2)
+        if trial % 5 == 0:
+            kw["threshold"] = float(rng.uniform(0, 1.5))
+        if trial % 3 == 0 and kw["distance"] > 2:
+            kw["distance"] = 2  # equal heights: scipy's priority order among ties is not defined
+        want_p, props = find_peaks(x, **kw)
+        got_p, lips, rips, proms = O.find_peaks_1d(x, **kw)
+        assert np.array_equal(got_p, want_p), (trial, kw)
+        assert np.array_equal(lips, props["left_ips"]) and np.array_equal(rips, props["right_ips"]), trial
+        assert np.array_equal(proms, props["prominences"]), trial

@@ -263,6 +263,39 @@ int wfb_group_time_window(const int64_t* ts_sorted_dev, int64_t n, double time_w
                           int64_t* event_id_dev, int64_t* n_events_dev, void* workspace_dev,
                           size_t workspace_bytes, void* stream);
 
+/* `hit` = scipy.signal.find_peaks per record (core/plugins/builtin/cpu/peak_finding.py:213-565
+ * HitFinderPlugin._compute_peaks / _find_peaks_in_waveform / _calculate_peak_height).
+ * wave_kind selects what the plugin calls `waveform` and the detection signal:
+ *   WFB_WAVE_AOS_I16 / WFB_WAVE_AOS_F32: rows of st_waveforms / filtered_waveforms (meta.wave_offset in
+ *     elements of that type); detection = -diff(wave) in the wave's own dtype, or baseline - wave;
+ *   WFB_WAVE_REC_U16 / WFB_WAVE_REC_F32: records + wave_pool(_filtered); waveform = -RecordsView.signals()
+ *     (float32 baseline subtraction, polarity-normalised) in float64; detection = +diff or the signal.
+ * Conditions are lower bounds as the plugin passes them; distance <= 2 is a no-op (local maxima are at
+ * least two samples apart).  Rows are packed HIT_DTYPE (48 B) in record order; peaks beyond row_cap are
+ * counted in *total_out_dev but not stored.  Synchronises the stream (error flag read-back). */
+#define WFB_WAVE_AOS_I16 0
+#define WFB_WAVE_AOS_F32 1
+#define WFB_WAVE_REC_U16 2
+#define WFB_WAVE_REC_F32 3
+typedef struct wfb_peak_params {
+    int32_t wave_kind;      /* WFB_WAVE_* */
+    int32_t use_derivative; /* detect on the first difference (default) or on the level */
+    double height;          /* find_peaks(height=) */
+    double prominence;      /* find_peaks(prominence=) */
+    double width;           /* find_peaks(width=), rel_height 0.5 */
+    double threshold;       /* find_peaks(threshold=) when has_threshold */
+    int32_t has_threshold;
+    int32_t distance;       /* find_peaks(distance=) */
+    int32_t height_method;  /* 0 "minmax", 1 "diff" */
+    int32_t height_window_extension;
+    int32_t lmax;           /* longest record (samples) */
+    int32_t reserved_;
+} wfb_peak_params;
+size_t wfb_find_peaks_workspace_bytes(int64_t n);
+int wfb_find_peaks(const void* waves_dev, int64_t waves_len, const wfb_rec_meta* meta_dev, int64_t n,
+                   const wfb_peak_params* params, void* rows_out_dev, int64_t row_cap, int32_t* counts_out_dev,
+                   int64_t* total_out_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* CAEN V1725 DAW_DEMO binary ingest (utils/formats/v1725.py:69-114, the per-waveform Python loop of
  * V1725Reader.iter_waves; core/processing/records_builder.py:164-209, 798-830).
  * wfb_v1725_scan_host walks the header chain of one .bin stream in HOST memory and fills one index entry

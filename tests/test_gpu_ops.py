@@ -264,3 +264,55 @@ def test_v1725_ingest_large_vs_oracle(ops):
     assert_rows_match(out["features"], O.basic_features(rec, pool), what="v1725 features", float_exact=("height", "amp", "max_abs_diff"))
     assert_rows_match(out["hits"], O.threshold_hits(rec, pool, threshold=25.0), what="v1725 hits", float_exact=("height", "width", "rise_time", "fall_time"))
     assert ops.build_records_from_v1725([], [], 4)[0].shape == (0,)
+
+
+def test_hit_find_peaks_golden(ops):
+    """`hit` rows against the reference HitFinderPlugin (tests/golden/hit_golden.npz): filtered float32 rows,
+    raw int16 rows, records source with unknown / positive polarity, every option the plugin passes."""
+    import os
+
+    from waveformanalysis_b200.dtypes import create_record_dtype
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "hit_golden.npz"), allow_pickle=False)
+    rec, pool, fpool = g["records"], g["pool"], g["filtered_pool"]
+    n, L = len(rec), 800
+    st = np.zeros(n, dtype=create_record_dtype(L))
+    for f in ("baseline", "baseline_upstream", "polarity", "timestamp", "record_id", "dt", "event_length", "board", "channel"):
+        st[f] = rec[f]
+    st["wave"] = pool.reshape(n, L).view(np.int16)
+    stf_dtype = np.dtype([(name, (np.float32, (L,)) if name == "wave" else st.dtype.fields[name][0]) for name in st.dtype.names])
+    stf = np.zeros(n, dtype=stf_dtype)
+    for f in st.dtype.names:
+        if f != "wave":
+            stf[f] = st[f]
+    stf["wave"] = fpool.reshape(n, L)
+    fx = ("height", "edge_start", "edge_end")
+    cases = [("filt_default", stf, {}),
+             ("filt_lowcut", stf, {"height": 3.0, "prominence": 0.5, "width": 2, "distance": 6, "height_window_extension": 1}),
+             ("filt_thr", stf, {"height": 5.0, "threshold": 0.5, "width": 1}),
+             ("filt_diffheight", stf, {"height": 10.0, "height_method": "diff"}),
+             ("st_default", st, {"height": 12.0, "width": 2}),
+             ("st_level", st, {"use_derivative": False, "height": 20.0, "prominence": 4.0, "width": 3})]
+    for tag, data, kw in cases:
+        assert_rows_match(ops.find_peaks_waveforms(data, **kw), g[tag], what=f"hit {tag}", float_exact=fx)
+    assert_rows_match(ops.find_peaks_records(rec, pool, height=12.0, width=2), g["rec_default"], what="hit rec_default", float_exact=fx)
+    prec, ppool = g["pos_records"], g["pos_pool"]
+    assert_rows_match(ops.find_peaks_records(prec, ppool, use_derivative=False, height=30.0, prominence=5.0, width=2), g["pos_level"],
+                      what="hit pos_level", float_exact=fx)
+    assert_rows_match(ops.find_peaks_records(prec, ppool, height=8.0, width=2), g["pos_deriv"], what="hit pos_deriv", float_exact=fx)
+
+
+def test_hit_find_peaks_vs_oracle_ragged_and_plateaus(ops):
+    """Ragged records, integer plateaus, a minimal distance > 2 on float data, truncated rows."""
+    from oracle import np_oracle as O
+    from waveformanalysis_b200.synth import make_ragged_records
+
+    rec, pool = make_ragged_records(300, seed=5, min_len=1, max_len=500)
+    waves = []
+    for o, l, b, pol in zip(rec["wave_offset"], rec["event_length"], rec["baseline"], rec["polarity"]):
+        s = pool[int(o):int(o) + int(l)].astype(np.float32) - np.float32(b)  # RecordsView.signals before polarity normalisation
+        waves.append((s if pol == "positive" else -s).astype(np.float64))    # the plugin's -signals()
+    for kw in ({"height": 6.0, "prominence": 2.0, "width": 1}, {"use_derivative": False, "height": 10.0, "prominence": 3.0, "width": 2}):
+        want = O.hit_find_peaks(waves, rec, source="records", **kw)
+        assert len(want) > 50
+        assert_rows_match(ops.find_peaks_records(rec, pool, **kw), want, what="ragged hit", float_exact=("height", "edge_start", "edge_end"))

@@ -191,3 +191,32 @@ def test_records_plugins_from_v1725_files(P, tmp_path):
         pool = P.B200WavePoolPlugin().compute(ctx, "run")
         assert np.array_equal(pool, want_pool), tag
         assert_rows_match(rec, want_rec, what=f"v1725 plugin {tag}", float_exact=("baseline",))
+
+
+def test_hit_finder_plugin(P):
+    """B200HitFinderPlugin against the reference HitFinderPlugin rows (hit_golden.npz) through the plugin
+    interface: filtered_waveforms (default), st_waveforms and records sources."""
+    import os
+
+    from waveformanalysis_b200.dtypes import HIT_DTYPE, create_record_dtype
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "hit_golden.npz"), allow_pickle=False)
+    rec, pool, fpool = g["records"], g["pool"], g["filtered_pool"]
+    n, L = len(rec), 800
+    st = st_from_records(rec, pool, L)
+    stf_dtype = np.dtype([(name, (np.float32, (L,)) if name == "wave" else st.dtype.fields[name][0]) for name in st.dtype.names])
+    stf = np.zeros(n, dtype=stf_dtype)
+    for f in st.dtype.names:
+        if f != "wave":
+            stf[f] = st[f]
+    stf["wave"] = fpool.reshape(n, L)
+    fx = ("height", "edge_start", "edge_end")
+    assert_rows_match(run(P.B200HitFinderPlugin(), {"filtered_waveforms": stf, "st_waveforms": st}, {}), g["filt_default"], what="hit default", float_exact=fx)
+    assert_rows_match(run(P.B200HitFinderPlugin(), {"st_waveforms": st}, {"use_filtered": False, "height": 12.0, "width": 2}), g["st_default"],
+                      what="hit st", float_exact=fx)
+    assert_rows_match(run(P.B200HitFinderPlugin(), {"records": rec, "wave_pool": pool},
+                          {"use_filtered": False, "wave_source": "records", "height": 12.0, "width": 2}), g["rec_default"], what="hit records", float_exact=fx)
+    empty = run(P.B200HitFinderPlugin(), {"st_waveforms": st[:0]}, {"use_filtered": False})
+    assert empty.dtype == HIT_DTYPE and len(empty) == 0
+    with pytest.raises(ValueError):
+        run(P.B200HitFinderPlugin(), {"st_waveforms": st}, {"use_filtered": False, "height_method": "area"})

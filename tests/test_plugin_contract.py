@@ -29,7 +29,7 @@ def test_profile_provides_the_hot_path_names():
     from waveformanalysis_b200 import profiles
 
     names = [p.provides for p in profiles.b200_default()]
-    assert names == ["records", "wave_pool", "wave_pool_filtered", "basic_features", "hit_threshold", "waveform_width",
+    assert names == ["records", "wave_pool", "wave_pool_filtered", "basic_features", "hit_threshold", "hit", "waveform_width",
                      "waveform_width_integral", "hit_merge_clusters", "hit_merged", "hit_merged_components", "hit_grouped",
                      "df_events"]
     for p in profiles.b200_default():
@@ -83,13 +83,14 @@ def test_structured_rows_as_pool_without_repacking():
 @pytest.mark.skipif(not HAVE_REF, reason="reference checkout not available")
 def test_contract_matches_reference_plugins():
     _import_ref()
-    from waveform_analysis.core.plugins.builtin.cpu import basic_features, event_analysis, hit_finder, hit_merge, records, waveform_width, waveform_width_integral
+    from waveform_analysis.core.plugins.builtin.cpu import basic_features, event_analysis, hit_finder, hit_merge, peak_finding, records, waveform_width, waveform_width_integral
 
     from waveformanalysis_b200 import plugins as P
 
     pairs = [
         (P.B200BasicFeaturesPlugin, basic_features.BasicFeaturesPlugin),
         (P.B200ThresholdHitPlugin, hit_finder.ThresholdHitPlugin),
+        (P.B200HitFinderPlugin, peak_finding.HitFinderPlugin),
         (P.B200WavePoolFilteredPlugin, records.WavePoolFilteredPlugin),
         (P.B200WaveformWidthPlugin, waveform_width.WaveformWidthPlugin),
         (P.B200WaveformWidthIntegralPlugin, waveform_width_integral.WaveformWidthIntegralPlugin),

@@ -106,6 +106,14 @@ class WidthParams(C.Structure):
 _vp, _i64, _i32, _sz, _dbl = C.c_void_p, C.c_int64, C.c_int32, C.c_size_t, C.c_double
 
 # name -> (restype, argtypes): exactly the prototypes of include/wfb200.h
+class PeakParams(C.Structure):  # wfb_peak_params
+    _fields_ = [("wave_kind", C.c_int32), ("use_derivative", C.c_int32), ("height", C.c_double), ("prominence", C.c_double),
+                ("width", C.c_double), ("threshold", C.c_double), ("has_threshold", C.c_int32), ("distance", C.c_int32),
+                ("height_method", C.c_int32), ("height_window_extension", C.c_int32), ("lmax", C.c_int32), ("reserved_", C.c_int32)]
+
+
+WAVE_AOS_I16, WAVE_AOS_F32, WAVE_REC_U16, WAVE_REC_F32 = 0, 1, 2, 3
+
 PROTOTYPES = {
     "wfb_last_error": (C.c_char_p, []),
     "wfb_version": (C.c_int, []),
@@ -118,6 +126,8 @@ PROTOTYPES = {
     "wfb_features_hits_check": (C.c_int, [_vp, _vp]),
     "wfb_process_host": (C.c_int, [_vp, _i64, _vp, _i64, C.POINTER(FHParams), _vp, _vp, _vp, _i64, _vp, C.POINTER(_i64), _i64]),
     "wfb_release_cache": (C.c_int, []),
+    "wfb_find_peaks_workspace_bytes": (_sz, [_i64]),
+    "wfb_find_peaks": (C.c_int, [_vp, _i64, _vp, _i64, C.POINTER(PeakParams), _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "wfb_v1725_scan_host": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i64), C.POINTER(_i64)]),
     "wfb_build_records_v1725_workspace_bytes": (_sz, [_i64]),
     "wfb_build_records_v1725": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),

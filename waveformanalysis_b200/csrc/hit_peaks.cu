@@ -1,0 +1,345 @@
+// `hit`: scipy.signal.find_peaks per record on the device (HitFinderPlugin).
+//
+// Reference: core/plugins/builtin/cpu/peak_finding.py:213-565 (_compute_peaks, _find_peaks_in_waveform,
+// _calculate_peak_height).  The arithmetic lives in scipy (un-vendored dependency, scipy>=1.7.0; restated
+// from scipy/signal/_peak_finding.py and _peak_finding_utils.pyx, see oracle/np_oracle.py:find_peaks_1d):
+//   local maxima (strict rise, plateau midpoint, strict fall) -> height >= hmin -> optional neighbour
+//   threshold -> minimal distance (highest peaks first) -> prominence (bases = lowest samples up to the next
+//   higher sample on each side) -> width at rel_height 0.5 with linearly interpolated crossings.
+//
+// One warp per record.  The record's waveform (float64, exact for int16 / float32 sources) and the
+// detection signal are staged in shared memory; lanes test 32 positions per step for a local maximum and
+// compact the survivors in order with ballots; prominence / width scans run one peak per lane.  Rows are
+// variable in number: a counting pass, a device scan and an emitting pass (same code, rows switched on).
+#include <algorithm>
+
+#include "common.cuh"
+#include "np_sum.cuh"
+#include "sort_scan.cuh"
+
+namespace wfb {
+
+constexpr int kPeakWarps = 4;
+constexpr int kPeakRowBytes = 48;  // HIT_DTYPE
+
+// numpy pairwise summation in float32 (np.sum of a float32 array accumulates in float32)
+template <typename Src>
+__device__ float numpy_pairwise_sum_f32(const Src& x, int off, int n) {
+    if (n < 8) {
+        float res = 0.f;
+        for (int i = 0; i < n; ++i) res = __fadd_rn(res, x(off + i));
+        return res;
+    }
+    if (n <= 128) {
+        float r[8];
+        for (int k = 0; k < 8; ++k) r[k] = x(off + k);
+        int i;
+        for (i = 8; i < n - (n % 8); i += 8)
+            for (int k = 0; k < 8; ++k) r[k] = __fadd_rn(r[k], x(off + i + k));
+        float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])), __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+        for (; i < n; ++i) res = __fadd_rn(res, x(off + i));
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return __fadd_rn(numpy_pairwise_sum_f32(x, off, n2), numpy_pairwise_sum_f32(x, off + n2, n - n2));
+}
+
+struct PeakRec {
+    int kind, len, m;  // wave kind, samples, detection samples
+    bool deriv;
+    double baseline;
+    const double* w;   // shared: waveform values
+    const double* x;   // shared: detection signal
+};
+
+__device__ __forceinline__ double detection_value(const PeakRec& r, int i) {
+    if (r.deriv) {
+        if (r.kind == WFB_WAVE_AOS_I16) {  // np.diff on int16 stays int16, so does the negation
+            const short d = (short)((int)r.w[i + 1] - (int)r.w[i]);
+            return (double)(short)(-(int)d);
+        }
+        if (r.kind == WFB_WAVE_AOS_F32) return (double)(-__fsub_rn((float)r.w[i + 1], (float)r.w[i]));
+        return __dsub_rn(r.w[i + 1], r.w[i]);  // records: +diff of the float64 signal
+    }
+    if (r.kind == WFB_WAVE_AOS_I16 || r.kind == WFB_WAVE_AOS_F32) return __dsub_rn(r.baseline, r.w[i]);
+    return r.w[i];
+}
+
+struct DiffSrcF32 {  // np.diff(-waveform) for a float32 waveform
+    const double* w;
+    __device__ float operator()(int i) const { return __fsub_rn(-(float)w[i + 1], -(float)w[i]); }
+};
+struct DiffSrcF64 {
+    const double* w;
+    __device__ double operator()(int i) const { return __dsub_rn(-w[i + 1], -w[i]); }
+};
+struct OffsetSrc {
+    DiffSrcF64 s;
+    int off;
+    __device__ double operator()(int i) const { return s(off + i); }
+};
+
+// peak_finding.py:567-614
+__device__ float peak_height(const PeakRec& r, double edge_start, double edge_end, int method, int ext) {
+    int s = max(0, (int)rint(edge_start));  // np.round: half to even
+    int e = min(r.len - 1, (int)rint(edge_end));
+    if (method == 1) {  // "diff": sum(diff(-w)[s:e]) in the waveform's own arithmetic
+        if (e <= s) return 0.f;
+        if (r.kind == WFB_WAVE_AOS_I16) {
+            long long acc = 0;  // int16 diffs summed in int64
+            for (int i = s; i < e; ++i) acc += (short)((int)(short)(-(int)r.w[i + 1]) - (int)(short)(-(int)r.w[i]));
+            return (float)(double)acc;
+        }
+        if (r.kind == WFB_WAVE_AOS_F32) return (float)(double)numpy_pairwise_sum_f32(DiffSrcF32{r.w}, s, e - s);
+        return (float)numpy_pairwise_sum(OffsetSrc{DiffSrcF64{r.w}, s}, e - s);
+    }
+    ext = max(0, ext);
+    const int a = max(0, s - ext), b = min(r.len, e + ext);
+    if (b <= a) return __int_as_float(0x7fc00000);  // numpy raises on an empty window; cannot happen for found peaks
+    double mx = r.w[a], mn = r.w[a];
+    for (int i = a + 1; i < b; ++i) { mx = fmax(mx, r.w[i]); mn = fmin(mn, r.w[i]); }
+    if (r.kind == WFB_WAVE_AOS_I16) return (float)(double)(short)((int)mx - (int)mn);
+    if (r.kind == WFB_WAVE_AOS_F32) return __fsub_rn((float)mx, (float)mn);
+    return (float)__dsub_rn(mx, mn);
+}
+
+template <bool EMIT>
+__global__ void __launch_bounds__(kPeakWarps * 32) find_peaks_kernel(const void* __restrict__ waves, long long waves_len,
+                                                                     const wfb_rec_meta* __restrict__ meta, long long n,
+                                                                     const wfb_peak_params p, int lcap, int* __restrict__ counts,
+                                                                     const long long* __restrict__ row_incl,
+                                                                     uint8_t* __restrict__ rows, long long row_cap, int* __restrict__ err) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const long long rec = (long long)blockIdx.x * kPeakWarps + warp;
+    if (rec >= n) return;
+    // per warp: w[lcap], x[lcap] doubles, peak positions int[lcap/2 + 2], keep flags
+    const size_t per_warp = (size_t)lcap * 16 + (size_t)(lcap / 2 + 2) * 4 + (size_t)(lcap / 2 + 2);
+    uint8_t* base = smem + (size_t)warp * ((per_warp + 15) & ~(size_t)15);
+    double* w = reinterpret_cast<double*>(base);
+    double* x = w + lcap;
+    int* peaks = reinterpret_cast<int*>(x + lcap);
+    uint8_t* keep = reinterpret_cast<uint8_t*>(peaks + (lcap / 2 + 2));
+
+    const wfb_rec_meta mrec = meta[rec];
+    int len = mrec.event_length;
+    const long long off = mrec.wave_offset;
+    if (len < 0) len = 0;
+    if (len > 0 && (off < 0 || off + len > waves_len)) {
+        if (lane == 0) atomicExch(err, 1);
+        len = 0;
+    }
+    if (len > lcap) {
+        if (lane == 0) atomicExch(err, 2);
+        len = 0;
+    }
+    // ---- stage the waveform as the plugin sees it
+    const bool records_src = p.wave_kind == WFB_WAVE_REC_U16 || p.wave_kind == WFB_WAVE_REC_F32;
+    const float b32 = (float)mrec.baseline;
+    for (int i = lane; i < len; i += 32) {
+        double v;
+        if (p.wave_kind == WFB_WAVE_AOS_I16) v = (double)static_cast<const short*>(waves)[off + i];
+        else if (p.wave_kind == WFB_WAVE_AOS_F32) v = (double)static_cast<const float*>(waves)[off + i];
+        else {
+            const float s = (p.wave_kind == WFB_WAVE_REC_U16) ? (float)static_cast<const unsigned short*>(waves)[off + i]
+                                                              : static_cast<const float*>(waves)[off + i];
+            // -RecordsView.signals(): signals = f32(w) - f32(b), negated once more for positive pulses (records_view.py:152-169)
+            v = (mrec.polarity == WFB_POL_POSITIVE) ? (double)__fsub_rn(s, b32) : (double)__fsub_rn(b32, s);
+        }
+        w[i] = v;
+    }
+    __syncwarp();
+    PeakRec r;
+    r.kind = records_src ? WFB_WAVE_REC_U16 : p.wave_kind;
+    r.len = len;
+    r.deriv = p.use_derivative != 0;
+    r.m = r.deriv ? max(len - 1, 0) : len;
+    r.baseline = mrec.baseline;
+    r.w = w;
+    r.x = x;
+    for (int i = lane; i < r.m; i += 32) x[i] = detection_value(r, i);
+    __syncwarp();
+
+    // ---- local maxima + height / threshold conditions, compacted in order
+    const int m = r.m;
+    int np = 0;
+    for (int b0 = 0; b0 < m; b0 += 32) {
+        const int i = b0 + lane;
+        int pos = -1;
+        if (i >= 1 && i < m - 1 && x[i - 1] < x[i]) {
+            int ahead = i + 1;
+            while (ahead < m - 1 && x[ahead] == x[i]) ++ahead;
+            if (x[ahead] < x[i]) pos = (i + ahead - 1) >> 1;
+        }
+        if (pos >= 0) {
+            bool ok = x[pos] >= p.height;
+            if (ok && p.has_threshold) ok = fmin(__dsub_rn(x[pos], x[pos - 1]), __dsub_rn(x[pos], x[pos + 1])) >= p.threshold;
+            if (!ok) pos = -1;
+        }
+        const unsigned bal = __ballot_sync(kFull, pos >= 0);
+        if (pos >= 0) {
+            const int k = np + __popc(bal & ((1u << lane) - 1u));
+            peaks[k] = pos;
+            keep[k] = 1;
+        }
+        np += __popc(bal);
+    }
+    __syncwarp();
+    // ---- minimal distance: highest peaks first (stable order among equal heights: the later peak wins)
+    if (p.distance > 2 && np > 1 && lane == 0) {
+        for (int round = 0; round < np; ++round) {
+            // the highest peak not yet visited: visited peaks are marked with bit 1 of keep
+            int best = -1;
+            for (int k = 0; k < np; ++k) {
+                if (keep[k] & 2) continue;
+                if (best < 0 || x[peaks[k]] >= x[peaks[best]]) best = k;
+            }
+            if (best < 0) break;
+            keep[best] |= 2;
+            if (!(keep[best] & 1)) continue;
+            for (int k = best - 1; k >= 0 && peaks[best] - peaks[k] < p.distance; --k) keep[k] &= ~1;
+            for (int k = best + 1; k < np && peaks[k] - peaks[best] < p.distance; ++k) keep[k] &= ~1;
+        }
+    }
+    __syncwarp();
+    // ---- prominence, width, rows: one peak per lane, survivors compacted in order
+    long long row0 = 0;
+    if (EMIT) row0 = row_incl[rec] - counts[rec];
+    int nout = 0;
+    for (int q0 = 0; q0 < np; q0 += 32) {
+        const int q = q0 + lane;
+        bool ok = q < np && (keep[q] & 1);
+        int pk = 0;
+        double lip = 0.0, rip = 0.0;
+        if (ok) {
+            pk = peaks[q];
+            const double xp = x[pk];
+            int i = pk, lb = pk, rb = pk;
+            double lmin = xp, rmin = xp;
+            while (i >= 0 && x[i] <= xp) {
+                if (x[i] < lmin) { lmin = x[i]; lb = i; }
+                --i;
+            }
+            i = pk;
+            while (i <= m - 1 && x[i] <= xp) {
+                if (x[i] < rmin) { rmin = x[i]; rb = i; }
+                ++i;
+            }
+            const double prom = __dsub_rn(xp, fmax(lmin, rmin));
+            ok = prom >= p.prominence;
+            if (ok) {
+                const double h = __dsub_rn(xp, __dmul_rn(prom, 0.5));
+                i = pk;
+                while (lb < i && h < x[i]) --i;
+                lip = (double)i;
+                if (x[i] < h) lip = __dadd_rn(lip, __ddiv_rn(__dsub_rn(h, x[i]), __dsub_rn(x[i + 1], x[i])));
+                i = pk;
+                while (i < rb && h < x[i]) ++i;
+                rip = (double)i;
+                if (x[i] < h) rip = __dsub_rn(rip, __ddiv_rn(__dsub_rn(h, x[i]), __dsub_rn(x[i - 1], x[i])));
+                ok = __dsub_rn(rip, lip) >= p.width;
+            }
+        }
+        const unsigned bal = __ballot_sync(kFull, ok);
+        if (EMIT && ok) {
+            const long long row = row0 + nout + __popc(bal & ((1u << lane) - 1u));
+            if (row < row_cap) {
+                const float hgt = peak_height(r, lip, rip, p.height_method, p.height_window_extension);
+                const double step = __dmul_rn((double)mrec.dt, 1e3);
+                const long long ti = (long long)__dadd_rn((double)mrec.timestamp, __dmul_rn((double)pk, step));
+                unsigned* dst = reinterpret_cast<unsigned*>(rows + row * kPeakRowBytes);
+                dst[0] = (unsigned)pk;
+                dst[1] = 0u;
+                dst[2] = __float_as_uint(hgt);
+                dst[3] = 0u;  // integral (always 0.0 in the reference)
+                dst[4] = __float_as_uint((float)lip);
+                dst[5] = __float_as_uint((float)rip);
+                dst[6] = (unsigned)mrec.dt;
+                dst[7] = (unsigned)(ti & 0xffffffffll);
+                dst[8] = (unsigned)((unsigned long long)ti >> 32);
+                dst[9] = ((unsigned)(unsigned short)mrec.board) | ((unsigned)(unsigned short)mrec.channel << 16);
+                dst[10] = (unsigned)(mrec.record_id & 0xffffffffll);
+                dst[11] = (unsigned)((unsigned long long)mrec.record_id >> 32);
+            }
+        }
+        nout += __popc(bal);
+    }
+    if (!EMIT && lane == 0) counts[rec] = nout;
+}
+
+__global__ void peaks_counts_to_i64_kernel(const int* __restrict__ counts, long long n, long long* __restrict__ out) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = counts[i];
+}
+__global__ void peaks_total_kernel(const long long* __restrict__ incl, long long n, long long* __restrict__ total) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *total = n > 0 ? incl[n - 1] : 0;
+}
+
+}  // namespace wfb
+
+using namespace wfb;
+
+static size_t pk_al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+extern "C" size_t wfb_find_peaks_workspace_bytes(int64_t n) {
+    const size_t m = pk_al256((size_t)std::max<int64_t>(n, 1) * 8);
+    return 2 * m + pk_al256((size_t)std::max<int64_t>(n, 1) * 4) + scan_workspace_bytes(n) + 512;
+}
+
+extern "C" int wfb_find_peaks(const void* waves_dev, int64_t waves_len, const wfb_rec_meta* meta_dev, int64_t n,
+                              const wfb_peak_params* params, void* rows_out_dev, int64_t row_cap, int32_t* counts_out_dev,
+                              int64_t* total_out_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+    WFB_REQUIRE(params != nullptr && total_out_dev != nullptr, "wfb_find_peaks: NULL params / total");
+    WFB_REQUIRE(n >= 0 && waves_len >= 0 && row_cap >= 0, "wfb_find_peaks: negative size");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (n == 0) {
+        WFB_CUDA(cudaMemsetAsync(total_out_dev, 0, 8, st));
+        return WFB_OK;
+    }
+    WFB_REQUIRE(meta_dev && workspace_dev && (waves_dev || waves_len == 0), "wfb_find_peaks: NULL pointer");
+    WFB_REQUIRE(row_cap == 0 || rows_out_dev != nullptr, "wfb_find_peaks: NULL row buffer");
+    WFB_REQUIRE(params->wave_kind >= WFB_WAVE_AOS_I16 && params->wave_kind <= WFB_WAVE_REC_F32, "wfb_find_peaks: unknown wave_kind");
+    WFB_REQUIRE(params->height_method == 0 || params->height_method == 1, "unsupported height_method");
+    WFB_REQUIRE(params->lmax > 0, "wfb_find_peaks: lmax must be the longest record");
+    WFB_REQUIRE(workspace_bytes >= wfb_find_peaks_workspace_bytes(n), "wfb_find_peaks: workspace too small");
+    const int lcap = (params->lmax + 1) & ~1;
+    const size_t per_warp = (((size_t)lcap * 16 + (size_t)(lcap / 2 + 2) * 4 + (size_t)(lcap / 2 + 2)) + 15) & ~(size_t)15;
+    const size_t dyn = per_warp * kPeakWarps;
+    WFB_REQUIRE(dyn <= 220 * 1024, "wfb_find_peaks: records longer than %d samples do not fit the shared-memory staging", 220 * 1024 / 18 / kPeakWarps);
+    uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
+    const size_t m = pk_al256((size_t)n * 8);
+    long long* cnt64 = reinterpret_cast<long long*>(ws);
+    long long* incl = reinterpret_cast<long long*>(ws + m);
+    int* counts = reinterpret_cast<int*>(ws + 2 * m);
+    int* err = reinterpret_cast<int*>(ws + 2 * m + pk_al256((size_t)n * 4));
+    void* scan_ws = ws + 2 * m + pk_al256((size_t)n * 4) + 256;
+    WFB_CUDA(cudaMemsetAsync(err, 0, 4, st));
+    wfb_peak_params p = *params;
+    p.distance = (int)std::min<long long>(std::max<long long>(p.distance, 0), 1 << 30);
+    const unsigned grid = (unsigned)((n + kPeakWarps - 1) / kPeakWarps);
+    WFB_CUDA(cudaFuncSetAttribute(find_peaks_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    WFB_CUDA(cudaFuncSetAttribute(find_peaks_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    find_peaks_kernel<false><<<grid, kPeakWarps * 32, dyn, st>>>(waves_dev, waves_len, meta_dev, n, p, lcap, counts, nullptr, nullptr, 0, err);
+    peaks_counts_to_i64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(counts, n, cnt64);
+    int rc = inclusive_scan_sum_i64(cnt64, incl, n, scan_ws, st);
+    if (rc != WFB_OK) return rc;
+    peaks_total_kernel<<<1, 32, 0, st>>>(incl, n, reinterpret_cast<long long*>(total_out_dev));
+    if (row_cap > 0)
+        find_peaks_kernel<true><<<grid, kPeakWarps * 32, dyn, st>>>(waves_dev, waves_len, meta_dev, n, p, lcap, counts, incl,
+                                                                  static_cast<uint8_t*>(rows_out_dev), row_cap, err);
+    if (counts_out_dev) WFB_CUDA(cudaMemcpyAsync(counts_out_dev, counts, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+    WFB_CUDA(cudaGetLastError());
+    int herr = 0;
+    WFB_CUDA(cudaMemcpyAsync(&herr, err, 4, cudaMemcpyDeviceToHost, st));
+    WFB_CUDA(cudaStreamSynchronize(st));
+    if (herr == 1) {
+        set_error("records reference samples outside the waveform buffer");
+        return WFB_ERR_LAYOUT;
+    }
+    if (herr == 2) {
+        set_error("a record is longer than params->lmax");
+        return WFB_ERR_INVALID;
+    }
+    return WFB_OK;
+}

@@ -7,7 +7,7 @@ sm_100a kernels through libwfb200.so.  Register with
 from .features import B200BasicFeaturesPlugin
 from .filtering import B200WavePoolFilteredPlugin
 from .grouping import B200GroupedEventsPlugin, B200HitGroupedPlugin
-from .hits import B200ThresholdHitPlugin
+from .hits import B200HitFinderPlugin, B200ThresholdHitPlugin
 from .merge import B200HitMergeClustersPlugin, B200HitMergedComponentsPlugin, B200HitMergePlugin
 from .records import B200RecordsPlugin, B200WavePoolPlugin
 from .widths import B200WaveformWidthIntegralPlugin, B200WaveformWidthPlugin
@@ -15,6 +15,7 @@ from .widths import B200WaveformWidthIntegralPlugin, B200WaveformWidthPlugin
 __all__ = [
     "B200BasicFeaturesPlugin",
     "B200ThresholdHitPlugin",
+    "B200HitFinderPlugin",
     "B200WavePoolFilteredPlugin",
     "B200WaveformWidthPlugin",
     "B200WaveformWidthIntegralPlugin",

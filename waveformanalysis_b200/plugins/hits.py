@@ -68,3 +68,72 @@ class B200ThresholdHitPlugin(Plugin):
                                   left_extension=left_extension, right_extension=right_extension, explicit_dt=dt_scalar,
                                   signed_samples=signed)
         return out["hits"]
+
+
+class B200HitFinderPlugin(Plugin):
+    """`hit`: scipy.signal.find_peaks per waveform on the device (reference:
+    core/plugins/builtin/cpu/peak_finding.py:43-614 HitFinderPlugin; same options and HIT_DTYPE rows)."""
+
+    provides = "hit"
+    depends_on = []
+    description = "Detect peaks in waveforms and extract peak features."
+    version = "3.0.0"
+    save_when = "always"
+    from ..dtypes import HIT_DTYPE as output_dtype  # noqa: N811
+
+    options = {
+        "use_filtered": Option(default=True, type=bool, help="use filtered_waveforms (needs the filtered waveform plugin)"),
+        "wave_source": Option(default=WAVE_SOURCE_AUTO, type=str, help="auto|records|st_waveforms|filtered_waveforms"),
+        "use_derivative": Option(default=True, type=bool, help="detect on the first difference (True) or on the level"),
+        "height": Option(default=30.0, type=float, help="minimal peak height"),
+        "distance": Option(default=2, type=int, help="minimal distance between peaks (samples)"),
+        "prominence": Option(default=0.7, type=float, help="minimal prominence"),
+        "width": Option(default=4, type=int, help="minimal width (samples)"),
+        "threshold": Option(default=None, help="optional neighbour threshold"),
+        "height_method": Option(default="minmax", type=str, help="'diff' or 'minmax'"),
+        "height_window_extension": Option(default=4, type=int, help="window extension of the minmax height"),
+        "dt": Option(default=None, type=int, help="sample interval (ns), only used when the input has no dt field"),
+        "parallel": Option(default=True, type=bool, help="unused on the GPU"),
+        "n_workers": Option(default=0, type=int, help="unused on the GPU"),
+        "chunk_size": Option(default=1024, type=int, help="unused on the GPU"),
+        "parallel_min_events": Option(default=20480, type=int, help="unused on the GPU"),
+    }
+
+    def resolve_depends_on(self, context: Any, run_id: str | None = None) -> list[str]:
+        return list(resolve_wave_input_spec(context, self).depends_on)
+
+    def compute(self, context: Any, run_id: str, **_kwargs) -> np.ndarray:
+        from .. import ops
+        from ..dtypes import HIT_DTYPE
+
+        threshold = context.get_config(self, "threshold")
+        opts = dict(use_derivative=bool(context.get_config(self, "use_derivative")), height=float(context.get_config(self, "height")),
+                    distance=int(context.get_config(self, "distance")), prominence=float(context.get_config(self, "prominence")),
+                    width=int(context.get_config(self, "width")), threshold=None if threshold is None else float(threshold),
+                    height_method=str(context.get_config(self, "height_method")),
+                    height_window_extension=int(context.get_config(self, "height_window_extension")))
+        explicit_dt = resolve_dt_config(context, self, deprecated_keys=("sampling_interval_ns", "dt_ns"))
+        wave_input = load_wave_input(context, self, run_id, needs_wave_samples=True)
+        if wave_input.spec.is_records:
+            records, pool = wave_input.records, wave_input.wave_pool
+            if records is None or pool is None:
+                raise ValueError("hit failed to load records_view for records source")
+            if len(records) == 0:
+                return np.zeros(0, dtype=HIT_DTYPE)
+            if "dt" not in (records.dtype.names or ()):
+                if explicit_dt is None:
+                    raise ValueError("[hit] records is missing required field 'dt'; provide explicit config 'dt'.")
+                from numpy.lib import recfunctions as rfn
+
+                records = rfn.append_fields(records, "dt", np.full(len(records), int(explicit_dt), np.int32), usemask=False)
+            if np.any(records["dt"] <= 0):
+                raise ValueError("[hit] dt must be > 0")
+            return ops.find_peaks_records(records, pool, **opts)
+        data = wave_input.waveform_data
+        if data is None:
+            raise ValueError("hit failed to load waveform input")
+        if len(data) == 0:
+            return np.zeros(0, dtype=HIT_DTYPE)
+        if "dt" in (data.dtype.names or ()) and np.any(data["dt"] <= 0):
+            raise ValueError("[hit] dt must be > 0")
+        return ops.find_peaks_waveforms(data, explicit_dt=explicit_dt, **opts)

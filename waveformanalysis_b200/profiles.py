@@ -9,7 +9,7 @@ def b200_default() -> list:
 
     return [
         P.B200RecordsPlugin(), P.B200WavePoolPlugin(), P.B200WavePoolFilteredPlugin(), P.B200BasicFeaturesPlugin(),
-        P.B200ThresholdHitPlugin(), P.B200WaveformWidthPlugin(), P.B200WaveformWidthIntegralPlugin(),
+        P.B200ThresholdHitPlugin(), P.B200HitFinderPlugin(), P.B200WaveformWidthPlugin(), P.B200WaveformWidthIntegralPlugin(),
         P.B200HitMergeClustersPlugin(), P.B200HitMergePlugin(), P.B200HitMergedComponentsPlugin(),
         P.B200HitGroupedPlugin(), P.B200GroupedEventsPlugin(),
     ]
@@ -19,5 +19,5 @@ def b200_hot_path() -> list:
     """Only the per-record plugins (no records builder, no grouping)."""
     from . import plugins as P
 
-    return [P.B200WavePoolFilteredPlugin(), P.B200BasicFeaturesPlugin(), P.B200ThresholdHitPlugin(),
+    return [P.B200WavePoolFilteredPlugin(), P.B200BasicFeaturesPlugin(), P.B200ThresholdHitPlugin(), P.B200HitFinderPlugin(),
             P.B200WaveformWidthPlugin(), P.B200WaveformWidthIntegralPlugin()]

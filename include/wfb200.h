@@ -277,6 +277,7 @@ int wfb_group_time_window(const int64_t* ts_sorted_dev, int64_t n, double time_w
 #define WFB_WAVE_AOS_F32 1
 #define WFB_WAVE_REC_U16 2
 #define WFB_WAVE_REC_F32 3
+#define WFB_WAVE_AOS_F32_AS_F64 4 /* float32 rows promoted to float64 first (signal_peaks_stream, signal_peaks.py:256-262) */
 typedef struct wfb_peak_params {
     int32_t wave_kind;      /* WFB_WAVE_* */
     int32_t use_derivative; /* detect on the first difference (default) or on the level */
@@ -286,7 +287,7 @@ typedef struct wfb_peak_params {
     double threshold;       /* find_peaks(threshold=) when has_threshold */
     int32_t has_threshold;
     int32_t distance;       /* find_peaks(distance=) */
-    int32_t height_method;  /* 0 "minmax", 1 "diff" */
+    int32_t height_method;  /* 0 "minmax", 1 "diff" (hit), 2 "diff" by float64 cumsum (signal_peaks_stream) */
     int32_t height_window_extension;
     int32_t lmax;           /* longest record (samples) */
     int32_t reserved_;

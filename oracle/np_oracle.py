@@ -1029,3 +1029,39 @@ def hit_find_peaks(waves, meta, *, source: str, use_derivative=True, height=30.0
                          int(meta["timestamp"][k] + p * (dt_ns * 1e3)), int(meta["board"][k]), int(meta["channel"][k]),
                          int(meta["record_id"][k])))
     return np.array(rows, dtype=HIT_DTYPE) if rows else np.zeros(0, dtype=HIT_DTYPE)
+
+
+def stream_find_peaks(waves, meta, *, use_derivative=True, height=30.0, distance=2, prominence=0.7, width=4, threshold=None,
+                      height_method="diff", minmax_window_expand=2):
+    """signal_peaks_stream rows of one chunk (plugins/builtin/streaming/cpu/signal_peaks.py:234-401): the
+    filtered row promoted to float64, detection = -diff(w) or baseline - w, heights by float64 cumsum
+    differences ("diff") or max - min over the expanded window ("minmax"), stored float32."""
+    from waveformanalysis_b200.dtypes import HIT_DTYPE
+
+    rows = []
+    for k, w in enumerate(waves):
+        w = np.asarray(w, dtype=np.float64)
+        det = -np.diff(w) if use_derivative else (np.float64(meta["baseline"][k]) - w)
+        peaks, lips, rips, _ = find_peaks_1d(det, height=height, threshold=threshold, distance=distance, prominence=prominence, width=width)
+        if len(peaks) == 0:
+            continue
+        if height_method == "diff":
+            d = -np.diff(w)
+            cs = np.concatenate(([0.0], np.cumsum(d, dtype=np.float64)))
+            s = np.clip(np.rint(lips).astype(np.int64), 0, len(d))
+            e = np.clip(np.rint(rips).astype(np.int64), 0, len(d))
+            hts = np.where(e > s, cs[e] - cs[s], 0.0).astype(np.float32)
+        elif height_method == "minmax":
+            hts = np.zeros(len(peaks), dtype=np.float32)
+            for i, (a, b) in enumerate(zip(lips, rips)):
+                s = max(0, int(np.round(a)))
+                e = min(len(w) - 1, int(np.round(b)))
+                win = w[max(0, s - minmax_window_expand):min(len(w), e + minmax_window_expand)]
+                hts[i] = np.max(win) - np.min(win)
+        else:
+            raise ValueError(f"unsupported height_method: {height_method}")
+        dt_ns = int(meta["dt"][k])
+        for p, a, b, h in zip(peaks.tolist(), lips.tolist(), rips.tolist(), hts.tolist()):
+            rows.append((p, h, 0.0, a, b, dt_ns, int(meta["timestamp"][k] + p * (float(dt_ns) * 1e3)), int(meta["board"][k]),
+                         int(meta["channel"][k]), int(meta["record_id"][k])))
+    return np.array(rows, dtype=HIT_DTYPE) if rows else np.zeros(0, dtype=HIT_DTYPE)

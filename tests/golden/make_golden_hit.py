@@ -64,6 +64,19 @@ def main():
                           "width": 2})
     G["pos_deriv"] = run(HitFinderPlugin(), {"records": rp_rec, "wave_pool": rp_pool},
                          {"use_filtered": False, "wave_source": "records", "height": 8.0, "width": 2})
+    # ---------------------------------------------------------------- signal_peaks_stream (streaming plugin, float64 rows)
+    from waveform_analysis.core.plugins.builtin.streaming.cpu.signal_peaks import SignalPeaksStreamPlugin
+
+    def stream(cfg):
+        plugin = SignalPeaksStreamPlugin()
+        plugin.parallel = False
+        chunks = list(plugin.compute(Ctx(cfg, {"filtered_waveforms": stf, "st_waveforms": st}), "run"))
+        rows = np.concatenate([c.data for c in chunks])
+        return rows, np.array([[c.start, c.end] for c in chunks], dtype=np.int64)
+
+    G["stream_default"], G["stream_default_bounds"] = stream({"height": 10.0})
+    G["stream_minmax"], G["stream_minmax_bounds"] = stream({"height": 10.0, "height_method": "minmax", "minmax_window_expand": 3, "width": 2})
+    G["stream_level"], G["stream_level_bounds"] = stream({"use_derivative": False, "height": 25.0, "prominence": 4.0, "width": 3})
     out = os.path.join(HERE, "hit_golden.npz")
     np.savez_compressed(out, **G)
     print("wrote", out, {k: len(v) for k, v in G.items() if v.dtype.names and "position" in v.dtype.names}, os.path.getsize(out) / 1e3, "kB")

@@ -196,3 +196,25 @@ def test_hit_find_peaks_matches_reference():
     for tag, waves, meta, source, kw, want in hit_cases():
         got = O.hit_find_peaks(list(waves), meta, source=source, **kw)
         assert_rows_match(got, want, what=f"hit {tag}", float_exact=("height", "edge_start", "edge_end"))
+
+
+def stream_cases():
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "hit_golden.npz"), allow_pickle=False)
+    rec, fpool = g["records"], g["filtered_pool"]
+    w = fpool.reshape(len(rec), 800)
+    for tag, kw in (("stream_default", {"height": 10.0}),
+                    ("stream_minmax", {"height": 10.0, "height_method": "minmax", "minmax_window_expand": 3, "width": 2}),
+                    ("stream_level", {"use_derivative": False, "height": 25.0, "prominence": 4.0, "width": 3})):
+        yield tag, rec, w, kw, g[tag], g[tag + "_bounds"]
+
+
+def test_stream_find_peaks_matches_reference():
+    """The streaming plugin emits one chunk per channel here (80 records < chunk_size): rows in channel order."""
+    for tag, rec, w, kw, want, _bounds in stream_cases():
+        parts = []
+        for ch in np.unique(rec["channel"]):
+            sel = rec["channel"] == ch
+            parts.append(O.stream_find_peaks(list(w[sel]), rec[sel], **kw))
+        assert_rows_match(np.concatenate(parts), want, what=tag, float_exact=("height", "edge_start", "edge_end"))

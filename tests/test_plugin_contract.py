@@ -12,6 +12,7 @@ import pytest
 from fakes import Ctx
 
 REF = os.environ.get("WFB_REFERENCE_ROOT", "/root/reference")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HAVE_REF = os.path.isdir(os.path.join(REF, "waveform_analysis"))
 
 
@@ -177,3 +178,54 @@ def test_registers_in_a_real_context(tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = subprocess.run([sys.executable, "-c", REAL_CONTEXT_SCRIPT, root, REF, str(tmp_path)], capture_output=True, text=True, timeout=300)
     assert "REAL_CONTEXT_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-3000:]
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference checkout not available")
+def test_streaming_plugin_runs_inside_the_reference_framework():
+    """B200SignalPeaksStreamPlugin subclasses the reference's streaming plugin and only replaces compute_chunk.
+    Here (no GPU) the device call is replaced by the oracle, so the test covers the host glue: the reference's own
+    chunk iterator, executor and result chunks around our compute_chunk must reproduce the reference rows."""
+    code = r"""
+import os, sys
+import numpy as np
+sys.path.insert(0, %(root)r)
+sys.path.insert(0, os.path.join(%(root)r, "tests"))
+sys.path.insert(0, os.path.join(%(root)r, "tests", "golden"))
+from make_golden import Ctx, import_reference
+import_reference()
+from waveform_analysis.core.plugins.builtin.streaming.cpu.signal_peaks import SignalPeaksStreamPlugin
+from waveform_analysis.core.processing.dtypes import create_record_dtype
+from waveform_analysis.core.plugins.builtin.cpu.filtering import create_filtered_waveform_dtype
+from oracle import np_oracle as O
+from waveformanalysis_b200 import ops, plugins as P
+assert issubclass(P.B200SignalPeaksStreamPlugin, SignalPeaksStreamPlugin)
+assert set(P.B200SignalPeaksStreamPlugin.options) == set(SignalPeaksStreamPlugin.options)
+assert P.B200SignalPeaksStreamPlugin.version == SignalPeaksStreamPlugin.version
+
+def fake(st_chunk, filtered_chunk, *, explicit_dt=None, event_offset=0, **kw):
+    return O.stream_find_peaks(list(filtered_chunk["wave"]), st_chunk, **kw)
+ops.find_peaks_stream_chunk = fake
+
+g = np.load(os.path.join(%(root)r, "tests", "golden", "hit_golden.npz"))
+rec, pool, fp = g["records"], g["pool"], g["filtered_pool"]
+n, L = len(rec), 800
+st = np.zeros(n, dtype=create_record_dtype(L))
+for f in ("baseline", "baseline_upstream", "polarity", "timestamp", "record_id", "dt", "event_length", "board", "channel"):
+    st[f] = rec[f]
+st["wave"] = pool.reshape(n, L).view(np.int16)
+stf = np.zeros(n, dtype=create_filtered_waveform_dtype(st.dtype))
+for f in st.dtype.names:
+    if f != "wave":
+        stf[f] = st[f]
+stf["wave"] = fp.reshape(n, L)
+for tag, cfg in (("stream_default", {"height": 10.0}), ("stream_minmax", {"height": 10.0, "height_method": "minmax", "minmax_window_expand": 3, "width": 2})):
+    chunks = list(P.B200SignalPeaksStreamPlugin().compute(Ctx(cfg, {"filtered_waveforms": stf, "st_waveforms": st}), "run"))
+    rows = np.concatenate([c.data for c in chunks])
+    assert rows.tobytes() == g[tag].tobytes(), tag
+    assert np.array_equal(np.array([[c.start, c.end] for c in chunks]), g[tag + "_bounds"])
+print("ok")
+""" % {"root": ROOT}
+    import subprocess
+
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "ok" in res.stdout, res.stderr[-2000:]

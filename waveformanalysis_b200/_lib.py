@@ -112,7 +112,7 @@ class PeakParams(C.Structure):  # wfb_peak_params
                 ("height_method", C.c_int32), ("height_window_extension", C.c_int32), ("lmax", C.c_int32), ("reserved_", C.c_int32)]
 
 
-WAVE_AOS_I16, WAVE_AOS_F32, WAVE_REC_U16, WAVE_REC_F32 = 0, 1, 2, 3
+WAVE_AOS_I16, WAVE_AOS_F32, WAVE_REC_U16, WAVE_REC_F32, WAVE_AOS_F32_AS_F64 = 0, 1, 2, 3, 4
 
 PROTOTYPES = {
     "wfb_last_error": (C.c_char_p, []),

@@ -60,9 +60,10 @@ __device__ __forceinline__ double detection_value(const PeakRec& r, int i) {
             return (double)(short)(-(int)d);
         }
         if (r.kind == WFB_WAVE_AOS_F32) return (double)(-__fsub_rn((float)r.w[i + 1], (float)r.w[i]));
+        if (r.kind == WFB_WAVE_AOS_F32_AS_F64) return -__dsub_rn(r.w[i + 1], r.w[i]);  // streaming: float64 copy of the row
         return __dsub_rn(r.w[i + 1], r.w[i]);  // records: +diff of the float64 signal
     }
-    if (r.kind == WFB_WAVE_AOS_I16 || r.kind == WFB_WAVE_AOS_F32) return __dsub_rn(r.baseline, r.w[i]);
+    if (r.kind == WFB_WAVE_AOS_I16 || r.kind == WFB_WAVE_AOS_F32 || r.kind == WFB_WAVE_AOS_F32_AS_F64) return __dsub_rn(r.baseline, r.w[i]);
     return r.w[i];
 }
 
@@ -84,6 +85,17 @@ struct OffsetSrc {
 __device__ float peak_height(const PeakRec& r, double edge_start, double edge_end, int method, int ext) {
     int s = max(0, (int)rint(edge_start));  // np.round: half to even
     int e = min(r.len - 1, (int)rint(edge_end));
+    if (method == 2) {  // streaming "diff": cumsum(-diff(w)) in float64, clipped rounded edges (signal_peaks.py:370-381)
+        const int max_idx = max(r.len - 1, 0);
+        const int s2 = min(max((int)rint(edge_start), 0), max_idx), e2 = min(max((int)rint(edge_end), 0), max_idx);
+        if (e2 <= s2) return 0.f;
+        double cs = 0.0, at_s = 0.0;
+        for (int j = 0; j < e2; ++j) {
+            if (j == s2) at_s = cs;
+            cs = __dadd_rn(cs, -__dsub_rn(r.w[j + 1], r.w[j]));
+        }
+        return (float)__dsub_rn(cs, at_s);
+    }
     if (method == 1) {  // "diff": sum(diff(-w)[s:e]) in the waveform's own arithmetic
         if (e <= s) return 0.f;
         if (r.kind == WFB_WAVE_AOS_I16) {
@@ -140,7 +152,7 @@ __global__ void __launch_bounds__(kPeakWarps * 32) find_peaks_kernel(const void*
     for (int i = lane; i < len; i += 32) {
         double v;
         if (p.wave_kind == WFB_WAVE_AOS_I16) v = (double)static_cast<const short*>(waves)[off + i];
-        else if (p.wave_kind == WFB_WAVE_AOS_F32) v = (double)static_cast<const float*>(waves)[off + i];
+        else if (p.wave_kind == WFB_WAVE_AOS_F32 || p.wave_kind == WFB_WAVE_AOS_F32_AS_F64) v = (double)static_cast<const float*>(waves)[off + i];
         else {
             const float s = (p.wave_kind == WFB_WAVE_REC_U16) ? (float)static_cast<const unsigned short*>(waves)[off + i]
                                                               : static_cast<const float*>(waves)[off + i];
@@ -151,7 +163,7 @@ __global__ void __launch_bounds__(kPeakWarps * 32) find_peaks_kernel(const void*
     }
     __syncwarp();
     PeakRec r;
-    r.kind = records_src ? WFB_WAVE_REC_U16 : p.wave_kind;
+    r.kind = records_src ? WFB_WAVE_REC_U16 : p.wave_kind;  // both records kinds share the float64 arithmetic
     r.len = len;
     r.deriv = p.use_derivative != 0;
     r.m = r.deriv ? max(len - 1, 0) : len;
@@ -299,8 +311,8 @@ extern "C" int wfb_find_peaks(const void* waves_dev, int64_t waves_len, const wf
     }
     WFB_REQUIRE(meta_dev && workspace_dev && (waves_dev || waves_len == 0), "wfb_find_peaks: NULL pointer");
     WFB_REQUIRE(row_cap == 0 || rows_out_dev != nullptr, "wfb_find_peaks: NULL row buffer");
-    WFB_REQUIRE(params->wave_kind >= WFB_WAVE_AOS_I16 && params->wave_kind <= WFB_WAVE_REC_F32, "wfb_find_peaks: unknown wave_kind");
-    WFB_REQUIRE(params->height_method == 0 || params->height_method == 1, "unsupported height_method");
+    WFB_REQUIRE(params->wave_kind >= WFB_WAVE_AOS_I16 && params->wave_kind <= WFB_WAVE_AOS_F32_AS_F64, "wfb_find_peaks: unknown wave_kind");
+    WFB_REQUIRE(params->height_method >= 0 && params->height_method <= 2, "unsupported height_method");
     WFB_REQUIRE(params->lmax > 0, "wfb_find_peaks: lmax must be the longest record");
     WFB_REQUIRE(workspace_bytes >= wfb_find_peaks_workspace_bytes(n), "wfb_find_peaks: workspace too small");
     const int lcap = (params->lmax + 1) & ~1;

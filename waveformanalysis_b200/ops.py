@@ -502,7 +502,7 @@ def build_records_from_v1725(blobs, names, dt_ns: int):
 # hit = scipy.signal.find_peaks per record
 # --------------------------------------------------------------------------------------------
 def _find_peaks(records: np.ndarray, pool: np.ndarray, kind: int, *, use_derivative=True, height=30.0, distance=2, prominence=0.7,
-                width=4, threshold=None, height_method="minmax", height_window_extension=4) -> np.ndarray:
+                width=4, threshold=None, height_method="minmax", height_window_extension=4, cumsum_diff=False) -> np.ndarray:
     from .dtypes import HIT_DTYPE
 
     lib = _lib.load()
@@ -521,7 +521,8 @@ def _find_peaks(records: np.ndarray, pool: np.ndarray, kind: int, *, use_derivat
     p = _lib.PeakParams(wave_kind=kind, use_derivative=int(bool(use_derivative)), height=float(height), prominence=float(prominence),
                         width=float(width), threshold=float(threshold) if threshold is not None else 0.0,
                         has_threshold=int(threshold is not None), distance=int(distance if distance is not None else 1),
-                        height_method=0 if height_method == "minmax" else 1, height_window_extension=int(height_window_extension),
+                        height_method=0 if height_method == "minmax" else (2 if cumsum_diff else 1),
+                        height_window_extension=int(height_window_extension),
                         lmax=lmax)
     ws = _empty(lib.wfb_find_peaks_workspace_bytes(n))
     total = torch.zeros(1, dtype=torch.int64, device="cuda")
@@ -566,3 +567,48 @@ def find_peaks_waveforms(data: np.ndarray, *, explicit_dt=None, **opts) -> np.nd
         raise NotImplementedError("hit on structured waveforms without a baseline field is not offloaded")
     rec["polarity"] = "unknown"
     return _find_peaks(rec, pool, kind, **opts)
+
+
+def find_peaks_stream_chunk(st_chunk: np.ndarray, filtered_chunk: np.ndarray, *, explicit_dt=None, event_offset=0, use_derivative=True,
+                            height=30.0, distance=2, prominence=0.7, width=4, threshold=None, height_method="diff",
+                            minmax_window_expand=2) -> np.ndarray:
+    """One chunk of signal_peaks_stream (plugins/builtin/streaming/cpu/signal_peaks.py:234-401): metadata from
+    the st_waveforms rows, samples from the filtered rows promoted to float64."""
+    from .aos import structured_as_records
+    from .dtypes import HIT_DTYPE
+
+    n = min(len(st_chunk), len(filtered_chunk))
+    if n == 0:
+        return np.zeros(0, dtype=HIT_DTYPE)
+    st_chunk, filtered_chunk = st_chunk[:n], filtered_chunk[:n]
+    names = st_chunk.dtype.names or ()
+    if filtered_chunk.dtype.names and "wave" in filtered_chunk.dtype.names:
+        rec, pool, _ = structured_as_records(filtered_chunk, explicit_dt=explicit_dt)
+    else:  # plain 2-D array of filtered rows
+        rows = np.ascontiguousarray(filtered_chunk, dtype=np.float32)
+        pool = rows.reshape(-1)
+        rec = np.zeros(n, dtype=RECORDS_DTYPE)
+        rec["wave_offset"] = np.arange(n, dtype=np.int64) * rows.shape[1]
+        rec["event_length"] = rows.shape[1]
+    if pool.dtype != np.float32:
+        pool = pool.astype(np.float32)  # the plugin promotes whatever dtype the rows have to float64; float32 rows are exact
+    rec["timestamp"] = st_chunk["timestamp"]
+    rec["channel"] = st_chunk["channel"]
+    rec["board"] = st_chunk["board"] if "board" in names else 0
+    if "baseline" in names:
+        rec["baseline"] = st_chunk["baseline"]
+    elif not use_derivative:
+        raise NotImplementedError("signal_peaks_stream without a baseline field and use_derivative=False is not offloaded")
+    if "dt" in names:
+        rec["dt"] = st_chunk["dt"]
+    elif explicit_dt is not None:
+        rec["dt"] = int(explicit_dt)
+    else:
+        raise ValueError("[signal_peaks_stream] st_waveforms is missing required field 'dt'; provide explicit config 'dt'.")
+    if np.any(rec["dt"] <= 0):
+        raise ValueError("[signal_peaks_stream] dt must be > 0")
+    rec["record_id"] = st_chunk["record_id"] if "record_id" in names else int(event_offset) + np.arange(n, dtype=np.int64)
+    rec["polarity"] = "unknown"
+    return _find_peaks(rec, pool, _lib.WAVE_AOS_F32_AS_F64, use_derivative=use_derivative, height=height, distance=distance,
+                       prominence=prominence, width=width, threshold=threshold, height_method=height_method,
+                       height_window_extension=minmax_window_expand, cumsum_diff=True)

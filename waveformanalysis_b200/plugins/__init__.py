@@ -10,6 +10,7 @@ from .grouping import B200GroupedEventsPlugin, B200HitGroupedPlugin
 from .hits import B200HitFinderPlugin, B200ThresholdHitPlugin
 from .merge import B200HitMergeClustersPlugin, B200HitMergedComponentsPlugin, B200HitMergePlugin
 from .records import B200RecordsPlugin, B200WavePoolPlugin
+from .streaming import B200SignalPeaksStreamPlugin
 from .widths import B200WaveformWidthIntegralPlugin, B200WaveformWidthPlugin
 
 __all__ = [
@@ -26,4 +27,5 @@ __all__ = [
     "B200GroupedEventsPlugin",
     "B200RecordsPlugin",
     "B200WavePoolPlugin",
+    "B200SignalPeaksStreamPlugin",
 ]

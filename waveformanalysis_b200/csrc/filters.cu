@@ -22,6 +22,34 @@ __device__ __forceinline__ double sample_f64(const T* p, long long i) {
     return (double)(float)p[i];  // reference casts the pool to float32 first (filtering.py:169)
 }
 
+// Interior of the Savitzky-Golay correlation for 8 consecutive outputs of one lane (uint16 pool, record start
+// 16-byte aligned): the 24 samples around the block are loaded as three 16-byte chunks and converted once,
+// the taps sit in registers; the accumulation order (j ascending, multiply then add, no contraction) is the
+// generic loop's, so the bits are the same.
+template <int H>
+__device__ __forceinline__ void sg_block8(const uint16_t* __restrict__ x, int k0, const double* __restrict__ taps, float* __restrict__ y) {
+    constexpr int W = 2 * H + 1;
+    const uint4* c = reinterpret_cast<const uint4*>(x + k0);
+    const uint4 q0 = __ldg(c - 1), q1 = __ldg(c), q2 = __ldg(c + 1);
+    const unsigned raw[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+    double v[24];
+#pragma unroll
+    for (int i = 8 - H; i < 16 + H; ++i) v[i] = (double)(float)((raw[i >> 1] >> ((i & 1) * 16)) & 0xffffu);
+    double t[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) t[j] = taps[j];
+    float out[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < W; ++j) acc = __dadd_rn(acc, __dmul_rn(t[j], v[8 + o - H + j]));
+        out[o] = (float)acc;
+    }
+    *reinterpret_cast<float4*>(y + k0) = make_float4(out[0], out[1], out[2], out[3]);
+    *reinterpret_cast<float4*>(y + k0 + 4) = make_float4(out[4], out[5], out[6], out[7]);
+}
+
 // ---- Savitzky-Golay: one warp per record -----------------------------------------------------
 // table layout (doubles): [0, w) taps (y[k] = sum_j taps[j] * x[k-h+j]); [w, w + h*w) rows of the
 // projector for outputs 0..h-1 over x[0..w); [w + h*w, w + 2*h*w) rows for outputs L-h..L-1 over
@@ -56,7 +84,28 @@ __global__ void __launch_bounds__(256) sg_filter_kernel(const T* __restrict__ po
     const double* taps = tables + toff;
     const double* first = taps + w;
     const double* last = first + (size_t)h * w;
+    // fast interior: blocks of 8 outputs that do not touch the polynomial-fit edges
+    int fast_lo = 0, fast_hi = 0;  // outputs [fast_lo, fast_hi) are written by sg_block8
+    if (sizeof(T) == 2 && h >= 1 && h <= 8 && (off & 7) == 0 && L >= 32) {
+        fast_lo = 8 * ((h + 7) / 8);
+        fast_hi = 8 * ((L - h) / 8);
+        if (fast_hi <= fast_lo) fast_lo = fast_hi = 0;
+        const uint16_t* xs = reinterpret_cast<const uint16_t*>(x);
+        for (int k0 = fast_lo + 8 * lane; k0 < fast_hi; k0 += 256) {
+            switch (h) {
+                case 1: sg_block8<1>(xs, k0, taps, y); break;
+                case 2: sg_block8<2>(xs, k0, taps, y); break;
+                case 3: sg_block8<3>(xs, k0, taps, y); break;
+                case 4: sg_block8<4>(xs, k0, taps, y); break;
+                case 5: sg_block8<5>(xs, k0, taps, y); break;
+                case 6: sg_block8<6>(xs, k0, taps, y); break;
+                case 7: sg_block8<7>(xs, k0, taps, y); break;
+                default: sg_block8<8>(xs, k0, taps, y); break;
+            }
+        }
+    }
     for (int k = lane; k < L; k += 32) {
+        if (k >= fast_lo && k < fast_hi) continue;
         double acc = 0.0;
         if (k >= h && k < L - h) {
             for (int j = 0; j < w; ++j) acc = __dadd_rn(acc, __dmul_rn(taps[j], sample_f64(x, k - h + j)));

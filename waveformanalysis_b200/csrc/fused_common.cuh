@@ -29,6 +29,8 @@ struct FHArgs {
     const long long* hit_base;
     long long* total_out;
     unsigned long long* tile_state;  // [n_tiles] decoupled look-back descriptors
+    unsigned long long* group_desc;  // [n_groups] per 32 tiles: finished tiles << 48 | sum of their hit counts
+    unsigned long long* group_pref;  // [n_groups] status | exclusive prefix of the group's first tile
     unsigned* ticket;                // dynamic tile counter
     int* err_flag;
     int n_tiles;
@@ -154,30 +156,67 @@ __device__ __forceinline__ void hit_row_words(unsigned w[15], int p, int s, int 
 }
 
 
-// decoupled look-back over the tile descriptors: returns the exclusive prefix (first output row) of
-// `tile`; called by one full warp.  `total` is the tile's own hit count.
+// Two-level decoupled look-back: returns the exclusive prefix (first output row) of `tile`; called by one
+// full warp.  `total` is the tile's own hit count.  With a persistent grid every resident block reaches this
+// point at about the same time, so a plain look-back walks over all ~SMs x blocks unresolved predecessors,
+// 32 per L2 round trip.  Here the 32 tiles of a GROUP also add their counts into one group descriptor: a tile
+// first looks at its in-group predecessors (one probe); if none of them holds a prefix yet it takes the
+// group's exclusive prefix from the 32 preceding group descriptors (one more probe reaches 1024 tiles back).
 __device__ __forceinline__ long long tile_lookback(const FHArgs& a, int tile, long long total) {
     const int lane = lane_id();
-    if (lane == 0) st_state(a.tile_state + tile, kStAgg | (unsigned long long)total);
-    long long excl = 0;
-    int look = tile - 1;
-    for (;;) {
-        int idx = look - lane;
-        unsigned long long v;
-        if (idx >= 0) {
-            while (((v = ld_state(a.tile_state + idx)) & kStMask) == 0) __nanosleep(64);  // do not steal issue slots from the streaming warps
-        } else {
-            v = (idx == -1) ? (kStPrefix | (unsigned long long)(a.hit_base ? *a.hit_base : 0)) : kStPrefix;
+    const int g = tile >> 5, r = tile & 31;
+    if (lane == 0) {
+        st_state(a.tile_state + tile, kStAgg | (unsigned long long)total);
+        atomicAdd(a.group_desc + g, (1ull << 48) | (unsigned long long)total);
+    }
+    // ---- in-group predecessors r-1 .. 0 (lane L looks at tile - 1 - L)
+    unsigned long long v = kStPrefix;  // lanes past the group start contribute nothing
+    if (lane < r) {
+        while (((v = ld_state(a.tile_state + tile - 1 - lane)) & kStMask) == 0) __nanosleep(64);  // do not steal issue slots
+    }
+    const unsigned isp = __ballot_sync(kFull, lane < r && (v & kStMask) == kStPrefix);
+    const int first = __ffs(isp) - 1;  // nearest in-group predecessor holding an inclusive prefix
+    long long excl = warp_sum_i64((lane < r && (first < 0 || lane <= first)) ? (long long)(v & ~kStMask) : 0);
+    if (first < 0) {
+        // ---- the group's exclusive prefix: nearest preceding group with a published prefix + complete groups between
+        long long gex = a.hit_base ? *a.hit_base : 0;
+        if (g > 0) {
+            gex = 0;
+            int look = g - 1;
+            for (;;) {
+                const int h = look - lane;
+                unsigned long long pv = 0, dv = 0;
+                bool have_p = false;
+                if (h >= 0) {
+                    const unsigned long long want = 32;  // every group in front of `g` is full
+                    while (((dv = ld_state(a.group_desc + h)) >> 48) < want) {
+                        pv = ld_state(a.group_pref + h);
+                        __nanosleep(64);
+                    }
+                    pv = ld_state(a.group_pref + h);
+                    have_p = (pv & kStMask) == kStPrefix;
+                } else if (h == -1) {
+                    have_p = true;  // in front of group 0: the caller's base
+                    pv = kStPrefix | (unsigned long long)(a.hit_base ? *a.hit_base : 0);
+                }
+                const unsigned gp = __ballot_sync(kFull, have_p);
+                const int gfirst = __ffs(gp) - 1;
+                long long val = 0;
+                if (h >= -1 && (gfirst < 0 || lane <= gfirst)) {
+                    val = (long long)(dv & 0xffffffffffffull);                       // the group's own sum
+                    if (lane == gfirst) val += (long long)(pv & ~kStMask);           // plus everything in front of it
+                }
+                gex += warp_sum_i64(val);
+                if (gfirst >= 0) break;
+                look -= 32;
+            }
         }
-        unsigned isp = __ballot_sync(kFull, (v & kStMask) == kStPrefix);
-        int first = __ffs(isp) - 1;  // nearest predecessor holding an inclusive prefix
-        long long val = (first < 0 || lane <= first) ? (long long)(v & ~kStMask) : 0;
-        excl += warp_sum_i64(val);
-        if (first >= 0) break;
-        look -= 32;
+        if (lane == 0) st_state(a.group_pref + g, kStPrefix | (unsigned long long)gex);
+        excl += gex;
     }
     if (lane == 0) {
         st_state(a.tile_state + tile, kStPrefix | (unsigned long long)(excl + total));
+        if (r == 0) st_state(a.group_pref + g, kStPrefix | (unsigned long long)excl);
         if (tile == a.n_tiles - 1) *a.total_out = excl + total;
     }
     return excl;

@@ -775,16 +775,19 @@ __global__ void max_len_kernel(const wfb_rec_meta* meta, long long n, int* out) 
 }
 
 struct WsLayout {
-    size_t ticket, err, lmax, state, total;
+    size_t ticket, err, lmax, state, gdesc, gpref, total;
 };
 static WsLayout ws_layout(long long n) {
-    long long n_tiles = (n + 127) / 128;  // smallest tile of the kernel variants
+    long long n_tiles = (n + 31) / 32;  // smallest tile of the kernel variants (one warp in the lane-per-record kernel)
     WsLayout w;
     w.ticket = 0;
     w.err = 4;
     w.lmax = 8;
+    const long long n_groups = (n_tiles + 31) / 32 + 1;
     w.state = 64;
-    w.total = 64 + (size_t)n_tiles * 8;
+    w.gdesc = w.state + (size_t)n_tiles * 8;
+    w.gpref = w.gdesc + (size_t)n_groups * 8;
+    w.total = w.gpref + (size_t)n_groups * 8;
     return w;
 }
 
@@ -877,6 +880,8 @@ extern "C" int wfb_features_hits(const void* pool_dev, int64_t pool_len, const w
     a.ticket = reinterpret_cast<unsigned*>(ws + w.ticket);
     a.err_flag = reinterpret_cast<int*>(ws + w.err);
     a.tile_state = reinterpret_cast<unsigned long long*>(ws + w.state);
+    a.group_desc = reinterpret_cast<unsigned long long*>(ws + w.gdesc);
+    a.group_pref = reinterpret_cast<unsigned long long*>(ws + w.gpref);
     a.n_tiles = 0;
     a.slot_bytes = 0;
     a.ring_bytes = 0;

@@ -33,7 +33,10 @@
 
 namespace wfb {
 
-constexpr int kLprWarps = 4;
+#ifndef WFB_LPR_WARPS
+#define WFB_LPR_WARPS 4
+#endif
+constexpr int kLprWarps = WFB_LPR_WARPS;
 constexpr int kLprTile = kLprWarps * 32;  // records per tile / look-back unit
 #ifndef WFB_LPR_ENT
 #define WFB_LPR_ENT 256

@@ -32,6 +32,7 @@ if args.summarise:
     alg = {
         "sg_filter_kernel": n * 6 * L, "bw_filter_kernel": n * 6 * L, "k1_gather_kernel": n * (4 * L + 126),
         "width_integral_kernel": n * (2 * L + 100), "waveform_width_kernel": None,
+        "find_peaks_kernel<0>": n * 4 * L, "find_peaks_kernel<1>": n * 4 * L,
     }
     peak = 6453.7
     print(f"{'kernel':44s} {'launches':>8s} {'total ms':>10s} {'alg GB/s':>10s} {'% of HBM peak':>14s}")
@@ -78,5 +79,8 @@ for f in ("position", "height", "integral", "edge_start", "edge_end", "dt", "tim
 # positive-going copy of the waves so waveform_width keeps its rows (it drops peaks below the baseline)
 waves = (16383 - pool.view(np.int16).reshape(n, L)).astype(np.int16)
 ww = ops.waveform_width(h2, rec["record_id"], waves)
+# hit = find_peaks on the SG-filtered pool (records source) and on the raw rows
+pk = ops.find_peaks_records(rec, sg, height=8.0, width=2)
+pk2 = ops.find_peaks_records(rec, pool, height=12.0, width=2)
 torch.cuda.synchronize()
-print(json.dumps({"records": n, "samples": L, "hits": int(len(hits)), "width_rows": int(len(ww)), "events": int(len(ev["event_id"])) if isinstance(ev, dict) and "event_id" in ev else None}))
+print(json.dumps({"records": n, "samples": L, "hits": int(len(hits)), "width_rows": int(len(ww)), "peaks": int(len(pk)), "events": int(len(ev["event_id"])) if isinstance(ev, dict) and "event_id" in ev else None}))

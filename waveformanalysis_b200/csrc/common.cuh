@@ -68,6 +68,11 @@ __device__ __forceinline__ double warp_max_f64(double v) {
     for (int m = 16; m > 0; m >>= 1) v = fmax(v, shfl_xor_f64(v, m));
     return v;
 }
+__device__ __forceinline__ double warp_min_f64(double v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v = fmin(v, shfl_xor_f64(v, m));
+    return v;
+}
 __device__ __forceinline__ float warp_max_f32(float v) {
 #pragma unroll
     for (int m = 16; m > 0; m >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, m));

@@ -22,34 +22,29 @@ namespace wfb {
 constexpr int kPeakWarps = 4;
 constexpr int kPeakRowBytes = 48;  // HIT_DTYPE
 
-// numpy pairwise summation in float32 (np.sum of a float32 array accumulates in float32)
-template <typename Src>
-__device__ float numpy_pairwise_sum_f32(const Src& x, int off, int n) {
-    if (n < 8) {
-        float res = 0.f;
-        for (int i = 0; i < n; ++i) res = __fadd_rn(res, x(off + i));
-        return res;
+// the record's waveform as the plugin sees it (float64, exact for int16 / float32 sources), read from global
+// memory on demand: only the detection signal is staged in shared memory
+struct Wave {
+    const void* base;
+    long long off;
+    int load_kind;  // params->wave_kind
+    float b32;
+    bool pos;
+    __device__ __forceinline__ double operator[](int i) const {
+        if (load_kind == WFB_WAVE_AOS_I16) return (double)static_cast<const short*>(base)[off + i];
+        if (load_kind == WFB_WAVE_AOS_F32 || load_kind == WFB_WAVE_AOS_F32_AS_F64) return (double)static_cast<const float*>(base)[off + i];
+        const float s = (load_kind == WFB_WAVE_REC_U16) ? (float)static_cast<const unsigned short*>(base)[off + i]
+                                                        : static_cast<const float*>(base)[off + i];
+        // -RecordsView.signals(): signals = f32(w) - f32(b), negated once more for positive pulses (records_view.py:152-169)
+        return pos ? (double)__fsub_rn(s, b32) : (double)__fsub_rn(b32, s);
     }
-    if (n <= 128) {
-        float r[8];
-        for (int k = 0; k < 8; ++k) r[k] = x(off + k);
-        int i;
-        for (i = 8; i < n - (n % 8); i += 8)
-            for (int k = 0; k < 8; ++k) r[k] = __fadd_rn(r[k], x(off + i + k));
-        float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])), __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
-        for (; i < n; ++i) res = __fadd_rn(res, x(off + i));
-        return res;
-    }
-    int n2 = n / 2;
-    n2 -= n2 % 8;
-    return __fadd_rn(numpy_pairwise_sum_f32(x, off, n2), numpy_pairwise_sum_f32(x, off + n2, n - n2));
-}
+};
 
 struct PeakRec {
     int kind, len, m;  // wave kind, samples, detection samples
     bool deriv;
     double baseline;
-    const double* w;   // shared: waveform values
+    Wave w;            // waveform values
     const double* x;   // shared: detection signal
 };
 
@@ -68,17 +63,18 @@ __device__ __forceinline__ double detection_value(const PeakRec& r, int i) {
 }
 
 struct DiffSrcF32 {  // np.diff(-waveform) for a float32 waveform
-    const double* w;
+    Wave w;
     __device__ float operator()(int i) const { return __fsub_rn(-(float)w[i + 1], -(float)w[i]); }
 };
 struct DiffSrcF64 {
-    const double* w;
+    Wave w;
     __device__ double operator()(int i) const { return __dsub_rn(-w[i + 1], -w[i]); }
 };
+template <typename S>
 struct OffsetSrc {
-    DiffSrcF64 s;
+    S s;
     int off;
-    __device__ double operator()(int i) const { return s(off + i); }
+    __device__ auto operator()(int i) const { return s(off + i); }
 };
 
 // peak_finding.py:567-614
@@ -103,8 +99,8 @@ __device__ float peak_height(const PeakRec& r, double edge_start, double edge_en
             for (int i = s; i < e; ++i) acc += (short)((int)(short)(-(int)r.w[i + 1]) - (int)(short)(-(int)r.w[i]));
             return (float)(double)acc;
         }
-        if (r.kind == WFB_WAVE_AOS_F32) return (float)(double)numpy_pairwise_sum_f32(DiffSrcF32{r.w}, s, e - s);
-        return (float)numpy_pairwise_sum(OffsetSrc{DiffSrcF64{r.w}, s}, e - s);
+        if (r.kind == WFB_WAVE_AOS_F32) return numpy_pairwise_sum_t<float>(OffsetSrc<DiffSrcF32>{DiffSrcF32{r.w}, s}, e - s);
+        return (float)numpy_pairwise_sum(OffsetSrc<DiffSrcF64>{DiffSrcF64{r.w}, s}, e - s);
     }
     ext = max(0, ext);
     const int a = max(0, s - ext), b = min(r.len, e + ext);
@@ -126,11 +122,10 @@ __global__ void __launch_bounds__(kPeakWarps * 32) find_peaks_kernel(const void*
     const int warp = threadIdx.x >> 5, lane = lane_id();
     const long long rec = (long long)blockIdx.x * kPeakWarps + warp;
     if (rec >= n) return;
-    // per warp: w[lcap], x[lcap] doubles, peak positions int[lcap/2 + 2], keep flags
-    const size_t per_warp = (size_t)lcap * 16 + (size_t)(lcap / 2 + 2) * 4 + (size_t)(lcap / 2 + 2);
+    // per warp: x[lcap] doubles, peak positions int[lcap/2 + 2], keep flags
+    const size_t per_warp = (size_t)lcap * 8 + (size_t)(lcap / 2 + 2) * 4 + (size_t)(lcap / 2 + 2);
     uint8_t* base = smem + (size_t)warp * ((per_warp + 15) & ~(size_t)15);
-    double* w = reinterpret_cast<double*>(base);
-    double* x = w + lcap;
+    double* x = reinterpret_cast<double*>(base);
     int* peaks = reinterpret_cast<int*>(x + lcap);
     uint8_t* keep = reinterpret_cast<uint8_t*>(peaks + (lcap / 2 + 2));
 
@@ -146,29 +141,14 @@ __global__ void __launch_bounds__(kPeakWarps * 32) find_peaks_kernel(const void*
         if (lane == 0) atomicExch(err, 2);
         len = 0;
     }
-    // ---- stage the waveform as the plugin sees it
     const bool records_src = p.wave_kind == WFB_WAVE_REC_U16 || p.wave_kind == WFB_WAVE_REC_F32;
-    const float b32 = (float)mrec.baseline;
-    for (int i = lane; i < len; i += 32) {
-        double v;
-        if (p.wave_kind == WFB_WAVE_AOS_I16) v = (double)static_cast<const short*>(waves)[off + i];
-        else if (p.wave_kind == WFB_WAVE_AOS_F32 || p.wave_kind == WFB_WAVE_AOS_F32_AS_F64) v = (double)static_cast<const float*>(waves)[off + i];
-        else {
-            const float s = (p.wave_kind == WFB_WAVE_REC_U16) ? (float)static_cast<const unsigned short*>(waves)[off + i]
-                                                              : static_cast<const float*>(waves)[off + i];
-            // -RecordsView.signals(): signals = f32(w) - f32(b), negated once more for positive pulses (records_view.py:152-169)
-            v = (mrec.polarity == WFB_POL_POSITIVE) ? (double)__fsub_rn(s, b32) : (double)__fsub_rn(b32, s);
-        }
-        w[i] = v;
-    }
-    __syncwarp();
     PeakRec r;
     r.kind = records_src ? WFB_WAVE_REC_U16 : p.wave_kind;  // both records kinds share the float64 arithmetic
     r.len = len;
     r.deriv = p.use_derivative != 0;
     r.m = r.deriv ? max(len - 1, 0) : len;
     r.baseline = mrec.baseline;
-    r.w = w;
+    r.w = Wave{waves, off, p.wave_kind, (float)mrec.baseline, mrec.polarity == WFB_POL_POSITIVE};
     r.x = x;
     for (int i = lane; i < r.m; i += 32) x[i] = detection_value(r, i);
     __syncwarp();
@@ -215,47 +195,65 @@ __global__ void __launch_bounds__(kPeakWarps * 32) find_peaks_kernel(const void*
         }
     }
     __syncwarp();
-    // ---- prominence, width, rows: one peak per lane, survivors compacted in order
+    // ---- prominence, width, rows: peaks one after the other, every scan done by the whole warp 32 samples at a
+    // time (the tallest peaks scan the whole record: one lane would walk hundreds of samples alone)
     long long row0 = 0;
     if (EMIT) row0 = row_incl[rec] - counts[rec];
     int nout = 0;
-    for (int q0 = 0; q0 < np; q0 += 32) {
-        const int q = q0 + lane;
-        bool ok = q < np && (keep[q] & 1);
-        int pk = 0;
-        double lip = 0.0, rip = 0.0;
-        if (ok) {
-            pk = peaks[q];
-            const double xp = x[pk];
-            int i = pk, lb = pk, rb = pk;
-            double lmin = xp, rmin = xp;
-            while (i >= 0 && x[i] <= xp) {
-                if (x[i] < lmin) { lmin = x[i]; lb = i; }
-                --i;
-            }
-            i = pk;
-            while (i <= m - 1 && x[i] <= xp) {
-                if (x[i] < rmin) { rmin = x[i]; rb = i; }
-                ++i;
-            }
-            const double prom = __dsub_rn(xp, fmax(lmin, rmin));
-            ok = prom >= p.prominence;
-            if (ok) {
-                const double h = __dsub_rn(xp, __dmul_rn(prom, 0.5));
-                i = pk;
-                while (lb < i && h < x[i]) --i;
-                lip = (double)i;
-                if (x[i] < h) lip = __dadd_rn(lip, __ddiv_rn(__dsub_rn(h, x[i]), __dsub_rn(x[i + 1], x[i])));
-                i = pk;
-                while (i < rb && h < x[i]) ++i;
-                rip = (double)i;
-                if (x[i] < h) rip = __dsub_rn(rip, __ddiv_rn(__dsub_rn(h, x[i]), __dsub_rn(x[i - 1], x[i])));
-                ok = __dsub_rn(rip, lip) >= p.width;
-            }
+    const double kInf = __longlong_as_double(0x7ff0000000000000ll);
+    for (int q = 0; q < np; ++q) {
+        if (!(keep[q] & 1)) continue;
+        const int pk = peaks[q];
+        const double xp = x[pk];
+        // left side: samples pk, pk-1, ... while x <= xp; lowest value, among equals the one nearest to the peak
+        double lmin = kInf;
+        int lidx = -1;
+        for (int hi = pk; hi >= 0; hi -= 32) {
+            const int i = hi - lane;
+            const bool in = i >= 0;
+            const double xi = in ? x[i] : 0.0;
+            const unsigned stop = __ballot_sync(kFull, in && xi > xp);
+            const int nstop = stop ? __ffs(stop) - 1 : 32;  // lanes below nstop are still inside the scan
+            if (in && lane < nstop && xi < lmin) { lmin = xi; lidx = i; }
+            if (stop) break;
         }
-        const unsigned bal = __ballot_sync(kFull, ok);
-        if (EMIT && ok) {
-            const long long row = row0 + nout + __popc(bal & ((1u << lane) - 1u));
+        double rmin = kInf;
+        int ridx = 0x7fffffff;
+        for (int lo = pk; lo <= m - 1; lo += 32) {
+            const int i = lo + lane;
+            const bool in = i <= m - 1;
+            const double xi = in ? x[i] : 0.0;
+            const unsigned stop = __ballot_sync(kFull, in && xi > xp);
+            const int nstop = stop ? __ffs(stop) - 1 : 32;
+            if (in && lane < nstop && xi < rmin) { rmin = xi; ridx = i; }
+            if (stop) break;
+        }
+        // each lane holds the nearest index of its own minimum (it scans away from the peak with a strict <)
+        const double lm = warp_min_f64(lmin), rm = warp_min_f64(rmin);
+        const int lb = __reduce_max_sync(kFull, (lmin == lm) ? lidx : -1);
+        const int rb = __reduce_min_sync(kFull, (rmin == rm) ? ridx : 0x7fffffff);
+        const double prom = __dsub_rn(xp, fmax(lm, rm));
+        if (!(prom >= p.prominence)) continue;
+        // width at half prominence: first sample at or below the level on each side, not beyond the bases
+        const double h = __dsub_rn(xp, __dmul_rn(prom, 0.5));
+        int il = lb;
+        for (int hi = pk; hi > lb; hi -= 32) {
+            const int i = hi - lane;
+            const unsigned stop = __ballot_sync(kFull, i > lb && !(h < x[i]));
+            if (stop) { il = hi - (__ffs(stop) - 1); break; }
+        }
+        int ir = rb;
+        for (int lo = pk; lo < rb; lo += 32) {
+            const int i = lo + lane;
+            const unsigned stop = __ballot_sync(kFull, i < rb && !(h < x[i]));
+            if (stop) { ir = lo + (__ffs(stop) - 1); break; }
+        }
+        double lip = (double)il, rip = (double)ir;
+        if (x[il] < h) lip = __dadd_rn(lip, __ddiv_rn(__dsub_rn(h, x[il]), __dsub_rn(x[il + 1], x[il])));
+        if (x[ir] < h) rip = __dsub_rn(rip, __ddiv_rn(__dsub_rn(h, x[ir]), __dsub_rn(x[ir - 1], x[ir])));
+        if (!(__dsub_rn(rip, lip) >= p.width)) continue;
+        if (EMIT && lane == 0) {
+            const long long row = row0 + nout;
             if (row < row_cap) {
                 const float hgt = peak_height(r, lip, rip, p.height_method, p.height_window_extension);
                 const double step = __dmul_rn((double)mrec.dt, 1e3);
@@ -275,7 +273,7 @@ __global__ void __launch_bounds__(kPeakWarps * 32) find_peaks_kernel(const void*
                 dst[11] = (unsigned)((unsigned long long)mrec.record_id >> 32);
             }
         }
-        nout += __popc(bal);
+        ++nout;
     }
     if (!EMIT && lane == 0) counts[rec] = nout;
 }
@@ -316,9 +314,9 @@ extern "C" int wfb_find_peaks(const void* waves_dev, int64_t waves_len, const wf
     WFB_REQUIRE(params->lmax > 0, "wfb_find_peaks: lmax must be the longest record");
     WFB_REQUIRE(workspace_bytes >= wfb_find_peaks_workspace_bytes(n), "wfb_find_peaks: workspace too small");
     const int lcap = (params->lmax + 1) & ~1;
-    const size_t per_warp = (((size_t)lcap * 16 + (size_t)(lcap / 2 + 2) * 4 + (size_t)(lcap / 2 + 2)) + 15) & ~(size_t)15;
+    const size_t per_warp = (((size_t)lcap * 8 + (size_t)(lcap / 2 + 2) * 4 + (size_t)(lcap / 2 + 2)) + 15) & ~(size_t)15;
     const size_t dyn = per_warp * kPeakWarps;
-    WFB_REQUIRE(dyn <= 220 * 1024, "wfb_find_peaks: records longer than %d samples do not fit the shared-memory staging", 220 * 1024 / 18 / kPeakWarps);
+    WFB_REQUIRE(dyn <= 220 * 1024, "wfb_find_peaks: records longer than %d samples do not fit the shared-memory staging", 220 * 1024 / 11 / kPeakWarps);
     uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
     const size_t m = pk_al256((size_t)n * 8);
     long long* cnt64 = reinterpret_cast<long long*>(ws);

@@ -90,3 +90,90 @@ def test_fused_hits_adversarial(block, monkeypatch):
         got = engine.DeviceRun.from_host(rec, pool).run_to_host(height_range=(2, -1), area_range=(0, None), **kw)
         assert_rows_match(got["hits"], want_h, what=f"seed {seed} hits {kw}", float_exact=FX_HIT)
         assert_rows_match(got["features"], want_f, what=f"seed {seed} features", float_exact=FX_BF)
+
+
+def test_find_peaks_adversarial():
+    """`hit` on plateaus, monotone ramps, peaks at the record edges, equal neighbours and tiny records, all
+    three sources of the plugin, against the oracle's find_peaks restatement (itself pinned to live scipy)."""
+    from oracle import np_oracle as O
+    from waveformanalysis_b200 import ops
+    from waveformanalysis_b200.dtypes import RECORDS_DTYPE, create_record_dtype
+
+    rng = np.random.default_rng(123)
+    fx = ("height", "edge_start", "edge_end")
+    for trial in range(12):
+        n, L = int(rng.integers(1, 40)), int(rng.choice([3, 4, 8, 17, 64, 200]))
+        w = np.full((n, L), 2000, dtype=np.int64)
+        for i in range(n):
+            kind = int(rng.integers(0, 5))
+            if kind == 0:
+                w[i] += np.cumsum(rng.integers(-4, 5, size=L))
+            elif kind == 1:
+                w[i] -= (np.arange(L) // 3) * 7          # descending staircase: plateaus in the derivative
+            elif kind == 2:
+                w[i, : L // 2] -= 300                      # step at the start / middle
+            elif kind == 3:
+                w[i] -= (100 * np.exp(-((np.arange(L) - L / 2) ** 2) / max(L / 3, 1))).astype(np.int64)
+            w[i] += rng.integers(-1, 2, size=L)
+        w = np.clip(w, 0, 16383)
+        st = np.zeros(n, dtype=create_record_dtype(L))
+        st["wave"] = w.astype(np.int16)
+        st["timestamp"] = np.arange(n) * 10**6
+        st["dt"] = 2
+        st["channel"] = rng.integers(0, 3, size=n)
+        st["record_id"] = np.arange(n)
+        st["event_length"] = L
+        st["baseline"] = 2000.25
+        kw = dict(height=float(rng.choice([1.0, 3.0, 10.0])), prominence=float(rng.choice([0.5, 2.0])), width=float(rng.choice([1, 2])),
+                  use_derivative=bool(trial % 2), distance=2)
+        want = O.hit_find_peaks(list(st["wave"]), st, source="aos", **kw)
+        assert_rows_match(ops.find_peaks_waveforms(st, **kw), want, what=f"aos trial {trial}", float_exact=fx)
+        rec = np.zeros(n, dtype=RECORDS_DTYPE)
+        for f in ("timestamp", "dt", "channel", "record_id", "event_length", "baseline"):
+            rec[f] = st[f]
+        rec["wave_offset"] = np.arange(n) * L
+        rec["polarity"] = rng.choice(["unknown", "positive"], size=n)
+        pool = w.astype(np.uint16).reshape(-1)
+        sig = pool.reshape(n, L).astype(np.float32) - rec["baseline"].astype(np.float32)[:, None]
+        waves = [(s if p == "positive" else -s).astype(np.float64) for s, p in zip(sig, rec["polarity"])]
+        want = O.hit_find_peaks(waves, rec, source="records", **kw)
+        assert_rows_match(ops.find_peaks_records(rec, pool, **kw), want, what=f"records trial {trial}", float_exact=fx)
+
+
+def test_fused_hits_signed_rows_adversarial():
+    """int16 structured rows used in place (offset-binary path of the kernel) with negative sample values."""
+    from oracle import np_oracle as O
+    from waveformanalysis_b200 import engine
+    from waveformanalysis_b200.aos import structured_as_records
+    from waveformanalysis_b200.dtypes import create_record_dtype
+
+    rng = np.random.default_rng(77)
+    for trial in range(10):
+        n, L = int(rng.integers(1, 70)), int(rng.choice([8, 16, 40, 96]))
+        st = np.zeros(n, dtype=create_record_dtype(L))
+        base = int(rng.choice([-3000, 0, 12, 9000]))
+        w = base + np.cumsum(rng.integers(-6, 7, size=(n, L)), axis=1)
+        w[:, L // 3: L // 3 + int(rng.integers(1, L // 2))] -= int(rng.integers(5, 60))
+        st["wave"] = np.clip(w, -32768, 32767).astype(np.int16)
+        st["timestamp"] = np.arange(n) * 10**6
+        st["dt"] = 4
+        st["channel"] = rng.integers(0, 4, size=n)
+        st["record_id"] = np.arange(n)
+        st["event_length"] = L
+        st["baseline"] = base + rng.choice([0.0, 0.5, -0.125], size=n)
+        st["polarity"] = "unknown"
+        rec, pool, signed = structured_as_records(st)
+        assert signed
+        kw = dict(threshold=float(rng.choice([2.0, 7.0, 20.0])), left_extension=int(rng.integers(0, 9)), right_extension=int(rng.integers(0, 9)))
+        # oracle on the true (signed) sample values: shift samples and baseline into the uint16 range
+        shift = 32768
+        rec_u = np.zeros(n, dtype=rec.dtype)
+        for f in rec.dtype.names:
+            rec_u[f] = rec[f]
+        rec_u["wave_offset"] = np.arange(n) * L
+        rec_u["baseline"] = rec["baseline"] + shift
+        pool_u = (st["wave"].astype(np.int64) + shift).astype(np.uint16).reshape(-1)
+        want = O.threshold_hits(rec_u, pool_u, **kw)
+        want["height"] = want["height"]  # heights are differences: the shift cancels
+        got = engine.process_host(rec, pool, features=False, signed_samples=True, **kw)["hits"]
+        assert_rows_match(got, want, what=f"signed trial {trial}", float_exact=("width", "rise_time", "fall_time"))

@@ -21,6 +21,12 @@ namespace wfb {
 
 constexpr int kPeakWarps = 4;
 constexpr int kPeakRowBytes = 48;  // HIT_DTYPE
+constexpr int kPeakCache = 6;      // peaks per record the counting pass remembers (position, left / right edge)
+
+struct PeakCacheEnt {  // 24 bytes
+    double lip, rip;
+    int pk, pad_;
+};
 
 // the record's waveform as the plugin sees it (float64, exact for int16 / float32 sources), read from global
 // memory on demand: only the detection signal is staged in shared memory
@@ -117,7 +123,8 @@ __global__ void __launch_bounds__(kPeakWarps * 32) find_peaks_kernel(const void*
                                                                      const wfb_rec_meta* __restrict__ meta, long long n,
                                                                      const wfb_peak_params p, int lcap, int* __restrict__ counts,
                                                                      const long long* __restrict__ row_incl,
-                                                                     uint8_t* __restrict__ rows, long long row_cap, int* __restrict__ err) {
+                                                                     uint8_t* __restrict__ rows, long long row_cap, int* __restrict__ err,
+                                                                     PeakCacheEnt* __restrict__ cache) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = lane_id();
     const long long rec = (long long)blockIdx.x * kPeakWarps + warp;
@@ -150,6 +157,36 @@ __global__ void __launch_bounds__(kPeakWarps * 32) find_peaks_kernel(const void*
     r.baseline = mrec.baseline;
     r.w = Wave{waves, off, p.wave_kind, (float)mrec.baseline, mrec.polarity == WFB_POL_POSITIVE};
     r.x = x;
+    auto write_row = [&](long long row, int pk, double lip, double rip) {
+        const float hgt = peak_height(r, lip, rip, p.height_method, p.height_window_extension);
+        const double step = __dmul_rn((double)mrec.dt, 1e3);
+        const long long ti = (long long)__dadd_rn((double)mrec.timestamp, __dmul_rn((double)pk, step));
+        unsigned* dst = reinterpret_cast<unsigned*>(rows + row * kPeakRowBytes);
+        dst[0] = (unsigned)pk;
+        dst[1] = 0u;
+        dst[2] = __float_as_uint(hgt);
+        dst[3] = 0u;  // integral (always 0.0 in the reference)
+        dst[4] = __float_as_uint((float)lip);
+        dst[5] = __float_as_uint((float)rip);
+        dst[6] = (unsigned)mrec.dt;
+        dst[7] = (unsigned)(ti & 0xffffffffll);
+        dst[8] = (unsigned)((unsigned long long)ti >> 32);
+        dst[9] = ((unsigned)(unsigned short)mrec.board) | ((unsigned)(unsigned short)mrec.channel << 16);
+        dst[10] = (unsigned)(mrec.record_id & 0xffffffffll);
+        dst[11] = (unsigned)((unsigned long long)mrec.record_id >> 32);
+    };
+    if (EMIT) {
+        // the counting pass left up to kPeakCache peaks per record: one lane per peak finishes the row, no re-scan
+        const int c = counts[rec];
+        if (c <= kPeakCache) {
+            if (lane < c) {
+                const PeakCacheEnt e = cache[rec * kPeakCache + lane];
+                const long long row = row_incl[rec] - c + lane;
+                if (row < row_cap) write_row(row, e.pk, e.lip, e.rip);
+            }
+            return;
+        }
+    }
     for (int i = lane; i < r.m; i += 32) x[i] = detection_value(r, i);
     __syncwarp();
 
@@ -254,25 +291,9 @@ __global__ void __launch_bounds__(kPeakWarps * 32) find_peaks_kernel(const void*
         if (!(__dsub_rn(rip, lip) >= p.width)) continue;
         if (EMIT && lane == 0) {
             const long long row = row0 + nout;
-            if (row < row_cap) {
-                const float hgt = peak_height(r, lip, rip, p.height_method, p.height_window_extension);
-                const double step = __dmul_rn((double)mrec.dt, 1e3);
-                const long long ti = (long long)__dadd_rn((double)mrec.timestamp, __dmul_rn((double)pk, step));
-                unsigned* dst = reinterpret_cast<unsigned*>(rows + row * kPeakRowBytes);
-                dst[0] = (unsigned)pk;
-                dst[1] = 0u;
-                dst[2] = __float_as_uint(hgt);
-                dst[3] = 0u;  // integral (always 0.0 in the reference)
-                dst[4] = __float_as_uint((float)lip);
-                dst[5] = __float_as_uint((float)rip);
-                dst[6] = (unsigned)mrec.dt;
-                dst[7] = (unsigned)(ti & 0xffffffffll);
-                dst[8] = (unsigned)((unsigned long long)ti >> 32);
-                dst[9] = ((unsigned)(unsigned short)mrec.board) | ((unsigned)(unsigned short)mrec.channel << 16);
-                dst[10] = (unsigned)(mrec.record_id & 0xffffffffll);
-                dst[11] = (unsigned)((unsigned long long)mrec.record_id >> 32);
-            }
+            if (row < row_cap) write_row(row, pk, lip, rip);
         }
+        if (!EMIT && lane == 0 && nout < kPeakCache) cache[rec * kPeakCache + nout] = PeakCacheEnt{lip, rip, pk, 0};
         ++nout;
     }
     if (!EMIT && lane == 0) counts[rec] = nout;
@@ -294,7 +315,8 @@ static size_t pk_al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 extern "C" size_t wfb_find_peaks_workspace_bytes(int64_t n) {
     const size_t m = pk_al256((size_t)std::max<int64_t>(n, 1) * 8);
-    return 2 * m + pk_al256((size_t)std::max<int64_t>(n, 1) * 4) + scan_workspace_bytes(n) + 512;
+    return 2 * m + pk_al256((size_t)std::max<int64_t>(n, 1) * 4) + scan_workspace_bytes(n) + 1024 +
+           pk_al256((size_t)std::max<int64_t>(n, 1) * kPeakCache * sizeof(PeakCacheEnt));
 }
 
 extern "C" int wfb_find_peaks(const void* waves_dev, int64_t waves_len, const wfb_rec_meta* meta_dev, int64_t n,
@@ -324,20 +346,21 @@ extern "C" int wfb_find_peaks(const void* waves_dev, int64_t waves_len, const wf
     int* counts = reinterpret_cast<int*>(ws + 2 * m);
     int* err = reinterpret_cast<int*>(ws + 2 * m + pk_al256((size_t)n * 4));
     void* scan_ws = ws + 2 * m + pk_al256((size_t)n * 4) + 256;
+    PeakCacheEnt* cache = reinterpret_cast<PeakCacheEnt*>(ws + 2 * m + pk_al256((size_t)n * 4) + 512 + pk_al256(scan_workspace_bytes(n)));
     WFB_CUDA(cudaMemsetAsync(err, 0, 4, st));
     wfb_peak_params p = *params;
     p.distance = (int)std::min<long long>(std::max<long long>(p.distance, 0), 1 << 30);
     const unsigned grid = (unsigned)((n + kPeakWarps - 1) / kPeakWarps);
     WFB_CUDA(cudaFuncSetAttribute(find_peaks_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     WFB_CUDA(cudaFuncSetAttribute(find_peaks_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    find_peaks_kernel<false><<<grid, kPeakWarps * 32, dyn, st>>>(waves_dev, waves_len, meta_dev, n, p, lcap, counts, nullptr, nullptr, 0, err);
+    find_peaks_kernel<false><<<grid, kPeakWarps * 32, dyn, st>>>(waves_dev, waves_len, meta_dev, n, p, lcap, counts, nullptr, nullptr, 0, err, cache);
     peaks_counts_to_i64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(counts, n, cnt64);
     int rc = inclusive_scan_sum_i64(cnt64, incl, n, scan_ws, st);
     if (rc != WFB_OK) return rc;
     peaks_total_kernel<<<1, 32, 0, st>>>(incl, n, reinterpret_cast<long long*>(total_out_dev));
     if (row_cap > 0)
         find_peaks_kernel<true><<<grid, kPeakWarps * 32, dyn, st>>>(waves_dev, waves_len, meta_dev, n, p, lcap, counts, incl,
-                                                                  static_cast<uint8_t*>(rows_out_dev), row_cap, err);
+                                                                  static_cast<uint8_t*>(rows_out_dev), row_cap, err, cache);
     if (counts_out_dev) WFB_CUDA(cudaMemcpyAsync(counts_out_dev, counts, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
     WFB_CUDA(cudaGetLastError());
     int herr = 0;

@@ -263,6 +263,16 @@ int wfb_group_time_window(const int64_t* ts_sorted_dev, int64_t n, double time_w
                           int64_t* event_id_dev, int64_t* n_events_dev, void* workspace_dev,
                           size_t workspace_bytes, void* stream);
 
+/* K1 for records of different lengths (channels / parts with different waveform widths,
+ * records_builder.py:212-302 per part + :870-945 merge): like wfb_build_records, but every record names its
+ * own int16 samples (byte offset into samples_dev + count) and the wave_pool is ragged (wave_offset = running
+ * sum of the lengths in output order).  baselines_in_dev == NULL: mean of samples [bl_start, min(bl_end, len)). */
+int wfb_build_records_ragged(const void* samples_dev, int64_t samples_bytes, const int64_t* sample_offset_dev,
+                             const int32_t* n_samples_dev, const int64_t* timestamp_ps_dev, const int16_t* board_dev,
+                             const int16_t* channel_dev, const double* baselines_in_dev, int64_t n, int32_t dt_ns,
+                             int32_t bl_start, int32_t bl_end, int64_t epoch_ns, void* records_aos_dev, uint16_t* pool_dev,
+                             int64_t pool_len, wfb_rec_meta* meta_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* `hit` = scipy.signal.find_peaks per record (core/plugins/builtin/cpu/peak_finding.py:213-565
  * HitFinderPlugin._compute_peaks / _find_peaks_in_waveform / _calculate_peak_height).
  * wave_kind selects what the plugin calls `waveform` and the detection signal:

@@ -1065,3 +1065,33 @@ def stream_find_peaks(waves, meta, *, use_derivative=True, height=30.0, distance
             rows.append((p, h, 0.0, a, b, dt_ns, int(meta["timestamp"][k] + p * (float(dt_ns) * 1e3)), int(meta["board"][k]),
                          int(meta["channel"][k]), int(meta["record_id"][k])))
     return np.array(rows, dtype=HIT_DTYPE) if rows else np.zeros(0, dtype=HIT_DTYPE)
+
+
+def build_records_ragged(timestamps_ps, boards, channels, sample_blocks, *, dt_ns: int, baseline_window=(0, 40)):
+    """build_records for parts of different waveform widths (records_builder.py:212-302 per part, :870-945
+    merge): same global order, baseline = mean over the window clipped to the row, ragged wave_pool."""
+    ts = np.asarray(timestamps_ps, dtype=np.int64)
+    n = len(ts)
+    rec = np.zeros(n, dtype=RECORDS_DTYPE)
+    rows, base = [], []
+    for blk in sample_blocks:
+        blk = np.asarray(blk)
+        for r in blk:
+            rows.append(r.astype(np.int16).view(np.uint16))
+            win = r[baseline_window[0]:baseline_window[1]]
+            base.append(np.mean(win.astype(np.float64)) if len(win) else np.nan)
+    order = np.lexsort((np.arange(n), np.asarray(channels), np.asarray(boards), np.zeros(n, np.int32), ts))
+    rec["timestamp"] = ts[order]
+    rec["board"] = np.asarray(boards)[order]
+    rec["channel"] = np.asarray(channels)[order]
+    rec["baseline"] = np.asarray(base)[order]
+    rec["baseline_upstream"] = np.nan
+    rec["polarity"] = "unknown"
+    rec["dt"] = dt_ns
+    lens = np.array([len(rows[i]) for i in order.tolist()], dtype=np.int64)
+    rec["event_length"] = lens
+    rec["wave_offset"] = np.cumsum(lens) - lens
+    rec["time"] = rec["timestamp"] // 1000
+    rec["record_id"] = np.arange(n)
+    pool = np.concatenate([rows[i] for i in order.tolist()]) if n else np.zeros(0, dtype=np.uint16)
+    return rec, pool

@@ -64,6 +64,28 @@ def main():
     G["cut_blob0"] = np.frombuffer(cut, dtype=np.uint8)
     G["cut_name0"] = np.array("t_b5_seg0.bin")
     G["cut_records"], G["cut_pool"], G["cut_dt_ns"], G["cut_nfiles"] = bundle.records, bundle.wave_pool, np.array(4), np.array(1)
+    # ---------------------------------------------------------------- VX2730-style parts of different waveform widths
+    from waveform_analysis.core.processing import records_builder as rb
+    from waveform_analysis.utils.formats import get_adapter
+    from waveformanalysis_b200.synth import make_raw_run
+
+    adapter = get_adapter("vx2730")
+    cols = adapter.format_spec.columns
+    parts = []
+    for c, (L, seed) in enumerate(((800, 5), (256, 6), (30, 7))):  # 30 < the 40-sample baseline window
+        raw = make_raw_run(1, 90, L, seed=seed)
+        arr = np.zeros((90, 7 + L), dtype=np.int64)
+        arr[:, cols.board] = c % 2
+        arr[:, cols.channel] = c
+        arr[:, cols.timestamp] = raw["timestamps_ps"] + c
+        arr[:, 7:] = raw["samples"]
+        G[f"rag_ts{c}"], G[f"rag_samples{c}"] = arr[:, cols.timestamp].copy(), raw["samples"].astype(np.int16)
+        parts.append(rb._build_records_part_from_raw_array(
+            arr, channel_idx=c, default_dt_ns=2, cols=cols,
+            normalize_timestamp_to_ps=adapter.format_spec.normalize_timestamp_to_ps, baseline_samples=None))
+    bundle = rb.merge_records_parts(parts)
+    bundle.records["record_id"] = np.arange(len(bundle.records))
+    G["rag_records"], G["rag_pool"] = bundle.records, bundle.wave_pool
     out = os.path.join(HERE, "v1725_golden.npz")
     np.savez_compressed(out, **G)
     print("wrote", out, {k: v.shape for k, v in G.items() if k.endswith("records")}, os.path.getsize(out) / 1e3, "kB")

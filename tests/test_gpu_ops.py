@@ -316,3 +316,14 @@ def test_hit_find_peaks_vs_oracle_ragged_and_plateaus(ops):
         want = O.hit_find_peaks(waves, rec, source="records", **kw)
         assert len(want) > 50
         assert_rows_match(ops.find_peaks_records(rec, pool, **kw), want, what="ragged hit", float_exact=("height", "edge_start", "edge_end"))
+
+
+def test_build_records_ragged_golden(ops):
+    """Parts of different waveform widths (one narrower than the baseline window) against the reference's
+    per-part builder + merge."""
+    from test_oracle_golden import ragged_parts_case
+
+    ts, boards, chans, blocks, want_rec, want_pool = ragged_parts_case()
+    rec, pool = ops.build_records_ragged(ts, boards, chans, blocks, dt_ns=2)
+    assert np.array_equal(pool, want_pool)
+    assert_rows_match(rec, want_rec, what="ragged parts", float_exact=("baseline",))

@@ -218,3 +218,21 @@ def test_stream_find_peaks_matches_reference():
             sel = rec["channel"] == ch
             parts.append(O.stream_find_peaks(list(w[sel]), rec[sel], **kw))
         assert_rows_match(np.concatenate(parts), want, what=tag, float_exact=("height", "edge_start", "edge_end"))
+
+
+def ragged_parts_case():
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "v1725_golden.npz"), allow_pickle=False)
+    blocks = [g[f"rag_samples{c}"] for c in range(3)]
+    ts = np.concatenate([g[f"rag_ts{c}"] for c in range(3)])
+    boards = np.concatenate([np.full(len(b), c % 2, dtype=np.int16) for c, b in enumerate(blocks)])
+    chans = np.concatenate([np.full(len(b), c, dtype=np.int16) for c, b in enumerate(blocks)])
+    return ts, boards, chans, blocks, g["rag_records"], g["rag_pool"]
+
+
+def test_records_from_parts_of_different_widths():
+    ts, boards, chans, blocks, want_rec, want_pool = ragged_parts_case()
+    rec, pool = O.build_records_ragged(ts, boards, chans, blocks, dt_ns=2)
+    assert np.array_equal(pool, want_pool)
+    assert_rows_match(rec, want_rec, what="ragged parts", float_exact=("baseline",))

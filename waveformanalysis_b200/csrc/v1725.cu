@@ -66,9 +66,11 @@ __global__ void __launch_bounds__(256) v1725_gather_kernel(const uint8_t* __rest
                                                           const int* __restrict__ n_samples, const long long* __restrict__ raw_ts,
                                                           const short* __restrict__ board, const short* __restrict__ channel,
                                                           const unsigned short* __restrict__ baseline,
+                                                          const double* __restrict__ baseline_f64,
                                                           const unsigned char* __restrict__ trunc,
                                                           const long long* __restrict__ order, const long long* __restrict__ len_incl,
-                                                          long long n, int dt_ns, long long blob_bytes, long long pool_len,
+                                                          long long n, int dt_ns, long long ts_scale, int bl_start, int bl_end,
+                                                          long long epoch_ns, long long blob_bytes, long long pool_len,
                                                           uint16_t* __restrict__ rows, uint16_t* __restrict__ pool,
                                                           wfb_rec_meta* __restrict__ meta) {
     const int lane = lane_id();
@@ -81,10 +83,22 @@ __global__ void __launch_bounds__(256) v1725_gather_kernel(const uint8_t* __rest
     const uint16_t* in = reinterpret_cast<const uint16_t*>(blob + payload_off[src]);
     uint16_t* out = pool + wave_offset;
     const bool ok = len >= 0 && payload_off[src] >= 0 && payload_off[src] + 2ll * len <= blob_bytes && wave_offset + len <= pool_len;
+    long long bsum = 0;
+    const int be = min(bl_end, len);
     if (ok)
-        for (int j = lane; j < len; j += 32) out[j] = in[j];
-    const long long ts = raw_ts[src] * ((long long)dt_ns * 1000ll);
-    const double bl = (double)baseline[src];
+        for (int j = lane; j < len; j += 32) {
+            const uint16_t v = in[j];
+            out[j] = v;
+            if (j >= bl_start && j < be) bsum += (short)v;
+        }
+    const long long ts = raw_ts[src] * ts_scale;
+    double bl;
+    if (baseline_f64 != nullptr) bl = baseline_f64[src];
+    else if (baseline != nullptr) bl = (double)baseline[src];
+    else {  // mean of the baseline window over the available samples (records_builder.py:243-257): exact integer sum
+        bsum = warp_sum_i64(bsum);
+        bl = (be > bl_start) ? (double)bsum / (double)(be - bl_start) : __longlong_as_double(0x7ff8000000000000ll);
+    }
     if (meta != nullptr && lane == 0) {
         wfb_rec_meta m;
         m.timestamp = ts;
@@ -102,9 +116,11 @@ __global__ void __launch_bounds__(256) v1725_gather_kernel(const uint8_t* __rest
     if (rows != nullptr) {
         long long t = ts / 1000;  // floor division like numpy's //
         if ((ts % 1000) != 0 && ts < 0) --t;
+        t += epoch_ns;
+        const unsigned fl = trunc != nullptr ? (unsigned)trunc[src] : 0u;
         uint16_t* row = rows + r * (kRecordsRowBytes / 2);
-        row[lane] = v1725_row_halfword(lane, ts, board[src], channel[src], bl, r, dt_ns, trunc[src], wave_offset, len, t);
-        if (lane + 32 < 51) row[lane + 32] = v1725_row_halfword(lane + 32, ts, board[src], channel[src], bl, r, dt_ns, trunc[src], wave_offset, len, t);
+        row[lane] = v1725_row_halfword(lane, ts, board[src], channel[src], bl, r, dt_ns, fl, wave_offset, len, t);
+        if (lane + 32 < 51) row[lane + 32] = v1725_row_halfword(lane + 32, ts, board[src], channel[src], bl, r, dt_ns, fl, wave_offset, len, t);
     }
 }
 
@@ -163,21 +179,20 @@ extern "C" size_t wfb_build_records_v1725_workspace_bytes(int64_t n) {
     return 6 * m + radix_sort_workspace_bytes(n) + scan_workspace_bytes(n) + 512;
 }
 
-extern "C" int wfb_build_records_v1725(const uint8_t* blob_dev, int64_t blob_bytes, const int64_t* payload_offset_dev,
-                                       const int32_t* n_samples_dev, const int64_t* timestamp_dev, const int16_t* board_dev,
-                                       const int16_t* channel_dev, const uint16_t* baseline_dev, const uint8_t* trunc_dev, int64_t n,
-                                       int32_t dt_ns, void* records_aos_dev, uint16_t* pool_dev, int64_t pool_len,
-                                       wfb_rec_meta* meta_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
-    WFB_REQUIRE(n >= 0 && blob_bytes >= 0 && pool_len >= 0, "wfb_build_records_v1725: negative size");
+// common device part: sort, ragged offsets, gather
+static int build_records_ragged(const uint8_t* blob_dev, int64_t blob_bytes, const int64_t* payload_offset_dev, const int32_t* n_samples_dev,
+                                const int64_t* timestamp_dev, long long ts_scale, const int16_t* board_dev, const int16_t* channel_dev,
+                                const uint16_t* baseline_u16_dev, const double* baseline_f64_dev, const uint8_t* flags_dev, int64_t n,
+                                int32_t dt_ns, int32_t bl_start, int32_t bl_end, int64_t epoch_ns, void* records_aos_dev, uint16_t* pool_dev,
+                                int64_t pool_len, wfb_rec_meta* meta_dev, void* workspace_dev, size_t workspace_bytes, cudaStream_t st,
+                                const char* who) {
+    WFB_REQUIRE(n >= 0 && blob_bytes >= 0 && pool_len >= 0, "%s: negative size", who);
     if (n == 0) return WFB_OK;
-    WFB_REQUIRE(blob_dev && payload_offset_dev && n_samples_dev && timestamp_dev && board_dev && channel_dev && baseline_dev && trunc_dev &&
-                    workspace_dev,
-                "wfb_build_records_v1725: NULL pointer");
-    WFB_REQUIRE(pool_len == 0 || pool_dev != nullptr, "wfb_build_records_v1725: NULL wave_pool");
-    WFB_REQUIRE(((uintptr_t)blob_dev & 3) == 0, "wfb_build_records_v1725: the stream must be 4-byte aligned");
-    WFB_REQUIRE(dt_ns > 0, "wfb_build_records_v1725: dt_ns must be positive");
-    WFB_REQUIRE(workspace_bytes >= wfb_build_records_v1725_workspace_bytes(n), "wfb_build_records_v1725: workspace too small");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    WFB_REQUIRE(blob_dev && payload_offset_dev && n_samples_dev && timestamp_dev && board_dev && channel_dev && workspace_dev, "%s: NULL pointer", who);
+    WFB_REQUIRE(pool_len == 0 || pool_dev != nullptr, "%s: NULL wave_pool", who);
+    WFB_REQUIRE(((uintptr_t)blob_dev & 1) == 0, "%s: the sample bytes must be 2-byte aligned", who);
+    WFB_REQUIRE(dt_ns > 0, "%s: dt_ns must be positive", who);
+    WFB_REQUIRE(workspace_bytes >= wfb_build_records_v1725_workspace_bytes(n), "%s: workspace too small", who);
     uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
     const size_t m = v_al256((size_t)n * 8);
     unsigned long long* kA = reinterpret_cast<unsigned long long*>(ws);
@@ -193,7 +208,7 @@ extern "C" int wfb_build_records_v1725(const uint8_t* blob_dev, int64_t blob_byt
     v1725_keys_kernel<<<v_nb(n), 256, 0, st>>>(board_dev, channel_dev, n, kA, vA);
     int rc = radix_sort_pairs(kA, vA, kB, vB, n, kKeyUnsigned, sws, sort_bytes, st);
     if (rc != WFB_OK) return rc;
-    v1725_gather_ts_kernel<<<v_nb(n), 256, 0, st>>>(reinterpret_cast<const long long*>(timestamp_dev), vB, n, (long long)dt_ns * 1000ll, kA);
+    v1725_gather_ts_kernel<<<v_nb(n), 256, 0, st>>>(reinterpret_cast<const long long*>(timestamp_dev), vB, n, ts_scale, kA);
     rc = radix_sort_pairs(kA, vB, kB, vA, n, kKeySigned, sws, sort_bytes, st);
     if (rc != WFB_OK) return rc;
     // ragged wave offsets
@@ -202,8 +217,32 @@ extern "C" int wfb_build_records_v1725(const uint8_t* blob_dev, int64_t blob_byt
     if (rc != WFB_OK) return rc;
     v1725_gather_kernel<<<v_nb(n * 32), 256, 0, st>>>(blob_dev, reinterpret_cast<const long long*>(payload_offset_dev), n_samples_dev,
                                                       reinterpret_cast<const long long*>(timestamp_dev), board_dev, channel_dev,
-                                                      baseline_dev, trunc_dev, vA, len_incl, n, dt_ns, blob_bytes, pool_len,
+                                                      baseline_u16_dev, baseline_f64_dev, flags_dev, vA, len_incl, n, dt_ns, ts_scale,
+                                                      bl_start, bl_end, epoch_ns, blob_bytes, pool_len,
                                                       static_cast<uint16_t*>(records_aos_dev), pool_dev, meta_dev);
     WFB_CUDA(cudaGetLastError());
     return WFB_OK;
+}
+
+extern "C" int wfb_build_records_ragged(const void* samples_dev, int64_t samples_bytes, const int64_t* sample_offset_dev,
+                                        const int32_t* n_samples_dev, const int64_t* timestamp_ps_dev, const int16_t* board_dev,
+                                        const int16_t* channel_dev, const double* baselines_in_dev, int64_t n, int32_t dt_ns,
+                                        int32_t bl_start, int32_t bl_end, int64_t epoch_ns, void* records_aos_dev, uint16_t* pool_dev,
+                                        int64_t pool_len, wfb_rec_meta* meta_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+    return build_records_ragged(static_cast<const uint8_t*>(samples_dev), samples_bytes, sample_offset_dev, n_samples_dev, timestamp_ps_dev, 1,
+                                board_dev, channel_dev, nullptr, baselines_in_dev, nullptr, n, dt_ns, bl_start, bl_end, epoch_ns,
+                                records_aos_dev, pool_dev, pool_len, meta_dev, workspace_dev, workspace_bytes,
+                                static_cast<cudaStream_t>(stream), "wfb_build_records_ragged");
+}
+
+extern "C" int wfb_build_records_v1725(const uint8_t* blob_dev, int64_t blob_bytes, const int64_t* payload_offset_dev,
+                                       const int32_t* n_samples_dev, const int64_t* timestamp_dev, const int16_t* board_dev,
+                                       const int16_t* channel_dev, const uint16_t* baseline_dev, const uint8_t* trunc_dev, int64_t n,
+                                       int32_t dt_ns, void* records_aos_dev, uint16_t* pool_dev, int64_t pool_len,
+                                       wfb_rec_meta* meta_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+    WFB_REQUIRE(n == 0 || (baseline_dev && trunc_dev), "wfb_build_records_v1725: NULL pointer");
+    WFB_REQUIRE(n == 0 || ((uintptr_t)blob_dev & 3) == 0, "wfb_build_records_v1725: the stream must be 4-byte aligned");
+    return build_records_ragged(blob_dev, blob_bytes, payload_offset_dev, n_samples_dev, timestamp_dev, (long long)dt_ns * 1000ll, board_dev,
+                                channel_dev, baseline_dev, nullptr, trunc_dev, n, dt_ns, 0, 0, 0, records_aos_dev, pool_dev, pool_len, meta_dev,
+                                workspace_dev, workspace_bytes, static_cast<cudaStream_t>(stream), "wfb_build_records_v1725");
 }

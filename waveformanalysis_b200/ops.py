@@ -45,6 +45,47 @@ def _empty(nbytes: int):
 # --------------------------------------------------------------------------------------------
 # K1: records builder
 # --------------------------------------------------------------------------------------------
+def build_records_ragged(timestamps_ps, boards, channels, sample_blocks, *, dt_ns: int, baseline_window=(0, 40), baselines=None,
+                         epoch_ns: int | None = None):
+    """Like build_records for parts of different waveform widths: ``sample_blocks`` is a list of int16
+    matrices (n_k, L_k) whose rows follow each other in the order of the per-record columns."""
+    lib = _lib.load()
+    torch = _torch()
+    blocks = [np.ascontiguousarray(b) for b in sample_blocks]
+    for b in blocks:
+        if b.dtype not in (np.int16, np.uint16) or b.ndim != 2:
+            raise ValueError(f"sample blocks must be 2-D int16 arrays, got {b.dtype} {b.shape}")
+    n = sum(len(b) for b in blocks)
+    if n == 0:
+        return np.zeros(0, dtype=RECORDS_DTYPE), np.zeros(0, dtype=np.uint16)
+    offs, lens, cursor = [], [], 0
+    for b in blocks:
+        offs.append(cursor + np.arange(len(b), dtype=np.int64) * (b.shape[1] * 2))
+        lens.append(np.full(len(b), b.shape[1], dtype=np.int32))
+        cursor += (b.nbytes + 15) & ~15
+    d_blob = torch.empty(cursor + 16, dtype=torch.uint8, device="cuda")
+    base = 0
+    for b in blocks:
+        if b.nbytes:
+            d_blob[base:base + b.nbytes].copy_(torch.from_numpy(b.view(np.uint8).reshape(-1)))
+        base += (b.nbytes + 15) & ~15
+    off, ln = np.concatenate(offs), np.concatenate(lens)
+    total = int(ln.astype(np.int64).sum())
+    d_off, d_len = _dev(off), _dev(ln)
+    d_ts = _dev(np.asarray(timestamps_ps, dtype=np.int64))
+    d_b = _dev(np.asarray(boards, dtype=np.int16))
+    d_c = _dev(np.asarray(channels, dtype=np.int16))
+    d_bl = _dev(np.asarray(baselines, dtype=np.float64)) if baselines is not None else None
+    rows = _empty(n * 102)
+    pool = torch.empty(total + 16, dtype=torch.int16, device="cuda")[:total]
+    ws = _empty(lib.wfb_build_records_v1725_workspace_bytes(n))
+    _lib.check(lib.wfb_build_records_ragged(_ptr(d_blob), cursor, _ptr(d_off), _ptr(d_len), _ptr(d_ts), _ptr(d_b), _ptr(d_c), _ptr(d_bl), n,
+                                            int(dt_ns), int(baseline_window[0]), int(baseline_window[1]), int(epoch_ns or 0), _ptr(rows),
+                                            _ptr(pool), total, C.c_void_p(0), _ptr(ws), ws.numel(), _stream()), "wfb_build_records_ragged")
+    rec = rows[: n * 102].cpu().numpy().view(RECORDS_DTYPE)
+    return rec, pool.cpu().numpy().view(np.uint16)
+
+
 
 
 def build_records(timestamps_ps, boards, channels, samples, *, dt_ns: int, baseline_window=(0, 40),

@@ -126,10 +126,12 @@ def build_bundle(context: Any, run_id: str, plugin: Plugin):
         bundle = (np.zeros(0, dtype=RECORDS_DTYPE), np.zeros(0, dtype=np.uint16))
     else:
         widths = {s.shape[1] for s in samples}
-        if len(widths) != 1:
-            raise NotImplementedError("records: channels with different record lengths are not built on the B200 in this round")
-        bundle = ops.build_records(np.concatenate(ts), np.concatenate(boards), np.concatenate(chans), np.vstack(samples),
-                                   dt_ns=int(dt_ns), baseline_window=(bl0, bl1))
+        if len(widths) != 1:  # channels with different waveform widths: ragged wave_pool
+            bundle = ops.build_records_ragged(np.concatenate(ts), np.concatenate(boards), np.concatenate(chans), samples,
+                                              dt_ns=int(dt_ns), baseline_window=(bl0, bl1))
+        else:
+            bundle = ops.build_records(np.concatenate(ts), np.concatenate(boards), np.concatenate(chans), np.vstack(samples),
+                                       dt_ns=int(dt_ns), baseline_window=(bl0, bl1))
     _apply_polarity(context, run_id, bundle[0])
     if isinstance(cache, dict):
         cache[key] = bundle

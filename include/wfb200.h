@@ -255,6 +255,14 @@ int wfb_group_hit_windows(const int64_t* timestamp_dev, const int64_t* position_
                           double* abs_end_dev, int64_t* n_events_dev, void* workspace_dev,
                           size_t workspace_bytes, void* stream);
 
+/* The same grouping for caller-provided absolute windows: hit_merged rows merged across records have no sample
+ * window (sample_start / sample_end = -1) and take min / max of their component hits' windows
+ * (event_grouping.py:369-414) - computed by the caller, then grouped here. */
+int wfb_group_abs_windows(const int64_t* timestamp_dev, const double* abs_start_dev, const double* abs_end_dev,
+                          const int32_t* dt_dev, const int64_t* record_id_dev, int64_t n, double time_window_ns,
+                          int64_t* order_dev, int64_t* event_id_dev, int64_t* n_events_dev, void* workspace_dev,
+                          size_t workspace_bytes, void* stream);
+
 /* Anchored fixed-window clustering of time-sorted timestamps.  Replaces
  * _find_cluster_boundaries_numba (event_grouping.py:477-510): cluster k starts at the first
  * timestamp > ts[anchor_k-1] + window.  ts_sorted_dev int64[n] ascending.

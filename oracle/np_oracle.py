@@ -711,9 +711,30 @@ def hit_merge(hits: np.ndarray, *, merge_gap_ns=0.0, max_total_width_ns=10000.0)
 # --------------------------------------------------------------------------------------
 
 
-def group_hit_windows(hits: np.ndarray, time_window_ns: float) -> dict:
-    """Restates group_hit_windows (event_grouping.py:287-471) for rows whose sample windows
-    are valid (no negative edges), as a prefix-max scan.
+def merged_abs_windows(hits, component_rows=None, component_hits=None):
+    """Absolute windows of hit_merged rows; rows merged across records carry sample_start/end = -1 and take
+    min / max of their component hits' windows (event_grouping.py:365-414)."""
+    names = hits.dtype.names
+    sn, en = ("sample_start", "sample_end") if "sample_start" in names else ("edge_start", "edge_end")
+    a0, a1 = hit_abs_windows(hits, sn, en)
+    bad = np.flatnonzero((hits[sn] < 0) | (hits[en] < 0))
+    if len(bad):
+        if component_rows is None or component_hits is None:
+            raise ValueError("component_rows and component_hits are required when hit windows contain invalid edges")
+        c0, c1 = hit_abs_windows(component_hits, "edge_start", "edge_end")
+        idx = component_rows["hit_index"].astype(np.int64)
+        for m in bad.tolist():
+            o, c = int(hits["component_offset"][m]), int(hits["component_count"][m])
+            if c <= 0:
+                raise ValueError(f"missing hit_merged_components rows for hit_merged index {m}")
+            a0[m] = c0[idx[o:o + c]].min()
+            a1[m] = c1[idx[o:o + c]].max()
+    return a0, a1
+
+
+def group_hit_windows(hits: np.ndarray, time_window_ns: float, component_rows=None, component_hits=None) -> dict:
+    """Restates group_hit_windows (event_grouping.py:287-471) as a prefix-max scan; rows without a valid
+    sample window use their components (merged_abs_windows).
 
     Returns dict with per-event arrays (event_id, t_min, t_max, dt_ns, n_hits), ``offsets``
     (n_events+1) and ``members`` (hit indices, event-major, each event ordered by
@@ -725,7 +746,7 @@ def group_hit_windows(hits: np.ndarray, time_window_ns: float) -> dict:
     if nh == 0:
         z = np.zeros(0, dtype=np.int64)
         return dict(event_id=z, t_min=z, t_max=z, dt_ns=np.zeros(0), n_hits=z, offsets=np.zeros(1, np.int64), members=z, event_of_hit=z)
-    a0, a1 = hit_abs_windows(hits, sn, en)
+    a0, a1 = merged_abs_windows(hits, component_rows, component_hits)
     ts = hits["timestamp"].astype(np.int64)
     dtv = hits["dt"].astype(np.int32)
     rid = hits["record_id"].astype(np.int64)

@@ -327,3 +327,15 @@ def test_build_records_ragged_golden(ops):
     rec, pool = ops.build_records_ragged(ts, boards, chans, blocks, dt_ns=2)
     assert np.array_equal(pool, want_pool)
     assert_rows_match(rec, want_rec, what="ragged parts", float_exact=("baseline",))
+
+
+def test_group_hit_windows_cross_record_clusters(ops, golden):
+    """hit_merged rows merged across records (sample window -1): windows from the component hits, then the
+    device grouping; against the reference HitGroupedPlugin (grouping_golden.npz)."""
+    from test_oracle_golden import check_grouping50, grouping50_cases
+
+    mg, cp, h = golden["m50_merged"], golden["m50_components"], golden["hits_thr15"]
+    for w, want in grouping50_cases(golden):
+        check_grouping50(ops.group_hit_windows(mg, w, cp, h), mg, want)
+    with pytest.raises(ValueError):
+        ops.group_hit_windows(mg, 100.0)

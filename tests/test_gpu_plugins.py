@@ -126,6 +126,18 @@ def test_merge_and_grouping_plugins(P, golden):
     assert_rows_match(cl50, golden["m50_clusters"], what="m50 clusters")
     assert_rows_match(mg50, golden["m50_merged"], what="m50 merged", float_exact=("height", "integral", "width", "rise_time", "fall_time"))
     assert len(mg50) < len(mg)
+    # grouping of the chain-merged rows, some of which span two records (windows from the component hits)
+    cp50 = P.B200HitMergedComponentsPlugin().compute(c50, "run")
+    assert_rows_match(cp50, golden["m50_components"], what="m50 components")
+    from test_oracle_golden import grouping50_cases
+
+    for w, want in grouping50_cases(golden):
+        gctx = Ctx({"time_window_ns": w}, {"hit_merged": mg50, "hit_merged_components": cp50, "hit_threshold": h})
+        df = P.B200HitGroupedPlugin().compute(gctx, "run")
+        assert np.array_equal(df["t_min"].to_numpy(), want["t_min"]) and np.array_equal(df["t_max"].to_numpy(), want["t_max"])
+        assert np.array_equal(df["n_hits"].to_numpy(), want["n_hits"])
+        assert np.array_equal(np.concatenate([np.asarray(v, np.int64) for v in df["record_ids"]]), want["record_ids"])
+        assert np.array_equal(np.concatenate([np.asarray(v, np.int64) for v in df["sample_starts"]]), want["sample_starts"])
     for wname, w in (("w100", 100.0), ("w0", 0.0)):
         ctx.config = {"time_window_ns": w}
         df = P.B200HitGroupedPlugin().compute(ctx, "run")

@@ -2,6 +2,7 @@
 (tests/golden/make_golden.py).  Integer fields bit-exact; floats rel 1e-5 / abs 1e-3."""
 
 import numpy as np
+import pytest
 
 from conftest import assert_rows_match
 from oracle import np_oracle as O
@@ -236,3 +237,29 @@ def test_records_from_parts_of_different_widths():
     rec, pool = O.build_records_ragged(ts, boards, chans, blocks, dt_ns=2)
     assert np.array_equal(pool, want_pool)
     assert_rows_match(rec, want_rec, what="ragged parts", float_exact=("baseline",))
+
+
+def grouping50_cases(golden):
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "grouping_golden.npz"), allow_pickle=False)
+    for wname, w in (("w100", 100.0), ("w0", 0.0), ("w5000", 5000.0)):
+        yield w, {k[len(f"hg50_{wname}_"):]: g[k] for k in g.files if k.startswith(f"hg50_{wname}_")}
+
+
+def check_grouping50(ev, mg, want):
+    m = ev["members"]
+    assert np.array_equal(ev["t_min"], want["t_min"]) and np.array_equal(ev["t_max"], want["t_max"])
+    assert np.array_equal(ev["n_hits"], want["n_hits"])
+    assert np.array_equal(mg["record_id"][m], want["record_ids"]) and np.array_equal(mg["timestamp"][m], want["timestamps"])
+    assert np.array_equal(mg["channel"][m].astype(np.int64), want["channels"])
+    assert np.array_equal(mg["sample_start"][m].astype(np.int64), want["sample_starts"])
+
+
+def test_grouping_of_cross_record_merged_hits(golden):
+    mg, cp, h = golden["m50_merged"], golden["m50_components"], golden["hits_thr15"]
+    assert (mg["sample_start"] < 0).any()
+    for w, want in grouping50_cases(golden):
+        check_grouping50(O.group_hit_windows(mg, w, cp, h), mg, want)
+    with pytest.raises(ValueError):
+        O.group_hit_windows(mg, 100.0)

@@ -228,22 +228,10 @@ extern "C" size_t wfb_group_workspace_bytes(int64_t n) {
     return 6 * m + radix_sort_workspace_bytes(n) + scan_workspace_bytes(n) + 512;
 }
 
-extern "C" int wfb_group_hit_windows(const int64_t* timestamp_dev, const int64_t* position_dev, const int32_t* start_dev,
-                                     const int32_t* end_dev, const int32_t* dt_dev, const int64_t* record_id_dev,
-                                     int64_t n, double time_window_ns, int64_t* order_dev, int64_t* event_id_dev,
-                                     double* abs_start_dev, double* abs_end_dev, int64_t* n_events_dev, void* workspace_dev,
-                                     size_t workspace_bytes, void* stream) {
-    WFB_REQUIRE(n >= 0, "wfb_group_hit_windows: negative n");
-    WFB_REQUIRE(time_window_ns >= 0, "time_window_ns must be >= 0");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (n == 0) {
-        if (n_events_dev) WFB_CUDA(cudaMemsetAsync(n_events_dev, 0, 8, st));
-        return WFB_OK;
-    }
-    WFB_REQUIRE(timestamp_dev && position_dev && start_dev && end_dev && dt_dev && record_id_dev && order_dev && event_id_dev &&
-                    abs_start_dev && abs_end_dev && n_events_dev && workspace_dev,
-                "wfb_group_hit_windows: NULL pointer");
-    WFB_REQUIRE(workspace_bytes >= wfb_group_workspace_bytes(n), "wfb_group_hit_windows: workspace too small");
+// sort by (abs_start, dt, timestamp, record_id), running maximum of the window ends, boundary flags, event ids
+static int group_from_abs_windows(const int64_t* timestamp_dev, const int32_t* dt_dev, const int64_t* record_id_dev, int64_t n,
+                                  double time_window_ns, int64_t* order_dev, int64_t* event_id_dev, const double* abs_start_dev,
+                                  const double* abs_end_dev, int64_t* n_events_dev, void* workspace_dev, cudaStream_t st) {
     uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
     const size_t m = al256((size_t)n * 8);
     unsigned long long* kA = reinterpret_cast<unsigned long long*>(ws);
@@ -258,8 +246,6 @@ extern "C" int wfb_group_hit_windows(const int64_t* timestamp_dev, const int64_t
     const long long* ts = reinterpret_cast<const long long*>(timestamp_dev);
     const long long* rid = reinterpret_cast<const long long*>(record_id_dev);
     long long* order = reinterpret_cast<long long*>(order_dev);
-    k4_abs_windows_kernel<<<nb(n), 256, 0, st>>>(ts, reinterpret_cast<const long long*>(position_dev), start_dev, end_dev, dt_dev, n,
-                                                 abs_start_dev, abs_end_dev);
     // order = lexsort((record_id, timestamp, dt, abs_start)): four stable passes, least significant first
     iota_kernel<<<nb(n), 256, 0, st>>>(vA, n);
     gather_i64_kernel<<<nb(n), 256, 0, st>>>(rid, vA, n, kA);
@@ -285,6 +271,46 @@ extern "C" int wfb_group_hit_windows(const int64_t* timestamp_dev, const int64_t
                                                  reinterpret_cast<long long*>(n_events_dev));
     WFB_CUDA(cudaGetLastError());
     return WFB_OK;
+}
+
+extern "C" int wfb_group_hit_windows(const int64_t* timestamp_dev, const int64_t* position_dev, const int32_t* start_dev,
+                                     const int32_t* end_dev, const int32_t* dt_dev, const int64_t* record_id_dev,
+                                     int64_t n, double time_window_ns, int64_t* order_dev, int64_t* event_id_dev,
+                                     double* abs_start_dev, double* abs_end_dev, int64_t* n_events_dev, void* workspace_dev,
+                                     size_t workspace_bytes, void* stream) {
+    WFB_REQUIRE(n >= 0, "wfb_group_hit_windows: negative n");
+    WFB_REQUIRE(time_window_ns >= 0, "time_window_ns must be >= 0");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (n == 0) {
+        if (n_events_dev) WFB_CUDA(cudaMemsetAsync(n_events_dev, 0, 8, st));
+        return WFB_OK;
+    }
+    WFB_REQUIRE(timestamp_dev && position_dev && start_dev && end_dev && dt_dev && record_id_dev && order_dev && event_id_dev &&
+                    abs_start_dev && abs_end_dev && n_events_dev && workspace_dev,
+                "wfb_group_hit_windows: NULL pointer");
+    WFB_REQUIRE(workspace_bytes >= wfb_group_workspace_bytes(n), "wfb_group_hit_windows: workspace too small");
+    k4_abs_windows_kernel<<<nb(n), 256, 0, st>>>(reinterpret_cast<const long long*>(timestamp_dev), reinterpret_cast<const long long*>(position_dev),
+                                                 start_dev, end_dev, dt_dev, n, abs_start_dev, abs_end_dev);
+    return group_from_abs_windows(timestamp_dev, dt_dev, record_id_dev, n, time_window_ns, order_dev, event_id_dev, abs_start_dev, abs_end_dev,
+                                  n_events_dev, workspace_dev, st);
+}
+
+extern "C" int wfb_group_abs_windows(const int64_t* timestamp_dev, const double* abs_start_dev, const double* abs_end_dev,
+                                     const int32_t* dt_dev, const int64_t* record_id_dev, int64_t n, double time_window_ns,
+                                     int64_t* order_dev, int64_t* event_id_dev, int64_t* n_events_dev, void* workspace_dev,
+                                     size_t workspace_bytes, void* stream) {
+    WFB_REQUIRE(n >= 0, "wfb_group_abs_windows: negative n");
+    WFB_REQUIRE(time_window_ns >= 0, "time_window_ns must be >= 0");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (n == 0) {
+        if (n_events_dev) WFB_CUDA(cudaMemsetAsync(n_events_dev, 0, 8, st));
+        return WFB_OK;
+    }
+    WFB_REQUIRE(timestamp_dev && abs_start_dev && abs_end_dev && dt_dev && record_id_dev && order_dev && event_id_dev && n_events_dev && workspace_dev,
+                "wfb_group_abs_windows: NULL pointer");
+    WFB_REQUIRE(workspace_bytes >= wfb_group_workspace_bytes(n), "wfb_group_abs_windows: workspace too small");
+    return group_from_abs_windows(timestamp_dev, dt_dev, record_id_dev, n, time_window_ns, order_dev, event_id_dev, abs_start_dev, abs_end_dev,
+                                  n_events_dev, workspace_dev, st);
 }
 
 extern "C" int wfb_group_time_window(const int64_t* ts_sorted_dev, int64_t n, double time_window_ns, int64_t* event_id_dev,

@@ -324,9 +324,10 @@ def width_integral(records: np.ndarray, pool: np.ndarray, *, q_low=0.10, q_high=
 # --------------------------------------------------------------------------------------------
 
 
-def group_hit_windows(hits: np.ndarray, time_window_ns: float) -> dict:
-    """Chain clustering of absolute hit windows (event_grouping.py:287-471) for rows with valid
-    sample windows.  The sort, running maximum, boundary flags and event ids are computed on the
+def group_hit_windows(hits: np.ndarray, time_window_ns: float, component_rows=None, component_hits=None) -> dict:
+    """Chain clustering of absolute hit windows (event_grouping.py:287-471).  Rows merged across records
+    (sample window -1) take their window from the component hits (``hit_merged_components`` rows +
+    ``hit_threshold``), a small host reduction; everything after the windows runs on the device.  The sort, running maximum, boundary flags and event ids are computed on the
     device; the per-event member ordering (a small lexsort) and the ragged packaging stay on the
     host.  Returns the same dict as the oracle."""
     lib = _lib.load()
@@ -339,18 +340,42 @@ def group_hit_windows(hits: np.ndarray, time_window_ns: float) -> dict:
     if nh == 0:
         z = np.zeros(0, dtype=np.int64)
         return dict(event_id=z, t_min=z, t_max=z, dt_ns=np.zeros(0), n_hits=z, offsets=np.zeros(1, np.int64), members=z, event_of_hit=z)
-    d_ts, d_pos = _dev(hits["timestamp"].astype(np.int64)), _dev(hits["position"].astype(np.int64))
-    d_s, d_e = _dev(hits[sn].astype(np.int32)), _dev(hits[en].astype(np.int32))
+    d_ts = _dev(hits["timestamp"].astype(np.int64))
     d_dt, d_rid = _dev(hits["dt"].astype(np.int32)), _dev(hits["record_id"].astype(np.int64))
     order = torch.empty(nh, dtype=torch.int64, device="cuda")
     ev = torch.empty(nh, dtype=torch.int64, device="cuda")
-    a0 = torch.empty(nh, dtype=torch.float64, device="cuda")
-    a1 = torch.empty(nh, dtype=torch.float64, device="cuda")
     n_ev = torch.zeros(1, dtype=torch.int64, device="cuda")
     ws = _empty(lib.wfb_group_workspace_bytes(nh))
-    _lib.check(lib.wfb_group_hit_windows(_ptr(d_ts), _ptr(d_pos), _ptr(d_s), _ptr(d_e), _ptr(d_dt), _ptr(d_rid), nh, float(time_window_ns),
-                                         _ptr(order), _ptr(ev), _ptr(a0), _ptr(a1), _ptr(n_ev), _ptr(ws), ws.numel(), _stream()),
-               "wfb_group_hit_windows")
+    bad = np.flatnonzero((hits[sn] < 0) | (hits[en] < 0))
+    if len(bad):
+        if component_rows is None or component_hits is None:
+            raise ValueError("component_rows and component_hits are required when hit windows contain invalid edges")
+        dt_ps = hits["dt"].astype(np.float64) * 1e3
+        pos = hits["position"].astype(np.float64)
+        h0 = hits["timestamp"].astype(np.float64) + (hits[sn].astype(np.int32) - pos) * dt_ps
+        h1 = hits["timestamp"].astype(np.float64) + (hits[en].astype(np.int32) - pos) * dt_ps
+        cdt = component_hits["dt"].astype(np.float64) * 1e3
+        cpos = component_hits["position"].astype(np.float64)
+        c0 = component_hits["timestamp"].astype(np.float64) + (component_hits["edge_start"].astype(np.int32) - cpos) * cdt
+        c1 = component_hits["timestamp"].astype(np.float64) + (component_hits["edge_end"].astype(np.int32) - cpos) * cdt
+        idx = component_rows["hit_index"].astype(np.int64)
+        for m in bad.tolist():  # a handful of rows: clusters that straddle two records
+            o, c = int(hits["component_offset"][m]), int(hits["component_count"][m])
+            if c <= 0:
+                raise ValueError(f"missing hit_merged_components rows for hit_merged index {m}")
+            h0[m] = c0[idx[o:o + c]].min()
+            h1[m] = c1[idx[o:o + c]].max()
+        a0, a1 = _dev(h0), _dev(h1)
+        _lib.check(lib.wfb_group_abs_windows(_ptr(d_ts), _ptr(a0), _ptr(a1), _ptr(d_dt), _ptr(d_rid), nh, float(time_window_ns), _ptr(order),
+                                             _ptr(ev), _ptr(n_ev), _ptr(ws), ws.numel(), _stream()), "wfb_group_abs_windows")
+    else:
+        d_pos = _dev(hits["position"].astype(np.int64))
+        d_s, d_e = _dev(hits[sn].astype(np.int32)), _dev(hits[en].astype(np.int32))
+        a0 = torch.empty(nh, dtype=torch.float64, device="cuda")
+        a1 = torch.empty(nh, dtype=torch.float64, device="cuda")
+        _lib.check(lib.wfb_group_hit_windows(_ptr(d_ts), _ptr(d_pos), _ptr(d_s), _ptr(d_e), _ptr(d_dt), _ptr(d_rid), nh, float(time_window_ns),
+                                             _ptr(order), _ptr(ev), _ptr(a0), _ptr(a1), _ptr(n_ev), _ptr(ws), ws.numel(), _stream()),
+                   "wfb_group_hit_windows")
     event_of_hit = ev.cpu().numpy()
     abs0, abs1 = a0.cpu().numpy(), a1.cpu().numpy()
     n_events = int(n_ev.item())

@@ -59,10 +59,11 @@ class B200HitGroupedPlugin(Plugin):
                 h[n] = hits[n]
             h["dt"] = dt_scalar
             hits = h
-        if np.any((hits[sn] < 0) | (hits[en] < 0)):
-            raise NotImplementedError("hit_merged rows that span several records (merge_gap_ns > 0) are not grouped on the B200 "
-                                      "in this round")
-        ev = ops.group_hit_windows(hits, time_window_ns)
+        comp_rows = comp_hits = None
+        if np.any((hits[sn] < 0) | (hits[en] < 0)):  # clusters merged across records: windows from the component hits
+            comp_rows = context.get_data(run_id, "hit_merged_components")
+            comp_hits = context.get_data(run_id, "hit_threshold")
+        ev = ops.group_hit_windows(hits, time_window_ns, comp_rows, comp_hits)
         m, off = ev["members"], ev["offsets"]
         return pd.DataFrame({
             "event_id": ev["event_id"], "t_min": ev["t_min"], "t_max": ev["t_max"], "dt/ns": ev["dt_ns"],

@@ -895,7 +895,7 @@ int launch_lpr(FHArgs a, int flags, cudaStream_t st) {
             cuuint32_t box[2] = {(cuuint32_t)(a.slot_bytes / 2), 32};
             cuuint32_t estr[2] = {1, 1};
             CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(a.pool), dims, strides, box, estr,
-                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             have_tmap = (cr == CUDA_SUCCESS) ? 1 : 0;
         }

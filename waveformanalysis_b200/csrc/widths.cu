@@ -193,12 +193,36 @@ struct ChargeSrc {
     float b32;
     int mode;  // 0: unknown polarity (b - w in f64), 1: negative known (b32 - w in f32), 2: positive known,
                // 3: raw positive (w - b in f64; st_waveforms branch, waveform_width_integral.py:187-191)
+    // one 16-byte chunk of the pool is kept in registers: a thread walks its record sequentially, so it issues
+    // one load per 8 (uint16) / 4 (float32) samples instead of one per sample (32 sectors per warp load)
+    const uint4* chunks;   // pool aligned down to 16 bytes
+    long long first;       // element index of w[0] relative to `chunks`
+    mutable long long cached;
+    mutable uint4 q;
+    __device__ __forceinline__ T sample(int i) const {
+        constexpr int PER = 16 / (int)sizeof(T);
+        const long long e = first + i;
+        const long long c = e / PER;
+        if (c != cached) {
+            q = __ldg(chunks + c);
+            cached = c;
+        }
+        const int k = (int)(e % PER);
+        if (sizeof(T) == 2) {
+            const unsigned word = (k < 4) ? ((k < 2) ? q.x : q.y) : ((k < 6) ? q.z : q.w);
+            const unsigned short h = (unsigned short)(word >> ((k & 1) * 16));
+            return *reinterpret_cast<const T*>(&h);
+        }
+        const unsigned word = (k < 2) ? ((k < 1) ? q.x : q.y) : ((k < 3) ? q.z : q.w);
+        return *reinterpret_cast<const T*>(&word);
+    }
     __device__ __forceinline__ double operator()(int i) const {
+        const T wi = sample(i);
         double sig;
-        if (mode == 0) sig = __dsub_rn(b, (double)w[i]);
-        else if (mode == 1) sig = (double)__fsub_rn(b32, (float)w[i]);
-        else if (mode == 2) sig = (double)__fsub_rn((float)w[i], b32);
-        else sig = __dsub_rn((double)w[i], b);
+        if (mode == 0) sig = __dsub_rn(b, (double)wi);
+        else if (mode == 1) sig = (double)__fsub_rn(b32, (float)wi);
+        else if (mode == 2) sig = (double)__fsub_rn((float)wi, b32);
+        else sig = __dsub_rn((double)wi, b);
         return fmax(sig, 0.0);
     }
 };
@@ -216,6 +240,15 @@ __global__ void __launch_bounds__(128) width_integral_kernel(const T* __restrict
     if (L < 0 || off < 0 || off + L > pool_len) L = 0;
     ChargeSrc<T> x;
     x.w = pool + off;
+    {
+        constexpr int PER = 16 / (int)sizeof(T);
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(pool + off);
+        x.chunks = reinterpret_cast<const uint4*>(addr & ~(uintptr_t)15);
+        x.first = (long long)((addr & 15) / sizeof(T));
+        x.cached = -1;
+        x.q = make_uint4(0u, 0u, 0u, 0u);
+        (void)PER;
+    }
     x.b = m.baseline;
     x.b32 = (float)m.baseline;
     x.mode = m.polarity == WFB_POL_NEGATIVE ? 1 : (m.polarity == WFB_POL_POSITIVE ? 2 : (m.polarity == WFB_POL_RAW_POSITIVE ? 3 : 0));

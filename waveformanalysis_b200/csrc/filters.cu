@@ -185,10 +185,24 @@ __global__ void __launch_bounds__(128) bw_filter_kernel(const T* __restrict__ po
             z0[s] = s < ns ? __dmul_rn(cfg.zi[s][0], x0) : 0.0;
             z1[s] = s < ns ? __dmul_rn(cfg.zi[s][1], x0) : 0.0;
         }
+        // inputs do not depend on the filter state: they are fetched kPre steps ahead so that the global-memory
+        // latency overlaps the (serial) cascade instead of stalling every step
+        constexpr int kPre = 4;
+        double pre[kPre];
+#pragma unroll
+        for (int k = 0; k < kPre; ++k) pre[k] = ext(min(k, n_ext - 1));
         double v = 0.0;
-        for (int t = 0; t < n_ext; ++t) {
-            v = cascade(ext(t));
-            scratch[(size_t)t * n_threads + tid] = v;
+        for (int t0 = 0; t0 < n_ext; t0 += kPre) {
+#pragma unroll
+            for (int k = 0; k < kPre; ++k) {
+                const int t = t0 + k;
+                const double in = pre[k];
+                pre[k] = ext(min(t + kPre, n_ext - 1));
+                if (t < n_ext) {
+                    v = cascade(in);
+                    scratch[(size_t)t * n_threads + tid] = v;
+                }
+            }
         }
         const double y0 = v;  // last forward output
 #pragma unroll
@@ -196,9 +210,19 @@ __global__ void __launch_bounds__(128) bw_filter_kernel(const T* __restrict__ po
             z0[s] = s < ns ? __dmul_rn(cfg.zi[s][0], y0) : 0.0;
             z1[s] = s < ns ? __dmul_rn(cfg.zi[s][1], y0) : 0.0;
         }
-        for (int t = n_ext - 1; t >= 0; --t) {
-            v = cascade(scratch[(size_t)t * n_threads + tid]);
-            if (t >= edge && t < edge + L) y[t - edge] = (float)v;
+#pragma unroll
+        for (int k = 0; k < kPre; ++k) pre[k] = scratch[(size_t)max(n_ext - 1 - k, 0) * n_threads + tid];
+        for (int t0 = n_ext - 1; t0 >= 0; t0 -= kPre) {
+#pragma unroll
+            for (int k = 0; k < kPre; ++k) {
+                const int t = t0 - k;
+                const double in = pre[k];
+                pre[k] = scratch[(size_t)max(t - kPre, 0) * n_threads + tid];
+                if (t >= 0) {
+                    v = cascade(in);
+                    if (t >= edge && t < edge + L) y[t - edge] = (float)v;
+                }
+            }
         }
     }
 }

@@ -169,6 +169,9 @@ __device__ __forceinline__ long long tile_lookback(const FHArgs& a, int tile, lo
         st_state(a.tile_state + tile, kStAgg | (unsigned long long)total);
         atomicAdd(a.group_desc + g, (1ull << 48) | (unsigned long long)total);
     }
+    // a tile without hits has no rows to place: it publishes its (zero) count and does not wait for its prefix
+    // (the last tile still resolves it, it reports the grand total)
+    if (total == 0 && tile != a.n_tiles - 1) return 0;
     // ---- in-group predecessors r-1 .. 0 (lane L looks at tile - 1 - L)
     unsigned long long v = kStPrefix;  // lanes past the group start contribute nothing
     if (lane < r) {

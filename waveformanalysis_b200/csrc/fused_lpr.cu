@@ -377,6 +377,7 @@ __device__ __forceinline__ void lpr_stream(const FHArgs& a, const uint16_t* pool
     // aggregate of the FULL chunks in front of chunk 4b-1 and of chunk 4b
     unsigned am_key = 0xffffffffu, am_n = 0u, am_sw = 0u, a0_key = 0xffffffffu, a0_n = 0u, a0_sw = 0u;
     int qn = 0;  // queued items (warp-uniform)
+    bool quiet_hint = false;  // the previous block produced no item in any lane (warp-uniform)
 
     auto issue = [&](int s) {
         const int b = s % kNBuf;
@@ -546,6 +547,8 @@ __device__ __forceinline__ void lpr_stream(const FHArgs& a, const uint16_t* pool
             ChunkSum c0s, c1s, c2s, c3s;
             bool fast = vc0 >= wholeA && vc0 + 4 <= wholeB && !(HITS && r.degen);
             if (FEAT) fast = fast && vc0 >= plainA && vc0 + 4 <= plainB && (vc0 + 4 <= plainHa || vc0 >= plainHb);
+            const bool warp_fast = HITS && __all_sync(kFull, fast);
+            bool step_skipped = false;  // warp-uniform
             if (fast) {
                 uint4 q0 = *reinterpret_cast<const uint4*>(buf + pos0 * 16);
                 uint4 q1 = *reinterpret_cast<const uint4*>(buf + pos0 * 16 + 16);
@@ -566,10 +569,25 @@ __device__ __forceinline__ void lpr_stream(const FHArgs& a, const uint16_t* pool
                 const unsigned s0 = csum4(q0), s1 = csum4(q1), s2 = csum4(q2), s3 = csum4(q3);
                 if (FEAT) { feat_plain(q0, s0); feat_plain(q1, s1); feat_plain(q2, s2); feat_plain(q3, s3); }
                 if (HITS) {
-                    class_whole(q0, vc0, s0, c0s);
-                    class_whole(q1, vc0 + 1, s1, c1s);
-                    class_whole(q2, vc0 + 2, s2, c2s);
-                    class_whole(q3, vc0 + 3, s3, c3s);
+                    // after a block without items, first ask whether ANY lane of the warp has a sample above threshold
+                    // in these 32 samples or a run coming in: if not, the whole hit bookkeeping of the block is skipped
+                    if (warp_fast && quiet_hint) {
+                        const unsigned mn2 = __vimin3_u16x2(
+                            __vimin3_u16x2(__vimin3_u16x2(q0.x, q0.y, q0.z), __vimin3_u16x2(q0.w, q1.x, q1.y), __vimin3_u16x2(q1.z, q1.w, q2.x)),
+                            __vimin3_u16x2(__vimin3_u16x2(q2.y, q2.z, q2.w), __vimin3_u16x2(q3.x, q3.y, q3.z), q3.w), 0xffffffffu);
+                        const unsigned mx2 = __vimax3_u16x2(
+                            __vimax3_u16x2(__vimax3_u16x2(q0.x, q0.y, q0.z), __vimax3_u16x2(q0.w, q1.x, q1.y), __vimax3_u16x2(q1.z, q1.w, q2.x)),
+                            __vimax3_u16x2(__vimax3_u16x2(q2.y, q2.z, q2.w), __vimax3_u16x2(q3.x, q3.y, q3.z), q3.w), 0u);
+                        const int wmin = (int)min(mn2 & 0xffffu, mn2 >> 16), wmax = (int)max(mx2 & 0xffffu, mx2 >> 16);
+                        const int kvmin = (int)((unsigned)(r.positive ? wmax : wmin) ^ xm16);
+                        step_skipped = !__any_sync(kFull, kvmin <= r.kmax || (Fm | Im | Lm) != 0u);
+                    }
+                    if (!step_skipped) {
+                        class_whole(q0, vc0, s0, c0s);
+                        class_whole(q1, vc0 + 1, s1, c1s);
+                        class_whole(q2, vc0 + 2, s2, c2s);
+                        class_whole(q3, vc0 + 3, s3, c3s);
+                    }
                 }
             } else {
                 chunk_generic(buf, pos0, vc0, c0s);
@@ -577,7 +595,11 @@ __device__ __forceinline__ void lpr_stream(const FHArgs& a, const uint16_t* pool
                 chunk_generic(buf, pos0 + 2, vc0 + 2, c2s);
                 chunk_generic(buf, pos0 + 3, vc0 + 3, c3s);
             }
-            if (HITS) {
+            if (HITS && step_skipped) {
+                // four QUIET chunks and nothing carried in: no items, the carries stay empty
+                am_key = 0xffffffffu; am_n = 0u; am_sw = 0u;
+                a0_key = 0xffffffffu; a0_n = 0u; a0_sw = 0u;
+            } else if (HITS) {
                 Fm |= (c0s.f << 2) | (c1s.f << 3) | (c2s.f << 4) | (c3s.f << 5);
                 Im |= (c0s.i << 2) | (c1s.i << 3) | (c2s.i << 4) | (c3s.i << 5);
                 Lm |= (c0s.l << 2) | (c1s.l << 3) | (c2s.l << 4) | (c3s.l << 5);
@@ -593,9 +615,11 @@ __device__ __forceinline__ void lpr_stream(const FHArgs& a, const uint16_t* pool
                 // chunks 4b-1 .. 4b+2 (bits 1..4): an item is a non-FULL chunk that holds, follows or precedes samples above threshold
                 unsigned pend = ~Fm & (Im | (Lm << 1) | (Fm >> 1)) & 0x1eu;
                 const bool last_step = (s == nseg - 1) && (t == tend - 1);
+                bool first_iter = true;
                 for (;;) {
                     const bool want = pend != 0u;
                     const unsigned bal = __ballot_sync(kFull, want);
+                    if (first_iter) { quiet_hint = bal == 0u; first_iter = false; }
                     const int np = __popc(bal);
                     if (qn + np > kQCap || (bal == 0u && last_step && qn > 0)) {
                         lpr_round(ws, qn, r, a, sink);

@@ -31,6 +31,9 @@ struct FHArgs {
     unsigned long long* tile_state;  // [n_tiles] decoupled look-back descriptors
     unsigned long long* group_desc;  // [n_groups] per 32 tiles: finished tiles << 48 | sum of their hit counts
     unsigned long long* group_pref;  // [n_groups] status | exclusive prefix of the group's first tile
+    uint4* gpool;                    // hit entries of the lane-per-record kernel: [block][warp][2][gpool_cap] (L2 resident)
+    int gpool_cap;
+    int gpool_blocks;                // blocks the pool area was sized for
     unsigned* ticket;                // dynamic tile counter
     int* err_flag;
     int n_tiles;
@@ -162,15 +165,20 @@ __device__ __forceinline__ void hit_row_words(unsigned w[15], int p, int s, int 
 // 32 per L2 round trip.  Here the 32 tiles of a GROUP also add their counts into one group descriptor: a tile
 // first looks at its in-group predecessors (one probe); if none of them holds a prefix yet it takes the
 // group's exclusive prefix from the 32 preceding group descriptors (one more probe reaches 1024 tiles back).
-__device__ __forceinline__ long long tile_lookback(const FHArgs& a, int tile, long long total) {
+// publish the tile's own hit count (aggregate): never waits
+__device__ __forceinline__ void tile_publish(const FHArgs& a, int tile, long long total) {
+    if (lane_id() == 0) {
+        st_state(a.tile_state + tile, kStAgg | (unsigned long long)total);
+        atomicAdd(a.group_desc + (tile >> 5), (1ull << 48) | (unsigned long long)total);
+    }
+}
+
+// resolve the exclusive prefix of a tile that has been published; publishes its inclusive prefix
+__device__ __forceinline__ long long tile_resolve(const FHArgs& a, int tile, long long total) {
     const int lane = lane_id();
     const int g = tile >> 5, r = tile & 31;
-    if (lane == 0) {
-        st_state(a.tile_state + tile, kStAgg | (unsigned long long)total);
-        atomicAdd(a.group_desc + g, (1ull << 48) | (unsigned long long)total);
-    }
-    // a tile without hits has no rows to place: it publishes its (zero) count and does not wait for its prefix
-    // (the last tile still resolves it, it reports the grand total)
+    // a tile without hits has no rows to place: it does not wait for its prefix (the last tile still resolves
+    // it, it reports the grand total)
     if (total == 0 && tile != a.n_tiles - 1) return 0;
     // ---- in-group predecessors r-1 .. 0 (lane L looks at tile - 1 - L)
     unsigned long long v = kStPrefix;  // lanes past the group start contribute nothing
@@ -223,6 +231,11 @@ __device__ __forceinline__ long long tile_lookback(const FHArgs& a, int tile, lo
         if (tile == a.n_tiles - 1) *a.total_out = excl + total;
     }
     return excl;
+}
+
+__device__ __forceinline__ long long tile_lookback(const FHArgs& a, int tile, long long total) {
+    tile_publish(a, tile, total);
+    return tile_resolve(a, tile, total);
 }
 
 __device__ __forceinline__ long long bcast_i64(long long v, int src) {

@@ -775,8 +775,12 @@ __global__ void max_len_kernel(const wfb_rec_meta* meta, long long n, int* out) 
 }
 
 struct WsLayout {
-    size_t ticket, err, lmax, state, gdesc, gpref, total;
+    size_t ticket, err, lmax, state, gdesc, gpref, total;  // total: end of the part that is cleared per call
+    size_t gpool, end;
+    int gpool_blocks;
 };
+constexpr int kPoolCap = 512;        // hits per warp per tile kept for the deferred row pass (16 B each)
+constexpr int kPoolBlocksMax = 640;  // resident blocks of the lane-per-record kernel the pool is sized for
 static WsLayout ws_layout(long long n) {
     long long n_tiles = (n + 31) / 32;  // smallest tile of the kernel variants (one warp in the lane-per-record kernel)
     WsLayout w;
@@ -788,6 +792,10 @@ static WsLayout ws_layout(long long n) {
     w.gdesc = w.state + (size_t)n_tiles * 8;
     w.gpref = w.gdesc + (size_t)n_groups * 8;
     w.total = w.gpref + (size_t)n_groups * 8;
+    // hit pool of the lane-per-record kernel: [block][4 warps][2 halves][kPoolCap] entries, never cleared
+    w.gpool = (w.total + 255) & ~(size_t)255;
+    w.gpool_blocks = (int)std::min<long long>(kPoolBlocksMax, (n + 127) / 128);
+    w.end = w.gpool + (size_t)w.gpool_blocks * 4 * 2 * kPoolCap * 16;
     return w;
 }
 
@@ -835,7 +843,7 @@ using namespace wfb;
 
 extern "C" size_t wfb_features_hits_workspace_bytes(int64_t n) {
     if (n < 0) n = 0;
-    return ws_layout(n).total + 64;
+    return ws_layout(n).end + 64;
 }
 
 extern "C" int wfb_features_hits(const void* pool_dev, int64_t pool_len, const wfb_rec_meta* meta_dev, int64_t n,
@@ -854,6 +862,7 @@ extern "C" int wfb_features_hits(const void* pool_dev, int64_t pool_len, const w
     WFB_REQUIRE(((uintptr_t)pool_dev & 15) == 0, "wfb_features_hits: pool_dev must be 16-byte aligned");
     WFB_REQUIRE(((uintptr_t)meta_dev & 15) == 0, "wfb_features_hits: meta_dev must be 16-byte aligned");
     WFB_REQUIRE(workspace_bytes >= wfb_features_hits_workspace_bytes(n), "wfb_features_hits: workspace too small");
+    WFB_REQUIRE(((uintptr_t)workspace_dev & 15) == 0, "wfb_features_hits: workspace_dev must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (n == 0) {
         if (flags & WFB_DO_HITS) {
@@ -882,6 +891,9 @@ extern "C" int wfb_features_hits(const void* pool_dev, int64_t pool_len, const w
     a.tile_state = reinterpret_cast<unsigned long long*>(ws + w.state);
     a.group_desc = reinterpret_cast<unsigned long long*>(ws + w.gdesc);
     a.group_pref = reinterpret_cast<unsigned long long*>(ws + w.gpref);
+    a.gpool = reinterpret_cast<uint4*>(ws + w.gpool);
+    a.gpool_cap = kPoolCap;
+    a.gpool_blocks = w.gpool_blocks;
     a.n_tiles = 0;
     a.slot_bytes = 0;
     a.ring_bytes = 0;

@@ -38,13 +38,10 @@ namespace wfb {
 #endif
 constexpr int kLprWarps = WFB_LPR_WARPS;
 constexpr int kLprTile = kLprWarps * 32;  // records per tile / look-back unit
-#ifndef WFB_LPR_ENT
-#define WFB_LPR_ENT 256
-#endif
 #ifndef WFB_LPR_MINBLOCKS
 #define WFB_LPR_MINBLOCKS 3  // blocks per SM the register allocation must allow
 #endif
-constexpr int kLprEnt = WFB_LPR_ENT;              // staged hits per warp per tile (8 per record on average)
+static_assert(WFB_LPR_WARPS <= 4, "the workspace's hit pool is sized for four warps per block");
 constexpr int kHist = 2;                  // chunks of history in front of each segment
 constexpr int kMaxExt = 8;                // extensions must fit the neighbouring chunk
 constexpr int kNBuf = 2;                  // slot buffers per lane
@@ -73,6 +70,14 @@ struct FeatState {  // per-lane feature accumulators
     double dsum;
 };
 
+struct DefLane {  // what phase B needs of a record once its registers are gone
+    long long ts, rid;
+    double b;
+    int len, dt;
+    unsigned bc;
+    unsigned rel_pos;  // first row of the record relative to the tile's first row << 1 | positive
+};
+
 struct WarpHits {  // per-warp shared memory of the hit machinery
     uint4 q_nb[2][32];     // the round's scratch: chunks P-1 and P+1 of lane t's item
     uint4 q_hdr[kQCap];    // owner | (P + 1) << 5 ; aggregate key, samples, sum of the FULL chunks in front
@@ -80,9 +85,11 @@ struct WarpHits {  // per-warp shared memory of the hit machinery
     uint4 carry[32];       // the same, per owner, across rounds
     int stage_n[32];       // runs started by this round's items
     int carry_n[32];       // runs started so far, per owner
-    LprEnt ent[kLprEnt];
+    DefLane def[32];       // row data of the tile whose rows are still to be written (deferred phase B)
     int pool_cnt;
     unsigned ovf;  // owners whose hits did not all fit the pool
+    int def_used;          // pooled hits / overflow owners of the deferred tile
+    unsigned def_ovf;
 };
 
 __device__ __forceinline__ int u16_at(const uint4& q, int j) {
@@ -108,16 +115,31 @@ __device__ __forceinline__ void hit_values(int kbest, unsigned cnt, unsigned sw,
     integral = (float)integ;
 }
 
+// L2 policy of the hit pool: it is written and read back one tile later, so it should stay in L2 (evict
+// last) instead of being pushed out to HBM by the streaming samples and fetched again
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void st_pool(uint4* dst, const uint4 v, unsigned long long policy) {
+    asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(policy)
+                 : "memory");
+}
+
 // ---- hit sinks ---------------------------------------------------------------------------------
-struct PoolSink {
+struct PoolSink {  // hits of the tile being streamed: the warp's half of its L2-resident pool
     WarpHits* ws;
+    uint4* ent;
     int cap;
     __device__ __forceinline__ void prepare(int, const LaneRec&) {}
     __device__ __forceinline__ void store(int p, int s, int e, int kbest, unsigned cnt, unsigned sw, int ord, int owner, const FHArgs&) {
         int idx = atomicAdd(&ws->pool_cnt, 1);
         if (idx < cap) {
-            *reinterpret_cast<uint4*>(&ws->ent[idx]) = make_uint4((unsigned)p | ((unsigned)s << 16), (unsigned)e | ((unsigned)owner << 16) | ((unsigned)ord << 21),
-                                                                  (unsigned)kbest | (cnt << 16), sw);
+            st_pool(ent + idx,
+                    make_uint4((unsigned)p | ((unsigned)s << 16), (unsigned)e | ((unsigned)owner << 16) | ((unsigned)ord << 21),
+                               (unsigned)kbest | (cnt << 16), sw),
+                    l2_policy_evict_last());
         } else {
             atomicOr(&ws->ovf, 1u << owner);
         }
@@ -330,6 +352,7 @@ struct Ring {
 };
 
 __device__ __forceinline__ void tma_tensor2d_g2s(void* dst_smem, const CUtensorMap* tmap, int x, int y, unsigned long long* bar) {
+    // (no evict-first hint here: with the 256-byte L2 promotion it made HBM re-fetch the promoted sectors, 2.6 x the reads)
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
                      smem_u32(dst_smem)),
                  "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar))
@@ -656,8 +679,11 @@ __global__ void __launch_bounds__(kLprWarps * 32, WFB_LPR_MINBLOCKS) lpr_kernel(
     extern __shared__ __align__(128) uint8_t dyn_smem[];  // [warp][kNBuf][lane] slots of a.slot_bytes
     __shared__ __align__(16) WarpHits s_hits[HITS ? kLprWarps : 1];
     __shared__ long long s_wtot[kLprWarps];
-    __shared__ long long s_wbase[kLprWarps];
+    __shared__ long long s_base[2];  // first row of the deferred tile / of this tile when it is finished at once
+    __shared__ long long s_total;
+    __shared__ int s_woff[kLprWarps];  // the warps' first rows relative to the tile's
     __shared__ int s_tile;
+    __shared__ unsigned s_ovf_any;
     __shared__ __align__(8) unsigned long long s_bar[kLprWarps * kNBuf];
 
     const int warp = threadIdx.x >> 5, lane = lane_id();
@@ -677,15 +703,55 @@ __global__ void __launch_bounds__(kLprWarps * 32, WFB_LPR_MINBLOCKS) lpr_kernel(
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
+    // Rows are written one tile late: a tile publishes its hit count as soon as it has been streamed, the
+    // block goes on to stream its next tile, and only then resolves the first tile's output offset (by then
+    // the predecessors have published) and writes its rows from the pool.  The pool is double buffered and
+    // lives in global memory (it never leaves L2); what phase B needs of the records stays in ws.def.
+    uint4* const gp = HITS ? a.gpool + (size_t)(blockIdx.x * kLprWarps + warp) * 2 * (size_t)a.gpool_cap : nullptr;
+    int cur = 0;
+    bool pend = false;  // block-uniform: the previous tile's rows are still to be written
+    int p_tile = 0;
+    long long p_total = 0;
+    const int c_bias = a.p.signed_samples ? 32768 : 0;
+    auto phase_b = [&](const uint4* ent, const long long base) {  // one pooled hit per lane -> packed row
+        const int used = ws.def_used;
+        const unsigned ovf = ws.def_ovf;
+        for (int e0 = 0; e0 < used; e0 += 32) {
+            const int e = e0 + lane;
+            if (e < used) {
+                const uint4 h = __ldcg(ent + e);
+                const int owner = (int)((h.y >> 16) & 31u);
+                const DefLane d = ws.def[owner];
+                const long long row = base + (long long)(d.rel_pos >> 1) + (long long)(h.y >> 21);
+                if (!((ovf >> owner) & 1u) && row < a.hit_cap) {
+                    RowRec rr;
+                    rr.ts = d.ts; rr.rid = d.rid; rr.len = d.len; rr.dt = d.dt; rr.bc = d.bc;
+                    float height, integral;
+                    hit_values((int)(h.z & 0xffffu), h.z >> 16, h.w, (d.rel_pos & 1u) != 0, d.b, c_bias, height, integral);
+                    unsigned w[15];
+                    hit_row_words(w, (int)(h.x & 0xffffu), (int)(h.x >> 16), (int)(h.y & 0xffffu), height, integral, rr,
+                                  a.p.left_extension, a.p.right_extension, a.lmax);
+                    unsigned* dst = reinterpret_cast<unsigned*>(a.hit_out + row * kHitRowBytes);
+#pragma unroll
+                    for (int k = 0; k < 15; ++k) dst[k] = w[k];
+                }
+            }
+        }
+    };
+
     for (;;) {
-        if (threadIdx.x == 0) s_tile = (int)atomicAdd(a.ticket, 1u);
+        if (threadIdx.x == 0) {
+            s_tile = (int)atomicAdd(a.ticket, 1u);
+            s_ovf_any = 0u;
+        }
         __syncthreads();
         const int tile = s_tile;
-        if (tile >= a.n_tiles) break;
+        const bool valid = tile < a.n_tiles;
+        if (!valid && !(HITS && pend)) break;  // a last pass without records writes the deferred rows
 
         // ---------------- per-lane bookkeeping
         const long long rec = (long long)tile * kLprTile + warp * 32 + lane;
-        const bool have = rec < a.n;
+        const bool have = valid && rec < a.n;
         LaneRec r;
         r.off = 0; r.ts = 0; r.rid = 0; r.len = 0; r.dt = 1; r.pol = 0; r.bc = 0;
         r.b_rec = 0.0; r.b_feat = 0.0; r.thr = a.p.threshold;
@@ -754,7 +820,7 @@ __global__ void __launch_bounds__(kLprWarps * 32, WFB_LPR_MINBLOCKS) lpr_kernel(
             if (lane == 0) { ws.pool_cnt = 0; ws.ovf = 0u; }
         }
         __syncwarp();
-        PoolSink psink{&ws, ent_cap};
+        PoolSink psink{&ws, gp + (size_t)cur * a.gpool_cap, ent_cap};
         lpr_stream<FEAT, HITS, SGN>(a, pool, r, sc, ring, p0, p1, c0, c1, fs, ws, psink);
 
         // ---------------- features of my record
@@ -821,6 +887,7 @@ __global__ void __launch_bounds__(kLprWarps * 32, WFB_LPR_MINBLOCKS) lpr_kernel(
             if (lane >= d) incl += t;
         }
         if (lane == 31) s_wtot[warp] = incl;
+        if (lane == 0 && ws.ovf != 0u) s_ovf_any = 1u;
         __syncthreads();
         if (warp == 0) {
             long long c = (lane < kLprWarps) ? s_wtot[lane] : 0;
@@ -831,52 +898,59 @@ __global__ void __launch_bounds__(kLprWarps * 32, WFB_LPR_MINBLOCKS) lpr_kernel(
                 if (lane >= d) wincl += t;
             }
             const long long total = bcast_i64(wincl, kLprWarps - 1);
-            const long long excl = tile_lookback(a, tile, total);
-            if (lane < kLprWarps) s_wbase[lane] = excl + (wincl - c);
+            if (lane < kLprWarps) s_woff[lane] = (int)(wincl - c);
+            if (valid) tile_publish(a, tile, total);  // never waits
+            if (pend) {
+                const long long excl = tile_resolve(a, p_tile, p_total);
+                if (lane == 0) s_base[0] = excl;
+            }
+            if (valid && s_ovf_any != 0u) {  // a pool overflowed: this tile is finished before the next one starts
+                const long long excl = tile_resolve(a, tile, total);
+                if (lane == 0) s_base[1] = excl;
+            }
+            if (lane == 0) s_total = total;
         }
         __syncthreads();
 
-        // ---------------- phase B: one pooled hit per lane -> packed row
-        const long long my_row0 = s_wbase[warp] + (incl - my_cnt);
-        const unsigned ovf = ws.ovf;
-        const int used = min(ws.pool_cnt, ent_cap);
-        for (int e0 = 0; e0 < used; e0 += 32) {
-            const int e = e0 + lane;
-            const bool act = e < used;
-            LprEnt h;
-            *reinterpret_cast<uint4*>(&h) = *reinterpret_cast<const uint4*>(&ws.ent[act ? e : 0]);
-            const int owner = (int)((h.eo >> 16) & 31u);
-            RowRec rr;
-            rr.ts = bcast_i64(r.ts, owner);
-            rr.rid = bcast_i64(r.rid, owner);
-            rr.len = __shfl_sync(kFull, r.len, owner);
-            rr.dt = __shfl_sync(kFull, r.dt, owner);
-            rr.bc = __shfl_sync(kFull, r.bc, owner);
-            const double o_b = shfl_f64(r.b_rec, owner);
-            const bool o_pos = __shfl_sync(kFull, (int)r.positive, owner) != 0;
-            const long long row = bcast_i64(my_row0, owner) + (long long)(h.eo >> 21);
-            if (act && !((ovf >> owner) & 1u) && row < a.hit_cap) {
-                float height, integral;
-                hit_values((int)(h.kc & 0xffffu), h.kc >> 16, h.sw, o_pos, o_b, r.bias, height, integral);
-                unsigned w[15];
-                hit_row_words(w, (int)(h.ps & 0xffffu), (int)(h.ps >> 16), (int)(h.eo & 0xffffu), height, integral, rr,
-                              a.p.left_extension, a.p.right_extension, a.lmax);
-                unsigned* dst = reinterpret_cast<unsigned*>(a.hit_out + row * kHitRowBytes);
-#pragma unroll
-                for (int k = 0; k < 15; ++k) dst[k] = w[k];
+        // ---------------- phase B of the PREVIOUS tile, from the other half of the pool
+        if (pend) phase_b(gp + (size_t)(cur ^ 1) * a.gpool_cap, s_base[0]);
+        __syncwarp();
+        // ---------------- this tile's row data replaces it
+        const int rel = s_woff[warp] + (incl - my_cnt);
+        {
+            DefLane d;
+            d.ts = r.ts; d.rid = r.rid; d.b = r.b_rec; d.len = r.len; d.dt = r.dt; d.bc = r.bc;
+            d.rel_pos = ((unsigned)rel << 1) | (r.positive ? 1u : 0u);
+            ws.def[lane] = d;
+            if (lane == 0) {
+                ws.def_used = min(ws.pool_cnt, ent_cap);
+                ws.def_ovf = ws.ovf;
             }
         }
-        if (ovf) {  // some records' hits did not all fit the pool: stream those again, rows go straight out
-            __syncwarp();
-            ws.carry_n[lane] = 0;
-            __syncwarp();
-            FeatState fs2 = fs;
-            DirectSink dsink;
-            dsink.my_row0 = my_row0;
-            dsink.my_active = (ovf >> lane) & 1u;
-            lpr_stream<false, true, SGN>(a, pool, r, sc, ring, 0, 0, 0, 0, fs2, ws, dsink);
+        __syncwarp();
+        if (valid && s_ovf_any != 0u) {
+            const long long base = s_base[1];
+            phase_b(gp + (size_t)cur * a.gpool_cap, base);
+            const unsigned ovf = ws.def_ovf;
+            if (ovf) {  // some records' hits did not all fit the pool: stream those again, rows go straight out
+                __syncwarp();
+                ws.carry_n[lane] = 0;
+                __syncwarp();
+                FeatState fs2 = fs;
+                DirectSink dsink;
+                dsink.my_row0 = base + rel;
+                dsink.my_active = (ovf >> lane) & 1u;
+                lpr_stream<false, true, SGN>(a, pool, r, sc, ring, 0, 0, 0, 0, fs2, ws, dsink);
+            }
+            pend = false;
+        } else {
+            pend = valid;
+            p_tile = tile;
+            p_total = s_total;
         }
-        __syncthreads();  // pool, slots and s_tile are reused by the next tile
+        cur ^= 1;
+        __syncthreads();  // slots, s_tile and the block totals are reused by the next tile
+        if (!valid) break;
     }
 }
 
@@ -889,8 +963,8 @@ int launch_lpr(FHArgs a, int flags, cudaStream_t st) {
     // segment length in chunks: kHist history chunks + sc new chunks per slot
     int sc = 8;  // a multiple of the 4-chunk scan block
     if (const char* e = getenv("WFB_LPR_SC")) sc = std::max(4, std::min(28, atoi(e) & ~3));
-    int ent_cap = kLprEnt;  // WFB_LPR_POOL shrinks the per-warp hit pool (exercises the overflow path in tests)
-    if (const char* e = getenv("WFB_LPR_POOL")) ent_cap = std::max(0, std::min(kLprEnt, atoi(e)));
+    int ent_cap = a.gpool_cap;  // WFB_LPR_POOL shrinks the per-warp hit pool (exercises the overflow path in tests)
+    if (const char* e = getenv("WFB_LPR_POOL")) ent_cap = std::max(0, std::min(a.gpool_cap, atoi(e)));
     int slot_chunks = sc + kHist;
     if ((slot_chunks & 1) == 0) ++slot_chunks;  // odd multiple of 16 bytes: conflict-free LDS.128
     a.slot_bytes = slot_chunks * 16;
@@ -933,6 +1007,7 @@ int launch_lpr(FHArgs a, int flags, cudaStream_t st) {
             return WFB_ERR_CUDA;
         }
         int grid = (int)std::min<long long>((long long)sm_count() * per_sm, a.n_tiles);
+        if (h) grid = std::min(grid, a.gpool_blocks);
         kern<<<grid, kLprWarps * 32, dyn, st>>>(a, sc, tmap, have_tmap, ent_cap);
         WFB_CUDA(cudaGetLastError());
         return WFB_OK;

@@ -352,6 +352,55 @@ int wfb_sort_pairs_i64(const int64_t* keys_in_dev, const int64_t* vals_in_dev, i
                        size_t workspace_bytes, void* stream);
 size_t wfb_sort_workspace_bytes(int64_t n);
 
+/* ---- the step after the path: df, s1_s2, df_paired ------------------------------------------ */
+
+/* `df` (core/plugins/builtin/cpu/dataframe.py:192-311): the columns of the events DataFrame in
+ * timestamp order.  feat_rows_dev = n packed BASIC_FEATURES rows (36 B); record_id_dev = int64[n]
+ * or NULL (then record_id = row index, dataframe.py:222-226).  order_dev[k] = input row of the k-th
+ * output row (a STABLE sort by timestamp; it is the index of df.sort_values("timestamp")).
+ * gains_host: n_gains (board, channel, gain_adc_per_pe) entries with gain > 0; with_pe != 0 also fills
+ * area_pe / height_pe = float64(value) / gain, NaN for channels without an entry (dataframe.py:296-309);
+ * with_pe == 0: both may be NULL. */
+typedef struct wfb_gain_rule {
+    int32_t board, channel;
+    double gain;
+} wfb_gain_rule;
+size_t wfb_df_columns_workspace_bytes(int64_t n);
+int wfb_df_columns(const void* feat_rows_dev, const int64_t* record_id_dev, int64_t n, const wfb_gain_rule* gains_host,
+                   int32_t n_gains, int32_t with_pe, int64_t* order_dev, int64_t* timestamp_dev, int64_t* record_id_out_dev,
+                   float* area_dev, float* height_dev, float* amp_dev, float* max_abs_diff_dev, int16_t* board_dev,
+                   int16_t* channel_dev, double* area_pe_dev, double* height_pe_dev, void* workspace_dev,
+                   size_t workspace_bytes, void* stream);
+
+/* `s1_s2` (core/plugins/builtin/cpu/s1_s2_classifier.py:133-228): one packed S1_S2_CLASSIFIER row (45 B)
+ * per waveform_width row (56 B).  height / area come from feat_rows_dev[record_id] (36-B rows) when
+ * 0 <= record_id < n_feat, else NaN (:170-180).  A range with present == 0 always passes; a NaN value fails
+ * a present range (:54-68).  width_in_samples selects total_width_samples instead of total_width (:182).
+ * conflict_policy: 0 unknown, 1 prefer_s1, 2 prefer_s2 (:194-204). */
+typedef struct wfb_range {
+    double lo, hi;
+    int32_t has_lo, has_hi;
+    int32_t present;
+    int32_t reserved_;
+} wfb_range;
+typedef struct wfb_s1s2_params {
+    wfb_range s1_width, s1_area, s1_height;
+    wfb_range s2_width, s2_area, s2_height;
+    int32_t width_in_samples;
+    int32_t conflict_policy;
+} wfb_s1s2_params;
+int wfb_s1s2_classify(const void* width_rows_dev, int64_t n_peaks, const void* feat_rows_dev, int64_t n_feat,
+                      const wfb_s1s2_params* params, void* out_rows_dev, void* stream);
+
+/* `df_paired` (core/processing/analyzer.py:66-110) on the grouped events in CSR form (event e owns members
+ * [offsets[e], offsets[e+1]) of the member arrays, in df_events order): keep_dev[e] = dt_ns[e] <= time_window_ns,
+ * delta_t_dev[e] = (last - first member timestamp) / 1000.0, area_ch_dev / height_ch_dev [e * n_channels + i] =
+ * the i-th member's value or NaN when the event has fewer members (:98-108). */
+int wfb_pair_events(const int64_t* offsets_dev, int64_t n_events, const int64_t* member_ts_dev,
+                    const float* member_area_dev, const float* member_height_dev, const double* dt_ns_dev,
+                    double time_window_ns, int32_t n_channels, uint8_t* keep_dev, double* delta_t_dev,
+                    float* area_ch_dev, float* height_ch_dev, void* stream);
+
 /* ---- synthetic input (bench / tests) ------------------------------------------------------- */
 
 /* Fill pool_dev / meta_dev with a seeded synthetic run of n fixed-length records

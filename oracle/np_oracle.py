@@ -1116,3 +1116,101 @@ def build_records_ragged(timestamps_ps, boards, channels, sample_blocks, *, dt_n
     rec["record_id"] = np.arange(n)
     pool = np.concatenate([rows[i] for i in order.tolist()]) if n else np.zeros(0, dtype=np.uint16)
     return rec, pool
+
+
+# --------------------------------------------------------------------------------------------
+# the step after the path: df, s1_s2, df_paired
+# --------------------------------------------------------------------------------------------
+
+
+def df_columns(features: np.ndarray, record_id=None, gains: dict | None = None) -> dict:
+    """Restates DataFramePlugin.compute (dataframe.py:192-311) as columns: rows in timestamp order (the reference
+    sorts with pandas' default quicksort, so only inputs with unique timestamps have a defined order; this
+    restatement is stable), `order` = the DataFrame index.  gains {(board, channel): gain} -> area_pe / height_pe =
+    float64(value) / gain, NaN where the channel has no entry (:296-309)."""
+    n = len(features)
+    ts = np.asarray(features["timestamp"], dtype=np.int64)
+    order = np.argsort(ts, kind="stable")
+    rid = np.arange(n, dtype=np.int64) if record_id is None else np.asarray(record_id, dtype=np.int64)
+    out = dict(order=order.astype(np.int64), timestamp=ts[order], record_id=rid[order], area=features["area"][order],
+               height=features["height"][order], amp=features["amp"][order], max_abs_diff=features["max_abs_diff"][order],
+               board=features["board"][order], channel=features["channel"][order])
+    if gains is not None:
+        g = np.full(n, np.nan, dtype=np.float64)
+        for i in range(n):
+            v = gains.get((int(out["board"][i]), int(out["channel"][i])))
+            if v is not None:
+                g[i] = v
+        out["area_pe"] = out["area"].astype(np.float64) / g
+        out["height_pe"] = out["height"].astype(np.float64) / g
+    return out
+
+
+def _in_range(values: np.ndarray, bounds) -> np.ndarray:  # s1_s2_classifier.py:54-68
+    if bounds is None:
+        return np.ones(len(values), dtype=bool)
+    lo, hi = bounds
+    ok = ~np.isnan(values)
+    if lo is not None:
+        ok &= ~(values < lo)
+    if hi is not None:
+        ok &= ~(values > hi)
+    return ok
+
+
+def s1s2_classify(widths: np.ndarray, features: np.ndarray, *, width_unit="ns", s1_width_range=None, s2_width_range=None,
+                  s1_area_range=None, s2_area_range=None, s1_height_range=None, s2_height_range=None,
+                  conflict_policy="unknown") -> np.ndarray:
+    """Restates S1S2ClassifierPlugin.compute (s1_s2_classifier.py:133-228) for the packed dtypes (basic_features has
+    no record_id column, so height / area are features[record_id] when 0 <= record_id < len(features), else NaN).
+    Ranges are already normalised: None or (lo, hi) with at least one bound."""
+    from waveformanalysis_b200.dtypes import S1_S2_CLASSIFIER_DTYPE
+
+    n = len(widths)
+    out = np.zeros(n, dtype=S1_S2_CLASSIFIER_DTYPE)
+    if n == 0:
+        return out
+    rid = widths["record_id"].astype(np.int64)
+    ok = (rid >= 0) & (rid < len(features))
+    height = np.full(n, np.nan, dtype=np.float64)
+    area = np.full(n, np.nan, dtype=np.float64)
+    height[ok] = features["height"][rid[ok]]
+    area[ok] = features["area"][rid[ok]]
+    wv = (widths["total_width_samples"] if width_unit == "samples" else widths["total_width"]).astype(np.float64)
+    s1_en = any(r is not None for r in (s1_width_range, s1_area_range, s1_height_range))
+    s2_en = any(r is not None for r in (s2_width_range, s2_area_range, s2_height_range))
+    s1 = _in_range(wv, s1_width_range) & _in_range(area, s1_area_range) & _in_range(height, s1_height_range) & s1_en
+    s2 = _in_range(wv, s2_width_range) & _in_range(area, s2_area_range) & _in_range(height, s2_height_range) & s2_en
+    label = np.zeros(n, dtype=np.int8)
+    label[s1 & ~s2] = 1
+    label[s2 & ~s1] = 2
+    label[s1 & s2] = {"unknown": 0, "prefer_s1": 1, "prefer_s2": 2}[conflict_policy]
+    out["label"] = label
+    out["width_ns"] = widths["total_width"]
+    out["width_samples"] = widths["total_width_samples"]
+    out["height"] = height
+    out["area"] = area
+    out["timestamp"] = widths["timestamp"]
+    out["board"] = widths["board"]
+    out["channel"] = widths["channel"]
+    out["record_id"] = rid
+    out["peak_position"] = widths["peak_position"]
+    return out
+
+
+def pair_events(offsets, member_ts, member_area, member_height, dt_ns, time_window_ns, n_channels: int) -> dict:
+    """Restates EventAnalyzer.pair_events (analyzer.py:66-110) on CSR events: keep = dt/ns <= window, delta_t =
+    (last - first member timestamp) / 1000.0, i-th member's area / height or NaN."""
+    offsets = np.asarray(offsets, dtype=np.int64)
+    n = len(offsets) - 1
+    keep = np.asarray(dt_ns, dtype=np.float64) <= time_window_ns
+    delta = np.zeros(n, dtype=np.float64)
+    a = np.full((n, n_channels), np.nan, dtype=np.float32)
+    h = np.full((n, n_channels), np.nan, dtype=np.float32)
+    for e in range(n):
+        s, t = int(offsets[e]), int(offsets[e + 1])
+        delta[e] = (int(member_ts[t - 1]) - int(member_ts[s])) / 1000.0
+        for i in range(min(n_channels, t - s)):
+            a[e, i] = member_area[s + i]
+            h[e, i] = member_height[s + i]
+    return dict(keep=keep, delta_t=delta, area_ch=a, height_ch=h)

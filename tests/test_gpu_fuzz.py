@@ -177,3 +177,53 @@ def test_fused_hits_signed_rows_adversarial():
         want["height"] = want["height"]  # heights are differences: the shift cancels
         got = engine.process_host(rec, pool, features=False, signed_samples=True, **kw)["hits"]
         assert_rows_match(got, want, what=f"signed trial {trial}", float_exact=("width", "rise_time", "fall_time"))
+
+
+def test_after_path_ops_fuzz():
+    """df_columns / s1s2_classify / pair_events against the oracle on seeded random rows (ties in the
+    timestamps included: both sides sort stably)."""
+    from oracle import np_oracle as O
+    from waveformanalysis_b200 import ops
+    from waveformanalysis_b200.dtypes import BASIC_FEATURES_DTYPE, WAVEFORM_WIDTH_DTYPE
+
+    rng = np.random.default_rng(99)
+    for n in (1, 257, 5000, 70001):
+        bf = np.zeros(n, dtype=BASIC_FEATURES_DTYPE)
+        bf["timestamp"] = rng.integers(-5, max(n // 3, 2), n) * 1000 - (1 << 40) * (rng.random(n) < 0.1)
+        for f in ("height", "amp", "area", "max_abs_diff"):
+            bf[f] = rng.normal(0, 1e3, n).astype(np.float32)
+        bf["area"][rng.random(n) < 0.02] = np.nan
+        bf["board"], bf["channel"] = rng.integers(0, 3, n), rng.integers(0, 5, n)
+        rid = rng.permutation(n).astype(np.int64)
+        gains = {(0, 0): 3.5, (1, 4): 0.25, (2, 2): 1e-3, (7, 7): 2.0}
+        for g, r in ((None, None), (gains, rid), ({}, rid)):
+            got, want = ops.df_columns(bf, r, g), O.df_columns(bf, r, g)
+            assert set(got) == set(want)
+            for k in want:
+                assert got[k].dtype == want[k].dtype, k
+                assert np.array_equal(got[k], want[k], equal_nan=want[k].dtype.kind == "f"), (n, k)
+        # s1_s2
+        m = max(n // 2, 1)
+        ww = np.zeros(m, dtype=WAVEFORM_WIDTH_DTYPE)
+        ww["total_width"] = rng.uniform(0, 500, m).astype(np.float32)
+        ww["total_width"][rng.random(m) < 0.05] = np.nan
+        ww["total_width_samples"] = ww["total_width"] / 2
+        ww["record_id"] = rng.integers(-3, n + 3, m)
+        ww["timestamp"], ww["peak_position"] = rng.integers(0, 1 << 50, m), rng.integers(0, 800, m)
+        ww["board"], ww["channel"] = rng.integers(0, 3, m), rng.integers(0, 5, m)
+        conf = dict(s1_width_range=(None, 250.0), s2_width_range=(200.0, None), s1_area_range=(-500.0, 500.0), s2_height_range=(0.0, None),
+                    conflict_policy=("unknown", "prefer_s1", "prefer_s2")[n % 3], width_unit=("ns", "samples")[n % 2])
+        got, want = ops.s1s2_classify(ww, bf, **conf), O.s1s2_classify(ww, bf, **conf)
+        assert got.tobytes() == want.tobytes() or all(np.array_equal(got[f], want[f], equal_nan=True) for f in want.dtype.names)
+        # df_paired
+        lens = rng.integers(1, 6, m)
+        off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        tot = int(off[-1])
+        ts = rng.integers(0, 1 << 45, tot)
+        ar, he = rng.normal(0, 100, tot).astype(np.float32), rng.normal(0, 10, tot).astype(np.float32)
+        dt = rng.uniform(0, 200, m)
+        dt[rng.random(m) < 0.05] = np.nan
+        for nch in (0, 1, 4):
+            got, want = ops.pair_events(off, ts, ar, he, dt, 100.0, nch), O.pair_events(off, ts, ar, he, dt, 100.0, nch)
+            for k in want:
+                assert np.array_equal(got[k], want[k], equal_nan=True), (n, nch, k)

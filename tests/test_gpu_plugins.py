@@ -269,3 +269,80 @@ def test_signal_peaks_stream_chunks(P):
         # (checked on the CPU in test_plugin_contract.py::test_streaming_plugin_runs_inside_the_reference_framework)
         for (lo, hi), part, (mlo, mhi) in zip(bounds, parts, g[tag + "_bounds"]):
             assert lo == part["timestamp"].min() and hi == part["timestamp"].max() and mlo <= lo and hi <= mhi
+
+
+# ---- the step after the path: df / df_events -> df_paired / s1_s2 ------------------------------------------
+
+
+def test_df_plugin(P, golden):
+    from after_cases import DF_COLUMNS, GAINS_CONFIG, check_df_columns, load_after
+
+    A = load_after()
+    rec, bf = A["df_in_records"], A["df_in_features"]
+
+    def as_cols(df):
+        cols = {c: df[c].to_numpy() for c in df.columns}
+        cols["order"] = df.index.to_numpy()
+        return cols
+
+    df = run(P.B200DataFramePlugin(), {"records": rec, "basic_features": bf}, {"wave_source": "records"})
+    assert tuple(df.columns) == DF_COLUMNS
+    check_df_columns(as_cols(df), A, "df_plain", False)
+    with pytest.warns(UserWarning, match="invalid 'gain_adc_per_pe'"):
+        df_pe = run(P.B200DataFramePlugin(), {"records": rec, "basic_features": bf}, {"wave_source": "records", "gain_adc_per_pe": GAINS_CONFIG})
+    assert tuple(df_pe.columns) == DF_COLUMNS + ("area_pe", "height_pe")
+    check_df_columns(as_cols(df_pe), A, "df_pe", True)
+    df_st = run(P.B200DataFramePlugin(), {"st_waveforms": A["df_in_st"], "basic_features": bf})
+    check_df_columns(as_cols(df_st), A, "df_st", False)
+    with pytest.raises(ValueError, match="basic_features length"):
+        run(P.B200DataFramePlugin(), {"records": rec[:-1], "basic_features": bf}, {"wave_source": "records"})
+    empty = run(P.B200DataFramePlugin(), {"records": rec[:0], "basic_features": bf[:0]}, {"wave_source": "records"})
+    assert len(empty) == 0 and tuple(empty.columns) == DF_COLUMNS
+
+
+def test_df_paired_chain(P):
+    """df -> df_events -> df_paired through the three B200 plugins against the reference chain."""
+    from after_cases import load_after
+
+    A = load_after()
+    rec, bf = A["df_in_records"], A["df_in_features"]
+    df = run(P.B200DataFramePlugin(), {"records": rec, "basic_features": bf}, {"wave_source": "records"})
+    w = float(A["pair_group_window_ns"])
+    ev = run(P.B200GroupedEventsPlugin(), {"df": df}, {"time_window_ns": w})
+    assert np.array_equal(np.concatenate(list(ev["timestamps"])), A["pair_ev_timestamps"])
+    assert np.array_equal(ev["dt/ns"].to_numpy(), A["pair_ev_dt_ns"])
+    for name in ("a", "b", "c"):
+        nch, start = (int(v) for v in A[f"pair_{name}_nch_start"])
+        for strip_attrs in (False, True):  # with and without the CSR side channel of the B200 df_events plugin
+            src = ev.copy()
+            if strip_attrs:
+                src.attrs.clear()
+            paired = P.B200PairedEventsPlugin().compute(Ctx({"n_channels": nch, "start_channel_slice": start, "time_window_ns": float(A[f"pair_{name}_tw"])},
+                                                            {"df_events": src}), "run")
+            assert np.array_equal(paired.index.to_numpy(), A[f"pair_{name}_index"]), name
+            assert np.array_equal(paired["delta_t"].to_numpy(), A[f"pair_{name}_delta_t"]), name
+            for i in range(nch):
+                for kind in ("area", "height"):
+                    col = f"{kind}_ch{start + i}"
+                    assert str(paired[col].dtype) == str(A[f"pair_{name}_{col}_dtype"]), (name, col)
+                    assert np.array_equal(paired[col].to_numpy(), A[f"pair_{name}_{col}"], equal_nan=True), (name, col)
+            assert np.array_equal(paired["n_hits"].to_numpy(), A[f"pair_{name}_n_hits"])
+
+
+def test_s1s2_plugin(P, golden):
+    from after_cases import S1S2_CASES, load_after
+
+    A = load_after()
+    ww, feats = golden["ww_default"], A["s1s2_in_features"]
+    for name, conf in S1S2_CASES.items():
+        out = run(P.B200S1S2ClassifierPlugin(), {"waveform_width": ww, "basic_features": feats}, dict(conf))
+        assert_rows_match(out, A[f"s1s2_{name}"], what=name, float_exact=("width_ns", "width_samples", "height", "area"))
+    # sizes around the 128-row staging block, and the unaligned tail
+    for n in (1, 127, 128, 129, 300):
+        out = run(P.B200S1S2ClassifierPlugin(), {"waveform_width": ww[:n], "basic_features": feats}, dict(S1S2_CASES["area_prefer_s1"]))
+        assert_rows_match(out, A["s1s2_area_prefer_s1"][:n], what=f"n={n}", float_exact=("width_ns", "width_samples", "height", "area"))
+    assert len(run(P.B200S1S2ClassifierPlugin(), {"waveform_width": ww[:0], "basic_features": feats})) == 0
+    with pytest.raises(ValueError, match="No S1/S2 criteria"):
+        run(P.B200S1S2ClassifierPlugin(), {"waveform_width": ww, "basic_features": feats}, {"strict": True})
+    with pytest.raises(ValueError, match="range must be a tuple"):
+        run(P.B200S1S2ClassifierPlugin(), {"waveform_width": ww, "basic_features": feats}, {"s1_width_range": [1, 2]})

@@ -263,3 +263,40 @@ def test_grouping_of_cross_record_merged_hits(golden):
         check_grouping50(O.group_hit_windows(mg, w, cp, h), mg, want)
     with pytest.raises(ValueError):
         O.group_hit_windows(mg, 100.0)
+
+
+# ---- the step after the path: df / df_paired / s1_s2 (tests/golden/make_golden_after.py) -------------------
+
+
+def test_df_columns_oracle():
+    from after_cases import GAINS_RESOLVED, check_df_columns, load_after
+
+    A = load_after()
+    rec, bf = A["df_in_records"], A["df_in_features"]
+    check_df_columns(O.df_columns(bf, rec["record_id"]), A, "df_plain", False)
+    check_df_columns(O.df_columns(bf, rec["record_id"], GAINS_RESOLVED), A, "df_pe", True)
+    assert np.isnan(A["df_pe_area_pe"]).any() and not np.isnan(A["df_pe_area_pe"]).all()
+    st_feat = bf.copy()
+    st_feat["board"] = 0
+    check_df_columns(O.df_columns(st_feat, None), A, "df_st", False)
+
+
+def test_s1s2_oracle(golden):
+    from after_cases import S1S2_CASES, load_after
+
+    A = load_after()
+    for name, conf in S1S2_CASES.items():
+        got = O.s1s2_classify(golden["ww_default"], A["s1s2_in_features"], **conf)
+        assert_rows_match(got, A[f"s1s2_{name}"], what=name, float_exact=("width_ns", "width_samples", "height", "area"))
+
+
+def test_pair_events_oracle():
+    from after_cases import check_pair, load_after
+
+    A = load_after()
+    off = A["pair_ev_offsets"]
+    for name in ("a", "b", "c"):
+        nch = int(A[f"pair_{name}_nch_start"][0])
+        out = O.pair_events(off, A["pair_ev_timestamps"], A["pair_ev_areas"], A["pair_ev_heights"], A["pair_ev_dt_ns"],
+                            float(A[f"pair_{name}_tw"]), nch)
+        check_pair(out, off, A, name)

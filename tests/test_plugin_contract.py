@@ -32,7 +32,7 @@ def test_profile_provides_the_hot_path_names():
     names = [p.provides for p in profiles.b200_default()]
     assert names == ["records", "wave_pool", "wave_pool_filtered", "basic_features", "hit_threshold", "hit", "waveform_width",
                      "waveform_width_integral", "hit_merge_clusters", "hit_merged", "hit_merged_components", "hit_grouped",
-                     "df_events"]
+                     "df", "df_events", "df_paired", "s1_s2"]
     for p in profiles.b200_default():
         assert callable(p.compute) and isinstance(p.options, dict) and p.version
 
@@ -84,7 +84,8 @@ def test_structured_rows_as_pool_without_repacking():
 @pytest.mark.skipif(not HAVE_REF, reason="reference checkout not available")
 def test_contract_matches_reference_plugins():
     _import_ref()
-    from waveform_analysis.core.plugins.builtin.cpu import basic_features, event_analysis, hit_finder, hit_merge, peak_finding, records, waveform_width, waveform_width_integral
+    from waveform_analysis.core.plugins.builtin.cpu import (basic_features, dataframe, event_analysis, hit_finder, hit_merge, peak_finding, records,
+                                                            s1_s2_classifier, waveform_width, waveform_width_integral)
 
     from waveformanalysis_b200 import plugins as P
 
@@ -102,6 +103,9 @@ def test_contract_matches_reference_plugins():
         (P.B200GroupedEventsPlugin, event_analysis.GroupedEventsPlugin),
         (P.B200RecordsPlugin, records.RecordsPlugin),
         (P.B200WavePoolPlugin, records.WavePoolPlugin),
+        (P.B200DataFramePlugin, dataframe.DataFramePlugin),
+        (P.B200PairedEventsPlugin, event_analysis.PairedEventsPlugin),
+        (P.B200S1S2ClassifierPlugin, s1_s2_classifier.S1S2ClassifierPlugin),
     ]
     for ours, ref in pairs:
         assert ours.provides == ref.provides
@@ -229,3 +233,61 @@ print("ok")
 
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert res.returncode == 0 and "ok" in res.stdout, res.stderr[-2000:]
+
+
+def test_gain_map_resolution_matches_the_reference_rules():
+    """dataframe.py:115-190 + channel.py:571-619: mappings unwrapped, non-positive gains dropped with a warning,
+    run blocks and a `channels` sub-tree selected, bad keys raise."""
+    from after_cases import GAINS_CONFIG, GAINS_RESOLVED
+    from waveformanalysis_b200.plugins.dataframe import B200DataFramePlugin, resolve_gain_values
+
+    with pytest.warns(UserWarning, match="board0:ch3"):
+        assert resolve_gain_values(GAINS_CONFIG, "run", True, "df") == GAINS_RESOLVED
+    assert resolve_gain_values({"run": {"channels": {"1:2": 4.0}}, "0:0": 9.0}, "run", True, "df") == {(1, 2): 4.0}
+    assert resolve_gain_values(GAINS_CONFIG, "run", False, "df") == {}
+    with pytest.raises(ValueError, match="Invalid channel key"):
+        resolve_gain_values({"nonsense": 1.0}, "run", True, "df")
+    plug = B200DataFramePlugin()
+    assert plug._resolve_gain_map(Ctx({}), "run", True) == ({}, False)
+    assert plug._resolve_gain_map(Ctx({"gain_adc_per_pe": {"0:0": 2.0}}), "run", True) == ({(0, 0): 2.0}, True)
+
+    class RunCfg(Ctx):
+        def get_run_config(self, run_id):
+            return {"calibration": {"gain_adc_per_pe": {"0:1": 5.0}}}
+
+        def has_explicit_config(self, plugin, name):
+            return name in self.config
+
+    assert plug._resolve_gain_map(RunCfg({}), "run", True) == ({(0, 1): 5.0}, True)
+    assert plug._resolve_gain_map(RunCfg({"gain_adc_per_pe": {}}), "run", True) == ({}, False)  # explicit empty map wins
+    assert plug.resolve_depends_on(Ctx({"wave_source": "records"})) == ["records", "basic_features"]
+    assert plug.resolve_depends_on(Ctx({"use_filtered": True})) == ["filtered_waveforms", "basic_features"]
+
+
+def test_paired_frame_host_logic(monkeypatch):
+    """pair_events_frame around a stand-in for the device op (the oracle): row filter, delta_t, float64 widening
+    of columns with missing members - against the live reference's DataFrame in after_golden.npz."""
+    import pandas as pd
+
+    from after_cases import load_after
+    from oracle import np_oracle as O
+    from waveformanalysis_b200 import ops
+    from waveformanalysis_b200.plugins.dataframe import pair_events_frame
+
+    monkeypatch.setattr(ops, "pair_events", O.pair_events)
+    A = load_after()
+    off = A["pair_ev_offsets"]
+    rag = lambda flat: [flat[off[i]:off[i + 1]] for i in range(len(off) - 1)]  # noqa: E731
+    ev = pd.DataFrame({"event_id": np.arange(len(off) - 1), "dt/ns": A["pair_ev_dt_ns"], "n_hits": A["pair_ev_n_hits"],
+                       "areas": rag(A["pair_ev_areas"]), "heights": rag(A["pair_ev_heights"]), "timestamps": rag(A["pair_ev_timestamps"])})
+    for name in ("a", "b", "c"):
+        nch, start = (int(v) for v in A[f"pair_{name}_nch_start"])
+        paired = pair_events_frame(ev, nch, start, float(A[f"pair_{name}_tw"]))
+        assert np.array_equal(paired.index.to_numpy(), A[f"pair_{name}_index"])
+        assert np.array_equal(paired["delta_t"].to_numpy(), A[f"pair_{name}_delta_t"])
+        for i in range(nch):
+            for kind in ("area", "height"):
+                col = f"{kind}_ch{start + i}"
+                assert str(paired[col].dtype) == str(A[f"pair_{name}_{col}_dtype"])
+                assert np.array_equal(paired[col].to_numpy(), A[f"pair_{name}_{col}"], equal_nan=True)
+    assert len(pair_events_frame(ev[:0], 2, 6, 100.0)) == 0

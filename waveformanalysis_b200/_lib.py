@@ -112,6 +112,20 @@ class PeakParams(C.Structure):  # wfb_peak_params
                 ("height_method", C.c_int32), ("height_window_extension", C.c_int32), ("lmax", C.c_int32), ("reserved_", C.c_int32)]
 
 
+class GainRule(C.Structure):  # wfb_gain_rule
+    _fields_ = [("board", C.c_int32), ("channel", C.c_int32), ("gain", C.c_double)]
+
+
+class Range(C.Structure):  # wfb_range
+    _fields_ = [("lo", C.c_double), ("hi", C.c_double), ("has_lo", C.c_int32), ("has_hi", C.c_int32), ("present", C.c_int32),
+                ("reserved_", C.c_int32)]
+
+
+class S1S2Params(C.Structure):  # wfb_s1s2_params
+    _fields_ = [("s1_width", Range), ("s1_area", Range), ("s1_height", Range), ("s2_width", Range), ("s2_area", Range),
+                ("s2_height", Range), ("width_in_samples", C.c_int32), ("conflict_policy", C.c_int32)]
+
+
 WAVE_AOS_I16, WAVE_AOS_F32, WAVE_REC_U16, WAVE_REC_F32, WAVE_AOS_F32_AS_F64 = 0, 1, 2, 3, 4
 
 PROTOTYPES = {
@@ -142,6 +156,10 @@ PROTOTYPES = {
     "wfb_group_workspace_bytes": (_sz, [_i64]),
     "wfb_group_hit_windows": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _dbl, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "wfb_group_time_window": (C.c_int, [_vp, _i64, _dbl, _vp, _vp, _vp, _sz, _vp]),
+    "wfb_df_columns_workspace_bytes": (_sz, [_i64]),
+    "wfb_df_columns": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _i32] + [_vp] * 11 + [_vp, _sz, _vp]),
+    "wfb_s1s2_classify": (C.c_int, [_vp, _i64, _vp, _i64, C.POINTER(S1S2Params), _vp, _vp]),
+    "wfb_pair_events": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _dbl, _i32, _vp, _vp, _vp, _vp, _vp]),
     "wfb_sort_pairs_i64": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
     "wfb_sort_workspace_bytes": (_sz, [_i64]),
     "wfb_synth_fill": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, C.c_uint64, _i64, _vp]),

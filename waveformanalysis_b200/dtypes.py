@@ -176,3 +176,21 @@ def polarity_codes(polarity: np.ndarray) -> np.ndarray:
     out[pol == "positive"] = POLARITY_POSITIVE
     out[pol == "negative"] = POLARITY_NEGATIVE
     return out
+
+
+# core/plugins/builtin/cpu/s1_s2_classifier.py:29-42 (packed, 45 bytes)
+S1_S2_CLASSIFIER_DTYPE = np.dtype(
+    [
+        ("label", "i1"),
+        ("width_ns", "f4"),
+        ("width_samples", "f4"),
+        ("height", "f4"),
+        ("area", "f4"),
+        ("timestamp", "i8"),
+        ("board", "i2"),
+        ("channel", "i2"),
+        ("record_id", "i8"),
+        ("peak_position", "i8"),
+    ]
+)
+LABEL_UNKNOWN, LABEL_S1, LABEL_S2 = 0, 1, 2

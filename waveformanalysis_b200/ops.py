@@ -678,3 +678,109 @@ def find_peaks_stream_chunk(st_chunk: np.ndarray, filtered_chunk: np.ndarray, *,
     return _find_peaks(rec, pool, _lib.WAVE_AOS_F32_AS_F64, use_derivative=use_derivative, height=height, distance=distance,
                        prominence=prominence, width=width, threshold=threshold, height_method=height_method,
                        height_window_extension=minmax_window_expand, cumsum_diff=True)
+
+
+# --------------------------------------------------------------------------------------------
+# the step after the path: df / s1_s2 / df_paired (dataframe.py:192-311, s1_s2_classifier.py:133-228,
+# analyzer.py:66-110)
+# --------------------------------------------------------------------------------------------
+
+
+def df_columns(features: np.ndarray, record_id: np.ndarray | None = None, gains: dict | None = None) -> dict:
+    """Columns of the `df` DataFrame in timestamp order (stable) plus ``order`` (the DataFrame index).
+    ``gains``: {(board, channel): gain_adc_per_pe > 0} or None (no calibrated columns)."""
+    from .dtypes import BASIC_FEATURES_DTYPE
+
+    lib = _lib.load()
+    torch = _torch()
+    features = np.ascontiguousarray(features)
+    if features.dtype != BASIC_FEATURES_DTYPE:
+        raise ValueError("df_columns expects packed BASIC_FEATURES rows")
+    n = len(features)
+    with_pe = gains is not None
+    cols = dict(order=torch.empty(n, dtype=torch.int64, device="cuda"), timestamp=torch.empty(n, dtype=torch.int64, device="cuda"),
+                record_id=torch.empty(n, dtype=torch.int64, device="cuda"), area=torch.empty(n, dtype=torch.float32, device="cuda"),
+                height=torch.empty(n, dtype=torch.float32, device="cuda"), amp=torch.empty(n, dtype=torch.float32, device="cuda"),
+                max_abs_diff=torch.empty(n, dtype=torch.float32, device="cuda"), board=torch.empty(n, dtype=torch.int16, device="cuda"),
+                channel=torch.empty(n, dtype=torch.int16, device="cuda"))
+    if with_pe:
+        cols["area_pe"] = torch.empty(n, dtype=torch.float64, device="cuda")
+        cols["height_pe"] = torch.empty(n, dtype=torch.float64, device="cuda")
+    if n:
+        rules = (_lib.GainRule * max(len(gains or {}), 1))()
+        for i, ((b, c), g) in enumerate((gains or {}).items()):
+            rules[i].board, rules[i].channel, rules[i].gain = int(b), int(c), float(g)
+        d_feat = _dev(features)
+        d_rid = _dev(np.asarray(record_id, dtype=np.int64)) if record_id is not None else None
+        ws = _empty(lib.wfb_df_columns_workspace_bytes(n))
+        _lib.check(lib.wfb_df_columns(_ptr(d_feat), _ptr(d_rid) if d_rid is not None else None, n, rules, len(gains or {}), int(with_pe),
+                                      _ptr(cols["order"]), _ptr(cols["timestamp"]), _ptr(cols["record_id"]), _ptr(cols["area"]),
+                                      _ptr(cols["height"]), _ptr(cols["amp"]), _ptr(cols["max_abs_diff"]), _ptr(cols["board"]),
+                                      _ptr(cols["channel"]), _ptr(cols["area_pe"]) if with_pe else None,
+                                      _ptr(cols["height_pe"]) if with_pe else None, _ptr(ws), ws.numel(), _stream()), "wfb_df_columns")
+        torch.cuda.current_stream().synchronize()  # `rules` (host) must outlive the staged copy
+    return {k: v.cpu().numpy() for k, v in cols.items()}
+
+
+def _range_struct(bounds) -> "_lib.Range":
+    r = _lib.Range()
+    if bounds is None:
+        return r
+    lo, hi = bounds
+    r.present = 1
+    if lo is not None:
+        r.has_lo, r.lo = 1, float(lo)
+    if hi is not None:
+        r.has_hi, r.hi = 1, float(hi)
+    return r
+
+
+def s1s2_classify(widths: np.ndarray, features: np.ndarray, *, width_unit: str = "ns", s1_width_range=None, s2_width_range=None,
+                  s1_area_range=None, s2_area_range=None, s1_height_range=None, s2_height_range=None,
+                  conflict_policy: str = "unknown") -> np.ndarray:
+    """Packed S1_S2_CLASSIFIER rows, one per waveform_width row; ranges are (lo, hi) with None = open,
+    already normalised (a (None, None) range is passed as None)."""
+    from .dtypes import BASIC_FEATURES_DTYPE, S1_S2_CLASSIFIER_DTYPE, WAVEFORM_WIDTH_DTYPE
+
+    lib = _lib.load()
+    torch = _torch()
+    widths = np.ascontiguousarray(widths)
+    features = np.ascontiguousarray(features)
+    if widths.dtype != WAVEFORM_WIDTH_DTYPE or features.dtype != BASIC_FEATURES_DTYPE:
+        raise ValueError("s1s2_classify expects packed WAVEFORM_WIDTH and BASIC_FEATURES rows")
+    n = len(widths)
+    if n == 0:
+        return np.zeros(0, dtype=S1_S2_CLASSIFIER_DTYPE)
+    p = _lib.S1S2Params()
+    p.s1_width, p.s1_area, p.s1_height = _range_struct(s1_width_range), _range_struct(s1_area_range), _range_struct(s1_height_range)
+    p.s2_width, p.s2_area, p.s2_height = _range_struct(s2_width_range), _range_struct(s2_area_range), _range_struct(s2_height_range)
+    p.width_in_samples = 1 if width_unit == "samples" else 0
+    p.conflict_policy = {"unknown": 0, "prefer_s1": 1, "prefer_s2": 2}[conflict_policy]
+    d_w = _dev(widths)
+    d_f = _dev(features) if len(features) else _empty(16)
+    out = torch.empty(n * S1_S2_CLASSIFIER_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.wfb_s1s2_classify(_ptr(d_w), n, _ptr(d_f), len(features), C.byref(p), _ptr(out), _stream()), "wfb_s1s2_classify")
+    return out.cpu().numpy().view(S1_S2_CLASSIFIER_DTYPE)
+
+
+def pair_events(offsets: np.ndarray, member_ts: np.ndarray, member_area: np.ndarray, member_height: np.ndarray, dt_ns: np.ndarray,
+                time_window_ns: float, n_channels: int) -> dict:
+    """keep mask, delta_t and the per-channel area / height columns of `df_paired` for CSR events."""
+    lib = _lib.load()
+    torch = _torch()
+    offsets = np.asarray(offsets, dtype=np.int64)
+    n_ev = len(offsets) - 1
+    nc = int(n_channels)
+    if n_ev <= 0:
+        return dict(keep=np.zeros(0, bool), delta_t=np.zeros(0), area_ch=np.zeros((0, nc), np.float32), height_ch=np.zeros((0, nc), np.float32))
+    d_off, d_ts = _dev(offsets), _dev(np.asarray(member_ts, dtype=np.int64))
+    d_a, d_h = _dev(np.asarray(member_area, dtype=np.float32)), _dev(np.asarray(member_height, dtype=np.float32))
+    d_dt = _dev(np.asarray(dt_ns, dtype=np.float64))
+    keep = torch.empty(n_ev, dtype=torch.uint8, device="cuda")
+    delta = torch.empty(n_ev, dtype=torch.float64, device="cuda")
+    a_ch = torch.empty(max(n_ev * nc, 1), dtype=torch.float32, device="cuda")
+    h_ch = torch.empty(max(n_ev * nc, 1), dtype=torch.float32, device="cuda")
+    _lib.check(lib.wfb_pair_events(_ptr(d_off), n_ev, _ptr(d_ts), _ptr(d_a), _ptr(d_h), _ptr(d_dt), float(time_window_ns), nc, _ptr(keep),
+                                   _ptr(delta), _ptr(a_ch), _ptr(h_ch), _stream()), "wfb_pair_events")
+    return dict(keep=keep.cpu().numpy().astype(bool), delta_t=delta.cpu().numpy(),
+                area_ch=a_ch.cpu().numpy()[: n_ev * nc].reshape(n_ev, nc), height_ch=h_ch.cpu().numpy()[: n_ev * nc].reshape(n_ev, nc))

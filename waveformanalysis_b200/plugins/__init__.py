@@ -4,6 +4,7 @@ sm_100a kernels through libwfb200.so.  Register with
 ``ctx.register(*waveformanalysis_b200.profiles.b200_default(), allow_override=True)``.
 """
 
+from .dataframe import B200DataFramePlugin, B200PairedEventsPlugin, B200S1S2ClassifierPlugin
 from .features import B200BasicFeaturesPlugin
 from .filtering import B200WavePoolFilteredPlugin
 from .grouping import B200GroupedEventsPlugin, B200HitGroupedPlugin
@@ -28,4 +29,7 @@ __all__ = [
     "B200RecordsPlugin",
     "B200WavePoolPlugin",
     "B200SignalPeaksStreamPlugin",
+    "B200DataFramePlugin",
+    "B200PairedEventsPlugin",
+    "B200S1S2ClassifierPlugin",
 ]

@@ -102,9 +102,14 @@ class B200GroupedEventsPlugin(Plugin):
         ch = df["channel"].to_numpy()
         ev = ops.group_time_window(ts, ch, float(tw))
         m, off = ev["members"], ev["offsets"]
-        return pd.DataFrame({
+        areas, heights = df[area_col].to_numpy(), df[height_col].to_numpy()
+        out = pd.DataFrame({
             "event_id": ev["event_id"], "t_min": ev["t_min"], "t_max": ev["t_max"], "dt/ns": ev["dt_ns"],
             "n_hits": ev["n_hits"].astype(np.int32),
-            "channels": _ragged(ch, m, off), "areas": _ragged(df[area_col].to_numpy(), m, off),
-            "heights": _ragged(df[height_col].to_numpy(), m, off), "timestamps": _ragged(ts, m, off),
+            "channels": _ragged(ch, m, off), "areas": _ragged(areas, m, off),
+            "heights": _ragged(heights, m, off), "timestamps": _ragged(ts, m, off),
         })
+        # the flat member arrays, for B200PairedEventsPlugin (saves re-flattening the object columns)
+        out.attrs["_wfb_csr"] = {"offsets": off, "timestamps": ts[m], "areas": areas[m].astype(np.float32),
+                                 "heights": heights[m].astype(np.float32)}
+        return out

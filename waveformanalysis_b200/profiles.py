@@ -11,7 +11,8 @@ def b200_default() -> list:
         P.B200RecordsPlugin(), P.B200WavePoolPlugin(), P.B200WavePoolFilteredPlugin(), P.B200BasicFeaturesPlugin(),
         P.B200ThresholdHitPlugin(), P.B200HitFinderPlugin(), P.B200WaveformWidthPlugin(), P.B200WaveformWidthIntegralPlugin(),
         P.B200HitMergeClustersPlugin(), P.B200HitMergePlugin(), P.B200HitMergedComponentsPlugin(),
-        P.B200HitGroupedPlugin(), P.B200GroupedEventsPlugin(),
+        P.B200HitGroupedPlugin(), P.B200DataFramePlugin(), P.B200GroupedEventsPlugin(), P.B200PairedEventsPlugin(),
+        P.B200S1S2ClassifierPlugin(),
     ]
 
 

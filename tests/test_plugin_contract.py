@@ -291,3 +291,44 @@ def test_paired_frame_host_logic(monkeypatch):
                 assert str(paired[col].dtype) == str(A[f"pair_{name}_{col}_dtype"])
                 assert np.array_equal(paired[col].to_numpy(), A[f"pair_{name}_{col}"], equal_nan=True)
     assert len(pair_events_frame(ev[:0], 2, 6, 100.0)) == 0
+
+
+def test_cache_entry_roundtrip(tmp_path):
+    from waveformanalysis_b200.cache_format import read_cache_entry, write_cache_entry
+    from waveformanalysis_b200.dtypes import BASIC_FEATURES_DTYPE
+
+    rows = np.zeros(17, dtype=BASIC_FEATURES_DTYPE)
+    rows["height"] = np.arange(17)
+    rows["timestamp"] = np.arange(17) * 1000
+    write_cache_entry(str(tmp_path), "run", "run-basic_features-abc", rows, {"lineage": {"plugin": "x"}})
+    back = read_cache_entry(str(tmp_path), "run", "run-basic_features-abc")
+    assert back.dtype == rows.dtype and np.array_equal(np.asarray(back), rows)
+    assert read_cache_entry(str(tmp_path), "run", "missing") is None
+    write_cache_entry(str(tmp_path), "run", "run-empty-abc", rows[:0])
+    assert read_cache_entry(str(tmp_path), "run", "run-empty-abc") is None
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference checkout not available")
+def test_cache_entry_is_loaded_by_the_reference_storage(tmp_path):
+    """What write_cache_entry stores, the reference's MemmapStorage finds, loads and reports (memmap.py:528-613,
+    689-760); and the other way round."""
+    _import_ref()
+    from waveform_analysis.core.storage.memmap import MemmapStorage
+
+    from waveformanalysis_b200.cache_format import read_cache_entry, write_cache_entry
+    from waveformanalysis_b200.dtypes import S1_S2_CLASSIFIER_DTYPE, THRESHOLD_HIT_DTYPE
+
+    store = MemmapStorage(str(tmp_path))
+    rng = np.random.default_rng(3)
+    for dt in (THRESHOLD_HIT_DTYPE, S1_S2_CLASSIFIER_DTYPE, np.dtype("f4")):
+        rows = np.frombuffer(rng.integers(0, 255, 40 * dt.itemsize, dtype=np.uint8).tobytes(), dtype=dt).copy()
+        key = f"run-thing{dt.itemsize}-0123abcd"
+        write_cache_entry(str(tmp_path), "run", key, rows, {"lineage": {"a": 1}})
+        assert store.exists(key, "run")
+        got = store.load_memmap(key, "run")
+        assert got.dtype == dt and np.asarray(got).tobytes() == rows.tobytes()
+        assert store.get_metadata(key, "run")["lineage"] == {"a": 1}
+        key2 = key + "-ref"
+        store.save_memmap(key2, rows, run_id="run")
+        mine = read_cache_entry(str(tmp_path), "run", key2)
+        assert mine.dtype == dt and np.asarray(mine).tobytes() == rows.tobytes()

@@ -46,6 +46,7 @@ constexpr int kHist = 2;                  // chunks of history in front of each 
 constexpr int kMaxExt = 8;                // extensions must fit the neighbouring chunk
 constexpr int kNBuf = 2;                  // slot buffers per lane
 constexpr int kQCap = 32;                 // items per dense round
+constexpr int kQRing = 64;                // queue slots: a round always takes 32 items while more are waiting
 
 struct LprEnt {  // 16 bytes, raw aggregates: height / integral are finished one hit per lane in phase B
     unsigned ps;  // p | s << 16
@@ -80,7 +81,7 @@ struct DefLane {  // what phase B needs of a record once its registers are gone
 
 struct WarpHits {  // per-warp shared memory of the hit machinery
     uint4 q_nb[2][32];     // the round's scratch: chunks P-1 and P+1 of lane t's item
-    uint4 q_hdr[kQCap];    // owner | (P + 1) << 5 ; aggregate key, samples, sum of the FULL chunks in front
+    uint4 q_hdr[kQRing];   // ring of queued items: owner | (P + 1) << 5 ; aggregate key, samples, sum of the FULL chunks in front
     uint4 stage[32];       // this round's "open at chunk end" fragments: start ; key, count, key sum
     uint4 carry[32];       // the same, per owner, across rounds
     int stage_n[32];       // runs started by this round's items
@@ -185,11 +186,11 @@ struct DirectSink {  // rows straight to the output (records whose hits did not 
 // whose minimum is the first arg-max of the signal, and count << 21 | sum(kv) of the signal-side
 // samples (at most 24 samples per fragment, so the packed sum cannot carry into the count).
 template <typename Sink>
-__device__ __forceinline__ void lpr_round(WarpHits& ws, int qn, const LaneRec& r, const FHArgs& a, Sink& sink) {
+__device__ __forceinline__ void lpr_round(WarpHits& ws, int qh, int qn, const LaneRec& r, const FHArgs& a, Sink& sink) {
     __syncwarp();  // the pushes are visible
     const int lane = lane_id();
     const bool act = lane < qn;
-    const uint4 hd = ws.q_hdr[act ? lane : 0];
+    const uint4 hd = ws.q_hdr[(qh + (act ? lane : 0)) & (kQRing - 1)];
     const int src = act ? (int)(hd.x & 31u) : lane;  // owner lane
     const int P = (int)((hd.x >> 5) & 0x3fffu) - 1;  // -1: the virtual chunk in front of a record that starts FULL
     // the owner's record constants
@@ -399,7 +400,7 @@ __device__ __forceinline__ void lpr_stream(const FHArgs& a, const uint16_t* pool
     unsigned Fm = 0u, Im = 0u, Lm = 0u;
     // aggregate of the FULL chunks in front of chunk 4b-1 and of chunk 4b
     unsigned am_key = 0xffffffffu, am_n = 0u, am_sw = 0u, a0_key = 0xffffffffu, a0_n = 0u, a0_sw = 0u;
-    int qn = 0;  // queued items (warp-uniform)
+    int qn = 0, qh = 0;  // queued items and the ring position of the first one (warp-uniform)
     bool quiet_hint = false;  // the previous block produced no item in any lane (warp-uniform)
 
     auto issue = [&](int s) {
@@ -639,26 +640,27 @@ __device__ __forceinline__ void lpr_stream(const FHArgs& a, const uint16_t* pool
                 unsigned pend = ~Fm & (Im | (Lm << 1) | (Fm >> 1)) & 0x1eu;
                 const bool last_step = (s == nseg - 1) && (t == tend - 1);
                 bool first_iter = true;
-                for (;;) {
+                for (;;) {  // every pass queues the next pending chunk of each lane; a round runs as soon as 32 items wait
                     const bool want = pend != 0u;
                     const unsigned bal = __ballot_sync(kFull, want);
                     if (first_iter) { quiet_hint = bal == 0u; first_iter = false; }
-                    const int np = __popc(bal);
-                    if (qn + np > kQCap || (bal == 0u && last_step && qn > 0)) {
-                        lpr_round(ws, qn, r, a, sink);
-                        qn = 0;
-                    }
-                    if (bal == 0u) break;
                     if (want) {
                         const int j = __ffs(pend) - 1;  // bit j <-> chunk vc0 + j - 2
                         pend &= pend - 1u;
-                        const int slot = qn + __popc(bal & ((1u << lane) - 1u));
+                        const int slot = (qh + qn + __popc(bal & ((1u << lane) - 1u))) & (kQRing - 1);
                         const unsigned sk = j == 1 ? am_key : (j == 2 ? a0_key : (j == 3 ? a1_key : a2_key));
                         const unsigned sn = j == 1 ? am_n : (j == 2 ? a0_n : (j == 3 ? a1_n : a2_n));
                         const unsigned ss = j == 1 ? am_sw : (j == 2 ? a0_sw : (j == 3 ? a1_sw : a2_sw));
                         ws.q_hdr[slot] = make_uint4((unsigned)lane | ((unsigned)(vc0 + j - 1) << 5), sk, sn, ss);
                     }
-                    qn += np;
+                    qn += __popc(bal);
+                    if (qn >= kQCap || (bal == 0u && last_step && qn > 0)) {
+                        const int take = min(qn, kQCap);
+                        lpr_round(ws, qh, take, r, a, sink);
+                        qh = (qh + take) & (kQRing - 1);
+                        qn -= take;
+                    }
+                    if (bal == 0u) break;
                 }
                 // carry to the next block
                 Fm = (Fm >> 4) & 0x2u;

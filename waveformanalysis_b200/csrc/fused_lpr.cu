@@ -13,15 +13,17 @@
 //     chunks only feed a per-lane running aggregate (first arg-min key, count, sum) - they are
 //     interior to a run.  Every run start and end lies in a non-FULL chunk that is MIXED, follows
 //     an above-threshold sample or precedes a FULL chunk; those chunks become ITEMS: the lane
-//     copies the chunk with both neighbours (48 bytes: the extensions, <= 8 samples, live there)
-//     plus a snapshot of its FULL-chunk aggregate into a 32-entry per-warp queue;
-//   * whenever the queue fills, the warp runs a DENSE ROUND: lane t takes item t whoever owns it,
-//     fetches the owner's record constants by shuffle, walks the runs of that chunk, and stitches
+//     queues (owner, chunk index, snapshot of its FULL-chunk aggregate) in a 64-slot per-warp ring;
+//   * whenever 32 items wait, the warp runs a DENSE ROUND: lane t takes item t whoever owns it,
+//     fetches the owner's record constants by shuffle, re-reads the chunk and its two neighbours
+//     from L2 (the extensions, <= 8 samples, live there), walks the runs of that chunk, and stitches
 //     "run still open at the chunk end" fragments to the next item of the same record through a
 //     per-owner carry in shared memory (the items of one record are consecutive in chunk order
 //     and only FULL chunks can lie between the two ends of a run).  Finished hits carry their
-//     owner and per-record ordinal into a per-warp pool; one decoupled look-back per 128-record
-//     tile gives the first output row; rows are assembled one hit per lane.
+//     owner and per-record ordinal into a per-warp pool in global memory (L2 resident, double
+//     buffered); one decoupled look-back per 128-record tile gives the first output row - resolved
+//     one tile LATER, after the block has streamed its next tile, so nobody waits for a
+//     predecessor - and the rows are assembled one hit per lane.
 //
 // Reference semantics: see fused_features_hits.cu (same arithmetic, same results).
 #include <cuda.h>

@@ -187,7 +187,9 @@ struct DirectSink {  // rows straight to the output (records whose hits did not 
 // above threshold <=> kv <= kmax, signal side <=> kv <= kin): a 32-bit key kv << 16 | sample index
 // whose minimum is the first arg-max of the signal, and count << 21 | sum(kv) of the signal-side
 // samples (at most 24 samples per fragment, so the packed sum cannot carry into the count).
-template <typename Sink>
+// EXT22: both extensions are two samples (the defaults): the four neighbour samples are decoded once per
+// round and every fragment is one unrolled masked pass over the 12-sample window, all in registers.
+template <bool EXT22, typename Sink>
 __device__ __forceinline__ void lpr_round(WarpHits& ws, int qh, int qn, const LaneRec& r, const FHArgs& a, Sink& sink) {
     __syncwarp();  // the pushes are visible
     const int lane = lane_id();
@@ -219,8 +221,10 @@ __device__ __forceinline__ void lpr_round(WarpHits& ws, int qh, int qn, const La
     const uint4 c0q = (act && P - 1 >= 0 && P - 1 < o_nch) ? __ldg(gsrc) : zero4;
     const uint4 c1 = (act && P >= 0 && P < o_nch) ? __ldg(gsrc + 1) : zero4;
     const uint4 c2q = (act && P + 1 < o_nch) ? __ldg(gsrc + 2) : zero4;
-    ws.q_nb[0][lane] = c0q;
-    ws.q_nb[1][lane] = c2q;
+    if (!EXT22) {
+        ws.q_nb[0][lane] = c0q;
+        ws.q_nb[1][lane] = c2q;
+    }
     // keys of the item's own chunk, packed contributions, above-threshold mask
     unsigned ckey[8], cval[8];
     unsigned m8 = 0;
@@ -247,12 +251,42 @@ __device__ __forceinline__ void lpr_round(WarpHits& ws, int qh, int qn, const La
     int ord_base = act ? ws.carry_n[src] : 0;
     for (unsigned m = lt; m; m &= m - 1) ord_base += ws.stage_n[__ffs(m) - 1];
 
-    // aggregate of samples [a0, a1): own chunk from registers, the neighbours' few samples from the queue
+    // EXT22: samples i0-2, i0-1 (end of chunk P-1) and i0+8, i0+9 (start of chunk P+1)
+    unsigned nkey[4], nval[4];
+    if (EXT22) {
+        const int kl0 = (int)((c0q.w & 0xffffu) ^ cx), kl1 = (int)((c0q.w >> 16) ^ cx);
+        const int kr0 = (i0 + 8 < o_len) ? (int)((c2q.x & 0xffffu) ^ cx) : padkv;
+        const int kr1 = (i0 + 9 < o_len) ? (int)((c2q.x >> 16) ^ cx) : padkv;
+        nkey[0] = ((unsigned)kl0 << 16) + (unsigned)(i0 - 2);
+        nkey[1] = ((unsigned)kl1 << 16) + (unsigned)(i0 - 1);
+        nkey[2] = ((unsigned)kr0 << 16) + (unsigned)(i0 + 8);
+        nkey[3] = ((unsigned)kr1 << 16) + (unsigned)(i0 + 9);
+        nval[0] = (kl0 <= kin) ? kOne + (unsigned)kl0 : 0u;
+        nval[1] = (kl1 <= kin) ? kOne + (unsigned)kl1 : 0u;
+        nval[2] = (kr0 <= kin) ? kOne + (unsigned)kr0 : 0u;
+        nval[3] = (kr1 <= kin) ? kOne + (unsigned)kr1 : 0u;
+    }
+    // aggregate of samples [a0, a1) (always inside [i0 - left, i0 + 8 + right)): own chunk from registers, the
+    // neighbours' few samples from registers (EXT22) or from the round's scratch rows
     auto frag = [&](int a0, int a1, unsigned& key, unsigned& acc) {
+        if (EXT22) {
+            const int wlo = min(max(a0 - (i0 - 2), 0), 12), whi = min(max(a1 - (i0 - 2), 0), 12);
+            const unsigned msk = ((1u << whi) - 1u) & ~((1u << wlo) - 1u);  // bit w <-> sample i0 - 2 + w
+            if (msk & 1u) { key = min(key, nkey[0]); acc += nval[0]; }
+            if (msk & 2u) { key = min(key, nkey[1]); acc += nval[1]; }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const bool in = (i0 + j >= a0) && (i0 + j < a1);
-            if (in) { key = min(key, ckey[j]); acc += cval[j]; }
+            for (int j = 0; j < 8; ++j)
+                if (msk & (4u << j)) { key = min(key, ckey[j]); acc += cval[j]; }
+            if (msk & 0x400u) { key = min(key, nkey[2]); acc += nval[2]; }
+            if (msk & 0x800u) { key = min(key, nkey[3]); acc += nval[3]; }
+            return;
+        }
+        {
+            const int jlo = min(max(a0 - i0, 0), 8), jhi = min(max(a1 - i0, 0), 8);
+            const unsigned msk = ((1u << jhi) - 1u) & ~((1u << jlo) - 1u);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (msk & (1u << j)) { key = min(key, ckey[j]); acc += cval[j]; }
         }
         // the neighbours' samples: warp-uniform trip counts (the extensions), predicated bodies
         const unsigned short* lo_row = reinterpret_cast<const unsigned short*>(&ws.q_nb[0][lane]);
@@ -369,7 +403,7 @@ struct ChunkSum {
     unsigned n, sw;     // signal-side samples and their sum (FULL chunks)
 };
 
-template <bool FEAT, bool HITS, bool SGN, typename Sink>
+template <bool FEAT, bool HITS, bool SGN, bool EXT22, typename Sink>
 __device__ __forceinline__ void lpr_stream(const FHArgs& a, const uint16_t* pool, const LaneRec& r, int sc, const Ring& ring,
                                            int p0, int p1, int c0, int c1, FeatState& fs, WarpHits& ws, Sink& sink) {
     const int lane = lane_id();
@@ -658,7 +692,7 @@ __device__ __forceinline__ void lpr_stream(const FHArgs& a, const uint16_t* pool
                     qn += __popc(bal);
                     if (qn >= kQCap || (bal == 0u && last_step && qn > 0)) {
                         const int take = min(qn, kQCap);
-                        lpr_round(ws, qh, take, r, a, sink);
+                        lpr_round<EXT22>(ws, qh, take, r, a, sink);
                         qh = (qh + take) & (kQRing - 1);
                         qn -= take;
                     }
@@ -677,7 +711,7 @@ __device__ __forceinline__ void lpr_stream(const FHArgs& a, const uint16_t* pool
 }
 
 // ---- the kernel --------------------------------------------------------------------------------
-template <bool FEAT, bool HITS, bool SGN>
+template <bool FEAT, bool HITS, bool SGN, bool EXT22>
 __global__ void __launch_bounds__(kLprWarps * 32, WFB_LPR_MINBLOCKS) lpr_kernel(const FHArgs a, const int sc, const __grid_constant__ CUtensorMap tmap,
                                                              const int have_tmap, const int ent_cap) {
     extern __shared__ __align__(128) uint8_t dyn_smem[];  // [warp][kNBuf][lane] slots of a.slot_bytes
@@ -825,7 +859,7 @@ __global__ void __launch_bounds__(kLprWarps * 32, WFB_LPR_MINBLOCKS) lpr_kernel(
         }
         __syncwarp();
         PoolSink psink{&ws, gp + (size_t)cur * a.gpool_cap, ent_cap};
-        lpr_stream<FEAT, HITS, SGN>(a, pool, r, sc, ring, p0, p1, c0, c1, fs, ws, psink);
+        lpr_stream<FEAT, HITS, SGN, EXT22>(a, pool, r, sc, ring, p0, p1, c0, c1, fs, ws, psink);
 
         // ---------------- features of my record
         if (FEAT && have) {
@@ -944,7 +978,7 @@ __global__ void __launch_bounds__(kLprWarps * 32, WFB_LPR_MINBLOCKS) lpr_kernel(
                 DirectSink dsink;
                 dsink.my_row0 = base + rel;
                 dsink.my_active = (ovf >> lane) & 1u;
-                lpr_stream<false, true, SGN>(a, pool, r, sc, ring, 0, 0, 0, 0, fs2, ws, dsink);
+                lpr_stream<false, true, SGN, EXT22>(a, pool, r, sc, ring, 0, 0, 0, 0, fs2, ws, dsink);
             }
             pend = false;
         } else {
@@ -1016,14 +1050,15 @@ int launch_lpr(FHArgs a, int flags, cudaStream_t st) {
         WFB_CUDA(cudaGetLastError());
         return WFB_OK;
     };
+    const bool e22 = h && a.p.left_extension == 2 && a.p.right_extension == 2;  // the defaults (hit_finder.py:104-105)
     if (a.p.signed_samples) {
-        if (f && h) return go(lpr_kernel<true, true, true>);
-        if (f) return go(lpr_kernel<true, false, true>);
-        return go(lpr_kernel<false, true, true>);
+        if (f && h) return e22 ? go(lpr_kernel<true, true, true, true>) : go(lpr_kernel<true, true, true, false>);
+        if (f) return go(lpr_kernel<true, false, true, false>);
+        return e22 ? go(lpr_kernel<false, true, true, true>) : go(lpr_kernel<false, true, true, false>);
     }
-    if (f && h) return go(lpr_kernel<true, true, false>);
-    if (f) return go(lpr_kernel<true, false, false>);
-    return go(lpr_kernel<false, true, false>);
+    if (f && h) return e22 ? go(lpr_kernel<true, true, false, true>) : go(lpr_kernel<true, true, false, false>);
+    if (f) return go(lpr_kernel<true, false, false, false>);
+    return e22 ? go(lpr_kernel<false, true, false, true>) : go(lpr_kernel<false, true, false, false>);
 }
 
 }  // namespace wfb

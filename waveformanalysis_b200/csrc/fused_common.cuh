@@ -31,9 +31,9 @@ struct FHArgs {
     unsigned long long* tile_state;  // [n_tiles] decoupled look-back descriptors
     unsigned long long* group_desc;  // [n_groups] per 32 tiles: finished tiles << 48 | sum of their hit counts
     unsigned long long* group_pref;  // [n_groups] status | exclusive prefix of the group's first tile
-    uint4* gpool;                    // hit entries of the lane-per-record kernel: [block][warp][2][gpool_cap] (L2 resident)
+    uint4* gpool;                    // hit entries of the lane-per-record kernel: [resident warp][2][gpool_cap] (L2 resident)
     int gpool_cap;
-    int gpool_blocks;                // blocks the pool area was sized for
+    int gpool_warps;                 // warps the pool area was sized for
     unsigned* ticket;                // dynamic tile counter
     int* err_flag;
     int n_tiles;

@@ -777,10 +777,10 @@ __global__ void max_len_kernel(const wfb_rec_meta* meta, long long n, int* out) 
 struct WsLayout {
     size_t ticket, err, lmax, state, gdesc, gpref, total;  // total: end of the part that is cleared per call
     size_t gpool, end;
-    int gpool_blocks;
+    int gpool_warps;
 };
 constexpr int kPoolCap = 512;        // hits per warp per tile kept for the deferred row pass (16 B each)
-constexpr int kPoolBlocksMax = 640;  // resident blocks of the lane-per-record kernel the pool is sized for
+constexpr int kPoolWarpsMax = 2560;  // resident warps of the lane-per-record kernel the pool is sized for (16 per SM)
 static WsLayout ws_layout(long long n) {
     long long n_tiles = (n + 31) / 32;  // smallest tile of the kernel variants (one warp in the lane-per-record kernel)
     WsLayout w;
@@ -792,10 +792,10 @@ static WsLayout ws_layout(long long n) {
     w.gdesc = w.state + (size_t)n_tiles * 8;
     w.gpref = w.gdesc + (size_t)n_groups * 8;
     w.total = w.gpref + (size_t)n_groups * 8;
-    // hit pool of the lane-per-record kernel: [block][4 warps][2 halves][kPoolCap] entries, never cleared
+    // hit pool of the lane-per-record kernel: [resident warp][2 halves][kPoolCap] entries, never cleared
     w.gpool = (w.total + 255) & ~(size_t)255;
-    w.gpool_blocks = (int)std::min<long long>(kPoolBlocksMax, (n + 127) / 128);
-    w.end = w.gpool + (size_t)w.gpool_blocks * 4 * 2 * kPoolCap * 16;
+    w.gpool_warps = (int)std::min<long long>(kPoolWarpsMax, (n + 31) / 32 + 8);
+    w.end = w.gpool + (size_t)w.gpool_warps * 2 * kPoolCap * 16;
     return w;
 }
 
@@ -893,7 +893,7 @@ extern "C" int wfb_features_hits(const void* pool_dev, int64_t pool_len, const w
     a.group_pref = reinterpret_cast<unsigned long long*>(ws + w.gpref);
     a.gpool = reinterpret_cast<uint4*>(ws + w.gpool);
     a.gpool_cap = kPoolCap;
-    a.gpool_blocks = w.gpool_blocks;
+    a.gpool_warps = w.gpool_warps;
     a.n_tiles = 0;
     a.slot_bytes = 0;
     a.ring_bytes = 0;

@@ -43,7 +43,7 @@ constexpr int kLprTile = kLprWarps * 32;  // records per tile / look-back unit
 #ifndef WFB_LPR_MINBLOCKS
 #define WFB_LPR_MINBLOCKS 3  // blocks per SM the register allocation must allow
 #endif
-static_assert(WFB_LPR_WARPS <= 4, "the workspace's hit pool is sized for four warps per block");
+static_assert(WFB_LPR_WARPS <= 8, "a block has at most eight warps (workspace hit pool, block scan)");
 constexpr int kHist = 2;                  // chunks of history in front of each segment
 constexpr int kMaxExt = 8;                // extensions must fit the neighbouring chunk
 constexpr int kNBuf = 2;                  // slot buffers per lane
@@ -1045,7 +1045,7 @@ int launch_lpr(FHArgs a, int flags, cudaStream_t st) {
             return WFB_ERR_CUDA;
         }
         int grid = (int)std::min<long long>((long long)sm_count() * per_sm, a.n_tiles);
-        if (h) grid = std::min(grid, a.gpool_blocks);
+        if (h) grid = std::min(grid, a.gpool_warps / kLprWarps);
         kern<<<grid, kLprWarps * 32, dyn, st>>>(a, sc, tmap, have_tmap, ent_cap);
         WFB_CUDA(cudaGetLastError());
         return WFB_OK;

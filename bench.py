@@ -138,7 +138,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -354,7 +354,7 @@ def run_ours(args):
             "gpu_launches": args.steps * 1,
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -408,8 +408,27 @@ def run_e2e(args, engine, torch, barrier, max_over_ranks, sum_over_ranks, rank):
     }
 
 
+_RESULT_FD = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    global _RESULT_FD
     args = parse_args()
+    # library chatter (the NCCL version banner, warnings printed by child processes) must not land on stdout:
+    # keep the original stdout for the result line only and point fd 1 at stderr for everything else
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

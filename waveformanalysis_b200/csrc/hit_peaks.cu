@@ -187,7 +187,58 @@ __global__ void __launch_bounds__(kPeakWarps * 32) find_peaks_kernel(const void*
             return;
         }
     }
-    for (int i = lane; i < r.m; i += 32) x[i] = detection_value(r, i);
+    // ---- stage the detection signal.  The sample format is resolved once, outside the loop, and with the
+    // derivative every sample is read from global memory once: lane i hands w[i] to its left neighbour's diff
+    {
+        const long long o = off;
+        const float b32 = (float)mrec.baseline;
+        const bool pos = mrec.polarity == WFB_POL_POSITIVE;
+        auto stage = [&](auto loadf, auto difff, auto levelf) {
+            const int m = r.m;
+            if (r.deriv) {
+                for (int b0 = 0; b0 < m; b0 += 32) {
+                    const int i = b0 + lane;
+                    const double wi = (i <= m) ? loadf(i) : 0.0;  // m = len - 1: w[m] exists
+                    double wn = shfl_f64(wi, (lane + 1) & 31);
+                    if (lane == 31 && i + 1 <= m) wn = loadf(i + 1);
+                    if (i < m) x[i] = difff(wn, wi);
+                }
+            } else {
+                for (int i = lane; i < m; i += 32) x[i] = levelf(loadf(i));
+            }
+        };
+        const double bl = r.baseline;
+        auto lvl_sub = [&](double w) { return __dsub_rn(bl, w); };
+        auto lvl_id = [](double w) { return w; };
+        switch (p.wave_kind) {
+            case WFB_WAVE_AOS_I16:  // np.diff on int16 stays int16, so does the negation
+                stage([&](int i) { return (double)static_cast<const short*>(waves)[o + i]; },
+                      [](double wn, double wi) { return (double)(short)(-(int)(short)((int)wn - (int)wi)); }, lvl_sub);
+                break;
+            case WFB_WAVE_AOS_F32:
+                stage([&](int i) { return (double)static_cast<const float*>(waves)[o + i]; },
+                      [](double wn, double wi) { return (double)(-__fsub_rn((float)wn, (float)wi)); }, lvl_sub);
+                break;
+            case WFB_WAVE_AOS_F32_AS_F64:  // streaming: float64 copy of the row
+                stage([&](int i) { return (double)static_cast<const float*>(waves)[o + i]; },
+                      [](double wn, double wi) { return -__dsub_rn(wn, wi); }, lvl_sub);
+                break;
+            case WFB_WAVE_REC_U16:  // records: +diff of the float64 copy of -RecordsView.signals() (records_view.py:152-169)
+                stage([&](int i) {
+                          const float sv = (float)static_cast<const unsigned short*>(waves)[o + i];
+                          return pos ? (double)__fsub_rn(sv, b32) : (double)__fsub_rn(b32, sv);
+                      },
+                      [](double wn, double wi) { return __dsub_rn(wn, wi); }, lvl_id);
+                break;
+            default:
+                stage([&](int i) {
+                          const float sv = static_cast<const float*>(waves)[o + i];
+                          return pos ? (double)__fsub_rn(sv, b32) : (double)__fsub_rn(b32, sv);
+                      },
+                      [](double wn, double wi) { return __dsub_rn(wn, wi); }, lvl_id);
+                break;
+        }
+    }
     __syncwarp();
 
     // ---- local maxima + height / threshold conditions, compacted in order
@@ -196,15 +247,18 @@ __global__ void __launch_bounds__(kPeakWarps * 32) find_peaks_kernel(const void*
     for (int b0 = 0; b0 < m; b0 += 32) {
         const int i = b0 + lane;
         int pos = -1;
-        if (i >= 1 && i < m - 1 && x[i - 1] < x[i]) {
+        // the height condition first: a plateau has one value, so x[pos] == x[i], and most samples (noise) fail it -
+        // 32 samples without a candidate cost one load, one compare and one vote
+        const double xi = (i >= 1 && i < m - 1) ? x[i] : 0.0;
+        const bool cand = i >= 1 && i < m - 1 && xi >= p.height;
+        if (!__any_sync(kFull, cand)) continue;
+        if (cand && x[i - 1] < xi) {
             int ahead = i + 1;
-            while (ahead < m - 1 && x[ahead] == x[i]) ++ahead;
-            if (x[ahead] < x[i]) pos = (i + ahead - 1) >> 1;
+            while (ahead < m - 1 && x[ahead] == xi) ++ahead;
+            if (x[ahead] < xi) pos = (i + ahead - 1) >> 1;
         }
-        if (pos >= 0) {
-            bool ok = x[pos] >= p.height;
-            if (ok && p.has_threshold) ok = fmin(__dsub_rn(x[pos], x[pos - 1]), __dsub_rn(x[pos], x[pos + 1])) >= p.threshold;
-            if (!ok) pos = -1;
+        if (pos >= 0 && p.has_threshold) {
+            if (!(fmin(__dsub_rn(x[pos], x[pos - 1]), __dsub_rn(x[pos], x[pos + 1])) >= p.threshold)) pos = -1;
         }
         const unsigned bal = __ballot_sync(kFull, pos >= 0);
         if (pos >= 0) {

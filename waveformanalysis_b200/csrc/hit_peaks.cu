@@ -196,12 +196,23 @@ __global__ void __launch_bounds__(kPeakWarps * 32) find_peaks_kernel(const void*
         auto stage = [&](auto loadf, auto difff, auto levelf) {
             const int m = r.m;
             if (r.deriv) {
-                for (int b0 = 0; b0 < m; b0 += 32) {
-                    const int i = b0 + lane;
-                    const double wi = (i <= m) ? loadf(i) : 0.0;  // m = len - 1: w[m] exists
-                    double wn = shfl_f64(wi, (lane + 1) & 31);
-                    if (lane == 31 && i + 1 <= m) wn = loadf(i + 1);
-                    if (i < m) x[i] = difff(wn, wi);
+                constexpr int U = 8;  // 32-sample groups in flight per pass: the loads are issued before any is used
+                for (int b0 = 0; b0 < m; b0 += 32 * U) {
+                    double wv[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int i = b0 + 32 * u + lane;
+                        wv[u] = (i <= m) ? loadf(i) : 0.0;  // m = len - 1: w[m] exists
+                    }
+                    const double wlast = (lane == 31 && b0 + 32 * U <= m) ? loadf(b0 + 32 * U) : 0.0;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int i = b0 + 32 * u + lane;
+                        double wn = shfl_f64(wv[u], (lane + 1) & 31);
+                        const double nx = (u + 1 < U) ? shfl_f64(wv[(u + 1 < U) ? u + 1 : u], 0) : wlast;  // lane 31's successor
+                        if (lane == 31) wn = nx;
+                        if (i < m) x[i] = difff(wn, wv[u]);
+                    }
                 }
             } else {
                 for (int i = lane; i < m; i += 32) x[i] = levelf(loadf(i));

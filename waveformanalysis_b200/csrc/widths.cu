@@ -197,17 +197,19 @@ struct ChargeSrc {
     // one load per 8 (uint16) / 4 (float32) samples instead of one per sample (32 sectors per warp load)
     const uint4* chunks;   // pool aligned down to 16 bytes
     long long first;       // element index of w[0] relative to `chunks`
+    long long last;        // last chunk that may be read (the record's own last chunk)
     mutable long long cached;
-    mutable uint4 q;
+    mutable uint4 q, qn;   // the current chunk and the one behind it, fetched one chunk ahead of its use
     __device__ __forceinline__ T sample(int i) const {
         constexpr int PER = 16 / (int)sizeof(T);
-        const long long e = first + i;
+        const int e = (int)first + i;  // first < PER, i < 2^31 - PER
         const long long c = e / PER;
         if (c != cached) {
-            q = __ldg(chunks + c);
+            q = (c == cached + 1) ? qn : __ldg(chunks + c);
+            if (c + 1 <= last) qn = __ldg(chunks + c + 1);  // in flight while this chunk's samples are consumed
             cached = c;
         }
-        const int k = (int)(e % PER);
+        const int k = e % PER;
         if (sizeof(T) == 2) {
             const unsigned word = (k < 4) ? ((k < 2) ? q.x : q.y) : ((k < 6) ? q.z : q.w);
             const unsigned short h = (unsigned short)(word >> ((k & 1) * 16));
@@ -245,9 +247,10 @@ __global__ void __launch_bounds__(128) width_integral_kernel(const T* __restrict
         const uintptr_t addr = reinterpret_cast<uintptr_t>(pool + off);
         x.chunks = reinterpret_cast<const uint4*>(addr & ~(uintptr_t)15);
         x.first = (long long)((addr & 15) / sizeof(T));
-        x.cached = -1;
+        x.cached = -2;  // neither this chunk nor its predecessor is in registers
         x.q = make_uint4(0u, 0u, 0u, 0u);
-        (void)PER;
+        x.qn = x.q;
+        x.last = (L > 0) ? (x.first + L - 1) / PER : -1;
     }
     x.b = m.baseline;
     x.b32 = (float)m.baseline;

@@ -38,12 +38,54 @@ __device__ float numpy_mean_f32(const float* w, int n) {
 template <typename F>
 __device__ __forceinline__ int warp_find_first(int lo, int hi, F pred) {
     const int lane = lane_id();
-    for (int base = lo; base < hi; base += 32) {
-        int i = base + lane;
-        unsigned m = __ballot_sync(kFull, i < hi && pred(i));
-        if (m) return base + __ffs(m) - 1;
+    // four 32-sample groups per pass: their loads are issued together, so a long scan (the rising edge is searched
+    // from the start of the record) pays the memory latency once per 128 samples
+    for (int base = lo; base < hi; base += 128) {
+        const int i0 = base + lane, i1 = i0 + 32, i2 = i0 + 64, i3 = i0 + 96;
+        const bool p0 = i0 < hi && pred(i0);
+        const bool p1 = i1 < hi && pred(i1);
+        const bool p2 = i2 < hi && pred(i2);
+        const bool p3 = i3 < hi && pred(i3);
+        const unsigned m0 = __ballot_sync(kFull, p0), m1 = __ballot_sync(kFull, p1);
+        const unsigned m2 = __ballot_sync(kFull, p2), m3 = __ballot_sync(kFull, p3);
+        if (m0) return base + __ffs(m0) - 1;
+        if (m1) return base + 32 + __ffs(m1) - 1;
+        if (m2) return base + 64 + __ffs(m2) - 1;
+        if (m3) return base + 96 + __ffs(m3) - 1;
     }
     return -1;
+}
+
+// the same for two predicates over one scan (both thresholds of an edge are searched in the same slice): every
+// sample is loaded once; the scan ends when both have been found
+template <typename V, typename PA, typename PB>
+__device__ __forceinline__ void warp_find_first2(int lo, int hi, V val, PA pa, PB pb, int& ia, int& ib) {
+    const int lane = lane_id();
+    ia = -1;
+    ib = -1;
+    for (int base = lo; base < hi && (ia < 0 || ib < 0); base += 128) {
+        unsigned ma[4], mb[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = base + 32 * u + lane;
+            const bool in = i < hi;
+            const auto v = val(in ? i : lo);
+            ma[u] = __ballot_sync(kFull, in && pa(v));
+            mb[u] = __ballot_sync(kFull, in && pb(v));
+        }
+        if (ia < 0) {
+            if (ma[0]) ia = base + __ffs(ma[0]) - 1;
+            else if (ma[1]) ia = base + 32 + __ffs(ma[1]) - 1;
+            else if (ma[2]) ia = base + 64 + __ffs(ma[2]) - 1;
+            else if (ma[3]) ia = base + 96 + __ffs(ma[3]) - 1;
+        }
+        if (ib < 0) {
+            if (mb[0]) ib = base + __ffs(mb[0]) - 1;
+            else if (mb[1]) ib = base + 32 + __ffs(mb[1]) - 1;
+            else if (mb[2]) ib = base + 64 + __ffs(mb[2]) - 1;
+            else if (mb[3]) ib = base + 96 + __ffs(mb[3]) - 1;
+        }
+    }
 }
 
 template <typename T>
@@ -106,19 +148,21 @@ __global__ void __launch_bounds__(256) waveform_width_kernel(const T* __restrict
     // crossing positions: value + kind (interpolated positions are float32 for float32 rows)
     double cross[4];
     bool found[4];
+    // both thresholds of an edge in one scan: rising edge in wave[:pos], falling edge in wave[pos:]
+    int idx4[4];
+    if (F32) {
+        const float ta = t32[0], tb = t32[1], tc = t32[2], td = t32[3];
+        warp_find_first2(0, left_hi, [&](int i) { return wc32(i); }, [&](float v) { return v >= ta; }, [&](float v) { return v >= tb; }, idx4[0], idx4[1]);
+        warp_find_first2(pos, length, [&](int i) { return wc32(i); }, [&](float v) { return v <= tc; }, [&](float v) { return v <= td; }, idx4[2], idx4[3]);
+    } else {
+        const double ta = t64[0], tb = t64[1], tc = t64[2], td = t64[3];
+        warp_find_first2(0, left_hi, [&](int i) { return wc64(i); }, [&](double v) { return v >= ta; }, [&](double v) { return v >= tb; }, idx4[0], idx4[1]);
+        warp_find_first2(pos, length, [&](int i) { return wc64(i); }, [&](double v) { return v <= tc; }, [&](double v) { return v <= td; }, idx4[2], idx4[3]);
+    }
     for (int k = 0; k < 4; ++k) {
         const bool rising = k < 2;
-        const int lo = rising ? 0 : pos, hi = rising ? left_hi : length;
-        int idx;
-        if (F32) {
-            const float th = t32[k];
-            idx = rising ? warp_find_first(lo, hi, [&](int i) { return wc32(i) >= th; })
-                         : warp_find_first(lo, hi, [&](int i) { return wc32(i) <= th; });
-        } else {
-            const double th = t64[k];
-            idx = rising ? warp_find_first(lo, hi, [&](int i) { return wc64(i) >= th; })
-                         : warp_find_first(lo, hi, [&](int i) { return wc64(i) <= th; });
-        }
+        const int lo = rising ? 0 : pos;
+        const int idx = idx4[k];
         found[k] = idx >= 0;
         cross[k] = 0.0;
         if (idx >= 0) {

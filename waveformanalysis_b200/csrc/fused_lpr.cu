@@ -44,7 +44,7 @@ constexpr int kLprTile = kLprWarps * 32;  // records per tile / look-back unit
 #define WFB_LPR_MINBLOCKS 3  // blocks per SM the register allocation must allow
 #endif
 static_assert(WFB_LPR_WARPS <= 8, "a block has at most eight warps (workspace hit pool, block scan)");
-constexpr int kHist = 2;                  // chunks of history in front of each segment
+constexpr int kHist = 0;                  // chunks of history in front of each segment (none: items re-read their chunks from L2)
 constexpr int kMaxExt = 8;                // extensions must fit the neighbouring chunk
 constexpr int kNBuf = 2;                  // slot buffers per lane
 constexpr int kQCap = 32;                 // items per dense round
@@ -712,7 +712,7 @@ __device__ __forceinline__ void lpr_stream(const FHArgs& a, const uint16_t* pool
 
 // ---- the kernel --------------------------------------------------------------------------------
 template <bool FEAT, bool HITS, bool SGN, bool EXT22>
-__global__ void __launch_bounds__(kLprWarps * 32, WFB_LPR_MINBLOCKS) lpr_kernel(const FHArgs a, const int sc, const __grid_constant__ CUtensorMap tmap,
+__global__ void __launch_bounds__(kLprWarps * 32, (HITS && !FEAT) ? WFB_LPR_MINBLOCKS + 1 : WFB_LPR_MINBLOCKS) lpr_kernel(const FHArgs a, const int sc, const __grid_constant__ CUtensorMap tmap,
                                                              const int have_tmap, const int ent_cap) {
     extern __shared__ __align__(128) uint8_t dyn_smem[];  // [warp][kNBuf][lane] slots of a.slot_bytes
     __shared__ __align__(16) WarpHits s_hits[HITS ? kLprWarps : 1];
@@ -999,7 +999,10 @@ int launch_lpr(FHArgs a, int flags, cudaStream_t st) {
     if (a.lmax >= 65536 - 16) return 1;  // positions are packed in 16 bits
     if (a.p.left_extension > kMaxExt || a.p.right_extension > kMaxExt) return 1;
     // segment length in chunks: kHist history chunks + sc new chunks per slot
-    int sc = 8;  // a multiple of the 4-chunk scan block
+    // a multiple of the 4-chunk scan block.  Measured per mode (profiles/README.md): features + hits 12 chunks at three
+    // blocks per SM; hits only 8 chunks, whose smaller slots and 128 registers let a fourth block in; features only 16
+    const bool want_f = flags & WFB_DO_FEATURES, want_h = flags & WFB_DO_HITS;
+    int sc = (want_f && want_h) ? 12 : (want_h ? 8 : 16);
     if (const char* e = getenv("WFB_LPR_SC")) sc = std::max(4, std::min(28, atoi(e) & ~3));
     int ent_cap = a.gpool_cap;  // WFB_LPR_POOL shrinks the per-warp hit pool (exercises the overflow path in tests)
     if (const char* e = getenv("WFB_LPR_POOL")) ent_cap = std::max(0, std::min(a.gpool_cap, atoi(e)));

@@ -33,6 +33,7 @@ struct FHArgs {
     unsigned long long* group_pref;  // [n_groups] status | exclusive prefix of the group's first tile
     uint4* gpool;                    // hit entries of the lane-per-record kernel: [resident warp][2][gpool_cap] (L2 resident)
     int gpool_cap;
+    int n_slots;                     // warp-per-record kernel: slots of the per-warp TMA ring in use (2 or 3)
     int gpool_warps;                 // warps the pool area was sized for
     unsigned* ticket;                // dynamic tile counter
     int* err_flag;

@@ -514,6 +514,7 @@ __global__ void __launch_bounds__(kWarps * 32) fused_features_hits_kernel(const 
     const T* pool = static_cast<const T*>(a.pool);
     uint8_t* ring = dyn_smem + (size_t)warp * a.ring_bytes;
     unsigned long long* bars = &s_bar[warp * kSlots];
+    const int nslots = a.n_slots;  // ring depth in use: 2 or 3 (warp-uniform)
     if (STAGED) {
         if (lane < kSlots) mbar_init(&bars[lane], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -589,7 +590,7 @@ __global__ void __launch_bounds__(kWarps * 32) fused_features_hits_kernel(const 
         };
         if (STAGED) {
             fence_proxy_async();  // generic-proxy accesses of the ring (previous tile) before the refill
-            if (lane < kSlots - 1) issue(lane);
+            if (lane < nslots - 1) issue(lane);
         }
 
         // ---------------- phase A: the warp scans its 32 records one after the other
@@ -616,14 +617,14 @@ __global__ void __launch_bounds__(kWarps * 32) fused_features_hits_kernel(const 
             StageSink sink{HITS ? &s_ent[warp][used] : nullptr, kEntPerWarp - used, 0, (unsigned)j};
             FeatAcc fa = {0.f, 0.f, 0.f, 0.f};
             if (STAGED) {
-                const int slot = j % kSlots;
-                // prefetch record j + kSlots - 1 into the slot record j - 1 just left
-                const int jn = j + kSlots - 1;
+                const int slot = j % nslots;
+                // prefetch record j + nslots - 1 into the slot record j - 1 just left
+                const int jn = j + nslots - 1;
                 if (jn < 32) {
                     __syncwarp();
                     if (lane == jn) {
                         fence_proxy_async();
-                        issue(jn % kSlots);
+                        issue(jn % nslots);
                     }
                 }
                 mbar_wait(&bars[slot], (phase_bits >> slot) & 1u);
@@ -647,8 +648,8 @@ __global__ void __launch_bounds__(kWarps * 32) fused_features_hits_kernel(const 
         }
         if (STAGED) {
             // drain the barriers of slots armed for records >= nrec (tail tile) so phases stay in step
-            for (int j = nrec; j < min(32, nrec + kSlots - 1); ++j) {
-                const int slot = j % kSlots;
+            for (int j = nrec; j < min(32, nrec + nslots - 1); ++j) {
+                const int slot = j % nslots;
                 mbar_wait(&bars[slot], (phase_bits >> slot) & 1u);
                 phase_bits ^= 1u << slot;
             }
@@ -827,12 +828,19 @@ static int launch_fused(FHArgs a, int flags, cudaStream_t st) {
     const char* force = getenv("WFB_FUSED_VARIANT");  // diagnostics: "global" | "staged"
     const bool want_global = force && !strcmp(force, "global");
     // three resident blocks per SM need <= ~64 KB each (ring + 20 KB of staged hits)
-    if (!want_global && slot * kSlots * kWarps <= 150 * 1024 && a.lmax < (1 << 27)) {
+    if (!want_global && slot * 2 * kWarps <= 150 * 1024 && a.lmax < (1 << 27)) {
+        // ring depth: three slots per warp unless two let more blocks share the SM (the staged hit pool of the
+        // hit variants is ~41 KB of static shared memory; float32 records of 800 samples: 1 block with 3 slots, 2 with 2)
+        const long long fixed = ((flags & WFB_DO_HITS) ? 42 : 1) * 1024 + 1024;
+        auto blocks = [&](int ns) { return (227 * 1024) / (std::max<long long>(slot * ns, kRowBufBytes) * kWarps + fixed); };
+        a.n_slots = (slot * kSlots * kWarps <= 150 * 1024 && blocks(kSlots) >= blocks(2)) ? kSlots : 2;
+        if (const char* e = getenv("WFB_FUSED_SLOTS")) a.n_slots = (atoi(e) == 2) ? 2 : ((slot * kSlots * kWarps <= 150 * 1024) ? 3 : 2);
         a.slot_bytes = (int)slot;
-        a.ring_bytes = (int)std::max<long long>(slot * kSlots, kRowBufBytes);
+        a.ring_bytes = (int)std::max<long long>(slot * a.n_slots, kRowBufBytes);
         return launch_variant<T, true>(a, flags, st);
     }
     a.slot_bytes = 0;
+    a.n_slots = kSlots;
     a.ring_bytes = kRowBufBytes;
     return launch_variant<T, false>(a, flags, st);
 }
@@ -897,6 +905,7 @@ extern "C" int wfb_features_hits(const void* pool_dev, int64_t pool_len, const w
     a.n_tiles = 0;
     a.slot_bytes = 0;
     a.ring_bytes = 0;
+    a.n_slots = kSlots;
     a.lmax = params->lmax;
     if (a.lmax <= 0) {
         // padded width = max event_length of the records passed (hit_finder.py:364); costs a sync

@@ -32,7 +32,7 @@ if args.summarise:
     alg = {
         "sg_filter_kernel": n * 6 * L, "bw_filter_kernel": n * 6 * L, "k1_gather_kernel": n * (4 * L + 126),
         "width_integral_kernel": n * (2 * L + 100), "waveform_width_kernel": None,
-        "find_peaks_kernel<0>": n * 4 * L, "find_peaks_kernel<1>": n * 4 * L,
+        "find_peaks_kernel<0>": n * 4 * L, "find_peaks_kernel<1>": None, "peaks_emit_cached_kernel": None,
     }
     peak = 6453.7
     print(f"{'kernel':44s} {'launches':>8s} {'total ms':>10s} {'alg GB/s':>10s} {'% of HBM peak':>14s}")

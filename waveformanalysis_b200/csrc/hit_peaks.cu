@@ -118,6 +118,55 @@ __device__ float peak_height(const PeakRec& r, double edge_start, double edge_en
     return (float)__dsub_rn(mx, mn);
 }
 
+// one packed HIT row (48 bytes) of a found peak
+__device__ __forceinline__ void write_peak_row(uint8_t* rows, long long row, const PeakRec& r, const wfb_rec_meta& mrec,
+                                               const wfb_peak_params& p, int pk, double lip, double rip) {
+    const float hgt = peak_height(r, lip, rip, p.height_method, p.height_window_extension);
+    const double step = __dmul_rn((double)mrec.dt, 1e3);
+    const long long ti = (long long)__dadd_rn((double)mrec.timestamp, __dmul_rn((double)pk, step));
+    unsigned* dst = reinterpret_cast<unsigned*>(rows + row * kPeakRowBytes);
+    dst[0] = (unsigned)pk;
+    dst[1] = 0u;
+    dst[2] = __float_as_uint(hgt);
+    dst[3] = 0u;  // integral (always 0.0 in the reference)
+    dst[4] = __float_as_uint((float)lip);
+    dst[5] = __float_as_uint((float)rip);
+    dst[6] = (unsigned)mrec.dt;
+    dst[7] = (unsigned)(ti & 0xffffffffll);
+    dst[8] = (unsigned)((unsigned long long)ti >> 32);
+    dst[9] = ((unsigned)(unsigned short)mrec.board) | ((unsigned)(unsigned short)mrec.channel << 16);
+    dst[10] = (unsigned)(mrec.record_id & 0xffffffffll);
+    dst[11] = (unsigned)((unsigned long long)mrec.record_id >> 32);
+}
+
+// emit pass for the records whose peaks all sit in the cache of the counting pass (the usual case): one THREAD per
+// cache slot finishes a row - a warp per record would keep 2 of its 32 lanes busy
+__global__ void __launch_bounds__(256) peaks_emit_cached_kernel(const void* __restrict__ waves, long long waves_len,
+                                                               const wfb_rec_meta* __restrict__ meta, long long n, const wfb_peak_params p,
+                                                               const int* __restrict__ counts, const long long* __restrict__ row_incl,
+                                                               uint8_t* __restrict__ rows, long long row_cap,
+                                                               const PeakCacheEnt* __restrict__ cache) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long rec = t / kPeakCache;
+    const int k = (int)(t % kPeakCache);
+    if (rec >= n) return;
+    const int c = counts[rec];
+    if (c > kPeakCache || k >= c) return;
+    const wfb_rec_meta mrec = meta[rec];
+    const bool records_src = p.wave_kind == WFB_WAVE_REC_U16 || p.wave_kind == WFB_WAVE_REC_F32;
+    PeakRec r;
+    r.kind = records_src ? WFB_WAVE_REC_U16 : p.wave_kind;
+    r.len = mrec.event_length;  // validated by the counting pass (a rejected record has no peaks)
+    r.deriv = p.use_derivative != 0;
+    r.m = r.deriv ? max(r.len - 1, 0) : r.len;
+    r.baseline = mrec.baseline;
+    r.w = Wave{waves, mrec.wave_offset, p.wave_kind, (float)mrec.baseline, mrec.polarity == WFB_POL_POSITIVE};
+    r.x = nullptr;
+    const PeakCacheEnt e = cache[rec * kPeakCache + k];
+    const long long row = row_incl[rec] - c + k;
+    if (row < row_cap) write_peak_row(rows, row, r, mrec, p, e.pk, e.lip, e.rip);
+}
+
 template <bool EMIT>
 __global__ void __launch_bounds__(kPeakWarps * 32) find_peaks_kernel(const void* __restrict__ waves, long long waves_len,
                                                                      const wfb_rec_meta* __restrict__ meta, long long n,
@@ -157,35 +206,10 @@ __global__ void __launch_bounds__(kPeakWarps * 32) find_peaks_kernel(const void*
     r.baseline = mrec.baseline;
     r.w = Wave{waves, off, p.wave_kind, (float)mrec.baseline, mrec.polarity == WFB_POL_POSITIVE};
     r.x = x;
-    auto write_row = [&](long long row, int pk, double lip, double rip) {
-        const float hgt = peak_height(r, lip, rip, p.height_method, p.height_window_extension);
-        const double step = __dmul_rn((double)mrec.dt, 1e3);
-        const long long ti = (long long)__dadd_rn((double)mrec.timestamp, __dmul_rn((double)pk, step));
-        unsigned* dst = reinterpret_cast<unsigned*>(rows + row * kPeakRowBytes);
-        dst[0] = (unsigned)pk;
-        dst[1] = 0u;
-        dst[2] = __float_as_uint(hgt);
-        dst[3] = 0u;  // integral (always 0.0 in the reference)
-        dst[4] = __float_as_uint((float)lip);
-        dst[5] = __float_as_uint((float)rip);
-        dst[6] = (unsigned)mrec.dt;
-        dst[7] = (unsigned)(ti & 0xffffffffll);
-        dst[8] = (unsigned)((unsigned long long)ti >> 32);
-        dst[9] = ((unsigned)(unsigned short)mrec.board) | ((unsigned)(unsigned short)mrec.channel << 16);
-        dst[10] = (unsigned)(mrec.record_id & 0xffffffffll);
-        dst[11] = (unsigned)((unsigned long long)mrec.record_id >> 32);
-    };
+    auto write_row = [&](long long row, int pk, double lip, double rip) { write_peak_row(rows, row, r, mrec, p, pk, lip, rip); };
     if (EMIT) {
-        // the counting pass left up to kPeakCache peaks per record: one lane per peak finishes the row, no re-scan
-        const int c = counts[rec];
-        if (c <= kPeakCache) {
-            if (lane < c) {
-                const PeakCacheEnt e = cache[rec * kPeakCache + lane];
-                const long long row = row_incl[rec] - c + lane;
-                if (row < row_cap) write_row(row, e.pk, e.lip, e.rip);
-            }
-            return;
-        }
+        // records whose peaks all fit the cache are finished by peaks_emit_cached_kernel
+        if (counts[rec] <= kPeakCache) return;
     }
     // ---- stage the detection signal.  The sample format is resolved once, outside the loop, and with the
     // derivative every sample is read from global memory once: lane i hands w[i] to its left neighbour's diff
@@ -423,9 +447,13 @@ extern "C" int wfb_find_peaks(const void* waves_dev, int64_t waves_len, const wf
     int rc = inclusive_scan_sum_i64(cnt64, incl, n, scan_ws, st);
     if (rc != WFB_OK) return rc;
     peaks_total_kernel<<<1, 32, 0, st>>>(incl, n, reinterpret_cast<long long*>(total_out_dev));
-    if (row_cap > 0)
+    if (row_cap > 0) {
+        const long long slots = n * kPeakCache;
+        peaks_emit_cached_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, st>>>(waves_dev, waves_len, meta_dev, n, p, counts, incl,
+                                                                               static_cast<uint8_t*>(rows_out_dev), row_cap, cache);
         find_peaks_kernel<true><<<grid, kPeakWarps * 32, dyn, st>>>(waves_dev, waves_len, meta_dev, n, p, lcap, counts, incl,
                                                                   static_cast<uint8_t*>(rows_out_dev), row_cap, err, cache);
+    }
     if (counts_out_dev) WFB_CUDA(cudaMemcpyAsync(counts_out_dev, counts, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
     WFB_CUDA(cudaGetLastError());
     int herr = 0;

@@ -220,8 +220,10 @@ def test_long_records_use_global_path(eng):
     assert_rows_match(out["hits"], O.threshold_hits(rec, pool, threshold=15.0), what="long hits", float_exact=FX_HIT)
 
 
-@pytest.mark.parametrize("knobs", [{"WFB_LPR_SC": "4"}, {"WFB_LPR_SC": "12"}, {"WFB_LPR_POOL": "24"}, {"WFB_LPR_POOL": "0", "WFB_LPR_SC": "4"},
-                                   {"WFB_LPR_NO_TMAP": "1"}])
+@pytest.mark.parametrize("knobs", [{"WFB_LPR_SC": "4"}, {"WFB_LPR_SC": "8"}, {"WFB_LPR_SC": "12"}, {"WFB_LPR_SC": "16"}, {"WFB_LPR_SC": "28"},
+                                   {"WFB_LPR_POOL": "24"}, {"WFB_LPR_POOL": "0", "WFB_LPR_SC": "4"}, {"WFB_LPR_NO_TMAP": "1"},
+                                   {"WFB_LPR_NO_TMAP": "1", "WFB_LPR_SC": "16", "WFB_LPR_POOL": "7"}, {"WFB_FUSED_VARIANT": "staged", "WFB_FUSED_SLOTS": "2"},
+                                   {"WFB_FUSED_VARIANT": "staged", "WFB_FUSED_SLOTS": "3"}])
 def test_lane_per_record_kernel_knobs(eng, golden, knobs, monkeypatch):
     """The lane-per-record kernel with other segment lengths, a tiny / absent per-warp hit pool (every
     record goes through the overflow re-stream with the direct row sink) and without the 2-D tensor

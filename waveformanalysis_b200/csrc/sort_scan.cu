@@ -147,6 +147,23 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const unsig
     }
 }
 
+// OR and AND of all sortable keys: a digit whose bits are the same in every key needs no pass
+__global__ void __launch_bounds__(256) radix_key_span_kernel(const unsigned long long* __restrict__ keys, long long n, int kind,
+                                                            unsigned long long* __restrict__ span /* [0] OR, [1] AND */) {
+    unsigned long long o = 0ull, a = ~0ull;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long k = sortable(keys[i], kind);
+        o |= k;
+        a &= k;
+    }
+    const unsigned olo = __reduce_or_sync(kFull, (unsigned)o), ohi = __reduce_or_sync(kFull, (unsigned)(o >> 32));
+    const unsigned alo = __reduce_and_sync(kFull, (unsigned)a), ahi = __reduce_and_sync(kFull, (unsigned)(a >> 32));
+    if (lane_id() == 0) {
+        atomicOr(span, ((unsigned long long)ohi << 32) | olo);
+        atomicAnd(span + 1, ((unsigned long long)ahi << 32) | alo);
+    }
+}
+
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 size_t radix_sort_workspace_bytes(long long n) {
@@ -170,11 +187,31 @@ int radix_sort_pairs(const unsigned long long* keys_in, const long long* vals_in
     const long long tile = std::max<long long>(4096, (total + 1023) / 1024);
     const int ntiles = (int)((total + tile - 1) / tile);
     unsigned* tile_sums = hist + total;
+    // which of the eight digits differ between keys at all (time stamps of one run share their top bytes, board /
+    // channel keys all but the lowest): one reduction + a 16-byte read-back saves every pass over a constant digit
+    unsigned long long* span = reinterpret_cast<unsigned long long*>(ws + radix_sort_workspace_bytes(n) - 256);
+    WFB_CUDA(cudaMemsetAsync(span, 0, 8, st));
+    WFB_CUDA(cudaMemsetAsync(span + 1, 0xff, 8, st));
+    radix_key_span_kernel<<<(unsigned)std::min<long long>(1184, (n + 255) / 256), 256, 0, st>>>(keys_in, n, (int)kind, span);
+    unsigned long long h_span[2] = {0ull, 0ull};
+    WFB_CUDA(cudaMemcpyAsync(h_span, span, 16, cudaMemcpyDeviceToHost, st));
+    WFB_CUDA(cudaStreamSynchronize(st));
+    const unsigned long long differ = h_span[0] ^ h_span[1];
+    int passes[8], np = 0;
+    for (int pass = 0; pass < 8; ++pass)
+        if ((differ >> (8 * pass)) & 0xffull) passes[np++] = pass;
+    if (np == 0) {  // all keys equal: the stable order is the input order
+        WFB_CUDA(cudaMemcpyAsync(keys_out, keys_in, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+        WFB_CUDA(cudaMemcpyAsync(vals_out, vals_in, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+        return WFB_OK;
+    }
     const unsigned long long* src_k = keys_in;
     const long long* src_v = vals_in;
-    for (int pass = 0; pass < 8; ++pass) {
-        unsigned long long* dst_k = (pass & 1) ? keys_out : tmp_k;  // the 8th pass lands in keys_out
-        long long* dst_v = (pass & 1) ? vals_out : tmp_v;
+    for (int j = 0; j < np; ++j) {
+        const int pass = passes[j];
+        const bool to_out = ((np - 1 - j) & 1) == 0;  // the last pass lands in keys_out
+        unsigned long long* dst_k = to_out ? keys_out : tmp_k;
+        long long* dst_v = to_out ? vals_out : tmp_v;
         radix_hist_kernel<<<nblocks, kSortThreads, 0, st>>>(src_k, n, pass * 8, (int)kind, hist, nblocks);
         radix_tile_sums_kernel<<<ntiles, 1024, 0, st>>>(hist, total, tile, tile_sums);
         radix_scan_sums_kernel<<<1, 1024, 0, st>>>(tile_sums, ntiles);

@@ -61,6 +61,16 @@ def test_sort_pairs(ops):
     k, v = ops.sort_pairs(keys, np.arange(len(keys)))
     order = np.argsort(keys, kind="stable")
     assert np.array_equal(v, order) and np.array_equal(k, keys[order])
+    # passes over digits that are the same in every key are skipped: all keys equal (no pass at all), one / two /
+    # three differing digits (odd and even numbers of passes end in the output buffers), the sign bit only
+    cases = [np.full(5000, 123456789, dtype=np.int64), rng.integers(0, 256, 70_001), rng.integers(0, 1 << 16, 70_001) << 24,
+             (rng.integers(0, 1 << 24, 33_333) << 8) + (7 << 40), rng.integers(-1, 1, 4097) * (1 << 62), np.array([5], dtype=np.int64),
+             1_700_000_000_000_000_000 + rng.integers(0, 1 << 37, 200_000)]
+    for keys in cases:
+        keys = np.asarray(keys, dtype=np.int64)
+        k, v = ops.sort_pairs(keys, np.arange(len(keys))[::-1].copy())
+        order = np.argsort(keys, kind="stable")
+        assert np.array_equal(k, keys[order]) and np.array_equal(v, np.arange(len(keys))[::-1][order])
 
 
 def _butter(order, lo, hi, fs):

@@ -103,22 +103,136 @@ def cpu_port_throughput(n_per_worker: int, workers: int, seed0: int = 100):
     return n_total / wall, n_total, wall
 
 
+# ---- the UNMODIFIED reference (pip --target install under baseline/_ref, tools/install_reference.sh) ----------
+
+
+def reference_root():
+    """Where the reference package can be imported from, or None.  baseline/_ref is git-ignored but travels
+    to the GPU box; /root/reference only exists in the build container."""
+    for cand in (os.environ.get("WFB_REFERENCE_ROOT"), os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if cand and os.path.isdir(os.path.join(cand, "waveform_analysis")):
+            return cand
+    return None
+
+
+def _ref_import(root):
+    from unittest.mock import MagicMock
+
+    # matplotlib is not in the image and the reference imports it unconditionally (core/context.py:34)
+    for mod in ("matplotlib", "matplotlib.pyplot", "matplotlib.patches", "matplotlib.colors", "matplotlib.figure", "matplotlib.axes",
+                "matplotlib.gridspec", "matplotlib.lines", "matplotlib.collections", "matplotlib.cm", "matplotlib.ticker", "matplotlib.dates"):
+        sys.modules.setdefault(mod, MagicMock())
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    import waveform_analysis  # noqa: F401
+
+
+def _ref_worker(task):
+    """One real reference Context (core/context.py) with profiles.cpu_default(): records + wave_pool of a
+    synthetic shard are seeded, basic_features and hit_threshold (records source, threshold 15) are pulled
+    with ctx.get_data - the reference's own plugins, scheduler, memmap cache write and profiler."""
+    root, seed, n = task
+    import contextlib
+    import io
+    import logging
+    import shutil
+    import tempfile
+
+    _ref_import(root)
+    logging.disable(logging.CRITICAL)
+    from waveform_analysis.core.context import Context
+    from waveform_analysis.core.plugins import profiles as ref_profiles
+
+    from waveformanalysis_b200.synth import make_raw_run, records_from_raw
+
+    raw = make_raw_run(N_CHANNELS, max(1, n // N_CHANNELS), N_SAMPLES, seed=seed)
+    rec, pool = records_from_raw(raw)
+    tmp = tempfile.mkdtemp(prefix="wfb_ref_")
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            ctx = Context(storage_dir=tmp)
+            ctx.register(*ref_profiles.cpu_default())
+            ctx.set_config({"wave_source": "records"}, plugin_name="basic_features")
+            ctx.set_config({"wave_source": "records", "threshold": THRESHOLD}, plugin_name="hit_threshold")
+            ctx._set_data("run", "records", rec)
+            ctx._set_data("run", "wave_pool", pool)
+            t0 = time.perf_counter()
+            feats = ctx.get_data("run", "basic_features")
+            hits = ctx.get_data("run", "hit_threshold")
+            wall = time.perf_counter() - t0
+        compute = 0.0
+        try:  # the reference's own Profiler keys (core/context_execution.py:147)
+            for key in ("plugin.basic_features.compute", "plugin.hit_threshold.compute"):
+                compute += float(ctx.profiler.durations[key])
+        except Exception:
+            compute = float("nan")
+        return len(rec), wall, compute, len(feats), len(hits)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+class ReferencePool:
+    """Worker processes that each run real reference Contexts (one shard per task): the reference's hot path is
+    single-threaded Python, so all host cores are used the way its BatchProcessor does - one Context per process."""
+
+    def __init__(self, workers: int):
+        import multiprocessing as mp
+
+        self.root = reference_root()
+        self.workers = workers
+        self.pool = mp.get_context("spawn").Pool(workers) if workers > 1 else None
+
+    def step(self, n_per_worker: int, seed0: int):
+        tasks = [(self.root, seed0 + i, n_per_worker) for i in range(self.workers)]
+        t0 = time.perf_counter()
+        res = self.pool.map(_ref_worker, tasks) if self.pool else [_ref_worker(tasks[0])]
+        outer = time.perf_counter() - t0
+        n_total = sum(r[0] for r in res)
+        wall = max(r[1] for r in res)  # slowest Context: input generation and interpreter start-up are not timed
+        compute = max(r[2] for r in res)
+        return dict(value=n_total / wall, n_total=n_total, wall=wall, compute=compute, outer=outer,
+                    hits_per_record=sum(r[4] for r in res) / max(n_total, 1))
+
+    def close(self):
+        if self.pool:
+            self.pool.close()
+            self.pool.join()
+
+
 def run_reference(args):
-    """--impl reference: the reference's algorithm for this path on the host cores.  The reference
-    is pure Python and cannot travel to the GPU box, so this is the oracle port (kind 'port'),
-    one process per host core."""
+    """--impl reference: the reference's OWN implementation of the path on the host cores: real Context +
+    profiles.cpu_default() from baseline/_ref (kind 'reference'); the numpy oracle port only when the
+    reference package is absent (kind 'port')."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     vals = []
-    for step in range(args.warmup + args.steps):
-        v, n_total, wall = cpu_port_throughput(args.cpu_sample // 2, cores, seed0=1000 + 17 * step)
-        if step >= args.warmup:
-            vals.append((v, n_total, wall))
+    if reference_root() is not None:
+        kind = "reference"
+        n_w = max(N_CHANNELS, args.cpu_sample // 2)
+        rp = ReferencePool(cores)
+        try:
+            for step in range(args.warmup + args.steps):
+                r = rp.step(n_w, seed0=1000 + 17 * step)
+                if step >= args.warmup:
+                    vals.append((r["value"], r["n_total"], r["wall"], r["compute"], r["hits_per_record"]))
+        finally:
+            rp.close()
+        sample = (f"{vals[0][1]} records per step ({cores} processes x {n_w} records, one real Context each): reference plugins "
+                  f"basic_features + hit_threshold (records source) through Context.get_data incl. memmap cache write; "
+                  f"plugin compute only (Profiler keys): {vals[0][1] / vals[0][3]:.0f} records/s")
+        hpr = sum(v[4] for v in vals) / len(vals)
+    else:
+        kind = "port"
+        for step in range(args.warmup + args.steps):
+            v, n_total, wall = cpu_port_throughput(args.cpu_sample // 2, cores, seed0=1000 + 17 * step)
+            if step >= args.warmup:
+                vals.append((v, n_total, wall))
+        sample = f"{vals[0][1]} records per step ({cores} processes x {args.cpu_sample // 2} records), numpy oracle basic_features+threshold_hits"
+        hpr = None
     value = sum(v[0] for v in vals) / len(vals)
     ms = 1e3 * sum(v[2] for v in vals) / len(vals)
-    sample = f"{vals[0][1]} records per step ({cores} processes x {args.cpu_sample // 2} records), numpy oracle basic_features+threshold_hits"
     line = {
         "impl": "reference",
         "metric": METRIC,
@@ -133,8 +247,8 @@ def run_reference(args):
         "vs_baseline": None,
         "dtype": "u16",
         "data": "synthetic",
-        "config": workload_config(args),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(args, {"hits_per_record": hpr}),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -330,6 +444,18 @@ def run_ours(args):
         v, n_total, wall = cpu_port_throughput(args.cpu_sample, cores)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{n_total} records ({cores} processes x {args.cpu_sample}), numpy oracle basic_features+threshold_hits, wall {wall:.2f} s"}
+        if reference_root() is not None:  # the reference's own plugins through a real Context; the port stays as a second figure
+            rp = ReferencePool(cores)
+            try:
+                rp.step(N_CHANNELS * 8, seed0=7)  # imports / numba warm-up
+                r = rp.step(args.cpu_sample // 2, seed0=100)
+            finally:
+                rp.close()
+            cpu = {"value": r["value"], "unit": UNIT, "cores": cores, "kind": "reference",
+                   "sample": (f"{r['n_total']} records ({cores} processes x {args.cpu_sample // 2}, one real Context + profiles.cpu_default() each): "
+                              f"basic_features + hit_threshold through Context.get_data, wall {r['wall']:.2f} s"),
+                   "compute_only_records_per_s": r["n_total"] / r["compute"] if r["compute"] == r["compute"] else None,
+                   "port": {"value": v, "kind": "port", "sample": f"{n_total} records, numpy oracle, wall {wall:.2f} s"}}
 
     if rank == 0:
         line = {

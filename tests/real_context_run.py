@@ -1,0 +1,87 @@
+#!/usr/bin/env python
+"""Run the records route of the hot path through a REAL reference ``Context`` and dump every result.
+
+    python tests/real_context_run.py cpu|b200 OUT.npz WORKDIR
+
+``cpu``: the reference's own plugins (``profiles.cpu_default()``).  ``b200``: the same Context with
+``ctx.register(*b200_default(), allow_override=True)`` on top (core/context.py:532-621), i.e. exactly the
+binding INTEGRATION.md shows.  Inputs: two synthetic V1725 ``.bin`` files written to WORKDIR and handed to
+the Context as ``raw_files``; everything downstream (records, wave_pool, wave_pool_filtered, basic_features,
+hit_threshold, the three hit-merge outputs with merge_gap_ns = 50, hit_grouped) is pulled with
+``ctx.get_data`` (core/context_execution.py:140-183), so dependency resolution, the memmap cache write and
+the memmap views handed to downstream plugins are the reference's.  Used by tests/test_real_context.py
+(run in fresh interpreters so that the B200 plugins subclass the reference's own Plugin base).
+"""
+
+from __future__ import annotations
+
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+
+
+def main():
+    mode, out_path, work = sys.argv[1], sys.argv[2], sys.argv[3]
+    import numpy as np
+    from refctx import import_reference
+
+    import_reference()
+    from waveform_analysis.core.context import Context
+    from waveform_analysis.core.plugins import profiles as ref_profiles
+
+    from waveformanalysis_b200.synth import make_v1725_blob
+
+    os.makedirs(work, exist_ok=True)
+    paths = []
+    for name, kw in (("run_b0_seg0.bin", dict(n_events=260, n_channels=16, seed=11, lengths=(300, 300), tie_every=9)),
+                     ("run_b1_seg0.bin", dict(n_events=200, n_channels=8, seed=12, lengths=(300, 300), tie_every=0, t0=23))):
+        p = os.path.join(work, name)
+        with open(p, "wb") as f:
+            f.write(make_v1725_blob(**kw))
+        paths.append(p)
+
+    ctx = Context(storage_dir=os.path.join(work, f"cache_{mode}"))
+    ctx.register(*ref_profiles.cpu_default())
+    if mode == "b200":
+        from waveformanalysis_b200 import plugin_api, profiles
+
+        assert plugin_api.HAVE_REFERENCE
+        ctx.register(*profiles.b200_default(), allow_override=True)
+        assert type(ctx._plugins["hit_threshold"]).__name__ == "B200ThresholdHitPlugin"
+    ctx.set_config({"daq_adapter": "v1725"})
+    for name in ("records", "wave_pool"):
+        ctx.set_config({"daq_adapter": "v1725", "dt": 4}, plugin_name=name)
+    ctx.set_config({"wave_source": "records", "height_range": (10, 60)}, plugin_name="basic_features")
+    ctx.set_config({"wave_source": "records", "threshold": 12.0}, plugin_name="hit_threshold")
+    for name in ("hit_merge_clusters", "hit_merged", "hit_merged_components"):
+        ctx.set_config({"merge_gap_ns": 50.0}, plugin_name=name)
+    ctx.set_config({"time_window_ns": 100.0}, plugin_name="hit_grouped")
+    run = "run_real"
+    ctx._set_data(run, "raw_files", [[paths[0]], [paths[1]]])
+
+    out = {}
+    for name in ("records", "wave_pool", "wave_pool_filtered", "basic_features", "hit_threshold", "hit_merge_clusters", "hit_merged",
+                 "hit_merged_components", "hit_grouped"):
+        res = ctx.get_data(run, name)
+        if hasattr(res, "columns"):  # DataFrame: one array per column (object columns flattened)
+            for col in res.columns:
+                v = res[col].to_numpy()
+                if v.dtype == object:
+                    lens = np.array([len(x) for x in v], dtype=np.int64)
+                    flat = np.concatenate([np.asarray(x).reshape(-1) for x in v]) if len(v) else np.zeros(0)
+                    out[f"{name}.{col}.len"] = lens
+                    out[f"{name}.{col}.flat"] = flat
+                else:
+                    out[f"{name}.{col}"] = v
+        else:
+            out[name] = np.asarray(res)
+    np.savez(out_path, **out)
+    print("REAL_CONTEXT_DONE", mode, {k: (v.shape, str(v.dtype)[:40]) for k, v in out.items() if "." not in k})
+
+
+if __name__ == "__main__":
+    main()

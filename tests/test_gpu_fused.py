@@ -223,7 +223,8 @@ def test_long_records_use_global_path(eng):
 @pytest.mark.parametrize("knobs", [{"WFB_LPR_SC": "4"}, {"WFB_LPR_SC": "8"}, {"WFB_LPR_SC": "12"}, {"WFB_LPR_SC": "16"}, {"WFB_LPR_SC": "28"},
                                    {"WFB_LPR_POOL": "24"}, {"WFB_LPR_POOL": "0", "WFB_LPR_SC": "4"}, {"WFB_LPR_NO_TMAP": "1"},
                                    {"WFB_LPR_NO_TMAP": "1", "WFB_LPR_SC": "16", "WFB_LPR_POOL": "7"}, {"WFB_FUSED_VARIANT": "staged", "WFB_FUSED_SLOTS": "2"},
-                                   {"WFB_FUSED_VARIANT": "staged", "WFB_FUSED_SLOTS": "3"}])
+                                   {"WFB_FUSED_VARIANT": "staged", "WFB_FUSED_SLOTS": "3"}, {"WFB_LPR_IMPL": "chunk"},
+                                   {"WFB_LPR_IMPL": "chunk", "WFB_LPR_SC": "8", "WFB_LPR_POOL": "5"}])
 def test_lane_per_record_kernel_knobs(eng, golden, knobs, monkeypatch):
     """The lane-per-record kernel with other segment lengths, a tiny / absent per-warp hit pool (every
     record goes through the overflow re-stream with the direct row sink) and without the 2-D tensor
@@ -251,6 +252,11 @@ def test_lane_per_record_kernel_knobs(eng, golden, knobs, monkeypatch):
     want = O.threshold_hits(r2, p2, threshold=6.0, left_extension=8, right_extension=8)
     got = eng.DeviceRun.from_host(r2, p2).run_to_host(features=False, threshold=6.0, left_extension=8, right_extension=8)
     assert_rows_match(got["hits"], want, what="ext8", float_exact=FX_HIT)
+    # every extension pair the block-item variant takes (0..2), dense flicker (threshold inside the noise)
+    for le, re_ in ((0, 0), (1, 2), (2, 1), (0, 2), (2, 0)):
+        want = O.threshold_hits(r2, p2, threshold=4.0, left_extension=le, right_extension=re_)
+        got = eng.DeviceRun.from_host(r2, p2).run_to_host(features=False, threshold=4.0, left_extension=le, right_extension=re_)
+        assert_rows_match(got["hits"], want, what=f"ext {le},{re_}", float_exact=FX_HIT)
 
 
 def test_full_size_properties(eng):

@@ -19,9 +19,9 @@ def adversarial_run(seed: int):
 
     rng = np.random.default_rng(seed)
     n = int(rng.integers(1, 90))
-    lens = rng.choice([0, 1, 7, 8, 9, 15, 16, 17, 31, 32, 33, 64, 100, 257], size=n).astype(np.int32)
+    lens = rng.choice([0, 1, 7, 8, 9, 15, 16, 17, 31, 32, 33, 64, 65, 100, 160, 257, 513], size=n).astype(np.int32)
     if rng.random() < 0.5:
-        lens[:] = int(rng.choice([8, 16, 24, 40, 64, 96]))  # fixed-length pool: the tensor-map path
+        lens[:] = int(rng.choice([8, 16, 24, 40, 64, 96, 128, 320]))  # fixed-length pool: the tensor-map path
     offs = np.zeros(n, dtype=np.int64)
     gap = int(rng.integers(0, 4)) if lens.min() != lens.max() else 0
     offs[1:] = np.cumsum(lens[:-1] + gap)
@@ -35,7 +35,7 @@ def adversarial_run(seed: int):
         L, o = int(lens[i]), int(offs[i])
         if L == 0:
             continue
-        kind = int(rng.integers(0, 7))
+        kind = int(rng.integers(0, 9))
         w = np.full(L, base, dtype=np.int64)
         sign = -1 if rng.random() < 0.6 else 1
         if kind == 0:      # everything above threshold
@@ -52,6 +52,20 @@ def adversarial_run(seed: int):
             w += sign * rng.integers(0, 2, size=L) * int(round(abs(thr)))
         elif kind == 4:    # random walk
             w += np.cumsum(rng.integers(-3, 4, size=L))
+        elif kind == 7:    # runs starting / ending on or next to 32-sample block boundaries (in pool coordinates)
+            for _ in range(int(rng.integers(1, 4))):
+                a = int(rng.integers(0, L))
+                a -= (o + a) % 32
+                b = a + 32 * int(rng.integers(1, 4))
+                a += int(rng.integers(-2, 3))
+                b += int(rng.integers(-2, 3))
+                w[max(a, 0):min(max(b, 0), L)] += sign * amp * 2
+        elif kind == 8:    # a long run with a distinct minimum somewhere inside, noise on top
+            a, b = sorted(int(x) for x in rng.integers(0, L + 1, size=2))
+            w[a:b] += sign * amp * 3
+            if b > a:
+                w[int(rng.integers(a, b))] += sign * amp * 5
+            w += sign * rng.integers(0, 2, size=L)
         elif kind == 5:    # one long pulse with a flickering tail
             a = int(rng.integers(0, L))
             w[a:] += sign * (amp * 4 * np.exp(-np.arange(L - a) / max(L / 6, 1))).astype(np.int64)
@@ -72,7 +86,7 @@ def adversarial_run(seed: int):
     return rec, pool, kw
 
 
-@pytest.mark.parametrize("block", range(8))
+@pytest.mark.parametrize("block", range(12))
 def test_fused_hits_adversarial(block, monkeypatch):
     from oracle import np_oracle as O
     from waveformanalysis_b200 import engine
@@ -85,6 +99,11 @@ def test_fused_hits_adversarial(block, monkeypatch):
         monkeypatch.setenv("WFB_LPR_NO_TMAP", "1")
     for seed in range(block * 40, block * 40 + 40):
         rec, pool, kw = adversarial_run(seed)
+        if block >= 4:  # extensions of at most two samples: the block-item variant of the lane-per-record kernel
+            kw["left_extension"] %= 3
+            kw["right_extension"] %= 3
+        if block >= 10:
+            monkeypatch.setenv("WFB_LPR_IMPL", "chunk")
         want_h = O.threshold_hits(rec, pool, **kw)
         want_f = O.basic_features(rec, pool, height_range=(2, -1), area_range=(0, None))
         got = engine.DeviceRun.from_host(rec, pool).run_to_host(height_range=(2, -1), area_range=(0, None), **kw)

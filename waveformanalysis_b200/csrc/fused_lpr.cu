@@ -81,9 +81,12 @@ struct DefLane {  // what phase B needs of a record once its registers are gone
     unsigned rel_pos;  // first row of the record relative to the tile's first row << 1 | positive
 };
 
-struct WarpHits {  // per-warp shared memory of the hit machinery
+struct ChunkQ {  // chunk-item queue of the chunk-granular variant (per warp)
     uint4 q_nb[2][32];     // the round's scratch: chunks P-1 and P+1 of lane t's item
     uint4 q_hdr[kQRing];   // ring of queued items: owner | (P + 1) << 5 ; aggregate key, samples, sum of the FULL chunks in front
+};
+
+struct WarpHits {  // per-warp shared memory of the hit machinery
     uint4 stage[32];       // this round's "open at chunk end" fragments: start ; key, count, key sum
     uint4 carry[32];       // the same, per owner, across rounds
     int stage_n[32];       // runs started by this round's items
@@ -190,11 +193,11 @@ struct DirectSink {  // rows straight to the output (records whose hits did not 
 // EXT22: both extensions are two samples (the defaults): the four neighbour samples are decoded once per
 // round and every fragment is one unrolled masked pass over the 12-sample window, all in registers.
 template <bool EXT22, typename Sink>
-__device__ __forceinline__ void lpr_round(WarpHits& ws, int qh, int qn, const LaneRec& r, const FHArgs& a, Sink& sink) {
+__device__ __forceinline__ void lpr_round(WarpHits& ws, ChunkQ& cq, int qh, int qn, const LaneRec& r, const FHArgs& a, Sink& sink) {
     __syncwarp();  // the pushes are visible
     const int lane = lane_id();
     const bool act = lane < qn;
-    const uint4 hd = ws.q_hdr[(qh + (act ? lane : 0)) & (kQRing - 1)];
+    const uint4 hd = cq.q_hdr[(qh + (act ? lane : 0)) & (kQRing - 1)];
     const int src = act ? (int)(hd.x & 31u) : lane;  // owner lane
     const int P = (int)((hd.x >> 5) & 0x3fffu) - 1;  // -1: the virtual chunk in front of a record that starts FULL
     // the owner's record constants
@@ -222,8 +225,8 @@ __device__ __forceinline__ void lpr_round(WarpHits& ws, int qh, int qn, const La
     const uint4 c1 = (act && P >= 0 && P < o_nch) ? __ldg(gsrc + 1) : zero4;
     const uint4 c2q = (act && P + 1 < o_nch) ? __ldg(gsrc + 2) : zero4;
     if (!EXT22) {
-        ws.q_nb[0][lane] = c0q;
-        ws.q_nb[1][lane] = c2q;
+        cq.q_nb[0][lane] = c0q;
+        cq.q_nb[1][lane] = c2q;
     }
     // keys of the item's own chunk, packed contributions, above-threshold mask
     unsigned ckey[8], cval[8];
@@ -289,7 +292,7 @@ __device__ __forceinline__ void lpr_round(WarpHits& ws, int qh, int qn, const La
                 if (msk & (1u << j)) { key = min(key, ckey[j]); acc += cval[j]; }
         }
         // the neighbours' samples: warp-uniform trip counts (the extensions), predicated bodies
-        const unsigned short* lo_row = reinterpret_cast<const unsigned short*>(&ws.q_nb[0][lane]);
+        const unsigned short* lo_row = reinterpret_cast<const unsigned short*>(&cq.q_nb[0][lane]);
         for (int e = 1; e <= left; ++e) {  // left neighbour (never padding: i < i0 <= len)
             const int i = i0 - e;
             const int kv = (int)((unsigned)lo_row[8 - e] ^ cx);
@@ -298,7 +301,7 @@ __device__ __forceinline__ void lpr_round(WarpHits& ws, int qh, int qn, const La
                 acc += (kv <= kin) ? kOne + (unsigned)kv : 0u;
             }
         }
-        const unsigned short* hi_row = reinterpret_cast<const unsigned short*>(&ws.q_nb[1][lane]);
+        const unsigned short* hi_row = reinterpret_cast<const unsigned short*>(&cq.q_nb[1][lane]);
         for (int e = 0; e < right; ++e) {  // right neighbour
             const int i = i0 + 8 + e;
             const int kv = (i < o_len) ? (int)((unsigned)hi_row[e] ^ cx) : padkv;
@@ -405,7 +408,7 @@ struct ChunkSum {
 
 template <bool FEAT, bool HITS, bool SGN, bool EXT22, typename Sink>
 __device__ __forceinline__ void lpr_stream(const FHArgs& a, const uint16_t* pool, const LaneRec& r, int sc, const Ring& ring,
-                                           int p0, int p1, int c0, int c1, FeatState& fs, WarpHits& ws, Sink& sink) {
+                                           int p0, int p1, int c0, int c1, FeatState& fs, WarpHits& ws, ChunkQ& cq, Sink& sink) {
     const int lane = lane_id();
     const int mis = r.mis, vtotal = r.mis + r.len;
     const int nch = (r.len > 0) ? ((vtotal + 7) >> 3) : 0;
@@ -687,12 +690,12 @@ __device__ __forceinline__ void lpr_stream(const FHArgs& a, const uint16_t* pool
                         const unsigned sk = j == 1 ? am_key : (j == 2 ? a0_key : (j == 3 ? a1_key : a2_key));
                         const unsigned sn = j == 1 ? am_n : (j == 2 ? a0_n : (j == 3 ? a1_n : a2_n));
                         const unsigned ss = j == 1 ? am_sw : (j == 2 ? a0_sw : (j == 3 ? a1_sw : a2_sw));
-                        ws.q_hdr[slot] = make_uint4((unsigned)lane | ((unsigned)(vc0 + j - 1) << 5), sk, sn, ss);
+                        cq.q_hdr[slot] = make_uint4((unsigned)lane | ((unsigned)(vc0 + j - 1) << 5), sk, sn, ss);
                     }
                     qn += __popc(bal);
                     if (qn >= kQCap || (bal == 0u && last_step && qn > 0)) {
                         const int take = min(qn, kQCap);
-                        lpr_round<EXT22>(ws, qh, take, r, a, sink);
+                        lpr_round<EXT22>(ws, cq, qh, take, r, a, sink);
                         qh = (qh + take) & (kQRing - 1);
                         qn -= take;
                     }
@@ -710,12 +713,20 @@ __device__ __forceinline__ void lpr_stream(const FHArgs& a, const uint16_t* pool
     }
 }
 
+}  // namespace wfb
+
+#include "fused_blk.cuh"
+
+namespace wfb {
+
 // ---- the kernel --------------------------------------------------------------------------------
-template <bool FEAT, bool HITS, bool SGN, bool EXT22>
+// BLK: block-granular items copied to a shared-memory ring (fused_blk.cuh); else chunk-granular items re-read from L2
+template <bool FEAT, bool HITS, bool SGN, bool EXT22, bool BLK>
 __global__ void __launch_bounds__(kLprWarps * 32, (HITS && !FEAT) ? WFB_LPR_MINBLOCKS + 1 : WFB_LPR_MINBLOCKS) lpr_kernel(const FHArgs a, const int sc, const __grid_constant__ CUtensorMap tmap,
                                                              const int have_tmap, const int ent_cap) {
-    extern __shared__ __align__(128) uint8_t dyn_smem[];  // [warp][kNBuf][lane] slots of a.slot_bytes
+    extern __shared__ __align__(128) uint8_t dyn_smem[];  // [warp][kNBuf][lane] slots of a.slot_bytes, then the block-item rings
     __shared__ __align__(16) WarpHits s_hits[HITS ? kLprWarps : 1];
+    __shared__ __align__(16) ChunkQ s_cq[(HITS && !BLK) ? kLprWarps : 1];
     __shared__ long long s_wtot[kLprWarps];
     __shared__ long long s_base[2];  // first row of the deferred tile / of this tile when it is finished at once
     __shared__ long long s_total;
@@ -727,6 +738,8 @@ __global__ void __launch_bounds__(kLprWarps * 32, (HITS && !FEAT) ? WFB_LPR_MINB
     const int warp = threadIdx.x >> 5, lane = lane_id();
     const uint16_t* pool = static_cast<const uint16_t*>(a.pool);
     WarpHits& ws = s_hits[HITS ? warp : 0];
+    ChunkQ& cq = s_cq[(HITS && !BLK) ? warp : 0];
+    unsigned* const bq = reinterpret_cast<unsigned*>(dyn_smem + (size_t)kLprTile * kNBuf * a.slot_bytes) + (size_t)warp * kBQRing * kBQWords;
     unsigned phase_bits = 0;
     Ring ring;
     // lane stride = slot_bytes (odd multiple of 16): conflict-free LDS.128; buffers kNBuf apart by 32 lanes
@@ -859,7 +872,8 @@ __global__ void __launch_bounds__(kLprWarps * 32, (HITS && !FEAT) ? WFB_LPR_MINB
         }
         __syncwarp();
         PoolSink psink{&ws, gp + (size_t)cur * a.gpool_cap, ent_cap};
-        lpr_stream<FEAT, HITS, SGN, EXT22>(a, pool, r, sc, ring, p0, p1, c0, c1, fs, ws, psink);
+        if constexpr (HITS && BLK) blk_stream<FEAT, SGN>(a, pool, r, sc, ring, p0, p1, c0, c1, fs, ws, bq, psink);
+        else lpr_stream<FEAT, HITS, SGN, EXT22>(a, pool, r, sc, ring, p0, p1, c0, c1, fs, ws, cq, psink);
 
         // ---------------- features of my record
         if (FEAT && have) {
@@ -978,7 +992,8 @@ __global__ void __launch_bounds__(kLprWarps * 32, (HITS && !FEAT) ? WFB_LPR_MINB
                 DirectSink dsink;
                 dsink.my_row0 = base + rel;
                 dsink.my_active = (ovf >> lane) & 1u;
-                lpr_stream<false, true, SGN, EXT22>(a, pool, r, sc, ring, 0, 0, 0, 0, fs2, ws, dsink);
+                if constexpr (BLK) blk_stream<false, SGN>(a, pool, r, sc, ring, 0, 0, 0, 0, fs2, ws, bq, dsink);
+                else lpr_stream<false, true, SGN, EXT22>(a, pool, r, sc, ring, 0, 0, 0, 0, fs2, ws, cq, dsink);
             }
             pend = false;
         } else {
@@ -1002,14 +1017,17 @@ int launch_lpr(FHArgs a, int flags, cudaStream_t st) {
     // a multiple of the 4-chunk scan block.  Measured per mode (profiles/README.md): features + hits 12 chunks at three
     // blocks per SM; hits only 8 chunks, whose smaller slots and 128 registers let a fourth block in; features only 16
     const bool want_f = flags & WFB_DO_FEATURES, want_h = flags & WFB_DO_HITS;
-    int sc = (want_f && want_h) ? 12 : (want_h ? 8 : 16);
+    // block-granular items (fused_blk.cuh): extensions of at most two samples; WFB_LPR_IMPL=chunk keeps the chunk-granular variant
+    const char* impl = getenv("WFB_LPR_IMPL");
+    const bool blk = want_h && a.p.left_extension <= kBQMaxExt && a.p.right_extension <= kBQMaxExt && !(impl && !strcmp(impl, "chunk"));
+    int sc = blk ? 8 : ((want_f && want_h) ? 12 : (want_h ? 8 : 16));
     if (const char* e = getenv("WFB_LPR_SC")) sc = std::max(4, std::min(28, atoi(e) & ~3));
     int ent_cap = a.gpool_cap;  // WFB_LPR_POOL shrinks the per-warp hit pool (exercises the overflow path in tests)
     if (const char* e = getenv("WFB_LPR_POOL")) ent_cap = std::max(0, std::min(a.gpool_cap, atoi(e)));
     int slot_chunks = sc + kHist;
     if ((slot_chunks & 1) == 0) ++slot_chunks;  // odd multiple of 16 bytes: conflict-free LDS.128
     a.slot_bytes = slot_chunks * 16;
-    const size_t dyn = (size_t)kLprTile * kNBuf * a.slot_bytes;
+    const size_t dyn = (size_t)kLprTile * kNBuf * a.slot_bytes + (blk ? (size_t)kLprWarps * kBQRing * kBQWords * 4 : 0);
     a.n_tiles = (int)((a.n + kLprTile - 1) / kLprTile);
     const bool f = flags & WFB_DO_FEATURES, h = flags & WFB_DO_HITS;
     // tensor map over the pool seen as rows of lmax samples: one box = 32 records x one slot
@@ -1054,14 +1072,18 @@ int launch_lpr(FHArgs a, int flags, cudaStream_t st) {
         return WFB_OK;
     };
     const bool e22 = h && a.p.left_extension == 2 && a.p.right_extension == 2;  // the defaults (hit_finder.py:104-105)
-    if (a.p.signed_samples) {
-        if (f && h) return e22 ? go(lpr_kernel<true, true, true, true>) : go(lpr_kernel<true, true, true, false>);
-        if (f) return go(lpr_kernel<true, false, true, false>);
-        return e22 ? go(lpr_kernel<false, true, true, true>) : go(lpr_kernel<false, true, true, false>);
+    if (blk) {
+        if (a.p.signed_samples) return f ? go(lpr_kernel<true, true, true, false, true>) : go(lpr_kernel<false, true, true, false, true>);
+        return f ? go(lpr_kernel<true, true, false, false, true>) : go(lpr_kernel<false, true, false, false, true>);
     }
-    if (f && h) return e22 ? go(lpr_kernel<true, true, false, true>) : go(lpr_kernel<true, true, false, false>);
-    if (f) return go(lpr_kernel<true, false, false, false>);
-    return e22 ? go(lpr_kernel<false, true, false, true>) : go(lpr_kernel<false, true, false, false>);
+    if (a.p.signed_samples) {
+        if (f && h) return e22 ? go(lpr_kernel<true, true, true, true, false>) : go(lpr_kernel<true, true, true, false, false>);
+        if (f) return go(lpr_kernel<true, false, true, false, false>);
+        return e22 ? go(lpr_kernel<false, true, true, true, false>) : go(lpr_kernel<false, true, true, false, false>);
+    }
+    if (f && h) return e22 ? go(lpr_kernel<true, true, false, true, false>) : go(lpr_kernel<true, true, false, false, false>);
+    if (f) return go(lpr_kernel<true, false, false, false, false>);
+    return e22 ? go(lpr_kernel<false, true, false, true, false>) : go(lpr_kernel<false, true, false, false, false>);
 }
 
 }  // namespace wfb

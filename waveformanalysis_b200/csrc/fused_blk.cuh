@@ -28,10 +28,11 @@
 namespace wfb {
 
 constexpr int kBQRing = 64;    // item slots per warp: < 32 complete items + <= 32 pushed in the current step
-constexpr int kBQWords = 21;   // 32-bit words per slot; odd, so that the lanes' scalar accesses fall into distinct banks
+constexpr int kBQWords = 27;   // 32-bit words per slot; odd, so that the lanes' scalar accesses fall into distinct banks
 // slot words: 0 last word of the previous block, 1..16 the block (offset-domain samples), 17 first word of the next
 // block, 18 owner | block << 5, 19 first-minimum key of the FULL blocks in front (key << 16 | block) or ~0, 20 their
-// raw sample sum.  As half-words: sample j of the block (j = -2 .. 33) sits at j + 2.
+// raw sample sum; 19 .. 26 are reused by the round for the {key, sum} pairs of up to four runs that end in the block.
+// As half-words: sample j of the block (j = -2 .. 33) sits at j + 2.
 constexpr int kBQMaxExt = 2;
 
 // bit j <=> (half-word j of d0..d3, xor cx) < k1; k1k1 = k1 | k1 << 16 with 1 <= k1 <= 65535
@@ -50,25 +51,29 @@ __device__ __forceinline__ unsigned lt_mask32(const uint4& d0, const uint4& d1, 
 }
 
 // ---- dense round: lane t walks the runs of queued block item t -----------------------------------
+// Fast path (thresholds >= 0): ONE unrolled, branch-free pass over the 32 positions keeps the running first-minimum
+// key and sample sum of the current run in two registers; where a run ends the pair is parked in the item's own slot
+// (its header words are in registers by then), so the per-run work that remains is a short loop over ENDED runs:
+// extension samples, the carried-in fragment of the first one, the row entry.  A negative threshold (FULL blocks are
+// items then, a run can cross a whole block) takes the general walker with per-sample loops.
 template <typename Sink>
-__device__ __forceinline__ void blk_round(WarpHits& ws, const unsigned* bq, int qh, int qn, const LaneRec& r, const FHArgs& a, Sink& sink) {
+__device__ __forceinline__ void blk_round(WarpHits& ws, unsigned* bq, int qh, int qn, const LaneRec& r, const FHArgs& a, Sink& sink) {
     __syncwarp();  // pushes and completions are visible
     const int lane = lane_id();
     const bool act = lane < qn;
-    const unsigned* sl = bq + ((qh + (act ? lane : 0)) & (kBQRing - 1)) * kBQWords;
-    const uint4 d0 = make_uint4(sl[1], sl[2], sl[3], sl[4]), d1 = make_uint4(sl[5], sl[6], sl[7], sl[8]);
-    const uint4 d2 = make_uint4(sl[9], sl[10], sl[11], sl[12]), d3 = make_uint4(sl[13], sl[14], sl[15], sl[16]);
-    const uint4 h4 = make_uint4(0u, sl[18], sl[19], sl[20]);  // -, owner | block << 5, FULL key, FULL sum
+    unsigned* sl = bq + ((qh + (act ? lane : 0)) & (kBQRing - 1)) * kBQWords;
+    const unsigned hdr = sl[18], fa_key = sl[19], fa_sum = sl[20];  // owner | block << 5, FULL key, FULL sum
     const unsigned prev_w = sl[0];
     const unsigned short* hw = reinterpret_cast<const unsigned short*>(sl) + 2;  // hw[j]: sample j of the block, j = -2 .. 33
-    const int src = act ? (int)(h4.y & 31u) : lane;  // owner lane
-    const int B = (int)(h4.y >> 5);
+    const int src = act ? (int)(hdr & 31u) : lane;  // owner lane
+    const int B = (int)(hdr >> 5);
     // the owner's record constants
     const int o_kmax = __shfl_sync(kFull, r.kmax, src);
     const int o_mis = __shfl_sync(kFull, r.mis, src);
     const int o_len = __shfl_sync(kFull, r.len, src);
     const int o_wlim = __shfl_sync(kFull, r.wlim, src);
-    const bool o_pos = __shfl_sync(kFull, (int)r.positive, src) != 0;
+    const unsigned o_flags = __shfl_sync(kFull, (r.positive ? 1u : 0u) | (r.degen ? 2u : 0u), src);
+    const bool o_pos = (o_flags & 1u) != 0u;
     const long long o_off = bcast_i64(r.off, src);
     sink.prepare(src, r);
     const int bias = r.bias;                       // uniform
@@ -78,30 +83,24 @@ __device__ __forceinline__ void blk_round(WarpHits& ws, const unsigned* bq, int 
     const int kin = o_pos ? 65535 - (o_wlim + bias) : o_wlim + bias;  // signal side <=> key <= kin
     const int left = a.p.left_extension, right = a.p.right_extension;
     const int i0 = 32 * B - o_mis;  // record index of the block's first sample
-    // positions of the block that belong to the record, and those above threshold
+    // positions of the block that belong to the record
     const int vlo = max(0, -i0), vhi = min(32, o_len - i0);
     unsigned vmask = 0u;
     if (act && vhi > vlo) vmask = (vhi >= 32 ? 0xffffffffu : ((1u << vhi) - 1u)) & ~((1u << vlo) - 1u);
-    const unsigned k1 = (unsigned)min(max(o_kmax + 1, 1), 65535);
-    const unsigned lt = lt_mask32(d0, d1, d2, d3, cx32, k1 | (k1 << 16));
-    const unsigned m32 = (o_kmax >= 65535) ? vmask : ((o_kmax >= 0) ? (lt & vmask) : 0u);
     // does a run come in (the sample in front of the block is above threshold)?
     const bool in_open = act && i0 >= 1 && i0 - 1 < o_len && (int)((prev_w >> 16) ^ cx) <= o_kmax;
-    const unsigned starts = m32 & ~((m32 << 1) | (in_open ? 1u : 0u));
-    const int nstarts = __popc(starts);
-    const bool has_trail = (m32 >> 31) != 0u;  // a run is still open at the block end
-    ws.stage_n[lane] = nstarts;
-    const unsigned peers = __match_any_sync(kFull, act ? src : 32 + lane);
-    const unsigned ltp = peers & ((1u << lane) - 1u);
-    __syncwarp();
-    int ord_base = act ? ws.carry_n[src] : 0;  // runs of the record started in front of this item
-    for (unsigned m = ltp; m; m &= m - 1) ord_base += ws.stage_n[__ffs(m) - 1];
+    const bool slow = __any_sync(kFull, act && ((o_flags & 2u) != 0u || o_kmax >= 65535));
 
     // one sample of the window by its position relative to the block (-2 .. 33)
     auto add_sample = [&](int rel, unsigned& key, unsigned& cnt, unsigned& skv) {
         const int i = i0 + rel;
         const int kv = (i < o_len) ? (int)((unsigned)hw[rel] ^ cx) : padkv;
         key = min(key, ((unsigned)kv << 16) + (unsigned)i);
+        if (kv <= kin) { cnt += 1u; skv += (unsigned)kv; }
+    };
+    // an extension sample with key kv at block position rel
+    auto ext_sample = [&](int rel, int kv, unsigned& key, unsigned& cnt, unsigned& skv) {
+        key = min(key, ((unsigned)kv << 16) + (unsigned)(i0 + rel));
         if (kv <= kin) { cnt += 1u; skv += (unsigned)kv; }
     };
     // samples [ja, jb) of the block, all inside the record
@@ -113,10 +112,144 @@ __device__ __forceinline__ void blk_round(WarpHits& ws, const unsigned* bq, int 
             if ((int)kv <= kin) { cnt += 1u; skv += kv; }
         }
     };
+    // the fragment carried in by the owner's previous item, with the FULL blocks between the two items
+    auto carried_in = [&](unsigned ltp) {
+        uint4 prev = ltp ? ws.stage[31 - __clz(ltp)] : ws.carry[src];
+        if (fa_key != 0xffffffffu) {
+            const unsigned fkv = fa_key >> 16;
+            const int fb = (int)(fa_key & 0xffffu);
+            const int bs = ((int)prev.x + o_mis) >> 5;  // block in which the run started
+            const unsigned nfull = 32u * (unsigned)(B - bs - 1);
+            if (fkv < (prev.y >> 16)) {  // the minimum lies in a FULL block: find its first position (L2)
+                const uint4* g = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(a.pool) + (o_off - o_mis) + 32ll * fb);
+                const uint4 g0 = __ldg(g), g1 = __ldg(g + 1), g2 = __ldg(g + 2), g3 = __ldg(g + 3);
+                const unsigned cxr = (bias ? 0x8000u : 0u) ^ cx;
+                unsigned eq = 0xffffffffu;
+                if (fkv < 65535u) eq = lt_mask32(g0, g1, g2, g3, cxr | (cxr << 16), (fkv + 1u) | ((fkv + 1u) << 16));
+                prev.y = (fkv << 16) + (unsigned)(32 * fb - o_mis + __ffs(eq) - 1);
+            }
+            prev.z += nfull;
+            prev.w += o_pos ? nfull * 65535u - fa_sum : fa_sum;
+        }
+        return prev;
+    };
 
+    if (!slow) {
+        // ---------------- fast path ----------------
+        unsigned kvp[16];
+#pragma unroll
+        for (int w = 0; w < 16; ++w) kvp[w] = sl[1 + w] ^ cx32;
+        if (__any_sync(kFull, vmask != 0xffffffffu)) {  // record start / end (or an idle lane): positions outside never count
+#pragma unroll
+            for (int w = 0; w < 16; ++w) {
+                const unsigned b2 = (vmask >> (2 * w)) & 3u;
+                kvp[w] |= ~((b2 & 1u) * 0xffffu + (b2 >> 1) * 0xffff0000u);
+            }
+        }
+        unsigned* fst = sl + 19;  // four parked {key, sum} pairs: words 19 .. 26
+        unsigned key = 0xffffffffu, sum = 0u, m32 = 0u;
+        int nf = 0;  // runs that ended so far
+        bool pprev = in_open;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const unsigned kv = (j & 1) ? (kvp[j >> 1] >> 16) : (kvp[j >> 1] & 0xffffu);
+            const bool p = (int)kv <= o_kmax;
+            if (pprev && !p) {  // a run ended in front of j: park it (the fourth slot is overwritten by later ones)
+                unsigned* f = fst + 2 * min(nf, 3);
+                f[0] = key;
+                f[1] = sum;
+                ++nf;
+                key = 0xffffffffu;
+                sum = 0u;
+            }
+            if (p) {
+                key = min(key, (kv << 16) + (unsigned)j);
+                sum += kv;
+                m32 |= 1u << j;
+            }
+            pprev = p;
+        }
+        const unsigned starts = m32 & ~((m32 << 1) | (in_open ? 1u : 0u));
+        const int nstarts = __popc(starts);
+        const bool has_trail = (m32 >> 31) != 0u;  // a run is still open at the block end
+        ws.stage_n[lane] = nstarts;
+        const unsigned peers = __match_any_sync(kFull, act ? src : 32 + lane);
+        const unsigned ltp = peers & ((1u << lane) - 1u);
+        __syncwarp();  // stage_n, and the parked pairs of this lane
+        int ord_base = act ? ws.carry_n[src] : 0;  // runs of the record started in front of this item
+        for (unsigned m = ltp; m; m &= m - 1) ord_base += ws.stage_n[__ffs(m) - 1];
+        if (has_trail) {  // staged for the owner's next item (key and sum are those of the trailing run)
+            const int js_tr = 32 - __clz(~m32);
+            const int s_tr = i0 + js_tr;
+            unsigned tkey = key + (unsigned)i0, cnt = (unsigned)(32 - js_tr), skv = sum;
+            if (left >= 1 && s_tr >= 1) ext_sample(js_tr - 1, (int)((unsigned)hw[js_tr - 1] ^ cx), tkey, cnt, skv);
+            if (left >= 2 && s_tr >= 2) ext_sample(js_tr - 2, (int)((unsigned)hw[js_tr - 2] ^ cx), tkey, cnt, skv);
+            ws.stage[lane] = make_uint4((unsigned)s_tr, tkey, cnt, skv);
+        }
+        __syncwarp();
+        unsigned em = ~m32 & ((m32 << 1) | (in_open ? 1u : 0u));  // bit j: a run ended in front of position j
+        unsigned sm = starts;
+        for (int k = 0; em; ++k) {
+            const int je = __ffs(em) - 1;
+            em &= em - 1u;
+            const bool lead = in_open && k == 0;
+            int js = 0;
+            if (!lead) {
+                js = __ffs(sm) - 1;
+                sm &= sm - 1u;
+            }
+            unsigned hkey = 0xffffffffu, cnt = 0u, skv = 0u;
+            if (k < 3 || (k == 3 && nf <= 4)) {
+                if (je > js) {  // (an incoming run that ends with the block's first sample has no sample here)
+                    hkey = fst[2 * k] + (unsigned)i0;
+                    skv = fst[2 * k + 1];
+                    cnt = (unsigned)(je - js);
+                }
+            } else {
+                add_core(js, je, hkey, cnt, skv);
+            }
+            int s = i0 + js, ord = ord_base + k - (in_open ? 1 : 0);
+            if (lead) {
+                const uint4 prev = carried_in(ltp);
+                s = (int)prev.x;
+                hkey = min(hkey, prev.y);
+                cnt += prev.z;
+                skv += prev.w;
+            } else {  // left extension: the samples in front of the run belong to the record
+                if (left >= 1 && s >= 1) ext_sample(js - 1, (int)((unsigned)hw[js - 1] ^ cx), hkey, cnt, skv);
+                if (left >= 2 && s >= 2) ext_sample(js - 2, (int)((unsigned)hw[js - 2] ^ cx), hkey, cnt, skv);
+            }
+            const int e = i0 + je;
+            if (right >= 1 && e < a.lmax) ext_sample(je, e < o_len ? (int)((unsigned)hw[je] ^ cx) : padkv, hkey, cnt, skv);
+            if (right >= 2 && e + 1 < a.lmax) ext_sample(je + 1, e + 1 < o_len ? (int)((unsigned)hw[je + 1] ^ cx) : padkv, hkey, cnt, skv);
+            sink.store((int)(hkey & 0xffffu), s, e, (int)(hkey >> 16), cnt, o_pos ? cnt * 65535u - skv : skv, ord, src, a);
+        }
+        __syncwarp();  // every read of stage / carry is done
+        if (act && !(peers >> lane >> 1)) {  // the last item of this owner in the round
+            if (has_trail) ws.carry[src] = ws.stage[lane];
+            ws.carry_n[src] = ord_base + nstarts;
+        }
+        __syncwarp();
+        return;
+    }
+
+    // ---------------- general walker ----------------
+    const uint4 d0 = make_uint4(sl[1], sl[2], sl[3], sl[4]), d1 = make_uint4(sl[5], sl[6], sl[7], sl[8]);
+    const uint4 d2 = make_uint4(sl[9], sl[10], sl[11], sl[12]), d3 = make_uint4(sl[13], sl[14], sl[15], sl[16]);
+    const unsigned k1 = (unsigned)min(max(o_kmax + 1, 1), 65535);
+    const unsigned lt = lt_mask32(d0, d1, d2, d3, cx32, k1 | (k1 << 16));
+    const unsigned m32 = (o_kmax >= 65535) ? vmask : ((o_kmax >= 0) ? (lt & vmask) : 0u);
+    const unsigned starts = m32 & ~((m32 << 1) | (in_open ? 1u : 0u));
+    const int nstarts = __popc(starts);
+    const bool has_trail = (m32 >> 31) != 0u;  // a run is still open at the block end
+    ws.stage_n[lane] = nstarts;
+    const unsigned peers = __match_any_sync(kFull, act ? src : 32 + lane);
+    const unsigned ltp = peers & ((1u << lane) - 1u);
+    __syncwarp();
+    int ord_base = act ? ws.carry_n[src] : 0;  // runs of the record started in front of this item
+    for (unsigned m = ltp; m; m &= m - 1) ord_base += ws.stage_n[__ffs(m) - 1];
     // the run still open at the block end: staged for the owner's next item.  A block that a run crosses
-    // from end to end (only with a negative threshold, where FULL blocks are items too) has to wait for
-    // the fragment in front of it.
+    // from end to end has to wait for the fragment in front of it.
     int js_tr = 32;
     bool passthru = false;
     if (has_trail) {
@@ -151,23 +284,7 @@ __device__ __forceinline__ void blk_round(WarpHits& ws, const unsigned* bq, int 
     // the run that comes in and ends in this block
     unsigned mm = m32;
     if (in_open && !passthru) {
-        uint4 prev = ltp ? ws.stage[31 - __clz(ltp)] : ws.carry[src];
-        if (h4.z != 0xffffffffu) {  // FULL blocks between the two items
-            const unsigned fkv = h4.z >> 16;
-            const int fb = (int)(h4.z & 0xffffu);
-            const int bs = ((int)prev.x + o_mis) >> 5;  // block in which the run started
-            const unsigned nfull = 32u * (unsigned)(B - bs - 1);
-            if (fkv < (prev.y >> 16)) {  // the minimum lies in a FULL block: find its first position (L2)
-                const uint4* g = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(a.pool) + (o_off - o_mis) + 32ll * fb);
-                const uint4 g0 = __ldg(g), g1 = __ldg(g + 1), g2 = __ldg(g + 2), g3 = __ldg(g + 3);
-                const unsigned cxr = (bias ? 0x8000u : 0u) ^ cx;
-                unsigned eq = 0xffffffffu;
-                if (fkv < 65535u) eq = lt_mask32(g0, g1, g2, g3, cxr | (cxr << 16), (fkv + 1u) | ((fkv + 1u) << 16));
-                prev.y = (fkv << 16) + (unsigned)(32 * fb - o_mis + __ffs(eq) - 1);
-            }
-            prev.z += nfull;
-            prev.w += o_pos ? nfull * 65535u - h4.w : h4.w;
-        }
+        const uint4 prev = carried_in(ltp);
         const int t0 = __ffs(~m32) - 1;  // the run ends at the first position that is not above threshold
         unsigned key = prev.y, cnt = prev.z, skv = prev.w;
         add_core(0, t0, key, cnt, skv);
@@ -227,7 +344,7 @@ __device__ __forceinline__ void blk_stream(const FHArgs& a, const uint16_t* pool
     bool open = false;                          // the last sample of the previous block is above threshold
     unsigned fa_key = 0xffffffffu, fa_sum = 0u; // FULL blocks since the lane's last item
     unsigned hprev = 0u;                        // last word of the previous block
-    int myslot = -1;                            // the item pushed in the previous step (waits for its next word)
+    unsigned* myslot = nullptr;                 // the item pushed in the previous step (waits for its next word)
     int qn_c = 0, qn_i = 0, qh = 0;             // complete / incomplete items, ring head (warp-uniform)
 
     auto issue = [&](int s) {
@@ -332,28 +449,34 @@ __device__ __forceinline__ void blk_stream(const FHArgs& a, const uint16_t* pool
     };
 
     if (nseg > 0) issue(0);
-    for (int s = 0; s < nseg; ++s) {
+    for (int s = 0; s <= nseg; ++s) {  // s == nseg: nothing is streamed any more, the queue is drained
+        const bool drain = s == nseg;
         const int b = s % kNBuf;
-        if (s + 1 < nseg) issue(s + 1);
-        mbar_wait(&ring.bars[b], (*ring.phase_bits >> b) & 1u);
-        *ring.phase_bits ^= 1u << b;
+        if (!drain) {
+            if (s + 1 < nseg) issue(s + 1);
+            mbar_wait(&ring.bars[b], (*ring.phase_bits >> b) & 1u);
+            *ring.phase_bits ^= 1u << b;
+        }
         const uint8_t* buf = ring.slot + b * ring.buf_stride;
-        const int tend = min(bps, nblk - s * bps);
+        const int tend = drain ? 1 : min(bps, nblk - s * bps);
         for (int t = 0; t < tend; ++t) {
             const int vc0 = s * sc + 4 * t;  // first chunk of the block
             const int B = vc0 >> 2;
-            // the items pushed one step ago get the first word of their next block; a round runs when 32 wait
-            if (myslot >= 0) {
-                bq[myslot * kBQWords + 17] = *reinterpret_cast<const unsigned*>(buf + t * 64) ^ (SGN ? 0x80008000u : 0u);
-                myslot = -1;
+            // the items pushed one step ago get the first word of their next block (the items of the last step lie
+            // behind their records and need none); a round runs when 32 complete items wait
+            if (myslot != nullptr && !drain) {
+                myslot[17] = *reinterpret_cast<const unsigned*>(buf + t * 64) ^ (SGN ? 0x80008000u : 0u);
+                myslot = nullptr;
             }
             qn_c += qn_i;
             qn_i = 0;
-            if (qn_c >= 32) {
-                blk_round(ws, bq, qh, 32, r, a, sink);
-                qh = (qh + 32) & (kBQRing - 1);
-                qn_c -= 32;
+            while (qn_c >= 32 || (drain && qn_c > 0)) {
+                const int take = min(qn_c, 32);
+                blk_round(ws, bq, qh, take, r, a, sink);
+                qh = (qh + take) & (kBQRing - 1);
+                qn_c -= take;
             }
+            if (drain) break;
             uint4 q0 = *reinterpret_cast<const uint4*>(buf + t * 64);
             uint4 q1 = *reinterpret_cast<const uint4*>(buf + t * 64 + 16);
             uint4 q2 = *reinterpret_cast<const uint4*>(buf + t * 64 + 32);
@@ -372,7 +495,12 @@ __device__ __forceinline__ void blk_stream(const FHArgs& a, const uint16_t* pool
                 if (fast) {
                     feat_plain(q0, s0); feat_plain(q1, s1); feat_plain(q2, s2); feat_plain(q3, s3);
                 } else {
-                    feat_generic(q0, vc0); feat_generic(q1, vc0 + 1); feat_generic(q2, vc0 + 2); feat_generic(q3, vc0 + 3);
+#pragma unroll 1
+                    for (int c = 0; c < 4; ++c) {  // record start / end, height range, known polarity: chunk by chunk
+                        uint4 q = *reinterpret_cast<const uint4*>(buf + t * 64 + c * 16);
+                        if (SGN) { q.x ^= 0x80008000u; q.y ^= 0x80008000u; q.z ^= 0x80008000u; q.w ^= 0x80008000u; }
+                        feat_generic(q, vc0 + c);
+                    }
                 }
             }
             // class of the block
@@ -419,7 +547,7 @@ __device__ __forceinline__ void blk_stream(const FHArgs& a, const uint16_t* pool
                 sl[18] = (unsigned)lane | ((unsigned)B << 5);
                 sl[19] = fa_key;
                 sl[20] = fa_sum;
-                myslot = slot;
+                myslot = sl;
                 fa_key = 0xffffffffu;
                 fa_sum = 0u;
             }
@@ -428,14 +556,6 @@ __device__ __forceinline__ void blk_stream(const FHArgs& a, const uint16_t* pool
             hprev = q3.w;
         }
         __syncwarp();  // every lane is done with buffer b before it is refilled
-    }
-    // the items of the last step need no next word (they lie behind their records)
-    qn_c += qn_i;
-    while (qn_c > 0) {
-        const int take = min(qn_c, 32);
-        blk_round(ws, bq, qh, take, r, a, sink);
-        qh = (qh + take) & (kBQRing - 1);
-        qn_c -= take;
     }
 }
 

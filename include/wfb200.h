@@ -57,7 +57,7 @@ typedef struct wfb_rec_meta {
     int16_t board;
     int16_t channel;
     uint8_t polarity; /* WFB_POL_* ('positive' / 'negative' / anything else) */
-    uint8_t pad_[3];
+    uint8_t pad_[3];  /* 0, or (edge clamp length + 1) little-endian: see wfb_meta_set_clamp */
     int64_t record_id;
 } wfb_rec_meta;
 
@@ -101,9 +101,19 @@ int wfb_device_info(int* sm_count, int* cc_major, int* cc_minor, char* name, int
 
 /* ---- K1: records ---------------------------------------------------------------------- */
 
+/* Host -> device copy of any host array (pageable, read-only or memory-mapped: what the reference's Context hands to
+ * plugins, core/context_execution.py:241-251) followed by a stream synchronise, so the source may be released at once. */
+int wfb_memcpy_h2d(void* dst_dev, const void* src_host, size_t bytes, void* stream);
+
 /* RECORDS_DTYPE rows (102 B packed, device) -> wfb_rec_meta[n].  Replaces the per-record
  * field access of RecordsView (core/data/records_view.py:16-33). */
 int wfb_records_unpack(const void* records_aos_dev, int64_t n, wfb_rec_meta* meta_dev, void* stream);
+
+/* Hit rows of record i have their edges clamped to clamp_len_dev[i] instead of event_length (a negative entry or a NULL
+ * array restores event_length).  This is hit_threshold on structured st_waveforms / filtered_waveforms rows whose
+ * `event_length` field differs from the row width: every sample of the row is scanned, the edges are clamped to the
+ * source's event_length (hit_finder.py:183-230, 388-391).  Lengths up to 2^24 - 2. */
+int wfb_meta_set_clamp(wfb_rec_meta* meta_dev, int64_t n, const int32_t* clamp_len_dev, void* stream);
 
 /* Raw int16 rows -> time-sorted records + wave_pool.  Replaces
  * _build_records_part_from_raw_array + _records_sort_order + _merge_records_part_refs
@@ -231,6 +241,7 @@ int wfb_waveform_width(const void* waves_dev, int64_t n_waves, int32_t length, i
 
 /* Per record cumulative-charge quantile indices.  Replaces
  * WaveformWidthIntegralPlugin.compute records branch (waveform_width_integral.py:166-231).
+ * pool_is_f32: 0 uint16 pool, 1 float32 pool, 2 int16 samples (structured st_waveforms rows used in place).
  * out_dev: n * 52 B WAVEFORM_WIDTH_INTEGRAL rows. */
 int wfb_width_integral(const void* pool_dev, int32_t pool_is_f32, int64_t pool_len,
                        const wfb_rec_meta* meta_dev, int64_t n, double q_low, double q_high,
@@ -296,6 +307,7 @@ int wfb_build_records_ragged(const void* samples_dev, int64_t samples_bytes, con
 #define WFB_WAVE_REC_U16 2
 #define WFB_WAVE_REC_F32 3
 #define WFB_WAVE_AOS_F32_AS_F64 4 /* float32 rows promoted to float64 first (signal_peaks_stream, signal_peaks.py:256-262) */
+#define WFB_WAVE_AOS_U16 5        /* uint16 rows: np.diff and the negation wrap modulo 65536 (peak_finding.py:488-495) */
 typedef struct wfb_peak_params {
     int32_t wave_kind;      /* WFB_WAVE_* */
     int32_t use_derivative; /* detect on the first difference (default) or on the level */
@@ -308,7 +320,7 @@ typedef struct wfb_peak_params {
     int32_t height_method;  /* 0 "minmax", 1 "diff" (hit), 2 "diff" by float64 cumsum (signal_peaks_stream) */
     int32_t height_window_extension;
     int32_t lmax;           /* longest record (samples) */
-    int32_t reserved_;
+    int32_t level_f32;      /* WFB_WAVE_AOS_F32 without derivative: baseline - wave in float32 (the baseline is np.mean of the float32 row) */
 } wfb_peak_params;
 size_t wfb_find_peaks_workspace_bytes(int64_t n);
 int wfb_find_peaks(const void* waves_dev, int64_t waves_len, const wfb_rec_meta* meta_dev, int64_t n,

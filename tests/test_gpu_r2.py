@@ -1,0 +1,192 @@
+"""GPU: inputs and shapes added in round 2 against goldens made by the LIVE reference
+(tests/golden/make_golden_r2.py): uint16 structured rows, rows without a baseline field, negative int16 rows in
+waveform_width_integral, rows whose event_length is shorter than the row, record lengths 256 / 2048 / 8192
+(BASELINE config 5), the 64-channel V1725-like chain SG -> hit -> waveform_width (config 3), and the host arrays a
+real Context hands to plugins (read-only, np.memmap)."""
+
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, assert_rows_match
+from fakes import Ctx
+
+pytestmark = pytest.mark.gpu
+
+FX_BF = ("height", "amp", "max_abs_diff")
+FX_HIT = ("height", "width", "rise_time", "fall_time")
+
+
+@pytest.fixture(scope="module")
+def G():
+    return np.load(os.path.join(ROOT, "tests", "golden", "r2_golden.npz"), allow_pickle=False)
+
+
+@pytest.fixture(scope="module")
+def P():
+    from waveformanalysis_b200 import plugins
+
+    return plugins
+
+
+def run(plugin, data, config=None):
+    return plugin.compute(Ctx(config, data), "run")
+
+
+def st_from_records(records, pool):
+    from waveformanalysis_b200.dtypes import create_record_dtype
+
+    L = int(records["event_length"][0])
+    st = np.zeros(len(records), dtype=create_record_dtype(L))
+    for f in ("baseline", "baseline_upstream", "polarity", "timestamp", "record_id", "dt", "event_length", "board", "channel"):
+        st[f] = records[f]
+    st["wave"] = pool.reshape(len(records), L).view(np.int16)
+    return st
+
+
+def strip_fields(arr, drop):
+    keep = [n for n in arr.dtype.names if n not in drop]
+    out = np.zeros(len(arr), dtype=np.dtype([(n, arr.dtype.fields[n][0]) for n in keep]))
+    for n in keep:
+        out[n] = arr[n]
+    return out
+
+
+def filtered_rows(st, fw):
+    L = st["wave"].shape[1]
+    dt = np.dtype([(n, (np.float32, (L,)) if n == "wave" else st.dtype.fields[n][0]) for n in st.dtype.names])
+    stf = np.zeros(len(st), dtype=dt)
+    for f in st.dtype.names:
+        if f != "wave":
+            stf[f] = st[f]
+    stf["wave"] = fw.reshape(len(st), L)
+    return stf
+
+
+def test_hit_on_uint16_rows(P, G):
+    st = st_from_records(G["a_records"], G["a_pool"])
+    dt_u16 = np.dtype([(n, (np.uint16, (400,)) if n == "wave" else st.dtype.fields[n][0]) for n in st.dtype.names])
+    st_u16 = np.zeros(len(st), dtype=dt_u16)
+    for n in st.dtype.names:
+        st_u16[n] = st[n] if n != "wave" else st["wave"].view(np.uint16)
+    assert_rows_match(run(P.B200HitFinderPlugin(), {"st_waveforms": st_u16}, {"use_filtered": False, "height": 12.0, "width": 2}),
+                      G["u16_deriv"], what="u16_deriv")
+    assert_rows_match(run(P.B200HitFinderPlugin(), {"st_waveforms": st_u16},
+                          {"use_filtered": False, "use_derivative": False, "height": 20.0, "prominence": 4.0, "width": 3}),
+                      G["u16_level"], what="u16_level")
+    assert_rows_match(run(P.B200HitFinderPlugin(), {"st_waveforms": st_u16},
+                          {"use_filtered": False, "height": 60000.0, "width": 1, "prominence": 1.0, "height_method": "diff"}),
+                      G["u16_diffheight"], what="u16_diffheight")
+
+
+def test_hit_without_baseline_field(P, G):
+    st = st_from_records(G["a_records"], G["a_pool"])
+    st_nb = strip_fields(st, {"baseline", "baseline_upstream"})
+    cfg = {"use_filtered": False, "use_derivative": False, "height": 20.0, "prominence": 4.0, "width": 3}
+    assert_rows_match(run(P.B200HitFinderPlugin(), {"st_waveforms": st_nb}, cfg), G["nobase_i16_level"], what="nobase_i16_level")
+    assert_rows_match(run(P.B200HitFinderPlugin(), {"st_waveforms": st_nb}, {"use_filtered": False, "height": 12.0, "width": 2}),
+                      G["nobase_i16_deriv"], what="nobase_i16_deriv")
+    stf_nb = strip_fields(filtered_rows(st, G["a_filtered_pool"]), {"baseline", "baseline_upstream"})
+    assert_rows_match(run(P.B200HitFinderPlugin(), {"filtered_waveforms": stf_nb, "st_waveforms": st_nb},
+                          {"use_derivative": False, "height": 20.0, "prominence": 4.0, "width": 3}),
+                      G["nobase_f32_level"], what="nobase_f32_level")
+    from waveformanalysis_b200 import ops
+
+    got = ops.find_peaks_stream_chunk(st_nb, stf_nb, use_derivative=False, height=25.0, prominence=4.0, width=3)
+    assert_rows_match(got, G["stream_nobase_level"], what="stream_nobase_level")
+
+
+def test_width_integral_on_negative_int16_rows(P, G):
+    st = st_from_records(G["a_records"], G["a_pool"])
+    st["wave"] = st["wave"] - 9000
+    st["baseline"] = st["baseline"] - 9000
+    st["polarity"] = G["neg_polarity"]
+    assert_rows_match(run(P.B200WaveformWidthIntegralPlugin(), {"st_waveforms": st}, {}), G["wint_neg"], what="wint_neg")
+
+
+def test_hit_threshold_rows_with_short_event_length(P, G):
+    st = st_from_records(G["a_records"], G["a_pool"])
+    st["event_length"] = G["short_event_length"]
+    assert_rows_match(run(P.B200ThresholdHitPlugin(), {"st_waveforms": st}, {"threshold": 15.0}), G["short_hits"], what="short_hits",
+                      float_exact=FX_HIT)
+    assert_rows_match(run(P.B200ThresholdHitPlugin(), {"st_waveforms": st}, {"threshold": 12.0, "left_extension": 5, "right_extension": 0}),
+                      G["short_hits_ext"], what="short_hits_ext", float_exact=FX_HIT)
+
+
+@pytest.mark.parametrize("L", [256, 2048, 8192])
+def test_config5_record_lengths(P, G, L):
+    r, p = G[f"L{L}_records"], G[f"L{L}_pool"]
+    base = {"records": r, "wave_pool": p}
+    assert_rows_match(run(P.B200BasicFeaturesPlugin(), base, {"wave_source": "records"}), G[f"L{L}_bf"], what="bf", float_exact=FX_BF)
+    assert_rows_match(run(P.B200ThresholdHitPlugin(), base, {"wave_source": "records", "threshold": 15.0}), G[f"L{L}_hits"], what="hits",
+                      float_exact=FX_HIT)
+    sg = run(P.B200WavePoolFilteredPlugin(), base, {})
+    assert sg.dtype == np.float32 and np.allclose(sg, G[f"L{L}_sg"], rtol=1e-5, atol=1e-3)
+    assert_rows_match(run(P.B200HitFinderPlugin(), base, {"use_filtered": False, "wave_source": "records", "height": 12.0, "width": 2}),
+                      G[f"L{L}_hit"], what="hit")
+    assert_rows_match(run(P.B200HitFinderPlugin(), {"records": r, "wave_pool_filtered": G[f"L{L}_sg"]},
+                          {"use_filtered": True, "wave_source": "records", "height": 8.0, "width": 2}), G[f"L{L}_hit_filt"], what="hit_filt")
+
+
+def test_find_peaks_long_records_use_the_global_staging(G):
+    """Records too long for any shared-memory staging (> ~18 k samples): same rows as the same samples cut into
+    pieces would give is not a property of find_peaks, so the check is against the numpy oracle."""
+    from oracle import np_oracle as O
+    from waveformanalysis_b200 import ops
+    from waveformanalysis_b200.synth import make_raw_run, records_from_raw
+
+    raw = make_raw_run(2, 3, 30_000, seed=17)
+    rec, pool = records_from_raw(raw)
+    got = ops.find_peaks_records(rec, pool, height=12.0, width=2)
+    L = 30_000
+    # -RecordsView.signals() in float64 (records_view.py:152-169, peak_finding.py:392-444): f32(baseline) - f32(wave)
+    waves = [(np.float32(rec["baseline"][i]) - pool[i * L:(i + 1) * L].astype(np.float32)).astype(np.float64) for i in range(len(rec))]
+    want = O.hit_find_peaks(waves, rec, source="records", height=12.0, width=2)
+    assert len(want) > 10
+    assert_rows_match(got, want, what="long hit")
+
+
+def test_config3_chain_64_channels(P, G):
+    r, p = G["c3_records"], G["c3_pool"]
+    base = {"records": r, "wave_pool": p}
+    sg = run(P.B200WavePoolFilteredPlugin(), base, {})
+    assert np.allclose(sg, G["c3_sg"], rtol=1e-5, atol=1e-3)
+    st = st_from_records(r, p)
+    stf = filtered_rows(st, sg)
+    assert_rows_match(run(P.B200HitFinderPlugin(), {"filtered_waveforms": stf, "st_waveforms": st}, {"height": 6.0, "width": 2}), G["c3_hit"],
+                      what="c3_hit")
+    hits = run(P.B200HitFinderPlugin(), {"records": r, "wave_pool_filtered": sg}, {"use_filtered": True, "wave_source": "records",
+                                                                                    "height": 8.0, "width": 2})
+    assert_rows_match(hits, G["c3_hit_records"], what="c3_hit_records")
+    data = {"hit": hits, "filtered_waveforms": stf, "st_waveforms": st}
+    assert_rows_match(run(P.B200WaveformWidthPlugin(), data, {"use_filtered": True, "sampling_rate": 0.25}), G["c3_width"], what="c3_width")
+    cfg = {"use_filtered": True, "sampling_rate": 0.25, "rise_low": 0.1, "rise_high": 0.5, "fall_high": 0.5, "fall_low": 0.1}
+    assert_rows_match(run(P.B200WaveformWidthPlugin(), data, cfg), G["c3_width_1050"], what="c3_width_1050")
+    assert_rows_match(run(P.B200BasicFeaturesPlugin(), base, {"wave_source": "records"}), G["c3_bf"], what="c3_bf", float_exact=FX_BF)
+    assert_rows_match(run(P.B200ThresholdHitPlugin(), base, {"wave_source": "records", "threshold": 15.0}), G["c3_hits_thr"], what="c3_hits",
+                      float_exact=FX_HIT)
+
+
+def test_memmap_and_read_only_inputs(P, golden, tmp_path):
+    """A real Context replaces every saved result by an np.memmap view of its cache file and may hand out read-only
+    arrays (core/context_execution.py:241-251): the plugins take those without copies on the Python side."""
+    rec, pool = golden["records"], golden["wave_pool"]
+    rp, pp = str(tmp_path / "records.bin"), str(tmp_path / "pool.bin")
+    rec.tofile(rp)
+    pool.tofile(pp)
+    rec_mm = np.memmap(rp, dtype=rec.dtype, mode="r")
+    pool_mm = np.memmap(pp, dtype=pool.dtype, mode="r")
+    assert not pool_mm.flags.writeable
+    base = {"records": rec_mm, "wave_pool": pool_mm}
+    assert_rows_match(run(P.B200BasicFeaturesPlugin(), base, {"wave_source": "records"}), golden["bf_default"], what="bf", float_exact=FX_BF)
+    assert_rows_match(run(P.B200ThresholdHitPlugin(), base, {"wave_source": "records", "threshold": 15.0}), golden["hits_thr15"], what="thr15",
+                      float_exact=FX_HIT)
+    sg = run(P.B200WavePoolFilteredPlugin(), base, {})
+    assert sg.shape == pool.shape and sg.dtype == np.float32
+    ro = pool.copy()
+    ro.setflags(write=False)
+    rr = rec[:200].copy()
+    rr.setflags(write=False)
+    out = run(P.B200WaveformWidthIntegralPlugin(), {"records": rr, "wave_pool": ro}, {"wave_source": "records"})
+    assert_rows_match(out, golden["wint_default"], what="wint")

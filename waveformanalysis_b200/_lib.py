@@ -109,7 +109,7 @@ _vp, _i64, _i32, _sz, _dbl = C.c_void_p, C.c_int64, C.c_int32, C.c_size_t, C.c_d
 class PeakParams(C.Structure):  # wfb_peak_params
     _fields_ = [("wave_kind", C.c_int32), ("use_derivative", C.c_int32), ("height", C.c_double), ("prominence", C.c_double),
                 ("width", C.c_double), ("threshold", C.c_double), ("has_threshold", C.c_int32), ("distance", C.c_int32),
-                ("height_method", C.c_int32), ("height_window_extension", C.c_int32), ("lmax", C.c_int32), ("reserved_", C.c_int32)]
+                ("height_method", C.c_int32), ("height_window_extension", C.c_int32), ("lmax", C.c_int32), ("level_f32", C.c_int32)]
 
 
 class GainRule(C.Structure):  # wfb_gain_rule
@@ -126,13 +126,15 @@ class S1S2Params(C.Structure):  # wfb_s1s2_params
                 ("s2_height", Range), ("width_in_samples", C.c_int32), ("conflict_policy", C.c_int32)]
 
 
-WAVE_AOS_I16, WAVE_AOS_F32, WAVE_REC_U16, WAVE_REC_F32, WAVE_AOS_F32_AS_F64 = 0, 1, 2, 3, 4
+WAVE_AOS_I16, WAVE_AOS_F32, WAVE_REC_U16, WAVE_REC_F32, WAVE_AOS_F32_AS_F64, WAVE_AOS_U16 = 0, 1, 2, 3, 4, 5
 
 PROTOTYPES = {
     "wfb_last_error": (C.c_char_p, []),
     "wfb_version": (C.c_int, []),
     "wfb_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3 + [C.c_char_p, C.c_int]),
+    "wfb_memcpy_h2d": (C.c_int, [_vp, _vp, C.c_size_t, _vp]),
     "wfb_records_unpack": (C.c_int, [_vp, _i64, _vp, _vp]),
+    "wfb_meta_set_clamp": (C.c_int, [_vp, _i64, _vp, _vp]),
     "wfb_build_records": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "wfb_build_records_workspace_bytes": (_sz, [_i64]),
     "wfb_features_hits_workspace_bytes": (_sz, [_i64]),

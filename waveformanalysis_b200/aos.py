@@ -13,8 +13,9 @@ RAW_POSITIVE = "rawpos"  # internal polarity tag: raw (unsigned-signal) arithmet
 
 
 def structured_as_records(data: np.ndarray, *, explicit_dt: int | None = None, raw_polarity: bool = False,
-                          check_event_length: bool = False):
-    """Return (records, pool, signed) for a structured waveform array.
+                          return_clamp: bool = False):
+    """Return (records, pool, signed) for a structured waveform array; with ``return_clamp`` a fourth value: None, or
+    the int32 lengths the edges of hit rows are clamped to when ``event_length`` differs from the row width.
 
     ``raw_polarity``: basic_features' st branch never uses the float32 signal path; a 'positive'
     polarity selects max-baseline / sum(wave-baseline) in float64 (basic_features.py:241-262).
@@ -45,9 +46,9 @@ def structured_as_records(data: np.ndarray, *, explicit_dt: int | None = None, r
         offsets = (np.arange(n, dtype=np.int64) * itemsize + wave_off) // elem
     # hit_threshold clamps hit edges to event_length (hit_finder.py:388-391); the other consumers
     # always use the whole row (basic_features.py:203, 225)
-    if check_event_length and "event_length" in names and n and np.any(data["event_length"] != L):
-        raise NotImplementedError("structured waveforms with event_length != row width are not supported by the B200 "
-                                  "plugins; use wave_source='records'")
+    clamp = None
+    if return_clamp and "event_length" in names and n and np.any(data["event_length"] != L):
+        clamp = np.maximum(data["event_length"].astype(np.int64), 0).astype(np.int32)
     rec = np.zeros(n, dtype=RECORDS_DTYPE)
     rec["baseline_upstream"] = np.nan
     rec["timestamp"] = data["timestamp"] if "timestamp" in names else 0
@@ -75,4 +76,6 @@ def structured_as_records(data: np.ndarray, *, explicit_dt: int | None = None, r
     rec["wave_offset"] = offsets
     rec["event_length"] = L
     rec["time"] = rec["timestamp"] // 1000
+    if return_clamp:
+        return rec, pool, signed, clamp
     return rec, pool, signed

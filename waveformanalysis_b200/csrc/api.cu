@@ -81,9 +81,37 @@ __global__ void records_unpack_kernel(const uint16_t* __restrict__ rows, long lo
     meta[i] = m;
 }
 
+__global__ void meta_set_clamp_kernel(wfb_rec_meta* __restrict__ meta, long long n, const int* __restrict__ clamp) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = clamp ? clamp[i] : -1;
+    const unsigned enc = (c >= 0) ? (unsigned)min(c, (1 << 24) - 2) + 1u : 0u;
+    meta[i].pad_[0] = (uint8_t)(enc & 0xff);
+    meta[i].pad_[1] = (uint8_t)((enc >> 8) & 0xff);
+    meta[i].pad_[2] = (uint8_t)((enc >> 16) & 0xff);
+}
+
 }  // namespace wfb
 
 using namespace wfb;
+
+extern "C" int wfb_meta_set_clamp(wfb_rec_meta* meta_dev, int64_t n, const int32_t* clamp_len_dev, void* stream) {
+    WFB_REQUIRE(n >= 0, "wfb_meta_set_clamp: negative n");
+    if (n == 0) return WFB_OK;
+    WFB_REQUIRE(meta_dev != nullptr, "wfb_meta_set_clamp: NULL meta");
+    meta_set_clamp_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(meta_dev, n, clamp_len_dev);
+    WFB_CUDA(cudaGetLastError());
+    return WFB_OK;
+}
+
+extern "C" int wfb_memcpy_h2d(void* dst_dev, const void* src_host, size_t bytes, void* stream) {
+    if (bytes == 0) return WFB_OK;
+    WFB_REQUIRE(dst_dev && src_host, "wfb_memcpy_h2d: NULL pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    WFB_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, st));
+    WFB_CUDA(cudaStreamSynchronize(st));  // pageable / memory-mapped sources: the caller may drop the array right away
+    return WFB_OK;
+}
 
 extern "C" const char* wfb_last_error(void) { return g_err; }
 extern "C" int wfb_version(void) { return 100; }
@@ -378,7 +406,12 @@ extern "C" int wfb_process_host(const void* records_host, int64_t n, const void*
 #undef PH_CUDA
 }
 
+namespace wfb {
+void release_peak_scratch();
+}
+
 extern "C" int wfb_release_cache(void) {
+    wfb::release_peak_scratch();
     std::lock_guard<std::mutex> lock(g_pipes_mu);
     for (HostPipe* hp : g_pipes) {
         if (!hp) continue;

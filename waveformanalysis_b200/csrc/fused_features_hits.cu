@@ -532,7 +532,7 @@ __global__ void __launch_bounds__(kWarps * 32) fused_features_hits_kernel(const 
         const long long rec = (long long)tile * kTile + warp * 32 + lane;
         const bool have = rec < a.n;
         long long off = 0, ts = 0, rid = 0;
-        int len = 0, dt = 1, pol = 0;
+        int len = 0, dt = 1, pol = 0, clen = -1;
         unsigned bc = 0;
         double b_rec = 0.0, b_feat = 0.0, thr = a.p.threshold;
         if (have) {
@@ -545,6 +545,7 @@ __global__ void __launch_bounds__(kWarps * 32) fused_features_hits_kernel(const 
             dt = (int)q1.w;
             bc = q2.x;
             pol = (int)(q2.y & 0xff);
+            clen = (int)(q2.y >> 8) - 1;  // edge clamp of the hit rows (wfb_meta_set_clamp), -1: event_length
             rid = (long long)(((unsigned long long)q2.w << 32) | q2.z);
             b_feat = b_rec;
             const int board = (int)(short)(bc & 0xffff), channel = (int)(short)(bc >> 16);
@@ -707,7 +708,7 @@ __global__ void __launch_bounds__(kWarps * 32) fused_features_hits_kernel(const 
             RowRec rr;
             rr.ts = bcast_i64(ts, owner);
             rr.rid = bcast_i64(rid, owner);
-            rr.len = __shfl_sync(kFull, len, owner);
+            rr.len = __shfl_sync(kFull, clen >= 0 ? clen : len, owner);
             rr.dt = __shfl_sync(kFull, dt, owner);
             rr.bc = __shfl_sync(kFull, bc, owner);
             const long long row = bcast_i64(my_row0, owner) + (e - __shfl_sync(kFull, my_ent0, owner));
@@ -750,7 +751,7 @@ __global__ void __launch_bounds__(kWarps * 32) fused_features_hits_kernel(const 
             sink.cap = a.hit_cap;
             sink.r.ts = bcast_i64(ts, j);
             sink.r.rid = bcast_i64(rid, j);
-            sink.r.len = r.len;
+            sink.r.len = __shfl_sync(kFull, clen >= 0 ? clen : len, j);
             sink.r.dt = __shfl_sync(kFull, dt, j);
             sink.r.bc = __shfl_sync(kFull, bc, j);
             sink.left = a.p.left_extension;

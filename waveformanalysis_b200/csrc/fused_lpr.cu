@@ -60,6 +60,7 @@ struct LprEnt {  // 16 bytes, raw aggregates: height / integral are finished one
 struct LaneRec {  // everything a lane knows about its record
     long long off, ts, rid;
     int len, dt, pol, mis, bias;
+    int clen;  // length the edges of the hit rows are clamped to (event_length unless wfb_meta_set_clamp set another)
     unsigned bc;
     double b_rec, b_feat, thr;
     int kmax;
@@ -167,7 +168,7 @@ struct DirectSink {  // rows straight to the output (records whose hits did not 
         bias = r.bias;
         rr.ts = bcast_i64(r.ts, src);
         rr.rid = bcast_i64(r.rid, src);
-        rr.len = __shfl_sync(kFull, r.len, src);
+        rr.len = __shfl_sync(kFull, r.clen, src);
         rr.dt = __shfl_sync(kFull, r.dt, src);
         rr.bc = __shfl_sync(kFull, r.bc, src);
     }
@@ -804,7 +805,7 @@ __global__ void __launch_bounds__(kLprWarps * 32, (HITS && !FEAT) ? WFB_LPR_MINB
         const long long rec = (long long)tile * kLprTile + warp * 32 + lane;
         const bool have = valid && rec < a.n;
         LaneRec r;
-        r.off = 0; r.ts = 0; r.rid = 0; r.len = 0; r.dt = 1; r.pol = 0; r.bc = 0;
+        r.off = 0; r.ts = 0; r.rid = 0; r.len = 0; r.dt = 1; r.pol = 0; r.bc = 0; r.clen = -1;
         r.b_rec = 0.0; r.b_feat = 0.0; r.thr = a.p.threshold;
         if (have) {
             const uint4* q = reinterpret_cast<const uint4*>(a.meta + rec);
@@ -816,6 +817,7 @@ __global__ void __launch_bounds__(kLprWarps * 32, (HITS && !FEAT) ? WFB_LPR_MINB
             r.dt = (int)q1.w;
             r.bc = q2.x;
             r.pol = (int)(q2.y & 0xff);
+            r.clen = (int)(q2.y >> 8) - 1;
             r.rid = (long long)(((unsigned long long)q2.w << 32) | q2.z);
             r.b_feat = r.b_rec;
             const int board = (int)(short)(r.bc & 0xffff), channel = (int)(short)(r.bc >> 16);
@@ -836,6 +838,7 @@ __global__ void __launch_bounds__(kLprWarps * 32, (HITS && !FEAT) ? WFB_LPR_MINB
                 r.len = 0;
             }
         }
+        if (r.clen < 0) r.clen = r.len;
         r.mis = (int)(r.off & 7);
         r.bias = a.p.signed_samples ? 32768 : 0;
         r.positive = r.pol == WFB_POL_POSITIVE || r.pol == WFB_POL_RAW_POSITIVE;
@@ -971,7 +974,7 @@ __global__ void __launch_bounds__(kLprWarps * 32, (HITS && !FEAT) ? WFB_LPR_MINB
         const int rel = s_woff[warp] + (incl - my_cnt);
         {
             DefLane d;
-            d.ts = r.ts; d.rid = r.rid; d.b = r.b_rec; d.len = r.len; d.dt = r.dt; d.bc = r.bc;
+            d.ts = r.ts; d.rid = r.rid; d.b = r.b_rec; d.len = r.clen; d.dt = r.dt; d.bc = r.bc;
             d.rel_pos = ((unsigned)rel << 1) | (r.positive ? 1u : 0u);
             ws.def[lane] = d;
             if (lane == 0) {

@@ -12,6 +12,7 @@
 // compact the survivors in order with ballots; prominence / width scans run one peak per lane.  Rows are
 // variable in number: a counting pass, a device scan and an emitting pass (same code, rows switched on).
 #include <algorithm>
+#include <mutex>
 
 #include "common.cuh"
 #include "np_sum.cuh"
@@ -38,6 +39,7 @@ struct Wave {
     bool pos;
     __device__ __forceinline__ double operator[](int i) const {
         if (load_kind == WFB_WAVE_AOS_I16) return (double)static_cast<const short*>(base)[off + i];
+        if (load_kind == WFB_WAVE_AOS_U16) return (double)static_cast<const unsigned short*>(base)[off + i];
         if (load_kind == WFB_WAVE_AOS_F32 || load_kind == WFB_WAVE_AOS_F32_AS_F64) return (double)static_cast<const float*>(base)[off + i];
         const float s = (load_kind == WFB_WAVE_REC_U16) ? (float)static_cast<const unsigned short*>(base)[off + i]
                                                         : static_cast<const float*>(base)[off + i];
@@ -60,11 +62,13 @@ __device__ __forceinline__ double detection_value(const PeakRec& r, int i) {
             const short d = (short)((int)r.w[i + 1] - (int)r.w[i]);
             return (double)(short)(-(int)d);
         }
+        if (r.kind == WFB_WAVE_AOS_U16) return (double)(((int)r.w[i] - (int)r.w[i + 1]) & 0xffff);  // uint16 diff and negation wrap
         if (r.kind == WFB_WAVE_AOS_F32) return (double)(-__fsub_rn((float)r.w[i + 1], (float)r.w[i]));
         if (r.kind == WFB_WAVE_AOS_F32_AS_F64) return -__dsub_rn(r.w[i + 1], r.w[i]);  // streaming: float64 copy of the row
         return __dsub_rn(r.w[i + 1], r.w[i]);  // records: +diff of the float64 signal
     }
-    if (r.kind == WFB_WAVE_AOS_I16 || r.kind == WFB_WAVE_AOS_F32 || r.kind == WFB_WAVE_AOS_F32_AS_F64) return __dsub_rn(r.baseline, r.w[i]);
+    if (r.kind == WFB_WAVE_AOS_I16 || r.kind == WFB_WAVE_AOS_U16 || r.kind == WFB_WAVE_AOS_F32 || r.kind == WFB_WAVE_AOS_F32_AS_F64)
+        return __dsub_rn(r.baseline, r.w[i]);
     return r.w[i];
 }
 
@@ -105,6 +109,11 @@ __device__ float peak_height(const PeakRec& r, double edge_start, double edge_en
             for (int i = s; i < e; ++i) acc += (short)((int)(short)(-(int)r.w[i + 1]) - (int)(short)(-(int)r.w[i]));
             return (float)(double)acc;
         }
+        if (r.kind == WFB_WAVE_AOS_U16) {
+            unsigned long long acc = 0;  // uint16 diffs of the wrapped negation, summed in uint64
+            for (int i = s; i < e; ++i) acc += (unsigned)(((int)r.w[i] - (int)r.w[i + 1]) & 0xffff);
+            return (float)(double)acc;
+        }
         if (r.kind == WFB_WAVE_AOS_F32) return numpy_pairwise_sum_t<float>(OffsetSrc<DiffSrcF32>{DiffSrcF32{r.w}, s}, e - s);
         return (float)numpy_pairwise_sum(OffsetSrc<DiffSrcF64>{DiffSrcF64{r.w}, s}, e - s);
     }
@@ -114,6 +123,7 @@ __device__ float peak_height(const PeakRec& r, double edge_start, double edge_en
     double mx = r.w[a], mn = r.w[a];
     for (int i = a + 1; i < b; ++i) { mx = fmax(mx, r.w[i]); mn = fmin(mn, r.w[i]); }
     if (r.kind == WFB_WAVE_AOS_I16) return (float)(double)(short)((int)mx - (int)mn);
+    if (r.kind == WFB_WAVE_AOS_U16) return (float)(double)(((int)mx - (int)mn) & 0xffff);
     if (r.kind == WFB_WAVE_AOS_F32) return __fsub_rn((float)mx, (float)mn);
     return (float)__dsub_rn(mx, mn);
 }
@@ -173,18 +183,19 @@ __global__ void __launch_bounds__(kPeakWarps * 32) find_peaks_kernel(const void*
                                                                      const wfb_peak_params p, int lcap, int* __restrict__ counts,
                                                                      const long long* __restrict__ row_incl,
                                                                      uint8_t* __restrict__ rows, long long row_cap, int* __restrict__ err,
-                                                                     PeakCacheEnt* __restrict__ cache) {
+                                                                     PeakCacheEnt* __restrict__ cache, uint8_t* __restrict__ gscratch) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = lane_id();
-    const long long rec = (long long)blockIdx.x * kPeakWarps + warp;
-    if (rec >= n) return;
-    // per warp: x[lcap] doubles, peak positions int[lcap/2 + 2], keep flags
-    const size_t per_warp = (size_t)lcap * 8 + (size_t)(lcap / 2 + 2) * 4 + (size_t)(lcap / 2 + 2);
-    uint8_t* base = smem + (size_t)warp * ((per_warp + 15) & ~(size_t)15);
+    const int nwarps = blockDim.x >> 5;  // 4, 2 or 1: as many as fit the shared memory with records of lcap samples
+    // per warp: x[lcap] doubles, peak positions int[lcap/2 + 2], keep flags; in shared memory, or (records too long
+    // even for one warp per block) in a global scratch area that stays in L2
+    const size_t per_warp = (((size_t)lcap * 8 + (size_t)(lcap / 2 + 2) * 4 + (size_t)(lcap / 2 + 2)) + 15) & ~(size_t)15;
+    uint8_t* base = gscratch ? gscratch + ((size_t)blockIdx.x * nwarps + warp) * per_warp : smem + (size_t)warp * per_warp;
     double* x = reinterpret_cast<double*>(base);
     int* peaks = reinterpret_cast<int*>(x + lcap);
     uint8_t* keep = reinterpret_cast<uint8_t*>(peaks + (lcap / 2 + 2));
 
+    auto do_record = [&](const long long rec) {
     const wfb_rec_meta mrec = meta[rec];
     int len = mrec.event_length;
     const long long off = mrec.wave_offset;
@@ -244,15 +255,21 @@ __global__ void __launch_bounds__(kPeakWarps * 32) find_peaks_kernel(const void*
         };
         const double bl = r.baseline;
         auto lvl_sub = [&](double w) { return __dsub_rn(bl, w); };
+        // float32 rows without a baseline field: the level is np.mean(row) (float32) minus the float32 row (peak_finding.py:508-511)
+        auto lvl_sub32 = [&](double w) { return p.level_f32 ? (double)__fsub_rn((float)bl, (float)w) : __dsub_rn(bl, w); };
         auto lvl_id = [](double w) { return w; };
         switch (p.wave_kind) {
+            case WFB_WAVE_AOS_U16:  // np.diff on uint16 and its negation wrap modulo 65536
+                stage([&](int i) { return (double)static_cast<const unsigned short*>(waves)[o + i]; },
+                      [](double wn, double wi) { return (double)(((int)wi - (int)wn) & 0xffff); }, lvl_sub);
+                break;
             case WFB_WAVE_AOS_I16:  // np.diff on int16 stays int16, so does the negation
                 stage([&](int i) { return (double)static_cast<const short*>(waves)[o + i]; },
                       [](double wn, double wi) { return (double)(short)(-(int)(short)((int)wn - (int)wi)); }, lvl_sub);
                 break;
             case WFB_WAVE_AOS_F32:
                 stage([&](int i) { return (double)static_cast<const float*>(waves)[o + i]; },
-                      [](double wn, double wi) { return (double)(-__fsub_rn((float)wn, (float)wi)); }, lvl_sub);
+                      [](double wn, double wi) { return (double)(-__fsub_rn((float)wn, (float)wi)); }, lvl_sub32);
                 break;
             case WFB_WAVE_AOS_F32_AS_F64:  // streaming: float64 copy of the row
                 stage([&](int i) { return (double)static_cast<const float*>(waves)[o + i]; },
@@ -386,6 +403,11 @@ __global__ void __launch_bounds__(kPeakWarps * 32) find_peaks_kernel(const void*
         ++nout;
     }
     if (!EMIT && lane == 0) counts[rec] = nout;
+    };
+    for (long long rec = (long long)blockIdx.x * nwarps + warp; rec < n; rec += (long long)gridDim.x * nwarps) {
+        do_record(rec);
+        __syncwarp();  // the staging area is reused by the warp's next record
+    }
 }
 
 __global__ void peaks_counts_to_i64_kernel(const int* __restrict__ counts, long long n, long long* __restrict__ out) {
@@ -401,6 +423,54 @@ __global__ void peaks_total_kernel(const long long* __restrict__ incl, long long
 using namespace wfb;
 
 static size_t pk_al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// Staging area of wfb_find_peaks for records too long for shared memory: kept per device between calls (the stream
+// order of the calls serialises its use), freed by wfb_release_cache().
+namespace {
+std::mutex g_scratch_mu;
+void* g_scratch[64];
+size_t g_scratch_cap[64];
+int peak_scratch(size_t bytes, uint8_t** out) {
+    std::lock_guard<std::mutex> lock(g_scratch_mu);
+    int dev = 0;
+    WFB_CUDA(cudaGetDevice(&dev));
+    WFB_REQUIRE(dev >= 0 && dev < 64, "wfb_find_peaks: device index %d out of range", dev);
+    if (g_scratch_cap[dev] < bytes) {
+        if (g_scratch[dev]) {
+            WFB_CUDA(cudaDeviceSynchronize());
+            cudaFree(g_scratch[dev]);
+            g_scratch[dev] = nullptr;
+            g_scratch_cap[dev] = 0;
+        }
+        cudaError_t e = cudaMalloc(&g_scratch[dev], bytes);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            g_scratch[dev] = nullptr;
+            set_error("wfb_find_peaks: cudaMalloc(%zu) for the long-record staging area failed", bytes);
+            return WFB_ERR_NOMEM;
+        }
+        g_scratch_cap[dev] = bytes;
+    }
+    *out = static_cast<uint8_t*>(g_scratch[dev]);
+    return WFB_OK;
+}
+}  // namespace
+
+namespace wfb {
+void release_peak_scratch() {
+    std::lock_guard<std::mutex> lock(g_scratch_mu);
+    for (int d = 0; d < 64; ++d) {
+        if (!g_scratch[d]) continue;
+        int cur = 0;
+        cudaGetDevice(&cur);
+        cudaSetDevice(d);
+        cudaFree(g_scratch[d]);
+        cudaSetDevice(cur);
+        g_scratch[d] = nullptr;
+        g_scratch_cap[d] = 0;
+    }
+}
+}  // namespace wfb
 
 extern "C" size_t wfb_find_peaks_workspace_bytes(int64_t n) {
     const size_t m = pk_al256((size_t)std::max<int64_t>(n, 1) * 8);
@@ -420,14 +490,26 @@ extern "C" int wfb_find_peaks(const void* waves_dev, int64_t waves_len, const wf
     }
     WFB_REQUIRE(meta_dev && workspace_dev && (waves_dev || waves_len == 0), "wfb_find_peaks: NULL pointer");
     WFB_REQUIRE(row_cap == 0 || rows_out_dev != nullptr, "wfb_find_peaks: NULL row buffer");
-    WFB_REQUIRE(params->wave_kind >= WFB_WAVE_AOS_I16 && params->wave_kind <= WFB_WAVE_AOS_F32_AS_F64, "wfb_find_peaks: unknown wave_kind");
+    WFB_REQUIRE(params->wave_kind >= WFB_WAVE_AOS_I16 && params->wave_kind <= WFB_WAVE_AOS_U16, "wfb_find_peaks: unknown wave_kind");
     WFB_REQUIRE(params->height_method >= 0 && params->height_method <= 2, "unsupported height_method");
     WFB_REQUIRE(params->lmax > 0, "wfb_find_peaks: lmax must be the longest record");
     WFB_REQUIRE(workspace_bytes >= wfb_find_peaks_workspace_bytes(n), "wfb_find_peaks: workspace too small");
     const int lcap = (params->lmax + 1) & ~1;
     const size_t per_warp = (((size_t)lcap * 8 + (size_t)(lcap / 2 + 2) * 4 + (size_t)(lcap / 2 + 2)) + 15) & ~(size_t)15;
-    const size_t dyn = per_warp * kPeakWarps;
-    WFB_REQUIRE(dyn <= 220 * 1024, "wfb_find_peaks: records longer than %d samples do not fit the shared-memory staging", 220 * 1024 / 11 / kPeakWarps);
+    // warps per block: as many (4, 2, 1) as fit the shared memory; longer records stage in a global scratch area
+    // (a bounded persistent grid, so the area stays small enough for L2)
+    int nwarps = kPeakWarps;
+    while (nwarps > 1 && per_warp * nwarps > 200 * 1024) nwarps >>= 1;
+    const bool in_global = per_warp * nwarps > 200 * 1024;
+    if (in_global) nwarps = kPeakWarps;
+    const size_t dyn = in_global ? 0 : per_warp * nwarps;
+    unsigned grid = (unsigned)std::min<long long>((n + nwarps - 1) / nwarps, 0x7fffffff);
+    uint8_t* gscratch = nullptr;
+    if (in_global) {
+        grid = (unsigned)std::min<long long>(grid, (long long)sm_count() * 2);
+        const int rc_s = peak_scratch((size_t)grid * nwarps * per_warp, &gscratch);
+        if (rc_s != WFB_OK) return rc_s;
+    }
     uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
     const size_t m = pk_al256((size_t)n * 8);
     long long* cnt64 = reinterpret_cast<long long*>(ws);
@@ -439,10 +521,9 @@ extern "C" int wfb_find_peaks(const void* waves_dev, int64_t waves_len, const wf
     WFB_CUDA(cudaMemsetAsync(err, 0, 4, st));
     wfb_peak_params p = *params;
     p.distance = (int)std::min<long long>(std::max<long long>(p.distance, 0), 1 << 30);
-    const unsigned grid = (unsigned)((n + kPeakWarps - 1) / kPeakWarps);
     WFB_CUDA(cudaFuncSetAttribute(find_peaks_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     WFB_CUDA(cudaFuncSetAttribute(find_peaks_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    find_peaks_kernel<false><<<grid, kPeakWarps * 32, dyn, st>>>(waves_dev, waves_len, meta_dev, n, p, lcap, counts, nullptr, nullptr, 0, err, cache);
+    find_peaks_kernel<false><<<grid, nwarps * 32, dyn, st>>>(waves_dev, waves_len, meta_dev, n, p, lcap, counts, nullptr, nullptr, 0, err, cache, gscratch);
     peaks_counts_to_i64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(counts, n, cnt64);
     int rc = inclusive_scan_sum_i64(cnt64, incl, n, scan_ws, st);
     if (rc != WFB_OK) return rc;
@@ -451,8 +532,8 @@ extern "C" int wfb_find_peaks(const void* waves_dev, int64_t waves_len, const wf
         const long long slots = n * kPeakCache;
         peaks_emit_cached_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, st>>>(waves_dev, waves_len, meta_dev, n, p, counts, incl,
                                                                                static_cast<uint8_t*>(rows_out_dev), row_cap, cache);
-        find_peaks_kernel<true><<<grid, kPeakWarps * 32, dyn, st>>>(waves_dev, waves_len, meta_dev, n, p, lcap, counts, incl,
-                                                                  static_cast<uint8_t*>(rows_out_dev), row_cap, err, cache);
+        find_peaks_kernel<true><<<grid, nwarps * 32, dyn, st>>>(waves_dev, waves_len, meta_dev, n, p, lcap, counts, incl,
+                                                              static_cast<uint8_t*>(rows_out_dev), row_cap, err, cache, gscratch);
     }
     if (counts_out_dev) WFB_CUDA(cudaMemcpyAsync(counts_out_dev, counts, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
     WFB_CUDA(cudaGetLastError());

@@ -373,8 +373,11 @@ extern "C" int wfb_width_integral(const void* pool_dev, int32_t pool_is_f32, int
     WFB_REQUIRE(meta_dev && out_dev, "wfb_width_integral: NULL pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const unsigned blocks = (unsigned)((n + 127) / 128);
-    if (pool_is_f32)
+    if (pool_is_f32 == 1)
         width_integral_kernel<float><<<blocks, 128, 0, st>>>(static_cast<const float*>(pool_dev), pool_len, meta_dev, n, q_low, q_high,
+                                                           dt_ns, pool_base, row_base, static_cast<uint8_t*>(out_dev));
+    else if (pool_is_f32 == 2)  // int16 samples (structured st_waveforms rows used in place)
+        width_integral_kernel<short><<<blocks, 128, 0, st>>>(static_cast<const short*>(pool_dev), pool_len, meta_dev, n, q_low, q_high,
                                                            dt_ns, pool_base, row_base, static_cast<uint8_t*>(out_dev));
     else
         width_integral_kernel<uint16_t><<<blocks, 128, 0, st>>>(static_cast<const uint16_t*>(pool_dev), pool_len, meta_dev, n, q_low,

@@ -53,6 +53,31 @@ def _hptr(a: np.ndarray | None) -> C.c_void_p:
     return C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(0)
 
 
+_TORCH_DTYPES: dict = {}
+
+
+def upload(a: np.ndarray, *, tail: int = 0):
+    """Host array -> device tensor through ``wfb_memcpy_h2d``.  Takes whatever a Context hands to a plugin - pageable,
+    read-only or ``np.memmap`` arrays (core/context_execution.py:241-251) - without ``torch.from_numpy`` (which wants
+    writable memory).  uint16 travels as int16, structured / string arrays as bytes; ``tail`` extra elements are
+    allocated behind the data (the kernels may read up to the next 16-byte boundary)."""
+    torch = _torch()
+    a = np.ascontiguousarray(a)
+    if a.dtype == np.uint16:
+        tdt, count = torch.int16, a.size
+    elif a.dtype.names is not None or a.dtype.kind in "USV":
+        tdt, count = torch.uint8, a.nbytes
+    else:
+        key = a.dtype.str
+        if key not in _TORCH_DTYPES:
+            _TORCH_DTYPES[key] = torch.from_numpy(np.empty(0, dtype=a.dtype)).dtype
+        tdt, count = _TORCH_DTYPES[key], a.size
+    t = torch.empty(count + int(tail), dtype=tdt, device="cuda")
+    if a.nbytes:
+        _lib.check(_lib.load().wfb_memcpy_h2d(C.c_void_p(t.data_ptr()), C.c_void_p(a.ctypes.data), a.nbytes, _stream()), "wfb_memcpy_h2d")
+    return t[:count] if tail else t
+
+
 # --------------------------------------------------------------------------------------------
 # host-side argument preparation
 # --------------------------------------------------------------------------------------------
@@ -244,21 +269,21 @@ class DeviceRun:
         return int(self.pool.numel())
 
     @classmethod
-    def from_host(cls, records: np.ndarray, pool: np.ndarray, explicit_dt: int | None = None, *, pool_base: int = 0, row_base: int = 0) -> "DeviceRun":
+    def from_host(cls, records: np.ndarray, pool: np.ndarray, explicit_dt: int | None = None, *, pool_base: int = 0, row_base: int = 0,
+                  clamp_lengths: np.ndarray | None = None) -> "DeviceRun":
         torch = _torch()
         lib = _lib.load()
         rec = packed_records(records, explicit_dt)
         pool, is_f32 = check_pool(pool)
         n = len(rec)
-        rows = torch.from_numpy(rec.view(np.uint8).reshape(-1).copy() if n else np.zeros(0, np.uint8)).cuda()
-        if is_f32:
-            d_pool = torch.empty(len(pool) + 16, dtype=torch.float32, device="cuda")[: len(pool)]
-            d_pool.copy_(torch.from_numpy(pool))
-        else:
-            d_pool = torch.empty(len(pool) + 16, dtype=torch.int16, device="cuda")[: len(pool)]
-            d_pool.copy_(torch.from_numpy(pool.view(np.int16)))
+        rows = upload(rec)
+        d_pool = upload(pool, tail=16)
         meta = torch.empty(max(n, 1) * 48, dtype=torch.uint8, device="cuda")
         _lib.check(lib.wfb_records_unpack(_ptr(rows), n, _ptr(meta), _stream()), "wfb_records_unpack")
+        if clamp_lengths is not None and n:
+            d_clamp = upload(np.ascontiguousarray(clamp_lengths, dtype=np.int32))
+            _lib.check(lib.wfb_meta_set_clamp(_ptr(meta), n, _ptr(d_clamp), _stream()), "wfb_meta_set_clamp")
+            torch.cuda.current_stream().synchronize()
         lmax = int(rec["event_length"].max()) if n else 0
         return cls(meta, d_pool, n, is_f32, max(lmax, 0), records_rows=rows, pool_base=pool_base, row_base=row_base)
 
@@ -294,6 +319,7 @@ class DeviceRun:
         out=None,
         want_counts: bool = False,
         lmax: int | None = None,
+        signed_samples: bool = False,
     ) -> dict:
         """One fused pass; returns device tensors (uint8 row buffers) + the int64 total tensor.
         Asynchronous: nothing is copied to the host."""
@@ -302,11 +328,12 @@ class DeviceRun:
         flags = (_lib.DO_FEATURES if features else 0) | (_lib.DO_HITS if hits else 0)
         d_rules = None
         if rules is not None and len(rules):
-            d_rules = torch.from_numpy(rules.view(np.uint8).reshape(-1).copy()).cuda()
+            d_rules = upload(rules)
         p = make_params(flags=flags, pool_is_f32=self.pool_is_f32, height_range=height_range, area_range=area_range,
                         threshold=threshold, left_extension=left_extension, right_extension=right_extension,
                         lmax=self.lmax if lmax is None else lmax, n_rules=0 if d_rules is None else len(rules),
-                        rules_dev=0 if d_rules is None else d_rules.data_ptr(), pool_base=self.pool_base, row_base=self.row_base)
+                        rules_dev=0 if d_rules is None else d_rules.data_ptr(), pool_base=self.pool_base, row_base=self.row_base,
+                        signed_samples=signed_samples)
         out = out or {}
         n = self.n
         feat = out.get("features")

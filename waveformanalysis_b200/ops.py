@@ -21,7 +21,7 @@ from .dtypes import (
     WAVEFORM_WIDTH_DTYPE,
     WAVEFORM_WIDTH_INTEGRAL_DTYPE,
 )
-from .engine import DeviceRun, _ptr, _stream, _torch, check_pool, packed_records
+from .engine import DeviceRun, _ptr, _stream, _torch, check_pool, packed_records, upload
 
 # --------------------------------------------------------------------------------------------
 # small helpers
@@ -29,13 +29,7 @@ from .engine import DeviceRun, _ptr, _stream, _torch, check_pool, packed_records
 
 
 def _dev(a: np.ndarray):
-    torch = _torch()
-    a = np.ascontiguousarray(a)
-    if a.dtype == np.uint16:
-        return torch.from_numpy(a.view(np.int16)).cuda()
-    if a.dtype.names is not None or a.dtype.kind in "US":
-        return torch.from_numpy(a.view(np.uint8).reshape(-1)).cuda()
-    return torch.from_numpy(a).cuda()
+    return upload(a)
 
 
 def _empty(nbytes: int):
@@ -67,7 +61,7 @@ def build_records_ragged(timestamps_ps, boards, channels, sample_blocks, *, dt_n
     base = 0
     for b in blocks:
         if b.nbytes:
-            d_blob[base:base + b.nbytes].copy_(torch.from_numpy(b.view(np.uint8).reshape(-1)))
+            d_blob[base:base + b.nbytes].copy_(upload(b.reshape(-1).view(np.uint8)))
         base += (b.nbytes + 15) & ~15
     off, ln = np.concatenate(offs), np.concatenate(lens)
     total = int(ln.astype(np.int64).sum())
@@ -100,8 +94,7 @@ def build_records(timestamps_ps, boards, channels, samples, *, dt_ns: int, basel
     n, L = samples.shape
     if n == 0:
         return np.zeros(0, dtype=RECORDS_DTYPE), np.zeros(0, dtype=np.uint16)
-    d_s = torch.empty(n * L + 16, dtype=torch.int16, device="cuda")[: n * L]
-    d_s.copy_(torch.from_numpy(samples.view(np.int16).reshape(-1)))
+    d_s = upload(samples.reshape(-1), tail=16)
     d_ts = _dev(np.asarray(timestamps_ps, dtype=np.int64))
     d_b = _dev(np.asarray(boards, dtype=np.int16))
     d_c = _dev(np.asarray(channels, dtype=np.int16))
@@ -299,8 +292,9 @@ def waveform_width(hits: np.ndarray, wave_record_ids: np.ndarray, waves: np.ndar
 
 
 def width_integral(records: np.ndarray, pool: np.ndarray, *, q_low=0.10, q_high=0.90, sampling_rate=0.5, dt=None,
-                   run: DeviceRun | None = None) -> np.ndarray:
-    """Per-record cumulative-charge quantile widths (waveform_width_integral.py:83-231)."""
+                   run: DeviceRun | None = None, signed_samples: bool = False) -> np.ndarray:
+    """Per-record cumulative-charge quantile widths (waveform_width_integral.py:83-231).  ``signed_samples``: the
+    16-bit pool holds int16 values (structured st_waveforms rows used in place)."""
     lib = _lib.load()
     if dt is None:
         if sampling_rate <= 0:
@@ -314,7 +308,8 @@ def width_integral(records: np.ndarray, pool: np.ndarray, *, q_low=0.10, q_high=
     if run is None:
         run = DeviceRun.from_host(records, pool, explicit_dt=1)
     out = _empty(n * 52)
-    _lib.check(lib.wfb_width_integral(_ptr(run.pool), run.pool_is_f32, run.pool_len, _ptr(run.meta), n, float(q_low), float(q_high),
+    kind = 2 if (signed_samples and not run.pool_is_f32) else run.pool_is_f32
+    _lib.check(lib.wfb_width_integral(_ptr(run.pool), kind, run.pool_len, _ptr(run.meta), n, float(q_low), float(q_high),
                                       float(dt), run.pool_base, run.row_base, _ptr(out), _stream()), "wfb_width_integral")
     return out[: n * 52].cpu().numpy().view(WAVEFORM_WIDTH_INTEGRAL_DTYPE)
 
@@ -475,7 +470,7 @@ def hit_merge(hits: np.ndarray, *, merge_gap_ns: float = 0.0, max_total_width_ns
         raise ValueError("hit_merge expects THRESHOLD_HIT_DTYPE rows")
     lib = _lib.load()
     torch = _torch()
-    d_hits = torch.from_numpy(np.ascontiguousarray(hits).view(np.uint8).reshape(-1).copy()).cuda()
+    d_hits = upload(hits)
     d_order = torch.empty(nh, dtype=torch.int64, device="cuda")
     d_cidx = torch.empty(nh, dtype=torch.int64, device="cuda")
     d_merged = torch.empty(nh * HIT_MERGED_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
@@ -568,7 +563,8 @@ def build_records_from_v1725(blobs, names, dt_ns: int):
 # hit = scipy.signal.find_peaks per record
 # --------------------------------------------------------------------------------------------
 def _find_peaks(records: np.ndarray, pool: np.ndarray, kind: int, *, use_derivative=True, height=30.0, distance=2, prominence=0.7,
-                width=4, threshold=None, height_method="minmax", height_window_extension=4, cumsum_diff=False) -> np.ndarray:
+                width=4, threshold=None, height_method="minmax", height_window_extension=4, cumsum_diff=False,
+                level_f32: bool = False) -> np.ndarray:
     from .dtypes import HIT_DTYPE
 
     lib = _lib.load()
@@ -589,7 +585,7 @@ def _find_peaks(records: np.ndarray, pool: np.ndarray, kind: int, *, use_derivat
                         has_threshold=int(threshold is not None), distance=int(distance if distance is not None else 1),
                         height_method=0 if height_method == "minmax" else (2 if cumsum_diff else 1),
                         height_window_extension=int(height_window_extension),
-                        lmax=lmax)
+                        lmax=lmax, level_f32=int(bool(level_f32)))
     ws = _empty(lib.wfb_find_peaks_workspace_bytes(n))
     total = torch.zeros(1, dtype=torch.int64, device="cuda")
     cap = max(1024, 2 * n)
@@ -624,15 +620,25 @@ def find_peaks_waveforms(data: np.ndarray, *, explicit_dt=None, **opts) -> np.nd
     elif signed:
         kind = _lib.WAVE_AOS_I16
     else:
-        raise NotImplementedError("hit on uint16 structured waveforms is not offloaded (numpy's uint16 diff wraps)")
+        kind = _lib.WAVE_AOS_U16  # np.diff / negation of uint16 rows wrap modulo 65536, as in the reference
+    L = int(rec["event_length"][0]) if len(rec) else 0
     if "event_length" in names and len(data):
         el = data["event_length"].astype(np.int64)
-        L = int(rec["event_length"][0])
         rec["event_length"] = np.where((el > 0) & (el < L), el, L)
-    if "baseline" not in names:
-        raise NotImplementedError("hit on structured waveforms without a baseline field is not offloaded")
+    level_f32 = False
+    if "baseline" not in names and len(data) and not opts.get("use_derivative", True):
+        # no baseline field: the level is np.mean of the (truncated) row, in the row's own mean dtype
+        # (peak_finding.py:508-511: float64 for integer rows, float32 for float32 rows)
+        lens = rec["event_length"].astype(np.int64)
+        wave = data["wave"]
+        if np.all(lens == L):
+            means = wave.mean(axis=1)
+        else:
+            means = np.array([wave[i, : lens[i]].mean() for i in range(len(data))])
+        rec["baseline"] = means.astype(np.float64)
+        level_f32 = pool.dtype == np.float32
     rec["polarity"] = "unknown"
-    return _find_peaks(rec, pool, kind, **opts)
+    return _find_peaks(rec, pool, kind, level_f32=level_f32, **opts)
 
 
 def find_peaks_stream_chunk(st_chunk: np.ndarray, filtered_chunk: np.ndarray, *, explicit_dt=None, event_offset=0, use_derivative=True,
@@ -663,8 +669,11 @@ def find_peaks_stream_chunk(st_chunk: np.ndarray, filtered_chunk: np.ndarray, *,
     rec["board"] = st_chunk["board"] if "board" in names else 0
     if "baseline" in names:
         rec["baseline"] = st_chunk["baseline"]
-    elif not use_derivative:
-        raise NotImplementedError("signal_peaks_stream without a baseline field and use_derivative=False is not offloaded")
+    elif not use_derivative:  # np.mean of the float64 copy of the row (signal_peaks.py:318-320)
+        L = int(rec["event_length"][0])
+        offs = rec["wave_offset"].astype(np.int64)
+        rows64 = pool[(offs[:, None] + np.arange(L)[None, :])].astype(np.float64)
+        rec["baseline"] = rows64.mean(axis=1)
     if "dt" in names:
         rec["dt"] = st_chunk["dt"]
     elif explicit_dt is not None:

@@ -44,6 +44,7 @@ class B200ThresholdHitPlugin(Plugin):
         channel_config_cfg = context.get_config(self, "channel_config")
         wave_input = load_wave_input(context, self, run_id, needs_wave_samples=True)
         signed = False
+        clamp = None
         if wave_input.spec.is_records:
             records, pool = wave_input.records, wave_input.wave_pool
             if records is None or pool is None:
@@ -58,12 +59,19 @@ class B200ThresholdHitPlugin(Plugin):
             if len(data) == 0:
                 return np.zeros(0, dtype=THRESHOLD_HIT_DTYPE)
             dt_scalar = check_dt_array(data, explicit_dt, self.provides, wave_input.spec.data_name)
-            records, pool, signed = structured_as_records(data, explicit_dt=dt_scalar, check_event_length=True)
+            records, pool, signed, clamp = structured_as_records(data, explicit_dt=dt_scalar, return_clamp=True)
         names = records.dtype.names
         boards = records["board"] if "board" in names else np.zeros(len(records), np.int16)
         channels = records["channel"] if "channel" in names else np.zeros(len(records), np.int16)
         thr = per_channel_option(channel_config_cfg, run_id, boards, channels, "threshold", threshold)
         thr = {k: float(v) for k, v in thr.items() if float(v) != threshold}
+        if clamp is not None:
+            # rows whose event_length differs from the row width: the whole row is scanned, the edges are clamped to
+            # the source's event_length (hit_finder.py:183-230, 388-391)
+            run = engine.DeviceRun.from_host(records, pool, explicit_dt=dt_scalar, clamp_lengths=clamp)
+            out = run.run_to_host(features=False, hits=True, threshold=threshold, rules=engine.make_rules(thr, None),
+                                  left_extension=left_extension, right_extension=right_extension, signed_samples=signed)
+            return out["hits"]
         out = engine.process_host(records, pool, features=False, hits=True, threshold=threshold, thresholds=thr,
                                   left_extension=left_extension, right_extension=right_extension, explicit_dt=dt_scalar,
                                   signed_samples=signed)

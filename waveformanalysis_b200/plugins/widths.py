@@ -98,6 +98,7 @@ class B200WaveformWidthIntegralPlugin(Plugin):
             dt = 1.0 / float(sampling_rate)
         if q_low <= 0 or q_high >= 1 or q_low >= q_high:
             raise ValueError(f"q_low/q_high invalid: q_low={q_low}, q_high={q_high}")
+        signed = False
         if wave_input.spec.is_records:
             records, pool = wave_input.records, wave_input.wave_pool
             if records is None or pool is None:
@@ -109,11 +110,9 @@ class B200WaveformWidthIntegralPlugin(Plugin):
             if len(data) == 0:
                 return np.zeros(0, dtype=WAVEFORM_WIDTH_INTEGRAL_DTYPE)
             records, pool, signed = structured_as_records(data, raw_polarity=True)
-            if signed and data["wave"].size and int(data["wave"].min()) < 0:
-                raise NotImplementedError("negative int16 samples in st_waveforms: use wave_source='records'")
             # st branch: raw float64 arithmetic, 'positive' keeps the sign (waveform_width_integral.py:187-191)
             records = records.copy()
             records["polarity"] = np.where(records["polarity"] == "rawpos", "rawpos", "unknown")
         if len(records) == 0:
             return np.zeros(0, dtype=WAVEFORM_WIDTH_INTEGRAL_DTYPE)
-        return ops.width_integral(records, pool, q_low=q_low, q_high=q_high, dt=float(dt))
+        return ops.width_integral(records, pool, q_low=q_low, q_high=q_high, dt=float(dt), signed_samples=signed)

@@ -486,10 +486,38 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+class PluginContext:
+    """The part of the reference Context a plugin's compute() uses (core/context.py get_config / get_data and the
+    plugin registry), holding host arrays: what ContextExecutionDomain.execute_plugin_compute hands to plugin.compute
+    (core/context_execution.py:140-183) without the cache write to disk."""
+
+    def __init__(self, config, plugins):
+        self.config = config
+        self._results = {}
+        self._plugins = plugins
+
+    def get_config(self, plugin, name):
+        p = plugin.provides
+        if p in self.config and isinstance(self.config[p], dict) and name in self.config[p]:
+            return self.config[p][name]
+        if name in self.config:
+            return self.config[name]
+        return plugin.options[name].default if name in plugin.options else None
+
+    def get_data(self, run_id, name):
+        return self._results.get((run_id, name))
+
+
 def run_e2e(args, engine, torch, barrier, max_over_ranks, sum_over_ranks, rank):
-    """Same pass through the plugin-facing host call: pinned host records + wave_pool in,
-    host feature / hit rows out, every step."""
+    """The same pass end to end through the reference-facing boundary: B200BasicFeaturesPlugin.compute and
+    B200ThresholdHitPlugin.compute on HOST records + wave_pool (pinned), host feature / hit rows out, every step.
+    The first plugin uploads the run once and computes both outputs in one fused pass; the second returns the rows
+    left for it (plugins/_fused.py).  Every step uses a new run id, so every step pays the upload."""
     import numpy as np
+
+    from waveformanalysis_b200 import residency
+    from waveformanalysis_b200.dtypes import RECORDS_DTYPE
+    from waveformanalysis_b200.plugins import B200BasicFeaturesPlugin, B200ThresholdHitPlugin
 
     n = min(args.e2e_records, args.records)
     dev = engine.DeviceRun.synth(n, N_SAMPLES, N_CHANNELS, seed=77 + rank, with_rows=True)
@@ -500,37 +528,44 @@ def run_e2e(args, engine, torch, barrier, max_over_ranks, sum_over_ranks, rank):
     torch.cuda.synchronize()
     del dev
     torch.cuda.empty_cache()
-    from waveformanalysis_b200.dtypes import BASIC_FEATURES_DTYPE, RECORDS_DTYPE
-
     records = rows_pin.numpy().view(RECORDS_DTYPE)
     pool = pool_pin.numpy().view(np.uint16)
-    feat_pin = torch.empty(n * 36, dtype=torch.uint8).pin_memory()
-    out_features = feat_pin.numpy().view(BASIC_FEATURES_DTYPE)
-    first = engine.process_host(records, pool, threshold=THRESHOLD, out_features=out_features)
-    cap = first["n_hits"] + 1024
-    from waveformanalysis_b200.dtypes import THRESHOLD_HIT_DTYPE
+    plugins = {"basic_features": B200BasicFeaturesPlugin(), "hit_threshold": B200ThresholdHitPlugin()}
+    ctx = PluginContext({"wave_source": "records", "hit_threshold": {"threshold": THRESHOLD}}, plugins)
 
-    hits_pin = torch.empty(cap * 60, dtype=torch.uint8).pin_memory()
-    out_hits = hits_pin.numpy().view(THRESHOLD_HIT_DTYPE)
+    def step(k):
+        run_id = f"e2e_{k}"
+        ctx._results[(run_id, "records")] = records
+        ctx._results[(run_id, "wave_pool")] = pool
+        feats = plugins["basic_features"].compute(ctx, run_id)
+        hits = plugins["hit_threshold"].compute(ctx, run_id)
+        residency.release(run_id)
+        ctx._results.clear()
+        return feats, hits
+
+    feats, hits = step(-1)
+    n_hits0 = len(hits)
     steps = max(2, min(args.steps, 5))
-    for _ in range(1):
-        engine.process_host(records, pool, threshold=THRESHOLD, out_features=out_features, out_hits=out_hits)
+    uploads0, rowhits0 = residency.STATS["uploads"], residency.STATS["row_hits"]
     barrier()
     t0 = time.perf_counter()
-    for _ in range(steps):
-        res = engine.process_host(records, pool, threshold=THRESHOLD, out_features=out_features, out_hits=out_hits)
+    for k in range(steps):
+        feats, hits = step(k)
     barrier()
     wall = max_over_ranks(time.perf_counter() - t0)
-    assert res["n_hits"] == first["n_hits"]
+    assert len(hits) == n_hits0 and len(feats) == n
+    assert residency.STATS["uploads"] - uploads0 == steps and residency.STATS["row_hits"] - rowhits0 == steps, residency.STATS
     n_all = sum_over_ranks(float(n))
     return {
         "value": n_all * steps / wall,
         "unit": UNIT,
         "h2d_bytes_per_step": int(n * (2 * N_SAMPLES + 102)),
-        "d2h_bytes_per_step": int(n * 36 + res["n_hits"] * 60),
+        "d2h_bytes_per_step": int(n * 36 + n_hits0 * 60),
         "records_per_gpu": n,
         "steps": steps,
-        "call": "waveformanalysis_b200.engine.process_host (wfb_process_host): pinned host records+wave_pool -> host feature/hit rows",
+        "pool_uploads_per_step": 1,
+        "call": ("B200BasicFeaturesPlugin.compute + B200ThresholdHitPlugin.compute (records source) on pinned host records + wave_pool: "
+                 "one upload, one fused pass, host feature / hit rows out"),
     }
 
 

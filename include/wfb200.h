@@ -10,7 +10,13 @@
  *     them.  Scratch comes from a caller-provided workspace (size from *_workspace_bytes).
  *   - `stream` is a cudaStream_t passed as void*; NULL = legacy default stream.  Calls are
  *     asynchronous with respect to the host unless stated otherwise and are re-entrant
- *     (no global mutable state; the last error string is thread-local).
+ *     (the last error string is thread-local; the only state kept between calls are the
+ *     per-device staging buffers of wfb_process_host / wfb_find_peaks, serialised by a mutex
+ *     and freed by wfb_release_cache).
+ *   - Every entry point that SORTS (wfb_sort_pairs_i64, wfb_build_records*, wfb_group_*,
+ *     wfb_hit_merge, wfb_df_columns) synchronises the stream one to four times: the radix
+ *     sort reads back which key digits differ (16 bytes) and skips the passes over constant
+ *     digits.  They cannot be captured into a CUDA graph.
  *   - Packed row layouts are the reference numpy dtypes byte for byte:
  *       RECORDS_DTYPE         102 B  core/processing/dtypes.py:80-100
  *       BASIC_FEATURES_DTYPE   36 B  core/plugins/builtin/cpu/basic_features.py:29-40

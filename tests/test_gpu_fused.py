@@ -331,3 +331,26 @@ def test_full_size_properties(eng):
     want_f["event_index"] += lo
     assert_rows_match(f_full, want_f, what="full-size slice features", float_exact=FX_BF)
     assert_rows_match(h_full, O.threshold_hits(rec, pool_h, threshold=15.0), what="full-size slice hits", float_exact=FX_HIT)
+
+
+def test_host_pipeline_keeps_error_flags_of_early_chunks(eng, golden):
+    """More chunks than pipeline slots: a record of the FIRST chunk that points outside the pool must still fail the
+    call (the per-chunk flag lives in a workspace that later chunks clear)."""
+    rec, pool = golden["records"].copy(), golden["wave_pool"]
+    rec["wave_offset"][3] = len(pool) + 5000
+    with pytest.raises(Exception, match="outside wave_pool bounds"):
+        eng.process_host(rec, pool, threshold=15.0, chunk_records=64)
+
+
+def test_host_pipeline_accepts_reordered_records(eng, golden):
+    """RecordsView resolves every record on its own (records_view.py:47-56), so records need not be in wave_offset
+    order: the host pipeline then takes the pool range of a chunk over all of its records."""
+    from oracle import np_oracle as O
+
+    rec, pool = golden["records"], golden["wave_pool"]
+    rng = np.random.default_rng(3)
+    perm = rng.permutation(len(rec))
+    shuffled = rec[perm].copy()
+    out = eng.process_host(shuffled, pool, threshold=15.0, chunk_records=100)
+    assert_rows_match(out["features"], O.basic_features(shuffled, pool), what="shuffled features", float_exact=FX_BF)
+    assert_rows_match(out["hits"], O.threshold_hits(shuffled, pool, threshold=15.0), what="shuffled hits", float_exact=FX_HIT)

@@ -1,0 +1,96 @@
+"""GPU: device residency across plugin calls (waveformanalysis_b200/residency.py, plugins/_fused.py).
+
+The first of basic_features / hit_threshold uploads the run once and computes both in one fused pass; the sibling
+then returns the rows left for it; wave_pool_filtered keeps its result in HBM for the plugins that read it.  The rows
+must be the reference's whatever the order of the calls."""
+
+import numpy as np
+import pytest
+
+from conftest import assert_rows_match
+from fakes import Ctx
+
+pytestmark = pytest.mark.gpu
+
+FX_BF = ("height", "amp", "max_abs_diff")
+FX_HIT = ("height", "width", "rise_time", "fall_time")
+
+
+@pytest.fixture()
+def env():
+    from waveformanalysis_b200 import plugins, residency
+
+    residency.release()
+    for k in residency.STATS:
+        residency.STATS[k] = 0
+    yield plugins, residency
+    residency.release()
+
+
+def make_ctx(P, data, config):
+    plugins = {"basic_features": P.B200BasicFeaturesPlugin(), "hit_threshold": P.B200ThresholdHitPlugin(),
+               "wave_pool_filtered": P.B200WavePoolFilteredPlugin(), "waveform_width_integral": P.B200WaveformWidthIntegralPlugin()}
+    return Ctx(config, data, plugins=plugins), plugins
+
+
+@pytest.mark.parametrize("first", ["basic_features", "hit_threshold"])
+def test_one_upload_and_one_fused_pass_for_both_plugins(env, golden, first):
+    P, residency = env
+    cfg = {"wave_source": "records",
+           "basic_features": {"channel_config": {"channels": {"0:1": {"fixed_baseline": 8000.5}, "0:3": {"fixed_baseline": 7990.0}}}},
+           "hit_threshold": {"threshold": 12.0, "left_extension": 5, "right_extension": 0, "channel_config": {"channels": {"0:2": {"threshold": 40.0}}}}}
+    ctx, plugins = make_ctx(P, {"records": golden["records"], "wave_pool": golden["wave_pool"]}, cfg)
+    order = [first, "hit_threshold" if first == "basic_features" else "basic_features"]
+    out = {name: plugins[name].compute(ctx, "run") for name in order}
+    assert residency.STATS["uploads"] == 1 and residency.STATS["row_hits"] == 1, residency.STATS
+    assert_rows_match(out["basic_features"], golden["bf_fixed"], what="bf_fixed", float_exact=FX_BF)
+    assert_rows_match(out["hit_threshold"], golden["hits_chan"], what="hits_chan", float_exact=FX_HIT)
+    # a second request finds the run resident (no upload), the sibling rows were consumed: a fresh fused pass
+    again = plugins["hit_threshold"].compute(ctx, "run")
+    assert residency.STATS["uploads"] == 1
+    assert_rows_match(again, golden["hits_chan"], what="hits_chan again", float_exact=FX_HIT)
+
+
+def test_changed_config_or_inputs_never_reuse_stale_rows(env, golden):
+    P, residency = env
+    data = {"records": golden["records"], "wave_pool": golden["wave_pool"]}
+    ctx, plugins = make_ctx(P, data, {"wave_source": "records", "hit_threshold": {"threshold": 15.0}})
+    plugins["basic_features"].compute(ctx, "run")  # leaves hit rows for threshold 15
+    ctx.config["hit_threshold"] = {"threshold": 12.0, "left_extension": 5, "right_extension": 0,
+                                   "channel_config": {"channels": {"0:2": {"threshold": 40.0}}}}
+    assert_rows_match(plugins["hit_threshold"].compute(ctx, "run"), golden["hits_chan"], what="other config", float_exact=FX_HIT)
+    # another pool under the same run id and name: the fingerprint differs, the run is uploaded again
+    pool2 = golden["wave_pool"].copy()
+    pool2[::3] = pool2[::3] // 2
+    from oracle import np_oracle as O
+
+    ctx2, plugins2 = make_ctx(P, {"records": golden["records"], "wave_pool": pool2}, {"wave_source": "records", "hit_threshold": {"threshold": 15.0}})
+    got = plugins2["hit_threshold"].compute(ctx2, "run")
+    assert_rows_match(got, O.threshold_hits(golden["records"], pool2, threshold=15.0), what="changed pool", float_exact=FX_HIT)
+    assert residency.STATS["uploads"] == 2
+
+
+def test_filtered_pool_stays_resident(env, golden):
+    P, residency = env
+    rec, pool = golden["filt_records"], golden["filt_pool"]
+    ctx, plugins = make_ctx(P, {"records": rec, "wave_pool": pool}, {"wave_source": "records", "use_filtered": True,
+                                                                   "hit_threshold": {"threshold": 15.0}})
+    sg = plugins["wave_pool_filtered"].compute(ctx, "run")
+    assert np.allclose(sg, golden["filt_sg"], rtol=1e-5, atol=1e-3)
+    ctx._set_data("run", "wave_pool_filtered", sg)
+    uploads = residency.STATS["uploads"]
+    assert_rows_match(plugins["basic_features"].compute(ctx, "run"), golden["filt_bf"], what="filt_bf")
+    assert_rows_match(plugins["hit_threshold"].compute(ctx, "run"), golden["filt_hits"], what="filt_hits")
+    assert residency.STATS["uploads"] == uploads, "the filtered pool was uploaded although it was produced on the device"
+    assert residency.STATS["row_hits"] == 1
+
+
+def test_without_a_sibling_only_the_own_rows_are_computed(env, golden, monkeypatch):
+    P, residency = env
+    ctx = Ctx({"wave_source": "records"}, {"records": golden["records"], "wave_pool": golden["wave_pool"]})  # no plugin registry
+    assert_rows_match(P.B200BasicFeaturesPlugin().compute(ctx, "run"), golden["bf_default"], what="bf", float_exact=FX_BF)
+    assert residency.STATS["row_hits"] == 0 and not residency._ROWS
+    monkeypatch.setenv("WFB_FUSE_SIBLINGS", "0")
+    ctx2, plugins = make_ctx(P, {"records": golden["records"], "wave_pool": golden["wave_pool"]}, {"wave_source": "records", "threshold": 15.0})
+    assert_rows_match(plugins["hit_threshold"].compute(ctx2, "run"), golden["hits_thr15"], what="hits", float_exact=FX_HIT)
+    assert not residency._ROWS

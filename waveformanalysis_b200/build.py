@@ -43,10 +43,29 @@ def _deps_mtime() -> float:
     return max(os.path.getmtime(p) for p in paths)
 
 
+STAMP = os.path.join(OBJ_DIR, "build_stamp.txt")
+
+
+def _stamp(nvcc: str) -> str:
+    """What the objects were built with: compiler version + flags.  A change rebuilds everything."""
+    try:
+        ver = subprocess.run([nvcc, "--version"], capture_output=True, text=True).stdout.strip().splitlines()[-1]
+    except OSError:
+        ver = "unknown"
+    return ver + "\n" + " ".join(NVCC_FLAGS) + "\n"
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= _deps_mtime():
+    try:
+        nvcc = _nvcc()
+    except RuntimeError:
+        if os.path.exists(OUT):  # a box without the toolkit (the prebuilt library travelled with the snapshot)
+            return OUT
+        raise
+    stamp = _stamp(nvcc)
+    same_toolchain = os.path.exists(STAMP) and open(STAMP).read() == stamp
+    if not force and same_toolchain and os.path.exists(OUT) and os.path.getmtime(OUT) >= _deps_mtime():
         return OUT
-    nvcc = _nvcc()
     os.makedirs(OBJ_DIR, exist_ok=True)
     extra = ["-Xptxas", "-v"] if verbose else []
 
@@ -66,6 +85,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+    with open(STAMP, "w") as f:
+        f.write(stamp)
     return OUT
 
 

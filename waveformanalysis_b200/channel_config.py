@@ -93,12 +93,14 @@ def unique_channels(boards: np.ndarray, channels: np.ndarray) -> list[tuple[int,
     keys = np.asarray(boards, dtype=np.int64) * 65536 + (np.asarray(channels, dtype=np.int64) & 0xFFFF)
     out = []
     for k in np.unique(keys).tolist():
-        out.append((int(k >> 16), int(np.int16(k & 0xFFFF))))
+        out.append((int(k >> 16), ((int(k) & 0xFFFF) ^ 0x8000) - 0x8000))  # sign-extend the 16-bit channel
     return sorted(out)
 
 
 def per_channel_option(channel_config: Any, run_id: str, boards: np.ndarray, channels: np.ndarray, name: str, base_value: Any) -> dict:
     """{(board, channel): effective value of option ``name``} for every channel present."""
+    if not channel_config:  # no overrides configured: every channel takes the base value (and nothing needs the channel list)
+        return {}
     out = {}
     for b, c in unique_channels(boards, channels):
         out[(b, c)] = resolve_channel_values(channel_config, run_id, b, c, {name: base_value}).get(name, base_value)

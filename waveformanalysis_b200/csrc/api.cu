@@ -81,6 +81,12 @@ __global__ void records_unpack_kernel(const uint16_t* __restrict__ rows, long lo
     meta[i] = m;
 }
 
+// keeps the first non-zero error flag of the chunks of one wfb_process_host call (the per-call flag in the workspace
+// is cleared by the next chunk that uses the slot)
+__global__ void err_accumulate_kernel(const int* __restrict__ chunk_flag, int* __restrict__ run_flag) {
+    if (*chunk_flag != 0 && *run_flag == 0) *run_flag = *chunk_flag;
+}
+
 __global__ void meta_set_clamp_kernel(wfb_rec_meta* __restrict__ meta, long long n, const int* __restrict__ clamp) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -247,10 +253,13 @@ extern "C" int wfb_process_host(const void* records_host, int64_t n, const void*
     chunk_records = std::min<int64_t>(chunk_records, n);
 
     // padded matrix width = max event_length over the whole run (hit_finder.py:364)
+    // (also without hits: a per-chunk maximum would cost a device round trip per chunk and make the kernel variant
+    // depend on the chunk)
     int lmax = params->lmax;
-    if (do_hits && lmax <= 0) {
+    if (lmax <= 0) {
         for (int64_t i = 0; i < n; ++i) lmax = std::max(lmax, rec_i32(rows + i * kRecordsRowBytes, 90));
     }
+    bool scan_all = false;
 
     int device = 0;
     WFB_CUDA(cudaGetDevice(&device));
@@ -296,9 +305,11 @@ extern "C" int wfb_process_host(const void* records_host, int64_t n, const void*
         }                                               \
     } while (0)
 
+again:
     if (do_hits) PH_CHECK(d_hits.ensure(std::max<size_t>((size_t)hit_cap * kHitRowBytes, 64)));
-    PH_CHECK(d_tot.ensure(64));  // ping-pong running totals
+    PH_CHECK(d_tot.ensure(64));  // ping-pong running totals (bytes 0..15) and the run-wide error flag (byte 32)
     PH_CUDA(cudaMemsetAsync(d_tot.p, 0, 64, s_comp));
+    int* const run_err = reinterpret_cast<int*>(static_cast<uint8_t*>(d_tot.p) + 32);
     wfb_fh_params p = *params;
     p.lmax = lmax;
     p.rules_dev = nullptr;
@@ -333,14 +344,26 @@ extern "C" int wfb_process_host(const void* records_host, int64_t n, const void*
     for (int64_t r0 = 0; r0 < n; r0 += chunk_records, ++chunk_idx) {
         const int64_t r1 = std::min<int64_t>(n, r0 + chunk_records), m = r1 - r0;
         Slot& s = slots[chunk_idx % kSlots];
-        // pool range of the chunk: wave_offsets ascend with the record index
+        // pool range of the chunk.  Records built by the records plugins have wave_offsets that ascend with the record
+        // index: the first and the last non-empty record bound the range.  If the device finds a record outside it
+        // (filtered / reordered records), the call runs again with the range taken over every record.
         long long lo = -1, hi = -1;
-        for (int64_t i = r0; i < r1; ++i) {
-            if (rec_i32(rows + i * kRecordsRowBytes, 90) > 0) { lo = rec_i64(rows + i * kRecordsRowBytes, 82); break; }
-        }
-        for (int64_t i = r1 - 1; i >= r0; --i) {
-            int len = rec_i32(rows + i * kRecordsRowBytes, 90);
-            if (len > 0) { hi = rec_i64(rows + i * kRecordsRowBytes, 82) + len; break; }
+        if (scan_all) {
+            for (int64_t i = r0; i < r1; ++i) {
+                const int len = rec_i32(rows + i * kRecordsRowBytes, 90);
+                if (len <= 0) continue;
+                const long long o = rec_i64(rows + i * kRecordsRowBytes, 82);
+                lo = (lo < 0) ? o : std::min(lo, o);
+                hi = std::max(hi, o + len);
+            }
+        } else {
+            for (int64_t i = r0; i < r1; ++i) {
+                if (rec_i32(rows + i * kRecordsRowBytes, 90) > 0) { lo = rec_i64(rows + i * kRecordsRowBytes, 82); break; }
+            }
+            for (int64_t i = r1 - 1; i >= r0; --i) {
+                int len = rec_i32(rows + i * kRecordsRowBytes, 90);
+                if (len > 0) { hi = rec_i64(rows + i * kRecordsRowBytes, 82) + len; break; }
+            }
         }
         if (lo < 0) lo = hi = 0;
         if (lo > hi || hi > pool_len || lo < 0) {
@@ -377,6 +400,8 @@ extern "C" int wfb_process_host(const void* records_host, int64_t n, const void*
         PH_CHECK(wfb_features_hits(s.pool.p, hi - lo_al, static_cast<const wfb_rec_meta*>(s.meta.p), m, &p, s.feat.p,
                                    d_hits.p, hit_cap, (do_hits && hit_counts_host) ? static_cast<int32_t*>(s.counts.p) : nullptr,
                                    tot + (chunk_idx & 1), tot + ((chunk_idx + 1) & 1), s.ws.p, s.ws.cap, s_comp));
+        err_accumulate_kernel<<<1, 1, 0, s_comp>>>(reinterpret_cast<const int*>(static_cast<uint8_t*>(s.ws.p) + 4), run_err);
+        PH_CUDA(cudaGetLastError());
         PH_CUDA(cudaMemcpyAsync(&hp->mailbox[chunk_idx % kSlots], tot + ((chunk_idx + 1) & 1), 8, cudaMemcpyDeviceToHost, s_comp));
         PH_CUDA(cudaEventRecord(s.computed, s_comp));
         PH_CUDA(cudaStreamWaitEvent(s_out, s.computed, 0));
@@ -387,10 +412,24 @@ extern "C" int wfb_process_host(const void* records_host, int64_t n, const void*
             PH_CUDA(cudaMemcpyAsync(hit_counts_host + r0, s.counts.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s_out));
         PH_CUDA(cudaEventRecord(s.drained, s_out));
     }
-    PH_CUDA(cudaStreamSynchronize(s_comp));
-    for (int k = 0; k < kSlots && k < chunk_idx; ++k) {
-        int err = wfb_features_hits_check(slots[k].ws.p, s_comp);
-        if (err != WFB_OK) { cleanup(); return err; }
+    {  // error flag of ANY chunk of the call (the workspaces are reused every kSlots chunks)
+        int h_err = 0;
+        PH_CUDA(cudaMemcpyAsync(&h_err, run_err, 4, cudaMemcpyDeviceToHost, s_comp));
+        PH_CUDA(cudaStreamSynchronize(s_comp));
+        if (h_err == 1) {
+            cleanup();
+            if (!scan_all) {  // records not in wave_offset order: take every record's range into account and run again
+                scan_all = true;
+                goto again;
+            }
+            set_error("records reference samples outside wave_pool bounds");
+            return WFB_ERR_LAYOUT;
+        }
+        if (h_err == 2) {
+            cleanup();
+            set_error("lmax is smaller than the longest record passed");
+            return WFB_ERR_INVALID;
+        }
     }
     if (do_hits) {
         *n_hits = hp->mailbox[(chunk_idx - 1) % kSlots];

@@ -208,7 +208,10 @@ def process_host(
     lmax: int | None = None,
 ) -> dict:
     """Fused pass over host buffers through ``wfb_process_host``.  Returns a dict with
-    ``features`` (BASIC_FEATURES_DTYPE), ``hits`` (THRESHOLD_HIT_DTYPE), ``counts`` (int32)."""
+    ``features`` (BASIC_FEATURES_DTYPE), ``hits`` (THRESHOLD_HIT_DTYPE), ``counts`` (int32).
+
+    Records are expected in ``wave_offset`` order (what the records plugins produce); any other order works too, the
+    call then runs a second time with the pool range of every chunk taken over all of its records."""
     lib = _lib.load()
     _torch()
     rec = packed_records(records, explicit_dt)
@@ -217,7 +220,7 @@ def process_host(
     flags = (_lib.DO_FEATURES if features else 0) | (_lib.DO_HITS if hits else 0)
     rules = make_rules(thresholds, fixed_baselines)
     if lmax is None:  # a shard of a run passes the run-wide maximum (hit_finder.py:364)
-        lmax = int(rec["event_length"].max()) if (hits and n) else 0
+        lmax = int(rec["event_length"].max()) if n else 0
     p = make_params(flags=flags, pool_is_f32=is_f32, height_range=height_range, area_range=area_range,
                     threshold=threshold, left_extension=left_extension, right_extension=right_extension,
                     lmax=max(lmax, 0), n_rules=len(rules), signed_samples=signed_samples, row_base=row_base)
@@ -288,6 +291,19 @@ class DeviceRun:
         return cls(meta, d_pool, n, is_f32, max(lmax, 0), records_rows=rows, pool_base=pool_base, row_base=row_base)
 
     @classmethod
+    def from_device_pool(cls, records: np.ndarray, d_pool, pool_is_f32: int = 0) -> "DeviceRun":
+        """records rows from the host (small) + a sample pool that already lives on the device (it was produced there)."""
+        torch = _torch()
+        lib = _lib.load()
+        rec = packed_records(records, None)
+        n = len(rec)
+        rows = upload(rec)
+        meta = torch.empty(max(n, 1) * 48, dtype=torch.uint8, device="cuda")
+        _lib.check(lib.wfb_records_unpack(_ptr(rows), n, _ptr(meta), _stream()), "wfb_records_unpack")
+        lmax = int(rec["event_length"].max()) if n else 0
+        return cls(meta, d_pool, n, int(pool_is_f32), max(lmax, 0), records_rows=rows)
+
+    @classmethod
     def synth(cls, n: int, n_samples: int, n_channels: int, *, dt_ns: int = 2, seed: int = 1234, with_rows: bool = False) -> "DeviceRun":
         torch = _torch()
         lib = _lib.load()
@@ -339,7 +355,7 @@ class DeviceRun:
         feat = out.get("features")
         if features and feat is None:
             feat = torch.empty(max(n, 1) * 36, dtype=torch.uint8, device="cuda")
-        cap = int(hit_cap) if hit_cap is not None else max(1024, 4 * n)
+        cap = int(hit_cap) if hit_cap is not None else max(1024, 8 * n)
         hit_rows = out.get("hits")
         if hits and hit_rows is None:
             hit_rows = torch.empty(max(cap, 1) * 60, dtype=torch.uint8, device="cuda")

@@ -83,7 +83,7 @@ def build_records_ragged(timestamps_ps, boards, channels, sample_blocks, *, dt_n
 
 
 def build_records(timestamps_ps, boards, channels, samples, *, dt_ns: int, baseline_window=(0, 40),
-                  baselines=None, epoch_ns: int | None = None):
+                  baselines=None, epoch_ns: int | None = None, return_device: bool = False):
     """raw rows (per-channel file order) -> (records[RECORDS_DTYPE], wave_pool[uint16]) in the
     reference's global order (records_builder.py:115-120, 212-302, 341-426)."""
     lib = _lib.load()
@@ -106,6 +106,8 @@ def build_records(timestamps_ps, boards, channels, samples, *, dt_ns: int, basel
                                      int(baseline_window[1]), int(dt_ns), int(epoch_ns or 0), _ptr(rows), _ptr(pool), C.c_void_p(0),
                                      _ptr(ws), ws.numel(), _stream()), "wfb_build_records")
     rec = rows[: n * 102].cpu().numpy().view(RECORDS_DTYPE)
+    if return_device:
+        return rec, pool.cpu().numpy().view(np.uint16), pool
     return rec, pool.cpu().numpy().view(np.uint16)
 
 
@@ -170,7 +172,8 @@ def sos_zi(sos: np.ndarray) -> np.ndarray:
     return zi
 
 
-def filter_pool(records: np.ndarray, pool: np.ndarray, *, configs: dict, default: dict, run: DeviceRun | None = None) -> np.ndarray:
+def filter_pool(records: np.ndarray, pool: np.ndarray, *, configs: dict, default: dict, run: DeviceRun | None = None,
+                return_device: bool = False):
     """uint16 wave_pool -> float32 wave_pool_filtered (records.py:368-438).
 
     ``default`` / ``configs[(board, channel)]``: {"filter_type": "SG", "sg_window_size", "sg_poly_order"} or
@@ -183,13 +186,13 @@ def filter_pool(records: np.ndarray, pool: np.ndarray, *, configs: dict, default
     rec = packed_records(records, explicit_dt=1)
     n = len(rec)
     if n == 0 or len(pool_h) == 0:
-        return out
+        return (out, None) if return_device else out
     # distinct configs -> wfb_filter_cfg[]
     keys = rec["board"].astype(np.int64) * 65536 + (rec["channel"].astype(np.int64) & 0xFFFF)
     uniq, inv = np.unique(keys, return_inverse=True)
     cfg_list = []
     for k in uniq.tolist():
-        b, c = int(k >> 16), int(np.int16(k & 0xFFFF))
+        b, c = int(k >> 16), ((int(k) & 0xFFFF) ^ 0x8000) - 0x8000
         cfg_list.append(configs.get((b, c), default))
     cfgs = (_lib.FilterCfg * len(cfg_list))()
     tables: list[np.ndarray] = []
@@ -230,8 +233,7 @@ def filter_pool(records: np.ndarray, pool: np.ndarray, *, configs: dict, default
     d_idx = _dev(inv.astype(np.int32))
     d_tab = _dev(np.concatenate(tables) if tables else np.zeros(1))
     d_toff = _dev(tab_off)
-    own = run is None
-    if own:
+    if run is None:
         run = DeviceRun.from_host(rec, pool_h)
     d_out = torch.empty(len(pool_h) + 16, dtype=torch.float32, device="cuda")[: len(pool_h)]
     lmax = max(int(lens.max()), 1)
@@ -240,7 +242,10 @@ def filter_pool(records: np.ndarray, pool: np.ndarray, *, configs: dict, default
     _lib.check(lib.wfb_filter_pool(_ptr(run.pool), is_f32, len(pool_h), _ptr(run.meta), n, _ptr(d_cfg), len(cfg_list), _ptr(d_idx),
                                    _ptr(d_tab), _ptr(d_toff), _ptr(d_out), 0, _ptr(ws), 0 if ws is None else ws.numel(), lmax,
                                    _stream()), "wfb_filter_pool")
-    return d_out.cpu().numpy()
+    host = d_out.cpu().numpy()
+    if return_device:  # the filtered pool stays in HBM for the next plugin (same records metadata, float32 samples)
+        return host, DeviceRun(run.meta, d_out, n, 1, run.lmax, records_rows=run.records_rows, pool_base=run.pool_base, row_base=run.row_base)
+    return host
 
 
 # --------------------------------------------------------------------------------------------
@@ -564,7 +569,7 @@ def build_records_from_v1725(blobs, names, dt_ns: int):
 # --------------------------------------------------------------------------------------------
 def _find_peaks(records: np.ndarray, pool: np.ndarray, kind: int, *, use_derivative=True, height=30.0, distance=2, prominence=0.7,
                 width=4, threshold=None, height_method="minmax", height_window_extension=4, cumsum_diff=False,
-                level_f32: bool = False) -> np.ndarray:
+                level_f32: bool = False, run: DeviceRun | None = None) -> np.ndarray:
     from .dtypes import HIT_DTYPE
 
     lib = _lib.load()
@@ -579,7 +584,8 @@ def _find_peaks(records: np.ndarray, pool: np.ndarray, kind: int, *, use_derivat
     lmax = int(records["event_length"].max())
     if lmax <= 0:
         return np.zeros(0, dtype=HIT_DTYPE)
-    run = DeviceRun.from_host(records, pool)
+    if run is None:
+        run = DeviceRun.from_host(records, pool)
     p = _lib.PeakParams(wave_kind=kind, use_derivative=int(bool(use_derivative)), height=float(height), prominence=float(prominence),
                         width=float(width), threshold=float(threshold) if threshold is not None else 0.0,
                         has_threshold=int(threshold is not None), distance=int(distance if distance is not None else 1),
@@ -599,11 +605,11 @@ def _find_peaks(records: np.ndarray, pool: np.ndarray, kind: int, *, use_derivat
         cap = nt
 
 
-def find_peaks_records(records: np.ndarray, pool: np.ndarray, **opts) -> np.ndarray:
+def find_peaks_records(records: np.ndarray, pool: np.ndarray, run: DeviceRun | None = None, **opts) -> np.ndarray:
     """`hit` rows from records + wave_pool / wave_pool_filtered (peak_finding.py:392-444: waveform =
-    -RecordsView.signals() in float64, positive-going pulses)."""
+    -RecordsView.signals() in float64, positive-going pulses).  ``run``: the device-resident copy, if there is one."""
     pool_h, is_f32 = check_pool(pool)
-    return _find_peaks(packed_records(records, None), pool_h, _lib.WAVE_REC_F32 if is_f32 else _lib.WAVE_REC_U16, **opts)
+    return _find_peaks(packed_records(records, None), pool_h, _lib.WAVE_REC_F32 if is_f32 else _lib.WAVE_REC_U16, run=run, **opts)
 
 
 def find_peaks_waveforms(data: np.ndarray, *, explicit_dt=None, **opts) -> np.ndarray:

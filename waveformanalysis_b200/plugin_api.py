@@ -115,11 +115,12 @@ def check_dt_array(data, explicit_dt, plugin_name: str, data_name: str) -> int |
 
     names = data.dtype.names or ()
     if "dt" in names:
-        dt = np.asarray(data["dt"], dtype=np.int64)
-        if np.any(dt <= 0):
-            raise ValueError(f"[{plugin_name}] {data_name}.dt must be positive for every row")
-        if np.any(dt > np.iinfo(np.int32).max):
-            raise ValueError(f"[{plugin_name}] {data_name}.dt exceeds int32 range")
+        if len(data):
+            dt = np.ascontiguousarray(data["dt"])  # one pass over the strided field
+            if int(dt.min()) <= 0:
+                raise ValueError(f"[{plugin_name}] {data_name}.dt must be positive for every row")
+            if int(dt.max()) > np.iinfo(np.int32).max:
+                raise ValueError(f"[{plugin_name}] {data_name}.dt exceeds int32 range")
         return None
     if explicit_dt is None:
         raise ValueError(f"[{plugin_name}] Input '{data_name}' is missing required field 'dt'; "

@@ -1,0 +1,124 @@
+"""One fused device pass for ``basic_features`` and ``hit_threshold`` on the records source.
+
+Both plugins read the same ``records`` + ``wave_pool`` (or ``wave_pool_filtered``) and both come out of the same
+kernel (``wfb_features_hits``).  The reference computes them one after the other from one in-memory bundle
+(core/plugins/builtin/cpu/records.py:441-464); here the FIRST of the two that a Context runs
+
+  * makes the run resident in HBM (``residency.device_run``: one upload per run and pool, shared with
+    ``wave_pool_filtered``, ``waveform_width_integral`` ...),
+  * resolves the sibling's configuration through the same Context, runs the fused pass for both, and
+  * leaves the sibling's rows in ``residency`` under a signature of (input fingerprint, configuration).
+
+When the Context then runs the sibling, it finds its rows and returns them without touching the device.  If the
+sibling is not registered, not a B200 plugin, reads another source, or its configuration does not resolve, the pass
+computes the caller's rows only - the results never depend on whether the fusion took place.
+``WFB_FUSE_SIBLINGS=0`` switches the sibling computation off.
+"""
+
+from __future__ import annotations
+
+import os
+from typing import Any
+
+import numpy as np
+
+from .. import engine, residency
+from ..channel_config import per_channel_option
+from ..dtypes import BASIC_FEATURES_DTYPE, RECORDS_DTYPE, THRESHOLD_HIT_DTYPE
+from ..plugin_api import check_dt_array, resolve_dt_config
+from ..wave_source import resolve_wave_input_spec
+
+
+def _columns(records: np.ndarray):
+    names = records.dtype.names
+    boards = records["board"] if "board" in names else np.zeros(len(records), np.int16)
+    channels = records["channel"] if "channel" in names else np.zeros(len(records), np.int16)
+    return boards, channels
+
+
+def feature_params(plugin: Any, context: Any, run_id: str, records: np.ndarray) -> dict:
+    """Kernel parameters of basic_features from the Context (basic_features.py:108-142)."""
+    boards, channels = _columns(records)
+    fixed = per_channel_option(context.get_config(plugin, "channel_config"), run_id, boards, channels, "fixed_baseline", None)
+    return dict(height_range=tuple(context.get_config(plugin, "height_range")), area_range=tuple(context.get_config(plugin, "area_range")),
+                fixed_baselines={k: float(v) for k, v in fixed.items() if v is not None})
+
+
+def hit_params(plugin: Any, context: Any, run_id: str, records: np.ndarray) -> dict:
+    """Kernel parameters of hit_threshold from the Context (hit_finder.py:122-150, 287-325)."""
+    threshold = float(context.get_config(plugin, "threshold"))
+    explicit_dt = resolve_dt_config(context, plugin, deprecated_keys=("sampling_interval_ns", "dt_ns"))
+    dt_scalar = check_dt_array(records, explicit_dt, plugin.provides, "records")
+    boards, channels = _columns(records)
+    thr = per_channel_option(context.get_config(plugin, "channel_config"), run_id, boards, channels, "threshold", threshold)
+    return dict(threshold=threshold, thresholds={k: float(v) for k, v in thr.items() if float(v) != threshold},
+                left_extension=max(0, int(context.get_config(plugin, "left_extension"))),
+                right_extension=max(0, int(context.get_config(plugin, "right_extension"))), explicit_dt=dt_scalar)
+
+
+def _signature(fp: tuple, kind: str, params: dict) -> tuple:
+    content = tuple(x[1:] for x in fp)  # sizes and probe hashes: memmap views of the same cache file have other addresses
+    return (content, kind, repr(sorted((k, repr(v) if not isinstance(v, dict) else repr(sorted(v.items()))) for k, v in params.items())))
+
+
+def _sibling(context: Any, name: str, cls_name: str, spec) -> Any:
+    if os.environ.get("WFB_FUSE_SIBLINGS", "1") == "0":
+        return None
+    plugins = getattr(context, "_plugins", None)
+    if not isinstance(plugins, dict):
+        return None
+    sib = plugins.get(name)
+    if sib is None or type(sib).__name__ != cls_name:
+        return None
+    try:
+        other = resolve_wave_input_spec(context, sib)
+    except Exception:
+        return None
+    if not other.is_records or other.wave_pool_name != spec.wave_pool_name:
+        return None
+    return sib
+
+
+def records_pass(plugin: Any, context: Any, run_id: str, spec, records: np.ndarray, pool: np.ndarray, want: str) -> np.ndarray:
+    """``want`` = "features" (called by basic_features) or "hits" (called by hit_threshold), records source."""
+    assert want in ("features", "hits")
+    own = feature_params(plugin, context, run_id, records) if want == "features" else hit_params(plugin, context, run_id, records)
+    pool_name = spec.wave_pool_name or "wave_pool"
+    empty = np.zeros(0, dtype=BASIC_FEATURES_DTYPE if want == "features" else THRESHOLD_HIT_DTYPE)
+    if len(records) == 0:
+        return empty
+    fusable = records.dtype == RECORDS_DTYPE and residency.fits_device(int(pool.nbytes))
+    if not fusable:  # partial record layouts / pools larger than the device: the chunked host pipeline, caller's rows only
+        if want == "features":
+            return engine.process_host(records, pool, features=True, hits=False, explicit_dt=1, **own)["features"]
+        kw = dict(own)
+        return engine.process_host(records, pool, features=False, hits=True, **kw)["hits"]
+    fp = residency.fingerprint(records, pool)
+    own_name, sib_name = ("basic_features", "hit_threshold") if want == "features" else ("hit_threshold", "basic_features")
+    ready = residency.take_rows(run_id, own_name, _signature(fp, want, own))
+    if ready is not None:
+        return ready
+    sib = _sibling(context, sib_name, "B200ThresholdHitPlugin" if want == "features" else "B200BasicFeaturesPlugin", spec)
+    other = None
+    if sib is not None:
+        try:
+            other = hit_params(sib, context, run_id, records) if want == "features" else feature_params(sib, context, run_id, records)
+        except Exception:
+            other = None  # the sibling will raise its own error when (if) the Context runs it
+    fpar = own if want == "features" else other
+    hpar = own if want == "hits" else other
+    run = residency.device_run(run_id, records, pool, pool_name)
+    kw: dict = dict(features=fpar is not None, hits=hpar is not None)
+    thresholds, fixed = {}, {}
+    if fpar is not None:
+        kw.update(height_range=fpar["height_range"], area_range=fpar["area_range"])
+        fixed = fpar["fixed_baselines"]
+    if hpar is not None:
+        kw.update(threshold=hpar["threshold"], left_extension=hpar["left_extension"], right_extension=hpar["right_extension"])
+        thresholds = hpar["thresholds"]
+    rules = engine.make_rules(thresholds, fixed)
+    out = run.run_to_host(rules=rules if len(rules) else None, **kw)
+    if other is not None:
+        sib_rows = out["hits"] if want == "features" else out["features"]
+        residency.put_rows(run_id, sib_name, _signature(fp, "hits" if want == "features" else "features", other), sib_rows)
+    return out["features"] if want == "features" else out["hits"]

@@ -7,6 +7,7 @@ from typing import Any
 import numpy as np
 
 from .. import engine
+from . import _fused
 from ..aos import structured_as_records
 from ..channel_config import per_channel_option
 from ..dtypes import BASIC_FEATURES_DTYPE
@@ -38,24 +39,22 @@ class B200BasicFeaturesPlugin(Plugin):
         return list(resolve_wave_input_spec(context, self).depends_on)
 
     def compute(self, context: Any, run_id: str, **kwargs) -> np.ndarray:
-        channel_config_cfg = context.get_config(self, "channel_config")
-        height_range = context.get_config(self, "height_range")
-        area_range = context.get_config(self, "area_range")
         wave_input = load_wave_input(context, self, run_id, needs_wave_samples=True)
-        signed = False
         if wave_input.spec.is_records:
             records, pool = wave_input.records, wave_input.wave_pool
             if records is None or pool is None:
                 raise ValueError("basic_features failed to load records_view for records source")
-        else:
-            data = wave_input.waveform_data
-            if data is None:
-                raise ValueError(f"basic_features failed to load {wave_input.spec.data_name}")
-            if len(data) == 0:
-                return np.zeros(0, dtype=BASIC_FEATURES_DTYPE)
-            records, pool, signed = structured_as_records(data, raw_polarity=True)
-        if len(records) == 0:
+            # records source: one fused, device-resident pass shared with hit_threshold (plugins/_fused.py)
+            return _fused.records_pass(self, context, run_id, wave_input.spec, records, pool, "features")
+        channel_config_cfg = context.get_config(self, "channel_config")
+        height_range = context.get_config(self, "height_range")
+        area_range = context.get_config(self, "area_range")
+        data = wave_input.waveform_data
+        if data is None:
+            raise ValueError(f"basic_features failed to load {wave_input.spec.data_name}")
+        if len(data) == 0:
             return np.zeros(0, dtype=BASIC_FEATURES_DTYPE)
+        records, pool, signed = structured_as_records(data, raw_polarity=True)
         names = records.dtype.names
         boards = records["board"] if "board" in names else np.zeros(len(records), np.int16)
         channels = records["channel"] if "channel" in names else np.zeros(len(records), np.int16)

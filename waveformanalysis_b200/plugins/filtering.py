@@ -100,4 +100,16 @@ class B200WavePoolFilteredPlugin(Plugin):
         ln = records["event_length"].astype(np.int64)
         if np.any((ln > 0) & ((off < 0) | (off + ln > len(wave_pool)))):
             raise ValueError("wave_pool_filtered found out-of-bounds wave slice")
-        return ops.filter_pool(records, wave_pool, configs=configs, default=resolve_filter_config(base_values))
+        from .. import residency
+        from ..dtypes import RECORDS_DTYPE
+
+        if records.dtype != RECORDS_DTYPE or not residency.fits_device(int(wave_pool.nbytes) * 3):
+            return ops.filter_pool(records, wave_pool, configs=configs, default=resolve_filter_config(base_values))
+        # the raw pool is (or becomes) resident; the filtered pool stays in HBM under the host array handed back, so a
+        # hit / feature plugin with use_filtered finds it there (the reference shares its bundle: records.py:441-464)
+        run = residency.device_run(run_id, records, wave_pool, "wave_pool")
+        host, frun = ops.filter_pool(records, wave_pool, configs=configs, default=resolve_filter_config(base_values), run=run,
+                                     return_device=True)
+        if frun is not None:
+            residency.adopt_run(run_id, records, host, "wave_pool_filtered", frun)
+        return host

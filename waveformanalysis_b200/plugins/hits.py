@@ -7,6 +7,7 @@ from typing import Any
 import numpy as np
 
 from .. import engine
+from . import _fused
 from ..aos import structured_as_records
 from ..channel_config import per_channel_option
 from ..dtypes import THRESHOLD_HIT_DTYPE
@@ -51,15 +52,15 @@ class B200ThresholdHitPlugin(Plugin):
                 raise ValueError("hit_threshold failed to load records_view for records source")
             if len(records) == 0:
                 return np.zeros(0, dtype=THRESHOLD_HIT_DTYPE)
-            dt_scalar = check_dt_array(records, explicit_dt, self.provides, "records")
-        else:
-            data = wave_input.waveform_data
-            if data is None:
-                raise ValueError(f"hit_threshold failed to load {wave_input.spec.data_name}")
-            if len(data) == 0:
-                return np.zeros(0, dtype=THRESHOLD_HIT_DTYPE)
-            dt_scalar = check_dt_array(data, explicit_dt, self.provides, wave_input.spec.data_name)
-            records, pool, signed, clamp = structured_as_records(data, explicit_dt=dt_scalar, return_clamp=True)
+            # records source: one fused, device-resident pass shared with basic_features (plugins/_fused.py)
+            return _fused.records_pass(self, context, run_id, wave_input.spec, records, pool, "hits")
+        data = wave_input.waveform_data
+        if data is None:
+            raise ValueError(f"hit_threshold failed to load {wave_input.spec.data_name}")
+        if len(data) == 0:
+            return np.zeros(0, dtype=THRESHOLD_HIT_DTYPE)
+        dt_scalar = check_dt_array(data, explicit_dt, self.provides, wave_input.spec.data_name)
+        records, pool, signed, clamp = structured_as_records(data, explicit_dt=dt_scalar, return_clamp=True)
         names = records.dtype.names
         boards = records["board"] if "board" in names else np.zeros(len(records), np.int16)
         channels = records["channel"] if "channel" in names else np.zeros(len(records), np.int16)
@@ -136,7 +137,13 @@ class B200HitFinderPlugin(Plugin):
                 records = rfn.append_fields(records, "dt", np.full(len(records), int(explicit_dt), np.int32), usemask=False)
             if np.any(records["dt"] <= 0):
                 raise ValueError("[hit] dt must be > 0")
-            return ops.find_peaks_records(records, pool, **opts)
+            from .. import residency
+            from ..dtypes import RECORDS_DTYPE
+
+            run = None
+            if records.dtype == RECORDS_DTYPE and residency.fits_device(int(pool.nbytes)):
+                run = residency.device_run(run_id, records, pool, wave_input.spec.wave_pool_name or "wave_pool")
+            return ops.find_peaks_records(records, pool, run=run, **opts)
         data = wave_input.waveform_data
         if data is None:
             raise ValueError("hit failed to load waveform input")

@@ -122,6 +122,7 @@ def build_bundle(context: Any, run_id: str, plugin: Plugin):
         boards.append(arr[:, c_board].astype(np.int16))
         chans.append(arr[:, c_chan].astype(np.int16))
         samples.append(arr[:, s0:].astype(np.int16))
+    d_pool = None
     if not samples:
         bundle = (np.zeros(0, dtype=RECORDS_DTYPE), np.zeros(0, dtype=np.uint16))
     else:
@@ -130,9 +131,17 @@ def build_bundle(context: Any, run_id: str, plugin: Plugin):
             bundle = ops.build_records_ragged(np.concatenate(ts), np.concatenate(boards), np.concatenate(chans), samples,
                                               dt_ns=int(dt_ns), baseline_window=(bl0, bl1))
         else:
-            bundle = ops.build_records(np.concatenate(ts), np.concatenate(boards), np.concatenate(chans), np.vstack(samples),
-                                       dt_ns=int(dt_ns), baseline_window=(bl0, bl1))
+            rec_h, pool_h, d_pool = ops.build_records(np.concatenate(ts), np.concatenate(boards), np.concatenate(chans), np.vstack(samples),
+                                                      dt_ns=int(dt_ns), baseline_window=(bl0, bl1), return_device=True)
+            bundle = (rec_h, pool_h)
     _apply_polarity(context, run_id, bundle[0])
+    if d_pool is not None and len(bundle[0]):
+        # the pool was gathered on the device: it stays there for the plugins downstream (records.py:441-464 shares
+        # the in-memory bundle the same way); the records rows are re-read from the host AFTER the polarity was applied
+        from .. import engine, residency
+
+        if residency.fits_device(int(bundle[1].nbytes)):
+            residency.adopt_run(run_id, bundle[0], bundle[1], "wave_pool", engine.DeviceRun.from_device_pool(bundle[0], d_pool))
     if isinstance(cache, dict):
         cache[key] = bundle
     return bundle

@@ -115,4 +115,11 @@ class B200WaveformWidthIntegralPlugin(Plugin):
             records["polarity"] = np.where(records["polarity"] == "rawpos", "rawpos", "unknown")
         if len(records) == 0:
             return np.zeros(0, dtype=WAVEFORM_WIDTH_INTEGRAL_DTYPE)
-        return ops.width_integral(records, pool, q_low=q_low, q_high=q_high, dt=float(dt), signed_samples=signed)
+        run = None
+        if wave_input.spec.is_records:
+            from .. import residency
+            from ..dtypes import RECORDS_DTYPE
+
+            if records.dtype == RECORDS_DTYPE and residency.fits_device(int(pool.nbytes)):
+                run = residency.device_run(run_id, records, pool, wave_input.spec.wave_pool_name or "wave_pool")
+        return ops.width_integral(records, pool, q_low=q_low, q_high=q_high, dt=float(dt), signed_samples=signed, run=run)

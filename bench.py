@@ -517,7 +517,7 @@ def run_e2e(args, engine, torch, barrier, max_over_ranks, sum_over_ranks, rank):
 
     from waveformanalysis_b200 import residency
     from waveformanalysis_b200.dtypes import RECORDS_DTYPE
-    from waveformanalysis_b200.plugins import B200BasicFeaturesPlugin, B200ThresholdHitPlugin
+    from waveformanalysis_b200.plugins import B200BasicFeaturesPlugin, B200RecordsPlugin, B200ThresholdHitPlugin, B200WavePoolPlugin
 
     n = min(args.e2e_records, args.records)
     dev = engine.DeviceRun.synth(n, N_SAMPLES, N_CHANNELS, seed=77 + rank, with_rows=True)
@@ -530,7 +530,8 @@ def run_e2e(args, engine, torch, barrier, max_over_ranks, sum_over_ranks, rank):
     torch.cuda.empty_cache()
     records = rows_pin.numpy().view(RECORDS_DTYPE)
     pool = pool_pin.numpy().view(np.uint16)
-    plugins = {"basic_features": B200BasicFeaturesPlugin(), "hit_threshold": B200ThresholdHitPlugin()}
+    plugins = {"records": B200RecordsPlugin(), "wave_pool": B200WavePoolPlugin(), "basic_features": B200BasicFeaturesPlugin(),
+               "hit_threshold": B200ThresholdHitPlugin()}
     ctx = PluginContext({"wave_source": "records", "hit_threshold": {"threshold": THRESHOLD}}, plugins)
 
     def step(k):

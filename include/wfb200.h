@@ -115,6 +115,12 @@ int wfb_memcpy_h2d(void* dst_dev, const void* src_host, size_t bytes, void* stre
  * field access of RecordsView (core/data/records_view.py:16-33). */
 int wfb_records_unpack(const void* records_aos_dev, int64_t n, wfb_rec_meta* meta_dev, void* stream);
 
+/* Longest record and the range of dt over the unpacked records, reduced on the device: out_host[0] = max event_length
+ * (0 when n == 0), out_host[1] = min dt, out_host[2] = max dt.  Replaces three passes over the 102-byte strided host rows
+ * (the dt validation of require_dt_array, _dt_compat.py:51-81, and the padded matrix width of hit_finder.py:364).
+ * scratch_dev: 12 bytes.  Synchronises the stream. */
+int wfb_meta_stats(const wfb_rec_meta* meta_dev, int64_t n, int32_t* scratch_dev, int32_t* out_host, void* stream);
+
 /* Hit rows of record i have their edges clamped to clamp_len_dev[i] instead of event_length (a negative entry or a NULL
  * array restores event_length).  This is hit_threshold on structured st_waveforms / filtered_waveforms rows whose
  * `event_length` field differs from the row width: every sample of the row is scanned, the edges are clamped to the

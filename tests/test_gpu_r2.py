@@ -150,21 +150,32 @@ def test_find_peaks_long_records_use_the_global_staging(G):
 
 
 def test_config3_chain_64_channels(P, G):
+    """SG filter -> `hit` -> waveform_width on 64 V1725-like channels with positive pulses.  Every stage is compared on
+    the reference's own input (exact parity bar); the chain on the device-filtered pool is compared with a tolerance that
+    covers the 2 x 5 edge samples per record, which scipy >= 1.15 fits in FLOAT32 (LAPACK sgelsd, up to ~6 ulp of noise
+    that no restatement reproduces) while the kernel evaluates the same least-squares polynomial in float64."""
     r, p = G["c3_records"], G["c3_pool"]
     base = {"records": r, "wave_pool": p}
     sg = run(P.B200WavePoolFilteredPlugin(), base, {})
     assert np.allclose(sg, G["c3_sg"], rtol=1e-5, atol=1e-3)
+    inner = np.ones(len(sg), dtype=bool)
+    inner.reshape(len(r), -1)[:, :5] = False
+    inner.reshape(len(r), -1)[:, -5:] = False
+    assert np.array_equal(sg[inner], G["c3_sg"][inner]), "SG interior samples are bit-exact"
     st = st_from_records(r, p)
-    stf = filtered_rows(st, sg)
-    assert_rows_match(run(P.B200HitFinderPlugin(), {"filtered_waveforms": stf, "st_waveforms": st}, {"height": 6.0, "width": 2}), G["c3_hit"],
-                      what="c3_hit")
-    hits = run(P.B200HitFinderPlugin(), {"records": r, "wave_pool_filtered": sg}, {"use_filtered": True, "wave_source": "records",
-                                                                                    "height": 8.0, "width": 2})
-    assert_rows_match(hits, G["c3_hit_records"], what="c3_hit_records")
-    data = {"hit": hits, "filtered_waveforms": stf, "st_waveforms": st}
-    assert_rows_match(run(P.B200WaveformWidthPlugin(), data, {"use_filtered": True, "sampling_rate": 0.25}), G["c3_width"], what="c3_width")
-    cfg = {"use_filtered": True, "sampling_rate": 0.25, "rise_low": 0.1, "rise_high": 0.5, "fall_high": 0.5, "fall_low": 0.1}
-    assert_rows_match(run(P.B200WaveformWidthPlugin(), data, cfg), G["c3_width_1050"], what="c3_width_1050")
+    width_cfg = {"use_filtered": True, "sampling_rate": 0.25}
+    cfg_1050 = {"use_filtered": True, "sampling_rate": 0.25, "rise_low": 0.1, "rise_high": 0.5, "fall_high": 0.5, "fall_low": 0.1}
+    for pool_f, exact in ((G["c3_sg"], True), (sg, False)):
+        stf = filtered_rows(st, pool_f)
+        tol = {} if exact else {"rtol": 1e-4, "atol": 2e-2}
+        assert_rows_match(run(P.B200HitFinderPlugin(), {"filtered_waveforms": stf, "st_waveforms": st}, {"height": 6.0, "width": 2}), G["c3_hit"],
+                          what="c3_hit", **tol)
+        hits = run(P.B200HitFinderPlugin(), {"records": r, "wave_pool_filtered": pool_f}, {"use_filtered": True, "wave_source": "records",
+                                                                                            "height": 8.0, "width": 2})
+        assert_rows_match(hits, G["c3_hit_records"], what="c3_hit_records", **tol)
+        data = {"hit": hits, "filtered_waveforms": stf, "st_waveforms": st}
+        assert_rows_match(run(P.B200WaveformWidthPlugin(), data, width_cfg), G["c3_width"], what="c3_width", **tol)
+        assert_rows_match(run(P.B200WaveformWidthPlugin(), data, cfg_1050), G["c3_width_1050"], what="c3_width_1050", **tol)
     assert_rows_match(run(P.B200BasicFeaturesPlugin(), base, {"wave_source": "records"}), G["c3_bf"], what="c3_bf", float_exact=FX_BF)
     assert_rows_match(run(P.B200ThresholdHitPlugin(), base, {"wave_source": "records", "threshold": 15.0}), G["c3_hits_thr"], what="c3_hits",
                       float_exact=FX_HIT)

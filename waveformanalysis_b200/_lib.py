@@ -135,6 +135,7 @@ PROTOTYPES = {
     "wfb_memcpy_h2d": (C.c_int, [_vp, _vp, C.c_size_t, _vp]),
     "wfb_records_unpack": (C.c_int, [_vp, _i64, _vp, _vp]),
     "wfb_meta_set_clamp": (C.c_int, [_vp, _i64, _vp, _vp]),
+    "wfb_meta_stats": (C.c_int, [_vp, _i64, _vp, _vp, _vp]),
     "wfb_build_records": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "wfb_build_records_workspace_bytes": (_sz, [_i64]),
     "wfb_features_hits_workspace_bytes": (_sz, [_i64]),

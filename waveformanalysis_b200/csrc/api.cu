@@ -1,4 +1,5 @@
 // C-ABI plumbing: errors, device info, RECORDS_DTYPE unpack, the host-buffer pipeline.
+#include <limits.h>
 #include <stdarg.h>
 
 #include <algorithm>
@@ -87,6 +88,23 @@ __global__ void err_accumulate_kernel(const int* __restrict__ chunk_flag, int* _
     if (*chunk_flag != 0 && *run_flag == 0) *run_flag = *chunk_flag;
 }
 
+__global__ void meta_stats_kernel(const wfb_rec_meta* __restrict__ meta, long long n, int* __restrict__ out) {
+    int mx_len = 0, mn_dt = INT_MAX, mx_dt = INT_MIN;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        mx_len = max(mx_len, meta[i].event_length);
+        mn_dt = min(mn_dt, meta[i].dt);
+        mx_dt = max(mx_dt, meta[i].dt);
+    }
+    mx_len = __reduce_max_sync(kFull, mx_len);
+    mn_dt = __reduce_min_sync(kFull, mn_dt);
+    mx_dt = __reduce_max_sync(kFull, mx_dt);
+    if (lane_id() == 0) {
+        atomicMax(out + 0, mx_len);
+        atomicMin(out + 1, mn_dt);
+        atomicMax(out + 2, mx_dt);
+    }
+}
+
 __global__ void meta_set_clamp_kernel(wfb_rec_meta* __restrict__ meta, long long n, const int* __restrict__ clamp) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -100,6 +118,22 @@ __global__ void meta_set_clamp_kernel(wfb_rec_meta* __restrict__ meta, long long
 }  // namespace wfb
 
 using namespace wfb;
+
+extern "C" int wfb_meta_stats(const wfb_rec_meta* meta_dev, int64_t n, int32_t* scratch_dev, int32_t* out_host, void* stream) {
+    WFB_REQUIRE(n >= 0 && out_host != nullptr, "wfb_meta_stats: bad arguments");
+    out_host[0] = 0;
+    out_host[1] = INT_MAX;
+    out_host[2] = INT_MIN;
+    if (n == 0) return WFB_OK;
+    WFB_REQUIRE(meta_dev && scratch_dev, "wfb_meta_stats: NULL pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    WFB_CUDA(cudaMemcpyAsync(scratch_dev, out_host, 12, cudaMemcpyHostToDevice, st));
+    meta_stats_kernel<<<(unsigned)std::min<long long>(2048, (n + 255) / 256), 256, 0, st>>>(meta_dev, n, scratch_dev);
+    WFB_CUDA(cudaGetLastError());
+    WFB_CUDA(cudaMemcpyAsync(out_host, scratch_dev, 12, cudaMemcpyDeviceToHost, st));
+    WFB_CUDA(cudaStreamSynchronize(st));
+    return WFB_OK;
+}
 
 extern "C" int wfb_meta_set_clamp(wfb_rec_meta* meta_dev, int64_t n, const int32_t* clamp_len_dev, void* stream) {
     WFB_REQUIRE(n >= 0, "wfb_meta_set_clamp: negative n");
@@ -367,10 +401,13 @@ again:
         }
         if (lo < 0) lo = hi = 0;
         if (lo > hi || hi > pool_len || lo < 0) {
-            set_error("records reference samples outside wave_pool bounds");
-            rc = WFB_ERR_LAYOUT;
             cleanup();
-            return rc;
+            if (!scan_all) {  // first / last record do not bound the chunk: records are not in wave_offset order
+                scan_all = true;
+                goto again;
+            }
+            set_error("records reference samples outside wave_pool bounds");
+            return WFB_ERR_LAYOUT;
         }
         if (do_hits && hit_out_host && chunk_idx >= 2) PH_CHECK(drain_hits(chunk_idx - 2));
         const long long lo_al = lo & ~7ll;  // keep 16-byte alignment of record starts relative to the pool

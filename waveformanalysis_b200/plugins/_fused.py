@@ -44,16 +44,32 @@ def feature_params(plugin: Any, context: Any, run_id: str, records: np.ndarray) 
                 fixed_baselines={k: float(v) for k, v in fixed.items() if v is not None})
 
 
-def hit_params(plugin: Any, context: Any, run_id: str, records: np.ndarray) -> dict:
-    """Kernel parameters of hit_threshold from the Context (hit_finder.py:122-150, 287-325)."""
+def hit_params(plugin: Any, context: Any, run_id: str, records: np.ndarray, *, dt_on_device: bool = False) -> dict:
+    """Kernel parameters of hit_threshold from the Context (hit_finder.py:122-150, 287-325).  ``dt_on_device``: the
+    records carry a dt field whose range is validated from the device copy (``check_dt_range``) instead of by a pass
+    over the strided host rows."""
     threshold = float(context.get_config(plugin, "threshold"))
     explicit_dt = resolve_dt_config(context, plugin, deprecated_keys=("sampling_interval_ns", "dt_ns"))
-    dt_scalar = check_dt_array(records, explicit_dt, plugin.provides, "records")
+    if dt_on_device and "dt" in (records.dtype.names or ()):
+        dt_scalar = None
+    else:
+        dt_scalar = check_dt_array(records, explicit_dt, plugin.provides, "records")
     boards, channels = _columns(records)
     thr = per_channel_option(context.get_config(plugin, "channel_config"), run_id, boards, channels, "threshold", threshold)
     return dict(threshold=threshold, thresholds={k: float(v) for k, v in thr.items() if float(v) != threshold},
                 left_extension=max(0, int(context.get_config(plugin, "left_extension"))),
                 right_extension=max(0, int(context.get_config(plugin, "right_extension"))), explicit_dt=dt_scalar)
+
+
+def check_dt_range(run, plugin_name: str) -> None:
+    """require_dt_array's checks (_dt_compat.py:51-81) on the dt range reduced on the device."""
+    if run.dt_range is None:
+        return
+    lo, hi = run.dt_range
+    if lo <= 0:
+        raise ValueError(f"[{plugin_name}] records.dt must be positive for every row")
+    if hi > np.iinfo(np.int32).max:
+        raise ValueError(f"[{plugin_name}] records.dt exceeds int32 range")
 
 
 def _signature(fp: tuple, kind: str, params: dict) -> tuple:
@@ -82,12 +98,13 @@ def _sibling(context: Any, name: str, cls_name: str, spec) -> Any:
 def records_pass(plugin: Any, context: Any, run_id: str, spec, records: np.ndarray, pool: np.ndarray, want: str) -> np.ndarray:
     """``want`` = "features" (called by basic_features) or "hits" (called by hit_threshold), records source."""
     assert want in ("features", "hits")
-    own = feature_params(plugin, context, run_id, records) if want == "features" else hit_params(plugin, context, run_id, records)
+    fusable = records.dtype == RECORDS_DTYPE and len(records) > 0 and residency.fits_device(int(pool.nbytes))
+    own = (feature_params(plugin, context, run_id, records) if want == "features"
+           else hit_params(plugin, context, run_id, records, dt_on_device=fusable))
     pool_name = spec.wave_pool_name or "wave_pool"
     empty = np.zeros(0, dtype=BASIC_FEATURES_DTYPE if want == "features" else THRESHOLD_HIT_DTYPE)
     if len(records) == 0:
         return empty
-    fusable = records.dtype == RECORDS_DTYPE and residency.fits_device(int(pool.nbytes))
     if not fusable:  # partial record layouts / pools larger than the device: the chunked host pipeline, caller's rows only
         if want == "features":
             return engine.process_host(records, pool, features=True, hits=False, explicit_dt=1, **own)["features"]
@@ -102,12 +119,17 @@ def records_pass(plugin: Any, context: Any, run_id: str, spec, records: np.ndarr
     other = None
     if sib is not None:
         try:
-            other = hit_params(sib, context, run_id, records) if want == "features" else feature_params(sib, context, run_id, records)
+            other = (hit_params(sib, context, run_id, records, dt_on_device=True) if want == "features"
+                     else feature_params(sib, context, run_id, records))
         except Exception:
             other = None  # the sibling will raise its own error when (if) the Context runs it
     fpar = own if want == "features" else other
     hpar = own if want == "hits" else other
     run = residency.device_run(run_id, records, pool, pool_name)
+    if want == "hits":
+        check_dt_range(run, plugin.provides)
+    elif hpar is not None and run.dt_range is not None and run.dt_range[0] <= 0:
+        hpar, other = None, None  # the sibling raises its own error when the Context runs it
     kw: dict = dict(features=fpar is not None, hits=hpar is not None)
     thresholds, fixed = {}, {}
     if fpar is not None:

@@ -23,9 +23,24 @@ from ..plugin_api import HAVE_REFERENCE, Option, Plugin
 _CACHE_ATTR = "_b200_records_bundle"
 
 
+def _seeded(context: Any, run_id: str, name: str):
+    """Data seeded into the context under ``name`` (tests, embedding applications), None if there is none.  A real
+    Context raises for names no plugin provides, so memory is looked at first."""
+    results = getattr(context, "_results", None)
+    if isinstance(results, dict) and (run_id, name) in results:
+        return results[(run_id, name)]
+    plugins = getattr(context, "_plugins", None)
+    if isinstance(plugins, dict) and plugins and name not in plugins:
+        return None
+    try:
+        return context.get_data(run_id, name) if hasattr(context, "get_data") else None
+    except Exception:
+        return None
+
+
 def _read_raw_arrays(context: Any, run_id: str, adapter_name: str):
     """[(channel_index, raw 2-D array (n, header + L))] via the reference's readers."""
-    raw = context.get_data(run_id, "raw_arrays") if hasattr(context, "get_data") else None
+    raw = _seeded(context, run_id, "raw_arrays")
     if raw is not None:
         return list(enumerate(raw)), None
     if not HAVE_REFERENCE:
@@ -90,7 +105,7 @@ def build_bundle(context: Any, run_id: str, plugin: Plugin):
     if isinstance(cache, dict) and key in cache:
         return cache[key]
     adapter_name = (context.get_config(plugin, "daq_adapter") or getattr(context, "config", {}).get("daq_adapter") or "vx2730").lower()
-    if adapter_name == "v1725" and (not hasattr(context, "get_data") or context.get_data(run_id, "raw_arrays") is None):
+    if adapter_name == "v1725" and _seeded(context, run_id, "raw_arrays") is None:
         bundle = _v1725_bundle(context, run_id, plugin)
         _apply_polarity(context, run_id, bundle[0])
         if isinstance(cache, dict):

@@ -147,6 +147,8 @@ def release(run_id: str | None = None) -> None:
         for d in (_RUNS, _ROWS):
             for k in [k for k in d if run_id is None or k[0] == str(run_id)]:
                 del d[k]
+    if run_id is not None:
+        return  # the blocks stay with torch's caching allocator: the next run of the same size reuses them
     try:
         import torch
 

@@ -286,6 +286,19 @@ int wfb_group_abs_windows(const int64_t* timestamp_dev, const double* abs_start_
                           int64_t* order_dev, int64_t* event_id_dev, int64_t* n_events_dev, void* workspace_dev,
                           size_t workspace_bytes, void* stream);
 
+/* Grouping columns straight from packed hit rows on the device (row_bytes 60: THRESHOLD_HIT, 72: HIT_MERGED; the first
+ * 60 bytes are laid out alike): timestamp, dt, record_id and - unless abs_start_dev is NULL - the absolute windows
+ * timestamp + (edge - position) * dt * 1e3 (event_grouping.py:365-367).  Keeps the time-sharded multi-GPU grouping on the
+ * device (no host round trip of the hit rows). */
+int wfb_hit_columns(const void* rows_dev, int64_t n, int32_t row_bytes, int64_t* timestamp_dev, int32_t* dt_dev,
+                    int64_t* record_id_dev, double* abs_start_dev, double* abs_end_dev, void* stream);
+
+/* Absolute window of every HIT_MERGED row as min / max over the windows of its component hits (event_grouping.py:369-414;
+ * rows merged across records carry no sample window of their own).  hits_dev / order_dev / merged_dev as passed to and
+ * filled by wfb_hit_merge. */
+int wfb_merged_abs_windows(const void* hits_dev, const int64_t* order_dev, const void* merged_dev, int64_t n_clusters,
+                           double* abs_start_dev, double* abs_end_dev, void* stream);
+
 /* Anchored fixed-window clustering of time-sorted timestamps.  Replaces
  * _find_cluster_boundaries_numba (event_grouping.py:477-510): cluster k starts at the first
  * timestamp > ts[anchor_k-1] + window.  ts_sorted_dev int64[n] ascending.

@@ -136,6 +136,8 @@ PROTOTYPES = {
     "wfb_records_unpack": (C.c_int, [_vp, _i64, _vp, _vp]),
     "wfb_meta_set_clamp": (C.c_int, [_vp, _i64, _vp, _vp]),
     "wfb_meta_stats": (C.c_int, [_vp, _i64, _vp, _vp, _vp]),
+    "wfb_hit_columns": (C.c_int, [_vp, _i64, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "wfb_merged_abs_windows": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "wfb_build_records": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "wfb_build_records_workspace_bytes": (_sz, [_i64]),
     "wfb_features_hits_workspace_bytes": (_sz, [_i64]),

@@ -181,6 +181,43 @@ __global__ void hm_rows_kernel(const uint8_t* __restrict__ rows, const long long
     dst[17] = (unsigned)cnt;                          // component_count
 }
 
+// grouping columns of packed hit rows (THRESHOLD_HIT 60 B or HIT_MERGED 72 B: the first 15 words are laid out alike)
+__global__ void hit_columns_kernel(const uint8_t* __restrict__ rows, long long n, int row_bytes, long long* __restrict__ ts,
+                                   int* __restrict__ dt, long long* __restrict__ rid, double* __restrict__ a0, double* __restrict__ a1) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const HitCols h{reinterpret_cast<const unsigned*>(rows + i * row_bytes)};
+    ts[i] = h.timestamp();
+    dt[i] = h.dt();
+    rid[i] = h.record_id();
+    if (a0 != nullptr) {
+        const double dt_ps = __dmul_rn((double)h.dt(), 1e3);
+        const double t = (double)h.timestamp(), p = (double)h.position();
+        a0[i] = __dadd_rn(t, __dmul_rn(__dsub_rn((double)h.edge_start(), p), dt_ps));
+        a1[i] = __dadd_rn(t, __dmul_rn(__dsub_rn((double)h.edge_end(), p), dt_ps));
+    }
+}
+
+// absolute window of every merged row = min / max over the windows of its component hits (event_grouping.py:369-414)
+__global__ void merged_windows_kernel(const uint8_t* __restrict__ hits, const long long* __restrict__ order, const uint8_t* __restrict__ merged,
+                                      long long n_clusters, double* __restrict__ a0, double* __restrict__ a1) {
+    long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (c >= n_clusters) return;
+    const unsigned* m = reinterpret_cast<const unsigned*>(merged + c * kMergedRowBytes);
+    const long long s = (long long)(((unsigned long long)m[16] << 32) | m[15]);
+    const int cnt = (int)m[17];
+    double lo = __longlong_as_double(0x7ff0000000000000ll), hi = -lo;
+    for (int k = 0; k < cnt; ++k) {
+        const HitCols h = hit_at(hits, order[s + k]);
+        const double dt_ps = __dmul_rn((double)h.dt(), 1e3);
+        const double t = (double)h.timestamp(), p = (double)h.position();
+        lo = fmin(lo, __dadd_rn(t, __dmul_rn(__dsub_rn((double)h.edge_start(), p), dt_ps)));
+        hi = fmax(hi, __dadd_rn(t, __dmul_rn(__dsub_rn((double)h.edge_end(), p), dt_ps)));
+    }
+    a0[c] = lo;
+    a1[c] = hi;
+}
+
 }  // namespace wfb
 
 using namespace wfb;
@@ -247,6 +284,31 @@ extern "C" int wfb_hit_merge(const void* hits_dev, int64_t n, double merge_gap_n
     if (rc != WFB_OK) return rc;
     hm_cluster_starts_kernel<<<hm_nb(n), 256, 0, st>>>(f0, vA, n, cidx, vB, ncl);
     hm_rows_kernel<<<hm_nb(n), 256, 0, st>>>(rows, order, vB, ncl, n, static_cast<uint8_t*>(merged_dev));
+    WFB_CUDA(cudaGetLastError());
+    return WFB_OK;
+}
+
+extern "C" int wfb_hit_columns(const void* rows_dev, int64_t n, int32_t row_bytes, int64_t* timestamp_dev, int32_t* dt_dev,
+                               int64_t* record_id_dev, double* abs_start_dev, double* abs_end_dev, void* stream) {
+    WFB_REQUIRE(n >= 0 && (row_bytes == kHitRowBytes || row_bytes == kMergedRowBytes), "wfb_hit_columns: bad arguments");
+    if (n == 0) return WFB_OK;
+    WFB_REQUIRE(rows_dev && timestamp_dev && dt_dev && record_id_dev, "wfb_hit_columns: NULL pointer");
+    WFB_REQUIRE((abs_start_dev == nullptr) == (abs_end_dev == nullptr), "wfb_hit_columns: abs_start / abs_end go together");
+    hit_columns_kernel<<<hm_nb(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint8_t*>(rows_dev), n, row_bytes,
+                                                                               reinterpret_cast<long long*>(timestamp_dev), dt_dev,
+                                                                               reinterpret_cast<long long*>(record_id_dev), abs_start_dev, abs_end_dev);
+    WFB_CUDA(cudaGetLastError());
+    return WFB_OK;
+}
+
+extern "C" int wfb_merged_abs_windows(const void* hits_dev, const int64_t* order_dev, const void* merged_dev, int64_t n_clusters,
+                                      double* abs_start_dev, double* abs_end_dev, void* stream) {
+    WFB_REQUIRE(n_clusters >= 0, "wfb_merged_abs_windows: negative count");
+    if (n_clusters == 0) return WFB_OK;
+    WFB_REQUIRE(hits_dev && order_dev && merged_dev && abs_start_dev && abs_end_dev, "wfb_merged_abs_windows: NULL pointer");
+    merged_windows_kernel<<<hm_nb(n_clusters), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint8_t*>(hits_dev), reinterpret_cast<const long long*>(order_dev), static_cast<const uint8_t*>(merged_dev), n_clusters,
+        abs_start_dev, abs_end_dev);
     WFB_CUDA(cudaGetLastError());
     return WFB_OK;
 }

@@ -332,14 +332,18 @@ class DeviceRun:
         return cls(meta, d_pool, n, int(pool_is_f32), max(lmax, 0), records_rows=rows)
 
     @classmethod
-    def synth(cls, n: int, n_samples: int, n_channels: int, *, dt_ns: int = 2, seed: int = 1234, with_rows: bool = False) -> "DeviceRun":
+    def synth(cls, n: int, n_samples: int, n_channels: int, *, dt_ns: int = 2, seed: int = 1234, with_rows: bool = False,
+              record_base: int = 0) -> "DeviceRun":
+        """Synthetic run generated on the device.  ``record_base``: this is the time shard [record_base, record_base + n)
+        of ONE run with that seed (timestamps, record ids and wave offsets are those of the whole run)."""
         torch = _torch()
         lib = _lib.load()
         pool = torch.empty(n * n_samples + 16, dtype=torch.int16, device="cuda")[: n * n_samples]
         meta = torch.empty(max(n, 1) * 48, dtype=torch.uint8, device="cuda")
         rows = torch.empty(n * 102, dtype=torch.uint8, device="cuda") if with_rows else None
-        _lib.check(lib.wfb_synth_fill(_ptr(pool), _ptr(meta), _ptr(rows), n, n_samples, n_channels, dt_ns, seed, 0, _stream()), "wfb_synth_fill")
-        return cls(meta, pool, n, 0, n_samples, records_rows=rows)
+        _lib.check(lib.wfb_synth_fill(_ptr(pool), _ptr(meta), _ptr(rows), n, n_samples, n_channels, dt_ns, seed, int(record_base), _stream()),
+                   "wfb_synth_fill")
+        return cls(meta, pool, n, 0, n_samples, records_rows=rows, pool_base=int(record_base) * n_samples, row_base=int(record_base))
 
     def workspace(self):
         torch = _torch()

@@ -799,3 +799,93 @@ def pair_events(offsets: np.ndarray, member_ts: np.ndarray, member_area: np.ndar
                                    _ptr(delta), _ptr(a_ch), _ptr(h_ch), _stream()), "wfb_pair_events")
     return dict(keep=keep.cpu().numpy().astype(bool), delta_t=delta.cpu().numpy(),
                 area_ch=a_ch.cpu().numpy()[: n_ev * nc].reshape(n_ev, nc), height_ch=h_ch.cpu().numpy()[: n_ev * nc].reshape(n_ev, nc))
+
+
+# --------------------------------------------------------------------------------------------
+# device-resident hit_merge -> hit_grouped (time-sharded multi-GPU runs keep the rows in HBM)
+# --------------------------------------------------------------------------------------------
+
+
+def hit_merge_device(d_hits, n: int, *, merge_gap_ns: float = 0.0, max_total_width_ns: float = 10000.0) -> dict:
+    """wfb_hit_merge on packed THRESHOLD_HIT rows that already live on the device (uint8 tensor, 60 B per row).
+    Returns device tensors: ``order`` / ``cluster_index`` (int64[n]), ``merged`` (uint8, 72 B per cluster), the
+    clusters' absolute windows ``abs_start`` / ``abs_end`` (float64) and ``n_clusters`` (int)."""
+    lib = _lib.load()
+    torch = _torch()
+    n = int(n)
+    order = torch.empty(max(n, 1), dtype=torch.int64, device="cuda")
+    cidx = torch.empty(max(n, 1), dtype=torch.int64, device="cuda")
+    merged = torch.empty(max(n, 1) * HIT_MERGED_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    d_ncl = torch.zeros(1, dtype=torch.int64, device="cuda")
+    if n:
+        ws = _empty(lib.wfb_hit_merge_workspace_bytes(n))
+        _lib.check(lib.wfb_hit_merge(_ptr(d_hits), n, float(merge_gap_ns), float(max_total_width_ns), _ptr(order), _ptr(cidx), _ptr(merged),
+                                     _ptr(d_ncl), _ptr(ws), ws.numel(), _stream()), "wfb_hit_merge")
+    ncl = int(d_ncl.item())
+    a0 = torch.empty(max(ncl, 1), dtype=torch.float64, device="cuda")
+    a1 = torch.empty(max(ncl, 1), dtype=torch.float64, device="cuda")
+    _lib.check(lib.wfb_merged_abs_windows(_ptr(d_hits), _ptr(order), _ptr(merged), ncl, _ptr(a0), _ptr(a1), _stream()), "wfb_merged_abs_windows")
+    return dict(order=order, cluster_index=cidx, merged=merged, abs_start=a0, abs_end=a1, n_clusters=ncl)
+
+
+def group_rows_device(d_rows, n: int, row_bytes: int, time_window_ns: float, abs_start=None, abs_end=None) -> dict:
+    """Chain clustering (event_grouping.py:287-471) of packed hit rows on the device: ``event_of_row`` (int64[n], in row
+    order), ``n_events``; ``abs_start`` / ``abs_end`` default to the rows' own sample windows."""
+    lib = _lib.load()
+    torch = _torch()
+    n = int(n)
+    ev = torch.empty(max(n, 1), dtype=torch.int64, device="cuda")
+    if n == 0:
+        return dict(event_of_row=ev[:0], n_events=0)
+    ts = torch.empty(n, dtype=torch.int64, device="cuda")
+    dt = torch.empty(n, dtype=torch.int32, device="cuda")
+    rid = torch.empty(n, dtype=torch.int64, device="cuda")
+    own = abs_start is None
+    if own:
+        abs_start = torch.empty(n, dtype=torch.float64, device="cuda")
+        abs_end = torch.empty(n, dtype=torch.float64, device="cuda")
+    _lib.check(lib.wfb_hit_columns(_ptr(d_rows), n, int(row_bytes), _ptr(ts), _ptr(dt), _ptr(rid), _ptr(abs_start) if own else None,
+                                   _ptr(abs_end) if own else None, _stream()), "wfb_hit_columns")
+    order = torch.empty(n, dtype=torch.int64, device="cuda")
+    n_ev = torch.zeros(1, dtype=torch.int64, device="cuda")
+    ws = _empty(lib.wfb_group_workspace_bytes(n))
+    _lib.check(lib.wfb_group_abs_windows(_ptr(ts), _ptr(abs_start), _ptr(abs_end), _ptr(dt), _ptr(rid), n, float(time_window_ns), _ptr(order),
+                                         _ptr(ev), _ptr(n_ev), _ptr(ws), ws.numel(), _stream()), "wfb_group_abs_windows")
+    return dict(event_of_row=ev, n_events=int(n_ev.item()), abs_start=abs_start, abs_end=abs_end)
+
+
+def filter_run_device(run: DeviceRun, cfg: dict):
+    """wfb_filter_pool on a device-resident run with ONE configuration for every record (benchmarks, multi-GPU shards):
+    returns the float32 pool as a device tensor, nothing crosses PCIe.  ``cfg`` as ``filter_pool``'s ``default``."""
+    lib = _lib.load()
+    torch = _torch()
+    n, L = run.n, max(run.lmax, 1)
+    cfgs = (_lib.FilterCfg * 1)()
+    tab = np.zeros(1)
+    toff = -1
+    if cfg["filter_type"] == "BW":
+        sos = np.asarray(cfg["sos"], dtype=np.float64)
+        zi = sos_zi(sos)
+        cfgs[0].type = 1
+        cfgs[0].n_sections = sos.shape[0]
+        for s in range(sos.shape[0]):
+            for j in range(6):
+                cfgs[0].sos[s][j] = sos[s, j]
+            cfgs[0].zi[s][0], cfgs[0].zi[s][1] = zi[s, 0], zi[s, 1]
+    else:
+        w0, poly = int(cfg["sg_window_size"]), int(cfg["sg_poly_order"])
+        cfgs[0].type, cfgs[0].sg_window, cfgs[0].sg_poly = 0, w0, poly
+        w = min(w0, L)
+        w -= (w % 2 == 0)
+        if w > poly and w > 0:
+            tab, toff = sg_tables(int(w), poly), 0
+    d_cfg = upload(np.frombuffer(bytes(cfgs), dtype=np.uint8).copy())
+    d_idx = torch.zeros(max(n, 1), dtype=torch.int32, device="cuda")
+    d_tab = upload(np.ascontiguousarray(tab, dtype=np.float64))
+    d_toff = torch.full((max(n, 1),), toff, dtype=torch.int32, device="cuda")
+    d_out = torch.empty(run.pool_len + 16, dtype=torch.float32, device="cuda")[: run.pool_len]
+    ws = _empty(lib.wfb_filter_workspace_bytes(n, L)) if cfg["filter_type"] == "BW" else None
+    _lib.check(lib.wfb_filter_pool(_ptr(run.pool), run.pool_is_f32, run.pool_len, _ptr(run.meta), n, _ptr(d_cfg), 1, _ptr(d_idx), _ptr(d_tab),
+                                   _ptr(d_toff), _ptr(d_out), run.pool_base, _ptr(ws), 0 if ws is None else ws.numel(), L, _stream()),
+               "wfb_filter_pool")
+    return d_out

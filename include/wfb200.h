@@ -146,6 +146,18 @@ int wfb_build_records(const int16_t* samples_dev, const int64_t* ts_dev, const i
                       void* stream);
 size_t wfb_build_records_workspace_bytes(int64_t n);
 
+/* Raw int16 rows -> structured st_waveforms rows (ST_WAVEFORM_DTYPE: 76 header bytes + wave_length int16 samples,
+ * core/processing/dtypes.py:36-64) in INPUT order.  Replaces WaveformStruct._structure_waveform
+ * (core/plugins/builtin/cpu/waveforms.py:644-799): baseline = mean over the sample window [bl_start, bl_end) clamped to
+ * the row (NaN when empty; baselines_in_dev overrides it), baseline_upstream from baseline_upstream_dev (NaN when NULL,
+ * :762-771), polarity 'unknown', record_id = record_base + row (:909-911), dt, event_length = min(n_samples,
+ * wave_length), samples copied / truncated, the rest of `wave` zero.  ts_dev already in ps. */
+int wfb_structure_waveforms(const int16_t* samples_dev, const int64_t* ts_dev, const int16_t* board_dev,
+                            const int16_t* channel_dev, const double* baselines_in_dev,
+                            const double* baseline_upstream_dev, int64_t n, int32_t n_samples, int32_t wave_length,
+                            int32_t bl_start, int32_t bl_end, int32_t dt_ns, int64_t record_base, void* rows_out_dev,
+                            void* stream);
+
 /* ---- K2 + K3: fused baseline / threshold hits / basic_features ----------------------------- */
 
 size_t wfb_features_hits_workspace_bytes(int64_t n);

@@ -141,6 +141,35 @@ def main():
                              {"use_filtered": True, "sampling_rate": 0.25, "rise_low": 0.1, "rise_high": 0.5, "fall_high": 0.5, "fall_low": 0.1})
     G["c3_bf"] = run(BasicFeaturesPlugin(), {"records": r, "wave_pool": p}, {"wave_source": "records"})
     G["c3_hits_thr"] = run(ThresholdHitPlugin(), {"records": r, "wave_pool": p}, {"wave_source": "records", "threshold": 15.0})
+    # ------------------------------------------------------------------ st_waveforms: dual baseline (waveforms.py:644-799)
+    from waveform_analysis.core.plugins.builtin.cpu.waveforms import WaveformStruct, WaveformStructConfig
+
+    raw = make_raw_run(3, 50, 400, seed=808)
+    cols = WaveformStructConfig.default_vx2730().format_spec.columns
+    arrays, upstream = [], []
+    rng = np.random.default_rng(9)
+    for c in range(3):
+        sel = raw["channels"] == c
+        arr = np.zeros((int(sel.sum()), 7 + 400), dtype=np.int64)
+        arr[:, cols.board] = c % 2
+        arr[:, cols.channel] = c
+        arr[:, cols.timestamp] = raw["timestamps_ps"][sel] // 1000  # the VX2730 adapter scales its time stamps to ps
+        arr[:, 7:] = raw["samples"][sel]
+        arrays.append(arr)
+        upstream.append(rng.normal(8000.0, 2.0, size=len(arr)))
+    upstream[1] = upstream[1][:-3]  # wrong length: the reference falls back to NaN for that channel (:762-771)
+    for k, arr in enumerate(arrays):
+        G[f"st_raw{k}"] = arr
+        G[f"st_up{k}"] = upstream[k]
+    cfg = WaveformStructConfig.default_vx2730()
+    G["st_default"] = WaveformStruct(arrays, config=cfg).structure_waveforms()
+    G["st_upstream"] = WaveformStruct(arrays, config=cfg, upstream_baselines=upstream).structure_waveforms()
+    G["st_window"] = WaveformStruct(arrays, config=cfg, baseline_samples=(10, 90)).structure_waveforms()
+    cfg2 = WaveformStructConfig.default_vx2730()
+    cfg2.wave_length = 256
+    G["st_trunc"] = WaveformStruct(arrays, config=cfg2).structure_waveforms()
+    bundle = rb.build_records_from_st_waveforms(G["st_upstream"], default_dt_ns=2)
+    G["st_records"], G["st_pool"] = bundle.records, bundle.wave_pool
     out = os.path.join(HERE, "r2_golden.npz")
     np.savez_compressed(out, **G)
     print("wrote", out, {k: len(v) for k, v in G.items() if v.dtype.names}, os.path.getsize(out) / 1e3, "kB")

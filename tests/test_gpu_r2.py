@@ -203,3 +203,27 @@ def test_memmap_and_read_only_inputs(P, golden, tmp_path):
     rr.setflags(write=False)
     out = run(P.B200WaveformWidthIntegralPlugin(), {"records": rr, "wave_pool": ro}, {"wave_source": "records"})
     assert_rows_match(out, golden["wint_default"], what="wint")
+
+
+def test_st_waveforms_dual_baseline(P, G):
+    """st_waveforms rows structured on the device (waveforms.py:644-799): baseline over the adapter window, the upstream
+    baseline carried (NaN for a channel whose upstream array has the wrong length), other windows, truncation to
+    wave_length; then records + wave_pool from those rows with both baselines (records_builder.py:645-777)."""
+    from waveformanalysis_b200 import ops
+
+    arrays = [G[f"st_raw{k}"] for k in range(3)]
+    upstream = [G[f"st_up{k}"] for k in range(3)]
+
+    def same(got, want, what):
+        assert got.dtype == want.dtype and got.shape == want.shape, (what, got.dtype, want.dtype, got.shape, want.shape)
+        for f in want.dtype.names:
+            assert np.array_equal(got[f], want[f], equal_nan=want[f].dtype.kind == "f"), f"{what}.{f}"
+
+    data = {"raw_arrays": arrays, "raw_files": [[], [], []]}
+    same(run(P.B200WaveformsPlugin(), data, {}), G["st_default"], "st_default")
+    same(run(P.B200WaveformsPlugin(), dict(data, baseline=upstream), {"use_upstream_baseline": True}), G["st_upstream"], "st_upstream")
+    same(run(P.B200WaveformsPlugin(), data, {"baseline_samples": (10, 90)}), G["st_window"], "st_window")
+    same(run(P.B200WaveformsPlugin(), data, {"wave_length": 256}), G["st_trunc"], "st_trunc")
+    rec, pool = ops.build_records_from_st(G["st_upstream"], default_dt_ns=2)
+    same(rec, G["st_records"], "st_records")
+    assert np.array_equal(pool, G["st_pool"])

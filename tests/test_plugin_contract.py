@@ -30,7 +30,7 @@ def test_profile_provides_the_hot_path_names():
     from waveformanalysis_b200 import profiles
 
     names = [p.provides for p in profiles.b200_default()]
-    assert names == ["records", "wave_pool", "wave_pool_filtered", "basic_features", "hit_threshold", "hit", "waveform_width",
+    assert names == ["st_waveforms", "records", "wave_pool", "wave_pool_filtered", "basic_features", "hit_threshold", "hit", "waveform_width",
                      "waveform_width_integral", "hit_merge_clusters", "hit_merged", "hit_merged_components", "hit_grouped",
                      "df", "df_events", "df_paired", "s1_s2"]
     for p in profiles.b200_default():

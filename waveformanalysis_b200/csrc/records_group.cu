@@ -178,6 +178,57 @@ __global__ void k4_anchor_walk_kernel(const long long* __restrict__ ts, long lon
     }
 }
 
+
+// ---- st_waveforms: structured rows (core/processing/dtypes.py:36-64, 76 header bytes + wave_length int16 samples) ----
+// One warp per raw row, in input order (channel by channel, waveforms.py:644-799, 906-913): the mean over the baseline
+// window is an integer sum divided once (exact, any summation order), the upstream baseline is carried along, the
+// samples are copied (truncated to wave_length, the rest of the row stays 0) and event_length records how many.
+__global__ void __launch_bounds__(256) st_structure_kernel(const short* __restrict__ samples, long long n, int l_src, int wave_len,
+                                                           const long long* __restrict__ ts, const short* __restrict__ board,
+                                                           const short* __restrict__ chan, const double* __restrict__ bl_in,
+                                                           const double* __restrict__ bl_up, int bl_lo, int bl_hi, int dt_ns,
+                                                           uint8_t* __restrict__ out, long long record_base) {
+    const int lane = lane_id();
+    const long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    if (i >= n) return;
+    const short* src = samples + i * (long long)l_src;
+    const long long row_bytes = 76 + 2ll * wave_len;
+    unsigned short* dst = reinterpret_cast<unsigned short*>(out + i * row_bytes);  // rows are 2-byte aligned
+    const int n_copy = min(l_src, wave_len);
+    double baseline;
+    if (bl_in != nullptr) {
+        baseline = bl_in[i];
+    } else if (bl_hi > bl_lo) {
+        long long acc = 0;
+        for (int j = bl_lo + lane; j < bl_hi; j += 32) acc += src[j];
+        acc = warp_sum_i64(acc);
+        baseline = (double)acc / (double)(bl_hi - bl_lo);
+    } else {
+        baseline = __longlong_as_double(0x7ff8000000000000ll);
+    }
+    const double upstream = bl_up != nullptr ? bl_up[i] : __longlong_as_double(0x7ff8000000000000ll);
+    // the 38 half-words of the header
+    auto q = [](unsigned long long v, int k) { return (unsigned short)(v >> (16 * k)); };
+    for (int k = lane; k < 38; k += 32) {
+        unsigned short h = 0;
+        if (k < 4) h = q((unsigned long long)__double_as_longlong(baseline), k);
+        else if (k < 8) h = q((unsigned long long)__double_as_longlong(upstream), k - 4);
+        else if (k < 24) {  // polarity 'unknown' as UTF-32
+            const char* u = "unknown";
+            const int ci = (k - 8) >> 1;
+            h = ((k & 1) == 0 && ci < 7) ? (unsigned short)u[ci] : (unsigned short)0;
+        } else if (k < 28) h = q((unsigned long long)ts[i], k - 24);
+        else if (k < 32) h = q((unsigned long long)(record_base + i), k - 28);
+        else if (k < 34) h = (unsigned short)((unsigned)dt_ns >> (16 * (k - 32)));
+        else if (k < 36) h = (unsigned short)((unsigned)n_copy >> (16 * (k - 34)));
+        else if (k == 36) h = (unsigned short)board[i];
+        else h = (unsigned short)chan[i];
+        dst[k] = h;
+    }
+    unsigned short* w = dst + 38;
+    for (int j = lane; j < wave_len; j += 32) w[j] = j < n_copy ? (unsigned short)src[j] : (unsigned short)0;
+}
+
 }  // namespace wfb
 
 using namespace wfb;
@@ -338,6 +389,24 @@ extern "C" int wfb_group_time_window(const int64_t* ts_sorted_dev, int64_t n, do
     if (rc != WFB_OK) return rc;
     k4_scatter_ids_kernel<<<nb(n), 256, 0, st>>>(incl, nullptr, n, reinterpret_cast<long long*>(event_id_dev),
                                                  reinterpret_cast<long long*>(n_events_dev));
+    WFB_CUDA(cudaGetLastError());
+    return WFB_OK;
+}
+
+extern "C" int wfb_structure_waveforms(const int16_t* samples_dev, const int64_t* ts_dev, const int16_t* board_dev, const int16_t* channel_dev,
+                                       const double* baselines_in_dev, const double* baseline_upstream_dev, int64_t n, int32_t n_samples,
+                                       int32_t wave_length, int32_t bl_start, int32_t bl_end, int32_t dt_ns, int64_t record_base,
+                                       void* rows_out_dev, void* stream) {
+    WFB_REQUIRE(n >= 0 && n_samples >= 0 && wave_length >= 0, "wfb_structure_waveforms: negative size");
+    if (n == 0) return WFB_OK;
+    WFB_REQUIRE(ts_dev && board_dev && channel_dev && rows_out_dev && (samples_dev || n_samples == 0), "wfb_structure_waveforms: NULL pointer");
+    bl_start = std::max(bl_start, 0);
+    bl_end = std::min(bl_end, n_samples);
+    const unsigned blocks = (unsigned)((n * 32 + 255) / 256);
+    st_structure_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(samples_dev, n, n_samples, wave_length,
+                                                                              reinterpret_cast<const long long*>(ts_dev), board_dev, channel_dev,
+                                                                              baselines_in_dev, baseline_upstream_dev, bl_start, bl_end, dt_ns,
+                                                                              static_cast<uint8_t*>(rows_out_dev), record_base);
     WFB_CUDA(cudaGetLastError());
     return WFB_OK;
 }

@@ -889,3 +889,63 @@ def filter_run_device(run: DeviceRun, cfg: dict):
                                    _ptr(d_toff), _ptr(d_out), run.pool_base, _ptr(ws), 0 if ws is None else ws.numel(), L, _stream()),
                "wfb_filter_pool")
     return d_out
+
+
+# --------------------------------------------------------------------------------------------
+# st_waveforms: structured rows with the dual baseline (waveforms.py:644-799)
+# --------------------------------------------------------------------------------------------
+
+
+def structure_waveforms(timestamps_ps, boards, channels, samples, *, dt_ns: int, wave_length: int | None = None, baseline_window=(0, 40),
+                        baselines=None, baseline_upstream=None, record_base: int = 0) -> np.ndarray:
+    """Raw rows (input order) -> ``st_waveforms`` rows (``create_record_dtype(wave_length)``): baseline over the sample
+    window, the upstream baseline carried along (NaN without one), samples truncated / zero padded to ``wave_length``."""
+    from .dtypes import create_record_dtype
+
+    lib = _lib.load()
+    samples = np.ascontiguousarray(samples)
+    if samples.dtype not in (np.int16, np.uint16) or samples.ndim != 2:
+        raise ValueError(f"samples must be a 2-D int16 array, got {samples.dtype} {samples.shape}")
+    n, L = samples.shape
+    wl = int(L if wave_length is None else wave_length)
+    dtype = create_record_dtype(wl)
+    if n == 0:
+        return np.zeros(0, dtype=dtype)
+    d_s = upload(samples.reshape(-1), tail=16)
+    d_ts = _dev(np.asarray(timestamps_ps, dtype=np.int64))
+    d_b = _dev(np.asarray(boards, dtype=np.int16))
+    d_c = _dev(np.asarray(channels, dtype=np.int16))
+    d_bl = _dev(np.asarray(baselines, dtype=np.float64)) if baselines is not None else None
+    d_up = _dev(np.asarray(baseline_upstream, dtype=np.float64)) if baseline_upstream is not None else None
+    rows = _empty(n * dtype.itemsize)
+    _lib.check(lib.wfb_structure_waveforms(_ptr(d_s), _ptr(d_ts), _ptr(d_b), _ptr(d_c), _ptr(d_bl), _ptr(d_up), n, L, wl, int(baseline_window[0]),
+                                           int(baseline_window[1]), int(dt_ns), int(record_base), _ptr(rows), _stream()), "wfb_structure_waveforms")
+    from .engine import to_host
+
+    return to_host(rows[: n * dtype.itemsize]).view(dtype)
+
+
+def build_records_from_st(st: np.ndarray, *, default_dt_ns: int = 1):
+    """records + wave_pool from structured st_waveforms rows (records_builder.py:645-777): time sort and gather on the
+    device, ``baseline`` / ``baseline_upstream`` / ``polarity`` of the rows carried into the records (:676-695).  The
+    device sort gets the source row index in the baseline slot and hands it back in the sorted rows."""
+    names = st.dtype.names or ()
+    n = len(st)
+    if n == 0:
+        return np.zeros(0, dtype=RECORDS_DTYPE), np.zeros(0, dtype=np.uint16)
+    L = st["wave"].shape[1]
+    lens = np.clip(st["event_length"].astype(np.int64), 0, L) if "event_length" in names else np.full(n, L, dtype=np.int64)
+    dts = st["dt"].astype(np.int64) if "dt" in names else np.full(n, int(default_dt_ns), dtype=np.int64)
+    if len(np.unique(dts)) != 1:
+        raise ValueError("build_records_from_st: rows with different dt are not supported on the device")
+    boards = st["board"] if "board" in names else np.zeros(n, np.int16)
+    waves = np.ascontiguousarray(st["wave"])
+    if np.all(lens == L):
+        rec, pool = build_records(st["timestamp"], boards, st["channel"], waves, dt_ns=int(dts[0]), baselines=np.arange(n, dtype=np.float64))
+    else:
+        raise ValueError("build_records_from_st: rows with event_length shorter than the row are not supported on the device")
+    src = rec["baseline"].astype(np.int64)
+    rec["baseline"] = st["baseline"][src] if "baseline" in names else 0.0
+    rec["baseline_upstream"] = st["baseline_upstream"][src] if "baseline_upstream" in names else np.nan
+    rec["polarity"] = st["polarity"][src] if "polarity" in names else "unknown"
+    return rec, pool

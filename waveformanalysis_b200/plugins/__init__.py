@@ -12,6 +12,7 @@ from .hits import B200HitFinderPlugin, B200ThresholdHitPlugin
 from .merge import B200HitMergeClustersPlugin, B200HitMergedComponentsPlugin, B200HitMergePlugin
 from .records import B200RecordsPlugin, B200WavePoolPlugin
 from .streaming import B200SignalPeaksStreamPlugin
+from .waveforms import B200WaveformsPlugin
 from .widths import B200WaveformWidthIntegralPlugin, B200WaveformWidthPlugin
 
 __all__ = [
@@ -29,6 +30,7 @@ __all__ = [
     "B200RecordsPlugin",
     "B200WavePoolPlugin",
     "B200SignalPeaksStreamPlugin",
+    "B200WaveformsPlugin",
     "B200DataFramePlugin",
     "B200PairedEventsPlugin",
     "B200S1S2ClassifierPlugin",

@@ -8,7 +8,7 @@ def b200_default() -> list:
     from . import plugins as P
 
     return [
-        P.B200RecordsPlugin(), P.B200WavePoolPlugin(), P.B200WavePoolFilteredPlugin(), P.B200BasicFeaturesPlugin(),
+        P.B200WaveformsPlugin(), P.B200RecordsPlugin(), P.B200WavePoolPlugin(), P.B200WavePoolFilteredPlugin(), P.B200BasicFeaturesPlugin(),
         P.B200ThresholdHitPlugin(), P.B200HitFinderPlugin(), P.B200WaveformWidthPlugin(), P.B200WaveformWidthIntegralPlugin(),
         P.B200HitMergeClustersPlugin(), P.B200HitMergePlugin(), P.B200HitMergedComponentsPlugin(),
         P.B200HitGroupedPlugin(), P.B200DataFramePlugin(), P.B200GroupedEventsPlugin(), P.B200PairedEventsPlugin(),

@@ -81,11 +81,14 @@ def test_structured_waveform_sources(P, golden):
     assert_rows_match(run(P.B200BasicFeaturesPlugin(), {"filtered_waveforms": stf}, {"use_filtered": True}), golden["stf_bf"], what="stf_bf")
 
 
-def test_wave_pool_filtered_plugin(P, golden):
+def test_wave_pool_filtered_plugin(P, golden, monkeypatch):
     fbase = {"records": golden["filt_records"], "wave_pool": golden["filt_pool"]}
     assert np.allclose(run(P.B200WavePoolFilteredPlugin(), fbase, {}), golden["filt_sg"], rtol=1e-5, atol=1e-3)
     bw = {"filter_type": "BW", "lowcut": 0.01, "highcut": 0.1, "fs": 0.5, "filter_order": 4}
+    assert np.allclose(run(P.B200WavePoolFilteredPlugin(), fbase, bw), golden["filt_bw"], rtol=1e-5, atol=1e-3)
+    monkeypatch.setenv("WFB_BW_EXACT", "1")  # scipy's order of operations without contraction: bit-exact
     assert np.array_equal(run(P.B200WavePoolFilteredPlugin(), fbase, bw), golden["filt_bw"])
+    monkeypatch.delenv("WFB_BW_EXACT")
     mixed = {"channel_config": {"channels": {"0:1": {"filter_type": "BW", "lowcut": 0.02, "highcut": 0.2, "fs": 1.0, "filter_order": 2}}}}
     assert np.allclose(run(P.B200WavePoolFilteredPlugin(), fbase, mixed), golden["filt_mixed"], rtol=1e-5, atol=1e-3)
     with pytest.raises(ValueError):  # the reference's default BW options are invalid (highcut >= fs/2), filtering.py:98-99

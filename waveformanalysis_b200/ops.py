@@ -940,6 +940,8 @@ def build_records_from_st(st: np.ndarray, *, default_dt_ns: int = 1):
         raise ValueError("build_records_from_st: rows with different dt are not supported on the device")
     boards = st["board"] if "board" in names else np.zeros(n, np.int16)
     waves = np.ascontiguousarray(st["wave"])
+    if waves.dtype == np.int16 and waves.size and int(waves.min()) < 0:
+        waves = np.clip(waves, 0, None)  # _clip_wave_to_uint16 (records_builder.py:760-768)
     if np.all(lens == L):
         rec, pool = build_records(st["timestamp"], boards, st["channel"], waves, dt_ns=int(dts[0]), baselines=np.arange(n, dtype=np.float64))
     else:
@@ -948,4 +950,6 @@ def build_records_from_st(st: np.ndarray, *, default_dt_ns: int = 1):
     rec["baseline"] = st["baseline"][src] if "baseline" in names else 0.0
     rec["baseline_upstream"] = st["baseline_upstream"][src] if "baseline_upstream" in names else np.nan
     rec["polarity"] = st["polarity"][src] if "polarity" in names else "unknown"
+    if "record_id" in names and np.all(st["record_id"] >= 0):  # the source ids survive the sort (:742-746)
+        rec["record_id"] = st["record_id"][src]
     return rec, pool

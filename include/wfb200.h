@@ -199,6 +199,16 @@ int wfb_process_host(const void* records_host, int64_t n, const void* pool_host,
                      void* feat_out_host, void* hit_out_host, int64_t hit_cap,
                      int32_t* hit_counts_host, int64_t* n_hits, int64_t chunk_records);
 
+/* The same pipeline, leaving the run RESIDENT: every chunk of the pool is uploaded into its place in pool_keep_dev (room
+ * for pool_len elements, 16-byte aligned, readable up to the next 16-byte boundary) and every chunk's records are unpacked
+ * into meta_keep_dev (n rows), so that later passes over the same run (wave_pool_filtered, widths, a second
+ * configuration) find it in HBM - the device-side counterpart of the records bundle the reference's plugins share
+ * (core/plugins/builtin/cpu/records.py:441-464).  The upload still overlaps the kernels and the copies back. */
+int wfb_process_host_resident(const void* records_host, int64_t n, const void* pool_host, int64_t pool_len,
+                              const wfb_fh_params* params, const wfb_chan_rule* rules_host, void* feat_out_host,
+                              void* hit_out_host, int64_t hit_cap, int32_t* hit_counts_host, int64_t* n_hits,
+                              int64_t chunk_records, void* pool_keep_dev, wfb_rec_meta* meta_keep_dev);
+
 /* wfb_process_host keeps its streams, events and device staging buffers between calls (one set per
  * device, calls on one device are serialised).  This frees the device buffers; the reference has
  * no counterpart (its plugins hold no device state), call it when a Context is done with the GPU. */

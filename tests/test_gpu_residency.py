@@ -103,3 +103,28 @@ def test_without_a_sibling_only_the_own_rows_are_computed(env, golden, monkeypat
     ctx2, plugins = make_ctx(P, {"records": golden["records"], "wave_pool": golden["wave_pool"]}, {"wave_source": "records", "threshold": 15.0})
     assert_rows_match(plugins["hit_threshold"].compute(ctx2, "run"), golden["hits_thr15"], what="hits", float_exact=FX_HIT)
     assert not residency._ROWS
+
+
+@pytest.mark.parametrize("chunk_records", [0, 37])
+def test_host_pipeline_leaves_the_run_resident(env, chunk_records):
+    """wfb_process_host_resident: same rows as the plain host pipeline, and the records + pool it uploaded chunk by
+    chunk are a complete DeviceRun afterwards (second pass from HBM gives the same rows again)."""
+    from waveformanalysis_b200 import engine
+    from waveformanalysis_b200.synth import make_raw_run, records_from_raw
+
+    rec, pool = records_from_raw(make_raw_run(5, 90, 333, seed=5))
+    want = engine.process_host(rec, pool, threshold=12.0, chunk_records=chunk_records)
+    got = engine.process_host(rec, pool, threshold=12.0, chunk_records=chunk_records, keep_resident=True, pinned_results=True)
+    assert np.array_equal(got["features"], want["features"]) and np.array_equal(got["hits"], want["hits"])
+    run = got["run"]
+    assert run.n == len(rec) and run.lmax == 333 and run.dt_range == (int(rec["dt"].min()), int(rec["dt"].max()))
+    assert np.array_equal(run.pool_to_host(), pool)
+    again = run.run_to_host(threshold=12.0)
+    assert np.array_equal(again["features"], want["features"]) and np.array_equal(again["hits"], want["hits"])
+    # records that are not in wave_offset order: the call repeats with per-chunk ranges over every record
+    perm = np.random.default_rng(0).permutation(len(rec))
+    got = engine.process_host(rec[perm], pool, threshold=12.0, chunk_records=41, keep_resident=True)
+    want = engine.process_host(rec[perm], pool, threshold=12.0)
+    assert np.array_equal(got["features"], want["features"]) and np.array_equal(got["hits"], want["hits"])
+    again = got["run"].run_to_host(threshold=12.0)
+    assert np.array_equal(again["hits"], want["hits"])

@@ -145,6 +145,7 @@ PROTOTYPES = {
     "wfb_features_hits": (C.c_int, [_vp, _i64, _vp, _i64, C.POINTER(FHParams), _vp, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "wfb_features_hits_check": (C.c_int, [_vp, _vp]),
     "wfb_process_host": (C.c_int, [_vp, _i64, _vp, _i64, C.POINTER(FHParams), _vp, _vp, _vp, _i64, _vp, C.POINTER(_i64), _i64]),
+    "wfb_process_host_resident": (C.c_int, [_vp, _i64, _vp, _i64, C.POINTER(FHParams), _vp, _vp, _vp, _i64, _vp, C.POINTER(_i64), _i64, _vp, _vp]),
     "wfb_release_cache": (C.c_int, []),
     "wfb_group_abs_windows": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _dbl, _vp, _vp, _vp, _vp, _sz, _vp]),
     "wfb_build_records_ragged": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i64, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),

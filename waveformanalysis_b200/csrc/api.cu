@@ -266,10 +266,13 @@ inline int rec_i32(const uint8_t* row, int off) {
 
 }  // namespace
 
-extern "C" int wfb_process_host(const void* records_host, int64_t n, const void* pool_host, int64_t pool_len,
-                                const wfb_fh_params* params, const wfb_chan_rule* rules_host, void* feat_out_host,
-                                void* hit_out_host, int64_t hit_cap, int32_t* hit_counts_host, int64_t* n_hits,
-                                int64_t chunk_records) {
+// pool_keep / meta_keep: device buffers for the WHOLE pool (pool_len elements, 16-byte aligned, readable to the next
+// 16-byte boundary) and the records' metadata (n rows): every chunk is uploaded / unpacked straight into its place there
+// instead of into the pipeline's slot buffers, so the run is resident in HBM when the call returns.
+static int process_host_impl(const void* records_host, int64_t n, const void* pool_host, int64_t pool_len,
+                             const wfb_fh_params* params, const wfb_chan_rule* rules_host, void* feat_out_host,
+                             void* hit_out_host, int64_t hit_cap, int32_t* hit_counts_host, int64_t* n_hits,
+                             int64_t chunk_records, void* pool_keep, wfb_rec_meta* meta_keep) {
     WFB_REQUIRE(params != nullptr && n_hits != nullptr, "wfb_process_host: NULL params / n_hits");
     WFB_REQUIRE(n >= 0 && pool_len >= 0 && hit_cap >= 0, "wfb_process_host: negative size");
     *n_hits = 0;
@@ -413,28 +416,30 @@ again:
         const long long lo_al = lo & ~7ll;  // keep 16-byte alignment of record starts relative to the pool
         const size_t pool_bytes = (size_t)(hi - lo_al) * esz;
         // (re)allocation waits for the slot's previous work: only ever happens while the buffers grow
-        const bool grow = pool_bytes + 64 > s.pool.cap || (size_t)m * kRecordsRowBytes + 64 > s.rows.cap ||
+        const bool grow = (!pool_keep && pool_bytes + 64 > s.pool.cap) || (size_t)m * kRecordsRowBytes + 64 > s.rows.cap ||
                           wfb_features_hits_workspace_bytes(m) > s.ws.cap;
         if (grow) cleanup();
-        PH_CHECK(s.pool.ensure(pool_bytes + 64));
+        if (!pool_keep) PH_CHECK(s.pool.ensure(pool_bytes + 64));
         PH_CHECK(s.rows.ensure((size_t)m * kRecordsRowBytes + 64));
-        PH_CHECK(s.meta.ensure((size_t)m * sizeof(wfb_rec_meta) + 64));
+        if (!meta_keep) PH_CHECK(s.meta.ensure((size_t)m * sizeof(wfb_rec_meta) + 64));
+        void* const pool_dst = pool_keep ? static_cast<void*>(static_cast<uint8_t*>(pool_keep) + (size_t)lo_al * esz) : s.pool.p;
+        wfb_rec_meta* const meta_dst = meta_keep ? meta_keep + r0 : static_cast<wfb_rec_meta*>(s.meta.p);
         if (do_feat) PH_CHECK(s.feat.ensure((size_t)m * kFeatRowBytes + 64));
         if (do_hits && hit_counts_host) PH_CHECK(s.counts.ensure((size_t)m * 4 + 64));
         PH_CHECK(s.ws.ensure(wfb_features_hits_workspace_bytes(m)));
         // the slot's previous results must have left the device before we overwrite them
         PH_CUDA(cudaStreamWaitEvent(s_copy, s.drained, 0));
         PH_CUDA(cudaStreamWaitEvent(s_copy, s.computed, 0));
-        if (pool_bytes) PH_CUDA(cudaMemcpyAsync(s.pool.p, pool + (size_t)lo_al * esz, pool_bytes, cudaMemcpyHostToDevice, s_copy));
+        if (pool_bytes) PH_CUDA(cudaMemcpyAsync(pool_dst, pool + (size_t)lo_al * esz, pool_bytes, cudaMemcpyHostToDevice, s_copy));
         PH_CUDA(cudaMemcpyAsync(s.rows.p, rows + (size_t)r0 * kRecordsRowBytes, (size_t)m * kRecordsRowBytes, cudaMemcpyHostToDevice, s_copy));
         PH_CUDA(cudaEventRecord(s.copied, s_copy));
         PH_CUDA(cudaStreamWaitEvent(s_comp, s.copied, 0));
         PH_CUDA(cudaStreamWaitEvent(s_comp, s.drained, 0));
-        PH_CHECK(wfb_records_unpack(s.rows.p, m, static_cast<wfb_rec_meta*>(s.meta.p), s_comp));
+        PH_CHECK(wfb_records_unpack(s.rows.p, m, meta_dst, s_comp));
         p.pool_base = params->pool_base + lo_al;
         p.row_base = params->row_base + r0;
         int64_t* tot = static_cast<int64_t*>(d_tot.p);
-        PH_CHECK(wfb_features_hits(s.pool.p, hi - lo_al, static_cast<const wfb_rec_meta*>(s.meta.p), m, &p, s.feat.p,
+        PH_CHECK(wfb_features_hits(pool_dst, hi - lo_al, meta_dst, m, &p, s.feat.p,
                                    d_hits.p, hit_cap, (do_hits && hit_counts_host) ? static_cast<int32_t*>(s.counts.p) : nullptr,
                                    tot + (chunk_idx & 1), tot + ((chunk_idx + 1) & 1), s.ws.p, s.ws.cap, s_comp));
         err_accumulate_kernel<<<1, 1, 0, s_comp>>>(reinterpret_cast<const int*>(static_cast<uint8_t*>(s.ws.p) + 4), run_err);
@@ -484,6 +489,24 @@ again:
 
 namespace wfb {
 void release_peak_scratch();
+}
+
+extern "C" int wfb_process_host(const void* records_host, int64_t n, const void* pool_host, int64_t pool_len,
+                                const wfb_fh_params* params, const wfb_chan_rule* rules_host, void* feat_out_host,
+                                void* hit_out_host, int64_t hit_cap, int32_t* hit_counts_host, int64_t* n_hits,
+                                int64_t chunk_records) {
+    return process_host_impl(records_host, n, pool_host, pool_len, params, rules_host, feat_out_host, hit_out_host, hit_cap,
+                             hit_counts_host, n_hits, chunk_records, nullptr, nullptr);
+}
+
+extern "C" int wfb_process_host_resident(const void* records_host, int64_t n, const void* pool_host, int64_t pool_len,
+                                         const wfb_fh_params* params, const wfb_chan_rule* rules_host, void* feat_out_host,
+                                         void* hit_out_host, int64_t hit_cap, int32_t* hit_counts_host, int64_t* n_hits,
+                                         int64_t chunk_records, void* pool_keep_dev, wfb_rec_meta* meta_keep_dev) {
+    WFB_REQUIRE(n == 0 || (pool_keep_dev && meta_keep_dev), "wfb_process_host_resident: NULL resident buffers");
+    WFB_REQUIRE(((uintptr_t)pool_keep_dev & 15) == 0 && ((uintptr_t)meta_keep_dev & 15) == 0, "wfb_process_host_resident: resident buffers must be 16-byte aligned");
+    return process_host_impl(records_host, n, pool_host, pool_len, params, rules_host, feat_out_host, hit_out_host, hit_cap,
+                             hit_counts_host, n_hits, chunk_records, pool_keep_dev, meta_keep_dev);
 }
 
 extern "C" int wfb_release_cache(void) {

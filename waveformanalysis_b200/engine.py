@@ -228,12 +228,18 @@ def process_host(
     signed_samples: bool = False,
     row_base: int = 0,
     lmax: int | None = None,
+    keep_resident: bool = False,
+    pinned_results: bool = False,
 ) -> dict:
     """Fused pass over host buffers through ``wfb_process_host``.  Returns a dict with
     ``features`` (BASIC_FEATURES_DTYPE), ``hits`` (THRESHOLD_HIT_DTYPE), ``counts`` (int32).
 
     Records are expected in ``wave_offset`` order (what the records plugins produce); any other order works too, the
-    call then runs a second time with the pool range of every chunk taken over all of its records."""
+    call then runs a second time with the pool range of every chunk taken over all of its records.
+
+    ``keep_resident``: the chunks are uploaded into one device buffer that holds the whole pool (``wfb_process_host_resident``)
+    and the result carries ``run``, the DeviceRun of the records + pool now resident in HBM.  ``pinned_results``: the row
+    arrays come from torch's caching pinned allocator (see ``to_host``)."""
     lib = _lib.load()
     _torch()
     rec = packed_records(records, explicit_dt)
@@ -246,11 +252,26 @@ def process_host(
     p = make_params(flags=flags, pool_is_f32=is_f32, height_range=height_range, area_range=area_range,
                     threshold=threshold, left_extension=left_extension, right_extension=right_extension,
                     lmax=max(lmax, 0), n_rules=len(rules), signed_samples=signed_samples, row_base=row_base)
+    torch = _torch()
+
+    def _rows(count, dtype):
+        nbytes = int(count) * dtype.itemsize
+        if pinned_results and (1 << 20) <= nbytes <= PINNED_RESULT_MAX:
+            try:
+                return torch.empty(nbytes, dtype=torch.uint8, pin_memory=True).numpy().view(dtype)
+            except RuntimeError:
+                pass
+        return np.empty(int(count), dtype=dtype)
+
     feat = None
     if features:
-        feat = out_features if out_features is not None else np.empty(n, dtype=BASIC_FEATURES_DTYPE)
+        feat = out_features if out_features is not None else _rows(n, BASIC_FEATURES_DTYPE)
     counts = np.empty(n, dtype=np.int32) if (hits and want_counts) else None
-    cap = int(hit_cap) if hit_cap is not None else max(1024, 4 * n)
+    d_pool = d_meta = None
+    if keep_resident and n:
+        d_pool = torch.empty(len(pool) + 16, dtype=torch.float32 if is_f32 else torch.int16, device="cuda")[: len(pool)]
+        d_meta = torch.empty(n * 48, dtype=torch.uint8, device="cuda")
+    cap = int(hit_cap) if hit_cap is not None else max(1024, 8 * n)
     if out_hits is not None:
         cap = len(out_hits)
     hit_rows = None
@@ -259,15 +280,26 @@ def process_host(
         if out_hits is not None and len(out_hits) >= cap:
             hit_rows = out_hits  # caller-provided (e.g. pinned) output rows
         else:
-            hit_rows = np.empty(cap if hits else 0, dtype=THRESHOLD_HIT_DTYPE)
-        rc = lib.wfb_process_host(_hptr(rec), n, _hptr(pool), len(pool), C.byref(p), _hptr(rules if len(rules) else None),
-                                  _hptr(feat), _hptr(hit_rows if hits and cap else None), cap if hits else 0,
-                                  _hptr(counts), C.byref(n_hits), int(chunk_records))
+            hit_rows = _rows(cap if hits else 0, THRESHOLD_HIT_DTYPE)
+        args = (_hptr(rec), n, _hptr(pool), len(pool), C.byref(p), _hptr(rules if len(rules) else None), _hptr(feat),
+                _hptr(hit_rows if hits and cap else None), cap if hits else 0, _hptr(counts), C.byref(n_hits), int(chunk_records))
+        if d_pool is not None:
+            rc = lib.wfb_process_host_resident(*args, _ptr(d_pool), _ptr(d_meta))
+        else:
+            rc = lib.wfb_process_host(*args)
         _lib.check(rc, "wfb_process_host")
         if not hits or n_hits.value <= cap:
             break
         cap = int(n_hits.value)  # rare: more hits than the initial estimate, run again with room
-    return dict(features=feat, hits=hit_rows[: n_hits.value] if hits else None, counts=counts, n_hits=int(n_hits.value))
+    res = dict(features=feat, hits=hit_rows[: n_hits.value] if hits else None, counts=counts, n_hits=int(n_hits.value))
+    if d_pool is not None:
+        stats = np.zeros(3, dtype=np.int32)
+        scratch = torch.empty(4, dtype=torch.int32, device="cuda")
+        _lib.check(lib.wfb_meta_stats(_ptr(d_meta), n, _ptr(scratch), _hptr(stats), _stream()), "wfb_meta_stats")
+        run = DeviceRun(d_meta, d_pool, n, is_f32, max(int(stats[0]), 0))
+        run.dt_range = (int(stats[1]), int(stats[2]))
+        res["run"] = run
+    return res
 
 
 # --------------------------------------------------------------------------------------------

@@ -125,21 +125,39 @@ def records_pass(plugin: Any, context: Any, run_id: str, spec, records: np.ndarr
             other = None  # the sibling will raise its own error when (if) the Context runs it
     fpar = own if want == "features" else other
     hpar = own if want == "hits" else other
-    run = residency.device_run(run_id, records, pool, pool_name)
-    if want == "hits":
-        check_dt_range(run, plugin.provides)
-    elif hpar is not None and run.dt_range is not None and run.dt_range[0] <= 0:
-        hpar, other = None, None  # the sibling raises its own error when the Context runs it
-    kw: dict = dict(features=fpar is not None, hits=hpar is not None)
-    thresholds, fixed = {}, {}
-    if fpar is not None:
-        kw.update(height_range=fpar["height_range"], area_range=fpar["area_range"])
-        fixed = fpar["fixed_baselines"]
-    if hpar is not None:
-        kw.update(threshold=hpar["threshold"], left_extension=hpar["left_extension"], right_extension=hpar["right_extension"])
-        thresholds = hpar["thresholds"]
-    rules = engine.make_rules(thresholds, fixed)
-    out = run.run_to_host(rules=rules if len(rules) else None, **kw)
+    thresholds = hpar["thresholds"] if hpar is not None else {}
+    fixed = fpar["fixed_baselines"] if fpar is not None else {}
+    run = residency.lookup_run(run_id, records, pool, pool_name, fp)
+    if run is None:
+        # first touch of the run: the chunked host pipeline uploads, computes and copies back concurrently and leaves the
+        # pool + metadata resident (wfb_process_host_resident)
+        residency._evict_for(int(pool.nbytes))
+        kw = dict(features=fpar is not None, hits=hpar is not None, thresholds=thresholds, fixed_baselines=fixed, keep_resident=True,
+                  pinned_results=True)
+        if fpar is not None:
+            kw.update(height_range=fpar["height_range"], area_range=fpar["area_range"])
+        if hpar is not None:
+            kw.update(threshold=hpar["threshold"], left_extension=hpar["left_extension"], right_extension=hpar["right_extension"])
+        out = engine.process_host(records, pool, **kw)
+        run = out["run"]
+        residency.store_run(run_id, records, pool, pool_name, run, fp)
+        bad_dt = run.dt_range is not None and (run.dt_range[0] <= 0 or run.dt_range[1] > np.iinfo(np.int32).max)
+        if want == "hits":
+            check_dt_range(run, plugin.provides)
+        elif bad_dt:
+            other = None  # the sibling raises its own error when the Context runs it
+    else:
+        if want == "hits":
+            check_dt_range(run, plugin.provides)
+        elif hpar is not None and run.dt_range is not None and run.dt_range[0] <= 0:
+            hpar, other = None, None
+        kw = dict(features=fpar is not None, hits=hpar is not None)
+        if fpar is not None:
+            kw.update(height_range=fpar["height_range"], area_range=fpar["area_range"])
+        if hpar is not None:
+            kw.update(threshold=hpar["threshold"], left_extension=hpar["left_extension"], right_extension=hpar["right_extension"])
+        rules = engine.make_rules(thresholds, fixed)
+        out = run.run_to_host(rules=rules if len(rules) else None, **kw)
     if other is not None:
         sib_rows = out["hits"] if want == "features" else out["features"]
         residency.put_rows(run_id, sib_name, _signature(fp, "hits" if want == "features" else "features", other), sib_rows)

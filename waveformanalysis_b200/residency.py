@@ -111,6 +111,31 @@ def device_run(run_id: str, records: np.ndarray, pool: np.ndarray, pool_name: st
         return run
 
 
+def lookup_run(run_id: str, records: np.ndarray, pool: np.ndarray, pool_name: str, fp: tuple | None = None):
+    """The resident DeviceRun of (run_id, pool_name) if it was made from these arrays, else None."""
+    key = (str(run_id), str(pool_name), False, None)
+    fp = fp or fingerprint(records, pool)
+    with _LOCK:
+        ent = _RUNS.get(key)
+        if ent is not None and _same(ent["fp"], fp) and ent["explicit_dt"] is None:
+            _RUNS.move_to_end(key)
+            STATS["hits"] += 1
+            return ent["run"]
+    return None
+
+
+def store_run(run_id: str, records: np.ndarray, pool: np.ndarray, pool_name: str, run, fp: tuple | None = None) -> None:
+    """Register a run that a host pipeline call left resident (one upload, counted as such)."""
+    key = (str(run_id), str(pool_name), False, None)
+    nbytes = int(pool.nbytes + len(records) * (102 + 48))
+    with _LOCK:
+        _RUNS.pop(key, None)
+        _evict_for(0)
+        _RUNS[key] = {"fp": fp or fingerprint(records, pool), "run": run, "bytes": nbytes, "explicit_dt": None}
+        STATS["uploads"] += 1
+        STATS["bytes_uploaded"] += nbytes
+
+
 def adopt_run(run_id: str, records: np.ndarray, pool: np.ndarray, pool_name: str, run, *, signed: bool = False) -> None:
     """Register a DeviceRun whose pool was PRODUCED on the device (records builder, filter) under the host arrays
     that were copied back from it, so that the next plugin finds the device copy instead of uploading the host one."""

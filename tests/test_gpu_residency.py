@@ -127,4 +127,9 @@ def test_host_pipeline_leaves_the_run_resident(env, chunk_records):
     want = engine.process_host(rec[perm], pool, threshold=12.0)
     assert np.array_equal(got["features"], want["features"]) and np.array_equal(got["hits"], want["hits"])
     again = got["run"].run_to_host(threshold=12.0)
-    assert np.array_equal(again["hits"], want["hits"])
+    assert np.array_equal(again["hits"], want["hits"]) and np.array_equal(got["run"].pool_to_host(), pool)
+    # samples that no record refers to are uploaded as well
+    sub = rec[10:-10:3]
+    got = engine.process_host(sub, pool, threshold=12.0, chunk_records=29, keep_resident=True)
+    assert np.array_equal(got["run"].pool_to_host(), pool)
+    assert np.array_equal(got["hits"], engine.process_host(sub, pool, threshold=12.0)["hits"])

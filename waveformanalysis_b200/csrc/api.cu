@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -293,8 +294,19 @@ static int process_host_impl(const void* records_host, int64_t n, const void* po
     // (also without hits: a per-chunk maximum would cost a device round trip per chunk and make the kernel variant
     // depend on the chunk)
     int lmax = params->lmax;
-    if (lmax <= 0) {
-        for (int64_t i = 0; i < n; ++i) lmax = std::max(lmax, rec_i32(rows + i * kRecordsRowBytes, 90));
+    if (lmax <= 0) {  // strided read of 4 of every 102 bytes: a few threads hide the cache misses
+        const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(8, n >> 16));
+        std::vector<int> part(nt, 0);
+        auto scan = [&](int t) {
+            int mx = 0;
+            for (int64_t i = n * t / nt, e = n * (t + 1) / nt; i < e; ++i) mx = std::max(mx, rec_i32(rows + i * kRecordsRowBytes, 90));
+            part[t] = mx;
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; ++t) th.emplace_back(scan, t);
+        scan(0);
+        for (auto& x : th) x.join();
+        for (int v : part) lmax = std::max(lmax, v);
     }
     bool scan_all = false;
 
@@ -377,6 +389,11 @@ again:
         return WFB_OK;
     };
 
+    // resident mode uploads EVERY sample of the pool (also those no record refers to): chunk ranges are stretched to tile
+    // [0, pool_len); records out of wave_offset order get the whole pool in one copy before the first chunk
+    long long keep_hi = 0;
+    if (pool_keep && scan_all && pool_len > 0)
+        PH_CUDA(cudaMemcpyAsync(pool_keep, pool, (size_t)pool_len * esz, cudaMemcpyHostToDevice, s_copy));
     int64_t chunk_idx = 0;
     for (int64_t r0 = 0; r0 < n; r0 += chunk_records, ++chunk_idx) {
         const int64_t r1 = std::min<int64_t>(n, r0 + chunk_records), m = r1 - r0;
@@ -413,8 +430,14 @@ again:
             return WFB_ERR_LAYOUT;
         }
         if (do_hits && hit_out_host && chunk_idx >= 2) PH_CHECK(drain_hits(chunk_idx - 2));
+        if (pool_keep && !scan_all) {
+            lo = std::min(lo, keep_hi);
+            if (r1 == n) hi = pool_len;
+            hi = std::max(hi, lo);
+            keep_hi = std::max(keep_hi, hi);
+        }
         const long long lo_al = lo & ~7ll;  // keep 16-byte alignment of record starts relative to the pool
-        const size_t pool_bytes = (size_t)(hi - lo_al) * esz;
+        const size_t pool_bytes = (pool_keep && scan_all) ? 0 : (size_t)(hi - lo_al) * esz;
         // (re)allocation waits for the slot's previous work: only ever happens while the buffers grow
         const bool grow = (!pool_keep && pool_bytes + 64 > s.pool.cap) || (size_t)m * kRecordsRowBytes + 64 > s.rows.cap ||
                           wfb_features_hits_workspace_bytes(m) > s.ws.cap;

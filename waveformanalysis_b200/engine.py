@@ -247,8 +247,8 @@ def process_host(
     n = len(rec)
     flags = (_lib.DO_FEATURES if features else 0) | (_lib.DO_HITS if hits else 0)
     rules = make_rules(thresholds, fixed_baselines)
-    if lmax is None:  # a shard of a run passes the run-wide maximum (hit_finder.py:364)
-        lmax = int(rec["event_length"].max()) if n else 0
+    if lmax is None:  # a shard of a run passes the run-wide maximum (hit_finder.py:364); 0 = the library scans the rows
+        lmax = 0
     p = make_params(flags=flags, pool_is_f32=is_f32, height_range=height_range, area_range=area_range,
                     threshold=threshold, left_extension=left_extension, right_extension=right_extension,
                     lmax=max(lmax, 0), n_rules=len(rules), signed_samples=signed_samples, row_base=row_base)

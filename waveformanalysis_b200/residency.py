@@ -59,11 +59,21 @@ def _same(fp_a: tuple, fp_b: tuple) -> bool:
     return len(fp_a) == len(fp_b) and all(x[1:] == y[1:] for x, y in zip(fp_a, fp_b))
 
 
-def _device_budget() -> int:
+_TOTAL: dict = {}
+
+
+def _device_total() -> int:
+    """HBM size of the current device (cudaMemGetInfo costs ~3 ms a call: asked once per device)."""
     import torch
 
-    free, total = torch.cuda.mem_get_info()
-    return int(total * MAX_FRACTION)
+    dev = torch.cuda.current_device()
+    if dev not in _TOTAL:
+        _TOTAL[dev] = int(torch.cuda.get_device_properties(dev).total_memory)
+    return _TOTAL[dev]
+
+
+def _device_budget() -> int:
+    return int(_device_total() * MAX_FRACTION)
 
 
 def _evict_for(nbytes: int) -> None:
@@ -74,17 +84,18 @@ def _evict_for(nbytes: int) -> None:
     while _RUNS and used + nbytes > budget:
         _, e = _RUNS.popitem(last=False)
         used -= e["bytes"]
-    free, _ = torch.cuda.mem_get_info()
-    if free < nbytes + (1 << 30):
-        torch.cuda.empty_cache()
+    # memory torch has reserved but not handed out is reusable; only what OTHER users of the device hold is not
+    reserved = torch.cuda.memory_reserved()
+    inside = reserved - torch.cuda.memory_allocated()
+    if inside < nbytes + (1 << 28) and _device_total() - reserved < nbytes + (1 << 30):
+        free, _ = torch.cuda.mem_get_info()
+        if free < nbytes + (1 << 30):
+            torch.cuda.empty_cache()
 
 
 def fits_device(nbytes: int) -> bool:
     """Whether a pool of ``nbytes`` can be made resident at all (else the chunked host pipeline is used)."""
-    import torch
-
-    _, total = torch.cuda.mem_get_info()
-    return nbytes < total * 0.45
+    return nbytes < _device_total() * 0.45
 
 
 def device_run(run_id: str, records: np.ndarray, pool: np.ndarray, pool_name: str, *, explicit_dt=None, signed: bool = False,

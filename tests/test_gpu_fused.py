@@ -354,3 +354,44 @@ def test_host_pipeline_accepts_reordered_records(eng, golden):
     out = eng.process_host(shuffled, pool, threshold=15.0, chunk_records=100)
     assert_rows_match(out["features"], O.basic_features(shuffled, pool), what="shuffled features", float_exact=FX_BF)
     assert_rows_match(out["hits"], O.threshold_hits(shuffled, pool, threshold=15.0), what="shuffled hits", float_exact=FX_HIT)
+
+
+@pytest.mark.parametrize("n_samples,variant", [(800, "auto"), (250, "auto"), (1031, "global"), (64, "auto")])
+def test_float32_pool_vs_oracle(eng, n_samples, variant, monkeypatch):
+    """float32 pools (wave_pool_filtered): the kernel compares raw samples with a per-record float32 bound instead of
+    evaluating b - x >= thr in float64 per sample.  Samples are planted on the bound and one float32 step to either side
+    of it, for all four polarity modes, fractional baselines and ragged record starts."""
+    from oracle import np_oracle as O
+    from waveformanalysis_b200.synth import make_raw_run, records_from_raw
+
+    monkeypatch.setenv("WFB_FUSED_VARIANT", variant)
+    rng = np.random.default_rng(n_samples)
+    raw = make_raw_run(8, 300, n_samples, seed=99 + n_samples)
+    rec, pool = records_from_raw(raw)
+    rec["polarity"][::5] = "negative"
+    rec["polarity"][2::7] = "positive"
+    rec["baseline"] += rng.uniform(-0.5, 0.5, len(rec))
+    poolf = pool.astype(np.float32) + rng.normal(0, 0.3, len(pool)).astype(np.float32)
+    thr = 15.0
+    positive = np.asarray(rec["polarity"]) == "positive"
+    for i in range(len(rec)):  # samples at the float32 neighbours of b -+ thr
+        o, b = int(rec["wave_offset"][i]), float(rec["baseline"][i])
+        x0 = np.float32(b + thr) if positive[i] else np.float32(b - thr)
+        around = [np.nextafter(x0, np.float32(-np.inf)), x0, np.nextafter(x0, np.float32(np.inf))]
+        for k, pos in enumerate(rng.choice(n_samples - 4, size=6, replace=False)):
+            poolf[o + 2 + pos] = around[k % 3]
+    # a ragged view: records that start off the 16-byte grid
+    sub = rec[3:-3:2].copy()
+    sub["wave_offset"] += 3
+    sub["event_length"] -= 5
+    for r_, tag in ((rec, "fixed"), (sub, "ragged")):
+        want_f = O.basic_features(r_, poolf, height_range=(40, 90), area_range=(0, None))
+        want_h = O.threshold_hits(r_, poolf, threshold=thr)
+        out = both_paths(eng, r_, poolf, chunk_records=700, height_range=(40, 90), area_range=(0, None), threshold=thr)
+        assert_rows_match(out["features"], want_f, what=f"{tag} features", float_exact=FX_BF)
+        assert_rows_match(out["hits"], want_h, what=f"{tag} hits", float_exact=("height",))
+        assert len(want_h) > 300
+    # height range that cuts through 8-sample chunks, area range that ends inside the record
+    want_f = O.basic_features(rec, poolf, height_range=(13, n_samples - 9), area_range=(5, -3))
+    out = eng.process_host(rec, poolf, hits=False, height_range=(13, n_samples - 9), area_range=(5, -3))
+    assert_rows_match(out["features"], want_f, what="cut ranges", float_exact=FX_BF)

@@ -52,6 +52,7 @@ struct ScanRec {
     int wlim;
     bool b_small;  // |b_rec| < 2e9: the integer split is usable
     int bias;      // 32768 when the 16-bit samples are int16: the kernel works on w' = w + 32768
+    float xb;      // float32 pools: a sample is above threshold iff x <= xb (negative pulses) / x >= xb (positive); NaN: never
 };
 // what a hit row needs beyond the staged entry
 struct RowRec {

@@ -103,6 +103,47 @@ struct RowSink {  // re-scan of a record whose hits did not fit: write rows stra
     }
 };
 
+// ---- float32 pools: the threshold as a bound on the raw sample ------------------------------
+// hit_finder.py:329-340 compares sig = b - x (negative pulses) or x - b (positive), evaluated in float64, with the
+// threshold.  Rounding is monotone, so the samples that pass are exactly those on one side of a float32 bound: the
+// largest x with fl64(b - x) >= thr, or the smallest x with fl64(x - b) >= thr.  The bound is found once per record
+// from the rounded estimate b -+ thr by stepping over neighbouring floats with the reference's own expression.
+__device__ __forceinline__ float f32_step(float x, bool up) {
+    if (x != x) return x;
+    if (x == 0.f) return __uint_as_float(up ? 1u : 0x80000001u);
+    unsigned u = __float_as_uint(x);
+    const bool pos = (u >> 31) == 0u;
+    if (pos == up) {
+        if ((u & 0x7fffffffu) == 0x7f800000u) return x;  // +-inf stays
+        ++u;
+    } else {
+        --u;
+    }
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ float f32_threshold_bound(double b, double thr, bool positive) {
+    const float qnan = __uint_as_float(0x7fc00000u);
+    if (b != b || thr != thr) return qnan;
+    auto ok = [&](float x) { return (positive ? __dsub_rn((double)x, b) : __dsub_rn(b, (double)x)) >= thr; };
+    float cand = positive ? (float)__dadd_rn(b, thr) : (float)__dsub_rn(b, thr);
+    if (cand != cand) return qnan;
+    // towards the passing side until the candidate passes, then back while the neighbour still passes
+    for (int it = 0; it < 4 && !ok(cand); ++it) cand = f32_step(cand, positive);
+    if (!ok(cand)) return qnan;  // (infinite baselines and the like: no sample is reported)
+    for (int it = 0; it < 4; ++it) {
+        const float nb = f32_step(cand, !positive);
+        if (nb == cand || !ok(nb)) break;
+        cand = nb;
+    }
+    return cand;
+}
+// unsigned key with the order of the floats (-inf lowest); NaN is handled by the callers
+__device__ __forceinline__ unsigned f32_order_key(float x) {
+    const unsigned u = __float_as_uint(x);
+    return (u >> 31) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float f32_from_key(unsigned k) { return __uint_as_float((k >> 31) ? (k ^ 0x80000000u) : ~k); }
+
 // ---- per-hit segment reduction (hit_finder.py:369-381) --------------------------------------
 template <typename T, typename Src, typename Sink>
 __device__ __forceinline__ void emit_hit(const Src& src, const ScanRec& r, const FHArgs& a, int s, int e, Sink& sink) {
@@ -168,18 +209,38 @@ __device__ __forceinline__ void emit_hit(const Src& src, const ScanRec& r, const
         }
         hint = (float)integ;
     } else {
-        double sbest = -DBL_MAX, acc = 0.0;
-        int ibest = INT_MAX;
-        for (int i = a0 + lane; i < a1; i += 32) {
-            double x = (i < r.len) ? (double)src.at(r.mis + i) : 0.0;
-            double sig = positive ? __dsub_rn(x, b) : __dsub_rn(b, x);
-            if (sig > sbest) { sbest = sig; ibest = i; }
-            acc += fmax(sig, 0.0);
+        if (a1 - a0 <= 32) {
+            // one sample per lane: the best sample through an integer min-reduction of the ordered float keys
+            // (sig is monotone in x), its position through a ballot on sig itself (first of equal sig values)
+            const int i = a0 + lane;
+            const bool act = lane < a1 - a0;
+            const float x = (act && i < r.len) ? (float)src.at(r.mis + i) : 0.f;
+            const double sig = positive ? __dsub_rn((double)x, b) : __dsub_rn(b, (double)x);
+            const unsigned key = (!act || x != x) ? 0xffffffffu : f32_order_key(positive ? -x : x);
+            const unsigned kmin = __reduce_min_sync(kFull, key);
+            double smax = -DBL_MAX;
+            hp = INT_MAX;
+            if (kmin != 0xffffffffu) {
+                const float xm = f32_from_key(kmin);
+                smax = positive ? __dsub_rn((double)(-xm), b) : __dsub_rn(b, (double)xm);
+                hp = a0 + __ffs(__ballot_sync(kFull, act && sig == smax)) - 1;
+            }
+            hheight = (float)smax;
+            hint = (float)warp_sum_f64(act ? fmax(sig, 0.0) : 0.0);
+        } else {
+            double sbest = -DBL_MAX, acc = 0.0;
+            int ibest = INT_MAX;
+            for (int i = a0 + lane; i < a1; i += 32) {
+                double x = (i < r.len) ? (double)src.at(r.mis + i) : 0.0;
+                double sig = positive ? __dsub_rn(x, b) : __dsub_rn(b, x);
+                if (sig > sbest) { sbest = sig; ibest = i; }
+                acc += fmax(sig, 0.0);
+            }
+            double smax = warp_max_f64(sbest);
+            hp = __reduce_min_sync(kFull, sbest == smax ? ibest : INT_MAX);
+            hheight = (float)smax;
+            hint = (float)warp_sum_f64(acc);
         }
-        double smax = warp_max_f64(sbest);
-        hp = __reduce_min_sync(kFull, sbest == smax ? ibest : INT_MAX);
-        hheight = (float)smax;
-        hint = (float)warp_sum_f64(acc);
     }
     sink.store(hp, s, e, hheight, hint);
 }
@@ -216,6 +277,11 @@ __device__ __forceinline__ void scan_record(const Src& src, const ScanRec& r, co
     double dsum = 0.0;
     int idiff = 0;
     double ddiff = 0.0;
+    // float32 fast path: |diff| in float32 (what np.diff of a float32 array gives), raw sum of the samples in the area range
+    float fdiff = 0.f;
+    double xsum = 0.0;
+    int nfast = 0;
+    const float xb = r.xb;
     unsigned carry_w = 0;  // last 32-bit word of the previous window (u16: 2 samples, f32: 1 sample)
     bool open = false;
     int run_start = 0;
@@ -314,8 +380,37 @@ __device__ __forceinline__ void scan_record(const Src& src, const ScanRec& r, co
                     }
                 }
             }
+        } else if (!U16 && hi - lo == 8 && (!FEAT || (((p0 <= i0 && p1 >= i0 + 8) || p1 <= p0 || p1 <= i0 || p0 >= i0 + 8) &&
+                                                      ((c0 <= i0 && c1 >= i0 + 8) || c1 <= c0 || c1 <= i0 || c0 >= i0 + 8)))) {
+            // ---------------- float32 fast path: 8 valid samples, each range holds all or none of them ---------
+            const float c[8] = {__uint_as_float(q0.x), __uint_as_float(q0.y), __uint_as_float(q0.z), __uint_as_float(q0.w),
+                                __uint_as_float(q1.x), __uint_as_float(q1.y), __uint_as_float(q1.z), __uint_as_float(q1.w)};
+            if (FEAT) {
+                float d = (i0 > 0) ? fabsf(__fsub_rn(c[0], __uint_as_float(prevw))) : 0.f;
+#pragma unroll
+                for (int j = 1; j < 8; ++j) d = fmaxf(d, fabsf(__fsub_rn(c[j], c[j - 1])));
+                fdiff = fmaxf(fdiff, d);
+                if (p1 > p0 && p0 <= i0 && p1 >= i0 + 8) {
+                    fmin_ = fminf(fmin_, fminf(fminf(fminf(c[0], c[1]), fminf(c[2], c[3])), fminf(fminf(c[4], c[5]), fminf(c[6], c[7]))));
+                    fmax_ = fmaxf(fmax_, fmaxf(fmaxf(fmaxf(c[0], c[1]), fmaxf(c[2], c[3])), fmaxf(fmaxf(c[4], c[5]), fmaxf(c[6], c[7]))));
+                }
+                if (c1 > c0 && c0 <= i0 && c1 >= i0 + 8) {
+                    if (!known) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) xsum += (double)c[j];
+                        nfast += 8;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) dsum += (double)(positive ? __fsub_rn(c[j], b32) : __fsub_rn(b32, c[j]));
+                    }
+                }
+            }
+            if (HITS) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) m8 |= ((positive ? (c[j] >= xb) : (c[j] <= xb)) ? 1u : 0u) << j;
+            }
         } else if (hi > lo) {
-            // ---------------- generic path: partial chunks and the float32 pool ---------------
+            // ---------------- generic path: partial chunks (and float32 chunks on a range boundary) ---------------
             T c[8];
             if (U16) {
                 const unsigned ww[4] = {q0.x, q0.y, q0.z, q0.w};
@@ -348,14 +443,10 @@ __device__ __forceinline__ void scan_record(const Src& src, const ScanRec& r, co
                             if (U16) {
                                 imin = min(imin, (int)c[j]);
                                 imax = max(imax, (int)c[j]);
-                            } else if (!known) {
+                            } else {
+                                // raw extremes; the float32 signal b32 - x / x - b32 is monotone in x and applied at the end
                                 fmin_ = fminf(fmin_, (float)c[j]);
                                 fmax_ = fmaxf(fmax_, (float)c[j]);
-                            } else {
-                                // -signals(): negative -> b32 - x, positive -> x - b32 (float32)
-                                float sv = positive ? __fsub_rn((float)c[j], b32) : __fsub_rn(b32, (float)c[j]);
-                                fmin_ = fminf(fmin_, sv);
-                                fmax_ = fmaxf(fmax_, sv);
                             }
                         }
                     }
@@ -431,7 +522,7 @@ __device__ __forceinline__ void scan_record(const Src& src, const ScanRec& r, co
             int d = max(idiff, (int)max(pdiff & 0xffffu, pdiff >> 16));
             fa.mad = (float)__reduce_max_sync(kFull, d);
         } else {
-            fa.mad = (float)warp_max_f64(ddiff);
+            fa.mad = fmaxf((float)warp_max_f64(ddiff), warp_max_f32(fdiff));
         }
         if (p1 > p0) {
             if (U16) {
@@ -456,8 +547,11 @@ __device__ __forceinline__ void scan_record(const Src& src, const ScanRec& r, co
                     fa.height = rawpos ? (float)__dsub_rn((double)vmax, r.b_feat) : (float)__dsub_rn(r.b_feat, (double)vmin);
                     fa.amp = (float)__dsub_rn((double)vmax, (double)vmin);
                 } else {
-                    fa.height = vmax;
-                    fa.amp = (float)__dsub_rn((double)vmax, (double)vmin);
+                    // -signals(): negative -> b32 - x, positive -> x - b32 (float32)
+                    const float smax = positive ? __fsub_rn(vmax, b32) : __fsub_rn(b32, vmin);
+                    const float smin = positive ? __fsub_rn(vmin, b32) : __fsub_rn(b32, vmax);
+                    fa.height = smax;
+                    fa.amp = (float)__dsub_rn((double)smax, (double)smin);
                 }
             }
         }
@@ -479,6 +573,7 @@ __device__ __forceinline__ void scan_record(const Src& src, const ScanRec& r, co
                 }
                 fa.area = (float)area;
             } else {
+                if (!U16 && nfast) dsum += rawpos ? __dsub_rn(xsum, __dmul_rn((double)nfast, r.b_feat)) : __dsub_rn(__dmul_rn((double)nfast, r.b_feat), xsum);
                 fa.area = (float)warp_sum_f64(dsum);
             }
         }
@@ -572,6 +667,8 @@ __global__ void __launch_bounds__(kWarps * 32) fused_features_hits_kernel(const 
         const int bias = (U16 && a.p.signed_samples) ? 32768 : 0;
         if (HITS && U16 && len > 0)
             kmax = integer_threshold_u16(b_rec, thr, pol == WFB_POL_POSITIVE || pol == WFB_POL_RAW_POSITIVE, bias);
+        float xb = 0.f;
+        if (HITS && !U16 && len > 0) xb = f32_threshold_bound(b_rec, thr, pol == WFB_POL_POSITIVE || pol == WFB_POL_RAW_POSITIVE);
         unsigned copy_bytes = 0;
         if (STAGED && len > 0) {
             copy_bytes = (unsigned)((((long long)mis + len + AL - 1) & ~(long long)(AL - 1)) * (long long)sizeof(T));
@@ -609,6 +706,7 @@ __global__ void __launch_bounds__(kWarps * 32) fused_features_hits_kernel(const 
             r.b_feat = FEAT ? bcast_f64(b_feat, j) : 0.0;
             r.thr = (HITS && !U16) ? bcast_f64(thr, j) : 0.0;
             r.kmax = (HITS && U16) ? __shfl_sync(kFull, kmax, j) : -1;
+            r.xb = (HITS && !U16) ? __shfl_sync(kFull, xb, j) : 0.f;
             r.p0 = FEAT ? __shfl_sync(kFull, p0, j) : 0;
             r.p1 = FEAT ? __shfl_sync(kFull, p1, j) : 0;
             r.c0 = FEAT ? __shfl_sync(kFull, c0, j) : 0;
@@ -742,6 +840,7 @@ __global__ void __launch_bounds__(kWarps * 32) fused_features_hits_kernel(const 
             r.b_feat = 0.0;
             r.thr = bcast_f64(thr, j);
             r.kmax = __shfl_sync(kFull, kmax, j);
+            r.xb = __shfl_sync(kFull, xb, j);
             r.p0 = r.p1 = r.c0 = r.c1 = 0;
             r.bias = bias;
             hit_constants(r);

@@ -79,6 +79,36 @@ def main():
                     out[f"{name}.{col}"] = v
         else:
             out[name] = np.asarray(res)
+    # ---- the streaming side: signal_peaks_stream over the reference's own chunk iterator, hit_threshold_stream ----------
+    from waveform_analysis.core.plugins.builtin.streaming.cpu.signal_peaks import SignalPeaksStreamPlugin
+
+    if mode == "b200":
+        from waveformanalysis_b200.plugins import B200HitThresholdStreamPlugin, B200SignalPeaksStreamPlugin
+
+        peaks_plugin = B200SignalPeaksStreamPlugin()
+        assert isinstance(peaks_plugin, SignalPeaksStreamPlugin)
+    else:
+        peaks_plugin = SignalPeaksStreamPlugin()
+    ctx.register(peaks_plugin, allow_override=True)
+    ctx.set_config({"height": 8.0}, plugin_name="signal_peaks_stream")
+    ctx.get_data(run, "st_waveforms")
+    ctx.get_data(run, "filtered_waveforms")
+    # many chunks per channel: the device pipeline overlaps them
+    chunks = list(peaks_plugin.compute(ctx, run, streaming_config={"chunk_size": 64, "parallel": False}))
+    out["signal_peaks_stream"] = np.concatenate([c.data for c in chunks])
+    out["signal_peaks_stream_bounds"] = np.array([[c.start, c.end] for c in chunks], dtype=np.int64)
+    if mode == "b200":
+        assert peaks_plugin.stream_stats["overlapped_chunks"] > 10, peaks_plugin.stream_stats
+        hs = B200HitThresholdStreamPlugin()
+        ctx.register(hs, allow_override=True)
+        ctx.set_config({"wave_source": "records", "threshold": 12.0, "height_range": (10, 60)}, plugin_name="hit_threshold_stream")
+        hchunks = list(hs.compute(ctx, run, streaming_config={"chunk_size": 500, "required_halo_ns": 2000}))
+        assert len(hchunks) > 5 and hs.stream_stats["overlapped_chunks"] > 3, hs.stream_stats
+        out["hit_threshold_stream"] = np.concatenate([c.data for c in hchunks])
+        out["basic_features_stream"] = np.concatenate([c.metadata["basic_features"] for c in hchunks])
+    else:  # the stream must reproduce the non-streaming rows
+        out["hit_threshold_stream"] = out["hit_threshold"]
+        out["basic_features_stream"] = out["basic_features"]
     np.savez(out_path, **out)
     print("REAL_CONTEXT_DONE", mode, {k: (v.shape, str(v.dtype)[:40]) for k, v in out.items() if "." not in k})
 

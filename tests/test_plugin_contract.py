@@ -186,9 +186,9 @@ def test_registers_in_a_real_context(tmp_path):
 
 @pytest.mark.skipif(not HAVE_REF, reason="reference checkout not available")
 def test_streaming_plugin_runs_inside_the_reference_framework():
-    """B200SignalPeaksStreamPlugin subclasses the reference's streaming plugin and only replaces compute_chunk.
-    Here (no GPU) the device call is replaced by the oracle, so the test covers the host glue: the reference's own
-    chunk iterator, executor and result chunks around our compute_chunk must reproduce the reference rows."""
+    """B200SignalPeaksStreamPlugin subclasses the reference's streaming plugin and replaces its executor by a two-slot
+    device pipeline.  Here (no GPU) the two device hooks are replaced by the oracle, so the test covers the host glue: the
+    reference's own chunk iterator, clipping and result chunks around our pipeline must reproduce the reference rows."""
     code = r"""
 import os, sys
 import numpy as np
@@ -206,9 +206,18 @@ assert issubclass(P.B200SignalPeaksStreamPlugin, SignalPeaksStreamPlugin)
 assert set(P.B200SignalPeaksStreamPlugin.options) == set(SignalPeaksStreamPlugin.options)
 assert P.B200SignalPeaksStreamPlugin.version == SignalPeaksStreamPlugin.version
 
-def fake(st_chunk, filtered_chunk, *, explicit_dt=None, event_offset=0, **kw):
-    return O.stream_find_peaks(list(filtered_chunk["wave"]), st_chunk, **kw)
-ops.find_peaks_stream_chunk = fake
+from waveform_analysis.core.processing.chunk import Chunk
+# no GPU here: the two device hooks of the pipeline are replaced by the oracle, everything around them is the real thing
+def fake_begin(self, chunk, slots, context, run_id, **kw):
+    return O.stream_find_peaks(list(chunk.metadata["filtered_waveforms"]["wave"]), chunk.data, **self.peak_options())
+def fake_end(self, peaks, chunk, context, run_id):
+    if len(peaks) == 0:
+        return None
+    return Chunk(data=peaks, start=int(peaks["timestamp"].min()), end=int(peaks["timestamp"].max()), run_id=run_id,
+                 data_type=self.provides, data_kind=self.output_data_kind, time_field="timestamp")
+P.B200SignalPeaksStreamPlugin.begin_chunk = fake_begin
+P.B200SignalPeaksStreamPlugin.end_chunk = fake_end
+P.B200SignalPeaksStreamPlugin._make_slots = lambda self: None
 
 g = np.load(os.path.join(%(root)r, "tests", "golden", "hit_golden.npz"))
 rec, pool, fp = g["records"], g["pool"], g["filtered_pool"]

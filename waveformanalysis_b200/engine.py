@@ -471,3 +471,109 @@ class DeviceRun:
     def pool_to_host(self) -> np.ndarray:
         a = self.pool.cpu().numpy()
         return a if self.pool_is_f32 else a.view(np.uint16)
+
+
+# --------------------------------------------------------------------------------------------
+# streaming: two device slots, chunk k + 1 uploads while chunk k computes
+# --------------------------------------------------------------------------------------------
+
+
+class StagedChunk:
+    """One chunk on its way through the device: slot buffers + the events that order the copy and the compute stream."""
+
+    def __init__(self):
+        self.slot = 0
+        self.n = 0
+        self.pool_len = 0
+        self.pool_is_f32 = 0
+        self.rows = self.pool = self.meta = None
+        self.copied = self.done = None
+        self.run = None
+        self.out = {}
+
+
+class StreamSlots:
+    """Double-buffered host -> device staging for the streaming plugins (core/plugins/core/streaming.py:447-548 processes
+    one chunk after the other on the host; here the chunks overlap on the device).
+
+    ``stage`` copies a chunk's packed record rows and its sample range into the slot's pinned staging area and enqueues
+    the host-to-device copies on the COPY stream; ``device_run`` makes the compute stream wait for them and unpacks the
+    rows.  A slot is reused two chunks later, after its owner has been finished (``finish`` waits for the slot's ``done``
+    event), so with two slots the upload of chunk k + 1 runs while the kernels of chunk k do."""
+
+    def __init__(self, depth: int = 2):
+        torch = _torch()
+        self.depth = int(depth)
+        self.copy_stream = torch.cuda.Stream()
+        self.compute_stream = torch.cuda.Stream()
+        self._pin = [dict() for _ in range(self.depth)]
+        self._dev = [dict() for _ in range(self.depth)]
+        self._busy = [None] * self.depth
+        self._k = 0
+        self.bytes_uploaded = 0
+        self.chunks = 0
+
+    def _buffer(self, store: dict, name: str, nbytes: int, *, pinned: bool):
+        torch = _torch()
+        t = store.get(name)
+        if t is None or t.numel() < nbytes:
+            cap = max(int(nbytes * 1.25), 1 << 16)
+            t = torch.empty(cap, dtype=torch.uint8, pin_memory=True) if pinned else torch.empty(cap, dtype=torch.uint8, device="cuda")
+            store[name] = t
+        return t
+
+    def stage(self, records_packed: np.ndarray, pool: np.ndarray) -> StagedChunk:
+        torch = _torch()
+        slot = self._k % self.depth
+        self._k += 1
+        prev = self._busy[slot]
+        if prev is not None and prev.done is not None:
+            prev.done.synchronize()  # (already finished by the pipeline; a direct user of the class may not have)
+        st = StagedChunk()
+        st.slot = slot
+        rec = np.ascontiguousarray(records_packed)
+        pool, st.pool_is_f32 = check_pool(pool)
+        st.n, st.pool_len = len(rec), len(pool)
+        nb_rows, nb_pool = rec.nbytes, pool.nbytes
+        pin_rows = self._buffer(self._pin[slot], "rows", nb_rows, pinned=True)
+        pin_pool = self._buffer(self._pin[slot], "pool", nb_pool, pinned=True)
+        d_rows = self._buffer(self._dev[slot], "rows", nb_rows + 64, pinned=False)
+        d_pool = self._buffer(self._dev[slot], "pool", nb_pool + 64, pinned=False)
+        if nb_rows:
+            pin_rows.numpy()[:nb_rows] = rec.view(np.uint8).reshape(-1)
+        if nb_pool:
+            pin_pool.numpy()[:nb_pool] = pool.view(np.uint8).reshape(-1)
+        with torch.cuda.stream(self.copy_stream):
+            if nb_rows:
+                d_rows[:nb_rows].copy_(pin_rows[:nb_rows], non_blocking=True)
+            if nb_pool:
+                d_pool[:nb_pool].copy_(pin_pool[:nb_pool], non_blocking=True)
+            st.copied = torch.cuda.Event()
+            st.copied.record(self.copy_stream)
+        st.rows = d_rows
+        st.pool = d_pool[:nb_pool].view(torch.float32 if st.pool_is_f32 else torch.int16)
+        self._busy[slot] = st
+        self.bytes_uploaded += nb_rows + nb_pool
+        self.chunks += 1
+        return st
+
+    def device_run(self, st: StagedChunk, *, lmax: int, pool_base: int = 0, row_base: int = 0) -> "DeviceRun":
+        """Call inside ``with torch.cuda.stream(slots.compute_stream)``: the DeviceRun of the staged chunk."""
+        torch = _torch()
+        lib = _lib.load()
+        torch.cuda.current_stream().wait_event(st.copied)
+        meta = self._buffer(self._dev[st.slot], "meta", max(st.n, 1) * 48, pinned=False)
+        _lib.check(lib.wfb_records_unpack(_ptr(st.rows), st.n, _ptr(meta), _stream()), "wfb_records_unpack")
+        st.meta = meta
+        st.run = DeviceRun(meta, st.pool, st.n, st.pool_is_f32, int(lmax), records_rows=st.rows, pool_base=int(pool_base), row_base=int(row_base))
+        return st.run
+
+    def mark_done(self, st: StagedChunk) -> None:
+        torch = _torch()
+        st.done = torch.cuda.Event()
+        st.done.record(torch.cuda.current_stream())
+
+    @staticmethod
+    def finish(st: StagedChunk) -> None:
+        if st.done is not None:
+            st.done.synchronize()

@@ -586,23 +586,55 @@ def _find_peaks(records: np.ndarray, pool: np.ndarray, kind: int, *, use_derivat
         return np.zeros(0, dtype=HIT_DTYPE)
     if run is None:
         run = DeviceRun.from_host(records, pool)
+    return find_peaks_collect(find_peaks_launch(run, kind, lmax, use_derivative=use_derivative, height=height, distance=distance,
+                                                prominence=prominence, width=width, threshold=threshold, height_method=height_method,
+                                                height_window_extension=height_window_extension, cumsum_diff=cumsum_diff,
+                                                level_f32=level_f32))
+
+
+def find_peaks_launch(run: DeviceRun, kind: int, lmax: int, *, use_derivative=True, height=30.0, distance=2, prominence=0.7, width=4,
+                      threshold=None, height_method="minmax", height_window_extension=4, cumsum_diff=False, level_f32=False,
+                      cap: int | None = None) -> dict:
+    """Enqueue ``wfb_find_peaks`` for a device-resident run on the current stream; nothing is read back (the streaming
+    backend launches chunk k + 1 before it collects chunk k)."""
+    lib = _lib.load()
+    torch = _torch()
+    n = run.n
     p = _lib.PeakParams(wave_kind=kind, use_derivative=int(bool(use_derivative)), height=float(height), prominence=float(prominence),
                         width=float(width), threshold=float(threshold) if threshold is not None else 0.0,
                         has_threshold=int(threshold is not None), distance=int(distance if distance is not None else 1),
                         height_method=0 if height_method == "minmax" else (2 if cumsum_diff else 1),
                         height_window_extension=int(height_window_extension),
-                        lmax=lmax, level_f32=int(bool(level_f32)))
+                        lmax=int(lmax), level_f32=int(bool(level_f32)))
     ws = _empty(lib.wfb_find_peaks_workspace_bytes(n))
     total = torch.zeros(1, dtype=torch.int64, device="cuda")
-    cap = max(1024, 2 * n)
-    while True:
-        rows = _empty(cap * HIT_DTYPE.itemsize)
-        _lib.check(lib.wfb_find_peaks(_ptr(run.pool), run.pool_len, _ptr(run.meta), n, C.byref(p), _ptr(rows), cap, C.c_void_p(0),
-                                      _ptr(total), _ptr(ws), ws.numel(), _stream()), "wfb_find_peaks")
-        nt = int(total.item())
-        if nt <= cap:
-            return rows[: nt * HIT_DTYPE.itemsize].cpu().numpy().view(HIT_DTYPE).copy()
+    cap = max(1024, 2 * n) if cap is None else int(cap)
+    rows = _empty(cap * 48)
+    _lib.check(lib.wfb_find_peaks(_ptr(run.pool), run.pool_len, _ptr(run.meta), n, C.byref(p), _ptr(rows), cap, C.c_void_p(0),
+                                  _ptr(total), _ptr(ws), ws.numel(), _stream()), "wfb_find_peaks")
+    total_h = torch.empty(1, dtype=torch.int64, pin_memory=True)
+    total_h.copy_(total, non_blocking=True)
+    return dict(run=run, params=p, ws=ws, total=total, total_h=total_h, rows=rows, cap=cap)
+
+
+def find_peaks_collect(job: dict) -> np.ndarray:
+    """Wait for a ``find_peaks_launch`` and return its HIT_DTYPE rows (launches again if the row buffer was too small)."""
+    from .dtypes import HIT_DTYPE
+
+    lib = _lib.load()
+    torch = _torch()
+    torch.cuda.current_stream().synchronize()
+    run, p = job["run"], job["params"]
+    nt = int(job["total_h"][0])
+    rows, cap = job["rows"], job["cap"]
+    while nt > cap:
         cap = nt
+        rows = _empty(cap * HIT_DTYPE.itemsize)
+        job["total"].zero_()
+        _lib.check(lib.wfb_find_peaks(_ptr(run.pool), run.pool_len, _ptr(run.meta), run.n, C.byref(p), _ptr(rows), cap, C.c_void_p(0),
+                                      _ptr(job["total"]), _ptr(job["ws"]), job["ws"].numel(), _stream()), "wfb_find_peaks")
+        nt = int(job["total"].item())
+    return rows[: nt * HIT_DTYPE.itemsize].cpu().numpy().view(HIT_DTYPE).copy()
 
 
 def find_peaks_records(records: np.ndarray, pool: np.ndarray, run: DeviceRun | None = None, **opts) -> np.ndarray:
@@ -647,17 +679,13 @@ def find_peaks_waveforms(data: np.ndarray, *, explicit_dt=None, **opts) -> np.nd
     return _find_peaks(rec, pool, kind, level_f32=level_f32, **opts)
 
 
-def find_peaks_stream_chunk(st_chunk: np.ndarray, filtered_chunk: np.ndarray, *, explicit_dt=None, event_offset=0, use_derivative=True,
-                            height=30.0, distance=2, prominence=0.7, width=4, threshold=None, height_method="diff",
-                            minmax_window_expand=2) -> np.ndarray:
-    """One chunk of signal_peaks_stream (plugins/builtin/streaming/cpu/signal_peaks.py:234-401): metadata from
-    the st_waveforms rows, samples from the filtered rows promoted to float64."""
+def peaks_stream_inputs(st_chunk: np.ndarray, filtered_chunk: np.ndarray, *, explicit_dt=None, event_offset=0, use_derivative=True):
+    """Host side of one signal_peaks_stream chunk: (records rows, float32 pool) or None for an empty chunk."""
     from .aos import structured_as_records
-    from .dtypes import HIT_DTYPE
 
     n = min(len(st_chunk), len(filtered_chunk))
     if n == 0:
-        return np.zeros(0, dtype=HIT_DTYPE)
+        return None
     st_chunk, filtered_chunk = st_chunk[:n], filtered_chunk[:n]
     names = st_chunk.dtype.names or ()
     if filtered_chunk.dtype.names and "wave" in filtered_chunk.dtype.names:
@@ -690,6 +718,20 @@ def find_peaks_stream_chunk(st_chunk: np.ndarray, filtered_chunk: np.ndarray, *,
         raise ValueError("[signal_peaks_stream] dt must be > 0")
     rec["record_id"] = st_chunk["record_id"] if "record_id" in names else int(event_offset) + np.arange(n, dtype=np.int64)
     rec["polarity"] = "unknown"
+    return rec, pool
+
+
+def find_peaks_stream_chunk(st_chunk: np.ndarray, filtered_chunk: np.ndarray, *, explicit_dt=None, event_offset=0, use_derivative=True,
+                            height=30.0, distance=2, prominence=0.7, width=4, threshold=None, height_method="diff",
+                            minmax_window_expand=2) -> np.ndarray:
+    """One chunk of signal_peaks_stream (plugins/builtin/streaming/cpu/signal_peaks.py:234-401): metadata from
+    the st_waveforms rows, samples from the filtered rows promoted to float64."""
+    from .dtypes import HIT_DTYPE
+
+    inp = peaks_stream_inputs(st_chunk, filtered_chunk, explicit_dt=explicit_dt, event_offset=event_offset, use_derivative=use_derivative)
+    if inp is None:
+        return np.zeros(0, dtype=HIT_DTYPE)
+    rec, pool = inp
     return _find_peaks(rec, pool, _lib.WAVE_AOS_F32_AS_F64, use_derivative=use_derivative, height=height, distance=distance,
                        prominence=prominence, width=width, threshold=threshold, height_method=height_method,
                        height_window_extension=minmax_window_expand, cumsum_diff=True)

@@ -11,7 +11,7 @@ from .grouping import B200GroupedEventsPlugin, B200HitGroupedPlugin
 from .hits import B200HitFinderPlugin, B200ThresholdHitPlugin
 from .merge import B200HitMergeClustersPlugin, B200HitMergedComponentsPlugin, B200HitMergePlugin
 from .records import B200RecordsPlugin, B200WavePoolPlugin
-from .streaming import B200SignalPeaksStreamPlugin
+from .streaming import B200HitThresholdStreamPlugin, B200SignalPeaksStreamPlugin
 from .waveforms import B200WaveformsPlugin
 from .widths import B200WaveformWidthIntegralPlugin, B200WaveformWidthPlugin
 
@@ -30,6 +30,7 @@ __all__ = [
     "B200RecordsPlugin",
     "B200WavePoolPlugin",
     "B200SignalPeaksStreamPlugin",
+    "B200HitThresholdStreamPlugin",
     "B200WaveformsPlugin",
     "B200DataFramePlugin",
     "B200PairedEventsPlugin",

@@ -680,7 +680,7 @@ def run_e2e(args, engine, torch, barrier, max_over_ranks, sum_over_ranks, rank):
     pool = pool_pin.numpy().view(np.uint16)
     plugins = {"records": B200RecordsPlugin(), "wave_pool": B200WavePoolPlugin(), "basic_features": B200BasicFeaturesPlugin(),
                "hit_threshold": B200ThresholdHitPlugin()}
-    ctx = PluginContext({"wave_source": "records", "hit_threshold": {"threshold": THRESHOLD}}, plugins)
+    ctx = PluginContext({"wave_source": "records", "hit_threshold": {"threshold": THRESHOLD}, "hit_threshold_stream": {"threshold": THRESHOLD}}, plugins)
 
     def step(k):
         run_id = f"e2e_{k}"
@@ -711,7 +711,33 @@ def run_e2e(args, engine, torch, barrier, max_over_ranks, sum_over_ranks, rank):
     assert ok and n_feats0 == n
     assert residency.STATS["uploads"] - uploads0 == steps and residency.STATS["row_hits"] - rowhits0 == steps, residency.STATS
     n_all = sum_over_ranks(float(n))
+    # the same host arrays through the streaming backend (plugins/streaming.py): time chunks of 262144 records, the upload
+    # of chunk k + 1 overlapping the fused pass of chunk k, hit + feature rows of every chunk back on the host
+    from waveformanalysis_b200.plugins import B200HitThresholdStreamPlugin
+
+    stream = B200HitThresholdStreamPlugin()
+    ctx._results[("stream", "records")] = records
+    ctx._results[("stream", "wave_pool")] = pool
+
+    def stream_pass():
+        rows = 0
+        for chunk in stream.compute(ctx, "stream"):
+            rows += len(chunk.data)
+        return rows
+
+    stream_pass()
+    barrier()
+    t0 = time.perf_counter()
+    rows = stream_pass()
+    barrier()
+    stream_wall = max_over_ranks(time.perf_counter() - t0)
+    assert rows == n_hits0, (rows, n_hits0)
+    ctx._results.clear()
+    stream_leg = {"value": n_all / stream_wall, "unit": UNIT, "chunk_records": int(stream.chunk_size), "chunks": stream.stream_stats["chunks"],
+                  "overlapped_chunks": stream.stream_stats["overlapped_chunks"],
+                  "call": "B200HitThresholdStreamPlugin.compute (hit_threshold_stream): three-slot device pipeline, rows of every chunk to the host"}
     return {
+        "stream": stream_leg,
         "value": n_all * steps / wall,
         "unit": UNIT,
         "h2d_bytes_per_step": int(n * (2 * N_SAMPLES + 102)),

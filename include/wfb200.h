@@ -110,6 +110,15 @@ int wfb_device_info(int* sm_count, int* cc_major, int* cc_minor, char* name, int
 /* Host -> device copy of any host array (pageable, read-only or memory-mapped: what the reference's Context hands to
  * plugins, core/context_execution.py:241-251) followed by a stream synchronise, so the source may be released at once. */
 int wfb_memcpy_h2d(void* dst_dev, const void* src_host, size_t bytes, void* stream);
+/* The same copy without the synchronise, for the streaming backend (core/plugins/core/streaming.py:447-548: chunk k + 1
+ * is uploaded while chunk k computes).  The source must stay valid until the stream has passed the copy; a pageable
+ * source is read before the call returns, a pinned one by DMA later. */
+int wfb_memcpy_h2d_async(void* dst_dev, const void* src_host, size_t bytes, void* stream);
+/* HOST helper of the chunk iteration (core/plugins/core/streaming.py:592-664, core/processing/chunk.py:345-385): one
+ * threaded pass over n packed RECORDS rows.  ts_out[i] = timestamp, end_ps_out[i] = timestamp + max(event_length, 0) * dt *
+ * 1000 (either may be NULL); stats[0..3] = first sample, one past the last sample the rows with event_length > 0 refer to
+ * (0, 0 if there is none), the longest event_length, the smallest dt. */
+int wfb_records_host_scan(const void* records_host, int64_t n, int64_t* ts_out, int64_t* end_ps_out, int64_t* stats);
 
 /* RECORDS_DTYPE rows (102 B packed, device) -> wfb_rec_meta[n].  Replaces the per-record
  * field access of RecordsView (core/data/records_view.py:16-33). */

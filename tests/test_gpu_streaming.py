@@ -1,5 +1,5 @@
 """GPU: the streaming backend (plugins/streaming.py, engine.StreamSlots) - records in time chunks with halo through the
-two-slot device pipeline must give the rows of the non-streaming plugins byte for byte."""
+device pipeline must give the rows of the non-streaming plugins byte for byte."""
 
 import numpy as np
 import pytest

@@ -67,9 +67,11 @@ def test_stream_chunks_cover_every_record_once(run_data, halo_ns):
     assert sorted(set(seg)) == [0, 1, 2] and seg == sorted(seg)
     for c in chunks:
         assert c.start == c.metadata["main_start"] and c.end == c.metadata["main_end"] and c.start < c.end
-    # pipeline order: chunk k + 1 begins before chunk k ends
+    # pipeline order: chunks k + 1 and k + 2 begin before chunk k ends (three slots)
     order = [kind for kind, _ in calls]
-    assert order[:3] == ["begin", "begin", "end"] and order[-2:] == ["end", "end"] and order.count("begin") == order.count("end") == len(chunks)
+    assert order[:4] == ["begin", "begin", "begin", "end"] and order[-3:] == ["end", "end", "end"]
+    assert order.count("begin") == order.count("end") == len(chunks)
+    assert [b for kind, b in calls if kind == "end"] == sorted(b for kind, b in calls if kind == "end")  # results in input order
 
 
 def test_halo_extends_the_input_chunks_inside_their_segment(run_data):
@@ -106,3 +108,23 @@ def test_stream_rejects_other_sources_and_bad_dt(run_data):
     with pytest.raises(ValueError, match="dt must be positive"):
         list(plugin._record_chunks(bad, "run"))
     assert list(plugin._record_chunks(rec[:0], "run")) == []
+
+
+def test_records_host_scan_matches_numpy(run_data):
+    """wfb_records_host_scan is plain host code in the library (no device): columns and ranges equal the numpy ones."""
+    from waveformanalysis_b200 import engine
+
+    rec, _ = run_data
+    rec = np.concatenate([rec] * 80)  # enough rows for several threads
+    rec["event_length"][7] = 0
+    rec["event_length"][11] = -3
+    got = engine.records_host_scan(rec, times=True)
+    ts = rec["timestamp"].astype(np.int64)
+    lens = rec["event_length"].astype(np.int64)
+    assert np.array_equal(got["ts"], ts)
+    assert np.array_equal(got["end"], ts + np.maximum(lens, 0) * rec["dt"].astype(np.int64) * 1000)
+    live = lens > 0
+    assert got["lo"] == rec["wave_offset"][live].min() and got["hi"] == (rec["wave_offset"][live] + lens[live]).max()
+    assert got["lmax"] == lens.max() and got["dt_min"] == rec["dt"].min()
+    empty = engine.records_host_scan(rec[:0])
+    assert (empty["lo"], empty["hi"], empty["lmax"]) == (0, 0, 0)

@@ -36,7 +36,7 @@ def T(label, fn):
     return out
 
 
-for rep in range(3):
+for rep in range(int(os.environ.get("PROBE_HOST_PASSES", "3"))):
     print("--- pass", rep)
     for ck in (1 << 17, 1 << 18, 1 << 19):
         r = T(f"process_host pageable results chunk={ck}", lambda: engine.process_host(records, pool, threshold=15.0, chunk_records=ck))
@@ -76,3 +76,27 @@ pr.enable()
 out = step()
 pr.disable()
 pstats.Stats(pr).sort_stats("cumulative").print_stats(25)
+
+# ---- the streaming backend over the same host arrays
+from waveformanalysis_b200.plugins import B200HitThresholdStreamPlugin
+
+ctx.config["hit_threshold_stream"] = {"threshold": 15.0}
+ctx._results[("stream", "records")] = records
+ctx._results[("stream", "wave_pool")] = pool
+sp = B200HitThresholdStreamPlugin()
+
+
+def stream_pass():
+    rows = 0
+    for chunk in sp.compute(ctx, "stream"):
+        rows += len(chunk.data)
+    return rows
+
+
+for rep in range(3):
+    T("stream pass", stream_pass)
+pr = cProfile.Profile()
+pr.enable()
+stream_pass()
+pr.disable()
+pstats.Stats(pr).sort_stats("cumulative").print_stats(30)

@@ -133,6 +133,8 @@ PROTOTYPES = {
     "wfb_version": (C.c_int, []),
     "wfb_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3 + [C.c_char_p, C.c_int]),
     "wfb_memcpy_h2d": (C.c_int, [_vp, _vp, C.c_size_t, _vp]),
+    "wfb_memcpy_h2d_async": (C.c_int, [_vp, _vp, C.c_size_t, _vp]),
+    "wfb_records_host_scan": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp]),
     "wfb_records_unpack": (C.c_int, [_vp, _i64, _vp, _vp]),
     "wfb_structure_waveforms": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _i64, _vp, _vp]),
     "wfb_meta_set_clamp": (C.c_int, [_vp, _i64, _vp, _vp]),

@@ -154,6 +154,13 @@ extern "C" int wfb_memcpy_h2d(void* dst_dev, const void* src_host, size_t bytes,
     return WFB_OK;
 }
 
+extern "C" int wfb_memcpy_h2d_async(void* dst_dev, const void* src_host, size_t bytes, void* stream) {
+    if (bytes == 0) return WFB_OK;
+    WFB_REQUIRE(dst_dev && src_host, "wfb_memcpy_h2d_async: NULL pointer");
+    WFB_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+    return WFB_OK;
+}
+
 extern "C" const char* wfb_last_error(void) { return g_err; }
 extern "C" int wfb_version(void) { return 100; }
 
@@ -530,6 +537,49 @@ extern "C" int wfb_process_host_resident(const void* records_host, int64_t n, co
     WFB_REQUIRE(((uintptr_t)pool_keep_dev & 15) == 0 && ((uintptr_t)meta_keep_dev & 15) == 0, "wfb_process_host_resident: resident buffers must be 16-byte aligned");
     return process_host_impl(records_host, n, pool_host, pool_len, params, rules_host, feat_out_host, hit_out_host, hit_cap,
                              hit_counts_host, n_hits, chunk_records, pool_keep_dev, meta_keep_dev);
+}
+
+// Host: one threaded pass over packed RECORDS rows (the strided numpy field reads it replaces cost one pass per field)
+extern "C" int wfb_records_host_scan(const void* records_host, int64_t n, int64_t* ts_out, int64_t* end_ps_out, int64_t* stats) {
+    WFB_REQUIRE(n >= 0 && stats != nullptr && (n == 0 || records_host != nullptr), "wfb_records_host_scan: bad arguments");
+    const uint8_t* rows = static_cast<const uint8_t*>(records_host);
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(8, n >> 15));
+    struct Part { long long lo, hi, lmax, dt_min; };
+    std::vector<Part> part(nt, Part{LLONG_MAX, LLONG_MIN, 0, LLONG_MAX});
+    auto scan = [&](int t) {
+        Part p{LLONG_MAX, LLONG_MIN, 0, LLONG_MAX};
+        for (int64_t i = n * t / nt, e = n * (t + 1) / nt; i < e; ++i) {
+            const uint8_t* r = rows + i * kRecordsRowBytes;
+            const long long ts = rec_i64(r, 0), off = rec_i64(r, 82);
+            const long long len = rec_i32(r, 90), dt = rec_i32(r, 72);
+            if (ts_out) ts_out[i] = ts;
+            if (end_ps_out) end_ps_out[i] = ts + std::max<long long>(len, 0) * dt * 1000;
+            if (len > 0) {
+                p.lo = std::min(p.lo, off);
+                p.hi = std::max(p.hi, off + len);
+                p.lmax = std::max(p.lmax, len);
+            }
+            p.dt_min = std::min(p.dt_min, dt);
+        }
+        part[t] = p;
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(scan, t);
+    scan(0);
+    for (auto& x : th) x.join();
+    Part a{LLONG_MAX, LLONG_MIN, 0, LLONG_MAX};
+    for (const Part& p : part) {
+        a.lo = std::min(a.lo, p.lo);
+        a.hi = std::max(a.hi, p.hi);
+        a.lmax = std::max(a.lmax, p.lmax);
+        a.dt_min = std::min(a.dt_min, p.dt_min);
+    }
+    if (a.hi == LLONG_MIN) a.lo = a.hi = 0;  // no row with samples
+    stats[0] = a.lo;
+    stats[1] = a.hi;
+    stats[2] = a.lmax;
+    stats[3] = (n > 0) ? a.dt_min : 0;
+    return WFB_OK;
 }
 
 extern "C" int wfb_release_cache(void) {

@@ -478,6 +478,21 @@ class DeviceRun:
 # --------------------------------------------------------------------------------------------
 
 
+def records_host_scan(records_packed: np.ndarray, *, times: bool = False) -> dict:
+    """One threaded pass over packed RECORDS rows on the host (``wfb_records_host_scan``; no device involved): the sample
+    range the rows refer to, the longest record, the smallest dt and - with ``times`` - the timestamp / end time (ps)
+    columns the chunk iteration needs."""
+    rec = np.ascontiguousarray(records_packed)
+    if rec.dtype != RECORDS_DTYPE:
+        raise ValueError("records_host_scan expects packed RECORDS rows")
+    n = len(rec)
+    ts = np.empty(n, dtype=np.int64) if times else None
+    end = np.empty(n, dtype=np.int64) if times else None
+    stats = np.zeros(4, dtype=np.int64)
+    _lib.check(_lib.load().wfb_records_host_scan(_hptr(rec) if n else C.c_void_p(0), n, _hptr(ts), _hptr(end), _hptr(stats)), "wfb_records_host_scan")
+    return dict(lo=int(stats[0]), hi=int(stats[1]), lmax=int(stats[2]), dt_min=int(stats[3]), ts=ts, end=end)
+
+
 class StagedChunk:
     """One chunk on its way through the device: slot buffers + the events that order the copy and the compute stream."""
 
@@ -496,17 +511,16 @@ class StreamSlots:
     """Double-buffered host -> device staging for the streaming plugins (core/plugins/core/streaming.py:447-548 processes
     one chunk after the other on the host; here the chunks overlap on the device).
 
-    ``stage`` copies a chunk's packed record rows and its sample range into the slot's pinned staging area and enqueues
-    the host-to-device copies on the COPY stream; ``device_run`` makes the compute stream wait for them and unpacks the
-    rows.  A slot is reused two chunks later, after its owner has been finished (``finish`` waits for the slot's ``done``
-    event), so with two slots the upload of chunk k + 1 runs while the kernels of chunk k do."""
+    ``stage`` enqueues the host-to-device copies of a chunk's packed record rows and of its sample range on the COPY
+    stream (into the slot's device buffers); ``device_run`` makes the compute stream wait for them and unpacks the
+    rows.  A slot is reused ``depth`` chunks later, after its owner has been finished (``finish`` waits for the slot's
+    ``done`` event), so the upload of the next chunk(s) runs while the kernels of chunk k do."""
 
     def __init__(self, depth: int = 2):
         torch = _torch()
-        self.depth = int(depth)
+        self.depth = max(2, int(depth))
         self.copy_stream = torch.cuda.Stream()
         self.compute_stream = torch.cuda.Stream()
-        self._pin = [dict() for _ in range(self.depth)]
         self._dev = [dict() for _ in range(self.depth)]
         self._busy = [None] * self.depth
         self._k = 0
@@ -535,21 +549,19 @@ class StreamSlots:
         pool, st.pool_is_f32 = check_pool(pool)
         st.n, st.pool_len = len(rec), len(pool)
         nb_rows, nb_pool = rec.nbytes, pool.nbytes
-        pin_rows = self._buffer(self._pin[slot], "rows", nb_rows, pinned=True)
-        pin_pool = self._buffer(self._pin[slot], "pool", nb_pool, pinned=True)
         d_rows = self._buffer(self._dev[slot], "rows", nb_rows + 64, pinned=False)
         d_pool = self._buffer(self._dev[slot], "pool", nb_pool + 64, pinned=False)
+        # straight from the caller's arrays: DMA at link speed when they are pinned, the driver's staged copy when they are
+        # pageable or memmap views (then the call returns once the source has been read, which is all the slot logic needs)
+        lib = _lib.load()
+        cs = C.c_void_p(self.copy_stream.cuda_stream)
         if nb_rows:
-            pin_rows.numpy()[:nb_rows] = rec.view(np.uint8).reshape(-1)
+            _lib.check(lib.wfb_memcpy_h2d_async(_ptr(d_rows), C.c_void_p(rec.ctypes.data), nb_rows, cs), "wfb_memcpy_h2d_async")
         if nb_pool:
-            pin_pool.numpy()[:nb_pool] = pool.view(np.uint8).reshape(-1)
-        with torch.cuda.stream(self.copy_stream):
-            if nb_rows:
-                d_rows[:nb_rows].copy_(pin_rows[:nb_rows], non_blocking=True)
-            if nb_pool:
-                d_pool[:nb_pool].copy_(pin_pool[:nb_pool], non_blocking=True)
-            st.copied = torch.cuda.Event()
-            st.copied.record(self.copy_stream)
+            _lib.check(lib.wfb_memcpy_h2d_async(_ptr(d_pool), C.c_void_p(pool.ctypes.data), nb_pool, cs), "wfb_memcpy_h2d_async")
+        st.copied = torch.cuda.Event()
+        st.copied.record(self.copy_stream)
+        st.host_refs = (rec, pool)  # keep the sources alive until the copy has run
         st.rows = d_rows
         st.pool = d_pool[:nb_pool].view(torch.float32 if st.pool_is_f32 else torch.int16)
         self._busy[slot] = st

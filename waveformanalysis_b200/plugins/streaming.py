@@ -4,10 +4,10 @@ core/plugins/builtin/streaming/cpu/signal_peaks.py:35-406).
 The reference's ``StreamingPlugin.compute`` walks a chunk iterator and calls ``compute_chunk`` for one chunk after the
 other (optionally on a thread / process pool).  On the GPU the parallel resource is the device, so the backend here keeps
 the protocol - chunks with ``main_start`` / ``main_end`` / ``segment_id`` metadata in, ``Chunk`` objects clipped to the
-main range out, ``compute_chunk`` still callable on its own - and replaces the executor by a two-slot device pipeline:
+main range out, ``compute_chunk`` still callable on its own - and replaces the executor by a device pipeline of three slots:
 
-    chunk k + 1:  host rows -> pinned staging -> H2D on the copy stream           (``begin_chunk``)
-    chunk k    :  kernels on the compute stream, results D2H, clip, yield         (``end_chunk``)
+    chunks k + 1, k + 2:  host rows + sample range -> H2D on the copy stream, kernels queued behind it   (``begin_chunk``)
+    chunk k            :  kernels on the compute stream, rows D2H, clip to the main range, yield        (``end_chunk``)
 
 ``GpuStreamingMixin`` holds that pipeline.  Two plugins use it:
 
@@ -21,6 +21,7 @@ When the reference package is importable the classes derive from its ``Streaming
 
 from __future__ import annotations
 
+from collections import deque
 from types import SimpleNamespace
 from typing import Any, Iterator
 
@@ -108,13 +109,13 @@ else:
 
 
 class GpuStreamingMixin:
-    """Two-slot device pipeline behind the StreamingPlugin protocol.  A subclass provides
+    """Device pipeline of ``pipeline_depth`` slots behind the StreamingPlugin protocol.  A subclass provides
 
     * ``begin_chunk(chunk, slots, context, run_id, **kw)`` - stage the chunk (``slots.stage``) and enqueue its kernels on
       ``slots.compute_stream``; returns a job object, or None to drop the chunk.  Nothing may wait for the device here.
     * ``end_chunk(job, chunk, context, run_id)`` - wait for the job and return the chunk's rows (or a Chunk, or None)."""
 
-    pipeline_depth = 2
+    pipeline_depth = 3  # device slots: one chunk computing / draining, two uploading or queued behind it
     parallel = False  # no executor: chunks overlap on the device, results come out in order
     executor_type = "thread"
 
@@ -143,7 +144,7 @@ class GpuStreamingMixin:
     def _pipeline(self, chunks: Iterator[Any], context: Any, run_id: str, **kwargs):
         slots = self._make_slots()
         self.stream_stats = {"chunks": 0, "bytes_uploaded": 0, "overlapped_chunks": 0}
-        pending = None
+        pending: deque = deque()  # chunks on the device, oldest first (at most pipeline_depth - 1 besides the one just begun)
 
         def emit(item):
             job, chunk = item
@@ -155,16 +156,16 @@ class GpuStreamingMixin:
 
         try:
             for chunk in chunks:
-                job = self.begin_chunk(chunk, slots, context, run_id, **kwargs)  # upload + launch of chunk k + 1 ...
-                if pending is not None:
-                    if job is not None and pending[0] is not None:
-                        self.stream_stats["overlapped_chunks"] += 1
-                    out = emit(pending)                                           # ... while chunk k finishes
+                job = self.begin_chunk(chunk, slots, context, run_id, **kwargs)  # upload + launch of the newest chunk ...
+                if job is not None and any(j is not None for j, _ in pending):
+                    self.stream_stats["overlapped_chunks"] += 1
+                pending.append((job, chunk))
+                if len(pending) >= max(2, int(self.pipeline_depth)):
+                    out = emit(pending.popleft())                                 # ... while the oldest one finishes
                     if out is not None:
                         yield out
-                pending = (job, chunk)
-            if pending is not None:
-                out = emit(pending)
+            while pending:
+                out = emit(pending.popleft())
                 if out is not None:
                     yield out
         finally:
@@ -311,24 +312,29 @@ class B200HitThresholdStreamPlugin(GpuStreamingMixin, _StreamBase):
         cc = context.get_config(self, "channel_config")
         thr = per_channel_option(cc, run_id, boards, channels, "threshold", threshold)
         fixed = per_channel_option(cc, run_id, boards, channels, "fixed_baseline", None)
-        lens = np.asarray(records["event_length"])
+        lmax = engine.records_host_scan(records)["lmax"] if records.dtype == RECORDS_DTYPE else int(np.asarray(records["event_length"]).max(initial=0))
         return dict(threshold=threshold, left_extension=max(0, int(context.get_config(self, "left_extension"))),
                     right_extension=max(0, int(context.get_config(self, "right_extension"))),
                     rules=engine.make_rules({k: float(v) for k, v in thr.items() if float(v) != threshold},
                                             {k: float(v) for k, v in fixed.items() if v is not None}),
                     height_range=tuple(context.get_config(self, "height_range")), area_range=tuple(context.get_config(self, "area_range")),
                     with_features=bool(context.get_config(self, "with_features")),
-                    lmax=int(lens.max()) if len(lens) else 0)  # the padded width is the run's, not the chunk's (hit_finder.py:364)
+                    lmax=lmax)  # the padded width is the run's, not the chunk's (hit_finder.py:364)
 
     def _record_chunks(self, records: np.ndarray, run_id: str) -> Iterator[Any]:
         n = len(records)
         if n == 0:
             return
-        ts = np.asarray(records["timestamp"]).astype(np.int64)
-        dt = np.asarray(records["dt"]).astype(np.int64)
-        if np.any(dt <= 0):
+        if records.dtype == RECORDS_DTYPE:  # one threaded pass in the library instead of a strided numpy pass per field
+            scan = engine.records_host_scan(records, times=True)
+            ts, end, dt_min = scan["ts"], scan["end"], scan["dt_min"]
+        else:
+            ts = np.asarray(records["timestamp"]).astype(np.int64)
+            dt = np.asarray(records["dt"]).astype(np.int64)
+            dt_min = int(dt.min())
+            end = ts + np.maximum(np.asarray(records["event_length"]).astype(np.int64), 0) * dt * 1000  # ps (chunk.py:345-385)
+        if dt_min <= 0:
             raise ValueError(f"[{self.provides}] records.dt must be positive for every row")
-        end = ts + np.maximum(np.asarray(records["event_length"]).astype(np.int64), 0) * dt * 1000  # ps (chunk.py:345-385)
         run_end = np.maximum.accumulate(end)
         bounds = [0, n]
         if self.break_threshold_ps and self.break_threshold_ps > 0 and n > 1:
@@ -369,11 +375,8 @@ class B200HitThresholdStreamPlugin(GpuStreamingMixin, _StreamBase):
             pool = self._pool = wave_input.wave_pool
             cfg = self._run_cfg = self._load_run_config(context, run_id, wave_input.records)
         rec = engine.packed_records(rows, None)
-        lens = rec["event_length"].astype(np.int64)
-        offs = rec["wave_offset"].astype(np.int64)
-        live = lens > 0
-        lo = int(offs[live].min()) if live.any() else 0
-        hi = int((offs[live] + lens[live]).max()) if live.any() else 0
+        scan = engine.records_host_scan(rec)
+        lo, hi = scan["lo"], scan["hi"]
         if lo < 0 or hi > len(pool):
             raise ValueError("records reference samples outside wave_pool bounds")
         lo_al = lo & ~7  # record starts keep their 16-byte phase relative to the slot

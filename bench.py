@@ -500,8 +500,11 @@ def run_ours(args):
 
 
 def _timed(torch, fn, reps=3):
-    """Average device time of fn() in ms (CUDA events on the current stream, one untimed call first)."""
-    fn()
+    """Average device time of fn() in ms (CUDA events on the current stream).  Two untimed calls first, the result held
+    the way the timed loop holds it: fn() allocates its output, and while one result is alive the next call needs a second
+    block - a cudaMalloc of several GB inside the timed region otherwise."""
+    r = fn()
+    r = fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

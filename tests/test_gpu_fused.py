@@ -356,8 +356,9 @@ def test_host_pipeline_accepts_reordered_records(eng, golden):
     assert_rows_match(out["hits"], O.threshold_hits(shuffled, pool, threshold=15.0), what="shuffled hits", float_exact=FX_HIT)
 
 
-@pytest.mark.parametrize("n_samples,variant", [(800, "auto"), (250, "auto"), (1031, "global"), (64, "auto")])
-def test_float32_pool_vs_oracle(eng, n_samples, variant, monkeypatch):
+@pytest.mark.parametrize("n_samples,variant,impl", [(800, "auto", "lane"), (250, "auto", "lane"), (1031, "auto", "lane"), (64, "auto", "lane"),
+                                                    (800, "auto", "warp"), (250, "auto", "warp"), (1031, "global", "warp"), (64, "auto", "warp")])
+def test_float32_pool_vs_oracle(eng, n_samples, variant, impl, monkeypatch):
     """float32 pools (wave_pool_filtered): the kernel compares raw samples with a per-record float32 bound instead of
     evaluating b - x >= thr in float64 per sample.  Samples are planted on the bound and one float32 step to either side
     of it, for all four polarity modes, fractional baselines and ragged record starts."""
@@ -365,6 +366,7 @@ def test_float32_pool_vs_oracle(eng, n_samples, variant, monkeypatch):
     from waveformanalysis_b200.synth import make_raw_run, records_from_raw
 
     monkeypatch.setenv("WFB_FUSED_VARIANT", variant)
+    monkeypatch.setenv("WFB_F32_IMPL", impl)  # lane: lane-per-record kernel (fused_f32.cuh), warp: warp-per-record kernel
     rng = np.random.default_rng(n_samples)
     raw = make_raw_run(8, 300, n_samples, seed=99 + n_samples)
     rec, pool = records_from_raw(raw)

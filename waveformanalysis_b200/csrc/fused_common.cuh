@@ -240,6 +240,47 @@ __device__ __forceinline__ long long tile_lookback(const FHArgs& a, int tile, lo
     return tile_resolve(a, tile, total);
 }
 
+// ---- float32 pools: the threshold as a bound on the raw sample ------------------------------
+// hit_finder.py:329-340 compares sig = b - x (negative pulses) or x - b (positive), evaluated in float64, with the
+// threshold.  Rounding is monotone, so the samples that pass are exactly those on one side of a float32 bound: the
+// largest x with fl64(b - x) >= thr, or the smallest x with fl64(x - b) >= thr.  The bound is found once per record
+// from the rounded estimate b -+ thr by stepping over neighbouring floats with the reference's own expression.
+__device__ __forceinline__ float f32_step(float x, bool up) {
+    if (x != x) return x;
+    if (x == 0.f) return __uint_as_float(up ? 1u : 0x80000001u);
+    unsigned u = __float_as_uint(x);
+    const bool pos = (u >> 31) == 0u;
+    if (pos == up) {
+        if ((u & 0x7fffffffu) == 0x7f800000u) return x;  // +-inf stays
+        ++u;
+    } else {
+        --u;
+    }
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ float f32_threshold_bound(double b, double thr, bool positive) {
+    const float qnan = __uint_as_float(0x7fc00000u);
+    if (b != b || thr != thr) return qnan;
+    auto ok = [&](float x) { return (positive ? __dsub_rn((double)x, b) : __dsub_rn(b, (double)x)) >= thr; };
+    float cand = positive ? (float)__dadd_rn(b, thr) : (float)__dsub_rn(b, thr);
+    if (cand != cand) return qnan;
+    // towards the passing side until the candidate passes, then back while the neighbour still passes
+    for (int it = 0; it < 4 && !ok(cand); ++it) cand = f32_step(cand, positive);
+    if (!ok(cand)) return qnan;  // (infinite baselines and the like: no sample is reported)
+    for (int it = 0; it < 4; ++it) {
+        const float nb = f32_step(cand, !positive);
+        if (nb == cand || !ok(nb)) break;
+        cand = nb;
+    }
+    return cand;
+}
+// unsigned key with the order of the floats (-inf lowest); NaN is handled by the callers
+__device__ __forceinline__ unsigned f32_order_key(float x) {
+    const unsigned u = __float_as_uint(x);
+    return (u >> 31) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float f32_from_key(unsigned k) { return __uint_as_float((k >> 31) ? (k ^ 0x80000000u) : ~k); }
+
 __device__ __forceinline__ long long bcast_i64(long long v, int src) {
     int lo = __shfl_sync(kFull, (int)(v & 0xffffffffll), src);
     int hi = __shfl_sync(kFull, (int)(v >> 32), src);

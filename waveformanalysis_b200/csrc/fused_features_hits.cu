@@ -103,47 +103,6 @@ struct RowSink {  // re-scan of a record whose hits did not fit: write rows stra
     }
 };
 
-// ---- float32 pools: the threshold as a bound on the raw sample ------------------------------
-// hit_finder.py:329-340 compares sig = b - x (negative pulses) or x - b (positive), evaluated in float64, with the
-// threshold.  Rounding is monotone, so the samples that pass are exactly those on one side of a float32 bound: the
-// largest x with fl64(b - x) >= thr, or the smallest x with fl64(x - b) >= thr.  The bound is found once per record
-// from the rounded estimate b -+ thr by stepping over neighbouring floats with the reference's own expression.
-__device__ __forceinline__ float f32_step(float x, bool up) {
-    if (x != x) return x;
-    if (x == 0.f) return __uint_as_float(up ? 1u : 0x80000001u);
-    unsigned u = __float_as_uint(x);
-    const bool pos = (u >> 31) == 0u;
-    if (pos == up) {
-        if ((u & 0x7fffffffu) == 0x7f800000u) return x;  // +-inf stays
-        ++u;
-    } else {
-        --u;
-    }
-    return __uint_as_float(u);
-}
-__device__ __forceinline__ float f32_threshold_bound(double b, double thr, bool positive) {
-    const float qnan = __uint_as_float(0x7fc00000u);
-    if (b != b || thr != thr) return qnan;
-    auto ok = [&](float x) { return (positive ? __dsub_rn((double)x, b) : __dsub_rn(b, (double)x)) >= thr; };
-    float cand = positive ? (float)__dadd_rn(b, thr) : (float)__dsub_rn(b, thr);
-    if (cand != cand) return qnan;
-    // towards the passing side until the candidate passes, then back while the neighbour still passes
-    for (int it = 0; it < 4 && !ok(cand); ++it) cand = f32_step(cand, positive);
-    if (!ok(cand)) return qnan;  // (infinite baselines and the like: no sample is reported)
-    for (int it = 0; it < 4; ++it) {
-        const float nb = f32_step(cand, !positive);
-        if (nb == cand || !ok(nb)) break;
-        cand = nb;
-    }
-    return cand;
-}
-// unsigned key with the order of the floats (-inf lowest); NaN is handled by the callers
-__device__ __forceinline__ unsigned f32_order_key(float x) {
-    const unsigned u = __float_as_uint(x);
-    return (u >> 31) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float f32_from_key(unsigned k) { return __uint_as_float((k >> 31) ? (k ^ 0x80000000u) : ~k); }
-
 // ---- per-hit segment reduction (hit_finder.py:369-381) --------------------------------------
 template <typename T, typename Src, typename Sink>
 __device__ __forceinline__ void emit_hit(const Src& src, const ScanRec& r, const FHArgs& a, int s, int e, Sink& sink) {
@@ -1016,10 +975,11 @@ extern "C" int wfb_features_hits(const void* pool_dev, int64_t pool_len, const w
         WFB_CUDA(cudaStreamSynchronize(st));
         a.lmax = h_l;
     }
-    if (params->pool_is_f32) return launch_fused<float>(a, flags, st);
-    // 16-bit pools: lane-per-record kernel when the records fit its shared-memory slots
+    // lane-per-record kernel (16-bit pools: block items; float32 pools: register-resident runs) when the records fit
+    // its shared-memory slots and the extensions its hit state
     const int rc = launch_lpr(a, flags, st);
     if (rc != 1) return rc;
+    if (params->pool_is_f32) return launch_fused<float>(a, flags, st);
     return launch_fused<uint16_t>(a, flags, st);
 }
 

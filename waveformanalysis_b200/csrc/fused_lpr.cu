@@ -27,6 +27,7 @@
 //
 // Reference semantics: see fused_features_hits.cu (same arithmetic, same results).
 #include <cuda.h>
+#include <float.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -65,6 +66,7 @@ struct LaneRec {  // everything a lane knows about its record
     double b_rec, b_feat, thr;
     int kmax;
     int wlim;  // integer bound of the samples on the signal side of the baseline (hit integral)
+    float xb;  // float32 pools: above threshold <=> x <= xb (negative pulses) / x >= xb (positive); NaN: never
     bool positive, degen;
 };
 
@@ -139,6 +141,7 @@ struct PoolSink {  // hits of the tile being streamed: the warp's half of its L2
     WarpHits* ws;
     uint4* ent;
     int cap;
+    unsigned long long policy;  // L2 evict-last descriptor, created once per tile
     __device__ __forceinline__ void prepare(int, const LaneRec&) {}
     __device__ __forceinline__ void store(int p, int s, int e, int kbest, unsigned cnt, unsigned sw, int ord, int owner, const FHArgs&) {
         int idx = atomicAdd(&ws->pool_cnt, 1);
@@ -146,7 +149,19 @@ struct PoolSink {  // hits of the tile being streamed: the warp's half of its L2
             st_pool(ent + idx,
                     make_uint4((unsigned)p | ((unsigned)s << 16), (unsigned)e | ((unsigned)owner << 16) | ((unsigned)ord << 21),
                                (unsigned)kbest | (cnt << 16), sw),
-                    l2_policy_evict_last());
+                    policy);
+        } else {
+            atomicOr(&ws->ovf, 1u << owner);
+        }
+    }
+    // float32 pools: height and integral are final already
+    __device__ __forceinline__ void store_f32(int p, int s, int e, float height, float integral, int ord, int owner, const FHArgs&) {
+        int idx = atomicAdd(&ws->pool_cnt, 1);
+        if (idx < cap) {
+            st_pool(ent + idx,
+                    make_uint4((unsigned)p | ((unsigned)s << 16), (unsigned)e | ((unsigned)owner << 16) | ((unsigned)ord << 21),
+                               __float_as_uint(height), __float_as_uint(integral)),
+                    policy);
         } else {
             atomicOr(&ws->ovf, 1u << owner);
         }
@@ -177,6 +192,16 @@ struct DirectSink {  // rows straight to the output (records whose hits did not 
         if (active && row < a.hit_cap) {
             float height, integral;
             hit_values(kbest, cnt, sw, pos, b, bias, height, integral);
+            unsigned w[15];
+            hit_row_words(w, p, s, e, height, integral, rr, a.p.left_extension, a.p.right_extension, a.lmax);
+            unsigned* dst = reinterpret_cast<unsigned*>(a.hit_out + row * kHitRowBytes);
+#pragma unroll
+            for (int k = 0; k < 15; ++k) dst[k] = w[k];
+        }
+    }
+    __device__ __forceinline__ void store_f32(int p, int s, int e, float height, float integral, int ord, int, const FHArgs& a) {
+        long long row = row0 + ord;
+        if (active && row < a.hit_cap) {
             unsigned w[15];
             hit_row_words(w, p, s, e, height, integral, rr, a.p.left_extension, a.p.right_extension, a.lmax);
             unsigned* dst = reinterpret_cast<unsigned*>(a.hit_out + row * kHitRowBytes);
@@ -717,13 +742,18 @@ __device__ __forceinline__ void lpr_stream(const FHArgs& a, const uint16_t* pool
 }  // namespace wfb
 
 #include "fused_blk.cuh"
+#include "fused_f32.cuh"
 
 namespace wfb {
 
 // ---- the kernel --------------------------------------------------------------------------------
 // BLK: block-granular items copied to a shared-memory ring (fused_blk.cuh); else chunk-granular items re-read from L2
-template <bool FEAT, bool HITS, bool SGN, bool EXT22, bool BLK>
-__global__ void __launch_bounds__(kLprWarps * 32, (HITS && !FEAT) ? WFB_LPR_MINBLOCKS + 1 : WFB_LPR_MINBLOCKS) lpr_kernel(const FHArgs a, const int sc, const __grid_constant__ CUtensorMap tmap,
+// F32: the pool holds float32 samples (fused_f32.cuh); SGN / EXT22 / BLK do not apply then
+#ifndef WFB_F32_MINBLOCKS
+#define WFB_F32_MINBLOCKS 4  // float32 pools: the register-resident hit state is small, more warps hide its latencies
+#endif
+template <bool FEAT, bool HITS, bool SGN, bool EXT22, bool BLK, bool F32 = false>
+__global__ void __launch_bounds__(kLprWarps * 32, F32 ? WFB_F32_MINBLOCKS : ((HITS && !FEAT) ? WFB_LPR_MINBLOCKS + 1 : WFB_LPR_MINBLOCKS)) lpr_kernel(const FHArgs a, const int sc, const __grid_constant__ CUtensorMap tmap,
                                                              const int have_tmap, const int ent_cap) {
     extern __shared__ __align__(128) uint8_t dyn_smem[];  // [warp][kNBuf][lane] slots of a.slot_bytes, then the block-item rings
     __shared__ __align__(16) WarpHits s_hits[HITS ? kLprWarps : 1];
@@ -779,7 +809,12 @@ __global__ void __launch_bounds__(kLprWarps * 32, (HITS && !FEAT) ? WFB_LPR_MINB
                     RowRec rr;
                     rr.ts = d.ts; rr.rid = d.rid; rr.len = d.len; rr.dt = d.dt; rr.bc = d.bc;
                     float height, integral;
-                    hit_values((int)(h.z & 0xffffu), h.z >> 16, h.w, (d.rel_pos & 1u) != 0, d.b, c_bias, height, integral);
+                    if constexpr (F32) {
+                        height = __uint_as_float(h.z);
+                        integral = __uint_as_float(h.w);
+                    } else {
+                        hit_values((int)(h.z & 0xffffu), h.z >> 16, h.w, (d.rel_pos & 1u) != 0, d.b, c_bias, height, integral);
+                    }
                     unsigned w[15];
                     hit_row_words(w, (int)(h.x & 0xffffu), (int)(h.x >> 16), (int)(h.y & 0xffffu), height, integral, rr,
                                   a.p.left_extension, a.p.right_extension, a.lmax);
@@ -839,7 +874,7 @@ __global__ void __launch_bounds__(kLprWarps * 32, (HITS && !FEAT) ? WFB_LPR_MINB
             }
         }
         if (r.clen < 0) r.clen = r.len;
-        r.mis = (int)(r.off & 7);
+        r.mis = (int)(r.off & (F32 ? 3 : 7));
         r.bias = a.p.signed_samples ? 32768 : 0;
         r.positive = r.pol == WFB_POL_POSITIVE || r.pol == WFB_POL_RAW_POSITIVE;
         const bool rawpos = r.pol == WFB_POL_RAW_POSITIVE;
@@ -851,8 +886,11 @@ __global__ void __launch_bounds__(kLprWarps * 32, (HITS && !FEAT) ? WFB_LPR_MINB
         }
         r.kmax = -1;
         r.wlim = 0;
+        r.xb = 0.f;
         r.degen = r.thr < 0.0;
-        if (HITS && r.len > 0) {
+        if (HITS && F32) {
+            if (r.len > 0) r.xb = f32_threshold_bound(r.b_rec, r.thr, r.positive);
+        } else if (HITS && r.len > 0) {
             r.kmax = integer_threshold_u16(r.b_rec, r.thr, r.positive, r.bias);
             const double bi = floor(r.b_rec);
             const int ib = (fabs(r.b_rec) < 2e9) ? (int)bi : (r.b_rec > 0 ? INT_MAX - 65536 : INT_MIN + 65536);
@@ -874,15 +912,38 @@ __global__ void __launch_bounds__(kLprWarps * 32, (HITS && !FEAT) ? WFB_LPR_MINB
             if (lane == 0) { ws.pool_cnt = 0; ws.ovf = 0u; }
         }
         __syncwarp();
-        PoolSink psink{&ws, gp + (size_t)cur * a.gpool_cap, ent_cap};
-        if constexpr (HITS && BLK) blk_stream<FEAT, SGN>(a, pool, r, sc, ring, p0, p1, c0, c1, fs, ws, bq, psink);
+        PoolSink psink{&ws, gp + (size_t)cur * a.gpool_cap, ent_cap, l2_policy_evict_last()};
+        FeatF32 ff;
+        ff.fmin = FLT_MAX; ff.fmax = -FLT_MAX; ff.fdiff = 0.f; ff.prev = 0.f; ff.xsum = 0.0; ff.dsum = 0.0; ff.nraw = 0;
+        if constexpr (F32) f32_stream<FEAT, HITS>(a, static_cast<const float*>(a.pool), r, sc, ring, p0, p1, c0, c1, ff, ws, psink);
+        else if constexpr (HITS && BLK) blk_stream<FEAT, SGN>(a, pool, r, sc, ring, p0, p1, c0, c1, fs, ws, bq, psink);
         else lpr_stream<FEAT, HITS, SGN, EXT22>(a, pool, r, sc, ring, p0, p1, c0, c1, fs, ws, cq, psink);
 
         // ---------------- features of my record
         if (FEAT && have) {
             const float b32 = (float)r.b_feat;
             float height = 0.f, amp = 0.f, area = 0.f;
-            const float mad = (float)max(fs.idiff, (int)max(fs.pdiff & 0xffffu, fs.pdiff >> 16));
+            float mad = 0.f;
+            if constexpr (F32) {  // as fused_features_hits.cu, float32 samples (basic_features.py:142-278)
+                mad = ff.fdiff;
+                if (p1 > p0) {
+                    if (!known) {
+                        height = rawpos ? (float)__dsub_rn((double)ff.fmax, r.b_feat) : (float)__dsub_rn(r.b_feat, (double)ff.fmin);
+                        amp = (float)__dsub_rn((double)ff.fmax, (double)ff.fmin);
+                    } else {
+                        const float smax = r.positive ? __fsub_rn(ff.fmax, b32) : __fsub_rn(b32, ff.fmin);
+                        const float smin = r.positive ? __fsub_rn(ff.fmin, b32) : __fsub_rn(b32, ff.fmax);
+                        height = smax;
+                        amp = (float)__dsub_rn((double)smax, (double)smin);
+                    }
+                }
+                if (c1 > c0) {
+                    double ds = ff.dsum;
+                    if (ff.nraw) ds += rawpos ? __dsub_rn(ff.xsum, __dmul_rn((double)ff.nraw, r.b_feat)) : __dsub_rn(__dmul_rn((double)ff.nraw, r.b_feat), ff.xsum);
+                    area = (float)ds;
+                }
+            } else {
+            mad = (float)max(fs.idiff, (int)max(fs.pdiff & 0xffffu, fs.pdiff >> 16));
             if (p1 > p0) {
                 const int wmin = min(fs.imin, (int)min(fs.pmin & 0xffffu, fs.pmin >> 16));
                 const int wmax = max(fs.imax, (int)max(fs.pmax & 0xffffu, fs.pmax >> 16));
@@ -914,6 +975,7 @@ __global__ void __launch_bounds__(kLprWarps * 32, (HITS && !FEAT) ? WFB_LPR_MINB
                 } else {
                     area = (float)fs.dsum;
                 }
+            }
             }
             unsigned* dst = reinterpret_cast<unsigned*>(a.feat_out + rec * kFeatRowBytes);
             const long long ev = a.p.row_base + rec;
@@ -995,7 +1057,8 @@ __global__ void __launch_bounds__(kLprWarps * 32, (HITS && !FEAT) ? WFB_LPR_MINB
                 DirectSink dsink;
                 dsink.my_row0 = base + rel;
                 dsink.my_active = (ovf >> lane) & 1u;
-                if constexpr (BLK) blk_stream<false, SGN>(a, pool, r, sc, ring, 0, 0, 0, 0, fs2, ws, bq, dsink);
+                if constexpr (F32) f32_stream<false, true>(a, static_cast<const float*>(a.pool), r, sc, ring, 0, 0, 0, 0, ff, ws, dsink);
+                else if constexpr (BLK) blk_stream<false, SGN>(a, pool, r, sc, ring, 0, 0, 0, 0, fs2, ws, bq, dsink);
                 else lpr_stream<false, true, SGN, EXT22>(a, pool, r, sc, ring, 0, 0, 0, 0, fs2, ws, cq, dsink);
             }
             pend = false;
@@ -1011,19 +1074,27 @@ __global__ void __launch_bounds__(kLprWarps * 32, (HITS && !FEAT) ? WFB_LPR_MINB
 }
 
 int launch_lpr(FHArgs a, int flags, cudaStream_t st) {
-    if (a.p.pool_is_f32) return 1;
     const char* force = getenv("WFB_FUSED_VARIANT");
     if (force && (!strcmp(force, "global") || !strcmp(force, "staged"))) return 1;
     if (a.lmax >= 65536 - 16) return 1;  // positions are packed in 16 bits
     if (a.p.left_extension > kMaxExt || a.p.right_extension > kMaxExt) return 1;
+    const bool f32 = a.p.pool_is_f32 != 0;
+    if (f32) {
+        // float32 pools: the register-resident run / tail state of fused_f32.cuh needs extensions of at most two samples;
+        // WFB_F32_IMPL=warp keeps the warp-per-record kernel
+        const char* fi = getenv("WFB_F32_IMPL");
+        if (fi && !strcmp(fi, "warp")) return 1;
+        if ((flags & WFB_DO_HITS) && (a.p.left_extension > kBQMaxExt || a.p.right_extension > kBQMaxExt)) return 1;
+    }
     // segment length in chunks: kHist history chunks + sc new chunks per slot
     // a multiple of the 4-chunk scan block.  Measured per mode (profiles/README.md): features + hits 12 chunks at three
     // blocks per SM; hits only 8 chunks, whose smaller slots and 128 registers let a fourth block in; features only 16
     const bool want_f = flags & WFB_DO_FEATURES, want_h = flags & WFB_DO_HITS;
     // block-granular items (fused_blk.cuh): extensions of at most two samples; WFB_LPR_IMPL=chunk keeps the chunk-granular variant
     const char* impl = getenv("WFB_LPR_IMPL");
-    const bool blk = want_h && a.p.left_extension <= kBQMaxExt && a.p.right_extension <= kBQMaxExt && !(impl && !strcmp(impl, "chunk"));
+    const bool blk = !f32 && want_h && a.p.left_extension <= kBQMaxExt && a.p.right_extension <= kBQMaxExt && !(impl && !strcmp(impl, "chunk"));
     int sc = blk ? 8 : ((want_f && want_h) ? 12 : (want_h ? 8 : 16));
+    if (f32) sc = 8;  // 32 samples per segment: four blocks (16 warps) per SM fit
     if (const char* e = getenv("WFB_LPR_SC")) sc = std::max(4, std::min(28, atoi(e) & ~3));
     int ent_cap = a.gpool_cap;  // WFB_LPR_POOL shrinks the per-warp hit pool (exercises the overflow path in tests)
     if (const char* e = getenv("WFB_LPR_POOL")) ent_cap = std::max(0, std::min(a.gpool_cap, atoi(e)));
@@ -1038,7 +1109,8 @@ int launch_lpr(FHArgs a, int flags, cudaStream_t st) {
     memset(&tmap, 0, sizeof(tmap));
     int have_tmap = 0;
     const char* no2d = getenv("WFB_LPR_NO_TMAP");
-    if (!(no2d && no2d[0] == '1') && a.lmax > 0 && a.lmax % 8 == 0 && a.pool_len >= a.lmax && a.n < (1ll << 31)) {
+    const int per16 = f32 ? 4 : 8;  // samples per 16-byte chunk
+    if (!(no2d && no2d[0] == '1') && a.lmax > 0 && a.lmax % per16 == 0 && a.pool_len >= a.lmax && a.n < (1ll << 31)) {
         typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1051,10 +1123,10 @@ int launch_lpr(FHArgs a, int flags, cudaStream_t st) {
         }
         if (encode) {
             cuuint64_t dims[2] = {(cuuint64_t)a.lmax, (cuuint64_t)(a.pool_len / a.lmax)};
-            cuuint64_t strides[1] = {(cuuint64_t)a.lmax * 2};
-            cuuint32_t box[2] = {(cuuint32_t)(a.slot_bytes / 2), 32};
+            cuuint64_t strides[1] = {(cuuint64_t)a.lmax * (f32 ? 4 : 2)};
+            cuuint32_t box[2] = {(cuuint32_t)(a.slot_bytes / (f32 ? 4 : 2)), 32};
             cuuint32_t estr[2] = {1, 1};
-            CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(a.pool), dims, strides, box, estr,
+            CUresult cr = encode(&tmap, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(a.pool), dims, strides, box, estr,
                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             have_tmap = (cr == CUDA_SUCCESS) ? 1 : 0;
@@ -1075,6 +1147,11 @@ int launch_lpr(FHArgs a, int flags, cudaStream_t st) {
         return WFB_OK;
     };
     const bool e22 = h && a.p.left_extension == 2 && a.p.right_extension == 2;  // the defaults (hit_finder.py:104-105)
+    if (f32) {
+        if (f && h) return go(lpr_kernel<true, true, false, false, false, true>);
+        if (f) return go(lpr_kernel<true, false, false, false, false, true>);
+        return go(lpr_kernel<false, true, false, false, false, true>);
+    }
     if (blk) {
         if (a.p.signed_samples) return f ? go(lpr_kernel<true, true, true, false, true>) : go(lpr_kernel<false, true, true, false, true>);
         return f ? go(lpr_kernel<true, true, false, false, true>) : go(lpr_kernel<false, true, false, false, true>);

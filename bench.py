@@ -603,8 +603,19 @@ def run_c3(args, engine, torch, peak):
         return int(valid[:nh].sum().item())
 
     w_ms, nw = _timed(torch, widths)
+    # hit_threshold + basic_features on the filtered (float32) pool: the lane-per-record kernel's float32 variant
+    fres = frun.features_hits(threshold=THRESHOLD, hit_cap=1024)
+    torch.cuda.synchronize()
+    fnh = int(fres["total"].item())
+    fout = {"features": torch.empty(n * 36, dtype=torch.uint8, device="cuda"), "hits": torch.empty((fnh + 16) * 60, dtype=torch.uint8, device="cuda"),
+            "total": torch.zeros(1, dtype=torch.int64, device="cuda")}
+    f32_ms, _ = _timed(torch, lambda: frun.features_hits(threshold=THRESHOLD, hit_cap=fnh + 16, out=fout))
+    f32_bpr = 4 * L + 72 + 60 * fnh / n
     gb = n * L * 6 / 1e9
     return {
+        "fused_f32": {"ms": f32_ms, "records_per_s": n / (f32_ms * 1e-3), "hits_per_record": fnh / n, "bytes_per_record": f32_bpr,
+                      "frac_hbm": n * f32_bpr / (f32_ms * 1e-3) / 1e9 / peak,
+                      "call": "wfb_features_hits on the SG-filtered float32 pool (threshold hits + basic_features, lane-per-record float32 kernel)"},
         "workload": f"64 ch V1725-like (dt 4 ns, positive pulses), {n} records x {L} samples, device resident: wave_pool_filtered, hit on the filtered pool, waveform_width",
         "sg": {"ms": sg_ms, "GBps": gb / (sg_ms * 1e-3), "frac_hbm": gb / (sg_ms * 1e-3) / peak, "bytes_per_record": 6 * L},
         "bw": {"ms": bw_ms, "GBps": gb / (bw_ms * 1e-3), "frac_hbm": gb / (bw_ms * 1e-3) / peak, "bytes_per_record": 6 * L,

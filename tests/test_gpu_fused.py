@@ -397,3 +397,65 @@ def test_float32_pool_vs_oracle(eng, n_samples, variant, impl, monkeypatch):
     want_f = O.basic_features(rec, poolf, height_range=(13, n_samples - 9), area_range=(5, -3))
     out = eng.process_host(rec, poolf, hits=False, height_range=(13, n_samples - 9), area_range=(5, -3))
     assert_rows_match(out["features"], want_f, what="cut ranges", float_exact=FX_BF)
+
+
+@pytest.mark.parametrize("ext,knobs", [((2, 2), {}), ((0, 0), {}), ((1, 2), {}), ((2, 1), {}), ((0, 2), {}), ((2, 0), {}),
+                                       ((2, 2), {"WFB_LPR_POOL": "24"}), ((2, 2), {"WFB_LPR_SC": "4"}), ((1, 1), {"WFB_LPR_SC": "16", "WFB_LPR_NO_TMAP": "1"}),
+                                       ((3, 2), {})])
+def test_float32_lane_kernel_edges(eng, ext, knobs, monkeypatch):
+    """The register-resident run / tail state of the float32 lane-per-record kernel (fused_f32.cuh): ragged records with
+    runs at both record ends (padding up to the run-wide width joins the window), runs one sample apart (overlapping
+    windows), single-sample runs, every extension pair up to two samples, the pool-overflow path (rows straight out),
+    other segment lengths, the per-lane bulk-copy ring.  (3, 2) is outside the lane kernel's range: the warp-per-record
+    kernel takes it.  Both kernels must agree with the oracle."""
+    from oracle import np_oracle as O
+    from waveformanalysis_b200.dtypes import RECORDS_DTYPE
+
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(sum(ext) * 7 + len(knobs))
+    n, Lmax = 700, 331
+    lens = rng.integers(1, Lmax + 1, n)
+    lens[:40] = Lmax
+    lens[40:60] = rng.integers(1, 6, 20)
+    rec = np.zeros(n, dtype=RECORDS_DTYPE)
+    rec["record_id"] = np.arange(n)
+    rec["timestamp"] = np.arange(n) * 1_000_000
+    rec["dt"] = 2
+    rec["channel"] = np.arange(n) % 5
+    rec["event_length"] = lens
+    gaps = rng.integers(0, 7, n)  # records start anywhere relative to the 16-byte grid
+    rec["wave_offset"] = np.cumsum(lens + gaps) - lens
+    rec["baseline"] = 1000.0 + rng.uniform(-0.5, 0.5, n)
+    pol = np.array(["unknown", "negative", "positive", "raw_positive"])[np.arange(n) % 4]
+    rec["polarity"] = pol
+    pool = (1000.0 + rng.normal(0, 2.0, int(rec["wave_offset"][-1] + lens[-1] + 8))).astype(np.float32)
+    positive = pol == "positive"
+    for i in range(n):
+        o, L = int(rec["wave_offset"][i]), int(lens[i])
+        sign = 1.0 if positive[i] else -1.0
+        w = pool[o:o + L]
+        kind = i % 6
+        if kind == 0 and L > 12:      # a run that reaches the record end
+            w[-rng.integers(1, 6):] += sign * 40
+        elif kind == 1 and L > 12:    # a run at the record start
+            w[: rng.integers(1, 6)] += sign * 40
+        elif kind == 2 and L > 30:    # runs one and two samples apart, single-sample runs
+            w[10:14] += sign * 40
+            w[15] += sign * 40
+            w[18:20] += sign * 40
+            w[21] += sign * 40
+        elif kind == 3 and L > 8:     # everything above threshold
+            w += sign * 40
+        elif kind == 4 and L > 40:    # a run ending one / two samples before the record end
+            w[L - 9:L - 1 - (i % 2)] += sign * 40
+    thr = 9.0
+    want_h = O.threshold_hits(rec, pool, threshold=thr, left_extension=ext[0], right_extension=ext[1])
+    want_f = O.basic_features(rec, pool, height_range=(3, 60), area_range=(0, None))
+    assert len(want_h) > 600
+    for impl in ("lane", "warp"):
+        monkeypatch.setenv("WFB_F32_IMPL", impl)
+        out = both_paths(eng, rec, pool, chunk_records=300, height_range=(3, 60), area_range=(0, None), threshold=thr,
+                         left_extension=ext[0], right_extension=ext[1])
+        assert_rows_match(out["hits"], want_h, what=f"{impl} hits ext={ext}", float_exact=("height",))
+        assert_rows_match(out["features"], want_f, what=f"{impl} features", float_exact=FX_BF)

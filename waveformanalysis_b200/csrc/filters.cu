@@ -142,45 +142,63 @@ __device__ __forceinline__ double bw_sample(const float* p, long long i, bool) {
 // produce padding and are skipped), the samples come in 16-byte vectors, the forward pass is parked as float32 with a
 // pointer that advances by the grid stride, and the cascade uses fused multiply-adds: ~28 instructions per sample and
 // pass instead of ~70.
-template <typename T, int MAXS>
-__global__ void __launch_bounds__(128) bw_fast_kernel(const T* __restrict__ pool, long long pool_len,
+// UNI: every record uses ONE configuration with exactly MAXS sections (the normal case: no per-channel filter
+// overrides).  The coefficients then are kernel parameters - the float64 instructions read them straight from the
+// constant bank, which frees ~40 registers: six blocks per SM instead of three hide the latency of the serial cascade.
+struct BwCoef {
+    double b0[4], b1[4], b2[4], na1[4], na2[4], zi0[4], zi1[4];
+    int edge;
+};
+template <typename T, int MAXS, bool UNI>
+__global__ void __launch_bounds__(128, UNI ? 6 : 1) bw_fast_kernel(const T* __restrict__ pool, long long pool_len,
                                                      const wfb_rec_meta* __restrict__ meta, long long n,
                                                      const int* __restrict__ cfg_index,
                                                      const wfb_filter_cfg* __restrict__ cfgs, float* __restrict__ out,
-                                                     long long pool_base, double* __restrict__ scratch_f64, int scratch_len) {
+                                                     long long pool_base, double* __restrict__ scratch_f64, int scratch_len,
+                                                     const __grid_constant__ BwCoef cc) {
     float* __restrict__ scratch = reinterpret_cast<float*>(scratch_f64);
     const long long n_threads = (long long)gridDim.x * blockDim.x;
     const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     for (long long rec = tid; rec < n; rec += n_threads) {
-        const wfb_filter_cfg& cfg = cfgs[cfg_index[rec]];
-        if (cfg.type != WFB_FILTER_BW || cfg.n_sections > MAXS) continue;
+        const wfb_filter_cfg& cfg = cfgs[UNI ? 0 : cfg_index[rec]];
+        if (!UNI && (cfg.type != WFB_FILTER_BW || cfg.n_sections > MAXS)) continue;
         const long long off = meta[rec].wave_offset - pool_base;
         const int L = meta[rec].event_length;
         if (L <= 0 || off < 0 || off + L > pool_len) continue;
         const T* x = pool + off;
         float* y = out + off;
-        const int ns = cfg.n_sections;
-        int z_b = 0, z_a = 0;
-        for (int s = 0; s < ns; ++s) {
-            z_b += cfg.sos[s][2] == 0.0;
-            z_a += cfg.sos[s][5] == 0.0;
+        const int ns = UNI ? MAXS : cfg.n_sections;
+        int edge = cc.edge;
+        if (!UNI) {
+            int z_b = 0, z_a = 0;
+            for (int s = 0; s < ns; ++s) {
+                z_b += cfg.sos[s][2] == 0.0;
+                z_a += cfg.sos[s][5] == 0.0;
+            }
+            edge = 3 * (2 * ns + 1 - min(z_b, z_a));  // filtering.py:198-203
         }
-        const int edge = 3 * (2 * ns + 1 - min(z_b, z_a));  // filtering.py:198-203
         if (L <= edge || L + 2 * edge > scratch_len) {       // unfiltered copy (filtering.py:221-222)
             for (int k = 0; k < L; ++k) y[k] = (float)x[k];
             continue;
         }
         double cb0[MAXS], cb1[MAXS], cb2[MAXS], na1[MAXS], na2[MAXS], z0[MAXS], z1[MAXS];
+        if (!UNI) {
 #pragma unroll
-        for (int s = 0; s < MAXS; ++s) {
-            const bool on = s < ns;
-            cb0[s] = on ? cfg.sos[s][0] : 1.0; cb1[s] = on ? cfg.sos[s][1] : 0.0; cb2[s] = on ? cfg.sos[s][2] : 0.0;
-            na1[s] = on ? -cfg.sos[s][4] : 0.0; na2[s] = on ? -cfg.sos[s][5] : 0.0;
+            for (int s = 0; s < MAXS; ++s) {
+                const bool on = s < ns;
+                cb0[s] = on ? cfg.sos[s][0] : 1.0; cb1[s] = on ? cfg.sos[s][1] : 0.0; cb2[s] = on ? cfg.sos[s][2] : 0.0;
+                na1[s] = on ? -cfg.sos[s][4] : 0.0; na2[s] = on ? -cfg.sos[s][5] : 0.0;
+            }
         }
         auto cascade = [&](double v) -> double {
 #pragma unroll
             for (int s = 0; s < MAXS; ++s) {
-                if (s < ns) {
+                if constexpr (UNI) {
+                    const double o = fma(cc.b0[s], v, z0[s]);
+                    z0[s] = fma(cc.b1[s], v, fma(cc.na1[s], o, z1[s]));
+                    z1[s] = fma(cc.b2[s], v, cc.na2[s] * o);
+                    v = o;
+                } else if (s < ns) {
                     const double o = fma(cb0[s], v, z0[s]);
                     z0[s] = fma(cb1[s], v, fma(na1[s], o, z1[s]));
                     z1[s] = fma(cb2[s], v, na2[s] * o);
@@ -194,8 +212,8 @@ __global__ void __launch_bounds__(128) bw_fast_kernel(const T* __restrict__ pool
         const double x0 = fma(2.0, x_first, -smp(edge));
 #pragma unroll
         for (int s = 0; s < MAXS; ++s) {
-            z0[s] = s < ns ? cfg.zi[s][0] * x0 : 0.0;
-            z1[s] = s < ns ? cfg.zi[s][1] * x0 : 0.0;
+            z0[s] = UNI ? cc.zi0[s] * x0 : (s < ns ? cfg.zi[s][0] * x0 : 0.0);
+            z1[s] = UNI ? cc.zi1[s] * x0 : (s < ns ? cfg.zi[s][1] * x0 : 0.0);
         }
         float* sp = scratch + tid;
         double v = 0.0;
@@ -240,8 +258,8 @@ __global__ void __launch_bounds__(128) bw_fast_kernel(const T* __restrict__ pool
         const double y0 = v;
 #pragma unroll
         for (int s = 0; s < MAXS; ++s) {
-            z0[s] = s < ns ? cfg.zi[s][0] * y0 : 0.0;
-            z1[s] = s < ns ? cfg.zi[s][1] * y0 : 0.0;
+            z0[s] = UNI ? cc.zi0[s] * y0 : (s < ns ? cfg.zi[s][0] * y0 : 0.0);
+            z1[s] = UNI ? cc.zi1[s] * y0 : (s < ns ? cfg.zi[s][1] * y0 : 0.0);
         }
         for (int k = 0; k < edge; ++k) {
             sp -= n_threads;
@@ -423,12 +441,15 @@ extern "C" int wfb_filter_pool(const void* pool_dev, int32_t pool_is_f32, int64_
     }
     // the Butterworth kernel keeps the section coefficients in registers: pick the smallest compiled size
     int max_sections = 0;
+    wfb_filter_cfg uni_cfg;
+    memset(&uni_cfg, 0, sizeof(uni_cfg));
     if (bw_threads > 0) {
         std::vector<wfb_filter_cfg> host_cfg((size_t)n_cfg);
         WFB_CUDA(cudaMemcpyAsync(host_cfg.data(), cfgs_dev, sizeof(wfb_filter_cfg) * (size_t)n_cfg, cudaMemcpyDeviceToHost, st));
         WFB_CUDA(cudaStreamSynchronize(st));
         for (const auto& c : host_cfg)
             if (c.type == WFB_FILTER_BW) max_sections = std::max(max_sections, (int)c.n_sections);
+        uni_cfg = host_cfg[0];
         WFB_REQUIRE(max_sections <= WFB_MAX_SOS_SECTIONS, "wfb_filter_pool: too many second-order sections");
     }
     auto launch_bw = [&](auto tag) {
@@ -438,14 +459,37 @@ extern "C" int wfb_filter_pool(const void* pool_dev, int32_t pool_is_f32, int64_
         const unsigned grid = (unsigned)(bw_threads / 128);
         const char* ex = getenv("WFB_BW_EXACT");
         const bool exact = ex && ex[0] == '1';
+        BwCoef cc;
+        memset(&cc, 0, sizeof(cc));
+        // one configuration for every record (no per-channel overrides): coefficients as kernel parameters
+        const char* nu = getenv("WFB_BW_UNIFORM");
+        const bool uni = !exact && n_cfg == 1 && uni_cfg.type == WFB_FILTER_BW && (uni_cfg.n_sections == 2 || uni_cfg.n_sections == 4) &&
+                         !(nu && nu[0] == '0');
+        if (uni) {
+            const int ns = uni_cfg.n_sections;
+            int z_b = 0, z_a = 0;
+            for (int s = 0; s < ns; ++s) {
+                cc.b0[s] = uni_cfg.sos[s][0]; cc.b1[s] = uni_cfg.sos[s][1]; cc.b2[s] = uni_cfg.sos[s][2];
+                cc.na1[s] = -uni_cfg.sos[s][4]; cc.na2[s] = -uni_cfg.sos[s][5];
+                cc.zi0[s] = uni_cfg.zi[s][0]; cc.zi1[s] = uni_cfg.zi[s][1];
+                z_b += uni_cfg.sos[s][2] == 0.0;
+                z_a += uni_cfg.sos[s][5] == 0.0;
+            }
+            cc.edge = 3 * (2 * ns + 1 - std::min(z_b, z_a));  // filtering.py:198-203
+            if (ns == 2)
+                bw_fast_kernel<T, 2, true><<<grid, 128, 0, st>>>(p, pool_len, meta_dev, n, cfg_index_dev, cfgs_dev, out_dev, pool_base, scr, (int)scratch_len, cc);
+            else
+                bw_fast_kernel<T, 4, true><<<grid, 128, 0, st>>>(p, pool_len, meta_dev, n, cfg_index_dev, cfgs_dev, out_dev, pool_base, scr, (int)scratch_len, cc);
+            return;
+        }
 #define WFB_BW_LAUNCH(MS)                                                                                                          \
     do {                                                                                                                           \
         if (exact)                                                                                                                 \
             bw_filter_kernel<T, MS, false><<<grid, 128, 0, st>>>(p, pool_len, meta_dev, n, cfg_index_dev, cfgs_dev, out_dev, pool_base, scr, \
                                                                 (int)scratch_len);                                                 \
         else                                                                                                                       \
-            bw_fast_kernel<T, MS><<<grid, 128, 0, st>>>(p, pool_len, meta_dev, n, cfg_index_dev, cfgs_dev, out_dev, pool_base, scr,       \
-                                                       (int)scratch_len);                                                         \
+            bw_fast_kernel<T, MS, false><<<grid, 128, 0, st>>>(p, pool_len, meta_dev, n, cfg_index_dev, cfgs_dev, out_dev, pool_base, scr,       \
+                                                       (int)scratch_len, cc);                                                      \
     } while (0)
         if (max_sections <= 4) WFB_BW_LAUNCH(4);
         else if (max_sections <= 8) WFB_BW_LAUNCH(8);

@@ -273,6 +273,118 @@ struct ChargeSrc {
     }
 };
 
+// Fast path of waveform_width_integral for 16-bit samples whose record starts on a 16-byte boundary (every record of a
+// fixed-length pool with L % 8 == 0): the SAME float64 operations in the SAME order as the generic path - numpy's pairwise
+// np.sum (blocks of <= 128 with eight accumulators; every block starts at a multiple of eight) and the sequential
+// np.cumsum - but eight samples come from one 16-byte load, the sample format and the polarity mode are resolved at
+// compile time and nothing is indexed dynamically: ~9 instead of ~47 instructions per sample and pass.
+template <typename T, int MODE>
+struct ChargeTerm {
+    double b;
+    float b32;
+    __device__ __forceinline__ double operator()(unsigned h) const {
+        const T wi = (T)(unsigned short)h;  // uint16_t or short
+        double sig;
+        if (MODE == 0) sig = __dsub_rn(b, (double)wi);
+        else if (MODE == 1) sig = (double)__fsub_rn(b32, (float)wi);
+        else if (MODE == 2) sig = (double)__fsub_rn((float)wi, b32);
+        else sig = __dsub_rn((double)wi, b);
+        return fmax(sig, 0.0);
+    }
+    __device__ __forceinline__ void load8(const uint4* chunks, int i, double v[8]) const {  // samples i .. i + 7, i % 8 == 0
+        const uint4 q = __ldg(chunks + (i >> 3));
+        v[0] = (*this)(q.x & 0xffffu); v[1] = (*this)(q.x >> 16);
+        v[2] = (*this)(q.y & 0xffffu); v[3] = (*this)(q.y >> 16);
+        v[4] = (*this)(q.z & 0xffffu); v[5] = (*this)(q.z >> 16);
+        v[6] = (*this)(q.w & 0xffffu); v[7] = (*this)(q.w >> 16);
+    }
+    __device__ __forceinline__ double at(const uint4* chunks, int i) const {
+        const unsigned short* hw = reinterpret_cast<const unsigned short*>(chunks);
+        return (*this)((unsigned)__ldg(hw + i));
+    }
+};
+
+template <typename T, int MODE>
+__device__ void width_integral_fast(const uint4* chunks, int L, const ChargeTerm<T, MODE> term, double q_low, double q_high, double& q_out,
+                                    int& lo_out, int& hi_out) {
+    // ---- q = np.sum: numpy's pairwise recursion, iterative (np_sum.cuh), blocks summed eight samples per load
+    auto block = [&](int off, int len) -> double {
+        if (len < 8) {
+            double res = 0.0;
+            for (int i = 0; i < len; ++i) res = __dadd_rn(res, term.at(chunks, off + i));
+            return res;
+        }
+        double r[8], v[8];
+        term.load8(chunks, off, r);
+        int i;
+        for (i = 8; i < len - (len % 8); i += 8) {
+            term.load8(chunks, off + i, v);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r[k] = __dadd_rn(r[k], v[k]);
+        }
+        double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])), __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+        for (; i < len; ++i) res = __dadd_rn(res, term.at(chunks, off + i));
+        return res;
+    };
+    int st_off[24], st_len[24], st_state[24];
+    double st_val[24];
+    int sp = 0;
+    st_off[0] = 0; st_len[0] = L; st_state[0] = 0;
+    double ret = 0.0;
+    while (sp >= 0) {
+        const int off = st_off[sp], len = st_len[sp];
+        if (st_state[sp] == 0) {
+            if (len <= 128) {
+                ret = block(off, len);
+                --sp;
+            } else {
+                int n2 = len / 2;
+                n2 -= n2 % 8;
+                st_state[sp] = 1;
+                ++sp;
+                st_off[sp] = off; st_len[sp] = n2; st_state[sp] = 0;
+            }
+        } else if (st_state[sp] == 1) {
+            int n2 = len / 2;
+            n2 -= n2 % 8;
+            st_val[sp] = ret;
+            st_state[sp] = 2;
+            ++sp;
+            st_off[sp] = off + n2; st_len[sp] = len - n2; st_state[sp] = 0;
+        } else {
+            ret = __dadd_rn(st_val[sp], ret);
+            --sp;
+        }
+    }
+    const double q = ret;
+    q_out = q;
+    lo_out = hi_out = 0;
+    if (!(q > 0.0 && isfinite(q))) return;
+    // ---- np.cumsum + searchsorted(..., 'left'): the first index whose cumulative sum reaches the target
+    const double tl = __dmul_rn(q_low, q), th = __dmul_rn(q_high, q);
+    int lo = L, hi = L;
+    bool fl = false, fh = false;
+    double cs = 0.0;
+    int i = 0;
+    for (; i + 8 <= L && !fh; i += 8) {
+        double v[8];
+        term.load8(chunks, i, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            cs = (i + k == 0) ? v[0] : __dadd_rn(cs, v[k]);
+            if (!fl && cs >= tl) { lo = i + k; fl = true; }
+            if (!fh && cs >= th) { hi = i + k; fh = true; }
+        }
+    }
+    for (; i < L && !fh; ++i) {
+        cs = (i == 0) ? term.at(chunks, 0) : __dadd_rn(cs, term.at(chunks, i));
+        if (!fl && cs >= tl) { lo = i; fl = true; }
+        if (!fh && cs >= th) { hi = i; fh = true; }
+    }
+    lo_out = lo;
+    hi_out = hi;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(128) width_integral_kernel(const T* __restrict__ pool, long long pool_len,
                                                             const wfb_rec_meta* __restrict__ meta, long long n,
@@ -299,9 +411,23 @@ __global__ void __launch_bounds__(128) width_integral_kernel(const T* __restrict
     x.b = m.baseline;
     x.b32 = (float)m.baseline;
     x.mode = m.polarity == WFB_POL_NEGATIVE ? 1 : (m.polarity == WFB_POL_POSITIVE ? 2 : (m.polarity == WFB_POL_RAW_POSITIVE ? 3 : 0));
-    const double q = numpy_pairwise_sum(x, L);
+    double q = 0.0;
     int lo = 0, hi = 0;
-    if (q > 0.0 && isfinite(q)) {
+    bool done = false;
+    if constexpr (sizeof(T) == 2) {
+        if (L >= 8 && (reinterpret_cast<uintptr_t>(pool + off) & 15) == 0) {
+            const uint4* ch = reinterpret_cast<const uint4*>(pool + off);
+            switch (x.mode) {
+                case 0: width_integral_fast<T, 0>(ch, L, ChargeTerm<T, 0>{x.b, x.b32}, q_low, q_high, q, lo, hi); break;
+                case 1: width_integral_fast<T, 1>(ch, L, ChargeTerm<T, 1>{x.b, x.b32}, q_low, q_high, q, lo, hi); break;
+                case 2: width_integral_fast<T, 2>(ch, L, ChargeTerm<T, 2>{x.b, x.b32}, q_low, q_high, q, lo, hi); break;
+                default: width_integral_fast<T, 3>(ch, L, ChargeTerm<T, 3>{x.b, x.b32}, q_low, q_high, q, lo, hi); break;
+            }
+            done = true;
+        }
+    }
+    if (!done) q = numpy_pairwise_sum(x, L);
+    if (!done && q > 0.0 && isfinite(q)) {
         const double tl = __dmul_rn(q_low, q), th = __dmul_rn(q_high, q);
         lo = hi = L;  // searchsorted returns len when no element reaches the target
         bool fl = false, fh = false;

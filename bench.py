@@ -740,18 +740,47 @@ def run_e2e(args, engine, torch, barrier, max_over_ranks, sum_over_ranks, rank):
         return rows
 
     stream_pass()
+    walls = []
+    for _ in range(3):  # median of three passes: one pass in five runs into a host-side hiccup (allocator / GC) of ~0.2 s
+        barrier()
+        t0 = time.perf_counter()
+        rows = stream_pass()
+        barrier()
+        walls.append(max_over_ranks(time.perf_counter() - t0))
+        assert rows == n_hits0, (rows, n_hits0)
+    stream_wall = sorted(walls)[1]
+    ctx._results.clear()
+    # the same plugin calls on PAGEABLE host arrays (what a Context hands over when the data was just computed; cached data
+    # comes as np.memmap views): the driver stages the upload, so the link runs below its pinned rate
+    n_pg = min(n, 1_000_000)
+    rec_pg = np.array(records[:n_pg])
+    pool_pg = np.array(pool[: n_pg * N_SAMPLES])
+
+    def pageable_step(k):
+        run_id = f"pg_{k}"
+        ctx._results[(run_id, "records")] = rec_pg
+        ctx._results[(run_id, "wave_pool")] = pool_pg
+        f = plugins["basic_features"].compute(ctx, run_id)
+        h = plugins["hit_threshold"].compute(ctx, run_id)
+        residency.release(run_id)
+        ctx._results.clear()
+        return len(f) + len(h)
+
+    pageable_step(-1)
     barrier()
     t0 = time.perf_counter()
-    rows = stream_pass()
+    for k in range(2):
+        pageable_step(k)
     barrier()
-    stream_wall = max_over_ranks(time.perf_counter() - t0)
-    assert rows == n_hits0, (rows, n_hits0)
-    ctx._results.clear()
+    pageable_wall = max_over_ranks(time.perf_counter() - t0)
+    pageable_leg = {"value": sum_over_ranks(float(n_pg)) * 2 / pageable_wall, "unit": UNIT, "records_per_gpu": n_pg,
+                    "note": "same plugin calls, inputs in ordinary (pageable) numpy arrays"}
     stream_leg = {"value": n_all / stream_wall, "unit": UNIT, "chunk_records": int(stream.chunk_size), "chunks": stream.stream_stats["chunks"],
-                  "overlapped_chunks": stream.stream_stats["overlapped_chunks"],
+                  "overlapped_chunks": stream.stream_stats["overlapped_chunks"], "pass_walls_s": [round(w, 4) for w in walls],
                   "call": "B200HitThresholdStreamPlugin.compute (hit_threshold_stream): three-slot device pipeline, rows of every chunk to the host"}
     return {
         "stream": stream_leg,
+        "pageable": pageable_leg,
         "value": n_all * steps / wall,
         "unit": UNIT,
         "h2d_bytes_per_step": int(n * (2 * N_SAMPLES + 102)),

@@ -93,8 +93,17 @@ def stream_pass():
     return rows
 
 
-for rep in range(3):
+def host_allocs():
+    try:
+        st = torch.cuda.host_memory_stats()
+        return {k: st[k] for k in st if ("num_host_alloc" in k or "host_alloc_time" in k or k.endswith("allocated_bytes.allocated") or k.endswith("segment.allocated")) }
+    except Exception as exc:  # noqa: BLE001
+        return str(exc)
+
+
+for rep in range(6):
     T("stream pass", stream_pass)
+    print("   pinned allocator:", host_allocs(), sp.stream_stats)
 pr = cProfile.Profile()
 pr.enable()
 stream_pass()

@@ -70,10 +70,14 @@ def to_host(t) -> np.ndarray:
     nbytes = t.numel() * t.element_size()
     if nbytes < (1 << 20) or nbytes > PINNED_RESULT_MAX or os.environ.get("WFB_PINNED_RESULTS", "1") == "0":
         return t.cpu().numpy()
+    # block sizes rounded up to 8 MB: result sizes vary from call to call (hit counts), exact sizes would seldom find a
+    # cached block and cudaHostAlloc costs ~0.3 ms per MB
+    quantum = 8 << 20
     try:
-        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        raw = torch.empty(-(-nbytes // quantum) * quantum, dtype=torch.uint8, pin_memory=True)
     except RuntimeError:  # no pinned memory left
         return t.cpu().numpy()
+    h = raw[:nbytes].view(t.dtype).view(t.shape)
     h.copy_(t)
     return h.numpy()
 
@@ -258,7 +262,8 @@ def process_host(
         nbytes = int(count) * dtype.itemsize
         if pinned_results and (1 << 20) <= nbytes <= PINNED_RESULT_MAX:
             try:
-                return torch.empty(nbytes, dtype=torch.uint8, pin_memory=True).numpy().view(dtype)
+                quantum = 8 << 20  # (see to_host)
+                return torch.empty(-(-nbytes // quantum) * quantum, dtype=torch.uint8, pin_memory=True)[:nbytes].numpy().view(dtype)
             except RuntimeError:
                 pass
         return np.empty(int(count), dtype=dtype)

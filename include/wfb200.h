@@ -108,7 +108,9 @@ int wfb_device_info(int* sm_count, int* cc_major, int* cc_minor, char* name, int
 /* ---- K1: records ---------------------------------------------------------------------- */
 
 /* Host -> device copy of any host array (pageable, read-only or memory-mapped: what the reference's Context hands to
- * plugins, core/context_execution.py:241-251) followed by a stream synchronise, so the source may be released at once. */
+ * plugins, core/context_execution.py:241-251) followed by a stream synchronise, so the source may be released at once.
+ * Sources that are not pinned are copied through a ring of pinned 32 MB pieces by a few threads (the driver's own staged
+ * copy runs on one); wfb_process_host(_resident) does the same for its chunks.  WFB_STAGED_H2D=0 switches that off. */
 int wfb_memcpy_h2d(void* dst_dev, const void* src_host, size_t bytes, void* stream);
 /* The same copy without the synchronise, for the streaming backend (core/plugins/core/streaming.py:447-548: chunk k + 1
  * is uploaded while chunk k computes).  The source must stay valid until the stream has passed the copy; a pageable

@@ -133,3 +133,35 @@ def test_host_pipeline_leaves_the_run_resident(env, chunk_records):
     got = engine.process_host(sub, pool, threshold=12.0, chunk_records=29, keep_resident=True)
     assert np.array_equal(got["run"].pool_to_host(), pool)
     assert np.array_equal(got["hits"], engine.process_host(sub, pool, threshold=12.0)["hits"])
+
+
+def test_pageable_and_memmap_sources_go_through_the_stager(env, tmp_path):
+    """Host sources of several MB that are not pinned (ordinary numpy arrays, np.memmap views of a cache file - what a
+    Context hands to a plugin, core/context_execution.py:241-251) are copied through the library's ring of pinned pieces
+    by a few threads; pinned sources go by DMA directly.  Same rows either way, and engine.upload round-trips."""
+    import torch
+
+    from waveformanalysis_b200 import engine
+    from waveformanalysis_b200.dtypes import RECORDS_DTYPE
+
+    n, L = 60_000, 800  # 96 MB of samples: three pieces of the staging ring per chunk and more
+    dev = engine.DeviceRun.synth(n, L, 16, seed=9, with_rows=True)
+    pool_pin = torch.empty(n * L, dtype=torch.int16).pin_memory()
+    rows_pin = torch.empty(n * 102, dtype=torch.uint8).pin_memory()
+    pool_pin.copy_(dev.pool)
+    rows_pin.copy_(dev.records_rows)
+    torch.cuda.synchronize()
+    rec_p, pool_p = rows_pin.numpy().view(RECORDS_DTYPE), pool_pin.numpy().view(np.uint16)
+    want = engine.process_host(rec_p, pool_p, threshold=15.0, chunk_records=25_000)
+    rec_a, pool_a = np.array(rec_p), np.array(pool_p)  # pageable copies
+    got = engine.process_host(rec_a, pool_a, threshold=15.0, chunk_records=25_000)
+    assert got["features"].tobytes() == want["features"].tobytes() and got["hits"].tobytes() == want["hits"].tobytes()
+    path = tmp_path / "pool.bin"
+    pool_a.tofile(path)
+    pool_m = np.memmap(path, dtype=np.uint16, mode="r")
+    rec_a.setflags(write=False)
+    got = engine.process_host(rec_a, pool_m, threshold=15.0, keep_resident=True, pinned_results=True)
+    assert got["features"].tobytes() == want["features"].tobytes() and got["hits"].tobytes() == want["hits"].tobytes()
+    assert np.array_equal(got["run"].pool_to_host(), pool_a)
+    up = engine.upload(pool_m)
+    assert np.array_equal(up.cpu().numpy().view(np.uint16), pool_a)

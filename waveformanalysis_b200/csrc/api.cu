@@ -145,11 +145,14 @@ extern "C" int wfb_meta_set_clamp(wfb_rec_meta* meta_dev, int64_t n, const int32
     return WFB_OK;
 }
 
+static int staged_upload(void* dst_dev, const void* src_host, size_t bytes, cudaStream_t st);  // (below: needs the device's stager)
+
 extern "C" int wfb_memcpy_h2d(void* dst_dev, const void* src_host, size_t bytes, void* stream) {
     if (bytes == 0) return WFB_OK;
     WFB_REQUIRE(dst_dev && src_host, "wfb_memcpy_h2d: NULL pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    WFB_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, st));
+    int rc = staged_upload(dst_dev, src_host, bytes, st);
+    if (rc != WFB_OK) return rc;
     WFB_CUDA(cudaStreamSynchronize(st));  // pageable / memory-mapped sources: the caller may drop the array right away
     return WFB_OK;
 }
@@ -237,9 +240,90 @@ constexpr int kMaxDevices = 64;
 // Streams, events and device buffers of wfb_process_host, kept between calls (one set per device,
 // calls on the same device are serialised by the mutex).  wfb_release_cache() frees them; they
 // are deliberately not freed at process exit (the CUDA context may already be gone).
+// Pageable (or memory-mapped) host sources - what a Context hands to a plugin - would be staged by the driver on one
+// thread at ~10 GB/s.  The stager copies them into a small ring of pinned pieces with a few threads and sends every piece
+// by DMA as soon as it is full, so the upload runs at the speed the host can read its own memory.
+constexpr int kStagePieces = 4;
+constexpr size_t kStagePieceBytes = 32u << 20;
+struct Stager {
+    uint8_t* buf[kStagePieces] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t sent[kStagePieces] = {nullptr, nullptr, nullptr, nullptr};
+    int next = 0;
+    bool ready = false;
+    int init() {
+        if (ready) return WFB_OK;
+        for (int k = 0; k < kStagePieces; ++k) {
+            WFB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&buf[k]), kStagePieceBytes, cudaHostAllocDefault));
+            WFB_CUDA(cudaEventCreateWithFlags(&sent[k], cudaEventDisableTiming));
+        }
+        ready = true;
+        return WFB_OK;
+    }
+    void release() {
+        for (int k = 0; k < kStagePieces; ++k) {
+            if (buf[k]) cudaFreeHost(buf[k]);
+            if (sent[k]) cudaEventDestroy(sent[k]);
+            buf[k] = nullptr;
+            sent[k] = nullptr;
+        }
+        ready = false;
+    }
+};
+
+bool host_pointer_is_pinned(const void* p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged;
+}
+
+void parallel_memcpy(uint8_t* dst, const uint8_t* src, size_t bytes) {
+    const int nt = (int)std::max<size_t>(1, std::min<size_t>(4, bytes >> 22));  // one thread per 4 MB, at most four
+    if (nt == 1) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    std::vector<std::thread> th;
+    const size_t per = ((bytes / nt) + 63) & ~(size_t)63;
+    for (int t = 1; t < nt; ++t) {
+        const size_t lo = std::min(bytes, per * t), hi = (t == nt - 1) ? bytes : std::min(bytes, per * (t + 1));
+        th.emplace_back([=]() { memcpy(dst + lo, src + lo, hi - lo); });
+    }
+    memcpy(dst, src, std::min(bytes, per));
+    for (auto& x : th) x.join();
+}
+
+// host -> device on `st`; the source may be released when the call returns unless it is pinned (then: after the stream
+// has passed the copy, as with cudaMemcpyAsync)
+int staged_h2d(Stager& sg, void* dst_dev, const void* src_host, size_t bytes, cudaStream_t st, bool src_pinned) {
+    if (bytes == 0) return WFB_OK;
+    static const bool off = [] { const char* e = getenv("WFB_STAGED_H2D"); return e && e[0] == '0'; }();
+    if (src_pinned || off || bytes < (1u << 20)) {
+        WFB_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, st));
+        return WFB_OK;
+    }
+    int rc = sg.init();
+    if (rc != WFB_OK) return rc;
+    const uint8_t* src = static_cast<const uint8_t*>(src_host);
+    uint8_t* dst = static_cast<uint8_t*>(dst_dev);
+    for (size_t o = 0; o < bytes; o += kStagePieceBytes) {
+        const size_t len = std::min(kStagePieceBytes, bytes - o);
+        const int k = sg.next;
+        sg.next = (sg.next + 1) % kStagePieces;
+        WFB_CUDA(cudaEventSynchronize(sg.sent[k]));  // the piece's previous content has left
+        parallel_memcpy(sg.buf[k], src + o, len);
+        WFB_CUDA(cudaMemcpyAsync(dst + o, sg.buf[k], len, cudaMemcpyHostToDevice, st));
+        WFB_CUDA(cudaEventRecord(sg.sent[k], st));
+    }
+    return WFB_OK;
+}
+
 struct HostPipe {
     std::mutex mu;
     bool ready = false;
+    Stager stager;
     cudaStream_t s_copy = nullptr, s_comp = nullptr, s_out = nullptr;
     Slot slots[kSlots];
     DevBuf d_hits, d_rules, d_tot;
@@ -249,6 +333,7 @@ struct HostPipe {
             s.pool.release(); s.rows.release(); s.meta.release(); s.feat.release(); s.counts.release(); s.ws.release();
         }
         d_hits.release(); d_rules.release(); d_tot.release();
+        stager.release();
     }
 };
 HostPipe* g_pipes[kMaxDevices];
@@ -273,6 +358,23 @@ inline int rec_i32(const uint8_t* row, int off) {
 }
 
 }  // namespace
+
+static int staged_upload(void* dst_dev, const void* src_host, size_t bytes, cudaStream_t st) {
+    const bool pinned = host_pointer_is_pinned(src_host);
+    if (pinned || bytes < (4u << 20)) {
+        WFB_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, st));
+        return WFB_OK;
+    }
+    int device = 0;
+    WFB_CUDA(cudaGetDevice(&device));
+    HostPipe* hp = host_pipe(device);
+    if (hp == nullptr) {
+        WFB_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, st));
+        return WFB_OK;
+    }
+    std::lock_guard<std::mutex> pipe_lock(hp->mu);
+    return staged_h2d(hp->stager, dst_dev, src_host, bytes, st, false);
+}
 
 // pool_keep / meta_keep: device buffers for the WHOLE pool (pool_len elements, 16-byte aligned, readable to the next
 // 16-byte boundary) and the records' metadata (n rows): every chunk is uploaded / unpacked straight into its place there
@@ -337,6 +439,8 @@ static int process_host_impl(const void* records_host, int64_t n, const void* po
     }
     cudaStream_t s_copy = hp->s_copy, s_comp = hp->s_comp, s_out = hp->s_out;
     Slot* slots = hp->slots;
+    const bool pool_pinned = pool_len == 0 || host_pointer_is_pinned(pool_host);
+    const bool rows_pinned = n == 0 || host_pointer_is_pinned(records_host);
     DevBuf &d_hits = hp->d_hits, &d_rules = hp->d_rules, &d_tot = hp->d_tot;
     auto cleanup = [&]() {  // leave the pipeline idle: nothing of this call is still in flight
         cudaStreamSynchronize(s_copy);
@@ -399,8 +503,7 @@ again:
     // resident mode uploads EVERY sample of the pool (also those no record refers to): chunk ranges are stretched to tile
     // [0, pool_len); records out of wave_offset order get the whole pool in one copy before the first chunk
     long long keep_hi = 0;
-    if (pool_keep && scan_all && pool_len > 0)
-        PH_CUDA(cudaMemcpyAsync(pool_keep, pool, (size_t)pool_len * esz, cudaMemcpyHostToDevice, s_copy));
+    if (pool_keep && scan_all && pool_len > 0) PH_CHECK(staged_h2d(hp->stager, pool_keep, pool, (size_t)pool_len * esz, s_copy, pool_pinned));
     int64_t chunk_idx = 0;
     for (int64_t r0 = 0; r0 < n; r0 += chunk_records, ++chunk_idx) {
         const int64_t r1 = std::min<int64_t>(n, r0 + chunk_records), m = r1 - r0;
@@ -460,8 +563,8 @@ again:
         // the slot's previous results must have left the device before we overwrite them
         PH_CUDA(cudaStreamWaitEvent(s_copy, s.drained, 0));
         PH_CUDA(cudaStreamWaitEvent(s_copy, s.computed, 0));
-        if (pool_bytes) PH_CUDA(cudaMemcpyAsync(pool_dst, pool + (size_t)lo_al * esz, pool_bytes, cudaMemcpyHostToDevice, s_copy));
-        PH_CUDA(cudaMemcpyAsync(s.rows.p, rows + (size_t)r0 * kRecordsRowBytes, (size_t)m * kRecordsRowBytes, cudaMemcpyHostToDevice, s_copy));
+        if (pool_bytes) PH_CHECK(staged_h2d(hp->stager, pool_dst, pool + (size_t)lo_al * esz, pool_bytes, s_copy, pool_pinned));
+        PH_CHECK(staged_h2d(hp->stager, s.rows.p, rows + (size_t)r0 * kRecordsRowBytes, (size_t)m * kRecordsRowBytes, s_copy, rows_pinned));
         PH_CUDA(cudaEventRecord(s.copied, s_copy));
         PH_CUDA(cudaStreamWaitEvent(s_comp, s.copied, 0));
         PH_CUDA(cudaStreamWaitEvent(s_comp, s.drained, 0));

@@ -248,7 +248,8 @@ def run_reference(args):
         "vs_baseline": None,
         "dtype": "u16",
         "data": "synthetic",
-        "config": workload_config(args, {"hits_per_record": hpr}),
+        "config": workload_config(args, {"hits_per_record": round(hpr, 1)}),  # nominal (one decimal): the same in both arms
+        "hits_per_record_measured": hpr,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -480,7 +481,7 @@ def run_ours(args):
             "vs_baseline": None,
             "dtype": "u16",
             "data": "synthetic",
-            "config": workload_config(args, {"hits_per_record": hits_all / records_all}),
+            "config": workload_config(args, {"hits_per_record": round(hits_all / records_all, 1)}),  # nominal; roofline carries the exact value
             "raw_sample_GBps": records_all * 2 * N_SAMPLES / (ms_per_step * 1e-3) / 1e9,
             "roofline": roofline,
             "roofline_features_only": feat_only,

@@ -95,3 +95,30 @@ def test_stream_slots_overlap_and_reuse():
         jobs[-1].rows_host = jobs[-1].out["hits"][: total * 60].cpu().numpy()
     assert np.concatenate([j.rows_host for j in jobs]).tobytes() == want.tobytes()
     assert [j.slot for j in jobs] == [0, 1, 0, 1] and slots.chunks == 4
+
+
+def test_hit_stream_on_the_filtered_pool_with_channel_rules(run_data):
+    """use_filtered = True: the stream reads records + wave_pool_filtered (float32 lane-per-record kernel per chunk);
+    per-channel thresholds and fixed baselines apply; rows equal the oracle's on the same float32 pool."""
+    from oracle import np_oracle as O
+    from waveformanalysis_b200.plugins import B200HitThresholdStreamPlugin
+
+    rec, pool = run_data
+    rng = np.random.default_rng(3)
+    poolf = pool.astype(np.float32) + rng.normal(0, 0.25, len(pool)).astype(np.float32)
+    cc = {"channels": {"0:2": {"threshold": 30.0}, "0:6": {"fixed_baseline": 7995.25}}}
+    cfg = {"wave_source": "records", "use_filtered": True, "threshold": 13.0, "channel_config": cc, "height_range": (0, None)}
+    ctx = Ctx(cfg, {"records": rec, "wave_pool": pool, "wave_pool_filtered": poolf})
+    plugin = B200HitThresholdStreamPlugin()
+    plugin.chunk_size = 900
+    plugin.required_halo_ns = 1000
+    chunks = list(plugin.compute(ctx, "run"))
+    got_h = np.concatenate([c.data for c in chunks])
+    got_f = np.concatenate([c.metadata["basic_features"] for c in chunks])
+    want_h = O.threshold_hits(rec, poolf, threshold=13.0, thresholds={(0, 2): 30.0})
+    want_f = O.basic_features(rec, poolf, height_range=(0, None), fixed_baseline={(0, 6): 7995.25})
+    from conftest import assert_rows_match
+
+    assert_rows_match(got_h, want_h, what="stream hits on the filtered pool", float_exact=("height",))
+    assert_rows_match(got_f, want_f, what="stream features on the filtered pool", float_exact=("height", "amp", "max_abs_diff"))
+    assert len(want_h) > 2000

@@ -246,3 +246,69 @@ def test_after_path_ops_fuzz():
             got, want = ops.pair_events(off, ts, ar, he, dt, 100.0, nch), O.pair_events(off, ts, ar, he, dt, 100.0, nch)
             for k in want:
                 assert np.array_equal(got[k], want[k], equal_nan=True), (n, nch, k)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_float32_lane_and_warp_kernels_agree_on_random_pools(seed, monkeypatch):
+    """Differential fuzz of the two float32 kernels (fused_f32.cuh lane-per-record / fused_features_hits.cu warp-per-record)
+    and the oracle: random lengths, offsets, polarities, thresholds (per channel too), extensions, samples that sit on
+    the threshold bound, NaN / inf samples inside and outside runs."""
+    from oracle import np_oracle as O
+    from waveformanalysis_b200 import engine
+    from waveformanalysis_b200.dtypes import RECORDS_DTYPE
+
+    rng = np.random.default_rng(1000 + seed)
+    n = 1500
+    Lmax = int(rng.choice([37, 128, 515, 800]))
+    lens = rng.integers(1, Lmax + 1, n)
+    lens[rng.random(n) < 0.5] = Lmax
+    rec = np.zeros(n, dtype=RECORDS_DTYPE)
+    rec["record_id"] = np.arange(n)
+    rec["timestamp"] = np.cumsum(rng.integers(1, 5000, n)) * 1000
+    rec["dt"] = rng.choice([1, 2, 4], n)
+    rec["board"] = rng.integers(0, 2, n)
+    rec["channel"] = rng.integers(0, 4, n)
+    rec["event_length"] = lens
+    rec["wave_offset"] = np.cumsum(lens + rng.integers(0, 5, n)) - lens
+    rec["baseline"] = rng.choice([0.0, 12.5, 1000.0, -40.25, 16000.7], n) + rng.uniform(-1, 1, n)
+    rec["polarity"] = rng.choice(["unknown", "negative", "positive"], n)
+    total = int(rec["wave_offset"][-1] + lens[-1] + 8)
+    pool = np.zeros(total, dtype=np.float32)
+    thr = float(rng.choice([3.0, 9.5, 25.0]))
+    positive = np.asarray(rec["polarity"]) == "positive"
+    for i in range(n):
+        o, L, b = int(rec["wave_offset"][i]), int(lens[i]), float(rec["baseline"][i])
+        w = (b + rng.normal(0, thr / 3.0, L)).astype(np.float32)
+        sign = 1.0 if positive[i] else -1.0
+        for _ in range(int(rng.integers(0, 4))):
+            a0 = int(rng.integers(0, L))
+            a1 = min(L, a0 + int(rng.integers(1, 40)))
+            w[a0:a1] += np.float32(sign * thr * rng.uniform(1.0, 6.0))
+        x0 = np.float32(b + sign * thr)
+        for k in rng.integers(0, L, size=3):  # on the bound and its float32 neighbours
+            w[k] = [np.nextafter(x0, np.float32(-np.inf)), x0, np.nextafter(x0, np.float32(np.inf))][int(k) % 3]
+        if i % 37 == 0 and L > 4:
+            w[int(rng.integers(0, L))] = np.float32(sign * np.inf)  # a sample far above threshold
+        if i % 41 == 0 and L > 4:
+            w[int(rng.integers(0, L))] = np.float32(-sign * np.inf)  # far below: never part of a run
+        pool[o:o + L] = w
+    ext = (int(rng.integers(0, 3)), int(rng.integers(0, 3)))
+    thrs = {(0, 1): thr * 2.0, (1, 3): thr * 0.5}
+    want_h = O.threshold_hits(rec, pool, threshold=thr, thresholds=thrs, left_extension=ext[0], right_extension=ext[1])
+    want_f = O.basic_features(rec, pool, height_range=(2, 30), area_range=(1, -1))
+    outs = {}
+    for impl in ("lane", "warp"):
+        monkeypatch.setenv("WFB_F32_IMPL", impl)
+        outs[impl] = engine.process_host(rec, pool, threshold=thr, thresholds=thrs, left_extension=ext[0], right_extension=ext[1],
+                                         height_range=(2, 30), area_range=(1, -1), chunk_records=400)
+        finite = np.isfinite(want_h["height"]) & np.isfinite(want_h["integral"])
+        for f in want_h.dtype.names:
+            g, w_ = outs[impl]["hits"][f], want_h[f]
+            if w_.dtype.kind in "iu":
+                assert np.array_equal(g, w_), (impl, f)
+            else:
+                assert np.allclose(g[finite], w_[finite], rtol=1e-5, atol=1e-3), (impl, f)
+        ok = np.isfinite(want_f["area"]) & np.isfinite(want_f["height"]) & np.isfinite(want_f["max_abs_diff"])
+        for f in ("height", "amp", "area", "max_abs_diff"):
+            assert np.allclose(outs[impl]["features"][f][ok], want_f[f][ok], rtol=1e-5, atol=1e-3), (impl, f)
+    assert len(want_h) > 1000

@@ -57,8 +57,11 @@ __device__ __forceinline__ void f32_stream(const FHArgs& a, const float* pool, c
     // sig > 0 <=> (double)y < bn <=> y <= ybn (the largest float below bn): one float compare, one float64 add per sample
     float ybn = (float)bn;
     if ((double)ybn >= bn) ybn = f32_step(ybn, false);
-    bool open = false;
-    int rs = 0, re = 0, bpos = 0, nh = 0, trem = 0, cnt = 0;
+    // st: -1 the run is open, k > 0 the run has ended and k samples of its right extension are still to come, 0 idle.
+    // best sample / count / sum are folded on EVERY sample: while idle they collect garbage that the next run start
+    // resets, so the per-sample code needs no "inside a window" predicate.
+    int st = 0;
+    int rs = 0, re = 0, bpos = 0, nh = 0, cnt = 0;
     float by = INFINITY;
     double acc = 0.0;  // sum of the signal-side samples y
     float y1 = 0.f, y2 = 0.f;  // the two samples in front of the current one
@@ -81,14 +84,13 @@ __device__ __forceinline__ void f32_stream(const FHArgs& a, const float* pool, c
     auto hit_step = [&](float x, int i) {
         const float y = __uint_as_float(__float_as_uint(x) ^ sgn);
         const bool in = y <= yb;
-        if (in != open) {  // an edge (rare per lane)
-            if (in) {      // a run starts
-                if (trem > 0) {  // ... on the last tail sample of the run before: that run takes the sample and is done
+        if (in != (st < 0)) {  // an edge (rare per lane)
+            if (in) {          // a run starts
+                if (st > 0) {  // ... on the last tail sample of the run before: that run takes the sample and is done
                     fold(y, i);
                     emit();
-                    trem = 0;
                 }
-                open = true;
+                st = -1;
                 rs = i;
                 by = INFINITY;
                 acc = 0.0;
@@ -96,24 +98,15 @@ __device__ __forceinline__ void f32_stream(const FHArgs& a, const float* pool, c
                 // the left extension, in index order (strict comparisons keep the FIRST maximum)
                 if (left >= 2 && i >= 2) fold(y2, i - 2);
                 if (left >= 1 && i >= 1) fold(y1, i - 1);
-            } else {       // the run ends in front of this sample, which is the first of the right extension
-                open = false;
+            } else {           // the run ends in front of this sample, which is the first of the right extension
                 re = i;
-                trem = right;
+                st = right;
                 if (right == 0) emit();
             }
         }
-        // the sample joins the run while it is open or in its tail: selects instead of branches (nearly every step has
-        // some lane of the warp in a run, a branch would only add its overhead)
-        const bool w = open || trem > 0;
-        const bool lt = w && (y < by);
-        by = lt ? y : by;
-        bpos = lt ? i : bpos;
-        const bool sg = w && (y <= ybn);
-        cnt += sg ? 1 : 0;
-        acc += (double)(sg ? y : 0.f);
-        const bool fire = !open && trem == 1;  // the last tail sample
-        trem -= (!open && trem > 0) ? 1 : 0;
+        fold(y, i);
+        const bool fire = st == 1;  // the last tail sample
+        st -= (st > 0) ? 1 : 0;
         if (fire) emit();
         y2 = y1;
         y1 = y;
@@ -211,10 +204,10 @@ __device__ __forceinline__ void f32_stream(const FHArgs& a, const float* pool, c
     if (HITS) {
         // behind the record: padding samples (true zeros) up to the padded width belong to the window of a run that
         // ends within `right` samples of the record end
-        if (r.len > 0 && (open || trem > 0)) {
-            if (open) { re = r.len; trem = right; }
+        if (r.len > 0 && st != 0) {
+            if (st < 0) { re = r.len; st = right; }
             const float yp = __uint_as_float(sgn);  // +-0
-            for (int idx = r.len; trem > 0 && idx < a.lmax; ++idx, --trem) fold(yp, idx);
+            for (int idx = r.len; st > 0 && idx < a.lmax; ++idx, --st) fold(yp, idx);
             emit();
         }
         ws.carry_n[lane] = nh;

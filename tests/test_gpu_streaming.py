@@ -122,3 +122,21 @@ def test_hit_stream_on_the_filtered_pool_with_channel_rules(run_data):
     assert_rows_match(got_h, want_h, what="stream hits on the filtered pool", float_exact=("height",))
     assert_rows_match(got_f, want_f, what="stream features on the filtered pool", float_exact=("height", "amp", "max_abs_diff"))
     assert len(want_h) > 2000
+
+
+def test_abandoned_stream_leaves_nothing_in_flight(run_data):
+    """A consumer that stops after the first chunk: the generator's finally waits for the chunks still on the device;
+    the next pass on the same plugin object gives the full result."""
+    from waveformanalysis_b200 import engine
+    from waveformanalysis_b200.plugins import B200HitThresholdStreamPlugin
+
+    rec, pool = run_data
+    ctx = Ctx({"wave_source": "records", "threshold": 14.0}, {"records": rec, "wave_pool": pool})
+    plugin = B200HitThresholdStreamPlugin()
+    plugin.chunk_size = 400
+    gen = plugin.compute(ctx, "run")
+    first = next(gen)
+    gen.close()
+    assert len(first.data) > 0 and plugin.stream_stats["chunks"] >= 1
+    want = engine.process_host(rec, pool, threshold=14.0)["hits"]
+    assert np.concatenate([c.data for c in plugin.compute(ctx, "run")]).tobytes() == want.tobytes()

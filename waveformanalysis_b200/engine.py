@@ -594,3 +594,9 @@ class StreamSlots:
     def finish(st: StagedChunk) -> None:
         if st.done is not None:
             st.done.synchronize()
+
+    def close(self) -> None:
+        """Wait for everything the slots still have in flight (a consumer that abandons the stream, an exception in a
+        chunk): the slot buffers go back to the allocator when this object dies and must not be in use then."""
+        self.copy_stream.synchronize()
+        self.compute_stream.synchronize()

@@ -170,6 +170,7 @@ class GpuStreamingMixin:
                     yield out
         finally:
             if slots is not None:
+                slots.close()  # also when the consumer stops early or a chunk raised: nothing stays in flight
                 self.stream_stats.update(chunks=slots.chunks, bytes_uploaded=slots.bytes_uploaded)
 
 

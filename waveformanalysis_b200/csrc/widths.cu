@@ -14,24 +14,32 @@ namespace wfb {
 // and the interpolated crossing in float32, sums with the int64 peak position in float64.
 // ---------------------------------------------------------------------------------------------
 
-// np.mean of the first n (<= 50) float32 samples: numpy's pairwise sum for n < 128 keeps eight
-// partial sums and folds them as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then adds the tail.
-__device__ float numpy_mean_f32(const float* w, int n) {
-    float res;
+// np.mean of the first n (<= 50) float32 samples: numpy's pairwise sum for n < 128 keeps eight partial sums (r[k] takes
+// samples k, k + 8, ...), folds them as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) and adds the tail n % 8 one by one.
+// Computed by the warp: lanes 0..7 own the eight partial sums (each adds its samples in numpy's order), the
+// fold is the same tree through shuffles, lane 0 adds the tail - the result is bit-identical, the dependent chain is six
+// loads deep instead of fifty.  Returns the mean in every lane.
+__device__ __forceinline__ float numpy_mean_f32_warp(const float* w, int n) {
+    const int lane = lane_id();
+    float res = 0.f;
     if (n < 8) {
-        res = 0.f;
-        for (int i = 0; i < n; ++i) res = __fadd_rn(res, w[i]);
+        if (lane == 0)
+            for (int i = 0; i < n; ++i) res = __fadd_rn(res, w[i]);
     } else {
-        float r[8];
-        for (int k = 0; k < 8; ++k) r[k] = w[k];
-        int i;
-        for (i = 8; i < n - (n % 8); i += 8)
-            for (int k = 0; k < 8; ++k) r[k] = __fadd_rn(r[k], w[i + k]);
-        res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
-                        __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
-        for (; i < n; ++i) res = __fadd_rn(res, w[i]);
+        const int body = n - (n % 8);
+        float r = 0.f;
+        if (lane < 8) {
+            r = w[lane];
+            for (int i = 8 + lane; i < body; i += 8) r = __fadd_rn(r, w[i]);
+        }
+        const float p1 = __fadd_rn(r, __shfl_down_sync(kFull, r, 1));    // lanes 0, 2, 4, 6: r0+r1, r2+r3, r4+r5, r6+r7
+        const float p2 = __fadd_rn(p1, __shfl_down_sync(kFull, p1, 2));  // lanes 0, 4
+        res = __fadd_rn(p2, __shfl_down_sync(kFull, p2, 4));             // lane 0
+        if (lane == 0)
+            for (int i = body; i < n; ++i) res = __fadd_rn(res, w[i]);
     }
-    return __fdiv_rn(res, (float)n);
+    res = __fdiv_rn(res, (float)n);
+    return __shfl_sync(kFull, res, 0);
 }
 
 // first index in [lo, hi) where pred(i) holds, -1 if none; warp-cooperative
@@ -118,8 +126,7 @@ __global__ void __launch_bounds__(256) waveform_width_kernel(const T* __restrict
     double bl64 = 0.0;
     float bl32 = 0.f;
     if (F32) {
-        if (lane == 0) bl32 = numpy_mean_f32(reinterpret_cast<const float*>(w), nb);
-        bl32 = __shfl_sync(kFull, bl32, 0);
+        bl32 = numpy_mean_f32_warp(reinterpret_cast<const float*>(w), nb);
     } else {
         long long s = 0;
         for (int i = lane; i < nb; i += 32) s += (long long)w[i];

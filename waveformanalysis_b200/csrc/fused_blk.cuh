@@ -28,7 +28,12 @@
 namespace wfb {
 
 constexpr int kBQRing = 64;    // item slots per warp: < 32 complete items + <= 32 pushed in the current step
-constexpr int kBQWords = 27;   // 32-bit words per slot; odd, so that the lanes' scalar accesses fall into distinct banks
+#ifndef WFB_BQ_WORDS
+#define WFB_BQ_WORDS 27
+#endif
+constexpr int kBQWords = WFB_BQ_WORDS;  // 32-bit words per slot; odd, so that the lanes' scalar accesses fall into distinct banks
+constexpr int kBQPark = (kBQWords - 19) / 2;  // {key, sum} pairs of ended runs a slot can park (words 19 ..)
+static_assert(kBQWords % 2 == 1 && kBQPark >= 1, "slot size");
 // slot words: 0 last word of the previous block, 1..16 the block (offset-domain samples), 17 first word of the next
 // block, 18 owner | block << 5, 19 first-minimum key of the FULL blocks in front (key << 16 | block) or ~0, 20 their
 // raw sample sum; 19 .. 26 are reused by the round for the {key, sum} pairs of up to four runs that end in the block.
@@ -146,7 +151,7 @@ __device__ __forceinline__ void blk_round(WarpHits& ws, unsigned* bq, int qh, in
                 kvp[w] |= ~((b2 & 1u) * 0xffffu + (b2 >> 1) * 0xffff0000u);
             }
         }
-        unsigned* fst = sl + 19;  // four parked {key, sum} pairs: words 19 .. 26
+        unsigned* fst = sl + 19;  // kBQPark parked {key, sum} pairs: words 19 .. (the last one is overwritten by later runs)
         unsigned key = 0xffffffffu, sum = 0u, m32 = 0u;
         int nf = 0;  // runs that ended so far
         bool pprev = in_open;
@@ -155,7 +160,7 @@ __device__ __forceinline__ void blk_round(WarpHits& ws, unsigned* bq, int qh, in
             const unsigned kv = (j & 1) ? (kvp[j >> 1] >> 16) : (kvp[j >> 1] & 0xffffu);
             const bool p = (int)kv <= o_kmax;
             if (pprev && !p) {  // a run ended in front of j: park it (the fourth slot is overwritten by later ones)
-                unsigned* f = fst + 2 * min(nf, 3);
+                unsigned* f = fst + 2 * min(nf, kBQPark - 1);
                 f[0] = key;
                 f[1] = sum;
                 ++nf;
@@ -199,7 +204,7 @@ __device__ __forceinline__ void blk_round(WarpHits& ws, unsigned* bq, int qh, in
                 sm &= sm - 1u;
             }
             unsigned hkey = 0xffffffffu, cnt = 0u, skv = 0u;
-            if (k < 3 || (k == 3 && nf <= 4)) {
+            if (k < kBQPark - 1 || (k == kBQPark - 1 && nf <= kBQPark)) {
                 if (je > js) {  // (an incoming run that ends with the block's first sample has no sample here)
                     hkey = fst[2 * k] + (unsigned)i0;
                     skv = fst[2 * k + 1];

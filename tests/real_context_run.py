@@ -6,7 +6,7 @@
 ``cpu``: the reference's own plugins (``profiles.cpu_default()``).  ``b200``: the same Context with
 ``ctx.register(*b200_default(), allow_override=True)`` on top (core/context.py:532-621), i.e. exactly the
 binding INTEGRATION.md shows.  Inputs: two synthetic V1725 ``.bin`` files written to WORKDIR and handed to
-the Context as ``raw_files``; everything downstream (records, wave_pool, wave_pool_filtered, basic_features,
+the Context as ``raw_files``; everything downstream (st_waveforms, records, wave_pool, wave_pool_filtered, basic_features,
 hit_threshold, the three hit-merge outputs with merge_gap_ns = 50, hit_grouped) is pulled with
 ``ctx.get_data`` (core/context_execution.py:140-183), so dependency resolution, the memmap cache write and
 the memmap views handed to downstream plugins are the reference's.  Used by tests/test_real_context.py
@@ -64,8 +64,8 @@ def main():
     ctx._set_data(run, "raw_files", [[paths[0]], [paths[1]]])
 
     out = {}
-    for name in ("records", "wave_pool", "wave_pool_filtered", "basic_features", "hit_threshold", "hit_merge_clusters", "hit_merged",
-                 "hit_merged_components", "hit_grouped"):
+    for name in ("st_waveforms", "records", "wave_pool", "wave_pool_filtered", "basic_features", "hit_threshold", "hit_merge_clusters",
+                 "hit_merged", "hit_merged_components", "hit_grouped"):
         res = ctx.get_data(run, name)
         if hasattr(res, "columns"):  # DataFrame: one array per column (object columns flattened)
             for col in res.columns:

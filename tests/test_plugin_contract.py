@@ -85,7 +85,7 @@ def test_structured_rows_as_pool_without_repacking():
 def test_contract_matches_reference_plugins():
     _import_ref()
     from waveform_analysis.core.plugins.builtin.cpu import (basic_features, dataframe, event_analysis, hit_finder, hit_merge, peak_finding, records,
-                                                            s1_s2_classifier, waveform_width, waveform_width_integral)
+                                                            s1_s2_classifier, waveform_width, waveform_width_integral, waveforms)
 
     from waveformanalysis_b200 import plugins as P
 
@@ -106,6 +106,7 @@ def test_contract_matches_reference_plugins():
         (P.B200DataFramePlugin, dataframe.DataFramePlugin),
         (P.B200PairedEventsPlugin, event_analysis.PairedEventsPlugin),
         (P.B200S1S2ClassifierPlugin, s1_s2_classifier.S1S2ClassifierPlugin),
+        (P.B200WaveformsPlugin, waveforms.WaveformsPlugin),
     ]
     for ours, ref in pairs:
         assert ours.provides == ref.provides

@@ -30,7 +30,9 @@ class B200WaveformsPlugin(Plugin):
     uses_run_config = True
     description = "Extract waveforms from raw CSV files and structure them into NumPy structured arrays."
     save_when = "always"
-    output_dtype = create_record_dtype(800)
+    # the reference's class default (DEFAULT_WAVE_LENGTH = 1500, core/processing/dtypes.py:16): the V1725 branch does not set a
+    # per-run dtype, so the Context casts its rows to this width (core/plugins/core/validation.py:182-184)
+    output_dtype = create_record_dtype(1500)
     options = {
         "daq_adapter": Option(default="vx2730", type=str, help="DAQ adapter name (e.g., 'vx2730')"),
         "wave_length": Option(default=None, type=int, help="Waveform length (samples); detected from the data when None"),

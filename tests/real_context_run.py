@@ -64,8 +64,11 @@ def main():
     ctx._set_data(run, "raw_files", [[paths[0]], [paths[1]]])
 
     out = {}
-    for name in ("st_waveforms", "records", "wave_pool", "wave_pool_filtered", "basic_features", "hit_threshold", "hit_merge_clusters",
-                 "hit_merged", "hit_merged_components", "hit_grouped"):
+    names = ["st_waveforms", "records", "wave_pool", "wave_pool_filtered", "basic_features", "hit_threshold", "hit_merge_clusters",
+             "hit_merged", "hit_merged_components", "hit_grouped"]
+    if os.environ.get("WFB_REAL_CONTEXT_ALL", "1") != "0":  # the default-profile chain as well: hit -> waveform_width -> s1_s2, df ...
+        names += ["hit", "waveform_width", "waveform_width_integral", "s1_s2", "df", "df_events", "df_paired"]
+    for name in names:
         res = ctx.get_data(run, name)
         if hasattr(res, "columns"):  # DataFrame: one array per column (object columns flattened)
             for col in res.columns:

@@ -195,7 +195,9 @@ def pair_events_frame(df_events, n_channels: int, start_channel_slice: int, time
         return df_events[df_events["dt/ns"] <= tw].copy()
     areas_key = "areas" if "areas" in df_events.columns else "charges"
     heights_key = "heights" if "heights" in df_events.columns else "peaks"
-    csr = df_events.attrs.get("_wfb_csr") if hasattr(df_events, "attrs") else None
+    from .grouping import member_arrays_of
+
+    csr = member_arrays_of(df_events)
     if isinstance(csr, dict) and len(csr.get("offsets", ())) == n + 1:
         offsets, ts, area, height = csr["offsets"], csr["timestamps"], csr["areas"], csr["heights"]
     else:

@@ -16,6 +16,22 @@ HIT_GROUPED_COLUMNS = ["event_id", "t_min", "t_max", "dt/ns", "n_hits", "dt", "b
 DF_EVENTS_COLUMNS = ["event_id", "t_min", "t_max", "dt/ns", "n_hits", "channels", "areas", "heights", "timestamps"]
 
 
+_MEMBER_ARRAYS: dict = {}
+
+
+def stash_member_arrays(frame, arrays: dict) -> None:
+    """Remember the flat member arrays of a df_events frame for as long as that frame object lives."""
+    import weakref
+
+    key = id(frame)
+    _MEMBER_ARRAYS[key] = arrays
+    weakref.finalize(frame, _MEMBER_ARRAYS.pop, key, None)
+
+
+def member_arrays_of(frame):
+    return _MEMBER_ARRAYS.get(id(frame))
+
+
 def _ragged(values: np.ndarray, members: np.ndarray, offsets: np.ndarray) -> list:
     flat = values[members]
     return np.split(flat, offsets[1:-1]) if len(offsets) > 1 else []
@@ -109,7 +125,9 @@ class B200GroupedEventsPlugin(Plugin):
             "channels": _ragged(ch, m, off), "areas": _ragged(areas, m, off),
             "heights": _ragged(heights, m, off), "timestamps": _ragged(ts, m, off),
         })
-        # the flat member arrays, for B200PairedEventsPlugin (saves re-flattening the object columns)
-        out.attrs["_wfb_csr"] = {"offsets": off, "timestamps": ts[m], "areas": areas[m].astype(np.float32),
-                                 "heights": heights[m].astype(np.float32)}
+        # the flat member arrays, for B200PairedEventsPlugin (saves re-flattening the object columns).  Kept beside the
+        # frame, not in df.attrs: the Context saves DataFrames with to_parquet, which json-dumps the attrs
+        # (core/storage/memmap.py:886)
+        stash_member_arrays(out, {"offsets": off, "timestamps": ts[m], "areas": areas[m].astype(np.float32),
+                                  "heights": heights[m].astype(np.float32)})
         return out

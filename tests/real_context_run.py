@@ -26,6 +26,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     mode, out_path, work = sys.argv[1], sys.argv[2], sys.argv[3]
+    scenario = sys.argv[4] if len(sys.argv) > 4 else "records"
     import numpy as np
     from refctx import import_reference
 
@@ -55,8 +56,17 @@ def main():
     ctx.set_config({"daq_adapter": "v1725"})
     for name in ("records", "wave_pool"):
         ctx.set_config({"daq_adapter": "v1725", "dt": 4}, plugin_name=name)
-    ctx.set_config({"wave_source": "records", "height_range": (10, 60)}, plugin_name="basic_features")
-    ctx.set_config({"wave_source": "records", "threshold": 12.0}, plugin_name="hit_threshold")
+    if scenario == "records":
+        ctx.set_config({"wave_source": "records", "height_range": (10, 60)}, plugin_name="basic_features")
+        ctx.set_config({"wave_source": "records", "threshold": 12.0}, plugin_name="hit_threshold")
+    else:
+        # "waves": structured rows as the wave source (st_waveforms for the features, filtered_waveforms for the hits and
+        # the charge widths), records on the filtered pool for `hit`, a per-channel threshold and a fixed baseline
+        cc = {"channels": {"0:3": {"threshold": 30.0, "fixed_baseline": 7990.0}}}
+        ctx.set_config({"wave_source": "st_waveforms", "height_range": (5, 200), "channel_config": cc}, plugin_name="basic_features")
+        ctx.set_config({"wave_source": "filtered_waveforms", "threshold": 9.0, "left_extension": 1, "channel_config": cc}, plugin_name="hit_threshold")
+        ctx.set_config({"wave_source": "records", "use_filtered": True, "height": 6.0, "width": 2}, plugin_name="hit")
+        ctx.set_config({"wave_source": "filtered_waveforms"}, plugin_name="waveform_width_integral")
     for name in ("hit_merge_clusters", "hit_merged", "hit_merged_components"):
         ctx.set_config({"merge_gap_ns": 50.0}, plugin_name=name)
     ctx.set_config({"time_window_ns": 100.0}, plugin_name="hit_grouped")
@@ -68,6 +78,8 @@ def main():
              "hit_merged", "hit_merged_components", "hit_grouped"]
     if os.environ.get("WFB_REAL_CONTEXT_ALL", "1") != "0":  # the default-profile chain as well: hit -> waveform_width -> s1_s2, df ...
         names += ["hit", "waveform_width", "waveform_width_integral", "s1_s2", "df", "df_events", "df_paired"]
+    if scenario != "records":
+        names = ["basic_features", "hit_threshold", "hit", "waveform_width", "waveform_width_integral"]
     for name in names:
         res = ctx.get_data(run, name)
         if hasattr(res, "columns"):  # DataFrame: one array per column (object columns flattened)
@@ -82,6 +94,10 @@ def main():
                     out[f"{name}.{col}"] = v
         else:
             out[name] = np.asarray(res)
+    if scenario != "records":
+        np.savez(out_path, **out)
+        print("REAL_CONTEXT_DONE", mode, scenario, {k: (v.shape, str(v.dtype)[:40]) for k, v in out.items() if "." not in k})
+        return
     # ---- the streaming side: signal_peaks_stream over the reference's own chunk iterator, hit_threshold_stream ----------
     from waveform_analysis.core.plugins.builtin.streaming.cpu.signal_peaks import SignalPeaksStreamPlugin
 

@@ -45,6 +45,25 @@ def main():
             f.write(make_v1725_blob(**kw))
         paths.append(p)
 
+    if scenario == "csv":
+        # VX2730 CSV files (utils/formats/vx2730.py:70-107: ';' separated, two header rows in the first file of a channel,
+        # board;channel;timestamp_ps;4 unused columns;samples...), one file per channel, ties in time across channels
+        rng = np.random.default_rng(5)
+        paths = []
+        n_ev, L = 160, 120
+        t = np.cumsum(rng.integers(200, 900, n_ev)) * 2000
+        for c in range(4):
+            pth = os.path.join(work, f"wave_CH{c}_0.CSV")
+            tc = t + (0 if c % 2 == 0 else rng.integers(-3, 4, n_ev) * 2000)
+            with open(pth, "w") as f:
+                f.write("HEADER LINE 1;;;\nBOARD;CHANNEL;TIMETAG;ENERGY;ENERGYSHORT;FLAGS;PROBE_CODE;SAMPLES\n")
+                for i in range(n_ev):
+                    w = 8000 + 10 * c + rng.normal(0, 3, L)
+                    s0 = int(rng.integers(45, L - 30))
+                    w[s0:s0 + 12] -= rng.uniform(30, 400) * np.exp(-np.arange(12) / 5.0)
+                    f.write(";".join(["0", str(c), str(int(tc[i])), "0", "0", "0", "0"] + [str(int(v)) for v in np.round(w)]) + "\n")
+            os.utime(pth, (1_700_000_000, 1_700_000_000))  # records.time = file mtime + timestamp // 1000: the same in both runs
+            paths.append(pth)
     ctx = Context(storage_dir=os.path.join(work, f"cache_{mode}"))
     ctx.register(*ref_profiles.cpu_default())
     if mode == "b200":
@@ -53,10 +72,13 @@ def main():
         assert plugin_api.HAVE_REFERENCE
         ctx.register(*profiles.b200_default(), allow_override=True)
         assert type(ctx._plugins["hit_threshold"]).__name__ == "B200ThresholdHitPlugin"
-    ctx.set_config({"daq_adapter": "v1725"})
-    for name in ("records", "wave_pool"):
-        ctx.set_config({"daq_adapter": "v1725", "dt": 4}, plugin_name=name)
-    if scenario == "records":
+    if scenario == "csv":
+        ctx.set_config({"daq_adapter": "vx2730"})
+    else:
+        ctx.set_config({"daq_adapter": "v1725"})
+        for name in ("records", "wave_pool"):
+            ctx.set_config({"daq_adapter": "v1725", "dt": 4}, plugin_name=name)
+    if scenario in ("records", "csv"):
         ctx.set_config({"wave_source": "records", "height_range": (10, 60)}, plugin_name="basic_features")
         ctx.set_config({"wave_source": "records", "threshold": 12.0}, plugin_name="hit_threshold")
     else:
@@ -71,15 +93,17 @@ def main():
         ctx.set_config({"merge_gap_ns": 50.0}, plugin_name=name)
     ctx.set_config({"time_window_ns": 100.0}, plugin_name="hit_grouped")
     run = "run_real"
-    ctx._set_data(run, "raw_files", [[paths[0]], [paths[1]]])
+    ctx._set_data(run, "raw_files", [[p] for p in paths])
 
     out = {}
     names = ["st_waveforms", "records", "wave_pool", "wave_pool_filtered", "basic_features", "hit_threshold", "hit_merge_clusters",
              "hit_merged", "hit_merged_components", "hit_grouped"]
     if os.environ.get("WFB_REAL_CONTEXT_ALL", "1") != "0":  # the default-profile chain as well: hit -> waveform_width -> s1_s2, df ...
         names += ["hit", "waveform_width", "waveform_width_integral", "s1_s2", "df", "df_events", "df_paired"]
-    if scenario != "records":
+    if scenario == "waves":
         names = ["basic_features", "hit_threshold", "hit", "waveform_width", "waveform_width_integral"]
+    if scenario == "csv":
+        names = ["st_waveforms", "records", "wave_pool", "basic_features", "hit_threshold", "hit_merged", "hit_grouped"]
     for name in names:
         res = ctx.get_data(run, name)
         if hasattr(res, "columns"):  # DataFrame: one array per column (object columns flattened)

@@ -126,3 +126,14 @@ def test_structured_wave_sources_through_a_real_context(tmp_path):
     _compare(cpu, gpu, loose={("hit", "height"): (at_edge, 0.02)})
     assert at_edge.sum() < len(pos) // 10
     assert len(cpu["hit_threshold"]) > 1000 and len(cpu["hit"]) > 1000
+
+
+@pytest.mark.skipif(reference_root() is None, reason="reference package not installed (baseline/_ref)")
+def test_vx2730_csv_route_through_a_real_context(tmp_path):
+    """VX2730 CSV files (the reference's default adapter): the reference's readers parse the text, B200WaveformsPlugin
+    structures the rows on the device (dual baseline), B200RecordsPlugin builds records + wave_pool (device sort with ties
+    across channels), then features, hits, merge and grouping."""
+    cpu = _run("cpu", tmp_path, "csv")
+    gpu = _run("b200", tmp_path, "csv")
+    _compare(cpu, gpu)
+    assert len(cpu["records"]) == 640 and len(cpu["hit_threshold"]) > 500

@@ -130,6 +130,23 @@ def build_bundle(context: Any, run_id: str, plugin: Plugin):
         bl0, bl1 = int(bs[0]), int(bs[1])
     elif isinstance(bs, int):
         bl1 = bl0 + int(bs)
+    # records.time = file epoch + timestamp // 1000 (records.py:168-180, records_builder.py:507-510)
+    epoch_ns = None
+    if adapter is not None and hasattr(adapter, "get_file_epoch"):
+        from pathlib import Path
+
+        raw_files = _seeded(context, run_id, "raw_files")
+        if raw_files is None:
+            try:
+                raw_files = context.get_data(run_id, "raw_files")
+            except Exception:
+                raw_files = None
+        first_file = next((group[0] for group in (raw_files or []) if group), None)
+        if first_file is not None:
+            try:
+                epoch_ns = adapter.get_file_epoch(Path(first_file))
+            except (FileNotFoundError, OSError):
+                epoch_ns = None
     ts, boards, chans, samples = [], [], [], []
     for ch_idx, arr in arrays:
         t = arr[:, c_ts].astype(np.int64)
@@ -144,10 +161,10 @@ def build_bundle(context: Any, run_id: str, plugin: Plugin):
         widths = {s.shape[1] for s in samples}
         if len(widths) != 1:  # channels with different waveform widths: ragged wave_pool
             bundle = ops.build_records_ragged(np.concatenate(ts), np.concatenate(boards), np.concatenate(chans), samples,
-                                              dt_ns=int(dt_ns), baseline_window=(bl0, bl1))
+                                              dt_ns=int(dt_ns), baseline_window=(bl0, bl1), epoch_ns=epoch_ns)
         else:
             rec_h, pool_h, d_pool = ops.build_records(np.concatenate(ts), np.concatenate(boards), np.concatenate(chans), np.vstack(samples),
-                                                      dt_ns=int(dt_ns), baseline_window=(bl0, bl1), return_device=True)
+                                                      dt_ns=int(dt_ns), baseline_window=(bl0, bl1), epoch_ns=epoch_ns, return_device=True)
             bundle = (rec_h, pool_h)
     _apply_polarity(context, run_id, bundle[0])
     if d_pool is not None and len(bundle[0]):

@@ -45,7 +45,7 @@ def main():
             f.write(make_v1725_blob(**kw))
         paths.append(p)
 
-    if scenario == "csv":
+    if scenario in ("csv", "mixed"):
         # VX2730 CSV files (utils/formats/vx2730.py:70-107: ';' separated, two header rows in the first file of a channel,
         # board;channel;timestamp_ps;4 unused columns;samples...), one file per channel, ties in time across channels
         rng = np.random.default_rng(5)
@@ -72,7 +72,7 @@ def main():
         assert plugin_api.HAVE_REFERENCE
         ctx.register(*profiles.b200_default(), allow_override=True)
         assert type(ctx._plugins["hit_threshold"]).__name__ == "B200ThresholdHitPlugin"
-    if scenario == "csv":
+    if scenario in ("csv", "mixed"):
         ctx.set_config({"daq_adapter": "vx2730"})
     else:
         ctx.set_config({"daq_adapter": "v1725"})
@@ -81,6 +81,15 @@ def main():
     if scenario in ("records", "csv"):
         ctx.set_config({"wave_source": "records", "height_range": (10, 60)}, plugin_name="basic_features")
         ctx.set_config({"wave_source": "records", "threshold": 12.0}, plugin_name="hit_threshold")
+    elif scenario == "mixed":
+        # polarity from the channel metadata (the float32 signal branch of the features), a Butterworth filter for one
+        # channel next to the default Savitzky-Golay, hits on the filtered pool, charge widths on records
+        ctx.set_config({"channel_metadata": {"channels": {"0:1": {"polarity": "negative"}, "0:2": {"polarity": "positive"}}}})
+        fcc = {"channels": {"0:3": {"filter_type": "BW", "lowcut": 0.02, "highcut": 0.2, "fs": 1.0, "filter_order": 2}}}
+        ctx.set_config({"channel_config": fcc}, plugin_name="wave_pool_filtered")
+        ctx.set_config({"wave_source": "records", "height_range": (0, None), "area_range": (10, 100)}, plugin_name="basic_features")
+        ctx.set_config({"wave_source": "records", "use_filtered": True, "threshold": 10.0, "right_extension": 1}, plugin_name="hit_threshold")
+        ctx.set_config({"wave_source": "records"}, plugin_name="waveform_width_integral")
     else:
         # "waves": structured rows as the wave source (st_waveforms for the features, filtered_waveforms for the hits and
         # the charge widths), records on the filtered pool for `hit`, a per-channel threshold and a fixed baseline
@@ -104,6 +113,8 @@ def main():
         names = ["basic_features", "hit_threshold", "hit", "waveform_width", "waveform_width_integral"]
     if scenario == "csv":
         names = ["st_waveforms", "records", "wave_pool", "basic_features", "hit_threshold", "hit_merged", "hit_grouped"]
+    if scenario == "mixed":
+        names = ["st_waveforms", "records", "wave_pool_filtered", "basic_features", "hit_threshold", "waveform_width_integral"]
     for name in names:
         res = ctx.get_data(run, name)
         if hasattr(res, "columns"):  # DataFrame: one array per column (object columns flattened)

@@ -137,3 +137,14 @@ def test_vx2730_csv_route_through_a_real_context(tmp_path):
     gpu = _run("b200", tmp_path, "csv")
     _compare(cpu, gpu)
     assert len(cpu["records"]) == 640 and len(cpu["hit_threshold"]) > 500
+
+
+@pytest.mark.skipif(reference_root() is None, reason="reference package not installed (baseline/_ref)")
+def test_polarity_metadata_and_mixed_filters_through_a_real_context(tmp_path):
+    """CSV route with channel metadata (one negative, one positive channel: the float32 signal branch of the features and
+    the polarity of the hits), a Butterworth override for one channel next to the default Savitzky-Golay filter, hits on
+    the filtered pool, charge widths on records."""
+    cpu = _run("cpu", tmp_path, "mixed")
+    gpu = _run("b200", tmp_path, "mixed")
+    assert set(np.unique(cpu["records"]["polarity"])) == {"negative", "positive", "unknown"}
+    _compare(cpu, gpu)

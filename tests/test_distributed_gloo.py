@@ -155,3 +155,21 @@ def test_plan_cuts_needs_a_gap_wider_than_the_window():
     assert ok and cuts[0] == 1000e3  # 320 -> 330 and 350 -> 360 are no gaps; 380 -> 1000 is
     cuts, ok = D.plan_cuts([a, b[:2]], [a[:0], b[:0]], [True, True], gap_ps=100e3, span_ps=0.0)
     assert not ok
+
+
+@pytest.mark.parametrize("world_size,zone_rows", [(3, 16), (4, 8)])
+def test_merge_group_sharded_more_ranks(world_size, zone_rows):
+    """The same with three and four time shards (cuts between every pair of neighbours, middle ranks hand rows over on both
+    sides, zones of a few rows so that they double several times before a gap is found)."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, world_size, port, zone_rows, 50.0, q)) for r in range(world_size)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] for r in res), res
